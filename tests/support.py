@@ -1,0 +1,268 @@
+"""Test support: golden-DB loading, oracle (ctypes) wrapper, synthetic read generator, text formats.
+
+TEST INFRASTRUCTURE — this module is the only place the oracle library is loaded from Python
+(tests/, __graft_entry__.smoke(), bench.py's cpu_baseline leg).
+"""
+import ctypes as C
+import gzip
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libcarpedeam_oracle.so")
+
+
+# ------------------------------------------------------------------------------------------------
+# canonical golden DBs  (format: oracle/make_golden.py)
+def load_golden(name):
+    """-> (keys[int], payloads[bytes], exts[int]) sorted by key."""
+    blob = gzip.open(os.path.join(GOLD, "cfg1_%s.gz" % name), "rb").read()
+    keys, payloads, exts = [], [], []
+    pos = 0
+    while pos < len(blob):
+        nl = blob.index(b"\n", pos)
+        k, e = blob[pos:nl].split(b"\t")
+        end = blob.index(b"\0", nl + 1)
+        keys.append(int(k)); exts.append(int(e)); payloads.append(blob[nl + 1:end])
+        pos = end + 1
+    return keys, payloads, exts
+
+
+class SeqSet:
+    """Flat sequence set as the C-ABI takes it: MMseqs2 data-file layout `BASES\\n\\0` per entry
+    (lib/mmseqs/src/commons/DBReader.h)."""
+
+    def __init__(self, seqs, keys=None, ext=None):
+        n = len(seqs)
+        self.n = n
+        self.keys = np.arange(n, dtype=np.uint32) if keys is None else np.asarray(keys, dtype=np.uint32)
+        self.ext = np.zeros(n, dtype=np.uint8) if ext is None else np.asarray(ext, dtype=np.uint8)
+        self.len = np.array([len(s) for s in seqs], dtype=np.uint32)
+        self.off = np.zeros(n, dtype=np.uint64)
+        if n:
+            self.off[1:] = np.cumsum(self.len[:-1].astype(np.uint64) + 2)
+        self.blob = np.frombuffer(b"".join(s + b"\n\0" for s in seqs), dtype=np.uint8).copy()
+        self.total = int(self.len.sum())
+
+    @classmethod
+    def from_golden(cls, name):
+        keys, payloads, exts = load_golden(name)
+        assert keys == sorted(keys)
+        return cls([p.rstrip(b"\n") for p in payloads], keys, exts)
+
+    def seq(self, i):
+        o = int(self.off[i])
+        return self.blob[o:o + int(self.len[i])].tobytes()
+
+    def key_to_index(self):
+        return {int(k): i for i, k in enumerate(self.keys)}
+
+
+# ------------------------------------------------------------------------------------------------
+def build_oracle():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+    return ORACLE_SO
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Oracle:
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build_oracle()
+        L = C.CDLL(ORACLE_SO)
+        L.orc_kmermatch.restype = C.c_long
+        L.orc_kmermatch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_float,
+                                    C.c_uint64, C.c_int, C.c_int]
+        L.orc_xxh64_u64.restype = C.c_uint64
+        L.orc_xxh64_u64.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_revcomp.restype = C.c_uint64
+        L.orc_revcomp.argtypes = [C.c_uint64, C.c_int]
+        L.orc_evalue.argtypes = [C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_load_damage.argtypes = [C.c_char_p, C.c_char_p]
+        self.L = L
+
+    def kmermatch(self, s, k=20, kmers_per_seq=200, scale=0.2, seed=67, only_ext=0, keep_records=False):
+        H = self.L.orc_kmermatch(s.blob.ctypes.data, s.off.ctypes.data, s.len.ctypes.data, s.n, k, kmers_per_seq, scale,
+                                 seed, only_ext, 1 if keep_records else 0)
+        rep = np.zeros(H, np.uint32); tgt = np.zeros(H, np.uint32); sc = np.zeros(H, np.int32); dg = np.zeros(H, np.int16)
+        self.L.orc_km_hits(rep.ctypes.data, tgt.ctypes.data, sc.ctypes.data, dg.ctypes.data)
+        r1 = C.c_uint64(); r2 = C.c_uint64()
+        self.L.orc_km_counts(C.byref(r1), C.byref(r2))
+        return dict(rep=rep, tgt=tgt, score=sc, diag=dg, R1=r1.value, R2=r2.value)
+
+    def km_records(self, stage, count):
+        kmer = np.zeros(count, np.uint64); ids = np.zeros(count, np.uint32)
+        sl = np.zeros(count, np.int32); pos = np.zeros(count, np.int32)
+        self.L.orc_km_records(stage, kmer.ctypes.data, ids.ctypes.data, sl.ctypes.data, pos.ctypes.data)
+        return kmer, ids, sl, pos
+
+    def evalue(self, score, qlen, dbres):
+        e = C.c_double(); b = C.c_double()
+        self.L.orc_evalue(score, qlen, dbres, C.byref(e), C.byref(b))
+        return e.value, b.value
+
+    def rescore(self, s, q_idx, t_idx, pref_score, diag16, db_res=None, eval_thr=0.001, seqid_thr=0.9):
+        M = len(q_idx)
+        q_idx = np.ascontiguousarray(q_idx, np.uint32); t_idx = np.ascontiguousarray(t_idx, np.uint32)
+        pref_score = np.ascontiguousarray(pref_score, np.int32); diag16 = np.ascontiguousarray(diag16, np.uint16)
+        out = dict(keep=np.zeros(M, np.uint8), score=np.zeros(M, np.int32), bits=np.zeros(M, np.int32),
+                   evalue=np.zeros(M, np.float64), seqid=np.zeros(M, np.float32), qs=np.zeros(M, np.int32),
+                   qe=np.zeros(M, np.int32), ds=np.zeros(M, np.int32), de=np.zeros(M, np.int32),
+                   idcnt=np.zeros(M, np.int32), alnlen=np.zeros(M, np.int32))
+        if db_res is None:
+            db_res = s.total
+        self.L.orc_rescore(C.c_void_p(s.blob.ctypes.data), C.c_void_p(s.off.ctypes.data), C.c_void_p(s.len.ctypes.data),
+                           C.c_size_t(s.n), C.c_void_p(q_idx.ctypes.data), C.c_void_p(t_idx.ctypes.data),
+                           C.c_void_p(pref_score.ctypes.data), C.c_void_p(diag16.ctypes.data), C.c_size_t(M),
+                           C.c_double(db_res), C.c_double(eval_thr), C.c_float(seqid_thr),
+                           *[C.c_void_p(out[k].ctypes.data) for k in
+                             ("keep", "score", "bits", "evalue", "seqid", "qs", "qe", "ds", "de", "idcnt", "alnlen")])
+        return out
+
+    def load_damage(self, prefix):
+        if prefix:
+            self.L.orc_load_damage((prefix + "5p.prof").encode(), (prefix + "3p.prof").encode())
+        else:
+            self.L.orc_load_damage(b"", b"")
+
+    def get_damage(self):
+        D = np.zeros((11, 4, 4)); R = np.zeros((11, 4, 4))
+        self.L.orc_get_damage(C.c_void_p(D.ctypes.data), C.c_void_p(R.ctypes.data))
+        return D, R
+
+    def correct(self, s, aln_off, t_idx, seqid, qs, qe, ds, de, seqid_thr=0.9, ry_thr=0.99, seq_err=0.01, want_lik=False):
+        aln_off = np.ascontiguousarray(aln_off, np.uint64); t_idx = np.ascontiguousarray(t_idx, np.uint32)
+        seqid = np.ascontiguousarray(seqid, np.float32)
+        qs, qe, ds, de = [np.ascontiguousarray(x, np.int32) for x in (qs, qe, ds, de)]
+        out = s.blob.copy()
+        lik_off = np.zeros(s.n + 1, np.uint64); lik_off[1:] = np.cumsum(s.len.astype(np.uint64))
+        lik = np.full((s.total, 4), np.nan) if want_lik else None
+        self.L.orc_correct(C.c_void_p(s.blob.ctypes.data), C.c_void_p(s.off.ctypes.data), C.c_void_p(s.len.ctypes.data),
+                           C.c_void_p(s.ext.ctypes.data), C.c_size_t(s.n), C.c_void_p(aln_off.ctypes.data),
+                           C.c_void_p(t_idx.ctypes.data), C.c_void_p(seqid.ctypes.data), C.c_void_p(qs.ctypes.data),
+                           C.c_void_p(qe.ctypes.data), C.c_void_p(ds.ctypes.data), C.c_void_p(de.ctypes.data),
+                           C.c_float(seqid_thr), C.c_float(ry_thr), C.c_double(seq_err), C.c_void_p(out.ctypes.data),
+                           C.c_void_p(lik_off.ctypes.data), C.c_void_p(lik.ctypes.data) if want_lik else None)
+        return out, lik
+
+
+# ------------------------------------------------------------------------------------------------
+# text formats between the stages (QueryMatcher.h:81-126, Matcher.cpp:274-401, Util.cpp:278-307)
+def parse_pref(s, payloads):
+    """pref DB entries -> flat lines (q_idx, t_idx, prefScore, diag16) in entry order, + per-query offsets."""
+    k2i = s.key_to_index()
+    q, t, sc, dg, offs = [], [], [], [], [0]
+    for qi, p in enumerate(payloads):
+        for line in p.split(b"\n"):
+            if not line:
+                continue
+            a, b, c = line.split(b"\t")
+            q.append(qi); t.append(k2i[int(a)]); sc.append(int(b)); dg.append(int(c) & 0xFFFF)
+        offs.append(len(q))
+    return (np.array(q, np.uint32), np.array(t, np.uint32), np.array(sc, np.int32), np.array(dg, np.uint16),
+            np.array(offs, np.uint64))
+
+
+def format_pref(s, hits):
+    """Oracle / device hit list (rep index ascending, target ascending) -> {key: payload} like the pref DB."""
+    out = {}
+    rep, tgt, sc, dg = hits["rep"], hits["tgt"], hits["score"], hits["diag"]
+    keys = s.keys
+    lines = {}
+    for r, t, c, d in zip(rep.tolist(), tgt.tolist(), sc.tolist(), dg.tolist()):
+        lines.setdefault(r, []).append(b"%d\t%d\t%d\n" % (int(keys[t]), c, d))
+    for i in range(s.n):
+        k = int(keys[i])
+        out[k] = b"%d\t0\t0\n" % k + b"".join(lines.get(i, []))
+    return out
+
+
+def seqid_text(x):
+    x = np.float32(x)
+    if x == np.float32(1.0):
+        return b"1.00"
+    s = b"0."
+    if x < 0.10:
+        s += b"0"
+    if x < 0.01:
+        s += b"0"
+    return s + b"%d" % int(np.float32(x * np.float32(1000)))
+
+
+def format_aln(s, q_off, t_idx, r):
+    """rescore outputs (per pref line) -> {key: payload} like the aln DB (kept lines only, pref order)."""
+    out = {}
+    keys = s.keys
+    for qi in range(s.n):
+        lines = []
+        for h in range(int(q_off[qi]), int(q_off[qi + 1])):
+            if not r["keep"][h]:
+                continue
+            t = int(t_idx[h])
+            lines.append(b"%d\t%d\t%s\t%s\t%d\t%d\t%d\t%d\t%d\t%d\n" % (
+                int(keys[t]), int(r["bits"][h]), seqid_text(r["seqid"][h]), ("%.3E" % r["evalue"][h]).encode(),
+                int(r["qs"][h]), int(r["qe"][h]), int(s.len[qi]), int(r["ds"][h]), int(r["de"][h]), int(s.len[t])))
+        out[int(keys[qi])] = b"".join(lines)
+    return out
+
+
+def parse_aln(s, payloads):
+    """aln DB entries -> CSR arrays as Matcher::parseAlignmentRecord yields them."""
+    k2i = s.key_to_index()
+    off, t, sid, qs, qe, ds, de = [0], [], [], [], [], [], []
+    for p in payloads:
+        for line in p.split(b"\n"):
+            if not line:
+                continue
+            f = line.split(b"\t")
+            t.append(k2i[int(f[0])]); sid.append(np.float32(float(f[2])))
+            qs.append(int(f[4])); qe.append(int(f[5])); ds.append(int(f[7])); de.append(int(f[8]))
+        off.append(len(t))
+    return (np.array(off, np.uint64), np.array(t, np.uint32), np.array(sid, np.float32), np.array(qs, np.int32),
+            np.array(qe, np.int32), np.array(ds, np.int32), np.array(de, np.int32))
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic damaged reads (SURVEY §8(d) config 2 shape, any size)
+DHIGH5 = (.329405, .221745, .187678, .161196, .144011)
+DHIGH3 = (.32891, .223405, .188599, .164419, .146352)   # positions L-1 .. L-5 are rows 4..0 of dhigh3p.prof
+_COMP = np.zeros(256, np.uint8)
+for _a, _b in zip(b"ACGT", b"TGCA"):
+    _COMP[_a] = _b
+
+
+def synth_reads(n, genome_len, seed, lmin=35, lmax=70, interior=0.01, sub_err=0.001, n_frac=0.0):
+    rng = np.random.default_rng(seed)
+    genome = rng.integers(0, 4, genome_len, dtype=np.uint8)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    genome = acgt[genome]
+    lens = rng.integers(lmin, lmax + 1, n)
+    starts = rng.integers(0, genome_len - lmax, n)
+    strand = rng.random(n) < 0.5
+    seqs = []
+    for i in range(n):
+        L = int(lens[i])
+        r = genome[starts[i]:starts[i] + L].copy()
+        if strand[i]:
+            r = _COMP[r[::-1]]
+        u = rng.random(L)
+        p_ct = np.full(L, interior); p_ct[:5] = DHIGH5
+        p_ga = np.full(L, interior); p_ga[L - 5:] = DHIGH3[::-1]
+        ct = (r == ord("C")) & (u < p_ct)
+        ga = (r == ord("G")) & (u < p_ga)
+        r[ct] = ord("T"); r[ga] = ord("A")
+        e = rng.random(L) < sub_err
+        if e.any():
+            r[e] = acgt[rng.integers(0, 4, int(e.sum()))]
+        if n_frac > 0:
+            m = rng.random(L) < n_frac
+            r[m] = ord("N")
+        seqs.append(r.tobytes())
+    return seqs
