@@ -1,0 +1,281 @@
+"""carpedeam_b200 — B200-native (sm_100a) drop-in for CarpeDeam's read-level hot path.
+
+Python is plumbing only: this module loads libcarpedeam_gpu.so (hand-written CUDA behind the C ABI
+of include/carpedeam_gpu.h) through ctypes and mirrors the three reference stage modules
+
+    kmermatcher         lib/mmseqs/src/linclust/kmermatcher.cpp
+    rescorediagonal     lib/mmseqs/src/alignment/rescorediagonal.cpp
+    ancient_correction  src/assembler/correction.cpp
+
+There is no CPU fallback: if the CUDA library or a device is missing, everything here raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcarpedeam_gpu.so")
+HOST_LIB_PATH = os.path.join(HERE, "libcarpedeam_host.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library (and the host-side C++ helpers) in-tree for sm_100a."""
+    src = os.path.join(HERE, "csrc", "cdg_api.cu")
+    deps = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))]
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "carpedeam_gpu.h"))
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src]
+        subprocess.run(cmd, check=True)
+    hsrc_dir = os.path.join(HERE, "host")
+    if os.path.isdir(hsrc_dir):
+        hsrc = sorted(os.path.join(hsrc_dir, f) for f in os.listdir(hsrc_dir) if f.endswith(".cpp") and not f.startswith("main_"))
+        hdeps = [os.path.join(hsrc_dir, f) for f in os.listdir(hsrc_dir)]
+        if hsrc and (force or not os.path.exists(HOST_LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(HOST_LIB_PATH) for d in hdeps)):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-o", HOST_LIB_PATH] + hsrc, check=True)
+    return LIB_PATH
+
+
+class CdgError(RuntimeError):
+    pass
+
+
+class KmerParams(C.Structure):
+    _fields_ = [("k", C.c_int32), ("kmers_per_seq", C.c_int32), ("kmers_per_seq_scale", C.c_float), ("hash_shift", C.c_uint64),
+                ("include_only_extendable", C.c_int32), ("hash_lo", C.c_uint32), ("hash_hi", C.c_uint32)]
+
+
+class Hits(C.Structure):
+    _fields_ = [("n_hits", C.c_uint64), ("rep", C.POINTER(C.c_uint32)), ("target", C.POINTER(C.c_uint32)),
+                ("score", C.POINTER(C.c_int32)), ("diag", C.POINTER(C.c_int16)), ("n_records", C.c_uint64), ("n_grouped", C.c_uint64)]
+
+
+class RescoreParams(C.Structure):
+    _fields_ = [("min_seq_id", C.c_float), ("evalue_thr", C.c_double), ("db_residues", C.c_uint64)]
+
+
+class Alns(C.Structure):
+    _fields_ = [("n_lines", C.c_uint64), ("n_queries", C.c_uint64), ("line_off", C.POINTER(C.c_uint64)), ("target", C.POINTER(C.c_uint32)),
+                ("keep", C.POINTER(C.c_uint8)), ("score", C.POINTER(C.c_int32)), ("bits", C.POINTER(C.c_int32)),
+                ("evalue", C.POINTER(C.c_double)), ("seq_id", C.POINTER(C.c_float)), ("q_start", C.POINTER(C.c_int32)),
+                ("q_end", C.POINTER(C.c_int32)), ("db_start", C.POINTER(C.c_int32)), ("db_end", C.POINTER(C.c_int32))]
+
+
+class Damage(C.Structure):
+    _fields_ = [("log_d", C.c_double * 176), ("log_drev", C.c_double * 176), ("log_seq_err", C.c_double * 16)]
+
+
+class CorrParams(C.Structure):
+    _fields_ = [("min_seqid_corr_reads", C.c_float), ("min_ryseq_id_corr_reads", C.c_float)]
+
+
+class IterParams(C.Structure):
+    _fields_ = [("kmer", KmerParams), ("rescore", RescoreParams), ("corr", CorrParams)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_seqs", C.c_uint64), ("n_bases", C.c_uint64), ("n_records", C.c_uint64), ("n_grouped", C.c_uint64),
+                ("n_hits", C.c_uint64), ("n_alns", C.c_uint64), ("sort1_passes", C.c_uint32), ("sort2_passes", C.c_uint32),
+                ("kernel_launches", C.c_uint64), ("ms_extract", C.c_float), ("ms_sort1", C.c_float), ("ms_group", C.c_float),
+                ("ms_sort2", C.c_float), ("ms_reduce", C.c_float), ("ms_rescore", C.c_float), ("ms_correct", C.c_float)]
+
+
+_lib = None
+_hostlib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CdgError("libcarpedeam_gpu.so is not built (python -c 'import __graft_entry__ as g; g.build()'); no CPU fallback exists")
+        L = C.CDLL(LIB_PATH)
+        L.cdg_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.cdg_destroy.argtypes = [C.c_void_p]
+        L.cdg_last_error.argtypes = [C.c_void_p]; L.cdg_last_error.restype = C.c_char_p
+        L.cdg_stream.argtypes = [C.c_void_p]; L.cdg_stream.restype = C.c_void_p
+        L.cdg_upload_seqs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.cdg_kmermatch.argtypes = [C.c_void_p, C.POINTER(KmerParams), C.POINTER(Hits)]
+        L.cdg_set_pref_lines.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.cdg_rescore.argtypes = [C.c_void_p, C.POINTER(RescoreParams), C.POINTER(Alns)]
+        L.cdg_set_damage.argtypes = [C.c_void_p, C.POINTER(Damage)]
+        L.cdg_set_alignments.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_void_p] * 6 + [C.c_uint64]
+        L.cdg_correct.argtypes = [C.c_void_p, C.POINTER(CorrParams), C.c_void_p, C.POINTER(C.c_uint64)]
+        L.cdg_correct_likelihoods.argtypes = [C.c_void_p, C.POINTER(CorrParams), C.c_void_p]
+        L.cdg_iteration.argtypes = [C.c_void_p, C.POINTER(IterParams), C.POINTER(Hits), C.POINTER(Alns), C.c_void_p, C.POINTER(C.c_uint64)]
+        L.cdg_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.cdg_test_radix_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+        L.cdg_test_hash_revcomp.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def hostlib():
+    global _hostlib
+    if _hostlib is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise CdgError("libcarpedeam_host.so is not built")
+        H = C.CDLL(HOST_LIB_PATH)
+        H.cdh_build_damage.argtypes = [C.c_char_p, C.c_double, C.POINTER(Damage), C.c_char_p, C.c_size_t]
+        H.cdh_build_damage.restype = C.c_int
+        _hostlib = H
+    return _hostlib
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _view(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype)
+    return np.ctypeslib.as_array(ptr, shape=(int(n),)).view(dtype).copy()
+
+
+def kmer_params(k=20, kmers_per_seq=200, scale=0.2, hash_shift=67, include_only_extendable=0, hash_lo=0, hash_hi=65535):
+    return KmerParams(k, kmers_per_seq, scale, hash_shift, include_only_extendable, hash_lo, hash_hi)
+
+
+def load_damage(prefix, seq_err=0.01):
+    """--ancient-damage PFX -> cdg_damage, built by the C++ host code (carpedeam_b200/host/damage.cpp)."""
+    d = Damage()
+    err = C.create_string_buffer(512)
+    rc = hostlib().cdh_build_damage((prefix or "").encode(), seq_err, C.byref(d), err, 512)
+    if rc != 0:
+        raise CdgError("damage profile: " + err.value.decode())
+    return d
+
+
+class Context:
+    """One GPU, one stream.  Mirrors the reference's stage modules on a resident sequence set."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().cdg_create(device, C.byref(self._h))
+        if rc != 0:
+            raise CdgError("cdg_create(device=%d) failed (%d): CUDA device required, no CPU fallback" % (device, rc))
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            lib().cdg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise CdgError("%s failed (%d): %s" % (what, rc, lib().cdg_last_error(self._h).decode()))
+
+    @property
+    def stream(self):
+        return lib().cdg_stream(self._h)
+
+    def upload(self, blob, off, lens, ext=None):
+        blob = np.ascontiguousarray(blob, np.uint8); off = np.ascontiguousarray(off, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+        ext = None if ext is None else np.ascontiguousarray(ext, np.uint8)
+        self.n = len(lens); self.data_bytes = blob.nbytes
+        self._ck(lib().cdg_upload_seqs(self._h, _ptr(blob), blob.nbytes, _ptr(off), _ptr(lens), _ptr(ext), len(lens)), "cdg_upload_seqs")
+
+    def upload_raw(self, blob_ptr, nbytes, off_ptr, len_ptr, ext_ptr, n):
+        """pointer-level upload (pinned host buffers owned by the caller, e.g. torch pinned tensors)"""
+        self.n = n; self.data_bytes = nbytes
+        self._ck(lib().cdg_upload_seqs(self._h, C.c_void_p(blob_ptr), nbytes, C.c_void_p(off_ptr), C.c_void_p(len_ptr),
+                                       C.c_void_p(ext_ptr) if ext_ptr else None, n), "cdg_upload_seqs")
+
+    @staticmethod
+    def _hits(h):
+        H = h.n_hits
+        return dict(rep=_view(h.rep, H, np.uint32), tgt=_view(h.target, H, np.uint32), score=_view(h.score, H, np.int32),
+                    diag=_view(h.diag, H, np.int16), R1=h.n_records, R2=h.n_grouped)
+
+    @staticmethod
+    def _alns(a):
+        M = a.n_lines
+        return dict(line_off=_view(a.line_off, a.n_queries + 1, np.uint64), tgt=_view(a.target, M, np.uint32), keep=_view(a.keep, M, np.uint8),
+                    score=_view(a.score, M, np.int32), bits=_view(a.bits, M, np.int32), evalue=_view(a.evalue, M, np.float64),
+                    seqid=_view(a.seq_id, M, np.float32), qs=_view(a.q_start, M, np.int32), qe=_view(a.q_end, M, np.int32),
+                    ds=_view(a.db_start, M, np.int32), de=_view(a.db_end, M, np.int32))
+
+    def kmermatch(self, params=None, fetch=True):
+        p = params or kmer_params()
+        h = Hits()
+        self._ck(lib().cdg_kmermatch(self._h, C.byref(p), C.byref(h) if fetch else None), "cdg_kmermatch")
+        return self._hits(h) if fetch else None
+
+    def set_pref_lines(self, line_off, tgt, pref_score, diag16):
+        line_off = np.ascontiguousarray(line_off, np.uint64); tgt = np.ascontiguousarray(tgt, np.uint32)
+        pref_score = np.ascontiguousarray(pref_score, np.int32); diag16 = np.ascontiguousarray(diag16, np.uint16)
+        self._ck(lib().cdg_set_pref_lines(self._h, _ptr(line_off), len(line_off) - 1, _ptr(tgt), _ptr(pref_score), _ptr(diag16), len(tgt)),
+                 "cdg_set_pref_lines")
+
+    def rescore(self, min_seq_id=0.9, evalue_thr=0.001, db_residues=0, fetch=True):
+        p = RescoreParams(min_seq_id, evalue_thr, db_residues)
+        a = Alns()
+        self._ck(lib().cdg_rescore(self._h, C.byref(p), C.byref(a) if fetch else None), "cdg_rescore")
+        return self._alns(a) if fetch else None
+
+    def set_damage(self, damage):
+        self._ck(lib().cdg_set_damage(self._h, C.byref(damage)), "cdg_set_damage")
+
+    def set_alignments(self, aln_off, tgt, seqid, qs, qe, ds, de):
+        aln_off = np.ascontiguousarray(aln_off, np.uint64); tgt = np.ascontiguousarray(tgt, np.uint32); seqid = np.ascontiguousarray(seqid, np.float32)
+        qs, qe, ds, de = [np.ascontiguousarray(x, np.int32) for x in (qs, qe, ds, de)]
+        self._ck(lib().cdg_set_alignments(self._h, _ptr(aln_off), len(aln_off) - 1, _ptr(tgt), _ptr(seqid), _ptr(qs), _ptr(qe), _ptr(ds), _ptr(de),
+                                          len(tgt)), "cdg_set_alignments")
+
+    def correct(self, min_seqid=0.9, min_ry=0.99, out=None):
+        p = CorrParams(min_seqid, min_ry)
+        if out is None:
+            out = np.zeros(self.data_bytes, np.uint8)
+        ch = C.c_uint64()
+        self._ck(lib().cdg_correct(self._h, C.byref(p), _ptr(out), C.byref(ch)), "cdg_correct")
+        return out, ch.value
+
+    def correct_likelihoods(self, total_bases, min_seqid=0.9, min_ry=0.99):
+        p = CorrParams(min_seqid, min_ry)
+        lik = np.zeros((total_bases, 4), np.float64)
+        self._ck(lib().cdg_correct_likelihoods(self._h, C.byref(p), _ptr(lik)), "cdg_correct_likelihoods")
+        return lik
+
+    def iteration(self, kmer=None, min_seq_id=0.9, evalue_thr=0.001, db_residues=0, min_seqid_corr=0.9, min_ry=0.99,
+                  fetch_hits=False, fetch_alns=True, out=None, out_ptr=None):
+        ip = IterParams(kmer or kmer_params(), RescoreParams(min_seq_id, evalue_thr, db_residues), CorrParams(min_seqid_corr, min_ry))
+        h = Hits(); a = Alns(); ch = C.c_uint64()
+        if out is None and out_ptr is None:
+            out = np.zeros(self.data_bytes, np.uint8)
+        optr = C.c_void_p(out_ptr) if out_ptr else _ptr(out)
+        self._ck(lib().cdg_iteration(self._h, C.byref(ip), C.byref(h) if fetch_hits else None, C.byref(a) if fetch_alns else None, optr,
+                                     C.byref(ch)), "cdg_iteration")
+        return (self._hits(h) if fetch_hits else None, self._alns(a) if fetch_alns else None, out, ch.value)
+
+    def iteration_raw(self, ip, hits, alns, out_ptr):
+        """no-copy variant for the benchmark: results stay in the library's pinned buffers"""
+        ch = C.c_uint64()
+        self._ck(lib().cdg_iteration(self._h, C.byref(ip), C.byref(hits) if hits is not None else None,
+                                     C.byref(alns) if alns is not None else None, C.c_void_p(out_ptr) if out_ptr else None, C.byref(ch)),
+                 "cdg_iteration")
+        return ch.value
+
+    def stats(self):
+        s = Stats()
+        self._ck(lib().cdg_get_stats(self._h, C.byref(s)), "cdg_get_stats")
+        return {f[0]: getattr(s, f[0]) for f in Stats._fields_}
+
+    def test_radix_sort(self, keys, vals, bit_lo, bit_hi):
+        keys = np.ascontiguousarray(keys, np.uint64).copy()
+        vals = None if vals is None else np.ascontiguousarray(vals, np.uint64).copy()
+        self._ck(lib().cdg_test_radix_sort(self._h, _ptr(keys), _ptr(vals), len(keys), bit_lo, bit_hi), "cdg_test_radix_sort")
+        return keys, vals
+
+    def test_hash_revcomp(self, x, k, seed):
+        x = np.ascontiguousarray(x, np.uint64)
+        h = np.zeros_like(x); r = np.zeros_like(x)
+        self._ck(lib().cdg_test_hash_revcomp(self._h, _ptr(x), len(x), k, seed, _ptr(h), _ptr(r)), "cdg_test_hash_revcomp")
+        return h, r

@@ -1,0 +1,327 @@
+// rescorediagonal (mode 3, nucleotides) and ancient_correction on the device.
+//   lines_kernel     prefilter hits -> per-query line list (self line first, hits in target order)
+//   rescore_kernel   one thread per line    (rescorediagonal.cpp:194-334, DistanceCalculator.h:93-220)
+//   correct_kernel   one warp per query     (correction.cpp:7-123,128-490)
+#pragma once
+#include <float.h>
+#include <math.h>
+#include "cdg_common.cuh"
+
+namespace cdgalign {
+
+// ---- line list -----------------------------------------------------------------------------------
+// pref entry of query q = `q 0 0` followed by its hits (kmermatcher.cpp:836,:710-730).  With hits sorted by
+// (rep,target): self line of q at q + lower_bound(hitRep, q); hit h of rep r at h + r + 1.
+__global__ void __launch_bounds__(256) lines_self_kernel(const u32 *__restrict__ hitRep, u64 H, u64 n, u64 *__restrict__ lineOff,
+                                                         u32 *__restrict__ lineQ, u32 *__restrict__ lineT, i32 *__restrict__ linePref,
+                                                         u16 *__restrict__ lineDiag) {
+    u64 q = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > n) return;
+    u64 lo = 0, hi = H;
+    while (lo < hi) { u64 mid = (lo + hi) >> 1; if (hitRep[mid] < q) lo = mid + 1; else hi = mid; }
+    u64 l = q + lo;
+    lineOff[q] = l;
+    if (q < n) { lineQ[l] = (u32) q; lineT[l] = (u32) q; linePref[l] = 0; lineDiag[l] = 0; }
+}
+__global__ void __launch_bounds__(256) lines_hits_kernel(const u32 *__restrict__ hitRep, const u32 *__restrict__ hitTgt,
+                                                         const i32 *__restrict__ hitScore, const i32 *__restrict__ hitDiag, u64 H,
+                                                         u32 *__restrict__ lineQ, u32 *__restrict__ lineT, i32 *__restrict__ linePref,
+                                                         u16 *__restrict__ lineDiag) {
+    u64 h = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    u32 r = hitRep[h];
+    u64 l = h + r + 1;
+    lineQ[l] = r; lineT[l] = hitTgt[h]; linePref[l] = hitScore[h];
+    lineDiag[l] = (u16) (short) hitDiag[h];   // (short) in writeKmerMatcherResult, parsed back as unsigned short
+}
+// for caller-provided lines: expand line_off into lineQ
+__global__ void __launch_bounds__(256) lines_fillq_kernel(const u64 *__restrict__ lineOff, u64 n, u32 *__restrict__ lineQ) {
+    u64 q = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    for (u64 l = lineOff[q]; l < lineOff[q + 1]; l++) lineQ[l] = (u32) q;
+}
+
+// ---- packed helpers ----------------------------------------------------------------------------------
+// c (1..32) bases starting at base p, left-aligned, rest zero.  Caller guarantees p + c <= L.
+CDG_D u64 get_bases(const u64 *__restrict__ w, u32 p, u32 c) {
+    u32 wi = p >> 5, sh = (p & 31) * 2;
+    u64 v = w[wi] << sh;
+    if (sh && (p & 31) + c > 32) v |= w[wi + 1] >> (64 - sh);
+    return c == 32 ? v : (v & ~(~0ull >> (2 * c)));
+}
+// c bases of revcomp(seq) starting at revcomp position a
+CDG_D u64 get_bases_rc(const u64 *__restrict__ w, u32 L, u32 a, u32 c) {
+    u64 x = get_bases(w, L - a - c, c);            // forward bases, left aligned
+    u64 r = cdg_rev2bit64(x) << (2 * (32 - c));    // reversed, left aligned again
+    r ^= 0xAAAAAAAAAAAAAAAAull;
+    return c == 32 ? r : (r & ~(~0ull >> (2 * c)));
+}
+
+struct RescoreParams { float seqIdThr; double evalThr; double dbRes; };
+struct LocalAln { i32 startPos, endPos; u32 score; u32 diagonalLen; u32 dist; i32 diagonal; u32 idCnt; };
+
+// fast path: both sequences are plain upper-case ACGT. q is read forward or as its reverse complement.
+CDG_D void score_packed(const u64 *__restrict__ qw, u32 qLen, bool qRev, u32 qOff, const u64 *__restrict__ tw, u32 tOff, u32 n,
+                        i64 &score, u32 &matches) {
+    u32 mism = 0;
+    for (u32 o = 0; o < n; o += 32) {
+        u32 c = n - o < 32 ? n - o : 32;
+        u64 a = qRev ? get_bases_rc(qw, qLen, qOff + o, c) : get_bases(qw, qOff + o, c);
+        u64 b = get_bases(tw, tOff + o, c);
+        u64 x = a ^ b;
+        mism += __popcll((x | (x >> 1)) & 0x5555555555555555ull);
+    }
+    matches = n - mism;
+    score = 2ll * (i64) matches - 3ll * (i64) mism;
+}
+// exact byte path (IUPAC letters, lower case, '*'): createAsciiSubMat scores + case-folded identity
+CDG_D unsigned char q_char(const u8 *q, u32 qLen, bool qRev, u32 i) {   // rescorediagonal.cpp:173-179
+    return qRev ? (unsigned char) cdg_num2aa(cdg_rev_code(cdg_map_letter(q[qLen - 1 - i]))) : q[i];
+}
+CDG_D int sub_score(unsigned char a, unsigned char b) {
+    int x = cdg_map_letter(a), y = cdg_map_letter(b);
+    return (x == y && x != 4) ? 2 : -3;
+}
+CDG_D LocalAln by_diagonal(bool fast, const u64 *qw, const u8 *qa, u32 qLen, bool qRev, const u64 *tw, const u8 *ta, u32 tLen, i32 diagonal) {
+    LocalAln r; r.startPos = -1; r.endPos = -1; r.score = 0; r.diagonalLen = 0; r.idCnt = 0;
+    u32 ad = (u32) (diagonal < 0 ? -diagonal : diagonal);
+    r.dist = ad; r.diagonal = diagonal;
+    u32 n, qOff, tOff;
+    if (diagonal >= 0 && ad < qLen) { n = min(tLen, qLen - ad); qOff = ad; tOff = 0; }
+    else if (diagonal < 0 && ad < tLen) { n = min(tLen - ad, qLen); qOff = 0; tOff = ad; }
+    else return r;
+    r.diagonalLen = n;
+    if (fast) {
+        i64 s; u32 m;
+        score_packed(qw, qLen, qRev, qOff, tw, tOff, n, s, m);
+        r.startPos = 0; r.endPos = (i32) n - 1; r.score = (u32) (s > 0 ? s : 0); r.idCnt = m;
+    } else {   // computeGlobalSubstitutionStartEndDistance (DistanceCalculator.h:204-220)
+        unsigned char q0 = q_char(qa, qLen, qRev, qOff), t0 = ta[tOff];
+        unsigned char q1 = q_char(qa, qLen, qRev, qOff + n - 1), t1 = ta[tOff + n - 1];
+        u32 first = (q0 == '*' || t0 == '*') ? 1 : 0;
+        u32 last = n - 1;
+        if (last > 0 && (q1 == '*' || t1 == '*')) last--;
+        i64 s = 0; u32 idc = 0;
+        for (u32 p = first; p <= last; p++) {
+            unsigned char a = q_char(qa, qLen, qRev, qOff + p), b = ta[tOff + p];
+            s += sub_score(a, b);
+            idc += ((a & (unsigned char) ~0x20) == (b & (unsigned char) ~0x20)) ? 1u : 0u;
+        }
+        r.startPos = (i32) first; r.endPos = (i32) last; r.score = (u32) (s > 0 ? s : 0); r.idCnt = idc;
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256) rescore_kernel(
+    const u8 *__restrict__ data, const u64 *__restrict__ off, const u32 *__restrict__ len, const u64 *__restrict__ words,
+    const u64 *__restrict__ wordOff, const u8 *__restrict__ flags,
+    const u32 *__restrict__ lineQ, const u32 *__restrict__ lineT, const i32 *__restrict__ linePref, const u16 *__restrict__ lineDiag,
+    u64 M, RescoreParams P,
+    u8 *__restrict__ keep, i32 *__restrict__ score, i32 *__restrict__ bits, double *__restrict__ evalue, float *__restrict__ seqId,
+    i32 *__restrict__ qS, i32 *__restrict__ qE, i32 *__restrict__ dS, i32 *__restrict__ dE, unsigned long long *__restrict__ keptCount) {
+    u64 l = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    u32 kept = 0;
+    if (l < M) {
+        const u32 q = lineQ[l], t = lineT[l];
+        const u32 qLen = len[q], tLen = len[t];
+        const bool isRev = linePref[l] < 0;
+        const bool isIdentity = q == t;
+        const bool fast = !(flags[q] | flags[t]);
+        const u64 *qw = words + wordOff[q], *tw = words + wordOff[t];
+        const u8 *qa = data + off[q], *ta = data + off[t];
+        const u32 diag16 = lineDiag[l];
+        LocalAln mx; mx.startPos = -1; mx.endPos = -1; mx.score = 0; mx.diagonalLen = 0; mx.dist = 0; mx.diagonal = 0; mx.idCnt = 0;
+        if (qLen > 0 && tLen > 0) {
+            for (u32 d = 1; d <= 1 + tLen / 32768; d++) {   // computeUngappedAlignment (DistanceCalculator.h:93-113)
+                LocalAln tmp = by_diagonal(fast, qw, qa, qLen, isRev, tw, ta, tLen, (i32) diag16 - (i32) (d * 65536));
+                if (tmp.score > mx.score) mx = tmp;
+            }
+            for (u32 d = 0; d <= qLen / 65536; d++) {
+                LocalAln tmp = by_diagonal(fast, qw, qa, qLen, isRev, tw, ta, tLen, (i32) (d * 65536 + diag16));
+                if (tmp.score > mx.score) mx = tmp;
+            }
+        }
+        const i32 distance = (i32) mx.score;
+        const double ev = cdg_evalue((double) distance, (double) qLen, P.dbRes);
+        const i32 bitScore = (i32) (cdg_bitscore((double) distance) + 0.5);
+        const i32 alnLen = (mx.endPos - mx.startPos) + 1;
+        i32 qs, qe, ds, de;
+        if (mx.diagonal >= 0) { qs = mx.startPos + (i32) mx.dist; qe = mx.endPos + (i32) mx.dist; ds = mx.startPos; de = mx.endPos; }
+        else { qs = mx.startPos; qe = mx.endPos; ds = mx.startPos + (i32) mx.dist; de = mx.endPos + (i32) mx.dist; }
+        float sid = 0.f;
+        if ((ev <= P.evalThr || isIdentity) && mx.startPos >= 0) sid = (float) mx.idCnt / (float) alnLen;   // Util::computeSeqId
+        if (isRev) { qs = (i32) qLen - qs - 1; qe = (i32) qLen - qe - 1; }
+        const bool hasSeqId = (double) sid >= (double) (P.seqIdThr - FLT_EPSILON);
+        const bool hasEvalue = ev <= P.evalThr;
+        const bool k = isIdentity || (hasSeqId && hasEvalue);   // rescorediagonal.cpp:304-314 with -c 0, --min-aln-len 0
+        keep[l] = k ? 1 : 0; score[l] = distance; bits[l] = bitScore; evalue[l] = ev; seqId[l] = sid;
+        qS[l] = qs; qE[l] = qe; dS[l] = ds; dE[l] = de;
+        kept = k ? 1u : 0u;
+    }
+    u32 b = __ballot_sync(0xffffffffu, kept);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(keptCount, (unsigned long long) __popc(b));
+}
+
+// ---- ancient_correction ----------------------------------------------------------------------------------
+struct CorrParams { float seqIdThr; float ryThr; int roundSeqId; };   // roundSeqId: emulate the aln DB's 3-decimal text
+struct DamageTables { double logD[11][4][4]; double logDrev[11][4][4]; double logSE[4][4]; };
+
+CDG_D int nuc_map(unsigned char c) { return c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0; }   // correction.cpp:170-174, operator[] -> 0
+CDG_D int ry_map(unsigned char c) { return (c == 'C' || c == 'T') ? 1 : 0; }                      // :175-180
+// target byte in alignment orientation: reverse targets go through getNuclRevFragment (nuclassembleUtil.cpp:67-76)
+CDG_D unsigned char t_char(const u8 *t, u32 tLen, bool rev, u32 p) {
+    if (!rev) return t[p];
+    char r = cdg_num2aa(cdg_rev_code(cdg_map_letter(t[tLen - 1 - p])));
+    return (unsigned char) (r == 'X' ? 'N' : r);
+}
+// Util::fastSeqIdToBuffer + strtod round trip (Util.cpp:278-307, Matcher.cpp:289)
+CDG_D float seqid_text_roundtrip(float x) {
+    if (x == 1.0f) return 1.0f;
+    int i = (int) (x * 1000);
+    return (float) ((double) i / 1000.0);
+}
+
+// mostLikeliBaseRead (correction.cpp:7-123).  cnt/rv: [t*11+l].  Sums are accumulated in the reference's
+// loop order with separately rounded multiplies and adds (no FMA contraction).
+CDG_D int most_likely_base(int b, u32 qIter, const u32 *cnt, const u32 *rv, const DamageTables &T, bool wasCorr, u32 qLen,
+                           double *liks, bool *evaluated) {
+    u32 cov[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) { u32 s = 0; for (int l = 0; l < 11; l++) s += cnt[t * 11 + l]; cov[t] = s; }
+    *evaluated = false;
+    if (!wasCorr) {
+        u32 tot = cov[1] + cov[3] + cov[0] + cov[2];
+        double ctRatio = (double) cov[3] / (double) tot, gaRatio = (double) cov[0] / (double) tot;
+        if (ctRatio >= 0.4 || gaRatio >= 0.4) return b;   // :56-60
+    }
+    int cq = 5;
+    if (qIter < 5) cq = (int) qIter;
+    else if (qIter >= qLen - 5) cq = 11 - (int) (qLen - qIter);
+    double lik[4];
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        const double logQ = wasCorr ? T.logSE[q][b] : T.logD[cq][q][b];
+        double acc = 0.0;
+        for (int t = 0; t < 4; t++) {
+            if (cov[t] == 0) continue;
+            const double base = __dadd_rn(T.logSE[t][b], logQ);
+            for (int l = 0; l < 11; l++) {
+                u32 c = cnt[t * 11 + l];
+                if (c != 0) {
+                    u32 nr = rv[t * 11 + l];
+                    acc = __dadd_rn(acc, __dmul_rn((double) (i32) (c - nr), __dadd_rn(base, T.logD[l][q][t])));
+                    acc = __dadd_rn(acc, __dmul_rn((double) (i32) nr, __dadd_rn(base, T.logDrev[l][q][t])));
+                }
+            }
+        }
+        lik[q] = acc;
+    }
+    *evaluated = true;
+    if (liks) { liks[0] = lik[0]; liks[1] = lik[1]; liks[2] = lik[2]; liks[3] = lik[3]; }
+    int best = 0;
+    for (int q = 1; q < 4; q++) if (lik[q] > lik[best]) best = q;   // std::max_element: first maximum
+    return best;
+}
+
+static constexpr int CORR_WARPS = 4;
+__global__ void __launch_bounds__(CORR_WARPS * 32) correct_kernel(
+    const u8 *__restrict__ data, const u64 *__restrict__ off, const u32 *__restrict__ len, const u8 *__restrict__ ext, u64 n,
+    const u64 *__restrict__ lineOff, const u32 *__restrict__ lineT, const u8 *__restrict__ keep, const float *__restrict__ seqId,
+    const i32 *__restrict__ qS_, const i32 *__restrict__ qE_, const i32 *__restrict__ dS_, const i32 *__restrict__ dE_,
+    CorrParams P, const DamageTables *__restrict__ tablesG, u8 *__restrict__ lineSel, u8 *__restrict__ out,
+    unsigned long long *__restrict__ changed, const u64 *__restrict__ likOff, double *__restrict__ likOut) {
+    __shared__ DamageTables T;
+    for (int i = threadIdx.x; i < (int) (sizeof(DamageTables) / sizeof(double)); i += blockDim.x) ((double *) &T)[i] = ((const double *) tablesG)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const u64 gwarp = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64) gridDim.x * blockDim.x) >> 5;
+    u32 nChanged = 0;
+    for (u64 qi = gwarp; qi < n; qi += nwarps) {
+        const u64 l0 = lineOff[qi], l1 = lineOff[qi + 1];
+        const u32 qLen = len[qi];
+        const u8 *q = data + off[qi];
+        u8 *o = out + off[qi];
+        // lines with nothing but (at most) the self alignment leave the sequence untouched: cov <= 1 everywhere
+        if (l1 - l0 <= 1) continue;
+        const bool qExt = ext[qi] != 0;
+        // pass 1 (:220-245): avCov over the alignments the aln DB holds (= kept lines), float accumulate in order
+        float avCov = 0.f;
+        for (u64 l = l0; l < l1; l++) {
+            if (!keep[l]) continue;
+            i32 a = max(abs(qE_[l] - qS_[l]), abs(dE_[l] - dS_[l])) + 1;   // Matcher::computeAlnLength
+            avCov += (float) a;
+        }
+        avCov = avCov / (float) qLen;
+        // pass 2 (:273-323, :353-359): which targets are counted
+        u32 nSel = 0;
+        for (u64 l = l0; l < l1; l++) {
+            u8 sel = 0;
+            if (keep[l]) {
+                const u32 t = lineT[l];
+                if (!ext[t]) {
+                    const u32 dL = len[t];
+                    i32 qs = qS_[l], qe = qE_[l], ds = dS_[l], de = dE_[l];
+                    const i32 aln = max(abs(qe - qs), abs(de - ds)) + 1;
+                    bool rev = false;
+                    if (qs > qe) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; rev = true; }
+                    const u8 *ts = data + off[t];
+                    u32 dist = 0;
+                    for (i32 p = lane; p < aln; p += 32) dist += (ry_map(q[qs + p]) != ry_map(t_char(ts, dL, rev, (u32) (ds + p)))) ? 1u : 0u;
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, s);
+                    const float ry = (float) ((u32) aln - dist) / (float) aln;   // getRYSeqId
+                    float thr = P.ryThr;
+                    if (aln <= 100) { thr = ((float) aln - 1) / (float) aln; thr = floorf(thr * 1000) / 1000; }
+                    const bool pick = (ry >= thr && ds == 0 && (u32) qe == qLen - 1) || (ry >= thr && qs == 0 && de == (i32) dL - 1) ||
+                                      (ry >= thr && avCov < 50);
+                    const float sid = P.roundSeqId ? seqid_text_roundtrip(seqId[l]) : seqId[l];
+                    if (pick && ry >= thr && sid >= P.seqIdThr && aln >= 30) sel = rev ? 2 : 1;
+                }
+            }
+            if (lane == 0) lineSel[l] = sel;
+            nSel += sel ? 1u : 0u;
+        }
+        __syncwarp();
+        if (nSel <= 1) continue;   // every column has coverage <= 1
+        // pass 3+4, 32 query columns at a time (lane = column)
+        for (u32 c0 = 0; c0 < qLen; c0 += 32) {
+            const u32 col = c0 + lane;
+            u32 cnt[44], rv[44];
+#pragma unroll
+            for (int i = 0; i < 44; i++) { cnt[i] = 0; rv[i] = 0; }
+            u32 tot = 0;
+            for (u64 l = l0; l < l1; l++) {
+                const u8 sel = lineSel[l];
+                if (!sel) continue;
+                const u32 t = lineT[l];
+                const u32 dL = len[t];
+                i32 qs = qS_[l], qe = qE_[l], ds = dS_[l], de = dE_[l];
+                const bool rev = sel == 2;
+                if (rev) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; }
+                const i32 aln = max(abs(qe - qs), abs(de - ds)) + 1;
+                if (col < qLen && (i32) col >= qs && (i32) col < qs + aln) {
+                    const u32 tp = (u32) ds + (col - (u32) qs);
+                    const int cl = ((i32) tp >= (i32) dL - 5) ? 6 + (int) (tp - (dL - 5)) : (tp < 5 ? (int) tp : 5);   // :361-371
+                    const int bse = nuc_map(t_char(data + off[t], dL, rev, tp));
+                    cnt[bse * 11 + cl] += 1; rv[bse * 11 + cl] += rev ? 1u : 0u; tot += 1;
+                }
+            }
+            if (col < qLen) {
+                const unsigned char orig = q[col];
+                unsigned char res = orig;
+                if (tot > 1) {
+                    double liks[4]; bool evaluated;
+                    int nb = most_likely_base(nuc_map(orig), col, cnt, rv, T, qExt, qLen, likOut ? liks : nullptr, &evaluated);
+                    res = (unsigned char) "ACGT"[nb];
+                    if (likOut && evaluated) { double *lo = likOut + (likOff[qi] + col) * 4; lo[0] = liks[0]; lo[1] = liks[1]; lo[2] = liks[2]; lo[3] = liks[3]; }
+                }
+                if (res != orig) { o[col] = res; nChanged++; }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) nChanged += __shfl_xor_sync(0xffffffffu, nChanged, s);
+    if (lane == 0 && nChanged) atomicAdd(changed, (unsigned long long) nChanged);
+}
+
+}   // namespace cdgalign

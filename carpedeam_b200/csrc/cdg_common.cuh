@@ -1,0 +1,107 @@
+// Shared device/host helpers for libcarpedeam_gpu (sm_100a).  Scalar arithmetic that must be
+// bit-identical to the reference lives here as __host__ __device__ functions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef uint16_t u16;
+typedef uint8_t u8;
+typedef int32_t i32;
+typedef int64_t i64;
+
+#define CDG_HD __host__ __device__ __forceinline__
+#define CDG_D __device__ __forceinline__
+
+static constexpr u64 CDG_B63 = 1ull << 63;
+static constexpr u64 CDG_SENTINEL = ~0ull;   // unused record slot, sorts last (kmermatcher.cpp:40 memset 0xFF)
+
+// ---- a1: letter mapping (NucleotideMatrix.cpp:17-61; alphabet order nucleotide.out:4) --------
+// codes A0 C1 T2 G3 X4.  U,W->T  K,B,D,V,R,S->G  M,Y,H->C, anything else X; case-insensitive.
+CDG_HD int cdg_map_letter(unsigned char c) {
+    unsigned char u = (c >= 'a' && c <= 'z') ? (unsigned char) (c - 32) : c;
+    switch (u) {
+        case 'A': return 0;
+        case 'C': case 'M': case 'Y': case 'H': return 1;
+        case 'T': case 'U': case 'W': return 2;
+        case 'G': case 'K': case 'B': case 'D': case 'V': case 'R': case 'S': return 3;
+        default: return 4;
+    }
+}
+// exact upper-case A/C/G/T -> code, everything else (lower case, IUPAC, N, ...) -> 4 ("exception"):
+// only sequences without exceptions take the packed fast paths of rescore/correction.
+CDG_HD int cdg_plain_code(unsigned char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'T' ? 2 : c == 'G' ? 3 : 4; }
+CDG_HD char cdg_num2aa(int code) { return code == 0 ? 'A' : code == 1 ? 'C' : code == 2 ? 'T' : code == 3 ? 'G' : 'X'; }
+CDG_HD int cdg_rev_code(int code) { return code == 4 ? 4 : (code ^ 2); }   // NucleotideMatrix::reverseResidue
+
+// ---- a3: XXH64 of one little-endian u64 (xxhash v0.8.0; hashUInt64, kmermatcher.cpp:33-38) ----
+CDG_HD u64 cdg_rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
+CDG_HD u64 cdg_xxh64_u64(u64 v, u64 seed) {
+    const u64 P1 = 11400714785074694791ull, P2 = 14029467366897019727ull, P3 = 1609587929392839161ull,
+              P4 = 9650029242287828579ull, P5 = 2870177450012600261ull;
+    u64 h = seed + P5 + 8;
+    u64 k = cdg_rotl64(v * P2, 31) * P1;
+    h ^= k;
+    h = cdg_rotl64(h, 27) * P1 + P4;
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
+// ---- a2: reverse complement of a 2-bit k-mer index (Util::revComplement, Util.cpp:601-638) ----
+// complement = xor 0b10 per base (A0<->T2, C1<->G3); reverse the k 2-bit groups.
+CDG_HD u64 cdg_rev2bit64(u64 x) {   // reverse all 32 2-bit groups of a word
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
+    return (x >> 32) | (x << 32);
+}
+CDG_HD u64 cdg_revcomp_kmer(u64 idx, int k) {
+    return cdg_rev2bit64(idx ^ 0xAAAAAAAAAAAAAAAAull) >> (64 - 2 * k);
+}
+
+// ---- E-values: Karlin-Altschul + ALP finite size correction ------------------------------------
+// EvalueComputation.h:36-40 -> Sls::AlignmentEvaluer::area (sls_pvalues.cpp:366-545, blast_=false) with
+// the Gumbel parameters ALP's initGapless derives for nucleotide.out (+2/-3, background 0.25): these
+// are constants of the matrix, embedded here the way the reference embeds its gapped parameter sets
+// (EvalueComputation.h:55-75).  Values dumped from the reference with oracle/ref_probe.cpp.
+struct CdgAlp {
+    static constexpr double lambda = 0.63373155264486880078;
+    static constexpr double K = 0.40796623464181452912;
+    static constexpr double a = 0.69454686319701297581;      // a_I = a_J, b = 0
+    static constexpr double alpha = 0.83333515157614945768;  // alpha_I = alpha_J = sigma, beta = tau = 0
+    static constexpr double thr = 2.6299310744375534732;     // vi_y_thr = vj_y_thr = c_y_thr
+    static constexpr double logK = -0.89657086696128563;     // log(K), filled for reference; recomputed on host
+};
+CDG_HD double cdg_alp_area(double y, double m, double n) {
+    const double const_val = 0.39894228040143267794;   // 1/sqrt(2*pi)
+    double m_li_y = m - CdgAlp::a * y;
+    double vi_y = fmax(CdgAlp::thr, CdgAlp::alpha * y);
+    double sqrt_vi_y = sqrt(vi_y);
+    double m_F = m_li_y / sqrt_vi_y;
+    double P_m_F = 0.5 * erfc(-0.70710678118654752440 * m_F);
+    double E_m_F = -const_val * exp(-0.5 * m_F * m_F);
+    double p1 = m_li_y * P_m_F - sqrt_vi_y * E_m_F;
+    double n_lj_y = n - CdgAlp::a * y;
+    double n_F = n_lj_y / sqrt_vi_y;
+    double P_n_F = 0.5 * erfc(-0.70710678118654752440 * n_F);
+    double E_n_F = -const_val * exp(-0.5 * n_F * n_F);
+    double p2 = n_lj_y * P_n_F - sqrt_vi_y * E_n_F;
+    double c_y = vi_y;   // sigma == alpha and the same threshold
+    return p1 * p2 + c_y * P_m_F * P_n_F;
+}
+CDG_HD double cdg_evalue(double score, double qLen, double dbRes) {
+    return (CdgAlp::K * exp(-CdgAlp::lambda * score)) * cdg_alp_area(score, dbRes, qLen);
+}
+CDG_HD double cdg_bitscore(double score) {
+    return (CdgAlp::lambda * score - log(CdgAlp::K)) / 0.69314718055994530942;
+}
+
+// ---- record value packing -----------------------------------------------------------------------
+// k-mer record = {key u64: canonical k-mer | bit63 (1 = forward, 0 = reverse complement picked),
+//                 val u64: id:32 | pos:32}  (KmerPosition, kmermatcher.h:49-54; seqLen is looked up by id)
+CDG_HD u64 cdg_pack_val(u32 id, u32 pos) { return ((u64) id << 32) | pos; }
+CDG_HD u32 cdg_val_id(u64 v) { return (u32) (v >> 32); }
+CDG_HD u32 cdg_val_pos(u64 v) { return (u32) v; }

@@ -1,0 +1,542 @@
+// kmermatcher on the device (reference: lib/mmseqs/src/linclust/kmermatcher.cpp).
+//   pack_kernel          ASCII -> 2-bit words + X mask            (Sequence::mapSequence, Sequence.cpp:476-489)
+//   extract_short_kernel per-sequence k-mer selection, warp/seq   (fillKmerPositionArray :77-388)
+//   extract_long_kernel  same for sequences where the hash threshold is active, block/seq
+//   group_kernel         rep selection + diagonal per member      (sort :412 + assignGroup :453-562)
+//   reduce kernels       best diagonal per (rep,target) + bleed   (sort :431 + writeKmerMatcherResult :815-930)
+#pragma once
+#include "cdg_common.cuh"
+#include "cdg_sort.cuh"
+
+namespace cdgkmer {
+
+// ---------------------------------------------------------------------------------------------------
+// Packed layout: sequence i owns words [wordOff[i], wordOff[i+1]) of `words` (u64, 32 bases per word,
+// base j of a word in bits [62-2j, 63-2j], i.e. first base most significant, like the k-mer index of
+// Indexer::computeKmerIdx, Indexer.h:136-143) and the same range of `xmask` (u32, bit 31-j set when base
+// j maps to X).  flags[i] bit0: some byte is not one of upper-case A,C,G,T ("exception" sequence).
+__global__ void __launch_bounds__(256) pack_kernel(const u8 *__restrict__ data, const u64 *__restrict__ off, const u32 *__restrict__ len,
+                                                   const u64 *__restrict__ wordOff, u64 n, u64 *__restrict__ words,
+                                                   u32 *__restrict__ xmask, u8 *__restrict__ flags) {
+    // one warp per sequence, lane per word (strided)
+    u64 seq = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (seq >= n) return;
+    const u8 *s = data + off[seq];
+    u32 L = len[seq];
+    u64 w0 = wordOff[seq];
+    u32 nw = (L + 31) >> 5;
+    u32 exc = 0;
+    for (u32 w = lane; w < nw; w += 32) {
+        u64 bits = 0; u32 xm = 0;
+        u32 base = w << 5;
+#pragma unroll 8
+        for (u32 j = 0; j < 32; j++) {
+            u32 p = base + j;
+            int c = 0;
+            if (p < L) {
+                unsigned char ch = s[p];
+                c = cdg_map_letter(ch);
+                if (cdg_plain_code(ch) == 4) exc = 1;
+            }
+            bits = (bits << 2) | (u64) (c & 3);
+            xm = (xm << 1) | (c == 4 ? 1u : 0u);
+        }
+        words[w0 + w] = bits;
+        xmask[w0 + w] = xm;
+    }
+    exc = __any_sync(0xffffffffu, exc);
+    if (lane == 0) flags[seq] = (u8) (exc ? 1 : 0);
+}
+
+// 2k-bit window starting at base p of a packed sequence (caller guarantees p + k <= L)
+CDG_D u64 window_bits(const u64 *__restrict__ w, u32 p, int k) {
+    u32 wi = p >> 5, sh = (p & 31) * 2;
+    u64 hi = w[wi];
+    u64 v = hi << sh;
+    if (sh && ((p & 31) + k > 32)) v |= w[wi + 1] >> (64 - sh);
+    return v >> (64 - 2 * k);
+}
+CDG_D u32 window_xmask(const u32 *__restrict__ xm, u32 p, int k) {   // nonzero iff the window contains X
+    u32 wi = p >> 5, sh = p & 31;
+    u64 two = ((u64) xm[wi] << 32);
+    if (sh + k > 32) two |= xm[wi + 1];
+    u64 v = two << sh;
+    return (u32) (v >> (64 - k)) ;
+}
+CDG_D int base_code(const u64 *__restrict__ w, const u32 *__restrict__ xm, u32 p) {   // A0 C1 T2 G3 X4
+    if ((xm[p >> 5] >> (31 - (p & 31))) & 1u) return 4;
+    return (int) ((w[p >> 5] >> (62 - 2 * (p & 31))) & 3ull);
+}
+
+struct ExtractParams {
+    int k; int kmersPerSeq; float scale; u64 seed; u32 hashLo, hashHi;
+};
+// slots reserved for sequence of length L: upper bound of selected k-mers (kmermatcher.cpp:226)
+CDG_HD u32 kmer_capacity(u32 L, int k, int kmersPerSeq, float scale) {
+    u32 W = L >= (u32) k ? L - k + 1 : 0;
+    float consF = (float) (kmersPerSeq - 1) + scale * (float) L;
+    u64 cons = consF > 0.f ? (u64) consF : 0;
+    return (u32) (cons < W ? cons : W);
+}
+CDG_HD bool is_short_seq(u32 L, int k, int kmersPerSeq, float scale) {   // no hash threshold, <= 256 windows
+    u32 W = L >= (u32) k ? L - k + 1 : 0;
+    return W <= 256 && kmer_capacity(L, k, kmersPerSeq, scale) >= W;
+}
+
+// powers of 31 (mod 2^64) for the identity hash Util::hash (Util.h:337-346): h = sum code_i * 31^(L-1-i)
+CDG_D u64 pow31(u32 e) {
+    u64 r = 1, b = 31;
+    while (e) { if (e & 1) r *= b; b *= b; e >>= 1; }
+    return r;
+}
+
+struct WinRec { u64 kmer; u32 pos; u32 score; };   // kmer carries the strand bit 63
+
+// canonical k-mer of window p; returns false for windows the reference skips (X, palindromes)
+CDG_D bool make_window(const u64 *__restrict__ w, const u32 *__restrict__ xm, u32 p, u32 L, const ExtractParams &P, WinRec &r) {
+    if (window_xmask(xm, p, P.k)) return false;                     // kmermatcher.cpp:146
+    u64 idx = window_bits(w, p, P.k);
+    u64 rc = cdg_revcomp_kmer(idx, P.k);
+    if (rc == idx) return false;                                    // :159
+    bool useRc = rc < idx;
+    u64 canon = useRc ? rc : idx;
+    r.score = (u32) (cdg_xxh64_u64(canon, P.seed) & 0xFFFFu);       // :164
+    r.kmer = useRc ? canon : (canon | CDG_B63);                     // :183
+    r.pos = useRc ? (L - p - P.k) : p;                              // :185
+    return true;
+}
+
+// order of SequencePosition::compareByScoreReverse (kmermatcher.h:29-46); full ties: forward first
+CDG_D bool win_less(const WinRec &a, const WinRec &b) {
+    if (a.score != b.score) return a.score < b.score;
+    u64 ka = a.kmer | CDG_B63, kb = b.kmer | CDG_B63;
+    if (ka != kb) return ka < kb;
+    if (a.pos != b.pos) return a.pos < b.pos;
+    return (a.kmer & CDG_B63) > (b.kmer & CDG_B63);
+}
+
+// The reference's sequential selection loop (kmermatcher.cpp:275-347) over records sorted by win_less.
+// keep[i] = 1 for selected records.  Run by ONE thread; only for sequences with repeated k-mers or an
+// active hash threshold.
+CDG_D void select_sequential(const WinRec *sorted, u32 cnt, u32 considered, u32 threshold, int tooMuch, u8 *keep) {
+    u32 selected = 0;
+    for (u32 i = 0; i < cnt && selected < considered; i++) {
+        u64 kmer = sorted[i].kmer | CDG_B63;
+        if (i + 1 < cnt) {
+            u64 next = sorted[i + 1].kmer | CDG_B63;
+            if (kmer == next) {
+                while (kmer == next && i < cnt) {
+                    i++;
+                    if (i >= cnt) break;
+                    next = sorted[i].kmer | CDG_B63;
+                }
+            }
+        }
+        if (i >= cnt) break;
+        if (sorted[i].score < threshold) {
+            if (sorted[i].score == threshold - 1 && tooMuch) {
+                tooMuch--;
+                threshold -= (tooMuch == 0) ? 1 : 0;
+            }
+            selected++;
+            keep[i] = 1;
+        }
+    }
+}
+
+// identity record (kmermatcher.cpp:133-137,244-262): key = XXH64(Util::hash(codes)), pos 0.
+// Goes to idKeys/idVals[seq] unless its value (bit 63 masked) lies inside the k-mer key range, in
+// which case it must be sorted among the k-mers: those go to the `extra` slots of the main array.
+CDG_D void emit_identity(u64 seqHash, u64 seq, const ExtractParams &P, u64 *idKeys, u64 *idVals, u64 *mainKeys, u64 *mainVals,
+                         u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow) {
+    u32 h16 = (u32) (seqHash & 0xFFFFu);
+    bool owned = h16 >= P.hashLo && h16 <= P.hashHi;
+    u64 key = CDG_SENTINEL, val = 0;
+    if (owned) { key = seqHash; val = cdg_pack_val((u32) seq, 0); }
+    if (owned && (seqHash & ~CDG_B63) < (1ull << (2 * P.k))) {
+        u32 slot = atomicAdd(extraCount, 1u);
+        if (slot < extraCap) { mainKeys[extraBase + slot] = key; mainVals[extraBase + slot] = val; }
+        else atomicExch(overflow, 1u);
+        key = CDG_SENTINEL; val = 0;
+    }
+    idKeys[seq] = key; idVals[seq] = val;
+}
+
+static constexpr int EX_WARPS = 8;
+static constexpr int EX_MAXW = 256;   // windows per short sequence
+
+// ---- short sequences: one warp per sequence ------------------------------------------------------------
+// Fast path (no repeated k-mer inside the sequence): every valid window is emitted.  A per-warp bitmap over
+// the 16-bit hash detects possible repeats (equal k-mers have equal hashes); on a hit the warp ranks its
+// windows in shared... global scratch and lane 0 replays the reference's sequential loop.
+__global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
+    const u64 *__restrict__ words, const u32 *__restrict__ xmask, const u64 *__restrict__ wordOff, const u32 *__restrict__ len,
+    u64 n, ExtractParams P, const u64 *__restrict__ slotOff /*[n] first main slot of seq*/,
+    u64 *__restrict__ mainKeys, u64 *__restrict__ mainVals, u64 *__restrict__ idKeys, u64 *__restrict__ idVals,
+    u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow, WinRec *__restrict__ scratch /*[gridWarps][2*EX_MAXW]*/,
+    u8 *__restrict__ scratchKeep /*[gridWarps][EX_MAXW]*/, unsigned long long *__restrict__ emitted) {
+    extern __shared__ u32 bitmapAll[];   // [EX_WARPS][2048] : 65536 bits per warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 *bitmap = bitmapAll + warp * 2048;
+    for (int i = lane; i < 2048; i += 32) bitmap[i] = 0;
+    __syncwarp();
+    const u64 gwarp = (u64) blockIdx.x * EX_WARPS + warp, nwarps = (u64) gridDim.x * EX_WARPS;
+    WinRec *myScratch = scratch + gwarp * (2 * EX_MAXW);
+    u8 *myKeep = scratchKeep + gwarp * EX_MAXW;
+    unsigned long long localEmitted = 0;
+
+    for (u64 seq = gwarp; seq < n; seq += nwarps) {
+        const u32 L = len[seq];
+        if (!is_short_seq(L, P.k, P.kmersPerSeq, P.scale)) continue;   // handled by extract_long_kernel
+        const u64 *w = words + wordOff[seq];
+        const u32 *xm = xmask + wordOff[seq];
+        const u32 W = L >= (u32) P.k ? L - P.k + 1 : 0;
+        // identity hash
+        u64 part = 0;
+        for (u32 p = lane; p < L; p += 32) part += (u64) base_code(w, xm, p) * pow31(L - 1 - p);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) emit_identity(cdg_xxh64_u64(part, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow);
+
+        // windows: lane handles p = lane + 32*it
+        WinRec rec[EX_MAXW / 32];
+        u32 validMask = 0;   // bit it
+        u32 collide = 0;
+#pragma unroll
+        for (int it = 0; it < EX_MAXW / 32; it++) {
+            u32 p = lane + 32 * it;
+            bool ok = false;
+            if (p < W) ok = make_window(w, xm, p, L, P, rec[it]);
+            if (ok) {
+                validMask |= 1u << it;
+                u32 bit = 1u << (rec[it].score & 31);
+                u32 old = atomicOr(&bitmap[rec[it].score >> 5], bit);
+                collide |= old & bit;
+            }
+        }
+        __syncwarp();
+        // clear the bits again (cheaper than wiping 8 KB per sequence)
+#pragma unroll
+        for (int it = 0; it < EX_MAXW / 32; it++) if (validMask & (1u << it)) bitmap[rec[it].score >> 5] = 0;
+        __syncwarp();
+        collide = __any_sync(0xffffffffu, collide);
+
+        const u64 slot0 = slotOff[seq];
+        const u32 cap = kmer_capacity(L, P.k, P.kmersPerSeq, P.scale);
+        u32 written = 0;   // warp-uniform
+        if (!collide) {
+#pragma unroll
+            for (int it = 0; it < EX_MAXW / 32; it++) {
+                bool ok = (validMask >> it) & 1u;
+                bool own = ok && rec[it].score >= P.hashLo && rec[it].score <= P.hashHi;
+                u32 b = __ballot_sync(0xffffffffu, own);
+                if (own) {
+                    u64 dst = slot0 + written + __popc(b & ((1u << lane) - 1));
+                    mainKeys[dst] = rec[it].kmer;
+                    mainVals[dst] = cdg_pack_val((u32) seq, rec[it].pos);
+                }
+                written += __popc(b);
+            }
+        } else {
+            // exact path: materialise, rank (O(cnt^2/32)), sequential replay by lane 0
+            u32 cnt = 0;
+#pragma unroll
+            for (int it = 0; it < EX_MAXW / 32; it++) {
+                bool ok = (validMask >> it) & 1u;
+                u32 b = __ballot_sync(0xffffffffu, ok);
+                if (ok) myScratch[cnt + __popc(b & ((1u << lane) - 1))] = rec[it];
+                cnt += __popc(b);
+            }
+            __syncwarp();
+            WinRec *sorted = myScratch + EX_MAXW;
+            for (u32 i = lane; i < cnt; i += 32) {
+                WinRec me = myScratch[i];
+                u32 r = 0;
+                for (u32 j = 0; j < cnt; j++) {
+                    WinRec o = myScratch[j];
+                    r += (win_less(o, me) || (!win_less(me, o) && j < i)) ? 1u : 0u;
+                }
+                sorted[r] = me;
+                myKeep[i] = 0;
+            }
+            __syncwarp();
+            if (lane == 0) select_sequential(sorted, cnt, cnt, 65536u, 0, myKeep);
+            __syncwarp();
+            for (u32 base = 0; base < cnt; base += 32) {
+                u32 i = base + lane;
+                bool own = i < cnt && myKeep[i] && sorted[i].score >= P.hashLo && sorted[i].score <= P.hashHi;
+                u32 b = __ballot_sync(0xffffffffu, own);
+                if (own) {
+                    u64 dst = slot0 + written + __popc(b & ((1u << lane) - 1));
+                    mainKeys[dst] = sorted[i].kmer;
+                    mainVals[dst] = cdg_pack_val((u32) seq, sorted[i].pos);
+                }
+                written += __popc(b);
+            }
+            __syncwarp();
+        }
+        for (u32 s = written + lane; s < cap; s += 32) { mainKeys[slot0 + s] = CDG_SENTINEL; mainVals[slot0 + s] = 0; }
+        localEmitted += written;
+    }
+    if (lane == 0 && localEmitted) atomicAdd(emitted, localEmitted);
+}
+
+// ---- long sequences (hash threshold active or > 256 windows): one block per sequence -------------------
+// scoreDist/hier histograms (kmermatcher.cpp:128-129,224-241) in shared memory; candidates below the
+// threshold are compacted to global scratch, bitonic-sorted by the block, replayed by thread 0.
+static constexpr int EXL_BLOCK = 256;
+__global__ void __launch_bounds__(EXL_BLOCK) extract_long_kernel(
+    const u64 *__restrict__ words, const u32 *__restrict__ xmask, const u64 *__restrict__ wordOff, const u32 *__restrict__ len,
+    const u32 *__restrict__ longList, u32 nLong, ExtractParams P, const u64 *__restrict__ slotOff,
+    u64 *__restrict__ mainKeys, u64 *__restrict__ mainVals, u64 *__restrict__ idKeys, u64 *__restrict__ idVals,
+    u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow,
+    WinRec *__restrict__ scratch, u8 *__restrict__ scratchKeep, const u64 *__restrict__ scratchOff /*[nLong] pow2-padded regions*/,
+    unsigned long long *__restrict__ emitted) {
+    extern __shared__ u32 shmem[];
+    u16 *scoreDist = (u16 *) shmem;               // 65536 x u16 (the reference uses unsigned short too)
+    u32 *hier = shmem + 32768;                    // 128
+    __shared__ u32 sThreshold, sCnt, sCand, sWritten;
+    __shared__ int sTooMuch;
+    __shared__ u32 sConsidered;
+    __shared__ unsigned long long sHash[EXL_BLOCK / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (u32 li = blockIdx.x; li < nLong; li += gridDim.x) {
+        const u64 seq = longList[li];
+        const u32 L = len[seq];
+        const u64 *w = words + wordOff[seq];
+        const u32 *xm = xmask + wordOff[seq];
+        const u32 W = L >= (u32) P.k ? L - P.k + 1 : 0;
+        for (int i = tid; i < 32768 + 128; i += EXL_BLOCK) shmem[i] = 0;
+        if (tid == 0) { sCnt = 0; sCand = 0; sWritten = 0; }
+        __syncthreads();
+        // identity hash
+        u64 part = 0;
+        for (u32 p = tid; p < L; p += EXL_BLOCK) part += (u64) base_code(w, xm, p) * pow31(L - 1 - p);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) sHash[warp] = part;
+        // pass 1: histograms
+        u32 myCnt = 0;
+        for (u32 p = tid; p < W; p += EXL_BLOCK) {
+            WinRec r;
+            if (make_window(w, xm, p, L, P, r)) {
+                myCnt++;
+                // 16-bit counters packed two per word
+                atomicAdd(&shmem[r.score >> 1], (r.score & 1) ? 0x10000u : 1u);
+                atomicAdd(&hier[r.score >> 9], 1u);
+            }
+        }
+        atomicAdd(&sCnt, myCnt);
+        __syncthreads();
+        if (tid == 0) {
+            u64 h = 0;
+            for (int i = 0; i < EXL_BLOCK / 32; i++) h += sHash[i];
+            emit_identity(cdg_xxh64_u64(h, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow);
+            u32 cnt = sCnt;
+            float consF = (float) (P.kmersPerSeq - 1) + P.scale * (float) L;
+            u64 cons64 = consF > 0.f ? (u64) consF : 0;
+            u32 considered = (u32) (cons64 < cnt ? cons64 : cnt);
+            u32 threshold = 0; u64 inBins = 0;
+            if (cnt > 0) {                                            // kmermatcher.cpp:228-241
+                u32 ht = 0;
+                for (ht = 0; ht < 128 && inBins < considered; ht++) inBins += hier[ht];
+                ht -= (ht > 0) ? 1 : 0;
+                inBins -= hier[ht];
+                for (threshold = ht * 512; threshold <= 65535 && inBins < considered; threshold++) inBins += scoreDist[threshold];
+            }
+            sThreshold = threshold; sTooMuch = (int) (inBins - considered); sConsidered = considered;
+        }
+        __syncthreads();
+        const u32 threshold = sThreshold;
+        WinRec *cand = scratch + scratchOff[li];
+        u8 *keep = scratchKeep + scratchOff[li];
+        // pass 2: compact candidates (score < threshold) — order irrelevant, sorted next
+        for (u32 base = 0; base < W; base += EXL_BLOCK) {
+            u32 p = base + tid;
+            WinRec r; bool ok = false;
+            if (p < W) ok = make_window(w, xm, p, L, P, r) && r.score < threshold;
+            u32 b = __ballot_sync(0xffffffffu, ok);
+            u32 wbase = 0;
+            if (lane == 0 && b) wbase = atomicAdd(&sCand, __popc(b));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (ok) cand[wbase + __popc(b & ((1u << lane) - 1))] = r;
+        }
+        __syncthreads();
+        const u32 nc = sCand;
+        u32 np2 = 1; while (np2 < nc) np2 <<= 1;
+        for (u32 i = nc + tid; i < np2; i += EXL_BLOCK) { WinRec pad; pad.kmer = CDG_SENTINEL; pad.pos = 0xFFFFFFFFu; pad.score = 0x10000u; cand[i] = pad; }
+        for (u32 i = tid; i < np2; i += EXL_BLOCK) keep[i] = 0;
+        __syncthreads();
+        for (u32 kk = 2; kk <= np2; kk <<= 1) {
+            for (u32 j = kk >> 1; j > 0; j >>= 1) {
+                for (u32 i = tid; i < np2; i += EXL_BLOCK) {
+                    u32 ixj = i ^ j;
+                    if (ixj > i) {
+                        WinRec a = cand[i], b = cand[ixj];
+                        bool up = (i & kk) == 0;
+                        if (up ? win_less(b, a) : win_less(a, b)) { cand[i] = b; cand[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (tid == 0) select_sequential(cand, nc, sConsidered, threshold, sTooMuch, keep);
+        __syncthreads();
+        const u64 slot0 = slotOff[seq];
+        const u32 cap = kmer_capacity(L, P.k, P.kmersPerSeq, P.scale);
+        for (u32 base = 0; base < nc; base += EXL_BLOCK) {
+            u32 i = base + tid;
+            bool own = i < nc && keep[i] && cand[i].score >= P.hashLo && cand[i].score <= P.hashHi;
+            u32 b = __ballot_sync(0xffffffffu, own);
+            u32 wbase = 0;
+            if (lane == 0 && b) wbase = atomicAdd(&sWritten, __popc(b));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (own) {
+                u64 dst = slot0 + wbase + __popc(b & ((1u << lane) - 1));
+                mainKeys[dst] = cand[i].kmer;
+                mainVals[dst] = cdg_pack_val((u32) seq, cand[i].pos);
+            }
+        }
+        __syncthreads();
+        const u32 written = sWritten;
+        for (u32 s = written + tid; s < cap; s += EXL_BLOCK) { mainKeys[slot0 + s] = CDG_SENTINEL; mainVals[slot0 + s] = 0; }
+        if (tid == 0 && written) atomicAdd(emitted, (unsigned long long) written);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// group assignment.  Input: records sorted by (key | bit63).  The thread of the first record of each run
+// of equal k-mers finds the representative = (max seqLen, min id, min pos) — the first record of the run
+// under compareRepSequenceAndIdAndPosReverse (kmermatcher.h:76-96) — and writes one compact record per
+// member (the representative included) for sort 2:
+//   key2 = rep << (idBits + diagBits + 1) | id << (diagBits + 1) | (diag + diagBias) << 1 | needRev
+struct GroupParams {
+    int idBits, diagBits; i32 diagBias; int onlyExtendable; int firstRunQuirk;   // :466 first run: repIsReverse=false
+};
+CDG_D bool rep_better(u32 lenA, u32 idA, u32 posA, u64 keyA, u32 lenB, u32 idB, u32 posB, u64 keyB) {   // A before B ?
+    if (lenA != lenB) return lenA > lenB;
+    if (idA != idB) return idA < idB;
+    if (posA != posB) return posA < posB;
+    return (keyA & CDG_B63) > (keyB & CDG_B63);
+}
+CDG_D void member_diag(bool repRev, u32 repLen, u32 repPos, bool tRev, u32 tLen, u32 tPos, i32 &diag, bool &need) {   // :489-521
+    i32 q, t;
+    if (repRev && !tRev) { q = (i32) repPos; t = (i32) tPos; need = true; }
+    else if (repRev && tRev) { q = (i32) (repLen - 1) - (i32) repPos; t = (i32) (tLen - 1) - (i32) tPos; need = false; }
+    else if (!repRev && tRev) { q = (i32) (repLen - 1) - (i32) repPos; t = (i32) (tLen - 1) - (i32) tPos; need = true; }
+    else { q = (i32) repPos; t = (i32) tPos; need = false; }
+    diag = q - t;
+}
+__global__ void __launch_bounds__(256) group_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, u64 n,
+                                                    const u32 *__restrict__ len, GroupParams G, u64 *__restrict__ out,
+                                                    unsigned long long *__restrict__ outCount) {
+    const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    u32 m = 0;          // members this thread will write
+    u64 runEnd = i;
+    u32 repLen = 0, repId = 0, repPos = 0; u64 repKey = 0;
+    bool head = false;
+    if (i < n) {
+        u64 k = keys[i];
+        if (k != CDG_SENTINEL && (i == 0 || (keys[i - 1] | CDG_B63) != (k | CDG_B63))) {
+            head = true;
+            u64 kk = k | CDG_B63;
+            u64 j = i;
+            while (j < n) {
+                u64 kj = keys[j];
+                if (kj == CDG_SENTINEL || (kj | CDG_B63) != kk) break;
+                u64 v = vals[j];
+                u32 id = cdg_val_id(v), pos = cdg_val_pos(v), l = len[id];
+                if (j == i || rep_better(l, id, pos, kj, repLen, repId, repPos, repKey)) { repLen = l; repId = id; repPos = pos; repKey = kj; }
+                j++;
+            }
+            runEnd = j;
+            if (j - i < 2) head = false;   // singletons are dropped (:476)
+        }
+    }
+    const bool repRev = head ? ((G.firstRunQuirk && i == 0) ? false : ((repKey & CDG_B63) == 0)) : false;
+    if (head) {
+        if (!G.onlyExtendable) m = (u32) (runEnd - i);
+        else {
+            for (u64 j = i; j < runEnd; j++) {
+                u64 v = vals[j]; u32 id = cdg_val_id(v); u32 tl = len[id];
+                i32 d; bool need;
+                member_diag(repRev, repLen, repPos, (keys[j] & CDG_B63) == 0, tl, cdg_val_pos(v), d, need);
+                if (d < 0 || d > (i32) repLen - (i32) tl) m++;   // :526-536
+            }
+        }
+    }
+    // warp-aggregated allocation of output slots
+    u32 incl = m;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    u32 total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && total) base = atomicAdd(outCount, (unsigned long long) total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (m) {
+        u64 dst = base + (incl - m);
+        const int sh1 = G.diagBits + 1, sh2 = G.idBits + G.diagBits + 1;
+        for (u64 j = i; j < runEnd; j++) {
+            u64 v = vals[j]; u32 id = cdg_val_id(v); u32 tl = len[id];
+            i32 d; bool need;
+            member_diag(repRev, repLen, repPos, (keys[j] & CDG_B63) == 0, tl, cdg_val_pos(v), d, need);
+            if (G.onlyExtendable && !(d < 0 || d > (i32) repLen - (i32) tl)) continue;
+            out[dst++] = ((u64) repId << sh2) | ((u64) id << sh1) | ((u64) (u32) (d + G.diagBias) << 1) | (need ? 1ull : 0ull);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// hit reduction over key2 sorted ascending.  A pair head is the first record of a (rep,target) pair; its
+// thread walks forward while the TARGET id stays equal — deliberately not checking the rep, which
+// reproduces the reference's rep-boundary bleed (kmermatcher.cpp:886-888) — and picks the most frequent
+// diagonal (ties: the larger one), the number of records and the strand of the last record on the best
+// diagonal (:889-905).  Self pairs (target == rep) produce no hit (:906).
+struct ReduceParams { int idBits, diagBits; i32 diagBias; };
+struct PairHeadFlag {
+    const u64 *keys; u64 n; int idBits, diagBits;
+    CDG_D u32 operator()(u64 i) const {
+        u64 k = keys[i];
+        u64 pair = k >> (diagBits + 1);
+        if (i > 0 && (keys[i - 1] >> (diagBits + 1)) == pair) return 0;
+        u32 id = (u32) (pair & ((1ull << idBits) - 1)), rep = (u32) (pair >> idBits);
+        return id != rep ? 1u : 0u;
+    }
+};
+__global__ void __launch_bounds__(cdgscan::BLOCK) reduce_kernel(PairHeadFlag f, ReduceParams R, const unsigned long long *__restrict__ tileSums,
+                                                                u32 *__restrict__ hitRep, u32 *__restrict__ hitTgt,
+                                                                i32 *__restrict__ hitScore, i32 *__restrict__ hitDiag) {
+    __shared__ u32 shWarp[cdgscan::BLOCK / 32 + 1];
+    u64 prefix[cdgscan::ITEMS]; u32 flag[cdgscan::ITEMS];
+    cdgscan::tile_prefix(f, f.n, tileSums, shWarp, prefix, flag);
+    const u64 base = (u64) blockIdx.x * cdgscan::TILE;
+    const u64 idMask = (1ull << R.idBits) - 1, diagMask = (1ull << R.diagBits) - 1;
+#pragma unroll 1
+    for (int it = 0; it < cdgscan::ITEMS; it++) {
+        if (!flag[it]) continue;
+        u64 i = base + (u64) it * cdgscan::BLOCK + threadIdx.x;
+        u64 k = f.keys[i];
+        u32 tgt = (u32) ((k >> (R.diagBits + 1)) & idMask), rep = (u32) (k >> (R.diagBits + 1 + R.idBits));
+        i32 prev = (i32) ((k >> 1) & diagMask), best = prev;
+        u32 dc = 0, mx = 0, top = 0; bool brev = (k & 1ull) != 0;
+        u64 e = i;
+        while (e < f.n) {
+            u64 ke = f.keys[e];
+            if ((u32) ((ke >> (R.diagBits + 1)) & idMask) != tgt) break;
+            i32 d = (i32) ((ke >> 1) & diagMask);
+            dc = (prev == d) ? dc + 1 : 1;
+            if (dc >= mx) { best = d; mx = dc; brev = (ke & 1ull) != 0; }
+            prev = d; e++; top++;
+        }
+        u64 h = prefix[it];
+        hitRep[h] = rep; hitTgt[h] = tgt;
+        hitScore[h] = brev ? -(i32) top : (i32) top;
+        hitDiag[h] = best - R.diagBias;
+    }
+}
+
+}   // namespace cdgkmer

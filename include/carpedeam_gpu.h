@@ -1,0 +1,180 @@
+/*
+ * carpedeam_gpu.h — C ABI of libcarpedeam_gpu.so (CUDA, sm_100a only; no CPU fallback).
+ *
+ * Drop-in boundary for CarpeDeam's read-level hot path.  The reference has no FFI: each stage is
+ * a C++ module `int stage(int argc, const char **argv, const Command&)` that reads and writes
+ * MMseqs2 databases.  These entry points are what the bodies of those modules call once the
+ * DBReader has mapped the databases (binding sketch: INTEGRATION.md):
+ *
+ *   kmermatcher        lib/mmseqs/src/linclust/kmermatcher.cpp:596 (kmermatcherInner)   -> cdg_kmermatch
+ *   rescorediagonal    lib/mmseqs/src/alignment/rescorediagonal.cpp:45 (doRescorediagonal) -> cdg_rescore
+ *   ancient_correction src/assembler/correction.cpp:128 (doCorrection)                   -> cdg_correct
+ *   one fused reads-only iteration (data/nuclassemble.sh:105-126)                         -> cdg_iteration
+ *
+ * Conventions: every function returns 0 on success or a negative cdg_status; cdg_last_error()
+ * gives the message.  Input buffers are caller-owned host memory (pinned memory makes the copies
+ * asynchronous).  Output views (cdg_hits, cdg_alns) point at library-owned pinned host memory
+ * that stays valid until the next call that produces the same kind of output, or cdg_destroy.
+ * Sequence ids are INDICES into the uploaded set (0..n-1); the caller uploads entries in ascending
+ * dbKey order (the order of an MMseqs2 .index file), so index order == dbKey order, which is what
+ * the reference's comparators use (kmermatcher.h:76-114, id = dbKey).
+ * One host thread per context.  A context owns one CUDA device and one stream.
+ */
+#ifndef CARPEDEAM_GPU_H
+#define CARPEDEAM_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cdg_ctx cdg_ctx;
+
+typedef enum {
+    CDG_OK = 0,
+    CDG_ERR_CUDA = -1,        /* CUDA runtime error (message has the call and the error string) */
+    CDG_ERR_ARG = -2,         /* invalid argument / call order */
+    CDG_ERR_UNSUPPORTED = -3, /* input outside what this build handles (message says which limit) */
+    CDG_ERR_NOMEM = -4
+} cdg_status;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int cdg_create(int device, cdg_ctx **out);
+void cdg_destroy(cdg_ctx *ctx);
+const char *cdg_last_error(const cdg_ctx *ctx);
+/* the CUDA stream (cudaStream_t) all work of this context is enqueued on — for event timing */
+void *cdg_stream(cdg_ctx *ctx);
+
+/* ---- sequence set (DBReader view: lib/mmseqs/src/commons/DBReader.h:169-237) -----------------
+ * data   : the DB data file bytes; entry i is data[offsets[i] .. offsets[i]+lens[i]) (then "\n\0")
+ * lens   : sequence lengths without the trailing "\n\0"  (DBReader::getSeqLen)
+ * ext    : CarpeDeam's 4th index column, "was extended" (DBReader::getExtData, DBReader.cpp:807-817)
+ * The set stays resident on the device until the next upload.  Packs the bases to 2 bit + N mask. */
+int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, const uint64_t *offsets,
+                    const uint32_t *lens, const uint8_t *ext, uint64_t n);
+
+/* ---- kmermatcher ----------------------------------------------------------------------------- */
+typedef struct {
+    int32_t k;                       /* -k (20 reads / 22 contigs) */
+    int32_t kmers_per_seq;           /* --kmer-per-seq 200 */
+    float kmers_per_seq_scale;       /* --kmer-per-seq-scale 0.2 */
+    uint64_t hash_shift;             /* --hash-shift 67 (XXH64 seed) */
+    int32_t include_only_extendable; /* --include-only-extendable */
+    uint32_t hash_lo, hash_hi;       /* 16-bit hash range owned by this call (0..65535 = unsplit;
+                                        kmermatcher.cpp:742-784 splits, multi-GPU owner ranges) */
+} cdg_kmer_params;
+
+/* prefilter hits in pref-DB order: for rep index ascending, target index ascending
+ * (writeKmerMatcherResult, kmermatcher.cpp:815-930).  score = +-#shared k-mers (sign = strand),
+ * diag = best diagonal truncated to int16 as prefilterHitToBuffer writes it (QueryMatcher.h:114-126).
+ * The `key 0 0` self lines are implicit: every sequence has one. */
+typedef struct {
+    uint64_t n_hits;
+    const uint32_t *rep;
+    const uint32_t *target;
+    const int32_t *score;
+    const int16_t *diag;
+    /* work counters: emitted k-mer records, records after group assignment */
+    uint64_t n_records, n_grouped;
+} cdg_hits;
+
+/* Runs extraction -> sort -> group -> sort -> reduce on the resident set.  The hit list stays on the
+ * device for cdg_rescore; `out` (may be NULL) receives a host copy. */
+int cdg_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p, cdg_hits *out);
+
+/* ---- rescorediagonal (mode 3, nucleotides, same query/target DB) ------------------------------ */
+typedef struct {
+    float min_seq_id;      /* --min-seq-id 0.9 */
+    double evalue_thr;     /* -e 0.001 */
+    uint64_t db_residues;  /* DBReader::getAminoAcidDBSize() of the target DB; 0 = resident set's total */
+} cdg_rescore_params;
+
+/* one record per prefilter line (self lines included), in pref order, grouped by query:
+ * lines of query q are [line_off[q], line_off[q+1]) */
+typedef struct {
+    uint64_t n_lines;
+    uint64_t n_queries;
+    const uint64_t *line_off; /* n_queries+1 */
+    const uint32_t *target;
+    const uint8_t *keep;      /* 1 = the reference writes this alignment (rescorediagonal.cpp:314) */
+    const int32_t *score;     /* raw ungapped score (DistanceCalculator.h:204-220) */
+    const int32_t *bits;      /* int(bitScore+0.5) */
+    const double *evalue;
+    const float *seq_id;      /* idCnt/alnLen (0 when the E-value gate failed, as in the reference) */
+    const int32_t *q_start, *q_end, *db_start, *db_end; /* as written: q_start > q_end = reverse strand */
+} cdg_alns;
+
+/* Replace the device-resident prefilter lines by caller-provided ones (stand-alone rescorediagonal:
+ * lines parsed from a pref DB with QueryMatcher::parsePrefilterHits, QueryMatcher.h:81-104).
+ * Lines must be grouped by query in ascending query index; every query has >= 0 lines. */
+int cdg_set_pref_lines(cdg_ctx *ctx, const uint64_t *line_off, uint64_t n_queries, const uint32_t *target,
+                       const int32_t *pref_score, const uint16_t *diag, uint64_t n_lines);
+
+int cdg_rescore(cdg_ctx *ctx, const cdg_rescore_params *p, cdg_alns *out);
+
+/* ---- ancient_correction ----------------------------------------------------------------------- */
+/* Damage model, host-built exactly as the reference builds it (nuclassembleUtil.cpp:821-1007,
+ * correction.cpp:51-75,93-107): natural logs, base order A0 C1 G2 T3.
+ *   log_d[l][q][t]    = log(max((double)D[l].p[q][t], 1e-3)),  log_drev likewise for Drev
+ *   log_seq_err[q][b] = (double)logl(seqErr.p[q][b])
+ * carpedeam_b200/host/damage.cpp builds these from the --ancient-damage .prof files. */
+typedef struct {
+    double log_d[11][4][4];
+    double log_drev[11][4][4];
+    double log_seq_err[4][4];
+} cdg_damage;
+int cdg_set_damage(cdg_ctx *ctx, const cdg_damage *d);
+
+typedef struct {
+    float min_seqid_corr_reads;   /* par.seqIdThr in correction.cpp:359 (--min-seq-id 0.9) */
+    float min_ryseq_id_corr_reads;/* --min-ryseq-id-corr-reads 0.99 */
+} cdg_corr_params;
+
+/* Replace the device-resident alignments by caller-provided ones (stand-alone ancient_correction:
+ * records parsed from the aln DB with Matcher::parseAlignmentRecord, Matcher.cpp:274-353). */
+int cdg_set_alignments(cdg_ctx *ctx, const uint64_t *aln_off, uint64_t n_queries, const uint32_t *target,
+                       const float *seq_id, const int32_t *q_start, const int32_t *q_end,
+                       const int32_t *db_start, const int32_t *db_end, uint64_t n_alns);
+
+/* Writes the corrected sequences into out_data, same layout as the uploaded data (only base bytes
+ * are written; copy the input first or pass a buffer of data_bytes — separators are copied too).
+ * n_changed (may be NULL) receives the number of bases that differ from the input. */
+int cdg_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data, uint64_t *n_changed);
+
+/* Per-column log-likelihoods of the last cdg_correct (north_star: within 1e-5 relative of the reference's
+ * long double sums): lik[(base_offset(q) + column) * 4 + qBase], NaN where mostLikeliBaseRead was not
+ * evaluated; base_offset = prefix sum of lens.  Debug/validation entry point. */
+int cdg_correct_likelihoods(cdg_ctx *ctx, const cdg_corr_params *p, double *lik);
+
+/* ---- fused iteration: kmermatch -> rescore -> correct with no host round trip ------------------ */
+typedef struct {
+    cdg_kmer_params kmer;
+    cdg_rescore_params rescore;
+    cdg_corr_params corr;
+} cdg_iter_params;
+int cdg_iteration(cdg_ctx *ctx, const cdg_iter_params *p, cdg_hits *hits, cdg_alns *alns, uint8_t *out_data,
+                  uint64_t *n_changed);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+typedef struct {
+    uint64_t n_seqs, n_bases;           /* N, S */
+    uint64_t n_records, n_grouped;      /* R1, R2 */
+    uint64_t n_hits, n_alns;            /* H, A (kept alignments incl. self) */
+    uint32_t sort1_passes, sort2_passes;/* P1, P2 */
+    uint64_t kernel_launches;           /* kernels launched by this context since creation */
+    float ms_extract, ms_sort1, ms_group, ms_sort2, ms_reduce, ms_rescore, ms_correct; /* last run, CUDA events */
+} cdg_stats;
+int cdg_get_stats(cdg_ctx *ctx, cdg_stats *out);
+
+/* ---- unit-test entry points (exercise single kernels through the ABI) -------------------------- */
+/* in-house LSD radix sort of (key,value) pairs on bits [bit_lo, bit_hi) of the key; values may be NULL */
+int cdg_test_radix_sort(cdg_ctx *ctx, uint64_t *keys, uint64_t *vals, uint64_t n, int bit_lo, int bit_hi);
+/* XXH64 of one u64 (kmermatcher.cpp:33-38) and 2-bit reverse complement (Util.cpp:601-638) on the device */
+int cdg_test_hash_revcomp(cdg_ctx *ctx, const uint64_t *in, uint64_t n, int k, uint64_t seed, uint64_t *hash_out,
+                          uint64_t *rc_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -476,7 +476,7 @@ extern "C" void orc_correct(const char *blob, const u64 *off, const u32 *len, co
                             float seqIdThr, float ryThr, double seqErrRate,
                             char *outBlob, const u64 *likOff, double *likOut) {
     DiNuc seqErr; long double err = (long double) seqErrRate;
-    if (seqErrRate == 0.01) err = 0.01L;   // correction.cpp:196 literal
+    // correction.cpp:196 `long double seqErrCorrection = 0.01;` is a double literal widened: same as the cast above
     for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) seqErr.p[i][j] = (i == j) ? 1 - err : err / 3;
     struct A { u32 t; float sid; int qS, qE, dS, dE, dL, aln; bool rev; };
     std::vector<A> alns; std::string trev;

@@ -1,0 +1,212 @@
+"""GPU parity tests: the CUDA path through the C ABI (carpedeam_b200 -> libcarpedeam_gpu.so) against the
+oracle on the same inputs, and against the reference's own golden DBs.  Bit-exact for hits, diagonals,
+integer scores, coordinates and corrected bases; 1e-5 relative for log-likelihoods (north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from support import GOLD, SeqSet, format_aln, format_pref, load_golden, parse_aln, parse_pref, synth_reads
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("nucl_reads", "pref_0", "aln_0", "correction_0", 20, 0),
+    ("assembly_reads_0", "pref_1", "aln_1", "correction_1", 20, 0),
+    ("assembly_reads_4", "pref_asm_5", "aln_asm_5", "correction_5", 22, 1),
+    ("assembly_contigs_8_noneCycle", "pref_asm_9", "aln_asm_9", "correction_9", 22, 1),
+]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import carpedeam_b200 as cd
+    c = cd.Context(0)
+    yield c
+    c.close()
+
+
+def test_hash_and_revcomp(ctx, oracle):
+    rng = np.random.default_rng(1)
+    for k in (20, 22, 6, 31):
+        x = rng.integers(0, 1 << (2 * k), 5000, dtype=np.uint64)
+        h, r = ctx.test_hash_revcomp(x, k, 67)
+        for i in range(0, 5000, 97):
+            assert int(h[i]) == oracle.L.orc_xxh64_u64(int(x[i]), 67)
+            assert int(r[i]) == oracle.L.orc_revcomp(int(x[i]), k)
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 4096, 4097, 100003, 3000001])
+@pytest.mark.parametrize("pairs", [False, True])
+def test_radix_sort(ctx, n, pairs):
+    rng = np.random.default_rng(n + 7)
+    keys = rng.integers(0, 1 << 62, n, dtype=np.uint64)
+    if n > 10:
+        keys[: n // 3] &= np.uint64(0xFFFF)      # skewed digits / many duplicates
+    vals = np.arange(n, dtype=np.uint64) if pairs else None
+    for lo, hi in ((0, 40), (0, 63), (3, 17)):
+        k2, v2 = ctx.test_radix_sort(keys, vals, lo, hi)
+        mask = np.uint64(((1 << hi) - 1) ^ ((1 << lo) - 1))
+        order = np.argsort(keys & mask, kind="stable")
+        assert np.array_equal(k2, keys[order])
+        if pairs:
+            assert np.array_equal(v2, vals[order])   # stability
+
+
+def _hits_equal(a, b):
+    for f in ("rep", "tgt", "score", "diag"):
+        assert np.array_equal(a[f], b[f]), f
+    assert a["R1"] == b["R1"] and a["R2"] == b["R2"]
+
+
+@pytest.mark.parametrize("seqdb,pref,aln,corr,k,only_ext", CASES)
+def test_kmermatch_vs_oracle_and_reference(ctx, oracle, seqdb, pref, aln, corr, k, only_ext):
+    import carpedeam_b200 as cd
+    s = SeqSet.from_golden(seqdb)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    got = ctx.kmermatch(cd.kmer_params(k=k, include_only_extendable=only_ext))
+    want = oracle.kmermatch(s, k=k, only_ext=only_ext)
+    _hits_equal(got, want)
+    keys, payloads, _ = load_golden(pref)
+    mine = format_pref(s, got)
+    assert all(mine[kk] == p for kk, p in zip(keys, payloads))
+
+
+@pytest.mark.parametrize("seqdb,pref,aln,corr,k,only_ext", CASES)
+def test_rescore_standalone_vs_reference(ctx, oracle, seqdb, pref, aln, corr, k, only_ext):
+    s = SeqSet.from_golden(seqdb)
+    keys, payloads, _ = load_golden(pref)
+    q, t, sc, dg, off = parse_pref(s, payloads)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_pref_lines(off, t, sc, dg)
+    got = ctx.rescore()
+    want = oracle.rescore(s, q, t, sc, dg)
+    for f in ("keep", "score", "bits", "qs", "qe", "ds", "de"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(got["seqid"], want["seqid"])
+    assert np.allclose(got["evalue"], want["evalue"], rtol=1e-12, atol=0)
+    mine = format_aln(s, got["line_off"], got["tgt"], got)
+    akeys, apay, _ = load_golden(aln)
+    bad = [kk for kk, p in zip(akeys, apay) if mine[kk] != p]
+    assert not bad, (len(bad), mine[bad[0]][:200], apay[akeys.index(bad[0])][:200])
+
+
+@pytest.mark.parametrize("seqdb,pref,aln,corr,k,only_ext", CASES)
+def test_correction_standalone_vs_reference(ctx, oracle, seqdb, pref, aln, corr, k, only_ext):
+    import carpedeam_b200 as cd
+    s = SeqSet.from_golden(seqdb)
+    akeys, apay, _ = load_golden(aln)
+    off, t, sid, qs, qe, ds, de = parse_aln(s, apay)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+    ctx.set_alignments(off, t, sid, qs, qe, ds, de)
+    out, changed = ctx.correct()
+    oracle.load_damage(os.path.join(GOLD, "dhigh"))
+    want, lik_want = oracle.correct(s, off, t, sid, qs, qe, ds, de, want_lik=True)
+    assert np.array_equal(out, want)
+    ckeys, cpay, _ = load_golden(corr)
+    for i, p in enumerate(cpay):
+        o = int(s.off[i]); L = int(s.len[i])
+        assert out[o:o + L].tobytes() + b"\n" == p
+    assert changed == int((out != s.blob).sum())
+    # log-likelihoods: within 1e-5 relative of the reference's long double sums
+    lik = ctx.correct_likelihoods(s.total)
+    m = ~np.isnan(lik_want)
+    assert np.array_equal(m, ~np.isnan(lik))
+    assert np.allclose(lik[m], lik_want[m], rtol=1e-5, atol=0)
+    assert m.sum() > 0
+
+
+@pytest.mark.parametrize("seqdb,pref,aln,corr,k,only_ext", CASES)
+def test_fused_iteration_vs_reference(ctx, seqdb, pref, aln, corr, k, only_ext):
+    import carpedeam_b200 as cd
+    s = SeqSet.from_golden(seqdb)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+    hits, alns, out, changed = ctx.iteration(kmer=cd.kmer_params(k=k, include_only_extendable=only_ext), fetch_hits=True)
+    keys, payloads, _ = load_golden(pref)
+    mine = format_pref(s, hits)
+    assert all(mine[kk] == p for kk, p in zip(keys, payloads))
+    akeys, apay, _ = load_golden(aln)
+    mine = format_aln(s, alns["line_off"], alns["tgt"], alns)
+    assert all(mine[kk] == p for kk, p in zip(akeys, apay))
+    ckeys, cpay, _ = load_golden(corr)
+    for i, p in enumerate(cpay):
+        o = int(s.off[i]); L = int(s.len[i])
+        assert out[o:o + L].tobytes() + b"\n" == p
+    st = ctx.stats()
+    assert st["n_hits"] == len(hits["rep"]) and st["kernel_launches"] > 0
+
+
+def _oracle_iteration(oracle, s, k=20):
+    hits = oracle.kmermatch(s, k=k)
+    n = s.n
+    H = len(hits["rep"])
+    lo = np.searchsorted(hits["rep"], np.arange(n + 1))
+    line_off = (np.arange(n + 1) + lo).astype(np.uint64)
+    M = n + H
+    q = np.zeros(M, np.uint32); t = np.zeros(M, np.uint32); sc = np.zeros(M, np.int32); dg = np.zeros(M, np.uint16)
+    self_pos = line_off[:n].astype(np.int64)
+    q[self_pos] = np.arange(n); t[self_pos] = np.arange(n)
+    hp = np.arange(H) + hits["rep"].astype(np.int64) + 1
+    q[hp] = hits["rep"]; t[hp] = hits["tgt"]; sc[hp] = hits["score"]; dg[hp] = hits["diag"].astype(np.uint16)
+    r = oracle.rescore(s, q, t, sc, dg)
+    kept = r["keep"].astype(bool)
+    from support import seqid_text
+    sid = np.array([np.float32(float(seqid_text(x))) for x in r["seqid"][kept]], np.float32)
+    aoff = np.zeros(n + 1, np.uint64)
+    np.add.at(aoff, q[kept].astype(np.int64) + 1, 1)
+    aoff = np.cumsum(aoff).astype(np.uint64)
+    out, _ = oracle.correct(s, aoff, t[kept], sid, r["qs"][kept], r["qe"][kept], r["ds"][kept], r["de"][kept])
+    return hits, r, line_off, out
+
+
+@pytest.mark.parametrize("n,glen,nfrac,seed", [(3000, 20000, 0.0, 11), (20000, 100000, 0.002, 12), (500, 3000, 0.05, 13)])
+def test_fused_iteration_vs_oracle_synthetic(ctx, oracle, n, glen, nfrac, seed):
+    import carpedeam_b200 as cd
+    seqs = synth_reads(n, glen, seed, n_frac=nfrac)
+    if seed == 13:   # ragged: lower case, IUPAC, tiny and long sequences, duplicates, reverse-complement duplicates
+        seqs[3] = seqs[3].lower(); seqs[5] = seqs[5][:10] + b"R" + seqs[5][11:]; seqs[7] = b"ACGTACGTAC"; seqs[9] = seqs[8]
+        seqs[11] = b"A" * 60; seqs[13] = (seqs[12] + seqs[14] + seqs[15] + seqs[16] + seqs[17] + seqs[18]) * 2
+    s = SeqSet(seqs)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+    oracle.load_damage(os.path.join(GOLD, "dhigh"))
+    hits, alns, out, changed = ctx.iteration(fetch_hits=True)
+    ohits, r, line_off, oout = _oracle_iteration(oracle, s)
+    _hits_equal(hits, ohits)
+    assert np.array_equal(alns["line_off"], line_off)
+    for f in ("keep", "score", "bits", "qs", "qe", "ds", "de"):
+        assert np.array_equal(alns[f], r[f]), f
+    assert np.array_equal(alns["seqid"], r["seqid"])
+    assert np.array_equal(out, oout)
+    assert changed == int((out != s.blob).sum())
+
+
+def test_full_size_properties(ctx):
+    """size-independent properties at a size the oracle cannot do in seconds (2M reads)."""
+    import carpedeam_b200 as cd
+    from bench import synth_reads_fast
+    s = synth_reads_fast(2_000_000, 10_000_000, 99)
+    ctx.upload(s["blob"], s["off"], s["len"], None)
+    ctx.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+    hits, alns, out, changed = ctx.iteration(fetch_hits=True)
+    rep, tgt = hits["rep"].astype(np.int64), hits["tgt"].astype(np.int64)
+    pair = rep * (1 << 32) + tgt
+    assert np.all(np.diff(pair) > 0)                       # hit list strictly sorted by (rep,target): no duplicates
+    assert np.all(rep != tgt)
+    L = s["len"].astype(np.int64)
+    assert np.all(L[rep] >= L[tgt])                        # representative = longest member of its k-mer group
+    assert np.all(np.abs(hits["score"]) >= 1)
+    # self alignments: always kept, full length, score 2L
+    lo = alns["line_off"].astype(np.int64)
+    selfl = lo[:-1]
+    assert np.all(alns["keep"][selfl] == 1) and np.all(alns["score"][selfl] == 2 * L) and np.all(alns["qe"][selfl] == L - 1)
+    k = alns["keep"].astype(bool)
+    assert np.all(alns["seqid"][k] >= np.float32(0.9) - np.float32(1.2e-7))
+    # correction only rewrites base bytes, lengths and separators untouched, and is idempotent w.r.t. unchanged reads
+    diff = np.nonzero(out != s["blob"])[0]
+    assert len(diff) == changed and changed > 0
+    assert set(np.unique(out[diff]).tolist()) <= set(b"ACGT")
+    hits2, alns2, out2, changed2 = ctx.iteration(fetch_hits=True)
+    assert np.array_equal(out, out2) and np.array_equal(hits["score"], hits2["score"])   # deterministic
