@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(
 }
 
 // ---- ancient_correction ----------------------------------------------------------------------------------
-struct CorrParams { float seqIdThr; float ryThr; int roundSeqId; };   // roundSeqId: emulate the aln DB's 3-decimal text
+struct CorrParams { float seqIdThr; float ryThr; int roundSeqId; u32 wideThreshold; };   // roundSeqId: emulate the aln DB's 3-decimal text
 struct DamageTables { double logD[11][4][4]; double logDrev[11][4][4]; double logSE[4][4]; };
 
 CDG_D int nuc_map(unsigned char c) { return c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0; }   // correction.cpp:170-174, operator[] -> 0
@@ -223,8 +223,11 @@ CDG_D int most_likely_base(int b, u32 qIter, const u32 *cnt, const u32 *rv, cons
     return best;
 }
 
+// Generic (slow) kernel: 32-bit counters in local memory, any coverage.  Runs only on the queries the fast kernel
+// hands over through `list` (more than 65535 counted targets).
 static constexpr int CORR_WARPS = 4;
-__global__ void __launch_bounds__(CORR_WARPS * 32) correct_kernel(
+__global__ void __launch_bounds__(CORR_WARPS * 32) correct_wide_kernel(
+    const u32 *__restrict__ list, const u32 *__restrict__ listCount,
     const u8 *__restrict__ data, const u64 *__restrict__ off, const u32 *__restrict__ len, const u8 *__restrict__ ext, u64 n,
     const u64 *__restrict__ lineOff, const u32 *__restrict__ lineT, const u8 *__restrict__ keep, const float *__restrict__ seqId,
     const i32 *__restrict__ qS_, const i32 *__restrict__ qE_, const i32 *__restrict__ dS_, const i32 *__restrict__ dE_,
@@ -236,7 +239,10 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) correct_kernel(
     const int lane = threadIdx.x & 31;
     const u64 gwarp = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64) gridDim.x * blockDim.x) >> 5;
     u32 nChanged = 0;
-    for (u64 qi = gwarp; qi < n; qi += nwarps) {
+    const u64 nList = *listCount;
+    for (u64 li = gwarp; li < nList; li += nwarps) {
+        const u64 qi = list[li];
+        if (qi >= n) continue;
         const u64 l0 = lineOff[qi], l1 = lineOff[qi + 1];
         const u32 qLen = len[qi];
         const u8 *q = data + off[qi];
@@ -318,6 +324,212 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) correct_kernel(
                 if (res != orig) { o[col] = res; nChanged++; }
             }
         }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) nChanged += __shfl_xor_sync(0xffffffffu, nChanged, s);
+    if (lane == 0 && nChanged) atomicAdd(changed, (unsigned long long) nChanged);
+}
+
+
+// ---- fast kernel ---------------------------------------------------------------------------------------------
+// One warp per query.  pass 1: exact integer sum of alignment lengths (lane per line).  pass 2: lane per line,
+// RY identity from the 2-bit words (xor + popcount) unless a sequence holds exception bytes; the counted targets
+// are compacted into a per-warp shared-memory line cache (up to 32; more fall back to re-reading the line arrays).
+// pass 3: lane per query column; per-column counters count[t][l] | reverse[t][l] << 16 live in shared memory, a
+// 44-bit mask remembers which are non-zero so that the likelihood visits only those, in the reference's (t,l) order.
+static constexpr int CF_WARPS = 8;
+static constexpr int CF_CACHE = 32;
+struct SeqMeta { u64 off; u32 wordOff; u32 lenFlags; };   // lenFlags: len | exception << 30 | ext << 31
+static constexpr u32 META_EXC = 1u << 30, META_EXT = 1u << 31, META_LEN = (1u << 30) - 1;
+struct LineCache { u64 tOff[CF_CACHE]; u32 dL[CF_CACHE]; i32 qs[CF_CACHE]; i32 aln[CF_CACHE]; i32 ds[CF_CACHE]; u32 rev[CF_CACHE]; };
+struct CorrSmem { DamageTables T; u32 cnt[CF_WARPS][44][32]; LineCache lc[CF_WARPS]; };
+
+__global__ void __launch_bounds__(256) meta_kernel(const u64 *__restrict__ off, const u64 *__restrict__ wordOff, const u32 *__restrict__ len,
+                                                   const u8 *__restrict__ flags, const u8 *__restrict__ ext, u64 n, SeqMeta *__restrict__ meta) {
+    u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SeqMeta m; m.off = off[i]; m.wordOff = (u32) wordOff[i];
+    m.lenFlags = (len[i] & META_LEN) | (flags[i] ? META_EXC : 0u) | (ext[i] ? META_EXT : 0u);
+    meta[i] = m;
+}
+
+CDG_D u32 ry_dist_packed(const u64 *__restrict__ qw, u32 qs, const u64 *__restrict__ tw, u32 dL, bool rev, u32 ds, u32 aln) {
+    u32 dist = 0;
+    for (u32 o = 0; o < aln; o += 32) {
+        u32 c = aln - o < 32 ? aln - o : 32;
+        u64 a = get_bases(qw, qs + o, c);
+        u64 b = rev ? get_bases_rc(tw, dL, ds + o, c) : get_bases(tw, ds + o, c);
+        u64 x = a ^ b;
+        dist += __popcll((x ^ (x >> 1)) & 0x5555555555555555ull);
+    }
+    return dist;
+}
+
+// one target column into the per-column counters
+CDG_D void count_column(const u8 *__restrict__ data, u64 tOff, u32 dL, bool rev, u32 tp, u32 (*cnt)[32], int lane, unsigned long long &mask,
+                        u32 &cov0, u32 &cov1, u32 &cov2, u32 &cov3) {
+    const int cl = ((i32) tp >= (i32) dL - 5) ? 6 + (int) (tp - (dL - 5)) : (tp < 5 ? (int) tp : 5);   // correction.cpp:361-371
+    const int bse = nuc_map(t_char(data + tOff, dL, rev, tp));
+    const int idx = bse * 11 + cl;
+    cnt[idx][lane] += rev ? 0x10001u : 1u;
+    mask |= 1ull << idx;
+    cov0 += bse == 0; cov1 += bse == 1; cov2 += bse == 2; cov3 += bse == 3;
+}
+
+__global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
+    const u8 *__restrict__ data, const SeqMeta *__restrict__ meta, const u64 *__restrict__ words, u64 n,
+    const u64 *__restrict__ lineOff, const u32 *__restrict__ lineT, const u8 *__restrict__ keep, const float *__restrict__ seqId,
+    const i32 *__restrict__ qS_, const i32 *__restrict__ qE_, const i32 *__restrict__ dS_, const i32 *__restrict__ dE_,
+    CorrParams P, const DamageTables *__restrict__ tablesG, u8 *__restrict__ lineSel, u8 *__restrict__ out,
+    unsigned long long *__restrict__ changed, const u64 *__restrict__ likOff, double *__restrict__ likOut,
+    u32 *__restrict__ wideList, u32 *__restrict__ wideCount) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    CorrSmem &S = *reinterpret_cast<CorrSmem *>(smemRaw);
+    for (int i = threadIdx.x; i < (int) (sizeof(DamageTables) / sizeof(double)); i += blockDim.x) ((double *) &S.T)[i] = ((const double *) tablesG)[i];
+    for (int i = threadIdx.x; i < CF_WARPS * 44 * 32; i += blockDim.x) (&S.cnt[0][0][0])[i] = 0;
+    __syncthreads();
+    const DamageTables &T = S.T;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 (*cnt)[32] = S.cnt[warp];
+    LineCache &LC = S.lc[warp];
+    const u64 gwarp = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64) gridDim.x * blockDim.x) >> 5;
+    u32 nChanged = 0;
+    for (u64 qi = gwarp; qi < n; qi += nwarps) {
+        const u64 l0 = lineOff[qi], l1 = lineOff[qi + 1];
+        if (l1 - l0 <= 1) continue;   // at most the self alignment: coverage <= 1 everywhere
+        const SeqMeta qm = meta[qi];
+        const u32 qLen = qm.lenFlags & META_LEN;
+        const u8 *q = data + qm.off;
+        const u64 *qw = words + qm.wordOff;
+        const bool qExc = (qm.lenFlags & META_EXC) != 0;
+        const bool qExt = (qm.lenFlags & META_EXT) != 0;
+        // pass 1 (correction.cpp:220-245)
+        unsigned long long sum = 0;
+        for (u64 l = l0 + lane; l < l1; l += 32)
+            if (keep[l]) sum += (unsigned long long) (max(abs(qE_[l] - qS_[l]), abs(dE_[l] - dS_[l])) + 1);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+        float avCov;
+        if (sum < (1ull << 24)) avCov = (float) sum;   // every partial sum of the reference's float accumulation is exact
+        else {
+            avCov = 0.f;
+            for (u64 l = l0; l < l1; l++) if (keep[l]) avCov += (float) (max(abs(qE_[l] - qS_[l]), abs(dE_[l] - dS_[l])) + 1);
+        }
+        avCov = avCov / (float) qLen;
+        // pass 2 (:273-323, :353-359), one line per lane
+        u32 nSel = 0;
+        for (u64 lb = l0; lb < l1; lb += 32) {
+            const u64 l = lb + lane;
+            u8 sel = 0;
+            u64 tOff = 0; u32 dL = 0; i32 qs = 0, aln = 0, ds = 0;
+            if (l < l1 && keep[l]) {
+                const SeqMeta tm = meta[lineT[l]];
+                if (!(tm.lenFlags & META_EXT)) {
+                    dL = tm.lenFlags & META_LEN; tOff = tm.off;
+                    i32 qe = qE_[l], de = dE_[l];
+                    qs = qS_[l]; ds = dS_[l];
+                    aln = max(abs(qe - qs), abs(de - ds)) + 1;
+                    bool rev = false;
+                    if (qs > qe) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; rev = true; }
+                    u32 dist = 0;
+                    if (!qExc && !(tm.lenFlags & META_EXC)) dist = ry_dist_packed(qw, (u32) qs, words + tm.wordOff, dL, rev, (u32) ds, (u32) aln);
+                    else {
+                        const u8 *ts = data + tOff;
+                        for (i32 p = 0; p < aln; p++) dist += (ry_map(q[qs + p]) != ry_map(t_char(ts, dL, rev, (u32) (ds + p)))) ? 1u : 0u;
+                    }
+                    const float ry = (float) ((u32) aln - dist) / (float) aln;   // getRYSeqId (nuclassembleUtil.cpp:78-92)
+                    float thr = P.ryThr;
+                    if (aln <= 100) { thr = ((float) aln - 1) / (float) aln; thr = floorf(thr * 1000) / 1000; }
+                    const bool pick = (ry >= thr && ds == 0 && (u32) qe == qLen - 1) || (ry >= thr && qs == 0 && de == (i32) dL - 1) ||
+                                      (ry >= thr && avCov < 50);
+                    const float sid = P.roundSeqId ? seqid_text_roundtrip(seqId[l]) : seqId[l];
+                    if (pick && ry >= thr && sid >= P.seqIdThr && aln >= 30) sel = rev ? 2 : 1;
+                }
+            }
+            if (l < l1) lineSel[l] = sel;
+            const u32 b = __ballot_sync(0xffffffffu, sel != 0);
+            if (sel) {
+                const u32 slot = nSel + __popc(b & ((1u << lane) - 1));
+                if (slot < CF_CACHE) { LC.tOff[slot] = tOff; LC.dL[slot] = dL; LC.qs[slot] = qs; LC.aln[slot] = aln; LC.ds[slot] = ds; LC.rev[slot] = sel == 2; }
+            }
+            nSel += __popc(b);
+        }
+        if (nSel <= 1) continue;
+        if (nSel > P.wideThreshold) {   // 16-bit counters could overflow (> 65535): hand over to the generic kernel
+            if (lane == 0) { u32 s = atomicAdd(wideCount, 1u); wideList[s] = (u32) qi; }
+            continue;
+        }
+        __syncwarp();
+        u8 *o = out + qm.off;
+        for (u32 c0 = 0; c0 < qLen; c0 += 32) {
+            const u32 col = c0 + lane;
+            unsigned long long mask = 0;
+            u32 cov0 = 0, cov1 = 0, cov2 = 0, cov3 = 0;
+            if (nSel <= CF_CACHE) {
+#pragma unroll 4
+                for (u32 i = 0; i < nSel; i++) {
+                    const i32 qs = LC.qs[i], aln = LC.aln[i];
+                    if (col < qLen && (i32) col >= qs && (i32) col < qs + aln)
+                        count_column(data, LC.tOff[i], LC.dL[i], LC.rev[i] != 0, (u32) LC.ds[i] + (col - (u32) qs), cnt, lane, mask, cov0, cov1, cov2, cov3);
+                }
+            } else {
+                for (u64 l = l0; l < l1; l++) {
+                    const u8 sel = lineSel[l];
+                    if (!sel) continue;
+                    const SeqMeta tm = meta[lineT[l]];
+                    const u32 dL = tm.lenFlags & META_LEN;
+                    i32 qs = qS_[l], qe = qE_[l], ds = dS_[l], de = dE_[l];
+                    const bool rev = sel == 2;
+                    if (rev) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; }
+                    const i32 aln = max(abs(qe - qs), abs(de - ds)) + 1;
+                    if (col < qLen && (i32) col >= qs && (i32) col < qs + aln)
+                        count_column(data, tm.off, dL, rev, (u32) ds + (col - (u32) qs), cnt, lane, mask, cov0, cov1, cov2, cov3);
+                }
+            }
+            const u32 tot = cov0 + cov1 + cov2 + cov3;
+            if (col < qLen && tot > 1) {
+                const unsigned char orig = q[col];
+                const int b = nuc_map(orig);
+                int nb = b;
+                bool evaluate = true;
+                if (!qExt) {   // mostLikeliBaseRead :56-60
+                    const u32 sumc = cov1 + cov3 + cov0 + cov2;
+                    const double ctRatio = (double) cov3 / (double) sumc, gaRatio = (double) cov0 / (double) sumc;
+                    if (ctRatio >= 0.4 || gaRatio >= 0.4) evaluate = false;
+                }
+                if (evaluate) {
+                    int cq = 5;
+                    if (col < 5) cq = (int) col;
+                    else if (col >= qLen - 5) cq = 11 - (int) (qLen - col);
+                    double logQ[4], acc[4];
+#pragma unroll
+                    for (int x = 0; x < 4; x++) { logQ[x] = qExt ? T.logSE[x][b] : T.logD[cq][x][b]; acc[x] = 0.0; }
+                    unsigned long long m = mask;
+                    while (m) {   // ascending idx = t*11+l: the reference's loop order (:80-117)
+                        const int idx = __ffsll((long long) m) - 1;
+                        m &= m - 1;
+                        const int t = idx / 11, l = idx - 11 * t;
+                        const u32 v = cnt[idx][lane];
+                        const u32 nr = v >> 16, fw = (v & 0xFFFFu) - nr;
+                        const double lt = T.logSE[t][b];
+#pragma unroll
+                        for (int x = 0; x < 4; x++) {
+                            const double base = __dadd_rn(lt, logQ[x]);
+                            if (fw) acc[x] = __dadd_rn(acc[x], __dmul_rn((double) fw, __dadd_rn(base, T.logD[l][x][t])));
+                            if (nr) acc[x] = __dadd_rn(acc[x], __dmul_rn((double) nr, __dadd_rn(base, T.logDrev[l][x][t])));
+                        }
+                    }
+                    nb = 0;
+#pragma unroll
+                    for (int x = 1; x < 4; x++) if (acc[x] > acc[nb]) nb = x;   // first maximum (std::max_element)
+                    if (likOut) { double *lo = likOut + (likOff[qi] + col) * 4; lo[0] = acc[0]; lo[1] = acc[1]; lo[2] = acc[2]; lo[3] = acc[3]; }
+                }
+                const unsigned char res = (unsigned char) "ACGT"[nb];
+                if (res != orig) { o[col] = res; nChanged++; }
+            }
+            while (mask) { const int idx = __ffsll((long long) mask) - 1; mask &= mask - 1; cnt[idx][lane] = 0; }
+        }
+        __syncwarp();   // the line cache is rewritten by the next query
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) nChanged += __shfl_xor_sync(0xffffffffu, nChanged, s);

@@ -55,9 +55,10 @@ struct cdg_ctx {
     cudaEvent_t ev[EV_N];
     bool evValid[EV_N];
     u64 launches = 0;
+    u32 wideThreshold = 65535;   // test knob CDG_WIDE_THRESHOLD: route queries with more counted targets to the generic kernel
     // resident sequence set
     u64 n = 0, dataBytes = 0, totalBases = 0, totalWords = 0; u32 maxLen = 0;
-    DevBuf dData, dOff, dLen, dExt, dWordOff, dWords, dXmask, dFlags, dLikOff;
+    DevBuf dData, dOff, dLen, dExt, dWordOff, dWords, dXmask, dFlags, dLikOff, dMeta;
     // scan / sort scratch
     DevBuf dTileSums, dScalars, dHist, dTileState;
     // kmermatcher
@@ -72,7 +73,7 @@ struct cdg_ctx {
     HostBuf hLineOff, hLineT, hKeep, hScore, hBits, hEvalue, hSeqId, hQS, hQE, hDS, hDE;
     u64 nLines = 0, nKept = 0; bool linesValid = false, alnsValid = false, alnsFromText = false;
     // correction
-    DevBuf dTables, dOut, dLik; bool damageSet = false;
+    DevBuf dTables, dOut, dLik, dWideList; bool damageSet = false;
 };
 
 namespace {
@@ -92,7 +93,7 @@ int fail(cdg_ctx *c, int code, const char *fmt, ...) {
 
 // scalars block on the device: [0] scan total, [1] emitted records, [2] grouped count, [3] kept lines,
 // [4] changed bases, [5] (u32) extraCount, [6] (u32) overflow, [7] (u32) long count, [8] long scratch total, [9] (u32) sort ticket
-enum { SC_SCAN = 0, SC_EMIT, SC_GROUPED, SC_KEPT, SC_CHANGED, SC_EXTRA, SC_OVERFLOW, SC_NLONG, SC_LONGSCR, SC_TICKET, SC_N = 16 };
+enum { SC_SCAN = 0, SC_EMIT, SC_GROUPED, SC_KEPT, SC_CHANGED, SC_EXTRA, SC_OVERFLOW, SC_NLONG, SC_LONGSCR, SC_TICKET, SC_WIDE, SC_N = 16 };
 
 void rec(cdg_ctx *ctx, int e) { cudaEventRecord(ctx->ev[e], ctx->st); ctx->evValid[e] = true; }
 
@@ -179,7 +180,9 @@ extern "C" int cdg_create(int device, cdg_ctx **out) {
     for (int i = 0; i < EV_N; i++) { cudaEventCreate(&ctx->ev[i]); ctx->evValid[i] = false; }
     if (ctx->dScalars.reserve(SC_N * 8) != cudaSuccess) { delete ctx; return CDG_ERR_CUDA; }
     cudaFuncSetAttribute(cdgkmer::extract_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cdgkmer::EX_WARPS * 2048 * 4);
+    cudaFuncSetAttribute(cdgalign::correct_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(cdgalign::CorrSmem));
     cudaFuncSetAttribute(cdgkmer::extract_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (32768 + 128) * 4);
+    if (const char *e = getenv("CDG_WIDE_THRESHOLD")) { long v = atol(e); if (v >= 1 && v < 65535) ctx->wideThreshold = (u32) v; }
     *out = ctx;
     return CDG_OK;
 }
@@ -188,13 +191,13 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
-    DevBuf *d[] = {&ctx->dData, &ctx->dOff, &ctx->dLen, &ctx->dExt, &ctx->dWordOff, &ctx->dWords, &ctx->dXmask, &ctx->dFlags, &ctx->dLikOff,
+    DevBuf *d[] = {&ctx->dMeta, &ctx->dData, &ctx->dOff, &ctx->dLen, &ctx->dExt, &ctx->dWordOff, &ctx->dWords, &ctx->dXmask, &ctx->dFlags, &ctx->dLikOff,
                    &ctx->dTileSums, &ctx->dScalars, &ctx->dHist, &ctx->dTileState, &ctx->dSlotOff, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA,
                    &ctx->dValsB, &ctx->dIdKeysA, &ctx->dIdKeysB, &ctx->dIdValsA, &ctx->dIdValsB, &ctx->dKey2A, &ctx->dKey2B, &ctx->dLongList,
                    &ctx->dScratchOff, &ctx->dScratch, &ctx->dScratchKeep, &ctx->dShortScratch, &ctx->dShortKeep, &ctx->dHitRep, &ctx->dHitTgt,
                    &ctx->dHitScore, &ctx->dHitDiag, &ctx->dLineOff, &ctx->dLineQ, &ctx->dLineT, &ctx->dLinePref, &ctx->dLineDiag, &ctx->dKeep,
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
-                   &ctx->dTables, &ctx->dOut, &ctx->dLik};
+                   &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList};
     for (DevBuf *b : d) b->release();
     HostBuf *h[] = {&ctx->hHitRep, &ctx->hHitTgt, &ctx->hHitScore, &ctx->hHitDiag, &ctx->hHitDiag16, &ctx->hLineOff, &ctx->hLineT, &ctx->hKeep,
                     &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE};
@@ -239,7 +242,11 @@ extern "C" int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_
     cdgkmer::pack_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->st>>>(ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(),
                                                                                     ctx->dWordOff.as<u64>(), n, ctx->dWords.as<u64>(),
                                                                                     ctx->dXmask.as<u32>(), ctx->dFlags.as<u8>());
-    ctx->launches++;
+    if (words >= (1ull << 32)) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_upload_seqs: more than 2^32 packed words per context");
+    CK(ctx->dMeta.reserve(n * sizeof(cdgalign::SeqMeta)));
+    cdgalign::meta_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dOff.as<u64>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(),
+                                                                           ctx->dFlags.as<u8>(), ctx->dExt.as<u8>(), n, ctx->dMeta.as<cdgalign::SeqMeta>());
+    ctx->launches += 2;
     CKL();
     CK(cudaStreamSynchronize(ctx->st));
     return CDG_OK;
@@ -580,9 +587,19 @@ static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data
         CK(cudaMemsetAsync(ctx->dLik.p, 0xFF, ctx->totalBases * 4 * 8, ctx->st));   // all-ones = NaN
         dLik = ctx->dLik.as<double>();
     }
-    cdgalign::CorrParams C; C.seqIdThr = p->min_seqid_corr_reads; C.ryThr = p->min_ryseq_id_corr_reads; C.roundSeqId = ctx->alnsFromText ? 0 : 1;
-    const int blocks = ctx->smCount * 8;
-    cdgalign::correct_kernel<<<blocks, cdgalign::CORR_WARPS * 32, 0, ctx->st>>>(
+    cdgalign::CorrParams C; C.seqIdThr = p->min_seqid_corr_reads; C.ryThr = p->min_ryseq_id_corr_reads; C.roundSeqId = ctx->alnsFromText ? 0 : 1; C.wideThreshold = ctx->wideThreshold;
+    const u64 wideCap = ctx->wideThreshold < 65535 ? n + 16 : (ctx->nLines >> 16) + 16;
+    CK(ctx->dWideList.reserve(wideCap * 4));
+    CK(cudaMemsetAsync(sc + SC_WIDE, 0, 8, ctx->st));
+    const int blocks = ctx->smCount * 4;
+    cdgalign::correct_fast_kernel<<<blocks, cdgalign::CF_WARPS * 32, sizeof(cdgalign::CorrSmem), ctx->st>>>(
+        ctx->dData.as<u8>(), ctx->dMeta.as<cdgalign::SeqMeta>(), ctx->dWords.as<u64>(), n, ctx->dLineOff.as<u64>(), ctx->dLineT.as<u32>(), ctx->dKeep.as<u8>(), ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(),
+        ctx->dQE.as<i32>(), ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), C, ctx->dTables.as<cdgalign::DamageTables>(), ctx->dLineSel.as<u8>(),
+        ctx->dOut.as<u8>(), sc + SC_CHANGED, ctx->dLikOff.as<u64>(), dLik, ctx->dWideList.as<u32>(), (u32 *) (sc + SC_WIDE));
+    ctx->launches++;
+    // queries with more than 65535 counted targets (16-bit counters): generic kernel, usually an empty list
+    cdgalign::correct_wide_kernel<<<ctx->smCount, cdgalign::CORR_WARPS * 32, 0, ctx->st>>>(
+        ctx->dWideList.as<u32>(), (const u32 *) (sc + SC_WIDE),
         ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dExt.as<u8>(), n, ctx->dLineOff.as<u64>(), ctx->dLineT.as<u32>(),
         ctx->dKeep.as<u8>(), ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(), ctx->dQE.as<i32>(), ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), C,
         ctx->dTables.as<cdgalign::DamageTables>(), ctx->dLineSel.as<u8>(), ctx->dOut.as<u8>(), sc + SC_CHANGED, ctx->dLikOff.as<u64>(), dLik);

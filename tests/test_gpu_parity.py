@@ -210,3 +210,26 @@ def test_full_size_properties(ctx):
     assert set(np.unique(out[diff]).tolist()) <= set(b"ACGT")
     hits2, alns2, out2, changed2 = ctx.iteration(fetch_hits=True)
     assert np.array_equal(out, out2) and np.array_equal(hits["score"], hits2["score"])   # deterministic
+
+
+def test_correction_generic_kernel_path(oracle, monkeypatch):
+    """queries with > 65535 counted targets go through the generic 32-bit-counter kernel; force that path with the
+    test knob and require identical corrected reads."""
+    import carpedeam_b200 as cd
+    monkeypatch.setenv("CDG_WIDE_THRESHOLD", "3")
+    c = cd.Context(0)
+    try:
+        s = SeqSet.from_golden("nucl_reads")
+        akeys, apay, _ = load_golden("aln_0")
+        off, t, sid, qs, qe, ds, de = parse_aln(s, apay)
+        c.upload(s.blob, s.off, s.len, s.ext)
+        c.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+        c.set_alignments(off, t, sid, qs, qe, ds, de)
+        out, changed = c.correct()
+        ckeys, cpay, _ = load_golden("correction_0")
+        for i, p in enumerate(cpay):
+            o = int(s.off[i]); L = int(s.len[i])
+            assert out[o:o + L].tobytes() + b"\n" == p
+        assert changed == 3348
+    finally:
+        c.close()
