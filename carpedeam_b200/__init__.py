@@ -18,6 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcarpedeam_gpu.so")
 HOST_LIB_PATH = os.path.join(HERE, "libcarpedeam_host.so")
+STAGE_BIN = os.path.join(HERE, "bin", "carpedeam_gpu")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
 
@@ -35,6 +36,12 @@ def build(force=False, verbose=False):
         hdeps = [os.path.join(hsrc_dir, f) for f in os.listdir(hsrc_dir)]
         if hsrc and (force or not os.path.exists(HOST_LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(HOST_LIB_PATH) for d in hdeps)):
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-o", HOST_LIB_PATH] + hsrc, check=True)
+        # the drop-in stage binary (same sub-commands and DB arguments as the reference's modules)
+        msrc = os.path.join(hsrc_dir, "main_stages.cpp")
+        if os.path.exists(msrc) and (force or not os.path.exists(STAGE_BIN) or any(os.path.getmtime(d) > os.path.getmtime(STAGE_BIN) for d in hdeps + [LIB_PATH])):
+            os.makedirs(os.path.dirname(STAGE_BIN), exist_ok=True)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", STAGE_BIN, msrc] + hsrc +
+                           ["-L" + HERE, "-lcarpedeam_gpu", "-Wl,-rpath," + HERE], check=True)
     return LIB_PATH
 
 

@@ -179,7 +179,9 @@ extern "C" int cdg_create(int device, cdg_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CDG_ERR_CUDA; }
     for (int i = 0; i < EV_N; i++) { cudaEventCreate(&ctx->ev[i]); ctx->evValid[i] = false; }
     if (ctx->dScalars.reserve(SC_N * 8) != cudaSuccess) { delete ctx; return CDG_ERR_CUDA; }
-    cudaFuncSetAttribute(cdgkmer::extract_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cdgkmer::EX_WARPS * 2048 * 4);
+    cudaFuncSetAttribute(cdgkmer::extract_short_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cdgkmer::EX_WARPS * 2048 * 4);
+    cudaFuncSetAttribute(cdgkmer::extract_short_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cdgkmer::EX_WARPS * 2048 * 4);
+    cudaFuncSetAttribute(cdgkmer::extract_short_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cdgkmer::EX_WARPS * 2048 * 4);
     cudaFuncSetAttribute(cdgalign::correct_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(cdgalign::CorrSmem));
     cudaFuncSetAttribute(cdgkmer::extract_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (32768 + 128) * 4);
     if (const char *e = getenv("CDG_WIDE_THRESHOLD")) { long v = atol(e); if (v >= 1 && v < 65535) ctx->wideThreshold = (u32) v; }
@@ -238,8 +240,7 @@ extern "C" int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_
     ctx->totalWords = words;
     if ((rc = scan_to(ctx, LenBasesF{ctx->dLen.as<u32>()}, n, ctx->dLikOff.as<u64>(), true))) return rc;
     CK(ctx->dWords.reserve((words + 2) * 8)); CK(ctx->dXmask.reserve((words + 2) * 4));
-    u64 threads = n * 32;
-    cdgkmer::pack_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->st>>>(ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(),
+    cdgkmer::pack_kernel<<<ctx->smCount * 16, 256, 0, ctx->st>>>(ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(),
                                                                                     ctx->dWordOff.as<u64>(), n, ctx->dWords.as<u64>(),
                                                                                     ctx->dXmask.as<u32>(), ctx->dFlags.as<u8>());
     if (words >= (1ull << 32)) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_upload_seqs: more than 2^32 packed words per context");
@@ -295,10 +296,14 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     const u64 gridWarps = (u64) shortBlocks * EX_WARPS;
     CK(ctx->dShortScratch.reserve(gridWarps * 2 * EX_MAXW * sizeof(WinRec)));
     CK(ctx->dShortKeep.reserve(gridWarps * EX_MAXW));
-    extract_short_kernel<<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>>(
-        ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), n, E, ctx->dSlotOff.as<u64>(),
-        ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), slots, extraCap, (u32 *) (sc + SC_EXTRA),
-        (u32 *) (sc + SC_OVERFLOW), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT);
+    {
+        const u32 maxW = ctx->maxLen >= (u32) p->k ? ctx->maxLen - p->k + 1 : 0;   // short sequences have <= 256 windows
+#define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), n, E, ctx->dSlotOff.as<u64>(), ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), slots, extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT)
+        if (maxW <= 64) extract_short_kernel<2><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
+        else if (maxW <= 128) extract_short_kernel<4><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
+        else extract_short_kernel<8><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
+#undef CDG_EXTRACT_ARGS
+    }
     ctx->launches++;
     CKL();
     if (nLong) {

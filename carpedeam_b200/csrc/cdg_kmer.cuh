@@ -15,38 +15,41 @@ namespace cdgkmer {
 // base j of a word in bits [62-2j, 63-2j], i.e. first base most significant, like the k-mer index of
 // Indexer::computeKmerIdx, Indexer.h:136-143) and the same range of `xmask` (u32, bit 31-j set when base
 // j maps to X).  flags[i] bit0: some byte is not one of upper-case A,C,G,T ("exception" sequence).
+// One warp per sequence; per 32-base word the lanes read 32 consecutive bytes (one coalesced load) and the word is
+// assembled from warp ballots of the two code bits.
+CDG_D u64 interleave32(u32 hi, u32 lo) {   // bit j of hi -> bit 2j+1, bit j of lo -> bit 2j
+    u64 a = hi, b = lo;
+    a = (a | (a << 16)) & 0x0000FFFF0000FFFFull; b = (b | (b << 16)) & 0x0000FFFF0000FFFFull;
+    a = (a | (a << 8)) & 0x00FF00FF00FF00FFull;  b = (b | (b << 8)) & 0x00FF00FF00FF00FFull;
+    a = (a | (a << 4)) & 0x0F0F0F0F0F0F0F0Full;  b = (b | (b << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    a = (a | (a << 2)) & 0x3333333333333333ull;  b = (b | (b << 2)) & 0x3333333333333333ull;
+    a = (a | (a << 1)) & 0x5555555555555555ull;  b = (b | (b << 1)) & 0x5555555555555555ull;
+    return (a << 1) | b;
+}
 __global__ void __launch_bounds__(256) pack_kernel(const u8 *__restrict__ data, const u64 *__restrict__ off, const u32 *__restrict__ len,
                                                    const u64 *__restrict__ wordOff, u64 n, u64 *__restrict__ words,
                                                    u32 *__restrict__ xmask, u8 *__restrict__ flags) {
-    // one warp per sequence, lane per word (strided)
-    u64 seq = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (seq >= n) return;
-    const u8 *s = data + off[seq];
-    u32 L = len[seq];
-    u64 w0 = wordOff[seq];
-    u32 nw = (L + 31) >> 5;
-    u32 exc = 0;
-    for (u32 w = lane; w < nw; w += 32) {
-        u64 bits = 0; u32 xm = 0;
-        u32 base = w << 5;
-#pragma unroll 8
-        for (u32 j = 0; j < 32; j++) {
-            u32 p = base + j;
-            int c = 0;
-            if (p < L) {
-                unsigned char ch = s[p];
-                c = cdg_map_letter(ch);
-                if (cdg_plain_code(ch) == 4) exc = 1;
-            }
-            bits = (bits << 2) | (u64) (c & 3);
-            xm = (xm << 1) | (c == 4 ? 1u : 0u);
+    const int lane = threadIdx.x & 31;
+    const u64 gwarp = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64) gridDim.x * blockDim.x) >> 5;
+    for (u64 seq = gwarp; seq < n; seq += nwarps) {
+        const u8 *s = data + off[seq];
+        const u32 L = len[seq];
+        const u64 w0 = wordOff[seq];
+        const u32 nw = (L + 31) >> 5;
+        u32 exc = 0;
+        for (u32 w = 0; w < nw; w++) {
+            const u32 p = (w << 5) + lane;
+            int c = 0; u32 e = 0;
+            if (p < L) { const unsigned char ch = s[p]; c = cdg_map_letter(ch); e = cdg_plain_code(ch) == 4; }
+            // lane j holds base j of the word; base 0 must land in the most significant bits: reverse the ballots
+            const u32 b1 = __brev(__ballot_sync(0xffffffffu, (c & 2) != 0));
+            const u32 b0 = __brev(__ballot_sync(0xffffffffu, (c & 1) != 0));
+            const u32 xm = __brev(__ballot_sync(0xffffffffu, c == 4));
+            exc |= __ballot_sync(0xffffffffu, e);
+            if (lane == 0) { words[w0 + w] = interleave32(b1, b0); xmask[w0 + w] = xm; }   // X is stored as code 0 (4 & 3)
         }
-        words[w0 + w] = bits;
-        xmask[w0 + w] = xm;
+        if (lane == 0) flags[seq] = (u8) (exc ? 1 : 0);
     }
-    exc = __any_sync(0xffffffffu, exc);
-    if (lane == 0) flags[seq] = (u8) (exc ? 1 : 0);
 }
 
 // 2k-bit window starting at base p of a packed sequence (caller guarantees p + k <= L)
@@ -170,6 +173,7 @@ static constexpr int EX_MAXW = 256;   // windows per short sequence
 // Fast path (no repeated k-mer inside the sequence): every valid window is emitted.  A per-warp bitmap over
 // the 16-bit hash detects possible repeats (equal k-mers have equal hashes); on a hit the warp ranks its
 // windows in shared... global scratch and lane 0 replays the reference's sequential loop.
+template <int ITERS>
 __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
     const u64 *__restrict__ words, const u32 *__restrict__ xmask, const u64 *__restrict__ wordOff, const u32 *__restrict__ len,
     u64 n, ExtractParams P, const u64 *__restrict__ slotOff /*[n] first main slot of seq*/,
@@ -194,17 +198,25 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
         const u32 W = L >= (u32) P.k ? L - P.k + 1 : 0;
         // identity hash
         u64 part = 0;
-        for (u32 p = lane; p < L; p += 32) part += (u64) base_code(w, xm, p) * pow31(L - 1 - p);
+        {   // lane handles a contiguous chunk of bases (Horner), then weights it by 31^(bases after the chunk)
+            const u32 c = (L + 31) >> 5;
+            const u32 b0 = lane * c, b1 = min(b0 + c, L);
+            if (b0 < L) {
+                u64 h = 0;
+                for (u32 p = b0; p < b1; p++) h = h * 31 + (u64) base_code(w, xm, p);
+                part = h * pow31(L - b1);
+            }
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) emit_identity(cdg_xxh64_u64(part, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow);
 
         // windows: lane handles p = lane + 32*it
-        WinRec rec[EX_MAXW / 32];
+        WinRec rec[ITERS];
         u32 validMask = 0;   // bit it
         u32 collide = 0;
 #pragma unroll
-        for (int it = 0; it < EX_MAXW / 32; it++) {
+        for (int it = 0; it < ITERS; it++) {
             u32 p = lane + 32 * it;
             bool ok = false;
             if (p < W) ok = make_window(w, xm, p, L, P, rec[it]);
@@ -218,7 +230,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
         __syncwarp();
         // clear the bits again (cheaper than wiping 8 KB per sequence)
 #pragma unroll
-        for (int it = 0; it < EX_MAXW / 32; it++) if (validMask & (1u << it)) bitmap[rec[it].score >> 5] = 0;
+        for (int it = 0; it < ITERS; it++) if (validMask & (1u << it)) bitmap[rec[it].score >> 5] = 0;
         __syncwarp();
         collide = __any_sync(0xffffffffu, collide);
 
@@ -227,7 +239,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
         u32 written = 0;   // warp-uniform
         if (!collide) {
 #pragma unroll
-            for (int it = 0; it < EX_MAXW / 32; it++) {
+            for (int it = 0; it < ITERS; it++) {
                 bool ok = (validMask >> it) & 1u;
                 bool own = ok && rec[it].score >= P.hashLo && rec[it].score <= P.hashHi;
                 u32 b = __ballot_sync(0xffffffffu, own);
@@ -242,7 +254,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
             // exact path: materialise, rank (O(cnt^2/32)), sequential replay by lane 0
             u32 cnt = 0;
 #pragma unroll
-            for (int it = 0; it < EX_MAXW / 32; it++) {
+            for (int it = 0; it < ITERS; it++) {
                 bool ok = (validMask >> it) & 1u;
                 u32 b = __ballot_sync(0xffffffffu, ok);
                 if (ok) myScratch[cnt + __popc(b & ((1u << lane) - 1))] = rec[it];

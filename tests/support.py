@@ -266,3 +266,28 @@ def synth_reads(n, genome_len, seed, lmin=35, lmax=70, interior=0.01, sub_err=0.
             r[m] = ord("N")
         seqs.append(r.tobytes())
     return seqs
+
+
+# ------------------------------------------------------------------------------------------------
+# MMseqs2 DB files on disk (for the drop-in stage binary tests)
+def write_db(path, keys, payloads, exts, dbtype):
+    """payloads without the trailing NUL; writes <path>, <path>.index (4 columns), <path>.dbtype"""
+    import struct
+    with open(path, "wb") as f, open(path + ".index", "w") as ix:
+        off = 0
+        for k, p, e in zip(keys, payloads, exts):
+            f.write(p + b"\0")
+            ix.write("%d\t%d\t%d\t%d\n" % (k, off, len(p) + 1, e))
+            off += len(p) + 1
+    open(path + ".dbtype", "wb").write(struct.pack("<i", dbtype))
+
+
+def read_db(path):
+    import glob
+    files = sorted(glob.glob(path + ".[0-9]*"), key=lambda s: int(s.rsplit(".", 1)[1])) or [path]
+    data = b"".join(open(f, "rb").read() for f in files)
+    out = {}
+    for line in open(path + ".index"):
+        f = line.split()
+        out[int(f[0])] = (data[int(f[1]):int(f[1]) + int(f[2]) - 1], int(f[3]) if len(f) > 3 else 0)
+    return out
