@@ -115,6 +115,7 @@ def lib():
         L.cdg_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.cdg_test_radix_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
         L.cdg_test_hash_revcomp.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.cdg_test_set_sort_variant.argtypes = [C.c_int, C.c_int]
         _lib = L
     return _lib
 

@@ -356,7 +356,7 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     ctx->nGrouped = R2;
     // sort 2
     u64 *k2 = ctx->dKey2A.as<u64>(), *dummy = nullptr;
-    cdgsort::Plan plan2 = cdgsort::make_plan(0, 0, 0, 2 * idBits + diagBits + 1);
+    cdgsort::Plan plan2 = cdgsort::make_plan(0, 0, 1, 2 * idBits + diagBits + 1);   // bit 0 (needRev) is not an ordering key
     if (R2 > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "grouped records exceed one sort");
     if ((rc = sort_ws(ctx, std::max(R2, std::max(Rtot, n)), ws))) return rc;
     int l3 = cdgsort::radix_sort(ctx->st, ws, ctx->dKey2A.as<u64>(), ctx->dKey2B.as<u64>(), nullptr, nullptr, R2, plan2, &k2, &dummy, ctx->smCount);
@@ -704,4 +704,49 @@ extern "C" int cdg_test_hash_revcomp(cdg_ctx *ctx, const uint64_t *in, uint64_t 
     CK(cudaStreamSynchronize(ctx->st));
     a.release(); b.release(); c.release();
     return CDG_OK;
+}
+
+__global__ void fill_random_kernel(u64 *k, u64 *v, u64 n, u64 seed) {
+    u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { k[i] = cdg_xxh64_u64(i, seed); if (v) v[i] = i; }
+}
+// sort micro-benchmark on device-generated random keys: average milliseconds per full sort (histogram + all passes)
+extern "C" int cdg_test_sort_bench(cdg_ctx *ctx, uint64_t n, int bit_lo, int bit_hi, int has_val, int variant, int reps, float *ms_per_sort,
+                                   int *passes) {
+    if (!ctx || !ms_per_sort) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf ka, kb, va, vb;
+    CK(ka.reserve(n * 8 + 8)); CK(kb.reserve(n * 8 + 8));
+    if (has_val) { CK(va.reserve(n * 8 + 8)); CK(vb.reserve(n * 8 + 8)); }
+    cdgsort::Workspace ws;
+    int rc = sort_ws(ctx, n, ws);
+    if (rc) return rc;
+    cdgsort::Plan plan = cdgsort::make_plan(0, 0, bit_lo, bit_hi);
+    if (passes) *passes = plan.n;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float total = 0.f;
+    for (int r = 0; r < reps + 1; r++) {
+        fill_random_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ka.as<u64>(), has_val ? va.as<u64>() : nullptr, n, 1234 + r);
+        cudaEventRecord(e0, ctx->st);
+        u64 *ok, *ov;
+        int l = cdgsort::radix_sort(ctx->st, ws, ka.as<u64>(), kb.as<u64>(), has_val ? va.as<u64>() : nullptr, has_val ? vb.as<u64>() : nullptr, n, plan,
+                                    &ok, &ov, ctx->smCount, variant);
+        if (l < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_test_sort_bench: sort refused");
+        cudaEventRecord(e1, ctx->st);
+        CK(cudaStreamSynchronize(ctx->st));
+        CKL();
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0) total += ms;   // first repetition is warm-up
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_per_sort = total / reps;
+    ka.release(); kb.release(); va.release(); vb.release();
+    return CDG_OK;
+}
+extern "C" int cdg_test_set_sort_variant(int keys_only_variant, int pairs_variant) {
+    if (keys_only_variant >= 0) cdgsort::default_variant(false) = keys_only_variant;
+    if (pairs_variant >= 0) cdgsort::default_variant(true) = pairs_variant;
+    return 0;
 }

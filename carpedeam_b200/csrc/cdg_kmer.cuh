@@ -534,15 +534,21 @@ __global__ void __launch_bounds__(cdgscan::BLOCK) reduce_kernel(PairHeadFlag f, 
         u64 k = f.keys[i];
         u32 tgt = (u32) ((k >> (R.diagBits + 1)) & idMask), rep = (u32) (k >> (R.diagBits + 1 + R.idBits));
         i32 prev = (i32) ((k >> 1) & diagMask), best = prev;
-        u32 dc = 0, mx = 0, top = 0; bool brev = (k & 1ull) != 0;
+        u32 dc = 0, mx = 0, top = 0, prevRep = rep; bool brev = false, runNeed = false;
         u64 e = i;
         while (e < f.n) {
             u64 ke = f.keys[e];
             if ((u32) ((ke >> (R.diagBits + 1)) & idMask) != tgt) break;
             i32 d = (i32) ((ke >> 1) & diagMask);
-            dc = (prev == d) ? dc + 1 : 1;
-            if (dc >= mx) { best = d; mx = dc; brev = (ke & 1ull) != 0; }
-            prev = d; e++; top++;
+            // records with equal (rep,id,diag) are unordered in the reference (its comparator masks the strand bit);
+            // our order puts needRev last, so "the last record of the run" is the OR over the run
+            // (across a rep boundary inside a bleeding walk only the later rep's records can be "last")
+            const u32 repE = (u32) (ke >> (R.diagBits + 1 + R.idBits));
+            const bool sameRun = prev == d;
+            dc = sameRun ? dc + 1 : 1;
+            runNeed = (sameRun && repE == prevRep) ? (runNeed || (ke & 1ull)) : ((ke & 1ull) != 0);
+            if (dc >= mx) { best = d; mx = dc; brev = runNeed; }
+            prev = d; prevRep = repE; e++; top++;
         }
         u64 h = prefix[it];
         hitRep[h] = rep; hitTgt[h] = tgt;

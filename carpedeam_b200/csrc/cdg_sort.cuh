@@ -13,10 +13,7 @@ namespace cdgsort {
 
 static constexpr int RADIX_BITS = 8;
 static constexpr int RADIX = 1 << RADIX_BITS;
-static constexpr int BLOCK = 256;                 // == RADIX: thread d owns digit d in the scan phases
-static constexpr int WARPS = BLOCK / 32;
-static constexpr int ITEMS = 16;
-static constexpr int TILE = BLOCK * ITEMS;        // 4096 records per tile
+static constexpr int BLOCK = 256;                 // histogram kernel block
 static constexpr int MAX_PASSES = 16;
 static constexpr u32 FLAG_AGG = 1u << 30, FLAG_INC = 2u << 30, FLAG_MASK = 3u << 30, VAL_MASK = ~FLAG_MASK;
 static constexpr u64 MAX_N = (1ull << 30) - 1;    // 30-bit tile-state counters
@@ -25,6 +22,10 @@ struct Pass { int word; int shift; u32 mask; };   // word: 0 = key, 1 = val
 struct Plan { int n; Pass p[MAX_PASSES]; };
 
 CDG_D u32 digit_of(u64 w, int shift, u32 mask) { return (u32) (w >> shift) & mask; }
+// tile-state words are single 32-bit values (flag | count): relaxed device-scope accesses are enough and much cheaper
+// than the system-scope accesses `volatile` compiles to
+CDG_D u32 ld_state(const u32 *p) { u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+CDG_D void st_state(u32 *p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 
 // ---- kernel 1: histograms of every pass in one read of the digit words --------------------------
 __global__ void __launch_bounds__(BLOCK) hist_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, u64 n,
@@ -69,114 +70,332 @@ __global__ void __launch_bounds__(RADIX) binscan_kernel(unsigned long long *__re
 
 // ---- kernel 3: one digit pass ----------------------------------------------------------------------
 // Tile order = order of arrival (atomic ticket), so every tile a block waits for is already running.
-template <bool HAS_VAL>
-__global__ void __launch_bounds__(BLOCK) onesweep_kernel(const u64 *__restrict__ keysIn, u64 *__restrict__ keysOut,
-                                                         const u64 *__restrict__ valsIn, u64 *__restrict__ valsOut, u64 n,
-                                                         Pass pass, const unsigned long long *__restrict__ binBase,
-                                                         u32 *tileState /*[tiles][RADIX]*/, u32 *ticket) {
-    __shared__ u64 exch[TILE];
-    __shared__ u32 warpHist[WARPS][RADIX];
-    __shared__ u32 tileOff[RADIX];          // exclusive offset of digit d inside the sorted tile
-    __shared__ unsigned long long gBase[RADIX];   // global position of the tile's first record with digit d
-    __shared__ u8 digitAt[TILE];
-    __shared__ u32 sTile;
-    __shared__ u32 warpSum[WARPS];
+// Digits always come from the key word.  Shared memory: exchange buffer (tile of u64), per-warp digit
+// counters (turned into per-warp scatter bases), per-digit `delta` = global base - tile offset.
+template <int BLOCK_T, int ITEMS_T, bool HAS_VAL>
+struct SweepSmem {
+    static constexpr int TILE_T = BLOCK_T * ITEMS_T;
+    static constexpr int WARPS_T = BLOCK_T / 32;
+    u64 exch[TILE_T];
+    u32 warpHist[WARPS_T][RADIX];
+    unsigned long long delta[RADIX];
+    u32 warpSum[8];
+    u32 sTile;
+    u8 digitAt[HAS_VAL ? TILE_T : 4];
+};
+
+template <int BLOCK_T, int ITEMS_T, bool HAS_VAL>
+__global__ void __launch_bounds__(BLOCK_T) onesweep_kernel(const u64 *__restrict__ keysIn, u64 *__restrict__ keysOut,
+                                                           const u64 *__restrict__ valsIn, u64 *__restrict__ valsOut, u64 n,
+                                                           Pass pass, const unsigned long long *__restrict__ binBase,
+                                                           u32 *tileState /*[tiles][RADIX]*/, u32 *ticket) {
+    constexpr int TILE_T = BLOCK_T * ITEMS_T, WARPS_T = BLOCK_T / 32;
+    extern __shared__ __align__(16) unsigned char sweepRaw[];
+    SweepSmem<BLOCK_T, ITEMS_T, HAS_VAL> &S = *reinterpret_cast<SweepSmem<BLOCK_T, ITEMS_T, HAS_VAL> *>(sweepRaw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sTile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < WARPS * RADIX; i += BLOCK) (&warpHist[0][0])[i] = 0;
+    if (tid == 0) S.sTile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < WARPS_T * RADIX; i += BLOCK_T) (&S.warpHist[0][0])[i] = 0;
     __syncthreads();
-    const u32 tile = sTile;
-    const u64 tileBase = (u64) tile * TILE;
-    const u32 tileValid = (u32) (n - tileBase < (u64) TILE ? n - tileBase : (u64) TILE);
+    const u32 tile = S.sTile;
+    const u64 tileBase = (u64) tile * TILE_T;
+    const u32 tileValid = (u32) (n - tileBase < (u64) TILE_T ? n - tileBase : (u64) TILE_T);
 
     // load (warp-striped: warp w owns records [w*ITEMS*32, (w+1)*ITEMS*32) of the tile, item-major)
-    u64 key[ITEMS];
-    u32 dig[ITEMS];
-    u32 rank[ITEMS];
-    const u32 warpBase = warp * ITEMS * 32;
+    u64 key[ITEMS_T];
+    u32 rank[ITEMS_T];
+    const u32 warpBase = warp * ITEMS_T * 32;
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        u32 local = warpBase + i * 32 + lane;
-        bool ok = local < tileValid;
-        key[i] = ok ? keysIn[tileBase + local] : 0;
-        u64 w = key[i];
-        if (HAS_VAL && pass.word == 1) w = ok ? valsIn[tileBase + local] : 0;
-        dig[i] = ok ? digit_of(w, pass.shift, pass.mask) : pass.mask;   // padding ranks last in the last bin
+    for (int i = 0; i < ITEMS_T; i++) {
+        const u32 local = warpBase + i * 32 + lane;
+        key[i] = local < tileValid ? keysIn[tileBase + local] : ~0ull;   // padding: all digit bits set -> last bin, ranks last
     }
-    // stable rank inside the warp's chunk
+    // stable rank inside the warp's chunk: all MATCH.ANY first (independent, their latency overlaps), then the
+    // dependent chain through the per-warp digit counters
+    u32 peers[ITEMS_T];
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        u32 d = dig[i];
-        u32 peers = __match_any_sync(0xffffffffu, d);
-        u32 pre = warpHist[warp][d];
+    for (int i = 0; i < ITEMS_T; i++) {
+        // lanes with the same digit: intersection of 8 ballots (MATCH.ANY iterates once per distinct value, ~30x slower
+        // on random digits; measured on B200)
+        const u32 d = digit_of(key[i], pass.shift, pass.mask);
+        u32 m = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < RADIX_BITS; b++) {
+            const u32 vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+            m &= ((d >> b) & 1u) ? vote : ~vote;
+        }
+        peers[i] = m;
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS_T; i++) {
+        const u32 d = digit_of(key[i], pass.shift, pass.mask);
+        const u32 pre = S.warpHist[warp][d];
+        const u32 lower = peers[i] & ((1u << lane) - 1);
         __syncwarp();
-        if (lane == (__ffs(peers) - 1)) warpHist[warp][d] = pre + __popc(peers);
+        if (lower == 0) S.warpHist[warp][d] = pre + __popc(peers[i]);   // lowest lane of the peer group publishes
         __syncwarp();
-        rank[i] = pre + __popc(peers & ((1u << lane) - 1));
+        rank[i] = pre + __popc(lower);
     }
     __syncthreads();
     // thread d: scan digit d over the warps, publish the tile aggregate, look back
-    {
+    u32 run = 0, incl = 0;
+    if (tid < RADIX) {
         const int d = tid;
-        u32 run = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) { u32 c = warpHist[w][d]; warpHist[w][d] = run; run += c; }
-        volatile u32 *state = tileState;
+        for (int w = 0; w < WARPS_T; w++) run += S.warpHist[w][d];
+        u32 *state = tileState;
         u64 excl = 0;
         if (tile == 0) {
-            state[d] = FLAG_INC | run;
+            st_state(state + d, FLAG_INC | run);
         } else {
-            state[(u64) tile * RADIX + d] = FLAG_AGG | run;
+            st_state(state + (u64) tile * RADIX + d, FLAG_AGG | run);
+            // decoupled look-back, LOOK predecessors per round trip (independent loads), consumed nearest first
+            constexpr int LOOK = 8;
             i64 p = (i64) tile - 1;
-            while (true) {
-                u32 s = state[(u64) p * RADIX + d];
-                if ((s & FLAG_MASK) == 0) continue;   // predecessor has not published yet
-                excl += s & VAL_MASK;
-                if ((s & FLAG_MASK) == FLAG_INC) break;
-                p--;
-            }
-            state[(u64) tile * RADIX + d] = FLAG_INC | (u32) (excl + run);
-        }
-        gBase[d] = binBase[d] + excl;
-        // exclusive scan of the tile's digit counts over d (block scan via warp shuffles)
-        u32 incl = run;
+            bool done = false;
+            while (!done) {
+                u32 sv[LOOK];
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
-        if (lane == 31) warpSum[warp] = incl;
-        __syncthreads();
+                for (int j = 0; j < LOOK; j++) sv[j] = (p - j) >= 0 ? ld_state(state + (u64) (p - j) * RADIX + d) : 0x80000000u /* FLAG_INC, value 0: nothing before tile 0 */;
+                int used = 0;
+#pragma unroll
+                for (int j = 0; j < LOOK; j++) {
+                    if (!done && used == j) {
+                        const u32 f = sv[j] & FLAG_MASK;
+                        if (f != 0) { excl += sv[j] & VAL_MASK; used = j + 1; if (f == FLAG_INC) done = true; }
+                    }
+                }
+                p -= used;   // first predecessor that had not published yet is polled again
+            }
+            st_state(state + (u64) tile * RADIX + d, FLAG_INC | (u32) (excl + run));
+        }
+        // exclusive scan of the tile's digit counts over d (8 warps of 32 digits)
+        incl = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+        if (lane == 31) S.warpSum[warp] = incl;
+        S.delta[d] = binBase[d] + excl;   // completed below
+    }
+    __syncthreads();
+    if (tid < RADIX) {
+        const int d = tid;
         u32 wpre = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) if (w < warp) wpre += warpSum[w];
-        tileOff[d] = wpre + incl - run;
+        for (int w = 0; w < 8; w++) if (w < warp) wpre += S.warpSum[w];
+        const u32 tileOff = wpre + incl - run;   // first position of digit d in the sorted tile
+        S.delta[d] -= tileOff;                    // out index = delta[d] + position in tile
+        u32 base = tileOff;                       // per-warp scatter base = tile offset + counts of the warps before
+#pragma unroll
+        for (int w = 0; w < WARPS_T; w++) { const u32 c = S.warpHist[w][d]; S.warpHist[w][d] = base; base += c; }
     }
     __syncthreads();
     // scatter into tile order through shared memory, then coalesced runs to global
-    u32 pos[ITEMS];
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        pos[i] = tileOff[dig[i]] + warpHist[warp][dig[i]] + rank[i];
-        exch[pos[i]] = key[i];
-        digitAt[pos[i]] = (u8) dig[i];
+    for (int i = 0; i < ITEMS_T; i++) {
+        const u32 d = digit_of(key[i], pass.shift, pass.mask);
+        rank[i] += S.warpHist[warp][d];
+        S.exch[rank[i]] = key[i];
+        if (HAS_VAL) S.digitAt[rank[i]] = (u8) d;
     }
     __syncthreads();
-    for (u32 j = tid; j < tileValid; j += BLOCK) {
-        u32 d = digitAt[j];
-        keysOut[gBase[d] + (j - tileOff[d])] = exch[j];
+#pragma unroll
+    for (int i = 0; i < ITEMS_T; i++) {
+        const u32 j = tid + i * BLOCK_T;
+        if (j < tileValid) {
+            const u64 k = S.exch[j];
+            keysOut[S.delta[digit_of(k, pass.shift, pass.mask)] + j] = k;
+        }
     }
     if (HAS_VAL) {
+        u64 v[ITEMS_T];
+#pragma unroll
+        for (int i = 0; i < ITEMS_T; i++) {
+            const u32 local = warpBase + i * 32 + lane;
+            v[i] = local < tileValid ? valsIn[tileBase + local] : 0;
+        }
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < ITEMS; i++) {
-            u32 local = warpBase + i * 32 + lane;
-            if (local < tileValid) exch[pos[i]] = valsIn[tileBase + local];
-        }
+        for (int i = 0; i < ITEMS_T; i++) S.exch[rank[i]] = v[i];
         __syncthreads();
-        for (u32 j = tid; j < tileValid; j += BLOCK) {
-            u32 d = digitAt[j];
-            valsOut[gBase[d] + (j - tileOff[d])] = exch[j];
+#pragma unroll
+        for (int i = 0; i < ITEMS_T; i++) {
+            const u32 j = tid + i * BLOCK_T;
+            if (j < tileValid) valsOut[S.delta[S.digitAt[j]] + j] = S.exch[j];
         }
     }
+}
+
+// ---- kernel 3b: persistent, software-pipelined digit pass --------------------------------------------------
+// Same algorithm; block b of a grid that is fully resident processes tiles b, b+G, b+2G, ... (every tile's predecessor
+// belongs to a resident block that reaches it in the same round, so the chained scan cannot stall on an unscheduled
+// tile).  The keys of the block's next tile are requested right after the current tile has been scattered into shared
+// memory and the look-back is moved behind the scatter, so the global round trips (key loads, predecessor states)
+// overlap the shared-memory work instead of serialising the tile.
+template <int BLOCK_T, int ITEMS_T, bool HAS_VAL>
+__global__ void __launch_bounds__(BLOCK_T) onesweep_persistent_kernel(const u64 *__restrict__ keysIn, u64 *__restrict__ keysOut,
+                                                                      const u64 *__restrict__ valsIn, u64 *__restrict__ valsOut, u64 n,
+                                                                      Pass pass, const unsigned long long *__restrict__ binBase,
+                                                                      u32 *tileState /*[tiles][RADIX]*/, u32 *ticket) {
+    constexpr int TILE_T = BLOCK_T * ITEMS_T, WARPS_T = BLOCK_T / 32;
+    extern __shared__ __align__(16) unsigned char sweepRaw[];
+    SweepSmem<BLOCK_T, ITEMS_T, HAS_VAL> &S = *reinterpret_cast<SweepSmem<BLOCK_T, ITEMS_T, HAS_VAL> *>(sweepRaw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 numTiles = (u32) ((n + TILE_T - 1) / TILE_T);
+    const u32 warpBase = warp * ITEMS_T * 32;
+
+    (void) ticket;
+    u32 tile = blockIdx.x;
+    u64 key[ITEMS_T];
+    if (tile < numTiles) {
+        const u64 tb = (u64) tile * TILE_T;
+        const u32 tv = (u32) (n - tb < (u64) TILE_T ? n - tb : (u64) TILE_T);
+#pragma unroll
+        for (int i = 0; i < ITEMS_T; i++) { const u32 local = warpBase + i * 32 + lane; key[i] = local < tv ? keysIn[tb + local] : ~0ull; }
+    }
+    while (tile < numTiles) {
+        const u64 tileBase = (u64) tile * TILE_T;
+        const u32 tileValid = (u32) (n - tileBase < (u64) TILE_T ? n - tileBase : (u64) TILE_T);
+        for (int i = tid; i < WARPS_T * RADIX; i += BLOCK_T) (&S.warpHist[0][0])[i] = 0;
+        __syncthreads();
+        // rank
+        u32 rank[ITEMS_T];
+        {
+            u32 peers[ITEMS_T];
+#pragma unroll
+            for (int i = 0; i < ITEMS_T; i++) {
+                const u32 d = digit_of(key[i], pass.shift, pass.mask);
+                u32 m = 0xffffffffu;
+#pragma unroll
+                for (int b = 0; b < RADIX_BITS; b++) {
+                    const u32 vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+                    m &= ((d >> b) & 1u) ? vote : ~vote;
+                }
+                peers[i] = m;
+            }
+#pragma unroll
+            for (int i = 0; i < ITEMS_T; i++) {
+                const u32 d = digit_of(key[i], pass.shift, pass.mask);
+                const u32 pre = S.warpHist[warp][d];
+                const u32 lower = peers[i] & ((1u << lane) - 1);
+                __syncwarp();
+                if (lower == 0) S.warpHist[warp][d] = pre + __popc(peers[i]);
+                __syncwarp();
+                rank[i] = pre + __popc(lower);
+            }
+        }
+        __syncthreads();
+        // tile aggregate out as early as possible; tile-local offsets
+        u32 run = 0, incl = 0;
+        if (tid < RADIX) {
+            const int d = tid;
+#pragma unroll
+            for (int w = 0; w < WARPS_T; w++) run += S.warpHist[w][d];
+            st_state(tileState + (u64) tile * RADIX + d, (tile == 0 ? FLAG_INC : FLAG_AGG) | run);
+            incl = run;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+            if (lane == 31) S.warpSum[warp] = incl;
+        }
+        __syncthreads();
+        u32 tileOff = 0;
+        if (tid < RADIX) {
+            const int d = tid;
+            u32 wpre = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) if (w < warp) wpre += S.warpSum[w];
+            tileOff = wpre + incl - run;
+            u32 base = tileOff;
+#pragma unroll
+            for (int w = 0; w < WARPS_T; w++) { const u32 c = S.warpHist[w][d]; S.warpHist[w][d] = base; base += c; }
+        }
+        __syncthreads();
+        // scatter into tile order
+#pragma unroll
+        for (int i = 0; i < ITEMS_T; i++) {
+            const u32 d = digit_of(key[i], pass.shift, pass.mask);
+            rank[i] += S.warpHist[warp][d];
+            S.exch[rank[i]] = key[i];
+            if (HAS_VAL) S.digitAt[rank[i]] = (u8) d;
+        }
+        // requests that overlap the look-back: values of this tile, keys of the next tile, the ticket after that
+        u64 v[HAS_VAL ? ITEMS_T : 1];
+        if (HAS_VAL) {
+#pragma unroll
+            for (int i = 0; i < ITEMS_T; i++) { const u32 local = warpBase + i * 32 + lane; v[i] = local < tileValid ? valsIn[tileBase + local] : 0; }
+        }
+        const u32 nextTile = tile + gridDim.x;
+        if (nextTile < numTiles) {
+            const u64 tb = (u64) nextTile * TILE_T;
+            const u32 tv = (u32) (n - tb < (u64) TILE_T ? n - tb : (u64) TILE_T);
+#pragma unroll
+            for (int i = 0; i < ITEMS_T; i++) { const u32 local = warpBase + i * 32 + lane; key[i] = local < tv ? keysIn[tb + local] : ~0ull; }
+        }
+        // look-back (predecessors published their aggregates a scatter phase ago)
+        if (tid < RADIX) {
+            const int d = tid;
+            u32 *state = tileState;
+            u64 excl = 0;
+            if (tile != 0) {
+                constexpr int LOOK = 8;
+                i64 p = (i64) tile - 1;
+                bool done = false;
+                while (!done) {
+                    u32 sv[LOOK];
+#pragma unroll
+                    for (int j = 0; j < LOOK; j++) sv[j] = (p - j) >= 0 ? ld_state(state + (u64) (p - j) * RADIX + d) : 0x80000000u;
+                    int used = 0;
+#pragma unroll
+                    for (int j = 0; j < LOOK; j++) {
+                        if (!done && used == j) {
+                            const u32 f = sv[j] & FLAG_MASK;
+                            if (f != 0) { excl += sv[j] & VAL_MASK; used = j + 1; if (f == FLAG_INC) done = true; }
+                        }
+                    }
+                    p -= used;
+                }
+                st_state(state + (u64) tile * RADIX + d, FLAG_INC | (u32) (excl + run));
+            }
+            S.delta[d] = binBase[d] + excl - tileOff;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS_T; i++) {
+            const u32 j = tid + i * BLOCK_T;
+            if (j < tileValid) {
+                const u64 k = S.exch[j];
+                keysOut[S.delta[digit_of(k, pass.shift, pass.mask)] + j] = k;
+            }
+        }
+        if (HAS_VAL) {
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < ITEMS_T; i++) S.exch[rank[i]] = v[i];
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < ITEMS_T; i++) {
+                const u32 j = tid + i * BLOCK_T;
+                if (j < tileValid) valsOut[S.delta[S.digitAt[j]] + j] = S.exch[j];
+            }
+        }
+        __syncthreads();   // exch / delta / warpHist are reused by the next tile
+        tile = nextTile;
+    }
+}
+
+template <int BLOCK_T, int ITEMS_T, bool HAS_VAL>
+inline void launch_persistent(cudaStream_t st, const u64 *ki, u64 *ko, const u64 *vi, u64 *vo, u64 n, const Pass &p,
+                              const unsigned long long *binBase, u32 *tileState, u32 *ticket, int smCount) {
+    typedef SweepSmem<BLOCK_T, ITEMS_T, HAS_VAL> SM;
+    static int blocksPerSm = 0;
+    if (!blocksPerSm) {
+        cudaFuncSetAttribute(onesweep_persistent_kernel<BLOCK_T, ITEMS_T, HAS_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(SM));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, onesweep_persistent_kernel<BLOCK_T, ITEMS_T, HAS_VAL>, BLOCK_T, sizeof(SM));
+        if (blocksPerSm < 1) blocksPerSm = 1;
+    }
+    const u64 tiles = (n + SM::TILE_T - 1) / SM::TILE_T;
+    u64 grid = (u64) smCount * blocksPerSm;
+    if (grid > tiles) grid = tiles;
+    onesweep_persistent_kernel<BLOCK_T, ITEMS_T, HAS_VAL><<<(unsigned) grid, BLOCK_T, sizeof(SM), st>>>(ki, ko, vi, vo, n, p, binBase, tileState, ticket);
 }
 
 // plan: passes of <= 8 bits over val bits [vLo,vHi) then key bits [kLo,kHi)
@@ -191,17 +410,54 @@ struct Workspace {   // device scratch owned by the caller
     unsigned long long *hist;   // [MAX_PASSES][RADIX]
     u32 *tileState;             // [tiles][RADIX]
     u32 *ticket;
-    u64 tilesCap;
+    u64 tilesCap;               // in tiles of MIN_TILE records
 };
-inline u64 tiles_for(u64 n) { return (n + TILE - 1) / TILE; }
+static constexpr int MIN_TILE = 2048;
+inline u64 tiles_for(u64 n) { return (n + MIN_TILE - 1) / MIN_TILE; }
 
-// Sorts in place semantics: input in (keysA, valsA); result pointer pair returned through outKeys/outVals
-// (either A or B, depending on the number of passes).  Returns number of kernels launched, <0 on error.
+template <int BLOCK_T, int ITEMS_T, bool HAS_VAL>
+inline void launch_pass(cudaStream_t st, const u64 *ki, u64 *ko, const u64 *vi, u64 *vo, u64 n, const Pass &p, const unsigned long long *binBase,
+                        u32 *tileState, u32 *ticket) {
+    typedef SweepSmem<BLOCK_T, ITEMS_T, HAS_VAL> SM;
+    static bool attrSet = false;
+    if (!attrSet) { cudaFuncSetAttribute(onesweep_kernel<BLOCK_T, ITEMS_T, HAS_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(SM)); attrSet = true; }
+    const u64 tiles = (n + SM::TILE_T - 1) / SM::TILE_T;
+    onesweep_kernel<BLOCK_T, ITEMS_T, HAS_VAL><<<(unsigned) tiles, BLOCK_T, sizeof(SM), st>>>(ki, ko, vi, vo, n, p, binBase, tileState, ticket);
+}
+
+// variant: 0 = 256 threads x 16 keys, 1 = 256 x 8, 2 = 512 x 8, 3 = 384... (tuning knob; default chosen by measurements)
+inline void launch_variant(int variant, bool hasVal, cudaStream_t st, const u64 *ki, u64 *ko, const u64 *vi, u64 *vo, u64 n, const Pass &p,
+                           const unsigned long long *binBase, u32 *tileState, u32 *ticket, int smCount) {
+    switch (variant * 2 + (hasVal ? 1 : 0)) {
+        case 8: launch_persistent<256, 16, false>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket, smCount); break;
+        case 9: launch_persistent<256, 16, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket, smCount); break;
+        case 10: launch_persistent<256, 8, false>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket, smCount); break;
+        case 11: launch_persistent<256, 8, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket, smCount); break;
+        case 12: launch_persistent<512, 8, false>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket, smCount); break;
+        case 13: launch_persistent<512, 8, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket, smCount); break;
+        case 14: launch_persistent<384, 8, false>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket, smCount); break;
+        case 15: launch_persistent<384, 8, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket, smCount); break;
+        case 0: launch_pass<256, 16, false>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
+        case 1: launch_pass<256, 16, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
+        case 2: launch_pass<256, 8, false>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
+        case 3: launch_pass<256, 8, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
+        case 4: launch_pass<512, 8, false>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
+        case 5: launch_pass<512, 8, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
+        case 6: launch_pass<512, 4, false>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
+        default: launch_pass<512, 4, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
+    }
+}
+inline int &default_variant(bool hasVal) { static int v[2] = {2, 2}; return v[hasVal ? 1 : 0]; }   // 512 threads x 8 keys: best measured on B200
+
+// Input in (keysA, valsA); result pointer pair returned through outKeys/outVals (A or B, depending on the number
+// of passes).  Returns number of kernels launched, <0 on error.  passMs (optional): per-pass event timing sink.
 inline int radix_sort(cudaStream_t st, Workspace &ws, u64 *keysA, u64 *keysB, u64 *valsA, u64 *valsB, u64 n, const Plan &plan,
-                      u64 **outKeys, u64 **outVals, int smCount) {
+                      u64 **outKeys, u64 **outVals, int smCount, int variant = -1) {
     *outKeys = keysA; *outVals = valsA;
     if (n == 0 || plan.n == 0) return 0;
     if (n > MAX_N || tiles_for(n) > ws.tilesCap || plan.n > MAX_PASSES) return -1;
+    for (int p = 0; p < plan.n; p++) if (plan.p[p].word != 0) return -1;   // digits come from the key word
+    if (variant < 0) variant = default_variant(valsA != nullptr);
     int launches = 0;
     cudaMemsetAsync(ws.hist, 0, sizeof(unsigned long long) * MAX_PASSES * RADIX, st);
     int hb = smCount * 8;
@@ -210,13 +466,11 @@ inline int radix_sort(cudaStream_t st, Workspace &ws, u64 *keysA, u64 *keysB, u6
     hist_kernel<<<hb, BLOCK, plan.n * RADIX * sizeof(u32), st>>>(keysA, valsA, n, plan, ws.hist);
     binscan_kernel<<<1, RADIX, 0, st>>>(ws.hist, plan.n);
     launches += 2;
-    u64 tiles = tiles_for(n);
     u64 *ki = keysA, *ko = keysB, *vi = valsA, *vo = valsB;
     for (int p = 0; p < plan.n; p++) {
-        cudaMemsetAsync(ws.tileState, 0, tiles * RADIX * sizeof(u32), st);
+        cudaMemsetAsync(ws.tileState, 0, tiles_for(n) * RADIX * sizeof(u32), st);
         cudaMemsetAsync(ws.ticket, 0, sizeof(u32), st);
-        if (valsA) onesweep_kernel<true><<<(unsigned) tiles, BLOCK, 0, st>>>(ki, ko, vi, vo, n, plan.p[p], ws.hist + p * RADIX, ws.tileState, ws.ticket);
-        else onesweep_kernel<false><<<(unsigned) tiles, BLOCK, 0, st>>>(ki, ko, nullptr, nullptr, n, plan.p[p], ws.hist + p * RADIX, ws.tileState, ws.ticket);
+        launch_variant(variant, valsA != nullptr, st, ki, ko, vi, vo, n, plan.p[p], ws.hist + p * RADIX, ws.tileState, ws.ticket, smCount);
         launches++;
         u64 *t = ki; ki = ko; ko = t;
         t = vi; vi = vo; vo = t;

@@ -174,6 +174,10 @@ int cdg_test_radix_sort(cdg_ctx *ctx, uint64_t *keys, uint64_t *vals, uint64_t n
 int cdg_test_hash_revcomp(cdg_ctx *ctx, const uint64_t *in, uint64_t n, int k, uint64_t seed, uint64_t *hash_out,
                           uint64_t *rc_out);
 
+/* sort micro-benchmark on device-generated random keys (ms per full sort incl. histogram); tuning knob for the tile shape */
+int cdg_test_sort_bench(cdg_ctx *ctx, uint64_t n, int bit_lo, int bit_hi, int has_val, int variant, int reps, float *ms_per_sort, int *passes);
+int cdg_test_set_sort_variant(int keys_only_variant, int pairs_variant);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,27 @@ def test_radix_sort(ctx, n, pairs):
             assert np.array_equal(v2, vals[order])   # stability
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+def test_radix_sort_all_tile_shapes(ctx, variant):
+    import carpedeam_b200 as cd
+    L = cd.lib()
+    rng = np.random.default_rng(variant)
+    try:
+        L.cdg_test_set_sort_variant(variant, variant)
+        for n in (5, 2047, 2049, 300001, 2500003):
+            keys = rng.integers(0, 1 << 63, n, dtype=np.uint64)
+            keys[: n // 2] &= np.uint64(0xFFFFF)
+            vals = np.arange(n, dtype=np.uint64)
+            for pairs in (False, True):
+                k2, v2 = ctx.test_radix_sort(keys, vals if pairs else None, 0, 44)
+                order = np.argsort(keys & np.uint64((1 << 44) - 1), kind="stable")
+                assert np.array_equal(k2, keys[order])
+                if pairs:
+                    assert np.array_equal(v2, vals[order])
+    finally:
+        L.cdg_test_set_sort_variant(2, 2)
+
+
 def _hits_equal(a, b):
     for f in ("rep", "tgt", "score", "diag"):
         assert np.array_equal(a[f], b[f]), f
