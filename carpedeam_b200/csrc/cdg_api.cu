@@ -63,7 +63,7 @@ struct cdg_ctx {
     DevBuf dTileSums, dScalars, dHist, dTileState;
     // kmermatcher
     DevBuf dSlotOff, dKeysA, dKeysB, dValsA, dValsB, dIdKeysA, dIdKeysB, dIdValsA, dIdValsB, dKey2A, dKey2B;
-    DevBuf dLongList, dScratchOff, dScratch, dScratchKeep, dShortScratch, dShortKeep;
+    DevBuf dLongList, dScratchOff, dScratch, dScratchKeep, dShortScratch, dShortKeep, dOrdKA, dOrdKB, dOrdVA, dOrdVB, dRankOf, dSlotRank;
     DevBuf dHitRep, dHitTgt, dHitScore, dHitDiag;
     HostBuf hHitRep, hHitTgt, hHitScore, hHitDiag, hHitDiag16;
     u64 nHits = 0, nRecords = 0, nGrouped = 0; bool hitsValid = false;
@@ -99,6 +99,17 @@ void rec(cdg_ctx *ctx, int e) { cudaEventRecord(ctx->ev[e], ctx->st); ctx->evVal
 
 struct LenWordsF { const u32 *len; __device__ u32 operator()(u64 i) const { return (len[i] + 31) >> 5; } };
 struct LenBasesF { const u32 *len; __device__ u32 operator()(u64 i) const { return len[i]; } };
+struct OrderedCapacityF { const u64 *order; const u32 *len; int k, kps; float scale;
+    __device__ u32 operator()(u64 r) const { return cdgkmer::kmer_capacity(len[(u32) order[r]], k, kps, scale); } };
+__global__ void __launch_bounds__(256) order_init_kernel(const u32 *__restrict__ len, u64 n, u32 maxLen, u64 *__restrict__ k, u64 *__restrict__ v) {
+    u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { k[i] = (u64) (maxLen - len[i]); v[i] = i; }
+}
+__global__ void __launch_bounds__(256) order_scatter_kernel(const u64 *__restrict__ order, const u64 *__restrict__ prefix, u64 n,
+                                                            u64 *__restrict__ slotOff, u32 *__restrict__ rankOf) {
+    u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) { const u32 seq = (u32) order[r]; slotOff[seq] = prefix[r]; rankOf[seq] = (u32) r; }
+}
 struct CapacityF { const u32 *len; int k, kps; float scale; __device__ u32 operator()(u64 i) const { return cdgkmer::kmer_capacity(len[i], k, kps, scale); } };
 
 template <class F>
@@ -196,7 +207,7 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
     DevBuf *d[] = {&ctx->dMeta, &ctx->dData, &ctx->dOff, &ctx->dLen, &ctx->dExt, &ctx->dWordOff, &ctx->dWords, &ctx->dXmask, &ctx->dFlags, &ctx->dLikOff,
                    &ctx->dTileSums, &ctx->dScalars, &ctx->dHist, &ctx->dTileState, &ctx->dSlotOff, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA,
                    &ctx->dValsB, &ctx->dIdKeysA, &ctx->dIdKeysB, &ctx->dIdValsA, &ctx->dIdValsB, &ctx->dKey2A, &ctx->dKey2B, &ctx->dLongList,
-                   &ctx->dScratchOff, &ctx->dScratch, &ctx->dScratchKeep, &ctx->dShortScratch, &ctx->dShortKeep, &ctx->dHitRep, &ctx->dHitTgt,
+                   &ctx->dOrdKA, &ctx->dOrdKB, &ctx->dOrdVA, &ctx->dOrdVB, &ctx->dRankOf, &ctx->dSlotRank, &ctx->dScratchOff, &ctx->dScratch, &ctx->dScratchKeep, &ctx->dShortScratch, &ctx->dShortKeep, &ctx->dHitRep, &ctx->dHitTgt,
                    &ctx->dHitScore, &ctx->dHitDiag, &ctx->dLineOff, &ctx->dLineQ, &ctx->dLineT, &ctx->dLinePref, &ctx->dLineDiag, &ctx->dKeep,
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
                    &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList};
@@ -266,10 +277,22 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
     CK(cudaMemsetAsync(sc, 0, SC_N * 8, ctx->st));
     rec(ctx, EV_START);
-    // slots
-    CK(ctx->dSlotOff.reserve((n + 1) * 8));
+    // slots, laid out in (sequence length desc, id asc) order: after the stable k-mer sort the first record of every
+    // run is the representative of compareRepSequenceAndIdAndPosReverse (kmermatcher.h:76-96)
+    CK(ctx->dSlotOff.reserve((n + 1) * 8)); CK(ctx->dSlotRank.reserve((n + 1) * 8)); CK(ctx->dRankOf.reserve(n * 4));
+    CK(ctx->dOrdKA.reserve(n * 8)); CK(ctx->dOrdKB.reserve(n * 8)); CK(ctx->dOrdVA.reserve(n * 8)); CK(ctx->dOrdVB.reserve(n * 8));
     int rc;
-    if ((rc = scan_to(ctx, CapacityF{ctx->dLen.as<u32>(), p->k, p->kmers_per_seq, p->kmers_per_seq_scale}, n, ctx->dSlotOff.as<u64>(), true))) return rc;
+    cdgsort::Workspace ws;
+    if ((rc = sort_ws(ctx, n, ws))) return rc;
+    order_init_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dLen.as<u32>(), n, ctx->maxLen, ctx->dOrdKA.as<u64>(), ctx->dOrdVA.as<u64>());
+    u64 *ordK, *ordV;
+    int lo = cdgsort::radix_sort(ctx->st, ws, ctx->dOrdKA.as<u64>(), ctx->dOrdKB.as<u64>(), ctx->dOrdVA.as<u64>(), ctx->dOrdVB.as<u64>(), n,
+                                 cdgsort::make_plan(0, 0, 0, std::max(1, ceil_log2((u64) ctx->maxLen + 1))), &ordK, &ordV, ctx->smCount);
+    if (lo < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "length-order sort failed");
+    ctx->launches += lo + 1;
+    if ((rc = scan_to(ctx, OrderedCapacityF{ordV, ctx->dLen.as<u32>(), p->k, p->kmers_per_seq, p->kmers_per_seq_scale}, n, ctx->dSlotRank.as<u64>(), false))) return rc;
+    order_scatter_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ordV, ctx->dSlotRank.as<u64>(), n, ctx->dSlotOff.as<u64>(), ctx->dRankOf.as<u32>());
+    ctx->launches++;
     u64 slots = 0;
     if ((rc = read_scalar(ctx, SC_SCAN, &slots))) return rc;
     const u32 extraCap = (u32) (1024 + (n >> 10));
@@ -298,7 +321,7 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     CK(ctx->dShortKeep.reserve(gridWarps * EX_MAXW));
     {
         const u32 maxW = ctx->maxLen >= (u32) p->k ? ctx->maxLen - p->k + 1 : 0;   // short sequences have <= 256 windows
-#define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), n, E, ctx->dSlotOff.as<u64>(), ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), slots, extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT)
+#define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), n, E, ctx->dSlotOff.as<u64>(), ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), slots, extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT)
         if (maxW <= 64) extract_short_kernel<2><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
         else if (maxW <= 128) extract_short_kernel<4><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
         else extract_short_kernel<8><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
@@ -312,14 +335,13 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
         extract_long_kernel<<<lb, EXL_BLOCK, (32768 + 128) * 4, ctx->st>>>(
             ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dLongList.as<u32>(), nLong, E,
             ctx->dSlotOff.as<u64>(), ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), slots, extraCap,
-            (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dScratch.as<WinRec>(), ctx->dScratchKeep.as<u8>(), ctx->dScratchOff.as<u64>(),
+            (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dScratch.as<WinRec>(), ctx->dScratchKeep.as<u8>(), ctx->dScratchOff.as<u64>(),
             sc + SC_EMIT);
         ctx->launches++;
         CKL();
     }
     rec(ctx, EV_EXTRACT);
     // sort 1: k-mer records by the 2k k-mer bits; identity records by their 63 hash bits
-    cdgsort::Workspace ws;
     if ((rc = sort_ws(ctx, Rtot > n ? Rtot : n, ws))) return rc;
     u64 *mk, *mv, *ik, *iv;
     cdgsort::Plan plan1 = cdgsort::make_plan(0, 0, 0, 2 * p->k);
@@ -343,9 +365,9 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     CK(ctx->dKey2A.reserve(key2Cap * 8)); CK(ctx->dKey2B.reserve(key2Cap * 8));
     GroupParams G; G.idBits = idBits; G.diagBits = diagBits; G.diagBias = (i32) ctx->maxLen; G.onlyExtendable = p->include_only_extendable;
     G.firstRunQuirk = (emitted + (u32) extra) > 0 ? 1 : 0;
-    group_kernel<<<(unsigned) ((Rtot + 255) / 256), 256, 0, ctx->st>>>(mk, mv, Rtot, ctx->dLen.as<u32>(), G, ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
+    group_kernel<<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(mk, mv, Rtot, ctx->dLen.as<u32>(), G, ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
     GroupParams GI = G; GI.firstRunQuirk = G.firstRunQuirk ? 0 : 1;
-    group_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ik, iv, n, ctx->dLen.as<u32>(), GI, ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
+    group_kernel<<<(unsigned) ((n + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ik, iv, n, ctx->dLen.as<u32>(), GI, ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
     ctx->launches += 2;
     CKL();
     u64 R2 = 0;
@@ -367,7 +389,7 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     // reduce
     u64 H = 0;
     if (R2 > 0) {
-        PairHeadFlag f; f.keys = k2; f.n = R2; f.idBits = idBits; f.diagBits = diagBits;
+        PairEndFlag f; f.keys = k2; f.n = R2; f.idBits = idBits; f.diagBits = diagBits;
         u64 tiles = cdgscan::tiles_for(R2);
         CK(ctx->dTileSums.reserve((tiles + 1) * 8));
         unsigned long long *ts = ctx->dTileSums.as<unsigned long long>();

@@ -152,7 +152,7 @@ CDG_D void select_sequential(const WinRec *sorted, u32 cnt, u32 considered, u32 
 // Goes to idKeys/idVals[seq] unless its value (bit 63 masked) lies inside the k-mer key range, in
 // which case it must be sorted among the k-mers: those go to the `extra` slots of the main array.
 CDG_D void emit_identity(u64 seqHash, u64 seq, const ExtractParams &P, u64 *idKeys, u64 *idVals, u64 *mainKeys, u64 *mainVals,
-                         u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow) {
+                         u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow, const u32 *__restrict__ rankOf) {
     u32 h16 = (u32) (seqHash & 0xFFFFu);
     bool owned = h16 >= P.hashLo && h16 <= P.hashHi;
     u64 key = CDG_SENTINEL, val = 0;
@@ -163,7 +163,8 @@ CDG_D void emit_identity(u64 seqHash, u64 seq, const ExtractParams &P, u64 *idKe
         else atomicExch(overflow, 1u);
         key = CDG_SENTINEL; val = 0;
     }
-    idKeys[seq] = key; idVals[seq] = val;
+    const u32 slot = rankOf[seq];   // (length desc, id asc) order: after the stable sort the representative comes first
+    idKeys[slot] = key; idVals[slot] = val;
 }
 
 static constexpr int EX_WARPS = 8;
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
     const u64 *__restrict__ words, const u32 *__restrict__ xmask, const u64 *__restrict__ wordOff, const u32 *__restrict__ len,
     u64 n, ExtractParams P, const u64 *__restrict__ slotOff /*[n] first main slot of seq*/,
     u64 *__restrict__ mainKeys, u64 *__restrict__ mainVals, u64 *__restrict__ idKeys, u64 *__restrict__ idVals,
-    u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow, WinRec *__restrict__ scratch /*[gridWarps][2*EX_MAXW]*/,
+    u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow, const u32 *__restrict__ rankOf, WinRec *__restrict__ scratch /*[gridWarps][2*EX_MAXW]*/,
     u8 *__restrict__ scratchKeep /*[gridWarps][EX_MAXW]*/, unsigned long long *__restrict__ emitted) {
     extern __shared__ u32 bitmapAll[];   // [EX_WARPS][2048] : 65536 bits per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) emit_identity(cdg_xxh64_u64(part, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow);
+        if (lane == 0) emit_identity(cdg_xxh64_u64(part, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow, rankOf);
 
         // windows: lane handles p = lane + 32*it
         WinRec rec[ITERS];
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(EXL_BLOCK) extract_long_kernel(
     const u64 *__restrict__ words, const u32 *__restrict__ xmask, const u64 *__restrict__ wordOff, const u32 *__restrict__ len,
     const u32 *__restrict__ longList, u32 nLong, ExtractParams P, const u64 *__restrict__ slotOff,
     u64 *__restrict__ mainKeys, u64 *__restrict__ mainVals, u64 *__restrict__ idKeys, u64 *__restrict__ idVals,
-    u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow,
+    u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow, const u32 *__restrict__ rankOf,
     WinRec *__restrict__ scratch, u8 *__restrict__ scratchKeep, const u64 *__restrict__ scratchOff /*[nLong] pow2-padded regions*/,
     unsigned long long *__restrict__ emitted) {
     extern __shared__ u32 shmem[];
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(EXL_BLOCK) extract_long_kernel(
         if (tid == 0) {
             u64 h = 0;
             for (int i = 0; i < EXL_BLOCK / 32; i++) h += sHash[i];
-            emit_identity(cdg_xxh64_u64(h, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow);
+            emit_identity(cdg_xxh64_u64(h, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow, rankOf);
             u32 cnt = sCnt;
             float consF = (float) (P.kmersPerSeq - 1) + P.scale * (float) L;
             u64 cons64 = consF > 0.f ? (u64) consF : 0;
@@ -442,64 +443,109 @@ CDG_D void member_diag(bool repRev, u32 repLen, u32 repPos, bool tRev, u32 tLen,
     else { q = (i32) repPos; t = (i32) tPos; need = false; }
     diag = q - t;
 }
-__global__ void __launch_bounds__(256) group_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, u64 n,
-                                                    const u32 *__restrict__ len, GroupParams G, u64 *__restrict__ out,
-                                                    unsigned long long *__restrict__ outCount) {
-    const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    u32 m = 0;          // members this thread will write
-    u64 runEnd = i;
-    u32 repLen = 0, repId = 0, repPos = 0; u64 repKey = 0;
-    bool head = false;
-    if (i < n) {
-        u64 k = keys[i];
-        if (k != CDG_SENTINEL && (i == 0 || (keys[i - 1] | CDG_B63) != (k | CDG_B63))) {
-            head = true;
-            u64 kk = k | CDG_B63;
-            u64 j = i;
-            while (j < n) {
-                u64 kj = keys[j];
-                if (kj == CDG_SENTINEL || (kj | CDG_B63) != kk) break;
-                u64 v = vals[j];
-                u32 id = cdg_val_id(v), pos = cdg_val_pos(v), l = len[id];
-                if (j == i || rep_better(l, id, pos, kj, repLen, repId, repPos, repKey)) { repLen = l; repId = id; repPos = pos; repKey = kj; }
-                j++;
-            }
-            runEnd = j;
-            if (j - i < 2) head = false;   // singletons are dropped (:476)
+// Walk-free: k-mer slots are laid out in (sequence length desc, id asc) order and the radix sort is stable, so
+// the first record of every run of equal k-mers already IS the representative (same-sequence repeats at the head
+// are resolved by a short scan).  One thread per record: the index of its run head comes from a block-wide max-scan
+// of head indices, the output position from a block-wide exclusive scan of keep flags.
+static constexpr int GROUP_BLOCK = 256;
+static constexpr int GROUP_ITEMS = 8;
+static constexpr int GROUP_TILE = GROUP_BLOCK * GROUP_ITEMS;
+__global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, u64 n,
+                                                            const u32 *__restrict__ len, GroupParams G, u64 *__restrict__ out,
+                                                            unsigned long long *__restrict__ outCount) {
+    __shared__ u64 sKey[GROUP_TILE + 1];   // +1: the record after the tile (singleton test)
+    __shared__ u64 sVal[GROUP_TILE];
+    __shared__ u32 shWarp[GROUP_BLOCK / 32 + 1];
+    __shared__ u32 sWarpMax[GROUP_BLOCK / 32];
+    __shared__ unsigned long long sBase;
+    __shared__ u64 sTileHead;              // head index of the run that is open at the tile start
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 tileBase = (u64) blockIdx.x * GROUP_TILE;
+    const u32 tileN = (u32) (n - tileBase < (u64) GROUP_TILE ? n - tileBase : (u64) GROUP_TILE);
+    for (u32 i = tid; i < tileN; i += GROUP_BLOCK) { sKey[i] = keys[tileBase + i]; sVal[i] = vals[tileBase + i]; }
+    if (tid == 0) {
+        sKey[tileN] = tileBase + tileN < n ? keys[tileBase + tileN] : CDG_SENTINEL;
+        // run open at the tile start: walk back to its head (one thread per tile, runs are short)
+        u64 h = tileBase;
+        if (tileBase > 0) {
+            const u64 k0 = keys[tileBase] | CDG_B63;
+            while (h > 0 && (keys[h - 1] | CDG_B63) == k0) h--;
         }
+        sTileHead = h;
     }
-    const bool repRev = head ? ((G.firstRunQuirk && i == 0) ? false : ((repKey & CDG_B63) == 0)) : false;
-    if (head) {
-        if (!G.onlyExtendable) m = (u32) (runEnd - i);
-        else {
-            for (u64 j = i; j < runEnd; j++) {
-                u64 v = vals[j]; u32 id = cdg_val_id(v); u32 tl = len[id];
-                i32 d; bool need;
-                member_diag(repRev, repLen, repPos, (keys[j] & CDG_B63) == 0, tl, cdg_val_pos(v), d, need);
-                if (d < 0 || d > (i32) repLen - (i32) tl) m++;   // :526-536
-            }
-        }
-    }
-    // warp-aggregated allocation of output slots
-    u32 incl = m;
+    __syncthreads();
+    // head flags and run-head index by max-scan (blocked arrangement: thread t owns records [t*ITEMS, (t+1)*ITEMS))
+    const u32 first = tid * GROUP_ITEMS;
+    u32 headOf[GROUP_ITEMS];   // tile-local index of the run head + 1, 0 = before the tile
+    u32 runMax = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    u32 total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned long long base = 0;
-    if (lane == 31 && total) base = atomicAdd(outCount, (unsigned long long) total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    if (m) {
-        u64 dst = base + (incl - m);
-        const int sh1 = G.diagBits + 1, sh2 = G.idBits + G.diagBits + 1;
-        for (u64 j = i; j < runEnd; j++) {
-            u64 v = vals[j]; u32 id = cdg_val_id(v); u32 tl = len[id];
-            i32 d; bool need;
-            member_diag(repRev, repLen, repPos, (keys[j] & CDG_B63) == 0, tl, cdg_val_pos(v), d, need);
-            if (G.onlyExtendable && !(d < 0 || d > (i32) repLen - (i32) tl)) continue;
-            out[dst++] = ((u64) repId << sh2) | ((u64) id << sh1) | ((u64) (u32) (d + G.diagBias) << 1) | (need ? 1ull : 0ull);
+    for (int j = 0; j < GROUP_ITEMS; j++) {
+        const u32 li = first + j;
+        if (li < tileN) {
+            const u64 k = sKey[li] | CDG_B63;
+            const bool head = li == 0 ? (sTileHead == tileBase) : ((sKey[li - 1] | CDG_B63) != k);
+            if (head) runMax = li + 1;
         }
+        headOf[j] = runMax;
     }
+    // exclusive max-scan of runMax over threads
+    u32 incl = runMax;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl = max(incl, t); }
+    if (lane == 31) sWarpMax[warp] = incl;
+    __syncthreads();
+    u32 carry = 0;
+#pragma unroll
+    for (int w = 0; w < GROUP_BLOCK / 32; w++) if (w < warp) carry = max(carry, sWarpMax[w]);
+    const u32 prevLane = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane > 0) carry = max(carry, prevLane);
+    // per record: representative, diagonal, keep flag
+    u64 outKey[GROUP_ITEMS];
+    u32 keep = 0;
+    const int sh1 = G.diagBits + 1, sh2 = G.idBits + G.diagBits + 1;
+#pragma unroll
+    for (int j = 0; j < GROUP_ITEMS; j++) {
+        const u32 li = first + j;
+        outKey[j] = 0;
+        if (li >= tileN) continue;
+        const u64 k = sKey[li];
+        if (k == CDG_SENTINEL) continue;
+        const u32 hl = max(headOf[j], carry);
+        const u64 headIdx = hl ? tileBase + hl - 1 : sTileHead;
+        const bool isHead = headIdx == tileBase + li;
+        if (isHead && (sKey[li + 1] == CDG_SENTINEL || (sKey[li + 1] | CDG_B63) != (k | CDG_B63))) continue;   // singleton (:476)
+        // representative = head record; repeats of the head's own sequence: smallest position (forward first)
+        auto keyAt = [&](u64 x) -> u64 { return (x >= tileBase && x < tileBase + tileN) ? sKey[x - tileBase] : (x < n ? keys[x] : CDG_SENTINEL); };
+        auto valAt = [&](u64 x) -> u64 { return (x >= tileBase && x < tileBase + tileN) ? sVal[x - tileBase] : vals[x]; };
+        u64 repKey = keyAt(headIdx), repVal = valAt(headIdx);
+        const u32 repId = cdg_val_id(repVal);
+        u32 repPos = cdg_val_pos(repVal);
+        for (u64 x = headIdx + 1; x < n; x++) {
+            const u64 kx = keyAt(x);
+            if (kx == CDG_SENTINEL || (kx | CDG_B63) != (k | CDG_B63)) break;
+            const u64 vx = valAt(x);
+            if (cdg_val_id(vx) != repId) break;
+            const u32 px = cdg_val_pos(vx);
+            if (px < repPos || (px == repPos && (kx & CDG_B63) > (repKey & CDG_B63))) { repPos = px; repKey = kx; }
+        }
+        const u32 repLen = len[repId];
+        const bool repRev = (G.firstRunQuirk && headIdx == 0) ? false : ((repKey & CDG_B63) == 0);
+        const u64 v = sVal[li];
+        const u32 id = cdg_val_id(v), tl = len[id];
+        i32 d; bool need;
+        member_diag(repRev, repLen, repPos, (k & CDG_B63) == 0, tl, cdg_val_pos(v), d, need);
+        if (G.onlyExtendable && !(d < 0 || d > (i32) repLen - (i32) tl)) continue;   // :526-536
+        outKey[j] = ((u64) repId << sh2) | ((u64) id << sh1) | ((u64) (u32) (d + G.diagBias) << 1) | (need ? 1ull : 0ull);
+        keep |= 1u << j;
+    }
+    // compaction: block scan of keep counts, one atomic per block
+    u32 blockTotal;
+    const u32 myOff = cdgscan::block_excl_scan((u32) __popc(keep), &blockTotal, shWarp);
+    if (tid == 0) sBase = blockTotal ? atomicAdd(outCount, (unsigned long long) blockTotal) : 0ull;
+    __syncthreads();
+    u64 dst = sBase + myOff;
+#pragma unroll
+    for (int j = 0; j < GROUP_ITEMS; j++) if (keep & (1u << j)) out[dst++] = outKey[j];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -509,51 +555,180 @@ __global__ void __launch_bounds__(256) group_kernel(const u64 *__restrict__ keys
 // diagonal (ties: the larger one), the number of records and the strand of the last record on the best
 // diagonal (:889-905).  Self pairs (target == rep) produce no hit (:906).
 struct ReduceParams { int idBits, diagBits; i32 diagBias; };
-struct PairHeadFlag {
+// flag = last record of a (rep,target) pair with target != rep: one hit each, in sorted (= pref DB) order
+struct PairEndFlag {
     const u64 *keys; u64 n; int idBits, diagBits;
     CDG_D u32 operator()(u64 i) const {
-        u64 k = keys[i];
-        u64 pair = k >> (diagBits + 1);
-        if (i > 0 && (keys[i - 1] >> (diagBits + 1)) == pair) return 0;
-        u32 id = (u32) (pair & ((1ull << idBits) - 1)), rep = (u32) (pair >> idBits);
+        const u64 pair = keys[i] >> (diagBits + 1);
+        if (i + 1 < n && (keys[i + 1] >> (diagBits + 1)) == pair) return 0;
+        const u32 id = (u32) (pair & ((1ull << idBits) - 1)), rep = (u32) (pair >> idBits);
         return id != rep ? 1u : 0u;
     }
 };
-__global__ void __launch_bounds__(cdgscan::BLOCK) reduce_kernel(PairHeadFlag f, ReduceParams R, const unsigned long long *__restrict__ tileSums,
-                                                                u32 *__restrict__ hitRep, u32 *__restrict__ hitTgt,
-                                                                i32 *__restrict__ hitScore, i32 *__restrict__ hitDiag) {
-    __shared__ u32 shWarp[cdgscan::BLOCK / 32 + 1];
-    u64 prefix[cdgscan::ITEMS]; u32 flag[cdgscan::ITEMS];
-    cdgscan::tile_prefix(f, f.n, tileSums, shWarp, prefix, flag);
-    const u64 base = (u64) blockIdx.x * cdgscan::TILE;
+
+// sequential replay of the reference's walk (kmermatcher.cpp:886-905) from the first record `s` of a pair; used for
+// pairs that start before the tile and for pairs whose target-id run bleeds into the next representative
+CDG_D void reduce_walk(const u64 *__restrict__ keys, u64 n, u64 s, const ReduceParams &R, u32 &top, i32 &best, bool &brev) {
     const u64 idMask = (1ull << R.idBits) - 1, diagMask = (1ull << R.diagBits) - 1;
-#pragma unroll 1
-    for (int it = 0; it < cdgscan::ITEMS; it++) {
-        if (!flag[it]) continue;
-        u64 i = base + (u64) it * cdgscan::BLOCK + threadIdx.x;
-        u64 k = f.keys[i];
-        u32 tgt = (u32) ((k >> (R.diagBits + 1)) & idMask), rep = (u32) (k >> (R.diagBits + 1 + R.idBits));
-        i32 prev = (i32) ((k >> 1) & diagMask), best = prev;
-        u32 dc = 0, mx = 0, top = 0, prevRep = rep; bool brev = false, runNeed = false;
-        u64 e = i;
-        while (e < f.n) {
-            u64 ke = f.keys[e];
-            if ((u32) ((ke >> (R.diagBits + 1)) & idMask) != tgt) break;
-            i32 d = (i32) ((ke >> 1) & diagMask);
-            // records with equal (rep,id,diag) are unordered in the reference (its comparator masks the strand bit);
-            // our order puts needRev last, so "the last record of the run" is the OR over the run
-            // (across a rep boundary inside a bleeding walk only the later rep's records can be "last")
-            const u32 repE = (u32) (ke >> (R.diagBits + 1 + R.idBits));
-            const bool sameRun = prev == d;
-            dc = sameRun ? dc + 1 : 1;
-            runNeed = (sameRun && repE == prevRep) ? (runNeed || (ke & 1ull)) : ((ke & 1ull) != 0);
-            if (dc >= mx) { best = d; mx = dc; brev = runNeed; }
-            prev = d; prevRep = repE; e++; top++;
+    const int pairShift = R.diagBits + 1;
+    const u64 k = keys[s];
+    const u32 tgt = (u32) ((k >> pairShift) & idMask);
+    u32 prevRep = (u32) (k >> (pairShift + R.idBits));
+    i32 prev = (i32) ((k >> 1) & diagMask);
+    best = prev; brev = false; top = 0;
+    u32 dc = 0, mx = 0; bool runNeed = false;
+    for (u64 e = s; e < n; e++) {
+        const u64 ke = keys[e];
+        if ((u32) ((ke >> pairShift) & idMask) != tgt) break;   // the rep is deliberately not checked
+        const i32 d = (i32) ((ke >> 1) & diagMask);
+        const u32 repE = (u32) (ke >> (pairShift + R.idBits));
+        const bool sameRun = prev == d;
+        dc = sameRun ? dc + 1 : 1;
+        // equal (rep,id,diag) records are unordered in the reference; our order puts needRev last -> OR over the run,
+        // restarted at a rep boundary inside a bleeding walk (only the later rep's records can be "last")
+        runNeed = (sameRun && repE == prevRep) ? (runNeed || (ke & 1ull)) : ((ke & 1ull) != 0);
+        if (dc >= mx) { best = d; mx = dc; brev = runNeed; }
+        prev = d; prevRep = repE; top++;
+    }
+}
+
+// Walk-free reduction: one thread per record, two block-wide segmented scans (diagonal-run length / strand OR, then
+// best run per pair), results taken at the last record of each pair.
+static constexpr int RED_BLOCK = cdgscan::BLOCK;
+static constexpr int RED_ITEMS = cdgscan::ITEMS;
+static constexpr int RED_TILE = cdgscan::TILE;
+
+// inclusive segmented scan over the tile (blocked arrangement); heads: bit j = item j starts a segment
+template <class Op>
+CDG_D void block_seg_scan(u64 (&val)[RED_ITEMS], u32 heads, Op op, u64 *shVal /*[warps]*/, u32 *shFlag /*[warps]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 1; j < RED_ITEMS; j++) if (!(heads & (1u << j))) val[j] = op(val[j - 1], val[j]);
+    u64 agg = val[RED_ITEMS - 1];
+    u32 flag = heads != 0;
+    // warp inclusive segmented scan of the thread aggregates
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 v2 = __shfl_up_sync(0xffffffffu, agg, o);
+        const u32 f2 = __shfl_up_sync(0xffffffffu, flag, o);
+        if (lane >= o) { if (!flag) agg = op(v2, agg); flag |= f2; }
+    }
+    __syncthreads();
+    if (lane == 31) { shVal[warp] = agg; shFlag[warp] = flag; }
+    __syncthreads();
+    // carry into this thread = segmented combination of everything before it in the tile
+    u64 carry = 0; u32 have = 0;   // have: carry holds a value
+    for (int w = 0; w < warp; w++) {
+        const u64 v = shVal[w]; const u32 f = shFlag[w];
+        carry = (f || !have) ? v : op(carry, v);
+        have = 1;
+    }
+    const u64 pv = __shfl_up_sync(0xffffffffu, agg, 1);
+    const u32 pf = __shfl_up_sync(0xffffffffu, flag, 1);
+    if (lane > 0) { carry = (pf || !have) ? pv : op(carry, pv); have = 1; }
+    if (have) {
+#pragma unroll
+        for (int j = 0; j < RED_ITEMS; j++) { if (heads & (1u << j)) break; val[j] = op(carry, val[j]); }
+    }
+}
+struct OpLenNeed { CDG_D u64 operator()(u64 a, u64 b) const { return (((a >> 1) + (b >> 1)) << 1) | ((a | b) & 1ull); } };
+struct OpMax { CDG_D u64 operator()(u64 a, u64 b) const { return a > b ? a : b; } };
+
+__global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(PairEndFlag f, ReduceParams R, const unsigned long long *__restrict__ tileSums,
+                                                           u32 *__restrict__ hitRep, u32 *__restrict__ hitTgt,
+                                                           i32 *__restrict__ hitScore, i32 *__restrict__ hitDiag) {
+    __shared__ u64 sKey[RED_TILE + 2];   // [0] = record before the tile, [tileN+1] = record after it
+    __shared__ u64 shVal[RED_BLOCK / 32];
+    __shared__ u32 shFlag[RED_BLOCK / 32];
+    __shared__ u32 shWarp[RED_BLOCK / 32 + 1];
+    __shared__ u32 sWarpMax[RED_BLOCK / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 base = (u64) blockIdx.x * RED_TILE;
+    const u32 tileN = (u32) (f.n - base < (u64) RED_TILE ? f.n - base : (u64) RED_TILE);
+    const u64 NONE = ~0ull;   // pair field of "no record": real pairs have at most 2*idBits < 64 bits
+    for (u32 i = tid; i < tileN; i += RED_BLOCK) sKey[i + 1] = f.keys[base + i];
+    if (tid == 0) { sKey[0] = base > 0 ? f.keys[base - 1] : NONE; sKey[tileN + 1] = base + tileN < f.n ? f.keys[base + tileN] : NONE; }
+    __syncthreads();
+    const int pairShift = R.diagBits + 1;
+    const u64 idMask = (1ull << R.idBits) - 1, diagMask = (1ull << R.diagBits) - 1;
+    auto pairOf = [&](u64 k) -> u64 { return k == NONE ? NONE : (k >> pairShift); };
+    const u32 first = tid * RED_ITEMS;
+    u32 pairHeads = 0, runHeads = 0, pairEnds = 0, runEnds = 0;
+    u64 v1[RED_ITEMS];
+    u32 headOf[RED_ITEMS]; u32 runMax = 0;   // tile-local index + 1 of the pair head, 0 = before the tile
+#pragma unroll
+    for (int j = 0; j < RED_ITEMS; j++) {
+        const u32 li = first + j;
+        v1[j] = 0;
+        if (li < tileN) {
+            const u64 k = sKey[li + 1], kp = sKey[li], kn = sKey[li + 2];
+            const bool ph = pairOf(kp) != pairOf(k), pe = pairOf(kn) != pairOf(k);
+            const bool rh = ph || ((kp >> 1) & diagMask) != ((k >> 1) & diagMask);
+            const bool re = pe || ((kn >> 1) & diagMask) != ((k >> 1) & diagMask);
+            pairHeads |= ph ? 1u << j : 0; runHeads |= rh ? 1u << j : 0; pairEnds |= pe ? 1u << j : 0; runEnds |= re ? 1u << j : 0;
+            v1[j] = 2ull | (k & 1ull);   // (length 1) << 1 | needRev
+            if (ph) runMax = li + 1;
+        } else { pairHeads |= 1u << j; runHeads |= 1u << j; }
+        headOf[j] = runMax;
+    }
+    // scan 1: per diagonal run (length, OR of needRev)
+    block_seg_scan(v1, runHeads, OpLenNeed(), shVal, shFlag);
+    // scan 2: per pair, best run so far = max of (runLength, position, needRev) taken at run ends
+    u64 v2[RED_ITEMS];
+#pragma unroll
+    for (int j = 0; j < RED_ITEMS; j++) v2[j] = (runEnds & (1u << j)) ? (((v1[j] >> 1) << 34) | ((u64) (first + j) << 1) | (v1[j] & 1ull)) : 0ull;
+    block_seg_scan(v2, pairHeads, OpMax(), shVal, shFlag);
+    // pair-head index by max-scan
+    u32 incl = runMax;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl = max(incl, t); }
+    __syncthreads();
+    if (lane == 31) sWarpMax[warp] = incl;
+    __syncthreads();
+    u32 carry = 0;
+#pragma unroll
+    for (int w = 0; w < RED_BLOCK / 32; w++) if (w < warp) carry = max(carry, sWarpMax[w]);
+    const u32 prevLane = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane > 0) carry = max(carry, prevLane);
+    // hits at pair ends, compacted in order
+    u32 flags = 0;
+#pragma unroll
+    for (int j = 0; j < RED_ITEMS; j++) {
+        const u32 li = first + j;
+        if (li < tileN && (pairEnds & (1u << j))) {
+            const u64 pair = sKey[li + 1] >> pairShift;
+            if ((u32) (pair & idMask) != (u32) (pair >> R.idBits)) flags |= 1u << j;
         }
-        u64 h = prefix[it];
+    }
+    u32 tot;
+    const u32 ex = cdgscan::block_excl_scan((u32) __popc(flags), &tot, shWarp);
+    u64 h = tileSums[blockIdx.x] + ex;
+#pragma unroll
+    for (int j = 0; j < RED_ITEMS; j++) {
+        if (!(flags & (1u << j))) continue;
+        const u32 li = first + j;
+        const u64 k = sKey[li + 1];
+        const u32 tgt = (u32) ((k >> pairShift) & idMask), rep = (u32) (k >> (pairShift + R.idBits));
+        const u32 hl = max(headOf[j], carry);
+        const u64 kn = sKey[li + 2];
+        const bool bleeds = kn != NONE && (u32) ((kn >> pairShift) & idMask) == tgt;   // next rep's first target is the same id
+        u32 top; i32 best; bool brev;
+        if (hl != 0 && !bleeds) {
+            const u32 startLi = hl - 1;
+            top = li - startLi + 1;
+            const u64 b = v2[j];
+            best = (i32) ((sKey[(u32) ((b >> 1) & 0xFFFFFFFFull) + 1] >> 1) & diagMask);
+            brev = (b & 1ull) != 0;
+        } else {
+            u64 s = base + li;
+            if (hl != 0) s = base + hl - 1;
+            else { const u64 pr = k >> pairShift; while (s > 0 && (f.keys[s - 1] >> pairShift) == pr) s--; }
+            reduce_walk(f.keys, f.n, s, R, top, best, brev);
+        }
         hitRep[h] = rep; hitTgt[h] = tgt;
         hitScore[h] = brev ? -(i32) top : (i32) top;
         hitDiag[h] = best - R.diagBias;
+        h++;
     }
 }
 
