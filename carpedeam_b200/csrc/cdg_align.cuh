@@ -12,25 +12,27 @@ namespace cdgalign {
 // ---- line list -----------------------------------------------------------------------------------
 // pref entry of query q = `q 0 0` followed by its hits (kmermatcher.cpp:836,:710-730).  With hits sorted by
 // (rep,target): self line of q at q + lower_bound(hitRep, q); hit h of rep r at h + r + 1.
-__global__ void __launch_bounds__(256) lines_self_kernel(const u32 *__restrict__ hitRep, u64 H, u64 n, u64 *__restrict__ lineOff,
+// Queries [qLo, qLo+n) (multi-GPU: the rank's query range; single GPU: all); lineOff is indexed by q - qLo.
+__global__ void __launch_bounds__(256) lines_self_kernel(const u32 *__restrict__ hitRep, u64 H, u64 qLo, u64 n, u64 *__restrict__ lineOff,
                                                          u32 *__restrict__ lineQ, u32 *__restrict__ lineT, i32 *__restrict__ linePref,
                                                          u16 *__restrict__ lineDiag) {
-    u64 q = (u64) blockIdx.x * blockDim.x + threadIdx.x;
-    if (q > n) return;
+    u64 ql = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    if (ql > n) return;
+    const u64 q = qLo + ql;
     u64 lo = 0, hi = H;
     while (lo < hi) { u64 mid = (lo + hi) >> 1; if (hitRep[mid] < q) lo = mid + 1; else hi = mid; }
-    u64 l = q + lo;
-    lineOff[q] = l;
-    if (q < n) { lineQ[l] = (u32) q; lineT[l] = (u32) q; linePref[l] = 0; lineDiag[l] = 0; }
+    u64 l = ql + lo;
+    lineOff[ql] = l;
+    if (ql < n) { lineQ[l] = (u32) q; lineT[l] = (u32) q; linePref[l] = 0; lineDiag[l] = 0; }
 }
 __global__ void __launch_bounds__(256) lines_hits_kernel(const u32 *__restrict__ hitRep, const u32 *__restrict__ hitTgt,
-                                                         const i32 *__restrict__ hitScore, const i32 *__restrict__ hitDiag, u64 H,
+                                                         const i32 *__restrict__ hitScore, const i32 *__restrict__ hitDiag, u64 H, u64 qLo,
                                                          u32 *__restrict__ lineQ, u32 *__restrict__ lineT, i32 *__restrict__ linePref,
                                                          u16 *__restrict__ lineDiag) {
     u64 h = (u64) blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
     u32 r = hitRep[h];
-    u64 l = h + r + 1;
+    u64 l = h + (r - qLo) + 1;
     lineQ[l] = r; lineT[l] = hitTgt[h]; linePref[l] = hitScore[h];
     lineDiag[l] = (u16) (short) hitDiag[h];   // (short) in writeKmerMatcherResult, parsed back as unsigned short
 }
@@ -228,7 +230,7 @@ CDG_D int most_likely_base(int b, u32 qIter, const u32 *cnt, const u32 *rv, cons
 static constexpr int CORR_WARPS = 4;
 __global__ void __launch_bounds__(CORR_WARPS * 32) correct_wide_kernel(
     const u32 *__restrict__ list, const u32 *__restrict__ listCount,
-    const u8 *__restrict__ data, const u64 *__restrict__ off, const u32 *__restrict__ len, const u8 *__restrict__ ext, u64 n,
+    const u8 *__restrict__ data, const u64 *__restrict__ off, const u32 *__restrict__ len, const u8 *__restrict__ ext, u64 qLo, u64 n,
     const u64 *__restrict__ lineOff, const u32 *__restrict__ lineT, const u8 *__restrict__ keep, const float *__restrict__ seqId,
     const i32 *__restrict__ qS_, const i32 *__restrict__ qE_, const i32 *__restrict__ dS_, const i32 *__restrict__ dE_,
     CorrParams P, const DamageTables *__restrict__ tablesG, u8 *__restrict__ lineSel, u8 *__restrict__ out,
@@ -242,8 +244,8 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) correct_wide_kernel(
     const u64 nList = *listCount;
     for (u64 li = gwarp; li < nList; li += nwarps) {
         const u64 qi = list[li];
-        if (qi >= n) continue;
-        const u64 l0 = lineOff[qi], l1 = lineOff[qi + 1];
+        if (qi < qLo || qi >= qLo + n) continue;
+        const u64 l0 = lineOff[qi - qLo], l1 = lineOff[qi - qLo + 1];
         const u32 qLen = len[qi];
         const u8 *q = data + off[qi];
         u8 *o = out + off[qi];
@@ -342,7 +344,7 @@ static constexpr int CF_CACHE = 32;
 struct SeqMeta { u64 off; u32 wordOff; u32 lenFlags; };   // lenFlags: len | exception << 30 | ext << 31
 static constexpr u32 META_EXC = 1u << 30, META_EXT = 1u << 31, META_LEN = (1u << 30) - 1;
 struct LineCache { u64 tOff[CF_CACHE]; u32 dL[CF_CACHE]; i32 qs[CF_CACHE]; i32 aln[CF_CACHE]; i32 ds[CF_CACHE]; u32 rev[CF_CACHE]; };
-struct CorrSmem { DamageTables T; u32 cnt[CF_WARPS][44][32]; LineCache lc[CF_WARPS]; };
+struct CorrSmem { DamageTables T; u32 cnt[CF_WARPS][44][32]; LineCache lc[CF_WARPS]; u8 lut[256]; };   // lut: bits 0-1 forward base index, 2-3 reverse-complement base index
 
 __global__ void __launch_bounds__(256) meta_kernel(const u64 *__restrict__ off, const u64 *__restrict__ wordOff, const u32 *__restrict__ len,
                                                    const u8 *__restrict__ flags, const u8 *__restrict__ ext, u64 n, SeqMeta *__restrict__ meta) {
@@ -365,19 +367,20 @@ CDG_D u32 ry_dist_packed(const u64 *__restrict__ qw, u32 qs, const u64 *__restri
     return dist;
 }
 
-// one target column into the per-column counters
-CDG_D void count_column(const u8 *__restrict__ data, u64 tOff, u32 dL, bool rev, u32 tp, u32 (*cnt)[32], int lane, unsigned long long &mask,
-                        u32 &cov0, u32 &cov1, u32 &cov2, u32 &cov3) {
+// one target column into the per-column counters; lut maps the raw target byte to its A0 C1 G2 T3 index
+// (forward: correction.cpp:170-174; reverse: getNuclRevFragment, nuclassembleUtil.cpp:67-76, then the same map)
+CDG_D void count_column(const u8 *__restrict__ data, u64 tOff, u32 dL, bool rev, u32 tp, u32 (*cnt)[32], int lane, const u8 *lut,
+                        unsigned long long &mask) {
     const int cl = ((i32) tp >= (i32) dL - 5) ? 6 + (int) (tp - (dL - 5)) : (tp < 5 ? (int) tp : 5);   // correction.cpp:361-371
-    const int bse = nuc_map(t_char(data + tOff, dL, rev, tp));
+    const u32 e = lut[data[tOff + (rev ? dL - 1 - tp : tp)]];
+    const int bse = rev ? (int) (e >> 2) : (int) (e & 3u);
     const int idx = bse * 11 + cl;
     cnt[idx][lane] += rev ? 0x10001u : 1u;
     mask |= 1ull << idx;
-    cov0 += bse == 0; cov1 += bse == 1; cov2 += bse == 2; cov3 += bse == 3;
 }
 
 __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
-    const u8 *__restrict__ data, const SeqMeta *__restrict__ meta, const u64 *__restrict__ words, u64 n,
+    const u8 *__restrict__ data, const SeqMeta *__restrict__ meta, const u64 *__restrict__ words, u64 qLo, u64 n,
     const u64 *__restrict__ lineOff, const u32 *__restrict__ lineT, const u8 *__restrict__ keep, const float *__restrict__ seqId,
     const i32 *__restrict__ qS_, const i32 *__restrict__ qE_, const i32 *__restrict__ dS_, const i32 *__restrict__ dE_,
     CorrParams P, const DamageTables *__restrict__ tablesG, u8 *__restrict__ lineSel, u8 *__restrict__ out,
@@ -387,16 +390,23 @@ __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
     CorrSmem &S = *reinterpret_cast<CorrSmem *>(smemRaw);
     for (int i = threadIdx.x; i < (int) (sizeof(DamageTables) / sizeof(double)); i += blockDim.x) ((double *) &S.T)[i] = ((const double *) tablesG)[i];
     for (int i = threadIdx.x; i < CF_WARPS * 44 * 32; i += blockDim.x) (&S.cnt[0][0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int fwd = nuc_map((unsigned char) i);
+        const int rvi = nuc_map(t_char((const u8 *) &i, 1, true, 0));   // little-endian: the low byte of i is the character
+        S.lut[i] = (u8) (fwd | (rvi << 2));
+    }
     __syncthreads();
     const DamageTables &T = S.T;
+    const u8 *lut = S.lut;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u32 (*cnt)[32] = S.cnt[warp];
     LineCache &LC = S.lc[warp];
     const u64 gwarp = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64) gridDim.x * blockDim.x) >> 5;
     u32 nChanged = 0;
-    for (u64 qi = gwarp; qi < n; qi += nwarps) {
-        const u64 l0 = lineOff[qi], l1 = lineOff[qi + 1];
+    for (u64 ql = gwarp; ql < n; ql += nwarps) {
+        const u64 l0 = lineOff[ql], l1 = lineOff[ql + 1];
         if (l1 - l0 <= 1) continue;   // at most the self alignment: coverage <= 1 everywhere
+        const u64 qi = qLo + ql;
         const SeqMeta qm = meta[qi];
         const u32 qLen = qm.lenFlags & META_LEN;
         const u8 *q = data + qm.off;
@@ -464,13 +474,12 @@ __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
         for (u32 c0 = 0; c0 < qLen; c0 += 32) {
             const u32 col = c0 + lane;
             unsigned long long mask = 0;
-            u32 cov0 = 0, cov1 = 0, cov2 = 0, cov3 = 0;
             if (nSel <= CF_CACHE) {
 #pragma unroll 4
                 for (u32 i = 0; i < nSel; i++) {
                     const i32 qs = LC.qs[i], aln = LC.aln[i];
                     if (col < qLen && (i32) col >= qs && (i32) col < qs + aln)
-                        count_column(data, LC.tOff[i], LC.dL[i], LC.rev[i] != 0, (u32) LC.ds[i] + (col - (u32) qs), cnt, lane, mask, cov0, cov1, cov2, cov3);
+                        count_column(data, LC.tOff[i], LC.dL[i], LC.rev[i] != 0, (u32) LC.ds[i] + (col - (u32) qs), cnt, lane, lut, mask);
                 }
             } else {
                 for (u64 l = l0; l < l1; l++) {
@@ -483,7 +492,18 @@ __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
                     if (rev) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; }
                     const i32 aln = max(abs(qe - qs), abs(de - ds)) + 1;
                     if (col < qLen && (i32) col >= qs && (i32) col < qs + aln)
-                        count_column(data, tm.off, dL, rev, (u32) ds + (col - (u32) qs), cnt, lane, mask, cov0, cov1, cov2, cov3);
+                        count_column(data, tm.off, dL, rev, (u32) ds + (col - (u32) qs), cnt, lane, lut, mask);
+                }
+            }
+            // coverage per target base from the non-zero counters
+            u32 cov0 = 0, cov1 = 0, cov2 = 0, cov3 = 0;
+            {
+                unsigned long long m = mask;
+                while (m) {
+                    const int idx = __ffsll((long long) m) - 1;
+                    m &= m - 1;
+                    const u32 c = cnt[idx][lane] & 0xFFFFu;
+                    if (idx < 11) cov0 += c; else if (idx < 22) cov1 += c; else if (idx < 33) cov2 += c; else cov3 += c;
                 }
             }
             const u32 tot = cov0 + cov1 + cov2 + cov3;

@@ -48,6 +48,11 @@ enum { EV_START, EV_EXTRACT, EV_SORT1, EV_GROUP, EV_SORT2, EV_REDUCE, EV_RS0, EV
 
 }   // namespace
 
+static constexpr int CDG_MAX_WORLD = 16;
+static constexpr u64 CDG_HEAD_RUN = 4096;   // records of the next rank's head run appended before the reduction
+struct KmPlanFwd {
+    int idBits, diagBits; u32 world, rank; u32 posLo, posHi; u64 slotBase, slots; u32 extraCap; u32 hashLo, hashHi; u32 repChunk; u64 qLo, nQ;
+};
 struct cdg_ctx {
     int device = 0, smCount = 148;
     cudaStream_t st = nullptr;
@@ -68,12 +73,14 @@ struct cdg_ctx {
     HostBuf hHitRep, hHitTgt, hHitScore, hHitDiag, hHitDiag16;
     u64 nHits = 0, nRecords = 0, nGrouped = 0; bool hitsValid = false;
     u32 sort1Passes = 0, sort2Passes = 0;
+    u64 *sortedMainK = nullptr, *sortedMainV = nullptr, *sortedIdK = nullptr, *sortedIdV = nullptr, *sortedKey2 = nullptr;
+    KmPlanFwd plan; u64 qLo = 0, nQ = 0; u64 mgRecv = 0, mgR2 = 0;
     // lines / alignments
     DevBuf dLineOff, dLineQ, dLineT, dLinePref, dLineDiag, dKeep, dScore, dBits, dEvalue, dSeqId, dQS, dQE, dDS, dDE, dLineSel;
     HostBuf hLineOff, hLineT, hKeep, hScore, hBits, hEvalue, hSeqId, hQS, hQE, hDS, hDE;
     u64 nLines = 0, nKept = 0; bool linesValid = false, alnsValid = false, alnsFromText = false;
     // correction
-    DevBuf dTables, dOut, dLik, dWideList; bool damageSet = false;
+    DevBuf dTables, dOut, dLik, dWideList, dRecvK, dRecvV, dRecv2; bool damageSet = false;
 };
 
 namespace {
@@ -93,7 +100,7 @@ int fail(cdg_ctx *c, int code, const char *fmt, ...) {
 
 // scalars block on the device: [0] scan total, [1] emitted records, [2] grouped count, [3] kept lines,
 // [4] changed bases, [5] (u32) extraCount, [6] (u32) overflow, [7] (u32) long count, [8] long scratch total, [9] (u32) sort ticket
-enum { SC_SCAN = 0, SC_EMIT, SC_GROUPED, SC_KEPT, SC_CHANGED, SC_EXTRA, SC_OVERFLOW, SC_NLONG, SC_LONGSCR, SC_TICKET, SC_WIDE, SC_N = 16 };
+enum { SC_SCAN = 0, SC_EMIT, SC_GROUPED, SC_KEPT, SC_CHANGED, SC_EXTRA, SC_OVERFLOW, SC_NLONG, SC_LONGSCR, SC_TICKET, SC_WIDE, SC_ROUTE /*16 counters*/, SC_BOUNDS = SC_ROUTE + 16 /*17 bounds*/, SC_N = SC_BOUNDS + 20 };
 
 void rec(cdg_ctx *ctx, int e) { cudaEventRecord(ctx->ev[e], ctx->st); ctx->evValid[e] = true; }
 
@@ -210,7 +217,7 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
                    &ctx->dOrdKA, &ctx->dOrdKB, &ctx->dOrdVA, &ctx->dOrdVB, &ctx->dRankOf, &ctx->dSlotRank, &ctx->dScratchOff, &ctx->dScratch, &ctx->dScratchKeep, &ctx->dShortScratch, &ctx->dShortKeep, &ctx->dHitRep, &ctx->dHitTgt,
                    &ctx->dHitScore, &ctx->dHitDiag, &ctx->dLineOff, &ctx->dLineQ, &ctx->dLineT, &ctx->dLinePref, &ctx->dLineDiag, &ctx->dKeep,
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
-                   &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList};
+                   &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2};
     for (DevBuf *b : d) b->release();
     HostBuf *h[] = {&ctx->hHitRep, &ctx->hHitTgt, &ctx->hHitScore, &ctx->hHitDiag, &ctx->hHitDiag16, &ctx->hLineOff, &ctx->hLineT, &ctx->hKeep,
                     &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE};
@@ -231,7 +238,7 @@ extern "C" int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_
     if (n >= (1ull << 31)) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_upload_seqs: more than 2^31 sequences per context");
     CK(cudaSetDevice(ctx->device));
     ctx->hitsValid = ctx->linesValid = ctx->alnsValid = false;
-    ctx->n = n; ctx->dataBytes = data_bytes;
+    ctx->n = n; ctx->dataBytes = data_bytes; ctx->qLo = 0; ctx->nQ = n;
     CK(ctx->dData.reserve(data_bytes + 64));
     CK(ctx->dOff.reserve(n * 8)); CK(ctx->dLen.reserve(n * 4)); CK(ctx->dExt.reserve(n)); CK(ctx->dFlags.reserve(n));
     CK(ctx->dWordOff.reserve((n + 1) * 8)); CK(ctx->dLikOff.reserve((n + 1) * 8));
@@ -265,20 +272,37 @@ extern "C" int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_
 }
 
 // ------------------------------------------------------------------------------------------------------
-static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
-    using namespace cdgkmer;
-    const u64 n = ctx->n;
+// ---- kmermatcher building blocks (shared by the single-GPU path and the multi-GPU phases) -----------------------------
+// idBits/diagBits: key2 layout; world/rank; posLo/posHi: slice of the (length desc, id asc) order this context extracts;
+// slotBase/slots: first slot / number of slots of the slice; hashLo/hashHi: hash range this context groups; repChunk: width
+// of the representative (= query) index range per rank; qLo/nQ: query range this context rescores and corrects
+typedef KmPlanFwd KmPlan;
+
+__global__ void slice_bounds_kernel(const u64 *__restrict__ prefix, u64 n, u64 total, u32 world, u64 *__restrict__ bounds /*[world+1]*/) {
+    const u32 j = threadIdx.x;
+    if (j > world) return;
+    if (j == world) { bounds[j] = n; return; }
+    const u64 target = total / world * j;   // first rank position whose slot prefix reaches j/world of the slots
+    u64 lo = 0, hi = n;
+    while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (prefix[mid] < target) lo = mid + 1; else hi = mid; }
+    bounds[j] = lo;
+}
+
+static int km_bits(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlan &K) {
     if (p->k < 8 || p->k > 31) return fail(ctx, CDG_ERR_UNSUPPORTED, "k=%d outside [8,31]", p->k);
-    const int idBits = std::max(1, ceil_log2(n));
-    const int diagBits = std::max(1, ceil_log2(2ull * ctx->maxLen + 1));
-    if (2 * idBits + diagBits + 1 > 64)
-        return fail(ctx, CDG_ERR_UNSUPPORTED, "n=%llu sequences x max length %u needs %d key bits (>64): split the set", (unsigned long long) n,
-                    ctx->maxLen, 2 * idBits + diagBits + 1);
+    if (ctx->maxLen >= (1u << CDG_OWNER_SHIFT)) return fail(ctx, CDG_ERR_UNSUPPORTED, "sequences longer than 2^28 are not supported");
+    K.idBits = std::max(1, ceil_log2(ctx->n));
+    K.diagBits = std::max(1, ceil_log2(2ull * ctx->maxLen + 1));
+    if (2 * K.idBits + K.diagBits + 1 > 64)
+        return fail(ctx, CDG_ERR_UNSUPPORTED, "n=%llu sequences x max length %u needs %d key bits (>64): split the set", (unsigned long long) ctx->n,
+                    ctx->maxLen, 2 * K.idBits + K.diagBits + 1);
+    return 0;
+}
+
+// (length desc, id asc) order, slot prefix in that order, rankOf, slice of this rank
+static int km_prepare(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlan &K) {
+    const u64 n = ctx->n;
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
-    CK(cudaMemsetAsync(sc, 0, SC_N * 8, ctx->st));
-    rec(ctx, EV_START);
-    // slots, laid out in (sequence length desc, id asc) order: after the stable k-mer sort the first record of every
-    // run is the representative of compareRepSequenceAndIdAndPosReverse (kmermatcher.h:76-96)
     CK(ctx->dSlotOff.reserve((n + 1) * 8)); CK(ctx->dSlotRank.reserve((n + 1) * 8)); CK(ctx->dRankOf.reserve(n * 4));
     CK(ctx->dOrdKA.reserve(n * 8)); CK(ctx->dOrdKB.reserve(n * 8)); CK(ctx->dOrdVA.reserve(n * 8)); CK(ctx->dOrdVB.reserve(n * 8));
     int rc;
@@ -290,21 +314,45 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
                                  cdgsort::make_plan(0, 0, 0, std::max(1, ceil_log2((u64) ctx->maxLen + 1))), &ordK, &ordV, ctx->smCount);
     if (lo < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "length-order sort failed");
     ctx->launches += lo + 1;
-    if ((rc = scan_to(ctx, OrderedCapacityF{ordV, ctx->dLen.as<u32>(), p->k, p->kmers_per_seq, p->kmers_per_seq_scale}, n, ctx->dSlotRank.as<u64>(), false))) return rc;
+    if ((rc = scan_to(ctx, OrderedCapacityF{ordV, ctx->dLen.as<u32>(), p->k, p->kmers_per_seq, p->kmers_per_seq_scale}, n, ctx->dSlotRank.as<u64>(), true))) return rc;
     order_scatter_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ordV, ctx->dSlotRank.as<u64>(), n, ctx->dSlotOff.as<u64>(), ctx->dRankOf.as<u32>());
     ctx->launches++;
-    u64 slots = 0;
-    if ((rc = read_scalar(ctx, SC_SCAN, &slots))) return rc;
-    const u32 extraCap = (u32) (1024 + (n >> 10));
-    const u64 Rtot = slots + extraCap;
-    if (Rtot > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "%llu k-mer records exceed one sort (2^30): use hash ranges", (unsigned long long) Rtot);
-    CK(ctx->dKeysA.reserve(Rtot * 8)); CK(ctx->dKeysB.reserve(Rtot * 8)); CK(ctx->dValsA.reserve(Rtot * 8)); CK(ctx->dValsB.reserve(Rtot * 8));
-    CK(ctx->dIdKeysA.reserve(n * 8)); CK(ctx->dIdKeysB.reserve(n * 8)); CK(ctx->dIdValsA.reserve(n * 8)); CK(ctx->dIdValsB.reserve(n * 8));
-    CK(cudaMemsetAsync(ctx->dKeysA.as<u64>() + slots, 0xFF, (size_t) extraCap * 8, ctx->st));
-    CK(cudaMemsetAsync(ctx->dValsA.as<u64>() + slots, 0, (size_t) extraCap * 8, ctx->st));
+    u64 total = 0;
+    if ((rc = read_scalar(ctx, SC_SCAN, &total))) return rc;
+    K.posLo = 0; K.posHi = (u32) n; K.slotBase = 0; K.slots = total;
+    if (K.world > 1) {   // slot-balanced slices of the order
+        u64 *bounds = (u64 *) (sc + SC_BOUNDS);
+        slice_bounds_kernel<<<1, 32, 0, ctx->st>>>(ctx->dSlotRank.as<u64>(), n, total, K.world, bounds);
+        ctx->launches++;
+        u64 hb[CDG_MAX_WORLD + 1];
+        CK(cudaMemcpyAsync(hb, bounds, (K.world + 1) * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        K.posLo = (u32) hb[K.rank]; K.posHi = (u32) hb[K.rank + 1];
+        u64 sb[2] = {0, total};
+        if (K.posLo < n) CK(cudaMemcpyAsync(&sb[0], ctx->dSlotRank.as<u64>() + K.posLo, 8, cudaMemcpyDeviceToHost, ctx->st));
+        if (K.posHi < n) CK(cudaMemcpyAsync(&sb[1], ctx->dSlotRank.as<u64>() + K.posHi, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        if (K.posLo >= n) sb[0] = total;
+        K.slotBase = sb[0]; K.slots = sb[1] - sb[0];
+    }
+    K.extraCap = (u32) (1024 + (n >> 10));
+    K.repChunk = (u32) ((n + K.world - 1) / K.world);
+    K.qLo = (u64) K.repChunk * K.rank; if (K.qLo > n) K.qLo = n;
+    K.nQ = std::min<u64>(K.repChunk, n - K.qLo);
+    K.hashLo = (u32) (((u64) K.rank * 65536 + K.world - 1) / K.world);
+    K.hashHi = (u32) (((u64) (K.rank + 1) * 65536 + K.world - 1) / K.world) - 1;
+    return 0;
+}
+
+// extraction of the slice into (keys, vals)[0, K.slots); extras (identity hashes inside the k-mer key range) at extraBase
+static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64 *keys, u64 *vals, u64 *idKeys, u64 *idVals, u64 extraBase,
+                      bool identityInline, u32 hashLo, u32 hashHi) {
+    using namespace cdgkmer;
+    const u64 n = ctx->n;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
     ExtractParams E; E.k = p->k; E.kmersPerSeq = p->kmers_per_seq; E.scale = p->kmers_per_seq_scale; E.seed = p->hash_shift;
-    E.hashLo = p->hash_lo; E.hashHi = p->hash_hi;
-    // long sequences
+    E.hashLo = hashLo; E.hashHi = hashHi; E.world = K.world; E.posLo = K.posLo; E.posHi = K.posHi; E.slotBase = K.slotBase; E.identity = identityInline ? 1 : 0;
+    int rc;
     CK(ctx->dLongList.reserve(n * 4)); CK(ctx->dScratchOff.reserve(n * 8));
     long_list_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dLen.as<u32>(), n, p->k, p->kmers_per_seq, p->kmers_per_seq_scale,
                                                                         ctx->dLongList.as<u32>(), ctx->dScratchOff.as<u64>(), (u32 *) (sc + SC_NLONG),
@@ -314,14 +362,13 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     if ((rc = read_scalar(ctx, SC_NLONG, &nLong64))) return rc;
     if ((rc = read_scalar(ctx, SC_LONGSCR, &longScr))) return rc;
     const u32 nLong = (u32) nLong64;
-    // short sequences
     const int shortBlocks = ctx->smCount * 3;
     const u64 gridWarps = (u64) shortBlocks * EX_WARPS;
     CK(ctx->dShortScratch.reserve(gridWarps * 2 * EX_MAXW * sizeof(WinRec)));
     CK(ctx->dShortKeep.reserve(gridWarps * EX_MAXW));
     {
         const u32 maxW = ctx->maxLen >= (u32) p->k ? ctx->maxLen - p->k + 1 : 0;   // short sequences have <= 256 windows
-#define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), n, E, ctx->dSlotOff.as<u64>(), ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), slots, extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT)
+#define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT)
         if (maxW <= 64) extract_short_kernel<2><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
         else if (maxW <= 128) extract_short_kernel<4><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
         else extract_short_kernel<8><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
@@ -334,71 +381,98 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
         unsigned lb = nLong < (u32) ctx->smCount ? nLong : (u32) ctx->smCount;
         extract_long_kernel<<<lb, EXL_BLOCK, (32768 + 128) * 4, ctx->st>>>(
             ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dLongList.as<u32>(), nLong, E,
-            ctx->dSlotOff.as<u64>(), ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), slots, extraCap,
-            (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dScratch.as<WinRec>(), ctx->dScratchKeep.as<u8>(), ctx->dScratchOff.as<u64>(),
-            sc + SC_EMIT);
+            ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW),
+            ctx->dRankOf.as<u32>(), ctx->dScratch.as<WinRec>(), ctx->dScratchKeep.as<u8>(), ctx->dScratchOff.as<u64>(), sc + SC_EMIT);
         ctx->launches++;
         CKL();
     }
-    rec(ctx, EV_EXTRACT);
-    // sort 1: k-mer records by the 2k k-mer bits; identity records by their 63 hash bits
+    return 0;
+}
+
+// sort 1 (main array of Rtot records in (ka,va) with partner (kb,vb); identity array of n records) + group -> key2 in dKey2A
+static int km_sort_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64 *ka, u64 *kb, u64 *va, u64 *vb, u64 Rtot, int quirkMode,
+                         u64 *minKeyOut, u64 *R2out) {
+    using namespace cdgkmer;
+    const u64 n = ctx->n;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    int rc;
+    cdgsort::Workspace ws;
     if ((rc = sort_ws(ctx, Rtot > n ? Rtot : n, ws))) return rc;
-    u64 *mk, *mv, *ik, *iv;
     cdgsort::Plan plan1 = cdgsort::make_plan(0, 0, 0, 2 * p->k);
-    int l1 = cdgsort::radix_sort(ctx->st, ws, ctx->dKeysA.as<u64>(), ctx->dKeysB.as<u64>(), ctx->dValsA.as<u64>(), ctx->dValsB.as<u64>(), Rtot, plan1, &mk,
-                                 &mv, ctx->smCount);
+    int l1 = cdgsort::radix_sort(ctx->st, ws, ka, kb, va, vb, Rtot, plan1, &ctx->sortedMainK, &ctx->sortedMainV, ctx->smCount);
     cdgsort::Plan planI = cdgsort::make_plan(0, 0, 0, 63);
     int l2 = cdgsort::radix_sort(ctx->st, ws, ctx->dIdKeysA.as<u64>(), ctx->dIdKeysB.as<u64>(), ctx->dIdValsA.as<u64>(), ctx->dIdValsB.as<u64>(), n, planI,
-                                 &ik, &iv, ctx->smCount);
+                                 &ctx->sortedIdK, &ctx->sortedIdV, ctx->smCount);
     if (l1 < 0 || l2 < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "radix sort: input too large for one pass set");
     ctx->launches += l1 + l2; ctx->sort1Passes = plan1.n;
     CKL();
     rec(ctx, EV_SORT1);
-    // overflow / counters
-    u64 overflow = 0, emitted = 0, extra = 0;
+    u64 overflow = 0;
     if ((rc = read_scalar(ctx, SC_OVERFLOW, &overflow))) return rc;
     if ((u32) overflow) return fail(ctx, CDG_ERR_UNSUPPORTED, "identity-record overflow area exhausted");
-    if ((rc = read_scalar(ctx, SC_EMIT, &emitted))) return rc;
-    if ((rc = read_scalar(ctx, SC_EXTRA, &extra))) return rc;
-    // group assignment (main array, then identity array)
-    const u64 key2Cap = Rtot + n;
+    u64 firstKey = CDG_SENTINEL;
+    if (Rtot) CK(cudaMemcpyAsync(&firstKey, ctx->sortedMainK, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (minKeyOut) *minKeyOut = firstKey == CDG_SENTINEL ? CDG_SENTINEL : (firstKey | CDG_B63);
+    if (quirkMode < 0) return 0;   // multi-GPU: the caller decides the first-run quirk after comparing the ranks' minima
+    return 0;
+}
+
+static int km_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64 Rtot, bool mainHasGlobalFirstRun, bool idHasGlobalFirstRun, u64 *R2out) {
+    using namespace cdgkmer;
+    const u64 n = ctx->n;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    int rc;
+    const u64 key2Cap = Rtot + n + CDG_HEAD_RUN;
     CK(ctx->dKey2A.reserve(key2Cap * 8)); CK(ctx->dKey2B.reserve(key2Cap * 8));
-    GroupParams G; G.idBits = idBits; G.diagBits = diagBits; G.diagBias = (i32) ctx->maxLen; G.onlyExtendable = p->include_only_extendable;
-    G.firstRunQuirk = (emitted + (u32) extra) > 0 ? 1 : 0;
-    group_kernel<<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(mk, mv, Rtot, ctx->dLen.as<u32>(), G, ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
-    GroupParams GI = G; GI.firstRunQuirk = G.firstRunQuirk ? 0 : 1;
-    group_kernel<<<(unsigned) ((n + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ik, iv, n, ctx->dLen.as<u32>(), GI, ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
+    CK(cudaMemsetAsync(sc + SC_GROUPED, 0, 8, ctx->st));
+    GroupParams G; G.idBits = K.idBits; G.diagBits = K.diagBits; G.diagBias = (i32) ctx->maxLen; G.onlyExtendable = p->include_only_extendable;
+    G.firstRunQuirk = mainHasGlobalFirstRun ? 1 : 0;   // kmermatcher.cpp:466: only the globally first run
+    if (Rtot) group_kernel<<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedMainK, ctx->sortedMainV, Rtot, ctx->dLen.as<u32>(), G,
+                                                                                                      ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
+    GroupParams GI = G; GI.firstRunQuirk = idHasGlobalFirstRun ? 1 : 0;
+    group_kernel<<<(unsigned) ((n + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedIdK, ctx->sortedIdV, n, ctx->dLen.as<u32>(), GI,
+                                                                                            ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
     ctx->launches += 2;
     CKL();
-    u64 R2 = 0;
-    if ((rc = read_scalar(ctx, SC_GROUPED, &R2))) return rc;
+    if ((rc = read_scalar(ctx, SC_GROUPED, R2out))) return rc;
     rec(ctx, EV_GROUP);
-    // identity records actually emitted: count of non-sentinel id keys is not needed for parity; R1 = k-mers + extras + identities
-    ctx->nRecords = emitted + n;   // every sequence owns one identity record when the hash range is full
-    ctx->nGrouped = R2;
-    // sort 2
-    u64 *k2 = ctx->dKey2A.as<u64>(), *dummy = nullptr;
-    cdgsort::Plan plan2 = cdgsort::make_plan(0, 0, 1, 2 * idBits + diagBits + 1);   // bit 0 (needRev) is not an ordering key
+    return 0;
+}
+
+// sort 2 of R2 records in dKey2A (partner dKey2B); result pointer in ctx->sortedKey2
+static int km_sort2(cdg_ctx *ctx, const KmPlan &K, u64 R2) {
+    int rc;
+    cdgsort::Workspace ws;
     if (R2 > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "grouped records exceed one sort");
-    if ((rc = sort_ws(ctx, std::max(R2, std::max(Rtot, n)), ws))) return rc;
-    int l3 = cdgsort::radix_sort(ctx->st, ws, ctx->dKey2A.as<u64>(), ctx->dKey2B.as<u64>(), nullptr, nullptr, R2, plan2, &k2, &dummy, ctx->smCount);
+    if ((rc = sort_ws(ctx, std::max<u64>(R2, ctx->n), ws))) return rc;
+    u64 *dummy = nullptr;
+    cdgsort::Plan plan2 = cdgsort::make_plan(0, 0, 1, 2 * K.idBits + K.diagBits + 1);   // bit 0 (needRev) is not an ordering key
+    int l3 = cdgsort::radix_sort(ctx->st, ws, ctx->dKey2A.as<u64>(), ctx->dKey2B.as<u64>(), nullptr, nullptr, R2, plan2, &ctx->sortedKey2, &dummy, ctx->smCount);
     if (l3 < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "radix sort 2 failed");
     ctx->launches += l3; ctx->sort2Passes = plan2.n;
     CKL();
     rec(ctx, EV_SORT2);
-    // reduce
+    return 0;
+}
+
+// best diagonal per pair over sortedKey2[0, nTotal); pairs ending at or after nOwn are walked but not emitted
+static int km_reduce(cdg_ctx *ctx, const KmPlan &K, u64 nOwn, u64 nTotal) {
+    using namespace cdgkmer;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    int rc;
     u64 H = 0;
-    if (R2 > 0) {
-        PairEndFlag f; f.keys = k2; f.n = R2; f.idBits = idBits; f.diagBits = diagBits;
-        u64 tiles = cdgscan::tiles_for(R2);
+    if (nOwn > 0) {
+        PairEndFlag f; f.keys = ctx->sortedKey2; f.n = nTotal; f.idBits = K.idBits; f.diagBits = K.diagBits; f.nOwn = nOwn;
+        u64 tiles = cdgscan::tiles_for(nTotal);
         CK(ctx->dTileSums.reserve((tiles + 1) * 8));
         unsigned long long *ts = ctx->dTileSums.as<unsigned long long>();
-        cdgscan::tile_sum_kernel<<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, R2, ts);
+        cdgscan::tile_sum_kernel<<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, nTotal, ts);
         cdgscan::tile_scan_kernel<<<1, 1024, 0, ctx->st>>>(ts, tiles, sc + SC_SCAN);
         ctx->launches += 2;
         if ((rc = read_scalar(ctx, SC_SCAN, &H))) return rc;
         CK(ctx->dHitRep.reserve((H + 1) * 4)); CK(ctx->dHitTgt.reserve((H + 1) * 4)); CK(ctx->dHitScore.reserve((H + 1) * 4)); CK(ctx->dHitDiag.reserve((H + 1) * 4));
-        ReduceParams R; R.idBits = idBits; R.diagBits = diagBits; R.diagBias = (i32) ctx->maxLen;
+        ReduceParams R; R.idBits = K.idBits; R.diagBits = K.diagBits; R.diagBias = (i32) ctx->maxLen;
         reduce_kernel<<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, R, ts, ctx->dHitRep.as<u32>(), ctx->dHitTgt.as<u32>(), ctx->dHitScore.as<i32>(),
                                                                       ctx->dHitDiag.as<i32>());
         ctx->launches++;
@@ -408,7 +482,39 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     }
     rec(ctx, EV_REDUCE);
     ctx->nHits = H; ctx->hitsValid = true; ctx->linesValid = false; ctx->alnsValid = false;
-    return CDG_OK;
+    return 0;
+}
+
+static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
+    const u64 n = ctx->n;
+    KmPlan K; K.world = 1; K.rank = 0;
+    int rc = km_bits(ctx, p, K);
+    if (rc) return rc;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    CK(cudaMemsetAsync(sc, 0, SC_N * 8, ctx->st));
+    rec(ctx, EV_START);
+    if ((rc = km_prepare(ctx, p, K))) return rc;
+    ctx->plan = K; ctx->qLo = 0; ctx->nQ = n;
+    const u64 Rtot = K.slots + K.extraCap;
+    if (Rtot > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "%llu k-mer records exceed one sort (2^30): use hash ranges", (unsigned long long) Rtot);
+    CK(ctx->dKeysA.reserve(Rtot * 8)); CK(ctx->dKeysB.reserve(Rtot * 8)); CK(ctx->dValsA.reserve(Rtot * 8)); CK(ctx->dValsB.reserve(Rtot * 8));
+    CK(ctx->dIdKeysA.reserve(n * 8)); CK(ctx->dIdKeysB.reserve(n * 8)); CK(ctx->dIdValsA.reserve(n * 8)); CK(ctx->dIdValsB.reserve(n * 8));
+    CK(cudaMemsetAsync(ctx->dKeysA.as<u64>() + K.slots, 0xFF, (size_t) K.extraCap * 8, ctx->st));
+    CK(cudaMemsetAsync(ctx->dValsA.as<u64>() + K.slots, 0, (size_t) K.extraCap * 8, ctx->st));
+    if ((rc = km_extract(ctx, p, K, ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), K.slots, true, p->hash_lo,
+                         p->hash_hi))) return rc;
+    rec(ctx, EV_EXTRACT);
+    u64 minKey = 0;
+    if ((rc = km_sort_group(ctx, p, K, ctx->dKeysA.as<u64>(), ctx->dKeysB.as<u64>(), ctx->dValsA.as<u64>(), ctx->dValsB.as<u64>(), Rtot, 0, &minKey, nullptr))) return rc;
+    u64 emitted = 0, extra = 0, R2 = 0;
+    if ((rc = read_scalar(ctx, SC_EMIT, &emitted))) return rc;
+    if ((rc = read_scalar(ctx, SC_EXTRA, &extra))) return rc;
+    const bool mainNonEmpty = minKey != CDG_SENTINEL;
+    if ((rc = km_group(ctx, p, K, Rtot, mainNonEmpty, !mainNonEmpty, &R2))) return rc;
+    ctx->nRecords = emitted + n;   // every sequence owns one identity record when the hash range is full
+    ctx->nGrouped = R2;
+    if ((rc = km_sort2(ctx, K, R2))) return rc;
+    return km_reduce(ctx, K, R2, R2);
 }
 
 __global__ void __launch_bounds__(256) diag16_kernel(const i32 *__restrict__ d, u64 n, short *__restrict__ o) {
@@ -457,16 +563,16 @@ static int reserve_lines(cdg_ctx *ctx, u64 M) {
 }
 
 static int build_lines_from_hits(cdg_ctx *ctx) {
-    const u64 n = ctx->n, H = ctx->nHits, M = n + H;
+    const u64 nQ = ctx->nQ, qLo = ctx->qLo, H = ctx->nHits, M = nQ + H;
     int rc = reserve_lines(ctx, M);
     if (rc) return rc;
-    cdgalign::lines_self_kernel<<<(unsigned) ((n + 1 + 255) / 256), 256, 0, ctx->st>>>(ctx->dHitRep.as<u32>(), H, n, ctx->dLineOff.as<u64>(),
-                                                                                       ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(),
-                                                                                       ctx->dLinePref.as<i32>(), ctx->dLineDiag.as<u16>());
+    cdgalign::lines_self_kernel<<<(unsigned) ((nQ + 1 + 255) / 256), 256, 0, ctx->st>>>(ctx->dHitRep.as<u32>(), H, qLo, nQ, ctx->dLineOff.as<u64>(),
+                                                                                        ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(),
+                                                                                        ctx->dLinePref.as<i32>(), ctx->dLineDiag.as<u16>());
     ctx->launches++;
     if (H) {
         cdgalign::lines_hits_kernel<<<(unsigned) ((H + 255) / 256), 256, 0, ctx->st>>>(ctx->dHitRep.as<u32>(), ctx->dHitTgt.as<u32>(), ctx->dHitScore.as<i32>(),
-                                                                                     ctx->dHitDiag.as<i32>(), H, ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(),
+                                                                                     ctx->dHitDiag.as<i32>(), H, qLo, ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(),
                                                                                      ctx->dLinePref.as<i32>(), ctx->dLineDiag.as<u16>());
         ctx->launches++;
     }
@@ -493,7 +599,7 @@ extern "C" int cdg_set_pref_lines(cdg_ctx *ctx, const uint64_t *line_off, uint64
     ctx->launches++;
     CKL();
     CK(cudaStreamSynchronize(ctx->st));
-    ctx->nLines = n_lines; ctx->linesValid = true; ctx->alnsValid = false;
+    ctx->nLines = n_lines; ctx->linesValid = true; ctx->alnsValid = false; ctx->qLo = 0; ctx->nQ = ctx->n;
     return CDG_OK;
 }
 
@@ -524,7 +630,7 @@ static int run_rescore(cdg_ctx *ctx, const cdg_rescore_params *p) {
 }
 
 static int export_alns(cdg_ctx *ctx, cdg_alns *out) {
-    const u64 M = ctx->nLines, n = ctx->n;
+    const u64 M = ctx->nLines, n = ctx->nQ;
     CK(ctx->hLineOff.reserve((n + 1) * 8)); CK(ctx->hLineT.reserve((M + 1) * 4)); CK(ctx->hKeep.reserve(M + 1)); CK(ctx->hScore.reserve((M + 1) * 4));
     CK(ctx->hBits.reserve((M + 1) * 4)); CK(ctx->hEvalue.reserve((M + 1) * 8)); CK(ctx->hSeqId.reserve((M + 1) * 4)); CK(ctx->hQS.reserve((M + 1) * 4));
     CK(ctx->hQE.reserve((M + 1) * 4)); CK(ctx->hDS.reserve((M + 1) * 4)); CK(ctx->hDE.reserve((M + 1) * 4));
@@ -595,14 +701,14 @@ extern "C" int cdg_set_alignments(cdg_ctx *ctx, const uint64_t *aln_off, uint64_
         CK(cudaMemsetAsync(ctx->dKeep.p, 1, n_alns, ctx->st));
     }
     CK(cudaStreamSynchronize(ctx->st));
-    ctx->nLines = n_alns; ctx->linesValid = false; ctx->hitsValid = false; ctx->alnsValid = true; ctx->alnsFromText = true;
+    ctx->nLines = n_alns; ctx->linesValid = false; ctx->hitsValid = false; ctx->alnsValid = true; ctx->alnsFromText = true; ctx->qLo = 0; ctx->nQ = ctx->n;
     return CDG_OK;
 }
 
 static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data, uint64_t *n_changed, double *lik) {
     if (!ctx->alnsValid) return fail(ctx, CDG_ERR_ARG, "cdg_correct: no alignments (run cdg_rescore or cdg_set_alignments)");
     if (!ctx->damageSet) return fail(ctx, CDG_ERR_ARG, "cdg_correct: cdg_set_damage not called");
-    const u64 n = ctx->n;
+    const u64 n = ctx->nQ, qLo = ctx->qLo;
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
     CK(ctx->dOut.reserve(ctx->dataBytes + 64));
     CK(cudaMemsetAsync(sc + SC_CHANGED, 0, 8, ctx->st));
@@ -615,19 +721,19 @@ static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data
         dLik = ctx->dLik.as<double>();
     }
     cdgalign::CorrParams C; C.seqIdThr = p->min_seqid_corr_reads; C.ryThr = p->min_ryseq_id_corr_reads; C.roundSeqId = ctx->alnsFromText ? 0 : 1; C.wideThreshold = ctx->wideThreshold;
-    const u64 wideCap = ctx->wideThreshold < 65535 ? n + 16 : (ctx->nLines >> 16) + 16;
+    const u64 wideCap = ctx->wideThreshold < 65535 ? ctx->n + 16 : (ctx->nLines >> 16) + 16;
     CK(ctx->dWideList.reserve(wideCap * 4));
     CK(cudaMemsetAsync(sc + SC_WIDE, 0, 8, ctx->st));
     const int blocks = ctx->smCount * 4;
     cdgalign::correct_fast_kernel<<<blocks, cdgalign::CF_WARPS * 32, sizeof(cdgalign::CorrSmem), ctx->st>>>(
-        ctx->dData.as<u8>(), ctx->dMeta.as<cdgalign::SeqMeta>(), ctx->dWords.as<u64>(), n, ctx->dLineOff.as<u64>(), ctx->dLineT.as<u32>(), ctx->dKeep.as<u8>(), ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(),
+        ctx->dData.as<u8>(), ctx->dMeta.as<cdgalign::SeqMeta>(), ctx->dWords.as<u64>(), qLo, n, ctx->dLineOff.as<u64>(), ctx->dLineT.as<u32>(), ctx->dKeep.as<u8>(), ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(),
         ctx->dQE.as<i32>(), ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), C, ctx->dTables.as<cdgalign::DamageTables>(), ctx->dLineSel.as<u8>(),
         ctx->dOut.as<u8>(), sc + SC_CHANGED, ctx->dLikOff.as<u64>(), dLik, ctx->dWideList.as<u32>(), (u32 *) (sc + SC_WIDE));
     ctx->launches++;
     // queries with more than 65535 counted targets (16-bit counters): generic kernel, usually an empty list
     cdgalign::correct_wide_kernel<<<ctx->smCount, cdgalign::CORR_WARPS * 32, 0, ctx->st>>>(
         ctx->dWideList.as<u32>(), (const u32 *) (sc + SC_WIDE),
-        ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dExt.as<u8>(), n, ctx->dLineOff.as<u64>(), ctx->dLineT.as<u32>(),
+        ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dExt.as<u8>(), qLo, n, ctx->dLineOff.as<u64>(), ctx->dLineT.as<u32>(),
         ctx->dKeep.as<u8>(), ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(), ctx->dQE.as<i32>(), ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), C,
         ctx->dTables.as<cdgalign::DamageTables>(), ctx->dLineSel.as<u8>(), ctx->dOut.as<u8>(), sc + SC_CHANGED, ctx->dLikOff.as<u64>(), dLik);
     ctx->launches++;
@@ -679,6 +785,195 @@ extern "C" int cdg_get_stats(cdg_ctx *ctx, cdg_stats *out) {
     cudaStreamSynchronize(ctx->st);
     out->ms_extract = el(EV_START, EV_EXTRACT); out->ms_sort1 = el(EV_EXTRACT, EV_SORT1); out->ms_group = el(EV_SORT1, EV_GROUP);
     out->ms_sort2 = el(EV_GROUP, EV_SORT2); out->ms_reduce = el(EV_SORT2, EV_REDUCE); out->ms_rescore = el(EV_RS0, EV_RS1); out->ms_correct = el(EV_CO0, EV_CO1);
+    return CDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Multi-GPU phases (one context per rank, the whole sequence set resident on every rank).  The caller moves the
+// buffers between ranks (NCCL all-to-all over NVLink through torch.distributed, see carpedeam_b200/multigpu.py):
+//   phase 1  cdg_mg_extract    k-mers of this rank's slice of the sequences, partitioned by owner of the hash range
+//            -> all-to-all of 16-byte records (the single data-carrying collective north_star names)
+//   phase 2  cdg_mg_sort       identity records of the owned hash range (local), sort 1; returns the smallest key
+//            -> the ranks compare their minima (8 bytes each): only the global first run gets the kmermatcher.cpp:466 quirk
+//   phase 3  cdg_mg_group      group assignment, grouped records routed to the owner of the representative's index range
+//            -> all-to-all of 8-byte grouped records (replaces the reference's host k-way merge of split files)
+//   phase 4  cdg_mg_sort2      sort 2; the first records (same target id) go to the previous rank for the rep-boundary bleed
+//   phase 5  cdg_mg_finish     reduce, rescore, correct for the rank's query range
+extern "C" int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world, int rank, uint64_t *send_counts, void **send_keys, void **send_vals) {
+    if (!ctx || !p || !send_counts || world < 1 || world > CDG_MAX_WORLD || rank < 0 || rank >= world) return CDG_ERR_ARG;
+    if (ctx->n == 0) return fail(ctx, CDG_ERR_ARG, "cdg_mg_extract: no sequence set uploaded");
+    CK(cudaSetDevice(ctx->device));
+    KmPlan K; K.world = (u32) world; K.rank = (u32) rank;
+    int rc = km_bits(ctx, p, K);
+    if (rc) return rc;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    CK(cudaMemsetAsync(sc, 0, SC_N * 8, ctx->st));
+    if ((rc = km_prepare(ctx, p, K))) return rc;
+    ctx->plan = K; ctx->qLo = K.qLo; ctx->nQ = K.nQ;
+    const u64 R = K.slots;
+    if (R > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "slice has too many k-mer records for one sort");
+    CK(ctx->dKeysA.reserve((R + 1) * 8)); CK(ctx->dKeysB.reserve((R + 1) * 8)); CK(ctx->dValsA.reserve((R + 1) * 8)); CK(ctx->dValsB.reserve((R + 1) * 8));
+    CK(ctx->dIdKeysA.reserve(ctx->n * 8)); CK(ctx->dIdKeysB.reserve(ctx->n * 8)); CK(ctx->dIdValsA.reserve(ctx->n * 8)); CK(ctx->dIdValsB.reserve(ctx->n * 8));
+    // all hash values of the slice's sequences; identity records are produced locally in phase 2
+    if ((rc = km_extract(ctx, p, K, ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), 0, false, 0, 65535))) return rc;
+    // partition by owner: one stable radix pass over the owner bits of the VALUE word (roles of the arrays swapped)
+    u64 *pv = ctx->dValsA.as<u64>(), *pk = ctx->dKeysA.as<u64>();
+    for (int o = 0; o < world; o++) send_counts[o] = 0;
+    if (R) {
+        cdgsort::Workspace ws;
+        if ((rc = sort_ws(ctx, std::max<u64>(R, ctx->n), ws))) return rc;
+        const int ownerBits = std::max(1, ceil_log2((u64) world));
+        cdgsort::Plan plan = cdgsort::make_plan(0, 0, CDG_OWNER_SHIFT, CDG_OWNER_SHIFT + ownerBits);
+        int l = cdgsort::radix_sort(ctx->st, ws, ctx->dValsA.as<u64>(), ctx->dValsB.as<u64>(), ctx->dKeysA.as<u64>(), ctx->dKeysB.as<u64>(), R, plan, &pv, &pk, ctx->smCount);
+        if (l < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "owner partition failed");
+        ctx->launches += l;
+        unsigned long long hoff[cdgsort::RADIX];
+        CK(cudaMemcpyAsync(hoff, ws.hist, sizeof hoff, cudaMemcpyDeviceToHost, ctx->st));   // exclusive bin offsets of the single pass
+        CK(cudaStreamSynchronize(ctx->st));
+        for (int o = 0; o < world; o++) send_counts[o] = (o + 1 < cdgsort::RADIX ? hoff[o + 1] : R) - hoff[o];
+        u64 acc = 0; for (int o = 0; o < world - 1; o++) acc += send_counts[o];
+        send_counts[world - 1] = R - acc;
+    }
+    CKL();
+    *send_keys = pk; *send_vals = pv;
+    return CDG_OK;
+}
+
+// receive area for `total` routed records; returns device pointers the exchange writes into
+extern "C" int cdg_mg_recv_records(cdg_ctx *ctx, uint64_t total, void **recv_keys, void **recv_vals) {
+    if (!ctx || !recv_keys || !recv_vals) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const u64 cap = total + ctx->plan.extraCap + 1;
+    CK(ctx->dRecvK.reserve(cap * 8)); CK(ctx->dRecvV.reserve(cap * 8));
+    ctx->mgRecv = total;
+    *recv_keys = ctx->dRecvK.p; *recv_vals = ctx->dRecvV.p;
+    return CDG_OK;
+}
+
+extern "C" int cdg_mg_sort(cdg_ctx *ctx, const cdg_kmer_params *p, uint64_t *min_key) {
+    if (!ctx || !p || !min_key) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    using namespace cdgkmer;
+    const KmPlan &K = ctx->plan;
+    const u64 total = ctx->mgRecv, Rtot = total + K.extraCap, n = ctx->n;
+    if (Rtot > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "too many routed records for one sort");
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    int rc;
+    // the send buffers of phase 1 are free now: they become the ping-pong partners of the receive area
+    CK(ctx->dKeysB.reserve(Rtot * 8)); CK(ctx->dValsB.reserve(Rtot * 8));
+    CK(cudaMemsetAsync(ctx->dRecvK.as<u64>() + total, 0xFF, (size_t) K.extraCap * 8, ctx->st));
+    CK(cudaMemsetAsync(ctx->dRecvV.as<u64>() + total, 0, (size_t) K.extraCap * 8, ctx->st));
+    ExtractParams E; E.k = p->k; E.kmersPerSeq = p->kmers_per_seq; E.scale = p->kmers_per_seq_scale; E.seed = p->hash_shift;
+    E.hashLo = K.hashLo; E.hashHi = K.hashHi; E.world = K.world; E.posLo = 0; E.posHi = (u32) n; E.slotBase = 0; E.identity = 1;
+    identity_kernel<<<ctx->smCount * 16, 256, 0, ctx->st>>>(ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), n, E,
+                                                         ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), ctx->dRecvK.as<u64>(), ctx->dRecvV.as<u64>(), total,
+                                                         K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>());
+    ctx->launches++;
+    CKL();
+    u64 mk = 0;
+    if ((rc = km_sort_group(ctx, p, K, ctx->dRecvK.as<u64>(), ctx->dKeysB.as<u64>(), ctx->dRecvV.as<u64>(), ctx->dValsB.as<u64>(), Rtot, -1, &mk, nullptr))) return rc;
+    *min_key = mk;
+    return CDG_OK;
+}
+
+// has_global_first_run: this rank's smallest key is the smallest of all ranks (ties: lowest rank)
+extern "C" int cdg_mg_group(cdg_ctx *ctx, const cdg_kmer_params *p, int has_global_first_run, uint64_t *send_counts, void **send_key2) {
+    if (!ctx || !p || !send_counts || !send_key2) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    using namespace cdgkmer;
+    const KmPlan &K = ctx->plan;
+    const u64 Rtot = ctx->mgRecv + K.extraCap;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    int rc;
+    u64 R2 = 0;
+    // identity hashes are >= 4^k: the identity array can only hold the global first run if no rank has any k-mer record
+    if ((rc = km_group(ctx, p, K, Rtot, has_global_first_run != 0, false, &R2))) return rc;
+    ctx->nGrouped = R2;
+    // route to the owner of the representative's index range
+    const int repShift = K.idBits + K.diagBits + 1;
+    unsigned long long *counts = sc + SC_ROUTE;
+    CK(cudaMemsetAsync(counts, 0, 16 * 8, ctx->st));
+    unsigned long long hc[16] = {0};
+    if (R2) {
+        const int blocks = (int) std::min<u64>((R2 + 255) / 256, (u64) ctx->smCount * 16);
+        route_count_kernel<<<blocks, 256, 0, ctx->st>>>(ctx->dKey2A.as<u64>(), R2, repShift, K.repChunk, K.world, counts);
+        CK(cudaMemcpyAsync(hc, counts, 16 * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        unsigned long long cur[16], acc = 0;
+        for (u32 o = 0; o < 16; o++) { cur[o] = acc; acc += o < K.world ? hc[o] : 0; }
+        CK(cudaMemcpyAsync(counts, cur, 16 * 8, cudaMemcpyHostToDevice, ctx->st));
+        route_scatter_kernel<<<blocks, 256, 0, ctx->st>>>(ctx->dKey2A.as<u64>(), R2, repShift, K.repChunk, K.world, counts, ctx->dKey2B.as<u64>());
+        ctx->launches += 2;
+        CKL();
+    }
+    for (u32 o = 0; o < K.world; o++) send_counts[o] = hc[o];
+    CK(cudaStreamSynchronize(ctx->st));
+    *send_key2 = ctx->dKey2B.p;
+    return CDG_OK;
+}
+
+extern "C" int cdg_mg_recv_grouped(cdg_ctx *ctx, uint64_t total, void **recv_key2) {
+    if (!ctx || !recv_key2) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    // dKey2A (group output, already scattered to dKey2B) is reused as the receive area; the exchange reads dKey2B
+    CK(ctx->dRecv2.reserve((total + CDG_HEAD_RUN + 1) * 8));
+    ctx->mgR2 = total;
+    *recv_key2 = ctx->dRecv2.p;
+    return CDG_OK;
+}
+
+// sorts the received grouped records; *sorted points at the sorted array, which has CDG_HEAD_RUN spare records after
+// `total` for the next rank's head run; *head_count = number of leading records that share the first record's target id
+extern "C" int cdg_mg_sort2(cdg_ctx *ctx, void **sorted, uint64_t *head_count, uint64_t *head_capacity) {
+    if (!ctx || !sorted || !head_count) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const KmPlan &K = ctx->plan;
+    const u64 R2 = ctx->mgR2;
+    int rc;
+    CK(ctx->dKey2A.reserve((R2 + CDG_HEAD_RUN + 1) * 8)); CK(ctx->dKey2B.reserve((R2 + CDG_HEAD_RUN + 1) * 8));
+    CK(cudaMemcpyAsync(ctx->dKey2A.p, ctx->dRecv2.p, R2 * 8, cudaMemcpyDeviceToDevice, ctx->st));
+    if ((rc = km_sort2(ctx, K, R2))) return rc;
+    // head run on the host: first min(R2, CDG_HEAD_RUN) keys, count the prefix with the first record's target id
+    std::vector<u64> head(std::min<u64>(R2, CDG_HEAD_RUN));
+    if (!head.empty()) CK(cudaMemcpyAsync(head.data(), ctx->sortedKey2, head.size() * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    u64 hcnt = 0;
+    if (!head.empty()) {
+        const u64 idMask = (1ull << K.idBits) - 1;
+        const u32 id0 = (u32) ((head[0] >> (K.diagBits + 1)) & idMask);
+        while (hcnt < head.size() && (u32) ((head[hcnt] >> (K.diagBits + 1)) & idMask) == id0) hcnt++;
+    }
+    *sorted = ctx->sortedKey2; *head_count = hcnt;
+    if (head_capacity) *head_capacity = CDG_HEAD_RUN;
+    return CDG_OK;
+}
+
+// n_appended records of the next rank's head run have been written behind the rank's own sorted records
+extern "C" int cdg_mg_finish(cdg_ctx *ctx, const cdg_rescore_params *rp, const cdg_corr_params *cp, uint64_t n_appended, cdg_hits *hits, cdg_alns *alns,
+                             uint8_t *out_range, uint64_t *range_offset, uint64_t *range_bytes, uint64_t *n_changed) {
+    if (!ctx || !rp || !cp) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const KmPlan &K = ctx->plan;
+    const u64 R2 = ctx->mgR2;
+    if (n_appended > CDG_HEAD_RUN) return fail(ctx, CDG_ERR_ARG, "cdg_mg_finish: head run longer than the reserved area");
+    int rc;
+    if ((rc = km_reduce(ctx, K, R2, R2 + n_appended))) return rc;
+    if (hits && (rc = export_hits(ctx, hits))) return rc;
+    if ((rc = run_rescore(ctx, rp))) return rc;
+    if (alns && (rc = export_alns(ctx, alns))) return rc;
+    if (!alns) { u64 kept = 0; if ((rc = read_scalar(ctx, SC_KEPT, &kept))) return rc; ctx->nKept = kept; }
+    if ((rc = run_correct(ctx, cp, nullptr, n_changed, nullptr))) return rc;
+    // corrected bytes of the rank's query range
+    u64 b0 = 0, b1 = ctx->dataBytes;
+    if (K.nQ) {
+        CK(cudaMemcpyAsync(&b0, ctx->dOff.as<u64>() + K.qLo, 8, cudaMemcpyDeviceToHost, ctx->st));
+        if (K.qLo + K.nQ < ctx->n) CK(cudaMemcpyAsync(&b1, ctx->dOff.as<u64>() + K.qLo + K.nQ, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+    } else b0 = b1 = 0;
+    if (range_offset) *range_offset = b0;
+    if (range_bytes) *range_bytes = b1 - b0;
+    if (out_range && b1 > b0) CK(cudaMemcpyAsync(out_range, ctx->dOut.as<u8>() + b0, b1 - b0, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
     return CDG_OK;
 }
 

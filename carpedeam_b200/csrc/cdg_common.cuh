@@ -102,6 +102,8 @@ CDG_HD double cdg_bitscore(double score) {
 // ---- record value packing -----------------------------------------------------------------------
 // k-mer record = {key u64: canonical k-mer | bit63 (1 = forward, 0 = reverse complement picked),
 //                 val u64: id:32 | pos:32}  (KmerPosition, kmermatcher.h:49-54; seqLen is looked up by id)
-CDG_HD u64 cdg_pack_val(u32 id, u32 pos) { return ((u64) id << 32) | pos; }
+// (multi-GPU: bits 28-31 of the value carry the owner rank of the k-mer's hash range until the records are routed)
+static constexpr int CDG_OWNER_SHIFT = 28;
+CDG_HD u64 cdg_pack_val(u32 id, u32 pos, u32 owner = 0) { return ((u64) id << 32) | ((u64) owner << CDG_OWNER_SHIFT) | pos; }
 CDG_HD u32 cdg_val_id(u64 v) { return (u32) (v >> 32); }
-CDG_HD u32 cdg_val_pos(u64 v) { return (u32) v; }
+CDG_HD u32 cdg_val_pos(u64 v) { return (u32) v & ((1u << CDG_OWNER_SHIFT) - 1); }

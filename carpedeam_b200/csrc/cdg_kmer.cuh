@@ -74,7 +74,12 @@ CDG_D int base_code(const u64 *__restrict__ w, const u32 *__restrict__ xm, u32 p
 
 struct ExtractParams {
     int k; int kmersPerSeq; float scale; u64 seed; u32 hashLo, hashHi;
+    // multi-GPU slice: this call extracts the sequences whose (length desc, id asc) rank lies in [posLo, posHi), tags
+    // every record with the owner of its hash (hash16 * world >> 16), writes slots relative to slotBase and leaves the
+    // identity records to identity_kernel.  Single GPU: world = 1, posLo = 0, posHi = n, slotBase = 0, identity = 1.
+    u32 world, posLo, posHi; u64 slotBase; int identity;
 };
+CDG_D u32 owner_of(u32 score, u32 world) { return (score * world) >> 16; }
 // slots reserved for sequence of length L: upper bound of selected k-mers (kmermatcher.cpp:226)
 CDG_HD u32 kmer_capacity(u32 L, int k, int kmersPerSeq, float scale) {
     u32 W = L >= (u32) k ? L - k + 1 : 0;
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) emit_identity(cdg_xxh64_u64(part, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow, rankOf);
+        if (lane == 0 && P.identity) emit_identity(cdg_xxh64_u64(part, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow, rankOf);
 
         // windows: lane handles p = lane + 32*it
         WinRec rec[ITERS];
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
         __syncwarp();
         collide = __any_sync(0xffffffffu, collide);
 
-        const u64 slot0 = slotOff[seq];
+        const u64 slot0 = slotOff[seq] - P.slotBase;
         const u32 cap = kmer_capacity(L, P.k, P.kmersPerSeq, P.scale);
         u32 written = 0;   // warp-uniform
         if (!collide) {
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
                 if (own) {
                     u64 dst = slot0 + written + __popc(b & ((1u << lane) - 1));
                     mainKeys[dst] = rec[it].kmer;
-                    mainVals[dst] = cdg_pack_val((u32) seq, rec[it].pos);
+                    mainVals[dst] = cdg_pack_val((u32) seq, rec[it].pos, owner_of(rec[it].score, P.world));
                 }
                 written += __popc(b);
             }
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
                 if (own) {
                     u64 dst = slot0 + written + __popc(b & ((1u << lane) - 1));
                     mainKeys[dst] = sorted[i].kmer;
-                    mainVals[dst] = cdg_pack_val((u32) seq, sorted[i].pos);
+                    mainVals[dst] = cdg_pack_val((u32) seq, sorted[i].pos, owner_of(sorted[i].score, P.world));
                 }
                 written += __popc(b);
             }
@@ -317,6 +322,7 @@ __global__ void __launch_bounds__(EXL_BLOCK) extract_long_kernel(
 
     for (u32 li = blockIdx.x; li < nLong; li += gridDim.x) {
         const u64 seq = longList[li];
+        { const u32 r = rankOf[seq]; if (r < P.posLo || r >= P.posHi) continue; }   // block-uniform
         const u32 L = len[seq];
         const u64 *w = words + wordOff[seq];
         const u32 *xm = xmask + wordOff[seq];
@@ -346,7 +352,7 @@ __global__ void __launch_bounds__(EXL_BLOCK) extract_long_kernel(
         if (tid == 0) {
             u64 h = 0;
             for (int i = 0; i < EXL_BLOCK / 32; i++) h += sHash[i];
-            emit_identity(cdg_xxh64_u64(h, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow, rankOf);
+            if (P.identity) emit_identity(cdg_xxh64_u64(h, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow, rankOf);
             u32 cnt = sCnt;
             float consF = (float) (P.kmersPerSeq - 1) + P.scale * (float) L;
             u64 cons64 = consF > 0.f ? (u64) consF : 0;
@@ -397,7 +403,7 @@ __global__ void __launch_bounds__(EXL_BLOCK) extract_long_kernel(
         }
         if (tid == 0) select_sequential(cand, nc, sConsidered, threshold, sTooMuch, keep);
         __syncthreads();
-        const u64 slot0 = slotOff[seq];
+        const u64 slot0 = slotOff[seq] - P.slotBase;
         const u32 cap = kmer_capacity(L, P.k, P.kmersPerSeq, P.scale);
         for (u32 base = 0; base < nc; base += EXL_BLOCK) {
             u32 i = base + tid;
@@ -409,7 +415,7 @@ __global__ void __launch_bounds__(EXL_BLOCK) extract_long_kernel(
             if (own) {
                 u64 dst = slot0 + wbase + __popc(b & ((1u << lane) - 1));
                 mainKeys[dst] = cand[i].kmer;
-                mainVals[dst] = cdg_pack_val((u32) seq, cand[i].pos);
+                mainVals[dst] = cdg_pack_val((u32) seq, cand[i].pos, owner_of(cand[i].score, P.world));
             }
         }
         __syncthreads();
@@ -417,6 +423,65 @@ __global__ void __launch_bounds__(EXL_BLOCK) extract_long_kernel(
         for (u32 s = written + tid; s < cap; s += EXL_BLOCK) { mainKeys[slot0 + s] = CDG_SENTINEL; mainVals[slot0 + s] = 0; }
         if (tid == 0 && written) atomicAdd(emitted, (unsigned long long) written);
         __syncthreads();
+    }
+}
+
+// identity records of ALL sequences whose hash falls into [hashLo, hashHi] (multi-GPU: every rank holds the whole
+// sequence set, so no exchange is needed for them); one warp per sequence.
+__global__ void __launch_bounds__(256) identity_kernel(const u64 *__restrict__ words, const u32 *__restrict__ xmask, const u64 *__restrict__ wordOff,
+                                                       const u32 *__restrict__ len, u64 n, ExtractParams P, u64 *__restrict__ idKeys,
+                                                       u64 *__restrict__ idVals, u64 *__restrict__ mainKeys, u64 *__restrict__ mainVals, u64 extraBase,
+                                                       u32 extraCap, u32 *extraCount, u32 *overflow, const u32 *__restrict__ rankOf) {
+    const int lane = threadIdx.x & 31;
+    const u64 gwarp = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64) gridDim.x * blockDim.x) >> 5;
+    for (u64 seq = gwarp; seq < n; seq += nwarps) {
+        const u32 L = len[seq];
+        const u64 *w = words + wordOff[seq];
+        const u32 *xm = xmask + wordOff[seq];
+        u64 part = 0;
+        const u32 c = (L + 31) >> 5;
+        const u32 b0 = lane * c, b1 = min(b0 + c, L);
+        if (b0 < L) {
+            u64 h = 0;
+            for (u32 p = b0; p < b1; p++) h = h * 31 + (u64) base_code(w, xm, p);
+            part = h * pow31(L - b1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) emit_identity(cdg_xxh64_u64(part, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow, rankOf);
+    }
+}
+
+// routing of grouped records to the rank that owns the representative (rep index ranges of width repChunk):
+// count, then unordered scatter (sort 2 follows on the receiver)
+__global__ void __launch_bounds__(256) route_count_kernel(const u64 *__restrict__ key2, u64 n, int repShift, u32 repChunk, u32 world,
+                                                          unsigned long long *__restrict__ counts) {
+    __shared__ u32 sc[16];
+    if (threadIdx.x < 16) sc[threadIdx.x] = 0;
+    __syncthreads();
+    for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) {
+        u32 o = (u32) (key2[i] >> repShift) / repChunk; if (o >= world) o = world - 1;
+        atomicAdd(&sc[o], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < world && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long) sc[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) route_scatter_kernel(const u64 *__restrict__ key2, u64 n, int repShift, u32 repChunk, u32 world,
+                                                            unsigned long long *__restrict__ cursors /*[world], start = segment offsets*/,
+                                                            u64 *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    for (u64 base = (u64) blockIdx.x * blockDim.x; base < n; base += (u64) gridDim.x * blockDim.x) {
+        const u64 i = base + threadIdx.x;
+        u32 o = 0xFFFFFFFFu; u64 k = 0;
+        if (i < n) { k = key2[i]; o = (u32) (k >> repShift) / repChunk; if (o >= world) o = world - 1; }
+        for (u32 w = 0; w < world; w++) {   // warp-aggregated append per owner
+            const u32 b = __ballot_sync(0xffffffffu, o == w);
+            if (!b) continue;
+            unsigned long long pos = 0;
+            if (lane == (__ffs(b) - 1)) pos = atomicAdd(&cursors[w], (unsigned long long) __popc(b));
+            pos = __shfl_sync(0xffffffffu, pos, __ffs(b) - 1);
+            if (o == w) out[pos + __popc(b & ((1u << lane) - 1))] = k;
+        }
     }
 }
 
@@ -557,8 +622,9 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
 struct ReduceParams { int idBits, diagBits; i32 diagBias; };
 // flag = last record of a (rep,target) pair with target != rep: one hit each, in sorted (= pref DB) order
 struct PairEndFlag {
-    const u64 *keys; u64 n; int idBits, diagBits;
+    const u64 *keys; u64 n; int idBits, diagBits; u64 nOwn;   // records [nOwn, n) are a neighbour's head run: walked, never emitted
     CDG_D u32 operator()(u64 i) const {
+        if (i >= nOwn) return 0;
         const u64 pair = keys[i] >> (diagBits + 1);
         if (i + 1 < n && (keys[i + 1] >> (diagBits + 1)) == pair) return 0;
         const u32 id = (u32) (pair & ((1ull << idBits) - 1)), rep = (u32) (pair >> idBits);
@@ -695,7 +761,7 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(PairEndFlag f, Reduce
 #pragma unroll
     for (int j = 0; j < RED_ITEMS; j++) {
         const u32 li = first + j;
-        if (li < tileN && (pairEnds & (1u << j))) {
+        if (li < tileN && (pairEnds & (1u << j)) && base + li < f.nOwn) {
             const u64 pair = sKey[li + 1] >> pairShift;
             if ((u32) (pair & idMask) != (u32) (pair >> R.idBits)) flags |= 1u << j;
         }

@@ -156,6 +156,24 @@ typedef struct {
 int cdg_iteration(cdg_ctx *ctx, const cdg_iter_params *p, cdg_hits *hits, cdg_alns *alns, uint8_t *out_data,
                   uint64_t *n_changed);
 
+/* ---- multi-GPU phases ------------------------------------------------------------
+ * One context per rank, the whole sequence set uploaded on every rank.  K-mer records are owned by hash range like
+ * kmermatcher's split passes (kmermatcher.cpp:742-784): rank r owns hash16 in [r*65536/world, (r+1)*65536/world).
+ * The caller exchanges the device buffers between the phases (carpedeam_b200/multigpu.py, NCCL through torch.distributed):
+ *   cdg_mg_extract  -> all-to-all of the 16-byte records (send_counts[o] records for rank o, contiguous, in rank order)
+ *   cdg_mg_recv_records / cdg_mg_sort -> min key of the rank (the ranks compare 8 bytes each: first-run quirk, :466)
+ *   cdg_mg_group    -> all-to-all of the 8-byte grouped records to the rank owning the representative's index range
+ *   cdg_mg_recv_grouped / cdg_mg_sort2 -> the leading records with one target id go to rank-1 (rep-boundary bleed, :886-888)
+ *   cdg_mg_finish   -> hits, alignments and corrected bytes of the rank's query range [rank*ceil(n/world), ...) */
+int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world, int rank, uint64_t *send_counts, void **send_keys, void **send_vals);
+int cdg_mg_recv_records(cdg_ctx *ctx, uint64_t total, void **recv_keys, void **recv_vals);
+int cdg_mg_sort(cdg_ctx *ctx, const cdg_kmer_params *p, uint64_t *min_key);
+int cdg_mg_group(cdg_ctx *ctx, const cdg_kmer_params *p, int has_global_first_run, uint64_t *send_counts, void **send_key2);
+int cdg_mg_recv_grouped(cdg_ctx *ctx, uint64_t total, void **recv_key2);
+int cdg_mg_sort2(cdg_ctx *ctx, void **sorted, uint64_t *head_count, uint64_t *head_capacity);
+int cdg_mg_finish(cdg_ctx *ctx, const cdg_rescore_params *rp, const cdg_corr_params *cp, uint64_t n_appended, cdg_hits *hits, cdg_alns *alns,
+                  uint8_t *out_range, uint64_t *range_offset, uint64_t *range_bytes, uint64_t *n_changed);
+
 /* ---- measurement ------------------------------------------------------------------------------ */
 typedef struct {
     uint64_t n_seqs, n_bases;           /* N, S */
