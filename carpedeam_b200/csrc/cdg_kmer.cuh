@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
     for (u64 seq = gwarp; seq < n; seq += nwarps) {
         const u32 L = len[seq];
         if (!is_short_seq(L, P.k, P.kmersPerSeq, P.scale)) continue;   // handled by extract_long_kernel
+        { const u32 r = rankOf[seq]; if (r < P.posLo || r >= P.posHi) continue; }   // not in this rank's slice
         const u64 *w = words + wordOff[seq];
         const u32 *xm = xmask + wordOff[seq];
         const u32 W = L >= (u32) P.k ? L - P.k + 1 : 0;

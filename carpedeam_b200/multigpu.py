@@ -1,0 +1,174 @@
+"""Multi-GPU iteration: one process per GPU, k-mer records owned by hash range (kmermatcher's split scheme,
+kmermatcher.cpp:742-784), exchanged with NCCL all-to-all over NVLink through torch.distributed.
+
+Plumbing only — every kernel lives in libcarpedeam_gpu.so (cdg_mg_* phases).  The exchange plan is written against a tiny
+`Comm` interface so that the host logic (split sizes, ordering by source rank, ring shift of the head run, first-run
+decision) is testable on CPU with gloo (tests/test_multigpu_host.py).
+
+Per iteration:
+  1. cdg_mg_extract      -> all_to_all of (key, value) records             [the data all-to-all north_star names]
+  2. cdg_mg_sort         -> all_gather of one u64 per rank (smallest key)  [first-run quirk, kmermatcher.cpp:466]
+  3. cdg_mg_group        -> all_to_all of 8-byte grouped records to the rank owning the representative
+                            (on-device replacement of the reference's host k-way merge of split files, :953-1111)
+  4. cdg_mg_sort2        -> head run (<= 4096 records) to rank-1           [rep-boundary bleed, :886-888]
+  5. cdg_mg_finish       -> hits / alignments / corrected bytes of the rank's query range
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import Alns, CorrParams, Hits, RescoreParams, lib, kmer_params
+
+SENTINEL = 0xFFFFFFFFFFFFFFFF
+
+
+class DevArray:
+    """zero-copy view of library-owned device memory for torch (`torch.as_tensor(DevArray(...), device='cuda')`)."""
+
+    def __init__(self, ptr, n, typestr="<i8"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def owner_hash_range(rank, world):
+    """hash16 values owned by `rank` (owner = hash16 * world >> 16)."""
+    lo = (rank * 65536 + world - 1) // world
+    hi = ((rank + 1) * 65536 + world - 1) // world - 1
+    return lo, hi
+
+
+def split_offsets(counts):
+    off = [0]
+    for c in counts:
+        off.append(off[-1] + int(c))
+    return off
+
+
+class TorchComm:
+    """torch.distributed adapter (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, device):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.device = torch, dist, device
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def exchange_counts(self, send_counts):
+        t = self.torch.tensor([int(c) for c in send_counts], dtype=self.torch.int64, device=self.device)
+        r = self.torch.empty_like(t)
+        self.dist.all_to_all_single(r, t)
+        return [int(x) for x in r.tolist()]
+
+    def all_to_all(self, recv, send, recv_counts, send_counts):
+        self.dist.all_to_all_single(recv, send, output_split_sizes=[int(c) for c in recv_counts], input_split_sizes=[int(c) for c in send_counts])
+
+    def all_gather_u64(self, value):
+        t = self.torch.tensor([np.uint64(value).astype(np.int64)], dtype=self.torch.int64, device=self.device)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [int(np.int64(o.item()).astype(np.uint64)) for o in out]
+
+    def shift_to_prev(self, send, n_send, recv_capacity_tensor):
+        """rank r sends `send[:n_send]` to rank r-1 and receives from rank r+1; returns the received count."""
+        torch, dist = self.torch, self.dist
+        cnt = self.all_gather_u64(n_send)
+        n_recv = cnt[self.rank + 1] if self.rank + 1 < self.world else 0
+        ops = []
+        if self.rank > 0 and n_send > 0:
+            ops.append(dist.P2POp(dist.isend, send[:n_send], self.rank - 1))
+        if n_recv > 0:
+            ops.append(dist.P2POp(dist.irecv, recv_capacity_tensor[:n_recv], self.rank + 1))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return n_recv
+
+
+def first_run_owner(min_keys):
+    """rank holding the globally smallest k-mer key (ties: lowest rank); None if no rank has a record."""
+    best, who = None, None
+    for r, k in enumerate(min_keys):
+        if k == SENTINEL:
+            continue
+        if best is None or k < best:
+            best, who = k, r
+    return who
+
+
+class ShardedIteration:
+    """Drives one context (= one GPU) through the five phases."""
+
+    def __init__(self, ctx, comm):
+        self.ctx, self.comm = ctx, comm
+        L = lib()
+        L.cdg_mg_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.cdg_mg_recv_records.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.cdg_mg_sort.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.cdg_mg_group.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
+        L.cdg_mg_recv_grouped.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        L.cdg_mg_sort2.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.cdg_mg_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
+                                    C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        self.L = L
+
+    def _t(self, ptr, n):
+        torch = self.comm.torch
+        if n == 0:
+            return torch.empty(0, dtype=torch.int64, device=self.comm.device)
+        return torch.as_tensor(DevArray(ptr, n), device=self.comm.device)
+
+    def run(self, kmer=None, rescore=None, corr=None, fetch_hits=False, fetch_alns=False, out_range=None):
+        ctx, comm, L = self.ctx, self.comm, self.L
+        world, rank = comm.world, comm.rank
+        kp = kmer or kmer_params()
+        rp = rescore or RescoreParams(0.9, 0.001, 0)
+        cp = corr or CorrParams(0.9, 0.99)
+        torch = comm.torch
+        # phase 1
+        sc = (C.c_uint64 * world)()
+        sk, sv = C.c_void_p(), C.c_void_p()
+        ctx._ck(L.cdg_mg_extract(ctx._h, C.byref(kp), world, rank, sc, C.byref(sk), C.byref(sv)), "cdg_mg_extract")
+        send_counts = list(sc)
+        recv_counts = comm.exchange_counts(send_counts)
+        total = sum(recv_counts)
+        rk, rv = C.c_void_p(), C.c_void_p()
+        ctx._ck(L.cdg_mg_recv_records(ctx._h, total, C.byref(rk), C.byref(rv)), "cdg_mg_recv_records")
+        nsend = sum(send_counts)
+        comm.all_to_all(self._t(rk.value, total), self._t(sk.value, nsend), recv_counts, send_counts)
+        comm.all_to_all(self._t(rv.value, total), self._t(sv.value, nsend), recv_counts, send_counts)
+        torch.cuda.synchronize()
+        # phase 2
+        mk = C.c_uint64()
+        ctx._ck(L.cdg_mg_sort(ctx._h, C.byref(kp), C.byref(mk)), "cdg_mg_sort")
+        owner = first_run_owner(comm.all_gather_u64(mk.value))
+        # phase 3
+        sc2 = (C.c_uint64 * world)()
+        s2 = C.c_void_p()
+        ctx._ck(L.cdg_mg_group(ctx._h, C.byref(kp), 1 if owner == rank else 0, sc2, C.byref(s2)), "cdg_mg_group")
+        send2 = list(sc2)
+        recv2 = comm.exchange_counts(send2)
+        total2 = sum(recv2)
+        r2 = C.c_void_p()
+        ctx._ck(L.cdg_mg_recv_grouped(ctx._h, total2, C.byref(r2)), "cdg_mg_recv_grouped")
+        comm.all_to_all(self._t(r2.value, total2), self._t(s2.value, sum(send2)), recv2, send2)
+        torch.cuda.synchronize()
+        # phase 4
+        sorted_ptr, head_n, head_cap = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        ctx._ck(L.cdg_mg_sort2(ctx._h, C.byref(sorted_ptr), C.byref(head_n), C.byref(head_cap)), "cdg_mg_sort2")
+        whole = self._t(sorted_ptr.value, total2 + head_cap.value)
+        n_app = comm.shift_to_prev(whole[:total2], int(head_n.value), whole[total2:])
+        torch.cuda.synchronize()
+        # phase 5
+        hits, alns = Hits(), Alns()
+        off, nbytes, changed = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        optr = None
+        if out_range is not None:
+            optr = C.c_void_p(out_range.ctypes.data) if hasattr(out_range, "ctypes") else C.c_void_p(int(out_range))
+        ctx._ck(L.cdg_mg_finish(ctx._h, C.byref(rp), C.byref(cp), n_app, C.byref(hits) if fetch_hits else None, C.byref(alns) if fetch_alns else None,
+                                optr, C.byref(off), C.byref(nbytes), C.byref(changed)), "cdg_mg_finish")
+        res = dict(range_offset=off.value, range_bytes=nbytes.value, changed=changed.value, records_sent=nsend, records_received=total,
+                   grouped_sent=sum(send2), grouped_received=total2, head_appended=n_app)
+        if fetch_hits:
+            res["hits"] = ctx._hits(hits)
+        if fetch_alns:
+            res["alns"] = ctx._alns(alns)
+        return res

@@ -1,0 +1,64 @@
+"""Multi-GPU parity worker (launched by torchrun, one rank per GPU): the sharded iteration must reproduce the single-GPU
+iteration exactly — hits, alignment records and corrected bytes — on the reference's config-1 reads and on synthetic reads."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import carpedeam_b200 as cd
+from carpedeam_b200.multigpu import ShardedIteration, TorchComm
+from support import GOLD, SeqSet, synth_reads
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    comm = TorchComm(torch.device("cuda", local))
+    ctx = cd.Context(local)
+    ctx.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+    cases = [("golden nucl_reads k=20", SeqSet.from_golden("nucl_reads"), cd.kmer_params()),
+             ("golden contigs k=22 ext", SeqSet.from_golden("assembly_contigs_8_noneCycle"), cd.kmer_params(k=22, include_only_extendable=1)),
+             ("synthetic 60k", SeqSet(synth_reads(60000, 300000, 21, n_frac=0.001)), cd.kmer_params())]
+    ok = True
+    for name, s, kp in cases:
+        ctx.upload(s.blob, s.off, s.len, s.ext)
+        out_range = np.zeros(len(s.blob), np.uint8)
+        res = ShardedIteration(ctx, comm).run(kmer=kp, fetch_hits=True, fetch_alns=True, out_range=out_range)
+        parts = [None] * world
+        dist.all_gather_object(parts, dict(hits=res["hits"], alns=res["alns"], off=res["range_offset"], nbytes=res["range_bytes"],
+                                           out=out_range[:res["range_bytes"]].copy(), changed=res["changed"],
+                                           stats={k: res[k] for k in ("records_sent", "records_received", "grouped_sent", "grouped_received", "head_appended")}))
+        if rank == 0:
+            hits, alns, out, changed = ctx.iteration(kmer=kp, fetch_hits=True)
+            for f in ("rep", "tgt", "score", "diag"):
+                got = np.concatenate([p["hits"][f] for p in parts])
+                if not np.array_equal(got, hits[f]):
+                    ok = False; print("MISMATCH", name, "hits", f, len(got), len(hits[f]))
+            for f in ("tgt", "keep", "score", "bits", "qs", "qe", "ds", "de", "seqid"):
+                got = np.concatenate([p["alns"][f] for p in parts])
+                if not np.array_equal(got, alns[f]):
+                    ok = False; print("MISMATCH", name, "alns", f)
+            merged = s.blob.copy()
+            for p in parts:
+                merged[p["off"]:p["off"] + p["nbytes"]] = p["out"]
+            if not np.array_equal(merged, out) or sum(p["changed"] for p in parts) != changed:
+                ok = False; print("MISMATCH", name, "corrected bytes")
+            print("case %-28s world=%d hits=%d changed=%d %s" % (name, world, len(hits["rep"]), changed, [p["stats"] for p in parts]))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    ctx.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTIGPU PARITY", "OK" if ok else "FAILED")
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size-2 gloo processes drive the same Comm adapter the GPU path
+uses (variable-split all-to-all ordered by source rank, u64 all-gather, ring shift of the head run) and the ownership
+arithmetic that must agree with the device code."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from support import ROOT
+
+WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from carpedeam_b200.multigpu import TorchComm, first_run_owner, owner_hash_range, split_offsets, SENTINEL
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+comm = TorchComm(torch.device("cpu"))
+# records: value = source rank * 1e6 + running index, routed by (value %% world); per-source order must survive
+n = 1000 + 37 * rank
+vals = np.arange(n, dtype=np.int64) + rank * 1_000_000
+owner = vals %% world
+order = np.argsort(owner, kind="stable")
+send = torch.from_numpy(vals[order].copy())
+send_counts = [int((owner == o).sum()) for o in range(world)]
+recv_counts = comm.exchange_counts(send_counts)
+recv = torch.empty(sum(recv_counts), dtype=torch.int64)
+comm.all_to_all(recv, send, recv_counts, send_counts)
+got = recv.numpy()
+off = split_offsets(recv_counts)
+for src in range(world):
+    seg = got[off[src]:off[src + 1]]
+    assert np.all(seg // 1_000_000 == src), "segments are ordered by source rank"
+    assert np.all(seg %% world == rank), "every record reached its owner"
+    assert np.all(np.diff(seg) > 0), "order inside a source segment is preserved"
+assert sum(recv_counts) == sum(int(((np.arange(1000 + 37 * r) + r * 1_000_000) %% world == rank).sum()) for r in range(world))
+# u64 all-gather incl. values above 2^63, and the first-run decision
+mine = SENTINEL if rank == 1 else (1 << 63) | 12345
+keys = comm.all_gather_u64(mine)
+assert keys[0] == (1 << 63) | 12345 and keys[1] == SENTINEL
+assert first_run_owner(keys) == 0 and first_run_owner([SENTINEL, SENTINEL]) is None and first_run_owner([7, 7]) == 0
+# ring shift of the head run: rank r sends its first k records to r-1
+buf = torch.arange(10, dtype=torch.int64) + 100 * rank
+tail = torch.zeros(8, dtype=torch.int64)
+k = 3 + rank
+n_recv = comm.shift_to_prev(buf, k, tail)
+if rank + 1 < world:
+    assert n_recv == 3 + rank + 1 and torch.equal(tail[:n_recv], torch.arange(n_recv) + 100 * (rank + 1))
+else:
+    assert n_recv == 0
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_comm_adapter_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29531", str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2
+
+
+def test_hash_ownership_partitions_the_16bit_space():
+    from carpedeam_b200.multigpu import owner_hash_range
+    for world in (1, 2, 3, 4, 8, 16):
+        h = np.arange(65536, dtype=np.uint64)
+        dev_owner = (h * np.uint64(world)) >> np.uint64(16)          # owner_of() in cdg_kmer.cuh
+        covered = np.zeros(65536, bool)
+        for r in range(world):
+            lo, hi = owner_hash_range(r, world)
+            assert np.all(dev_owner[lo:hi + 1] == r)
+            assert not covered[lo:hi + 1].any()
+            covered[lo:hi + 1] = True
+        assert covered.all()
