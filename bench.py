@@ -74,6 +74,53 @@ def synth_reads_fast(n, genome_len, seed, lmin=35, lmax=70, interior=0.01, sub_e
     return dict(blob=blob, off=off, len=lens, n=n, total=total)
 
 
+def synth_reads_torch(n, genome_len, seed, device, lmin=35, lmax=70, interior=0.01, sub_err=0.001, chunk=4_000_000):
+    """Same read model generated on the GPU (torch.Generator, identical on every rank) — used for the multi-GPU runs where
+    the numpy generator would take minutes; returns host numpy arrays in the MMseqs2 data-file layout."""
+    import torch
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    comp = torch.zeros(256, dtype=torch.uint8, device=device)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    genome = acgt[torch.randint(0, 4, (genome_len,), generator=g, device=device)]
+    lens = torch.randint(lmin, lmax + 1, (n,), generator=g, device=device, dtype=torch.int64)
+    off = torch.zeros(n, dtype=torch.int64, device=device)
+    off[1:] = torch.cumsum(lens[:-1] + 2, 0)
+    total = int(lens.sum().item())
+    blob = torch.zeros(total + 2 * n, dtype=torch.uint8, device=device)
+    j = torch.arange(lmax, device=device)[None, :]
+    d5 = torch.tensor(DHIGH5, device=device, dtype=torch.float32); d3 = torch.tensor(DHIGH3, device=device, dtype=torch.float32)
+    for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        L = lens[c0:c0 + m][:, None]
+        start = torch.randint(0, genome_len - lmax, (m, 1), generator=g, device=device)
+        strand = torch.rand((m, 1), generator=g, device=device) < 0.5
+        valid = j < L
+        idx = torch.where(strand, start + L - 1 - j, start + j)
+        idx = torch.where(valid, idx, torch.zeros_like(idx))
+        r = genome[idx]
+        r = torch.where(strand, comp[r.long()], r)
+        p_ct = torch.full((m, lmax), interior, device=device); p_ct[:, :5] = d5
+        dd = L - 1 - j
+        p_ga = torch.where((dd >= 0) & (dd < 5), d3[dd.clamp(0, 4)], torch.full_like(p_ct, interior))
+        u = torch.rand((m, lmax), generator=g, device=device)
+        r = torch.where((r == ord("C")) & (u < p_ct), torch.full_like(r, ord("T")), r)
+        r = torch.where((r == ord("G")) & (u < p_ga), torch.full_like(r, ord("A")), r)
+        e = torch.rand((m, lmax), generator=g, device=device) < sub_err
+        r = torch.where(e, acgt[torch.randint(0, 4, (m, lmax), generator=g, device=device)], r)
+        flat = r[valid]
+        row = torch.repeat_interleave(torch.arange(m, device=device), lens[c0:c0 + m])
+        pos = torch.arange(flat.numel(), device=device) + 2 * row + off[c0]
+        blob[pos] = flat
+        blob[off[c0:c0 + m] + lens[c0:c0 + m]] = ord("\n")
+        del r, u, e, idx, flat, row, pos, p_ct, p_ga
+    out = dict(blob=blob.cpu().numpy(), off=off.cpu().numpy().astype(np.uint64), len=lens.cpu().numpy().astype(np.uint32), n=n, total=total)
+    del blob, genome
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def clocks_sampler(stop, out, dev):
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -260,11 +307,22 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: a CUDA device is required (no CPU fallback)")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    # ---- workload (identical on every rank) ----
-    s = synth_reads_fast(args.reads, args.genome, 20260102)
+        from carpedeam_b200.multigpu import ShardedIteration, TorchComm
+        dist.init_process_group("nccl", device_id=dev)
+    # ---- workload: identical on every rank; weak scaling = world x the single-GPU read set (same coverage) ----
+    n_total = args.reads * world
+    genome = args.genome * world
+    if world == 1:
+        s = synth_reads_fast(n_total, genome, 20260102)
+        data_note = "synthetic (numpy default_rng(20260102))"
+    else:
+        s = synth_reads_torch(n_total, genome, 20260102, dev)
+        data_note = "synthetic (same read model, torch.Generator seed 20260102 on the GPU, %d x the single-GPU set)" % world
+    workload = "synthetic %d merged reads, 35-70 bp, dhigh damage, %d bp genome (BASELINE configs[1]%s)" % (
+        n_total, genome, "" if world == 1 else " x %d, hash-sharded" % world)
     n = s["n"]
     pin = lambda a: torch.from_numpy(a).pin_memory()
     h_blob, h_off, h_len = pin(s["blob"]), pin(s["off"].view(np.int64)), pin(s["len"].view(np.int32))
@@ -273,20 +331,38 @@ def main():
     ctx.set_damage(cd.load_damage(os.path.join(ROOT, "tests", "golden", "dhigh")))
     ip = cd.IterParams(cd.kmer_params(), cd.RescoreParams(0.9, 0.001, 0), cd.CorrParams(0.9, 0.99))
     stream = torch.cuda.ExternalStream(ctx.stream)
+    sharded = ShardedIteration(ctx, TorchComm(dev)) if world > 1 else None
 
     def barrier():
         if world > 1:
-            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
 
     def upload():
         ctx.upload_raw(h_blob.data_ptr(), h_blob.numel(), h_off.data_ptr(), h_len.data_ptr(), 0, n)
 
+    def step_resident():
+        if world == 1:
+            ctx.iteration_raw(ip, None, None, 0)
+        else:
+            last["phase_ms"] = sharded.run()["phase_ms"]
+
+    alns = cd.Alns()
+    last = {}
+
+    def step_e2e():
+        upload()
+        if world == 1:
+            ctx.iteration_raw(ip, None, alns, h_out.data_ptr())
+            last["M"] = alns.n_lines; last["d2h_seq"] = h_blob.numel()
+        else:
+            r = sharded.run(fetch_alns="raw", out_range=h_out.data_ptr())
+            last["M"] = int(r["alns_raw"].n_lines); last["d2h_seq"] = r["range_bytes"]; last["sent"] = r["records_sent"]; last["sent2"] = r["grouped_sent"]
+
     # ---- resident-input timing ----
     upload()
     for _ in range(args.warmup):
-        ctx.iteration_raw(ip, None, None, 0)
+        step_resident()
     samples = []; stop = threading.Event()
     th = threading.Thread(target=clocks_sampler, args=(stop, samples, local)); th.start()
     l0 = ctx.stats()["kernel_launches"]
@@ -294,63 +370,63 @@ def main():
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        ctx.iteration_raw(ip, None, None, 0)
+        step_resident()
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ctx.stats()["kernel_launches"] - l0
     st = ctx.stats()
     # ---- end to end through the C ABI with host buffers ----
-    hits = cd.Hits(); alns = cd.Alns()
-    ctx.upload_raw(h_blob.data_ptr(), h_blob.numel(), h_off.data_ptr(), h_len.data_ptr(), 0, n)
-    ctx.iteration_raw(ip, None, alns, h_out.data_ptr())
+    step_e2e()
     barrier()
     t0 = time.perf_counter()
     f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
     f0.record(stream)
     for _ in range(args.steps):
-        upload()
-        changed = ctx.iteration_raw(ip, None, alns, h_out.data_ptr())
+        step_e2e()
     f1.record(stream)
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     wall_e2e = (time.perf_counter() - t0) * 1e3
     stop.set(); th.join()
-    M = alns.n_lines
+    M = last["M"]
     h2d = int(h_blob.numel() + n * 8 + n * 4)
-    d2h = int(h_blob.numel() + (n + 1) * 8 + M * (4 + 1 + 4 + 4 + 8 + 4 + 16))
-    # max over ranks
+    d2h = int(last["d2h_seq"] + (st["n_seqs"] // world + 1) * 8 + M * (4 + 1 + 4 + 4 + 8 + 4 + 16))
     if world > 1:
-        import torch.distributed as dist
         t = torch.tensor([ms, ms_e2e, wall_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e, wall_e2e = t.tolist()
     ms_step = ms / args.steps
     e2e_ms_step = max(ms_e2e, wall_e2e) / args.steps
-    value = world * n / (ms_step * 1e-3) / 1e6
-    e2e_val = world * n / (e2e_ms_step * 1e-3) / 1e6
+    value = n / (ms_step * 1e-3) / 1e6
+    e2e_val = n / (e2e_ms_step * 1e-3) / 1e6
     peak, peak_src = measured_peak()
-    # roofline of the dominant kernel: one LSD pass of sort 1 reads and writes every 16-byte record once
-    sort_launches = st["sort1_passes"]
-    rec_total = st["n_records"]
-    per_launch_bytes = 2 * 16 * rec_total
-    sort1_ms = st["ms_sort1"]
-    ach = per_launch_bytes * sort_launches / (sort1_ms * 1e-3) / 1e9 if sort1_ms > 0 else 0.0
-    whole = alg_bytes(st, 20) / (ms_step * 1e-3) / 1e9
     line = {"metric": "Mreads/s kmermatch+rescore+correction", "value": value, "unit": "Mreads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8/int64 (+f64 likelihoods)", "data": "synthetic",
-            "config": {"workload": workload, "l2": "inputs larger than L2 (%.1f GB of k-mer records per pass)" % (rec_total * 16 / 1e9),
-                       "parallelism": "replicas" if world > 1 else "single GPU"},
+            "dtype": "u8/int64 (+f64 likelihoods)", "data": data_note,
+            "config": {"workload": workload, "l2": "inputs larger than L2 (k-mer records of one pass: GBs)",
+                       "parallelism": "single GPU" if world == 1 else "k-mer records owned by hash range, %d ranks, NCCL all-to-all" % world},
             "e2e": {"value": e2e_val, "unit": "Mreads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_step},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "cdgsort::onesweep_kernel<true> (sort 1, %d passes incl. histogram+identity sort)" % sort_launches,
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                         "whole_iteration_alg_GBps": whole, "whole_iteration_frac": whole / peak},
-            "stage_ms": {k: st[k] for k in st if k.startswith("ms_")},
-            "counters": {k: st[k] for k in ("n_seqs", "n_bases", "n_records", "n_grouped", "n_hits", "n_alns", "sort1_passes", "sort2_passes")},
-            "clocks": clocks_summary(samples)}
-    if rank == 0 and not args.no_cpu_baseline:
+            "gpu_launches": int(launches), "clocks": clocks_summary(samples)}
+    if world == 1:
+        # roofline of the dominant kernel: one LSD pass of sort 1 reads and writes every 16-byte record once
+        rec_total = st["n_records"]
+        passes = st["sort1_passes"]
+        sort1_ms = st["ms_sort1"]
+        ach = 2 * 16 * rec_total * passes / (sort1_ms * 1e-3) / 1e9 if sort1_ms > 0 else 0.0
+        whole = alg_bytes(st, 20) / (ms_step * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "cdgsort::onesweep_kernel<512,8,true> (sort 1: %d passes; time includes the histogram pass and the identity-record sort)" % passes,
+                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                            "whole_iteration_alg_GBps": whole, "whole_iteration_frac": whole / peak}
+        line["stage_ms"] = {k: st[k] for k in st if k.startswith("ms_")}
+        line["counters"] = {k: st[k] for k in ("n_seqs", "n_bases", "n_records", "n_grouped", "n_hits", "n_alns", "sort1_passes", "sort2_passes")}
+    else:
+        line["roofline"] = {"bound": "hbm", "kernel": "see the n_gpus=1 line (same kernels per rank)", "achieved": None, "peak": peak, "unit": "GB/s",
+                            "frac": None, "traffic": None, "peak_source": peak_src}
+        line["phase_ms_rank0"] = {k: round(v, 2) for k, v in last.get("phase_ms", {}).items()}
+        line["exchange"] = {"records_sent_per_rank": last.get("sent"), "grouped_sent_per_rank": last.get("sent2"),
+                            "nvlink_bytes_per_rank_per_step": int(16 * (last.get("sent") or 0) + 8 * (last.get("sent2") or 0))}
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
         try:
             r = reference_arm(argparse.Namespace(steps=1, warmup=0), args.cpu_sample)
             line["cpu_baseline"] = {"value": r["value"], "unit": "Mreads/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "note": r["note"]}
@@ -360,7 +436,6 @@ def main():
         print(json.dumps(line))
     ctx.close()
     if world > 1:
-        import torch.distributed as dist
         dist.destroy_process_group()
     return 0
 

@@ -470,19 +470,37 @@ __global__ void __launch_bounds__(256) route_count_kernel(const u64 *__restrict_
 __global__ void __launch_bounds__(256) route_scatter_kernel(const u64 *__restrict__ key2, u64 n, int repShift, u32 repChunk, u32 world,
                                                             unsigned long long *__restrict__ cursors /*[world], start = segment offsets*/,
                                                             u64 *__restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    for (u64 base = (u64) blockIdx.x * blockDim.x; base < n; base += (u64) gridDim.x * blockDim.x) {
-        const u64 i = base + threadIdx.x;
-        u32 o = 0xFFFFFFFFu; u64 k = 0;
-        if (i < n) { k = key2[i]; o = (u32) (k >> repShift) / repChunk; if (o >= world) o = world - 1; }
-        for (u32 w = 0; w < world; w++) {   // warp-aggregated append per owner
-            const u32 b = __ballot_sync(0xffffffffu, o == w);
-            if (!b) continue;
-            unsigned long long pos = 0;
-            if (lane == (__ffs(b) - 1)) pos = atomicAdd(&cursors[w], (unsigned long long) __popc(b));
-            pos = __shfl_sync(0xffffffffu, pos, __ffs(b) - 1);
-            if (o == w) out[pos + __popc(b & ((1u << lane) - 1))] = k;
+    // block-aggregated append: per-owner counts of a 2048-record tile in shared memory, one global atomic per owner and block
+    constexpr int ITEMS = 8;
+    __shared__ u32 sCnt[16];
+    __shared__ unsigned long long sBase[16];
+    const u64 tiles = (n + 256 * ITEMS - 1) / (256 * ITEMS);
+    for (u64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        if (threadIdx.x < 16) sCnt[threadIdx.x] = 0;
+        __syncthreads();
+        u64 k[ITEMS]; u32 o[ITEMS], r[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const u64 i = tile * (256 * ITEMS) + (u64) j * 256 + threadIdx.x;
+            o[j] = 0xFFFFFFFFu; k[j] = 0; r[j] = 0;
+            if (i < n) {
+                k[j] = key2[i];
+                o[j] = (u32) (k[j] >> repShift) / repChunk; if (o[j] >= world) o[j] = world - 1;
+                // warp-aggregated shared atomic
+                const u32 peers = __match_any_sync(__activemask(), o[j]);
+                const int leader = __ffs(peers) - 1;
+                u32 base = 0;
+                if ((threadIdx.x & 31) == leader) base = atomicAdd(&sCnt[o[j]], (u32) __popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                r[j] = base + __popc(peers & ((1u << (threadIdx.x & 31)) - 1));
+            }
         }
+        __syncthreads();
+        if (threadIdx.x < world && sCnt[threadIdx.x]) sBase[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], (unsigned long long) sCnt[threadIdx.x]);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) if (o[j] != 0xFFFFFFFFu) out[sBase[o[j]] + r[j]] = k[j];
+        __syncthreads();
     }
 }
 
@@ -533,7 +551,7 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
         sKey[tileN] = tileBase + tileN < n ? keys[tileBase + tileN] : CDG_SENTINEL;
         // run open at the tile start: walk back to its head (one thread per tile, runs are short)
         u64 h = tileBase;
-        if (tileBase > 0) {
+        if (tileBase > 0 && keys[tileBase] != CDG_SENTINEL) {   // (a tile inside the sentinel tail has nothing to find)
             const u64 k0 = keys[tileBase] | CDG_B63;
             while (h > 0 && (keys[h - 1] | CDG_B63) == k0) h--;
         }

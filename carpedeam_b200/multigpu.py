@@ -123,11 +123,21 @@ class ShardedIteration:
         rp = rescore or RescoreParams(0.9, 0.001, 0)
         cp = corr or CorrParams(0.9, 0.99)
         torch = comm.torch
+        import time
+        tm = {}
+        t_last = [time.perf_counter()]
+
+        def lap(name):
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            tm[name] = tm.get(name, 0.0) + (now - t_last[0]) * 1e3
+            t_last[0] = now
         # phase 1
         sc = (C.c_uint64 * world)()
         sk, sv = C.c_void_p(), C.c_void_p()
         ctx._ck(L.cdg_mg_extract(ctx._h, C.byref(kp), world, rank, sc, C.byref(sk), C.byref(sv)), "cdg_mg_extract")
         send_counts = list(sc)
+        lap("extract+partition")
         recv_counts = comm.exchange_counts(send_counts)
         total = sum(recv_counts)
         rk, rv = C.c_void_p(), C.c_void_p()
@@ -135,28 +145,31 @@ class ShardedIteration:
         nsend = sum(send_counts)
         comm.all_to_all(self._t(rk.value, total), self._t(sk.value, nsend), recv_counts, send_counts)
         comm.all_to_all(self._t(rv.value, total), self._t(sv.value, nsend), recv_counts, send_counts)
-        torch.cuda.synchronize()
+        lap("all_to_all records")
         # phase 2
         mk = C.c_uint64()
         ctx._ck(L.cdg_mg_sort(ctx._h, C.byref(kp), C.byref(mk)), "cdg_mg_sort")
+        lap("identity+sort1")
         owner = first_run_owner(comm.all_gather_u64(mk.value))
         # phase 3
         sc2 = (C.c_uint64 * world)()
         s2 = C.c_void_p()
         ctx._ck(L.cdg_mg_group(ctx._h, C.byref(kp), 1 if owner == rank else 0, sc2, C.byref(s2)), "cdg_mg_group")
         send2 = list(sc2)
+        lap("group+route")
         recv2 = comm.exchange_counts(send2)
         total2 = sum(recv2)
         r2 = C.c_void_p()
         ctx._ck(L.cdg_mg_recv_grouped(ctx._h, total2, C.byref(r2)), "cdg_mg_recv_grouped")
         comm.all_to_all(self._t(r2.value, total2), self._t(s2.value, sum(send2)), recv2, send2)
-        torch.cuda.synchronize()
+        lap("all_to_all grouped")
         # phase 4
         sorted_ptr, head_n, head_cap = C.c_void_p(), C.c_uint64(), C.c_uint64()
         ctx._ck(L.cdg_mg_sort2(ctx._h, C.byref(sorted_ptr), C.byref(head_n), C.byref(head_cap)), "cdg_mg_sort2")
+        lap("sort2")
         whole = self._t(sorted_ptr.value, total2 + head_cap.value)
         n_app = comm.shift_to_prev(whole[:total2], int(head_n.value), whole[total2:])
-        torch.cuda.synchronize()
+        lap("head shift")
         # phase 5
         hits, alns = Hits(), Alns()
         off, nbytes, changed = C.c_uint64(), C.c_uint64(), C.c_uint64()
@@ -165,10 +178,13 @@ class ShardedIteration:
             optr = C.c_void_p(out_range.ctypes.data) if hasattr(out_range, "ctypes") else C.c_void_p(int(out_range))
         ctx._ck(L.cdg_mg_finish(ctx._h, C.byref(rp), C.byref(cp), n_app, C.byref(hits) if fetch_hits else None, C.byref(alns) if fetch_alns else None,
                                 optr, C.byref(off), C.byref(nbytes), C.byref(changed)), "cdg_mg_finish")
-        res = dict(range_offset=off.value, range_bytes=nbytes.value, changed=changed.value, records_sent=nsend, records_received=total,
+        lap("reduce+rescore+correct")
+        res = dict(phase_ms=tm, range_offset=off.value, range_bytes=nbytes.value, changed=changed.value, records_sent=nsend, records_received=total,
                    grouped_sent=sum(send2), grouped_received=total2, head_appended=n_app)
         if fetch_hits:
             res["hits"] = ctx._hits(hits)
-        if fetch_alns:
+        if fetch_alns == "raw":
+            res["alns_raw"] = alns     # library-owned pinned arrays, no numpy copies (benchmark)
+        elif fetch_alns:
             res["alns"] = ctx._alns(alns)
         return res
