@@ -74,7 +74,7 @@ struct cdg_ctx {
     u64 nHits = 0, nRecords = 0, nGrouped = 0; bool hitsValid = false;
     u32 sort1Passes = 0, sort2Passes = 0;
     u64 *sortedMainK = nullptr, *sortedMainV = nullptr, *sortedIdK = nullptr, *sortedIdV = nullptr, *sortedKey2 = nullptr;
-    KmPlanFwd plan; u64 qLo = 0, nQ = 0; u64 mgRecv = 0, mgR2 = 0;
+    KmPlanFwd plan; u64 qLo = 0, nQ = 0; u64 mgRecv = 0, mgR2 = 0; u64 nIdent = 0; bool identCompacted = false;
     // lines / alignments
     DevBuf dLineOff, dLineQ, dLineT, dLinePref, dLineDiag, dKeep, dScore, dBits, dEvalue, dSeqId, dQS, dQE, dDS, dDE, dLineSel;
     HostBuf hLineOff, hLineT, hKeep, hScore, hBits, hEvalue, hSeqId, hQS, hQE, hDS, hDE;
@@ -116,6 +116,12 @@ __global__ void __launch_bounds__(256) order_scatter_kernel(const u64 *__restric
                                                             u64 *__restrict__ slotOff, u32 *__restrict__ rankOf) {
     u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
     if (r < n) { const u32 seq = (u32) order[r]; slotOff[seq] = prefix[r]; rankOf[seq] = (u32) r; }
+}
+struct NonSentinelF { const u64 *keys; __device__ u32 operator()(u64 i) const { return keys[i] != CDG_SENTINEL ? 1u : 0u; } };
+__global__ void __launch_bounds__(256) compact_pairs_kernel(const u64 *__restrict__ k, const u64 *__restrict__ v, const u64 *__restrict__ prefix, u64 n,
+                                                            u64 *__restrict__ ko, u64 *__restrict__ vo) {
+    u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && k[i] != CDG_SENTINEL) { ko[prefix[i]] = k[i]; vo[prefix[i]] = v[i]; }
 }
 struct CapacityF { const u32 *len; int k, kps; float scale; __device__ u32 operator()(u64 i) const { return cdgkmer::kmer_capacity(len[i], k, kps, scale); } };
 
@@ -401,8 +407,12 @@ static int km_sort_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K
     cdgsort::Plan plan1 = cdgsort::make_plan(0, 0, 0, 2 * p->k);
     int l1 = cdgsort::radix_sort(ctx->st, ws, ka, kb, va, vb, Rtot, plan1, &ctx->sortedMainK, &ctx->sortedMainV, ctx->smCount);
     cdgsort::Plan planI = cdgsort::make_plan(0, 0, 0, 63);
-    int l2 = cdgsort::radix_sort(ctx->st, ws, ctx->dIdKeysA.as<u64>(), ctx->dIdKeysB.as<u64>(), ctx->dIdValsA.as<u64>(), ctx->dIdValsB.as<u64>(), n, planI,
-                                 &ctx->sortedIdK, &ctx->sortedIdV, ctx->smCount);
+    const u64 nId = ctx->identCompacted ? ctx->nIdent : n;
+    int l2 = ctx->identCompacted
+                 ? cdgsort::radix_sort(ctx->st, ws, ctx->dIdKeysB.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsB.as<u64>(), ctx->dIdValsA.as<u64>(), nId, planI,
+                                       &ctx->sortedIdK, &ctx->sortedIdV, ctx->smCount)
+                 : cdgsort::radix_sort(ctx->st, ws, ctx->dIdKeysA.as<u64>(), ctx->dIdKeysB.as<u64>(), ctx->dIdValsA.as<u64>(), ctx->dIdValsB.as<u64>(), nId, planI,
+                                       &ctx->sortedIdK, &ctx->sortedIdV, ctx->smCount);
     if (l1 < 0 || l2 < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "radix sort: input too large for one pass set");
     ctx->launches += l1 + l2; ctx->sort1Passes = plan1.n;
     CKL();
@@ -431,8 +441,9 @@ static int km_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64
     if (Rtot) group_kernel<<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedMainK, ctx->sortedMainV, Rtot, ctx->dLen.as<u32>(), G,
                                                                                                       ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
     GroupParams GI = G; GI.firstRunQuirk = idHasGlobalFirstRun ? 1 : 0;
-    group_kernel<<<(unsigned) ((n + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedIdK, ctx->sortedIdV, n, ctx->dLen.as<u32>(), GI,
-                                                                                            ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
+    const u64 nId = ctx->identCompacted ? ctx->nIdent : n;
+    if (nId) group_kernel<<<(unsigned) ((nId + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedIdK, ctx->sortedIdV, nId, ctx->dLen.as<u32>(), GI,
+                                                                                                    ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
     ctx->launches += 2;
     CKL();
     if ((rc = read_scalar(ctx, SC_GROUPED, R2out))) return rc;
@@ -494,7 +505,7 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     CK(cudaMemsetAsync(sc, 0, SC_N * 8, ctx->st));
     rec(ctx, EV_START);
     if ((rc = km_prepare(ctx, p, K))) return rc;
-    ctx->plan = K; ctx->qLo = 0; ctx->nQ = n;
+    ctx->plan = K; ctx->qLo = 0; ctx->nQ = n; ctx->identCompacted = false; ctx->nIdent = n;
     const u64 Rtot = K.slots + K.extraCap;
     if (Rtot > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "%llu k-mer records exceed one sort (2^30): use hash ranges", (unsigned long long) Rtot);
     CK(ctx->dKeysA.reserve(Rtot * 8)); CK(ctx->dKeysB.reserve(Rtot * 8)); CK(ctx->dValsA.reserve(Rtot * 8)); CK(ctx->dValsB.reserve(Rtot * 8));
@@ -870,6 +881,14 @@ extern "C" int cdg_mg_sort(cdg_ctx *ctx, const cdg_kmer_params *p, uint64_t *min
                                                          K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>());
     ctx->launches++;
     CKL();
+    // keep only the owned identity records (1/world of the slots), in slot order
+    if ((rc = scan_to(ctx, NonSentinelF{ctx->dIdKeysA.as<u64>()}, n, ctx->dSlotRank.as<u64>(), false))) return rc;
+    compact_pairs_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), ctx->dSlotRank.as<u64>(), n,
+                                                                         ctx->dIdKeysB.as<u64>(), ctx->dIdValsB.as<u64>());
+    ctx->launches++;
+    u64 nOwnedId = 0;
+    if ((rc = read_scalar(ctx, SC_SCAN, &nOwnedId))) return rc;
+    ctx->nIdent = nOwnedId; ctx->identCompacted = true;
     u64 mk = 0;
     if ((rc = km_sort_group(ctx, p, K, ctx->dRecvK.as<u64>(), ctx->dKeysB.as<u64>(), ctx->dRecvV.as<u64>(), ctx->dValsB.as<u64>(), Rtot, -1, &mk, nullptr))) return rc;
     *min_key = mk;

@@ -58,8 +58,9 @@ class TorchComm:
         self.dist.all_to_all_single(r, t)
         return [int(x) for x in r.tolist()]
 
-    def all_to_all(self, recv, send, recv_counts, send_counts):
-        self.dist.all_to_all_single(recv, send, output_split_sizes=[int(c) for c in recv_counts], input_split_sizes=[int(c) for c in send_counts])
+    def all_to_all(self, recv, send, recv_counts, send_counts, async_op=False):
+        return self.dist.all_to_all_single(recv, send, output_split_sizes=[int(c) for c in recv_counts],
+                                           input_split_sizes=[int(c) for c in send_counts], async_op=async_op)
 
     def all_gather_u64(self, value):
         t = self.torch.tensor([np.uint64(value).astype(np.int64)], dtype=self.torch.int64, device=self.device)
@@ -143,8 +144,9 @@ class ShardedIteration:
         rk, rv = C.c_void_p(), C.c_void_p()
         ctx._ck(L.cdg_mg_recv_records(ctx._h, total, C.byref(rk), C.byref(rv)), "cdg_mg_recv_records")
         nsend = sum(send_counts)
-        comm.all_to_all(self._t(rk.value, total), self._t(sk.value, nsend), recv_counts, send_counts)
-        comm.all_to_all(self._t(rv.value, total), self._t(sv.value, nsend), recv_counts, send_counts)
+        w1 = comm.all_to_all(self._t(rk.value, total), self._t(sk.value, nsend), recv_counts, send_counts, async_op=True)
+        w2 = comm.all_to_all(self._t(rv.value, total), self._t(sv.value, nsend), recv_counts, send_counts, async_op=True)
+        w1.wait(); w2.wait()
         lap("all_to_all records")
         # phase 2
         mk = C.c_uint64()
