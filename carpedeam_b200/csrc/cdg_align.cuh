@@ -379,7 +379,21 @@ CDG_D void count_column(const u8 *__restrict__ data, u64 tOff, u32 dL, bool rev,
     mask |= 1ull << idx;
 }
 
+// queries with more than one line (only those can change): compact list, order irrelevant
+__global__ void __launch_bounds__(256) multi_line_queries_kernel(const u64 *__restrict__ lineOff, u64 n, u32 *__restrict__ list, u32 *__restrict__ count) {
+    const u64 q = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    const bool multi = q < n && lineOff[q + 1] - lineOff[q] > 1;
+    const u32 b = __ballot_sync(0xffffffffu, multi);
+    if (!b) return;
+    const int lane = threadIdx.x & 31;
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(count, (u32) __popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (multi) list[base + __popc(b & ((1u << lane) - 1))] = (u32) q;
+}
+
 __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
+    const u32 *__restrict__ qList, const u32 *__restrict__ qCount,
     const u8 *__restrict__ data, const SeqMeta *__restrict__ meta, const u64 *__restrict__ words, u64 qLo, u64 n,
     const u64 *__restrict__ lineOff, const u32 *__restrict__ lineT, const u8 *__restrict__ keep, const float *__restrict__ seqId,
     const i32 *__restrict__ qS_, const i32 *__restrict__ qE_, const i32 *__restrict__ dS_, const i32 *__restrict__ dE_,
@@ -403,9 +417,11 @@ __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
     LineCache &LC = S.lc[warp];
     const u64 gwarp = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64) gridDim.x * blockDim.x) >> 5;
     u32 nChanged = 0;
-    for (u64 ql = gwarp; ql < n; ql += nwarps) {
+    const u64 nList = *qCount;
+    for (u64 li = gwarp; li < nList; li += nwarps) {
+        const u64 ql = qList[li];   // local query index; queries with a single line are not in the list (coverage <= 1)
+        if (ql >= n) continue;
         const u64 l0 = lineOff[ql], l1 = lineOff[ql + 1];
-        if (l1 - l0 <= 1) continue;   // at most the self alignment: coverage <= 1 everywhere
         const u64 qi = qLo + ql;
         const SeqMeta qm = meta[qi];
         const u32 qLen = qm.lenFlags & META_LEN;
@@ -413,10 +429,18 @@ __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
         const u64 *qw = words + qm.wordOff;
         const bool qExc = (qm.lenFlags & META_EXC) != 0;
         const bool qExt = (qm.lenFlags & META_EXT) != 0;
-        // pass 1 (correction.cpp:220-245)
+        // pass 1 (correction.cpp:220-245): exact integer sum of the alignment lengths -> avCov
+        const bool single = (l1 - l0) <= 32;   // one line per lane: pass 1 and pass 2 share their loads
+        u8 myKeep = 0; u32 myT = 0; i32 mqs = 0, mqe = 0, mds = 0, mde = 0;
         unsigned long long sum = 0;
-        for (u64 l = l0 + lane; l < l1; l += 32)
-            if (keep[l]) sum += (unsigned long long) (max(abs(qE_[l] - qS_[l]), abs(dE_[l] - dS_[l])) + 1);
+        if (single) {
+            const u64 l = l0 + lane;
+            if (l < l1) { myKeep = keep[l]; myT = lineT[l]; mqs = qS_[l]; mqe = qE_[l]; mds = dS_[l]; mde = dE_[l]; }
+            if (myKeep) sum = (unsigned long long) (max(abs(mqe - mqs), abs(mde - mds)) + 1);
+        } else {
+            for (u64 l = l0 + lane; l < l1; l += 32)
+                if (keep[l]) sum += (unsigned long long) (max(abs(qE_[l] - qS_[l]), abs(dE_[l] - dS_[l])) + 1);
+        }
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
         float avCov;
@@ -432,12 +456,13 @@ __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
             const u64 l = lb + lane;
             u8 sel = 0;
             u64 tOff = 0; u32 dL = 0; i32 qs = 0, aln = 0, ds = 0;
-            if (l < l1 && keep[l]) {
-                const SeqMeta tm = meta[lineT[l]];
+            if (!single && l < l1) { myKeep = keep[l]; if (myKeep) { myT = lineT[l]; mqs = qS_[l]; mqe = qE_[l]; mds = dS_[l]; mde = dE_[l]; } }
+            if (l < l1 && myKeep) {
+                const SeqMeta tm = meta[myT];
                 if (!(tm.lenFlags & META_EXT)) {
                     dL = tm.lenFlags & META_LEN; tOff = tm.off;
-                    i32 qe = qE_[l], de = dE_[l];
-                    qs = qS_[l]; ds = dS_[l];
+                    i32 qe = mqe, de = mde;
+                    qs = mqs; ds = mds;
                     aln = max(abs(qe - qs), abs(de - ds)) + 1;
                     bool rev = false;
                     if (qs > qe) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; rev = true; }

@@ -55,7 +55,8 @@ struct KmPlanFwd {
 };
 struct cdg_ctx {
     int device = 0, smCount = 148;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, copySt = nullptr;   // copySt: device-to-host exports that overlap the next stage
+    cudaEvent_t evReady = nullptr, evCopied = nullptr; bool copyPending = false;
     std::string err;
     cudaEvent_t ev[EV_N];
     bool evValid[EV_N];
@@ -80,7 +81,7 @@ struct cdg_ctx {
     HostBuf hLineOff, hLineT, hKeep, hScore, hBits, hEvalue, hSeqId, hQS, hQE, hDS, hDE;
     u64 nLines = 0, nKept = 0; bool linesValid = false, alnsValid = false, alnsFromText = false;
     // correction
-    DevBuf dTables, dOut, dLik, dWideList, dRecvK, dRecvV, dRecv2; bool damageSet = false;
+    DevBuf dTables, dOut, dLik, dWideList, dRecvK, dRecvV, dRecv2, dQList; bool damageSet = false;
 };
 
 namespace {
@@ -100,7 +101,7 @@ int fail(cdg_ctx *c, int code, const char *fmt, ...) {
 
 // scalars block on the device: [0] scan total, [1] emitted records, [2] grouped count, [3] kept lines,
 // [4] changed bases, [5] (u32) extraCount, [6] (u32) overflow, [7] (u32) long count, [8] long scratch total, [9] (u32) sort ticket
-enum { SC_SCAN = 0, SC_EMIT, SC_GROUPED, SC_KEPT, SC_CHANGED, SC_EXTRA, SC_OVERFLOW, SC_NLONG, SC_LONGSCR, SC_TICKET, SC_WIDE, SC_ROUTE /*16 counters*/, SC_BOUNDS = SC_ROUTE + 16 /*17 bounds*/, SC_N = SC_BOUNDS + 20 };
+enum { SC_SCAN = 0, SC_EMIT, SC_GROUPED, SC_KEPT, SC_CHANGED, SC_EXTRA, SC_OVERFLOW, SC_NLONG, SC_LONGSCR, SC_TICKET, SC_WIDE, SC_QLIST, SC_ROUTE /*16 counters*/, SC_BOUNDS = SC_ROUTE + 16 /*17 bounds*/, SC_N = SC_BOUNDS + 20 };
 
 void rec(cdg_ctx *ctx, int e) { cudaEventRecord(ctx->ev[e], ctx->st); ctx->evValid[e] = true; }
 
@@ -116,6 +117,13 @@ __global__ void __launch_bounds__(256) order_scatter_kernel(const u64 *__restric
                                                             u64 *__restrict__ slotOff, u32 *__restrict__ rankOf) {
     u64 r = (u64) blockIdx.x * blockDim.x + threadIdx.x;
     if (r < n) { const u32 seq = (u32) order[r]; slotOff[seq] = prefix[r]; rankOf[seq] = (u32) r; }
+}
+__global__ void __launch_bounds__(256) max_len_kernel(const u32 *__restrict__ len, u64 n, u32 *__restrict__ out) {
+    u32 m = 0;
+    for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) m = max(m, len[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 struct NonSentinelF { const u64 *keys; __device__ u32 operator()(u64 i) const { return keys[i] != CDG_SENTINEL ? 1u : 0u; } };
 __global__ void __launch_bounds__(256) compact_pairs_kernel(const u64 *__restrict__ k, const u64 *__restrict__ v, const u64 *__restrict__ prefix, u64 n,
@@ -201,6 +209,8 @@ extern "C" int cdg_create(int device, cdg_ctx **out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return CDG_ERR_CUDA; }
     ctx->smCount = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CDG_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->copySt, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CDG_ERR_CUDA; }
+    cudaEventCreateWithFlags(&ctx->evReady, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->evCopied, cudaEventDisableTiming);
     for (int i = 0; i < EV_N; i++) { cudaEventCreate(&ctx->ev[i]); ctx->evValid[i] = false; }
     if (ctx->dScalars.reserve(SC_N * 8) != cudaSuccess) { delete ctx; return CDG_ERR_CUDA; }
     cudaFuncSetAttribute(cdgkmer::extract_short_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cdgkmer::EX_WARPS * 2048 * 4);
@@ -223,13 +233,13 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
                    &ctx->dOrdKA, &ctx->dOrdKB, &ctx->dOrdVA, &ctx->dOrdVB, &ctx->dRankOf, &ctx->dSlotRank, &ctx->dScratchOff, &ctx->dScratch, &ctx->dScratchKeep, &ctx->dShortScratch, &ctx->dShortKeep, &ctx->dHitRep, &ctx->dHitTgt,
                    &ctx->dHitScore, &ctx->dHitDiag, &ctx->dLineOff, &ctx->dLineQ, &ctx->dLineT, &ctx->dLinePref, &ctx->dLineDiag, &ctx->dKeep,
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
-                   &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2};
+                   &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2, &ctx->dQList};
     for (DevBuf *b : d) b->release();
     HostBuf *h[] = {&ctx->hHitRep, &ctx->hHitTgt, &ctx->hHitScore, &ctx->hHitDiag, &ctx->hHitDiag16, &ctx->hLineOff, &ctx->hLineT, &ctx->hKeep,
                     &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE};
     for (HostBuf *b : h) b->release();
     for (int i = 0; i < EV_N; i++) cudaEventDestroy(ctx->ev[i]);
-    cudaStreamDestroy(ctx->st);
+    cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->copySt); cudaEventDestroy(ctx->evReady); cudaEventDestroy(ctx->evCopied);
     delete ctx;
 }
 
@@ -253,16 +263,21 @@ extern "C" int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_
     CK(cudaMemcpyAsync(ctx->dLen.p, lens, n * 4, cudaMemcpyHostToDevice, ctx->st));
     if (ext) CK(cudaMemcpyAsync(ctx->dExt.p, ext, n, cudaMemcpyHostToDevice, ctx->st));
     else CK(cudaMemsetAsync(ctx->dExt.p, 0, n, ctx->st));
-    // host-side facts needed for sizing (one pass over lens)
-    u64 total = 0; u32 mx = 0;
-    for (u64 i = 0; i < n; i++) { total += lens[i]; if (lens[i] > mx) mx = lens[i]; }
-    ctx->totalBases = total; ctx->maxLen = mx;
+    // facts needed for sizing: total bases, longest sequence, packed words (all reduced on the device)
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    CK(cudaMemsetAsync(sc + SC_WIDE, 0, 8, ctx->st));
+    max_len_kernel<<<ctx->smCount * 4, 256, 0, ctx->st>>>(ctx->dLen.as<u32>(), n, (u32 *) (sc + SC_WIDE));
+    ctx->launches++;
     int rc;
+    if ((rc = scan_to(ctx, LenBasesF{ctx->dLen.as<u32>()}, n, ctx->dLikOff.as<u64>(), true))) return rc;
+    u64 total = 0, mx64 = 0;
+    if ((rc = read_scalar(ctx, SC_SCAN, &total))) return rc;
+    if ((rc = read_scalar(ctx, SC_WIDE, &mx64))) return rc;
+    ctx->totalBases = total; ctx->maxLen = (u32) mx64;
     if ((rc = scan_to(ctx, LenWordsF{ctx->dLen.as<u32>()}, n, ctx->dWordOff.as<u64>(), true))) return rc;
     u64 words = 0;
     if ((rc = read_scalar(ctx, SC_SCAN, &words))) return rc;
     ctx->totalWords = words;
-    if ((rc = scan_to(ctx, LenBasesF{ctx->dLen.as<u32>()}, n, ctx->dLikOff.as<u64>(), true))) return rc;
     CK(ctx->dWords.reserve((words + 2) * 8)); CK(ctx->dXmask.reserve((words + 2) * 4));
     cdgkmer::pack_kernel<<<ctx->smCount * 16, 256, 0, ctx->st>>>(ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(),
                                                                                     ctx->dWordOff.as<u64>(), n, ctx->dWords.as<u64>(),
@@ -640,28 +655,32 @@ static int run_rescore(cdg_ctx *ctx, const cdg_rescore_params *p) {
     return CDG_OK;
 }
 
-static int export_alns(cdg_ctx *ctx, cdg_alns *out) {
+// overlap = true: the copies run on the copy stream behind the rescore kernel; the caller finishes with wait_exports()
+static int export_alns(cdg_ctx *ctx, cdg_alns *out, bool overlap = false) {
     const u64 M = ctx->nLines, n = ctx->nQ;
+    cudaStream_t cs = ctx->st;
     CK(ctx->hLineOff.reserve((n + 1) * 8)); CK(ctx->hLineT.reserve((M + 1) * 4)); CK(ctx->hKeep.reserve(M + 1)); CK(ctx->hScore.reserve((M + 1) * 4));
     CK(ctx->hBits.reserve((M + 1) * 4)); CK(ctx->hEvalue.reserve((M + 1) * 8)); CK(ctx->hSeqId.reserve((M + 1) * 4)); CK(ctx->hQS.reserve((M + 1) * 4));
     CK(ctx->hQE.reserve((M + 1) * 4)); CK(ctx->hDS.reserve((M + 1) * 4)); CK(ctx->hDE.reserve((M + 1) * 4));
-    CK(cudaMemcpyAsync(ctx->hLineOff.p, ctx->dLineOff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->st));
-    if (M) {
-        CK(cudaMemcpyAsync(ctx->hLineT.p, ctx->dLineT.p, M * 4, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaMemcpyAsync(ctx->hKeep.p, ctx->dKeep.p, M, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaMemcpyAsync(ctx->hScore.p, ctx->dScore.p, M * 4, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaMemcpyAsync(ctx->hBits.p, ctx->dBits.p, M * 4, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaMemcpyAsync(ctx->hEvalue.p, ctx->dEvalue.p, M * 8, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaMemcpyAsync(ctx->hSeqId.p, ctx->dSeqId.p, M * 4, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaMemcpyAsync(ctx->hQS.p, ctx->dQS.p, M * 4, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaMemcpyAsync(ctx->hQE.p, ctx->dQE.p, M * 4, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaMemcpyAsync(ctx->hDS.p, ctx->dDS.p, M * 4, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaMemcpyAsync(ctx->hDE.p, ctx->dDE.p, M * 4, cudaMemcpyDeviceToHost, ctx->st));
-    }
     u64 kept = 0;
-    int rc = read_scalar(ctx, SC_KEPT, &kept);
+    int rc = read_scalar(ctx, SC_KEPT, &kept);   // synchronises the compute stream: rescore has finished
     if (rc) return rc;
     ctx->nKept = kept;
+    if (overlap) cs = ctx->copySt;
+    CK(cudaMemcpyAsync(ctx->hLineOff.p, ctx->dLineOff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, cs));
+    if (M) {
+        CK(cudaMemcpyAsync(ctx->hLineT.p, ctx->dLineT.p, M * 4, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(ctx->hKeep.p, ctx->dKeep.p, M, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(ctx->hScore.p, ctx->dScore.p, M * 4, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(ctx->hBits.p, ctx->dBits.p, M * 4, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(ctx->hEvalue.p, ctx->dEvalue.p, M * 8, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(ctx->hSeqId.p, ctx->dSeqId.p, M * 4, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(ctx->hQS.p, ctx->dQS.p, M * 4, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(ctx->hQE.p, ctx->dQE.p, M * 4, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(ctx->hDS.p, ctx->dDS.p, M * 4, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(ctx->hDE.p, ctx->dDE.p, M * 4, cudaMemcpyDeviceToHost, cs));
+    }
+    if (overlap) { CK(cudaEventRecord(ctx->evCopied, cs)); ctx->copyPending = true; } else CK(cudaStreamSynchronize(cs));
     out->n_lines = M; out->n_queries = n; out->line_off = ctx->hLineOff.as<u64>(); out->target = ctx->hLineT.as<u32>(); out->keep = ctx->hKeep.as<u8>();
     out->score = ctx->hScore.as<i32>(); out->bits = ctx->hBits.as<i32>(); out->evalue = ctx->hEvalue.as<double>(); out->seq_id = ctx->hSeqId.as<float>();
     out->q_start = ctx->hQS.as<i32>(); out->q_end = ctx->hQE.as<i32>(); out->db_start = ctx->hDS.as<i32>(); out->db_end = ctx->hDE.as<i32>();
@@ -716,6 +735,11 @@ extern "C" int cdg_set_alignments(cdg_ctx *ctx, const uint64_t *aln_off, uint64_
     return CDG_OK;
 }
 
+static int wait_exports(cdg_ctx *ctx) {
+    if (ctx->copyPending) { CK(cudaEventSynchronize(ctx->evCopied)); ctx->copyPending = false; }
+    return 0;
+}
+
 static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data, uint64_t *n_changed, double *lik) {
     if (!ctx->alnsValid) return fail(ctx, CDG_ERR_ARG, "cdg_correct: no alignments (run cdg_rescore or cdg_set_alignments)");
     if (!ctx->damageSet) return fail(ctx, CDG_ERR_ARG, "cdg_correct: cdg_set_damage not called");
@@ -735,9 +759,13 @@ static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data
     const u64 wideCap = ctx->wideThreshold < 65535 ? ctx->n + 16 : (ctx->nLines >> 16) + 16;
     CK(ctx->dWideList.reserve(wideCap * 4));
     CK(cudaMemsetAsync(sc + SC_WIDE, 0, 8, ctx->st));
+    CK(ctx->dQList.reserve((n + 1) * 4));
+    CK(cudaMemsetAsync(sc + SC_QLIST, 0, 8, ctx->st));
+    if (n) cdgalign::multi_line_queries_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dLineOff.as<u64>(), n, ctx->dQList.as<u32>(), (u32 *) (sc + SC_QLIST));
+    ctx->launches++;
     const int blocks = ctx->smCount * 4;
     cdgalign::correct_fast_kernel<<<blocks, cdgalign::CF_WARPS * 32, sizeof(cdgalign::CorrSmem), ctx->st>>>(
-        ctx->dData.as<u8>(), ctx->dMeta.as<cdgalign::SeqMeta>(), ctx->dWords.as<u64>(), qLo, n, ctx->dLineOff.as<u64>(), ctx->dLineT.as<u32>(), ctx->dKeep.as<u8>(), ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(),
+        ctx->dQList.as<u32>(), (const u32 *) (sc + SC_QLIST), ctx->dData.as<u8>(), ctx->dMeta.as<cdgalign::SeqMeta>(), ctx->dWords.as<u64>(), qLo, n, ctx->dLineOff.as<u64>(), ctx->dLineT.as<u32>(), ctx->dKeep.as<u8>(), ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(),
         ctx->dQE.as<i32>(), ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), C, ctx->dTables.as<cdgalign::DamageTables>(), ctx->dLineSel.as<u8>(),
         ctx->dOut.as<u8>(), sc + SC_CHANGED, ctx->dLikOff.as<u64>(), dLik, ctx->dWideList.as<u32>(), (u32 *) (sc + SC_WIDE));
     ctx->launches++;
@@ -778,9 +806,11 @@ extern "C" int cdg_iteration(cdg_ctx *ctx, const cdg_iter_params *p, cdg_hits *h
     if (rc) return rc;
     if (hits && (rc = export_hits(ctx, hits))) return rc;
     if ((rc = run_rescore(ctx, &p->rescore))) return rc;
-    if (alns && (rc = export_alns(ctx, alns))) return rc;
+    if (alns && (rc = export_alns(ctx, alns, true))) return rc;   // alignment export overlaps the correction kernel
     if (!alns) { u64 kept = 0; if ((rc = read_scalar(ctx, SC_KEPT, &kept))) return rc; ctx->nKept = kept; }
-    return run_correct(ctx, &p->corr, out_data, n_changed, nullptr);
+    rc = run_correct(ctx, &p->corr, out_data, n_changed, nullptr);
+    int rc2 = wait_exports(ctx);
+    return rc ? rc : rc2;
 }
 
 extern "C" int cdg_get_stats(cdg_ctx *ctx, cdg_stats *out) {
@@ -979,9 +1009,10 @@ extern "C" int cdg_mg_finish(cdg_ctx *ctx, const cdg_rescore_params *rp, const c
     if ((rc = km_reduce(ctx, K, R2, R2 + n_appended))) return rc;
     if (hits && (rc = export_hits(ctx, hits))) return rc;
     if ((rc = run_rescore(ctx, rp))) return rc;
-    if (alns && (rc = export_alns(ctx, alns))) return rc;
+    if (alns && (rc = export_alns(ctx, alns, true))) return rc;
     if (!alns) { u64 kept = 0; if ((rc = read_scalar(ctx, SC_KEPT, &kept))) return rc; ctx->nKept = kept; }
     if ((rc = run_correct(ctx, cp, nullptr, n_changed, nullptr))) return rc;
+    if ((rc = wait_exports(ctx))) return rc;
     // corrected bytes of the rank's query range
     u64 b0 = 0, b1 = ctx->dataBytes;
     if (K.nQ) {
