@@ -169,6 +169,11 @@ def alg_bytes(st, k):
         H * (8 + 2 * Lbar / 4 + 32) + A * (32 + Lbar / 4) + S / 4 * 2
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of onesweep_kernel<true> over its algorithmic 2*16*records bytes, measured with
+# ncu --set full (profiles/r01c_ncu_full_raw_2Mreads.csv: 1.079 GB + 1.043 GB per launch for 68.998M+ records)
+ONESWEEP_TRAFFIC_RATIO = 0.961
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the unmodified reference binary on a bounded sample
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "carpedeam_ref")
@@ -409,15 +414,18 @@ def main():
             "e2e": {"value": e2e_val, "unit": "Mreads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_step},
             "gpu_launches": int(launches), "clocks": clocks_summary(samples)}
     if world == 1:
-        # roofline of the dominant kernel: one LSD pass of sort 1 reads and writes every 16-byte record once
-        rec_total = st["n_records"]
-        passes = st["sort1_passes"]
-        sort1_ms = st["ms_sort1"]
-        ach = 2 * 16 * rec_total * passes / (sort1_ms * 1e-3) / 1e9 if sort1_ms > 0 else 0.0
+        # roofline of the dominant kernel: one LSD pass of sort 1 reads and writes every 16-byte record once; launch times
+        # from CUDA events recorded around every onesweep launch on the library's stream (last timed step)
+        launches1 = max(1, st["n_sort1_pass_launches"])
+        per_launch_bytes = 2 * 16 * st["sort1_records"]
+        per_launch_ms = st["ms_sort1_passes"] / launches1
+        ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         whole = alg_bytes(st, 20) / (ms_step * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "cdgsort::onesweep_kernel<512,8,true> (sort 1: %d passes; time includes the histogram pass and the identity-record sort)" % passes,
-                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                            "whole_iteration_alg_GBps": whole, "whole_iteration_frac": whole / peak}
+        line["roofline"] = {"bound": "hbm", "kernel": "cdgsort::onesweep_kernel<256,16,true> (sort 1, %d launches per step, %.3f ms each, %d records x 32 B)" % (
+                                launches1, per_launch_ms, st["sort1_records"]),
+                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ONESWEEP_TRAFFIC_RATIO * per_launch_bytes,
+                            "traffic_note": "dram read+write per launch = %.3f x algorithmic bytes, ratio from the ncu --set full capture in profiles/ (2 M-read run)" % ONESWEEP_TRAFFIC_RATIO,
+                            "peak_source": peak_src, "whole_iteration_alg_GBps": whole, "whole_iteration_frac": whole / peak}
         line["stage_ms"] = {k: st[k] for k in st if k.startswith("ms_")}
         line["counters"] = {k: st[k] for k in ("n_seqs", "n_bases", "n_records", "n_grouped", "n_hits", "n_alns", "sort1_passes", "sort2_passes")}
     else:

@@ -86,7 +86,8 @@ class Stats(C.Structure):
     _fields_ = [("n_seqs", C.c_uint64), ("n_bases", C.c_uint64), ("n_records", C.c_uint64), ("n_grouped", C.c_uint64),
                 ("n_hits", C.c_uint64), ("n_alns", C.c_uint64), ("sort1_passes", C.c_uint32), ("sort2_passes", C.c_uint32),
                 ("kernel_launches", C.c_uint64), ("ms_extract", C.c_float), ("ms_sort1", C.c_float), ("ms_group", C.c_float),
-                ("ms_sort2", C.c_float), ("ms_reduce", C.c_float), ("ms_rescore", C.c_float), ("ms_correct", C.c_float)]
+                ("ms_sort2", C.c_float), ("ms_reduce", C.c_float), ("ms_rescore", C.c_float), ("ms_correct", C.c_float),
+                ("ms_sort1_passes", C.c_float), ("n_sort1_pass_launches", C.c_uint32), ("sort1_records", C.c_uint64)]
 
 
 _lib = None

@@ -341,8 +341,7 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) correct_wide_kernel(
 // 44-bit mask remembers which are non-zero so that the likelihood visits only those, in the reference's (t,l) order.
 static constexpr int CF_WARPS = 8;
 static constexpr int CF_CACHE = 32;
-struct SeqMeta { u64 off; u32 wordOff; u32 lenFlags; };   // lenFlags: len | exception << 30 | ext << 31
-static constexpr u32 META_EXC = 1u << 30, META_EXT = 1u << 31, META_LEN = (1u << 30) - 1;
+using ::SeqMeta; using ::META_EXC; using ::META_EXT; using ::META_LEN;
 struct LineCache { u64 tOff[CF_CACHE]; u32 dL[CF_CACHE]; i32 qs[CF_CACHE]; i32 aln[CF_CACHE]; i32 ds[CF_CACHE]; u32 rev[CF_CACHE]; };
 struct CorrSmem { DamageTables T; u32 cnt[CF_WARPS][44][32]; LineCache lc[CF_WARPS]; u8 lut[256]; };   // lut: bits 0-1 forward base index, 2-3 reverse-complement base index
 

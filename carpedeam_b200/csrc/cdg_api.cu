@@ -59,6 +59,7 @@ struct cdg_ctx {
     cudaEvent_t evReady = nullptr, evCopied = nullptr; bool copyPending = false;
     std::string err;
     cudaEvent_t ev[EV_N];
+    cudaEvent_t passEv[2 * cdgsort::MAX_PASSES]; int passEvN = 0;   // per-pass timing of sort 1 (roofline of the dominant kernel)
     bool evValid[EV_N];
     u64 launches = 0;
     u32 wideThreshold = 65535;   // test knob CDG_WIDE_THRESHOLD: route queries with more counted targets to the generic kernel
@@ -73,7 +74,7 @@ struct cdg_ctx {
     DevBuf dHitRep, dHitTgt, dHitScore, dHitDiag;
     HostBuf hHitRep, hHitTgt, hHitScore, hHitDiag, hHitDiag16;
     u64 nHits = 0, nRecords = 0, nGrouped = 0; bool hitsValid = false;
-    u32 sort1Passes = 0, sort2Passes = 0;
+    u32 sort1Passes = 0, sort2Passes = 0; u64 sort1Records = 0;
     u64 *sortedMainK = nullptr, *sortedMainV = nullptr, *sortedIdK = nullptr, *sortedIdV = nullptr, *sortedKey2 = nullptr;
     KmPlanFwd plan; u64 qLo = 0, nQ = 0; u64 mgRecv = 0, mgR2 = 0; u64 nIdent = 0; bool identCompacted = false;
     // lines / alignments
@@ -212,6 +213,7 @@ extern "C" int cdg_create(int device, cdg_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->copySt, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CDG_ERR_CUDA; }
     cudaEventCreateWithFlags(&ctx->evReady, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->evCopied, cudaEventDisableTiming);
     for (int i = 0; i < EV_N; i++) { cudaEventCreate(&ctx->ev[i]); ctx->evValid[i] = false; }
+    for (int i = 0; i < 2 * cdgsort::MAX_PASSES; i++) cudaEventCreate(&ctx->passEv[i]);
     if (ctx->dScalars.reserve(SC_N * 8) != cudaSuccess) { delete ctx; return CDG_ERR_CUDA; }
     cudaFuncSetAttribute(cdgkmer::extract_short_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cdgkmer::EX_WARPS * 2048 * 4);
     cudaFuncSetAttribute(cdgkmer::extract_short_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cdgkmer::EX_WARPS * 2048 * 4);
@@ -239,6 +241,7 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
                     &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE};
     for (HostBuf *b : h) b->release();
     for (int i = 0; i < EV_N; i++) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2 * cdgsort::MAX_PASSES; i++) cudaEventDestroy(ctx->passEv[i]);
     cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->copySt); cudaEventDestroy(ctx->evReady); cudaEventDestroy(ctx->evCopied);
     delete ctx;
 }
@@ -389,7 +392,7 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
     CK(ctx->dShortKeep.reserve(gridWarps * EX_MAXW));
     {
         const u32 maxW = ctx->maxLen >= (u32) p->k ? ctx->maxLen - p->k + 1 : 0;   // short sequences have <= 256 windows
-#define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT)
+#define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT)
         if (maxW <= 64) extract_short_kernel<2><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
         else if (maxW <= 128) extract_short_kernel<4><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
         else extract_short_kernel<8><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
@@ -420,7 +423,8 @@ static int km_sort_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K
     cdgsort::Workspace ws;
     if ((rc = sort_ws(ctx, Rtot > n ? Rtot : n, ws))) return rc;
     cdgsort::Plan plan1 = cdgsort::make_plan(0, 0, 0, 2 * p->k);
-    int l1 = cdgsort::radix_sort(ctx->st, ws, ka, kb, va, vb, Rtot, plan1, &ctx->sortedMainK, &ctx->sortedMainV, ctx->smCount);
+    int l1 = cdgsort::radix_sort(ctx->st, ws, ka, kb, va, vb, Rtot, plan1, &ctx->sortedMainK, &ctx->sortedMainV, ctx->smCount, -1, ctx->passEv);
+    ctx->passEvN = plan1.n; ctx->sort1Records = Rtot;
     cdgsort::Plan planI = cdgsort::make_plan(0, 0, 0, 63);
     const u64 nId = ctx->identCompacted ? ctx->nIdent : n;
     int l2 = ctx->identCompacted
@@ -825,7 +829,9 @@ extern "C" int cdg_get_stats(cdg_ctx *ctx, cdg_stats *out) {
     };
     cudaStreamSynchronize(ctx->st);
     out->ms_extract = el(EV_START, EV_EXTRACT); out->ms_sort1 = el(EV_EXTRACT, EV_SORT1); out->ms_group = el(EV_SORT1, EV_GROUP);
-    out->ms_sort2 = el(EV_GROUP, EV_SORT2); out->ms_reduce = el(EV_SORT2, EV_REDUCE); out->ms_rescore = el(EV_RS0, EV_RS1); out->ms_correct = el(EV_CO0, EV_CO1);
+    out->ms_sort2 = el(EV_GROUP, EV_SORT2);
+    out->ms_sort1_passes = 0.f; out->n_sort1_pass_launches = 0; out->sort1_records = ctx->sort1Records;
+    for (int i = 0; i < ctx->passEvN; i++) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->passEv[2 * i], ctx->passEv[2 * i + 1]) == cudaSuccess) { out->ms_sort1_passes += ms; out->n_sort1_pass_launches++; } } out->ms_reduce = el(EV_SORT2, EV_REDUCE); out->ms_rescore = el(EV_RS0, EV_RS1); out->ms_correct = el(EV_CO0, EV_CO1);
     return CDG_OK;
 }
 

@@ -107,3 +107,7 @@ static constexpr int CDG_OWNER_SHIFT = 28;
 CDG_HD u64 cdg_pack_val(u32 id, u32 pos, u32 owner = 0) { return ((u64) id << 32) | ((u64) owner << CDG_OWNER_SHIFT) | pos; }
 CDG_HD u32 cdg_val_id(u64 v) { return (u32) (v >> 32); }
 CDG_HD u32 cdg_val_pos(u64 v) { return (u32) v & ((1u << CDG_OWNER_SHIFT) - 1); }
+
+// per-sequence metadata in one 16-byte load: byte offset in the DB data, first packed word, length and flags
+struct SeqMeta { u64 off; u32 wordOff; u32 lenFlags; };   // lenFlags: len | exception << 30 | ext << 31
+static constexpr u32 META_EXC = 1u << 30, META_EXT = 1u << 31, META_LEN = (1u << 30) - 1;

@@ -181,7 +181,7 @@ static constexpr int EX_MAXW = 256;   // windows per short sequence
 // windows in shared... global scratch and lane 0 replays the reference's sequential loop.
 template <int ITERS>
 __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
-    const u64 *__restrict__ words, const u32 *__restrict__ xmask, const u64 *__restrict__ wordOff, const u32 *__restrict__ len,
+    const u64 *__restrict__ words, const u32 *__restrict__ xmask, const SeqMeta *__restrict__ meta,
     u64 n, ExtractParams P, const u64 *__restrict__ slotOff /*[n] first main slot of seq*/,
     u64 *__restrict__ mainKeys, u64 *__restrict__ mainVals, u64 *__restrict__ idKeys, u64 *__restrict__ idVals,
     u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow, const u32 *__restrict__ rankOf, WinRec *__restrict__ scratch /*[gridWarps][2*EX_MAXW]*/,
@@ -197,11 +197,14 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
     unsigned long long localEmitted = 0;
 
     for (u64 seq = gwarp; seq < n; seq += nwarps) {
-        const u32 L = len[seq];
+        const SeqMeta sm = meta[seq];   // one 16-byte load: length and first word
+        const u32 myRank = rankOf[seq];
+        const u64 slotAbs = slotOff[seq];
+        const u32 L = sm.lenFlags & META_LEN;
         if (!is_short_seq(L, P.k, P.kmersPerSeq, P.scale)) continue;   // handled by extract_long_kernel
-        { const u32 r = rankOf[seq]; if (r < P.posLo || r >= P.posHi) continue; }   // not in this rank's slice
-        const u64 *w = words + wordOff[seq];
-        const u32 *xm = xmask + wordOff[seq];
+        if (myRank < P.posLo || myRank >= P.posHi) continue;            // not in this rank's slice
+        const u64 *w = words + sm.wordOff;
+        const u32 *xm = xmask + sm.wordOff;
         const u32 W = L >= (u32) P.k ? L - P.k + 1 : 0;
         // identity hash
         u64 part = 0;
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
         __syncwarp();
         collide = __any_sync(0xffffffffu, collide);
 
-        const u64 slot0 = slotOff[seq] - P.slotBase;
+        const u64 slot0 = slotAbs - P.slotBase;
         const u32 cap = kmer_capacity(L, P.k, P.kmersPerSeq, P.scale);
         u32 written = 0;   // warp-uniform
         if (!collide) {

@@ -84,6 +84,19 @@ struct SweepSmem {
     u8 digitAt[HAS_VAL ? TILE_T : 4];
 };
 
+// lanes of the warp that hold the same 8-bit digit: intersection of 8 ballots, 5 instructions per bit
+// (MATCH.ANY iterates once per distinct value in the warp, ~30 for random digits; measured 25-30 % slower on B200)
+CDG_D u32 digit_peers(u32 d) {
+    u32 m = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < RADIX_BITS; b++) {
+        const u32 vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+        const u32 bitmask = (u32) ((i32) (d << (31 - b)) >> 31);   // all ones when bit b of d is set
+        m &= ~(vote ^ bitmask);                                    // bit set: keep voters, else keep non-voters (one LOP3)
+    }
+    return m;
+}
+
 template <int BLOCK_T, int ITEMS_T, bool HAS_VAL>
 __global__ void __launch_bounds__(BLOCK_T) onesweep_kernel(const u64 *__restrict__ keysIn, u64 *__restrict__ keysOut,
                                                            const u64 *__restrict__ valsIn, u64 *__restrict__ valsOut, u64 n,
@@ -100,41 +113,35 @@ __global__ void __launch_bounds__(BLOCK_T) onesweep_kernel(const u64 *__restrict
     const u32 tile = S.sTile;
     const u64 tileBase = (u64) tile * TILE_T;
     const u32 tileValid = (u32) (n - tileBase < (u64) TILE_T ? n - tileBase : (u64) TILE_T);
+    const bool full = tileValid == TILE_T;
 
     // load (warp-striped: warp w owns records [w*ITEMS*32, (w+1)*ITEMS*32) of the tile, item-major)
     u64 key[ITEMS_T];
-    u32 rank[ITEMS_T];
+    u32 dig[ITEMS_T];    // digit in the low byte, later rank << 8 | digit
     const u32 warpBase = warp * ITEMS_T * 32;
+    const u64 *kin = keysIn + tileBase + warpBase + lane;
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < ITEMS_T; i++) {
-        const u32 local = warpBase + i * 32 + lane;
-        key[i] = local < tileValid ? keysIn[tileBase + local] : ~0ull;   // padding: all digit bits set -> last bin, ranks last
+        for (int i = 0; i < ITEMS_T; i++) key[i] = kin[i * 32];
+    } else {
+#pragma unroll
+        for (int i = 0; i < ITEMS_T; i++) key[i] = warpBase + i * 32 + lane < tileValid ? kin[i * 32] : ~0ull;   // padding -> last bin, ranks last
     }
-    // stable rank inside the warp's chunk: all MATCH.ANY first (independent, their latency overlaps), then the
-    // dependent chain through the per-warp digit counters
+    // stable rank inside the warp's chunk: all peer masks first (independent), then the chain through the warp's counters
     u32 peers[ITEMS_T];
 #pragma unroll
-    for (int i = 0; i < ITEMS_T; i++) {
-        // lanes with the same digit: intersection of 8 ballots (MATCH.ANY iterates once per distinct value, ~30x slower
-        // on random digits; measured on B200)
-        const u32 d = digit_of(key[i], pass.shift, pass.mask);
-        u32 m = 0xffffffffu;
-#pragma unroll
-        for (int b = 0; b < RADIX_BITS; b++) {
-            const u32 vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
-            m &= ((d >> b) & 1u) ? vote : ~vote;
-        }
-        peers[i] = m;
-    }
+    for (int i = 0; i < ITEMS_T; i++) { dig[i] = digit_of(key[i], pass.shift, pass.mask); peers[i] = digit_peers(dig[i]); }
+    u32 *myHist = S.warpHist[warp];
+    const u32 ltMask = (1u << lane) - 1;
 #pragma unroll
     for (int i = 0; i < ITEMS_T; i++) {
-        const u32 d = digit_of(key[i], pass.shift, pass.mask);
-        const u32 pre = S.warpHist[warp][d];
-        const u32 lower = peers[i] & ((1u << lane) - 1);
+        const u32 d = dig[i];
+        const u32 pre = myHist[d];
+        const u32 lower = peers[i] & ltMask;
         __syncwarp();
-        if (lower == 0) S.warpHist[warp][d] = pre + __popc(peers[i]);   // lowest lane of the peer group publishes
+        if (lower == 0) myHist[d] = pre + __popc(peers[i]);   // lowest lane of the peer group publishes
         __syncwarp();
-        rank[i] = pre + __popc(lower);
+        dig[i] = d | ((pre + __popc(lower)) << 8);
     }
     __syncthreads();
     // thread d: scan digit d over the warps, publish the tile aggregate, look back
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(BLOCK_T) onesweep_kernel(const u64 *__restrict
         } else {
             st_state(state + (u64) tile * RADIX + d, FLAG_AGG | run);
             // decoupled look-back, LOOK predecessors per round trip (independent loads), consumed nearest first
-            constexpr int LOOK = 8;
+            constexpr int LOOK = 4;
             i64 p = (i64) tile - 1;
             bool done = false;
             while (!done) {
@@ -190,37 +197,44 @@ __global__ void __launch_bounds__(BLOCK_T) onesweep_kernel(const u64 *__restrict
     }
     __syncthreads();
     // scatter into tile order through shared memory, then coalesced runs to global
+    u32 pos[ITEMS_T];
 #pragma unroll
     for (int i = 0; i < ITEMS_T; i++) {
-        const u32 d = digit_of(key[i], pass.shift, pass.mask);
-        rank[i] += S.warpHist[warp][d];
-        S.exch[rank[i]] = key[i];
-        if (HAS_VAL) S.digitAt[rank[i]] = (u8) d;
+        const u32 d = dig[i] & 0xFFu;
+        pos[i] = (dig[i] >> 8) + myHist[d];
+        S.exch[pos[i]] = key[i];
+        if (HAS_VAL) S.digitAt[pos[i]] = (u8) d;
+    }
+    u64 v[HAS_VAL ? ITEMS_T : 1];
+    if (HAS_VAL) {   // values are requested now and arrive while the keys are written out
+        const u64 *vin = valsIn + tileBase + warpBase + lane;
+#pragma unroll
+        for (int i = 0; i < ITEMS_T; i++) v[i] = (full || warpBase + i * 32 + lane < tileValid) ? vin[i * 32] : 0;
     }
     __syncthreads();
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < ITEMS_T; i++) {
-        const u32 j = tid + i * BLOCK_T;
-        if (j < tileValid) {
+        for (int i = 0; i < ITEMS_T; i++) {
+            const u32 j = tid + i * BLOCK_T;
             const u64 k = S.exch[j];
             keysOut[S.delta[digit_of(k, pass.shift, pass.mask)] + j] = k;
         }
-    }
-    if (HAS_VAL) {
-        u64 v[ITEMS_T];
+    } else {
 #pragma unroll
         for (int i = 0; i < ITEMS_T; i++) {
-            const u32 local = warpBase + i * 32 + lane;
-            v[i] = local < tileValid ? valsIn[tileBase + local] : 0;
+            const u32 j = tid + i * BLOCK_T;
+            if (j < tileValid) { const u64 k = S.exch[j]; keysOut[S.delta[digit_of(k, pass.shift, pass.mask)] + j] = k; }
         }
+    }
+    if (HAS_VAL) {
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < ITEMS_T; i++) S.exch[rank[i]] = v[i];
+        for (int i = 0; i < ITEMS_T; i++) S.exch[pos[i]] = v[i];
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < ITEMS_T; i++) {
             const u32 j = tid + i * BLOCK_T;
-            if (j < tileValid) valsOut[S.delta[S.digitAt[j]] + j] = S.exch[j];
+            if (full || j < tileValid) valsOut[S.delta[S.digitAt[j]] + j] = S.exch[j];
         }
     }
 }
@@ -447,12 +461,12 @@ inline void launch_variant(int variant, bool hasVal, cudaStream_t st, const u64 
         default: launch_pass<512, 4, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
     }
 }
-inline int &default_variant(bool hasVal) { static int v[2] = {2, 2}; return v[hasVal ? 1 : 0]; }   // 512 threads x 8 keys: best measured on B200
+inline int &default_variant(bool hasVal) { static int v[2] = {0, 0}; return v[hasVal ? 1 : 0]; }   // 256 threads x 16 keys: best measured on B200
 
 // Input in (keysA, valsA); result pointer pair returned through outKeys/outVals (A or B, depending on the number
 // of passes).  Returns number of kernels launched, <0 on error.  passMs (optional): per-pass event timing sink.
 inline int radix_sort(cudaStream_t st, Workspace &ws, u64 *keysA, u64 *keysB, u64 *valsA, u64 *valsB, u64 n, const Plan &plan,
-                      u64 **outKeys, u64 **outVals, int smCount, int variant = -1) {
+                      u64 **outKeys, u64 **outVals, int smCount, int variant = -1, cudaEvent_t *passEvents = nullptr /*[2*plan.n]*/) {
     *outKeys = keysA; *outVals = valsA;
     if (n == 0 || plan.n == 0) return 0;
     if (n > MAX_N || tiles_for(n) > ws.tilesCap || plan.n > MAX_PASSES) return -1;
@@ -470,7 +484,9 @@ inline int radix_sort(cudaStream_t st, Workspace &ws, u64 *keysA, u64 *keysB, u6
     for (int p = 0; p < plan.n; p++) {
         cudaMemsetAsync(ws.tileState, 0, tiles_for(n) * RADIX * sizeof(u32), st);
         cudaMemsetAsync(ws.ticket, 0, sizeof(u32), st);
+        if (passEvents) cudaEventRecord(passEvents[2 * p], st);
         launch_variant(variant, valsA != nullptr, st, ki, ko, vi, vo, n, plan.p[p], ws.hist + p * RADIX, ws.tileState, ws.ticket, smCount);
+        if (passEvents) cudaEventRecord(passEvents[2 * p + 1], st);
         launches++;
         u64 *t = ki; ki = ko; ko = t;
         t = vi; vi = vo; vo = t;

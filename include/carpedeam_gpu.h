@@ -182,6 +182,8 @@ typedef struct {
     uint32_t sort1_passes, sort2_passes;/* P1, P2 */
     uint64_t kernel_launches;           /* kernels launched by this context since creation */
     float ms_extract, ms_sort1, ms_group, ms_sort2, ms_reduce, ms_rescore, ms_correct; /* last run, CUDA events */
+    /* dominant kernel: the LSD passes of sort 1 alone (events around every onesweep launch), records per launch */
+    float ms_sort1_passes; uint32_t n_sort1_pass_launches; uint64_t sort1_records;
 } cdg_stats;
 int cdg_get_stats(cdg_ctx *ctx, cdg_stats *out);
 
