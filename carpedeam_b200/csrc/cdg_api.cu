@@ -82,7 +82,7 @@ struct cdg_ctx {
     HostBuf hLineOff, hLineT, hKeep, hScore, hBits, hEvalue, hSeqId, hQS, hQE, hDS, hDE;
     u64 nLines = 0, nKept = 0; bool linesValid = false, alnsValid = false, alnsFromText = false;
     // correction
-    DevBuf dTables, dOut, dLik, dWideList, dRecvK, dRecvV, dRecv2, dQList; bool damageSet = false;
+    DevBuf dTables, dOut, dLik, dWideList, dRecvK, dRecvV, dRecv2, dQList, dPow31; bool damageSet = false;
 };
 
 namespace {
@@ -220,6 +220,8 @@ extern "C" int cdg_create(int device, cdg_ctx **out) {
     cudaFuncSetAttribute(cdgkmer::extract_short_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cdgkmer::EX_WARPS * 2048 * 4);
     cudaFuncSetAttribute(cdgalign::correct_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(cdgalign::CorrSmem));
     cudaFuncSetAttribute(cdgkmer::extract_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (32768 + 128) * 4);
+    if (ctx->dPow31.reserve(cdgkmer::POW31_TABLE * 8) != cudaSuccess) { delete ctx; return CDG_ERR_CUDA; }
+    cdgkmer::pow31_table_kernel<<<1, 32, 0, ctx->st>>>(ctx->dPow31.as<u64>(), cdgkmer::POW31_TABLE);
     if (const char *e = getenv("CDG_WIDE_THRESHOLD")) { long v = atol(e); if (v >= 1 && v < 65535) ctx->wideThreshold = (u32) v; }
     *out = ctx;
     return CDG_OK;
@@ -235,7 +237,7 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
                    &ctx->dOrdKA, &ctx->dOrdKB, &ctx->dOrdVA, &ctx->dOrdVB, &ctx->dRankOf, &ctx->dSlotRank, &ctx->dScratchOff, &ctx->dScratch, &ctx->dScratchKeep, &ctx->dShortScratch, &ctx->dShortKeep, &ctx->dHitRep, &ctx->dHitTgt,
                    &ctx->dHitScore, &ctx->dHitDiag, &ctx->dLineOff, &ctx->dLineQ, &ctx->dLineT, &ctx->dLinePref, &ctx->dLineDiag, &ctx->dKeep,
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
-                   &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2, &ctx->dQList};
+                   &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2, &ctx->dQList, &ctx->dPow31};
     for (DevBuf *b : d) b->release();
     HostBuf *h[] = {&ctx->hHitRep, &ctx->hHitTgt, &ctx->hHitScore, &ctx->hHitDiag, &ctx->hHitDiag16, &ctx->hLineOff, &ctx->hLineT, &ctx->hKeep,
                     &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE};
@@ -392,7 +394,7 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
     CK(ctx->dShortKeep.reserve(gridWarps * EX_MAXW));
     {
         const u32 maxW = ctx->maxLen >= (u32) p->k ? ctx->maxLen - p->k + 1 : 0;   // short sequences have <= 256 windows
-#define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT)
+#define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dPow31.as<u64>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT)
         if (maxW <= 64) extract_short_kernel<2><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
         else if (maxW <= 128) extract_short_kernel<4><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
         else extract_short_kernel<8><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;

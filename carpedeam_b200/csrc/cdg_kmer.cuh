@@ -93,6 +93,10 @@ CDG_HD bool is_short_seq(u32 L, int k, int kmersPerSeq, float scale) {   // no h
 }
 
 // powers of 31 (mod 2^64) for the identity hash Util::hash (Util.h:337-346): h = sum code_i * 31^(L-1-i)
+__global__ void pow31_table_kernel(u64 *__restrict__ tab, u32 n) {   // tab[e] = 31^e, e < n (n is small: sequential)
+    if (blockIdx.x == 0 && threadIdx.x == 0) { u64 r = 1; for (u32 e = 0; e < n; e++) { tab[e] = r; r *= 31; } }
+}
+static constexpr u32 POW31_TABLE = 1024;   // exponents below this come from the table (short sequences always do)
 CDG_D u64 pow31(u32 e) {
     u64 r = 1, b = 31;
     while (e) { if (e & 1) r *= b; b *= b; e >>= 1; }
@@ -184,7 +188,8 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
     const u64 *__restrict__ words, const u32 *__restrict__ xmask, const SeqMeta *__restrict__ meta,
     u64 n, ExtractParams P, const u64 *__restrict__ slotOff /*[n] first main slot of seq*/,
     u64 *__restrict__ mainKeys, u64 *__restrict__ mainVals, u64 *__restrict__ idKeys, u64 *__restrict__ idVals,
-    u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow, const u32 *__restrict__ rankOf, WinRec *__restrict__ scratch /*[gridWarps][2*EX_MAXW]*/,
+    u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow, const u32 *__restrict__ rankOf, const u64 *__restrict__ pow31tab,
+    WinRec *__restrict__ scratch /*[gridWarps][2*EX_MAXW]*/,
     u8 *__restrict__ scratchKeep /*[gridWarps][EX_MAXW]*/, unsigned long long *__restrict__ emitted) {
     extern __shared__ u32 bitmapAll[];   // [EX_WARPS][2048] : 65536 bits per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
             if (b0 < L) {
                 u64 h = 0;
                 for (u32 p = b0; p < b1; p++) h = h * 31 + (u64) base_code(w, xm, p);
-                part = h * pow31(L - b1);
+                part = h * pow31tab[L - b1];   // L - b1 < 288 for short sequences
             }
         }
 #pragma unroll

@@ -159,8 +159,8 @@ def test_fused_iteration_vs_reference(ctx, seqdb, pref, aln, corr, k, only_ext):
     assert st["n_hits"] == len(hits["rep"]) and st["kernel_launches"] > 0
 
 
-def _oracle_iteration(oracle, s, k=20):
-    hits = oracle.kmermatch(s, k=k)
+def _oracle_iteration(oracle, s, k=20, only_ext=0):
+    hits = oracle.kmermatch(s, k=k, only_ext=only_ext)
     n = s.n
     H = len(hits["rep"])
     lo = np.searchsorted(hits["rep"], np.arange(n + 1))
@@ -254,3 +254,43 @@ def test_correction_generic_kernel_path(oracle, monkeypatch):
         assert changed == 3348
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("k,only_ext", [(22, 1), (20, 0)])
+def test_long_contigs_and_u16_diagonal_wrap(ctx, oracle, k, only_ext):
+    """contigs of 40-150 kb next to reads cut from them: exercises the block-per-sequence extraction with an active hash
+    threshold, diagonals beyond +-32767 (stored as u16 and re-expanded by trying +-65536 multiples,
+    DistanceCalculator.h:93-113) and ext-flagged queries/targets in the correction."""
+    import carpedeam_b200 as cd
+    rng = np.random.default_rng(5 + k)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    contigs = [acgt[rng.integers(0, 4, L)].tobytes() for L in (150000, 70001, 40000)]
+    seqs, ext = [], []
+    for c in contigs:
+        seqs.append(c); ext.append(1)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    for c in contigs:
+        for _ in range(400):
+            L = int(rng.integers(60, 400)); st = int(rng.integers(0, len(c) - L))
+            r = bytearray(c[st:st + L])
+            for _m in range(int(rng.integers(0, 3))):
+                r[int(rng.integers(0, L))] = int(acgt[rng.integers(0, 4)])
+            r = bytes(r)
+            if rng.random() < 0.5:
+                r = r.translate(comp)[::-1]
+            seqs.append(r); ext.append(0)
+    order = rng.permutation(len(seqs))
+    seqs = [seqs[i] for i in order]; ext = [ext[i] for i in order]
+    s = SeqSet(seqs, ext=ext)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+    oracle.load_damage(os.path.join(GOLD, "dhigh"))
+    hits, alns, out, changed = ctx.iteration(kmer=cd.kmer_params(k=k, include_only_extendable=only_ext), fetch_hits=True)
+    ohits, r, line_off, oout = _oracle_iteration(oracle, s, k=k, only_ext=only_ext)
+    _hits_equal(hits, ohits)
+    assert np.abs(ohits["diag"].astype(np.int64)).max() > 0 and len(ohits["rep"]) > 500
+    for f in ("keep", "score", "bits", "qs", "qe", "ds", "de"):
+        assert np.array_equal(alns[f], r[f]), f
+    if not only_ext:   # (with include-only-extendable reads inside a contig are dropped, kmermatcher.cpp:526-536)
+        assert (np.abs(alns["qs"][alns["keep"] == 1].astype(np.int64)).max()) > 40000   # diagonals beyond the u16 range were recovered
+    assert np.array_equal(out, oout)
