@@ -82,6 +82,15 @@ class IterParams(C.Structure):
     _fields_ = [("kmer", KmerParams), ("rescore", RescoreParams), ("corr", CorrParams)]
 
 
+class PairModel(C.Structure):
+    _fields_ = [("log_lik", C.c_double * 352), ("log_excess", C.c_float), ("log_rand", C.c_float)]
+
+
+class Pairs(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("query", C.c_void_p), ("target", C.c_void_p), ("rev", C.c_void_p), ("q_start", C.c_void_p),
+                ("q_end", C.c_void_p), ("db_start", C.c_void_p), ("db_end", C.c_void_p), ("max_aln", C.c_void_p)]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_seqs", C.c_uint64), ("n_bases", C.c_uint64), ("n_records", C.c_uint64), ("n_grouped", C.c_uint64),
                 ("n_hits", C.c_uint64), ("n_alns", C.c_uint64), ("sort1_passes", C.c_uint32), ("sort2_passes", C.c_uint32),
@@ -113,6 +122,9 @@ def lib():
         L.cdg_correct.argtypes = [C.c_void_p, C.POINTER(CorrParams), C.c_void_p, C.POINTER(C.c_uint64)]
         L.cdg_correct_likelihoods.argtypes = [C.c_void_p, C.POINTER(CorrParams), C.c_void_p]
         L.cdg_iteration.argtypes = [C.c_void_p, C.POINTER(IterParams), C.POINTER(Hits), C.POINTER(Alns), C.c_void_p, C.POINTER(C.c_uint64)]
+        L.cdg_set_pair_model.argtypes = [C.c_void_p, C.POINTER(PairModel)]
+        L.cdg_pair_loglik.argtypes = [C.c_void_p, C.POINTER(Pairs), C.c_void_p, C.c_void_p]
+        L.cdg_pair_loglik_consensus.argtypes = [C.c_void_p, C.POINTER(Pairs), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cdg_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.cdg_test_radix_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
         L.cdg_test_hash_revcomp.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -129,6 +141,8 @@ def hostlib():
         H = C.CDLL(HOST_LIB_PATH)
         H.cdh_build_damage.argtypes = [C.c_char_p, C.c_double, C.POINTER(Damage), C.c_char_p, C.c_size_t]
         H.cdh_build_damage.restype = C.c_int
+        H.cdh_build_pair_model.argtypes = [C.c_char_p, C.c_double, C.c_float, C.c_float, C.POINTER(PairModel), C.c_char_p, C.c_size_t]
+        H.cdh_build_pair_model.restype = C.c_int
         _hostlib = H
     return _hostlib
 
@@ -155,6 +169,16 @@ def load_damage(prefix, seq_err=0.01):
     if rc != 0:
         raise CdgError("damage profile: " + err.value.decode())
     return d
+
+
+def load_pair_model(prefix, seq_err=0.001, rand_align_penal=0.85, excess_penal=0.0625):
+    """--ancient-damage PFX (+ --ext-random-align, --excess-penalty) -> cdg_pair_model (carpedeam_b200/host/damage.cpp)."""
+    m = PairModel()
+    err = C.create_string_buffer(512)
+    rc = hostlib().cdh_build_pair_model((prefix or "").encode(), seq_err, rand_align_penal, excess_penal, C.byref(m), err, 512)
+    if rc != 0:
+        raise CdgError("damage profile: " + err.value.decode())
+    return m
 
 
 class Context:
@@ -271,6 +295,25 @@ class Context:
                                      C.byref(alns) if alns is not None else None, C.c_void_p(out_ptr) if out_ptr else None, C.byref(ch)),
                  "cdg_iteration")
         return ch.value
+
+    def set_pair_model(self, model):
+        self._ck(lib().cdg_set_pair_model(self._h, C.byref(model)), "cdg_set_pair_model")
+
+    def pair_loglik(self, query, target, rev, qs, qe, ds, de, max_aln, consensus=None, cons_off=None):
+        """calcLikelihood (consensus=None) / calcLikelihoodConsensus over n pairs of the resident set -> (sLenNorm, sRatio)"""
+        query = np.ascontiguousarray(query, np.uint32); target = np.ascontiguousarray(target, np.uint32); rev = np.ascontiguousarray(rev, np.uint8)
+        qs, qe, ds, de = [np.ascontiguousarray(x, np.int32) for x in (qs, qe, ds, de)]
+        max_aln = np.ascontiguousarray(max_aln, np.uint32)
+        n = len(query)
+        P = Pairs(n, *[x.ctypes.data for x in (query, target, rev, qs, qe, ds, de, max_aln)])
+        a = np.zeros(n, np.float64); b = np.zeros(n, np.float64)
+        if consensus is None:
+            self._ck(lib().cdg_pair_loglik(self._h, C.byref(P), _ptr(a), _ptr(b)), "cdg_pair_loglik")
+        else:
+            consensus = np.ascontiguousarray(consensus, np.uint8); cons_off = np.ascontiguousarray(cons_off, np.uint64)
+            self._ck(lib().cdg_pair_loglik_consensus(self._h, C.byref(P), _ptr(consensus), consensus.nbytes, _ptr(cons_off), _ptr(a), _ptr(b)),
+                     "cdg_pair_loglik_consensus")
+        return a, b
 
     def stats(self):
         s = Stats()

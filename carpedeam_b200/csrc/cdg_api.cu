@@ -11,6 +11,7 @@
 #include "cdg_align.cuh"
 #include "cdg_common.cuh"
 #include "cdg_kmer.cuh"
+#include "cdg_pairlik.cuh"
 #include "cdg_sort.cuh"
 
 namespace {
@@ -83,6 +84,8 @@ struct cdg_ctx {
     u64 nLines = 0, nKept = 0; bool linesValid = false, alnsValid = false, alnsFromText = false;
     // correction
     DevBuf dTables, dOut, dLik, dWideList, dRecvK, dRecvV, dRecv2, dQList, dPow31; bool damageSet = false;
+    // pair likelihood (a19)
+    DevBuf dPairModel, dPairIn, dPairCons, dPairOut; bool pairModelSet = false;
 };
 
 namespace {
@@ -237,7 +240,8 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
                    &ctx->dOrdKA, &ctx->dOrdKB, &ctx->dOrdVA, &ctx->dOrdVB, &ctx->dRankOf, &ctx->dSlotRank, &ctx->dScratchOff, &ctx->dScratch, &ctx->dScratchKeep, &ctx->dShortScratch, &ctx->dShortKeep, &ctx->dHitRep, &ctx->dHitTgt,
                    &ctx->dHitScore, &ctx->dHitDiag, &ctx->dLineOff, &ctx->dLineQ, &ctx->dLineT, &ctx->dLinePref, &ctx->dLineDiag, &ctx->dKeep,
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
-                   &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2, &ctx->dQList, &ctx->dPow31};
+                   &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2, &ctx->dQList, &ctx->dPow31,
+                   &ctx->dPairModel, &ctx->dPairIn, &ctx->dPairCons, &ctx->dPairOut};
     for (DevBuf *b : d) b->release();
     HostBuf *h[] = {&ctx->hHitRep, &ctx->hHitTgt, &ctx->hHitScore, &ctx->hHitDiag, &ctx->hHitDiag16, &ctx->hLineOff, &ctx->hLineT, &ctx->hKeep,
                     &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE};
@@ -817,6 +821,76 @@ extern "C" int cdg_iteration(cdg_ctx *ctx, const cdg_iter_params *p, cdg_hits *h
     rc = run_correct(ctx, &p->corr, out_data, n_changed, nullptr);
     int rc2 = wait_exports(ctx);
     return rc ? rc : rc2;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// a19: damage-aware pair likelihood
+extern "C" int cdg_set_pair_model(cdg_ctx *ctx, const cdg_pair_model *m) {
+    if (!ctx || !m) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    static_assert(sizeof(cdg_pair_model) == sizeof(cdgpair::PairModel), "pair model layout");
+    CK(ctx->dPairModel.reserve(sizeof(cdgpair::PairModel)));
+    CK(cudaMemcpyAsync(ctx->dPairModel.p, m, sizeof(cdg_pair_model), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->pairModelSet = true;
+    return CDG_OK;
+}
+
+static int run_pair_loglik(cdg_ctx *ctx, const cdg_pairs *P, const uint8_t *cons, uint64_t consBytes, const uint64_t *consOff, double *sLen,
+                           double *sRatio) {
+    if (!ctx || !P || !sLen || !sRatio) return CDG_ERR_ARG;
+    if (!ctx->pairModelSet) return fail(ctx, CDG_ERR_ARG, "cdg_pair_loglik: cdg_set_pair_model not called");
+    if (ctx->n == 0) return fail(ctx, CDG_ERR_ARG, "cdg_pair_loglik: no resident sequence set");
+    const u64 n = P->n;
+    if (n == 0) return CDG_OK;
+    CK(cudaSetDevice(ctx->device));
+    // validate on the host what would otherwise be an out-of-bounds device read
+    for (u64 i = 0; i < n; i++) {
+        if (P->query[i] >= ctx->n || P->target[i] >= ctx->n)
+            return fail(ctx, CDG_ERR_ARG, "cdg_pair_loglik: pair %llu: sequence index out of range", (unsigned long long) i);
+        if (P->q_start[i] < 0 || P->db_start[i] < 0 || P->q_end[i] < P->q_start[i] || P->db_end[i] - P->db_start[i] != P->q_end[i] - P->q_start[i])
+            return fail(ctx, CDG_ERR_ARG, "cdg_pair_loglik: pair %llu: coordinates are not an oriented ungapped alignment", (unsigned long long) i);
+        if (cons && consOff[i] > consBytes) return fail(ctx, CDG_ERR_ARG, "cdg_pair_loglik_consensus: pair %llu: consensus offset out of range", (unsigned long long) i);
+    }
+    // one staging buffer: query, target, qS, qE, dS, dE, maxAln (u32 each) | rev (u8) | consOff (u64)
+    const u64 words = 7 * n;
+    const u64 consOffAt = (words * 4 + n + 7) & ~7ull;
+    CK(ctx->dPairIn.reserve(consOffAt + n * 8));
+    u8 *base = ctx->dPairIn.as<u8>();
+    const void *src[7] = {P->query, P->target, P->q_start, P->q_end, P->db_start, P->db_end, P->max_aln};
+    for (int a = 0; a < 7; a++) CK(cudaMemcpyAsync(base + (u64) a * n * 4, src[a], n * 4, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(base + words * 4, P->rev, n, cudaMemcpyHostToDevice, ctx->st));
+    if (cons) {
+        CK(ctx->dPairCons.reserve(consBytes + 16));
+        CK(cudaMemcpyAsync(ctx->dPairCons.p, cons, consBytes, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(base + consOffAt, consOff, n * 8, cudaMemcpyHostToDevice, ctx->st));
+    }
+    CK(ctx->dPairOut.reserve(2 * n * 8));
+    double *dLen = ctx->dPairOut.as<double>(), *dRatio = dLen + n;
+    const u32 *w = (const u32 *) base;
+    const unsigned grid = (unsigned) std::min<u64>((n + cdgpair::PL_WARPS - 1) / cdgpair::PL_WARPS, (u64) ctx->smCount * 8);
+#define CDG_PAIR_ARGS ctx->dData.as<u8>(), ctx->dMeta.as<SeqMeta>(), n, w, w + n, base + words * 4, (const i32 *) (w + 2 * n), (const i32 *) (w + 3 * n), \
+                      (const i32 *) (w + 4 * n), (const i32 *) (w + 5 * n), w + 6 * n, ctx->dPairCons.as<u8>(), (const u64 *) (base + consOffAt),                 \
+                      ctx->dPairModel.as<cdgpair::PairModel>(), dLen, dRatio
+    if (cons) cdgpair::pair_loglik_kernel<1><<<grid, cdgpair::PL_WARPS * 32, 0, ctx->st>>>(CDG_PAIR_ARGS);
+    else cdgpair::pair_loglik_kernel<0><<<grid, cdgpair::PL_WARPS * 32, 0, ctx->st>>>(CDG_PAIR_ARGS);
+#undef CDG_PAIR_ARGS
+    ctx->launches++;
+    CKL();
+    CK(cudaMemcpyAsync(sLen, dLen, n * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(sRatio, dRatio, n * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return CDG_OK;
+}
+
+extern "C" int cdg_pair_loglik(cdg_ctx *ctx, const cdg_pairs *pairs, double *s_len_norm, double *s_ratio) {
+    return run_pair_loglik(ctx, pairs, nullptr, 0, nullptr, s_len_norm, s_ratio);
+}
+
+extern "C" int cdg_pair_loglik_consensus(cdg_ctx *ctx, const cdg_pairs *pairs, const uint8_t *consensus, uint64_t consensus_bytes,
+                                         const uint64_t *cons_off, double *s_len_norm, double *s_ratio) {
+    if (!consensus || !cons_off) return CDG_ERR_ARG;
+    return run_pair_loglik(ctx, pairs, consensus, consensus_bytes, cons_off, s_len_norm, s_ratio);
 }
 
 extern "C" int cdg_get_stats(cdg_ctx *ctx, cdg_stats *out) {

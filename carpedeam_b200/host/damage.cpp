@@ -65,7 +65,8 @@ Matrix4 matrix_from_rates(const Rates &r) {
 
 }   // namespace
 
-extern "C" int cdh_build_damage(const char *prefix, double seq_err, cdg_damage *out, char *errbuf, size_t errlen) {
+// D[11] / Drev[11] of initDeamProbabilities (nuclassembleUtil.cpp:821-1007)
+static int build_matrices(const char *prefix, Matrix4 *D, Matrix4 *Drev, char *errbuf, size_t errlen) {
     std::string pfx = prefix ? prefix : "";
     std::vector<Rates> p5, p3;
     std::string err;
@@ -90,7 +91,6 @@ extern "C" int cdh_build_damage(const char *prefix, double seq_err, cdg_damage *
     std::vector<Matrix4> all;
     for (const Rates &r : p5) { Matrix4 m = matrix_from_rates(r); m.p[2][0] = defGA; m.p[2][2] = defGG; all.push_back(m); }
     for (const Rates &r : p3) { Matrix4 m = matrix_from_rates(r); m.p[1][1] = defCC; m.p[1][3] = defCT; all.push_back(m); }
-    Matrix4 D[11], Drev[11];
     for (int l = 0; l < 11; l++) D[l] = interior;
     for (int l = 0; l < 5; l++) { D[l] = all[l]; D[6 + l] = all[all.size() - 5 + l]; }
     for (int l = 0; l < 11; l++) {   // :995-1005
@@ -99,7 +99,14 @@ extern "C" int cdh_build_damage(const char *prefix, double seq_err, cdg_damage *
         Drev[l].p[1][3] = e.p[2][0]; Drev[l].p[1][1] = e.p[2][2];
         Drev[l].p[2][0] = e.p[1][3]; Drev[l].p[2][2] = e.p[1][1];
     }
-    const double SMOOTHING_VALUE = 0.001;   // correction.cpp:2
+    return 0;
+}
+
+static const double SMOOTHING_VALUE = 0.001;   // correction.cpp:2, nuclassembleUtil.cpp:2
+
+extern "C" int cdh_build_damage(const char *prefix, double seq_err, cdg_damage *out, char *errbuf, size_t errlen) {
+    Matrix4 D[11], Drev[11];
+    if (build_matrices(prefix, D, Drev, errbuf, errlen)) return -1;
     for (int l = 0; l < 11; l++)
         for (int q = 0; q < 4; q++)
             for (int t = 0; t < 4; t++) {
@@ -112,5 +119,34 @@ extern "C" int cdh_build_damage(const char *prefix, double seq_err, cdg_damage *
             ld p = (q == b) ? 1 - e : e / 3;
             out->log_seq_err[q][b] = (double) logl(p);
         }
+    return 0;
+}
+
+// Pair-likelihood model: the per-column term of calcLikelihood / calcLikelihoodConsensus
+// (nuclassembleUtil.cpp:150-168, :262-283) tabulated over (strand, class, qBase, tBase) in the reference's arithmetic:
+// match = (double) max((long double) 1e-3, p[q][x]); lik (double) += seqErr.p[x][t] (long double) * match; log(lik) in double.
+// seq_err = 0.001 in ancient_read_assemble (ancientReadsResults.cpp:172); the two penalties enter as logf(float).
+extern "C" int cdh_build_pair_model(const char *prefix, double seq_err, float rand_align_penal, float excess_penal, cdg_pair_model *out,
+                                    char *errbuf, size_t errlen) {
+    Matrix4 D[11], Drev[11];
+    if (build_matrices(prefix, D, Drev, errbuf, errlen)) return -1;
+    ld e = (ld) seq_err;
+    Matrix4 se;
+    for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) se.p[a][b] = (a == b) ? 1 - e : e / 3;
+    for (int rev = 0; rev < 2; rev++)
+        for (int l = 0; l < 11; l++) {
+            const Matrix4 &m = rev ? Drev[l] : D[l];
+            for (int q = 0; q < 4; q++)
+                for (int t = 0; t < 4; t++) {
+                    double lik = 0;
+                    for (int x = 0; x < 4; x++) {
+                        double match = (double) std::max((ld) SMOOTHING_VALUE, m.p[q][x]);
+                        lik += (se.p[x][t] * match);
+                    }
+                    out->log_lik[rev][l][q][t] = std::log(lik);
+                }
+        }
+    out->log_excess = logf(excess_penal);
+    out->log_rand = logf(rand_align_penal);
     return 0;
 }

@@ -147,6 +147,37 @@ int cdg_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data, uint6
  * evaluated; base_offset = prefix sum of lens.  Debug/validation entry point. */
 int cdg_correct_likelihoods(cdg_ctx *ctx, const cdg_corr_params *p, double *lik);
 
+/* ---- damage-aware pair likelihood (extension scoring) ---------------------------------
+ * calcLikelihood (src/assembler/nuclassembleUtil.cpp:95-200) and calcLikelihoodConsensus (:203-374) as r_s_pair calls
+ * them (src/assembler/ancientReadsResults.cpp:48-70).  The per-column term depends only on (strand, position class,
+ * query base, target base); the host tabulates it (carpedeam_b200/host/damage.cpp: cdh_build_pair_model):
+ *   log_lik[rev][l][q][t] = log( sum_x seqErr.p[x][t] * max(1e-3, (rev ? Drev : D)[l].p[q][x]) ),  A0 C1 G2 T3
+ *   log_excess = logf(--excess-penalty 0.0625f), log_rand = logf(--ext-random-align 0.85f)  (float, as the reference) */
+typedef struct {
+    double log_lik[2][11][4][4];
+    float log_excess;
+    float log_rand;
+} cdg_pair_model;
+int cdg_set_pair_model(cdg_ctx *ctx, const cdg_pair_model *m);
+
+/* n pairs over the resident set; coordinates are the reference's working frame after ancientReadsResults.cpp:225-236:
+ * q_start <= q_end, and for rev[i] != 0 the target is reverse-complemented (getNuclRevFragment) and db_start/db_end index
+ * that oriented target.  max_aln = the maxAln argument (longest left/right overlap of the query). */
+typedef struct {
+    uint64_t n;
+    const uint32_t *query, *target;
+    const uint8_t *rev;
+    const int32_t *q_start, *q_end, *db_start, *db_end;
+    const uint32_t *max_aln;
+} cdg_pairs;
+/* calcLikelihood: columns q_start..q_end of the query read against db_start.. of the oriented target.
+ * Outputs (host, n doubles each): scorePerRes::sLenNorm and ::sRatio. */
+int cdg_pair_loglik(cdg_ctx *ctx, const cdg_pairs *pairs, double *s_len_norm, double *s_ratio);
+/* calcLikelihoodConsensus: the query side is the caller's consensus string of pair i, consensus + cons_off[i], 3*qLen bytes
+ * ('N' = no call; layout of consensusCaller, nuclassembleUtil.cpp:570-702), qLen = length of resident sequence query[i]. */
+int cdg_pair_loglik_consensus(cdg_ctx *ctx, const cdg_pairs *pairs, const uint8_t *consensus, uint64_t consensus_bytes,
+                              const uint64_t *cons_off, double *s_len_norm, double *s_ratio);
+
 /* ---- fused iteration: kmermatch -> rescore -> correct with no host round trip ------------------ */
 typedef struct {
     cdg_kmer_params kmer;

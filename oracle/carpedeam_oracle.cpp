@@ -532,3 +532,72 @@ extern "C" void orc_correct(const char *blob, const u64 *off, const u32 *len, co
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// damage-aware pair likelihood: calcLikelihood (nuclassembleUtil.cpp:95-200),
+// calcLikelihoodConsensus (:203-374), called through r_s_pair (ancientReadsResults.cpp:48-70, D or Drev by
+// isRevToAlignment).  Pinned by tests/golden/pairlik_kat.txt (outputs of the reference's own functions).
+static double column_lik(const DiNuc &tp, const DiNuc &seqErr, int qBase, int tBase) {   // :150-165
+    double lik = 0;
+    for (int x = 0; x < 4; x++) {
+        double match = (double) std::max((long double) SMOOTH, tp.p[qBase][x]);
+        long double tErr = seqErr.p[x][tBase];
+        lik += (tErr * match);
+    }
+    return lik;
+}
+static const DiNuc &class_of(const std::vector<DiNuc> &tab, unsigned pos, unsigned dbLen) {   // subdeam_lookup :126-136
+    if (pos >= dbLen - 5) return tab[6 + (pos - (dbLen - 5))];   // the last loop overwrites the earlier ones
+    return tab[pos < 5 ? pos : 5];
+}
+static void oriented_target(const char *t, unsigned dbLen, bool rev, std::string &out) {
+    out.assign(t, dbLen);
+    if (rev) for (unsigned p = 0; p < dbLen; p++) { char r = NUM2AA[rev_code(map_letter((unsigned char) t[dbLen - 1 - p]))]; out[p] = (r == 'X') ? 'N' : r; }
+}
+static void finish_pair(long double likMod, unsigned maxAln, unsigned counted, float randAlnPenal, float excessPenal, double *sLen, double *sRatio) {
+    unsigned excess = maxAln - counted;                // unsigned wrap kept (:178, :331)
+    // `log(float)` resolves to the float overload there, so both products are FLOAT products (unsigned * float),
+    // pinned by the known answers: (float) maxAln * logf(0.85f) reproduces sRatio to the last bit
+    likMod += (float) excess * logf(excessPenal);
+    double randAln = (float) maxAln * logf(randAlnPenal);
+    *sLen = (double) likMod;
+    *sRatio = 1.0 / (1.0 + exp(randAln - (double) likMod));
+}
+// coordinates in the oriented frame; `target` is the stored sequence (reverse-complemented here when rev)
+extern "C" void orc_pair_loglik(const char *query, const char *target, unsigned dbLen, int rev, int qStart, int dbStart,
+                                unsigned alnLen, unsigned maxAln, double seqErrRate, float randAlnPenal, float excessPenal,
+                                double *sLen, double *sRatio) {
+    DiNuc seqErr; long double err = (long double) seqErrRate;
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) seqErr.p[i][j] = (i == j) ? 1 - err : err / 3;
+    const std::vector<DiNuc> &tab = rev ? g_Drev : g_D;
+    std::string t; oriented_target(target, dbLen, rev != 0, t);
+    long double likMod = 0.0;
+    for (unsigned c = 0; c < alnLen; c++)
+        likMod += log(column_lik(class_of(tab, dbStart + c, dbLen), seqErr, nuc_map(query[qStart + c]), nuc_map(t[dbStart + c])));
+    finish_pair(likMod, maxAln, alnLen, randAlnPenal, excessPenal, sLen, sRatio);
+}
+extern "C" void orc_pair_loglik_consensus(const char *consensus, unsigned qLen, const char *target, unsigned dbLen, int rev,
+                                          int qStart, int qEnd, int dbStart, int dbEnd, unsigned alnLen, unsigned maxAln,
+                                          double seqErrRate, float randAlnPenal, float excessPenal, double *sLen, double *sRatio) {
+    DiNuc seqErr; long double err = (long double) seqErrRate;
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) seqErr.p[i][j] = (i == j) ? 1 - err : err / 3;
+    const std::vector<DiNuc> &tab = rev ? g_Drev : g_D;
+    std::string t; oriented_target(target, dbLen, rev != 0, t);
+    const bool rightStart = dbStart == 0 && (unsigned) qEnd == qLen - 1;
+    const bool leftStart = qStart == 0 && (unsigned) dbEnd == dbLen - 1;
+    long double likMod = 0.0; unsigned counted = 0;
+    if (leftStart || rightStart) {
+        unsigned pad = qLen - (dbLen - alnLen);   // consensusStart :246,:289
+        // left: the target sits at consensus[pad ..]; right: it ends pad columns before the end of the 3*qLen consensus
+        unsigned base = leftStart ? pad : 3 * qLen - (dbLen + pad);
+        unsigned tIdx = 0;
+        for (unsigned j = 0; j < dbLen; j++) {
+            if (t[j] != 'N') tIdx++;
+            char c = consensus[base + j];
+            if (c == 'N' || t[j] == 'N') continue;
+            counted++;
+            likMod += log(column_lik(class_of(tab, tIdx - 1, dbLen), seqErr, nuc_map(c), nuc_map(t[j])));
+        }
+    }
+    finish_pair(likMod, maxAln, counted, randAlnPenal, excessPenal, sLen, sRatio);
+}

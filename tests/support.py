@@ -62,6 +62,20 @@ class SeqSet:
         return {int(k): i for i, k in enumerate(self.keys)}
 
 
+def load_pairlik_kat():
+    """tests/golden/pairlik_kat.txt (oracle/ref_pairlik.cpp): outputs of the reference's calcLikelihood[Consensus]."""
+    out = []
+    for line in open(os.path.join(GOLD, "pairlik_kat.txt")):
+        f = line.rstrip("\n").split("\t")
+        if f[0] == "L":
+            out.append(dict(mode="L", rev=int(f[1]), qs=int(f[2]), qe=int(f[3]), ds=int(f[4]), de=int(f[5]), max_aln=int(f[6]),
+                            query=f[7].encode(), target=f[8].encode(), slen=float(f[9]), sratio=float(f[10])))
+        else:
+            out.append(dict(mode="C", rev=int(f[1]), qlen=int(f[2]), qs=int(f[3]), qe=int(f[4]), ds=int(f[5]), de=int(f[6]),
+                            max_aln=int(f[7]), query=f[8].encode(), target=f[9].encode(), slen=float(f[10]), sratio=float(f[11])))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def build_oracle():
     subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
@@ -136,6 +150,24 @@ class Oracle:
         D = np.zeros((11, 4, 4)); R = np.zeros((11, 4, 4))
         self.L.orc_get_damage(C.c_void_p(D.ctypes.data), C.c_void_p(R.ctypes.data))
         return D, R
+
+    def pair_loglik(self, query, target, rev, q_start, db_start, aln_len, max_aln, seq_err=0.001, rand=0.85, excess=0.0625):
+        """calcLikelihood (nuclassembleUtil.cpp:95-200); target = stored bytes, coordinates in the oriented frame."""
+        a = C.c_double(); b = C.c_double()
+        self.L.orc_pair_loglik(query, target, C.c_uint(len(target)), C.c_int(rev), C.c_int(q_start), C.c_int(db_start),
+                               C.c_uint(aln_len), C.c_uint(max_aln), C.c_double(seq_err), C.c_float(rand), C.c_float(excess),
+                               C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def pair_loglik_consensus(self, consensus, q_len, target, rev, q_start, q_end, db_start, db_end, max_aln,
+                              seq_err=0.001, rand=0.85, excess=0.0625):
+        """calcLikelihoodConsensus (nuclassembleUtil.cpp:203-374)."""
+        a = C.c_double(); b = C.c_double()
+        self.L.orc_pair_loglik_consensus(consensus, C.c_uint(q_len), target, C.c_uint(len(target)), C.c_int(rev), C.c_int(q_start),
+                                         C.c_int(q_end), C.c_int(db_start), C.c_int(db_end), C.c_uint(q_end - q_start + 1),
+                                         C.c_uint(max_aln), C.c_double(seq_err), C.c_float(rand), C.c_float(excess),
+                                         C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def correct(self, s, aln_off, t_idx, seqid, qs, qe, ds, de, seqid_thr=0.9, ry_thr=0.99, seq_err=0.01, want_lik=False):
         aln_off = np.ascontiguousarray(aln_off, np.uint64); t_idx = np.ascontiguousarray(t_idx, np.uint32)

@@ -63,3 +63,29 @@ def test_damage_profile_errors():
     import carpedeam_b200 as cd
     with pytest.raises(cd.CdgError):
         cd.load_damage("/nonexistent/prefix")
+
+
+def test_host_pair_model_matches_oracle_columns(oracle):
+    """cdh_build_pair_model tabulates the per-column term of calcLikelihood: a one-column pair through the oracle
+    (restatement pinned by tests/golden/pairlik_kat.txt) must give the same log for every (strand, class, qBase, tBase)."""
+    import carpedeam_b200 as cd
+    cd.build()
+    pfx = os.path.join(GOLD, "dhigh")
+    m = cd.load_pair_model(pfx)
+    oracle.load_damage(pfx)
+    tab = np.array(m.log_lik).reshape(2, 11, 4, 4)
+    assert m.log_excess == np.log(np.float32(0.0625)) and m.log_rand == np.log(np.float32(0.85))
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    dbLen = 30
+    for rev in (0, 1):
+        for cls in range(11):
+            pos = cls if cls < 5 else (12 if cls == 5 else dbLen - 5 + (cls - 6))
+            for qi, qb in enumerate("ACGT"):
+                for ti, tb in enumerate("ACGT"):
+                    t = ["A"] * dbLen
+                    t[pos] = tb
+                    stored = "".join(comp[c] for c in reversed(t)) if rev else "".join(t)
+                    query = "A" * pos + qb
+                    # one aligned column at oriented target position pos; maxAln = 1 -> no excess term
+                    a, _ = oracle.pair_loglik(query.encode(), stored.encode(), rev, pos, pos, 1, 1)
+                    assert a == tab[rev, cls, qi, ti], (rev, cls, qb, tb, a, tab[rev, cls, qi, ti])

@@ -294,3 +294,56 @@ def test_long_contigs_and_u16_diagonal_wrap(ctx, oracle, k, only_ext):
     if not only_ext:   # (with include-only-extendable reads inside a contig are dropped, kmermatcher.cpp:526-536)
         assert (np.abs(alns["qs"][alns["keep"] == 1].astype(np.int64)).max()) > 40000   # diagonals beyond the u16 range were recovered
     assert np.array_equal(out, oout)
+
+
+def test_pair_likelihood_known_answers(ctx, oracle):
+    """a19: cdg_pair_loglik / cdg_pair_loglik_consensus against the outputs of the reference's own calcLikelihood /
+    calcLikelihoodConsensus (tests/golden/pairlik_kat.txt) and against the oracle.  Tolerance: north_star asks for 1e-5
+    relative; the fp64 warp reduction agrees with the reference's long double sums to ~1e-15, asserted at 1e-12."""
+    import carpedeam_b200 as cd
+    from support import load_pairlik_kat
+    kat = load_pairlik_kat()
+    seqs = []
+    for k in kat:   # consensus-mode queries: the middle third of the consensus is the query read ('N' holes -> 'A', only its length matters)
+        q = k["query"] if k["mode"] == "L" else k["query"][k["qlen"]:2 * k["qlen"]].replace(b"N", b"A")
+        seqs += [q, k["target"]]
+    s = SeqSet(seqs)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_pair_model(cd.load_pair_model(os.path.join(GOLD, "dhigh")))
+    oracle.load_damage(os.path.join(GOLD, "dhigh"))
+    for mode in ("L", "C"):
+        idx = [i for i, k in enumerate(kat) if k["mode"] == mode]
+        sub = [kat[i] for i in idx]
+        q = [2 * i for i in idx]; t = [2 * i + 1 for i in idx]
+        args = (q, t, [k["rev"] for k in sub], [k["qs"] for k in sub], [k["qe"] for k in sub], [k["ds"] for k in sub],
+                [k["de"] for k in sub], [k["max_aln"] for k in sub])
+        if mode == "L":
+            a, b = ctx.pair_loglik(*args)
+        else:
+            blob = b"".join(k["query"] for k in sub)
+            off = np.cumsum([0] + [len(k["query"]) for k in sub[:-1]]).astype(np.uint64)
+            a, b = ctx.pair_loglik(*args, consensus=np.frombuffer(blob, np.uint8), cons_off=off)
+        want_a = np.array([k["slen"] for k in sub]); want_b = np.array([k["sratio"] for k in sub])
+        assert np.all(np.abs(a - want_a) <= 1e-12 * np.abs(want_a)), np.abs(a / want_a - 1).max()
+        assert np.all(np.abs(b - want_b) <= 1e-10 * np.abs(want_b) + 1e-300), (b, want_b)
+        assert (want_b > 0.5).sum() >= 0 and (want_a > -1e9).sum() > 100      # mostly real (non-wrapped) cases
+        for j in range(0, len(sub), 17):   # oracle cross-check on the same inputs
+            k = sub[j]
+            if mode == "L":
+                oa, ob = oracle.pair_loglik(k["query"], k["target"], k["rev"], k["qs"], k["ds"], k["qe"] - k["qs"] + 1, k["max_aln"])
+            else:
+                oa, ob = oracle.pair_loglik_consensus(k["query"], k["qlen"], k["target"], k["rev"], k["qs"], k["qe"], k["ds"], k["de"], k["max_aln"])
+            assert abs(a[j] - oa) <= 1e-12 * abs(oa)
+
+
+def test_pair_likelihood_argument_errors(ctx):
+    import carpedeam_b200 as cd
+    s = SeqSet([b"ACGTACGTACGTACGTACGT", b"ACGTACGTACGTACGTACGTAA"])
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_pair_model(cd.load_pair_model(""))
+    with pytest.raises(cd.CdgError):
+        ctx.pair_loglik([0], [7], [0], [0], [9], [0], [9], [10])          # target index out of range
+    with pytest.raises(cd.CdgError):
+        ctx.pair_loglik([0], [1], [0], [0], [9], [0], [8], [10])          # not an ungapped alignment
+    a, b = ctx.pair_loglik([0], [1], [0], [0], [19], [0], [19], [20])     # no damage, identical columns
+    assert abs(a[0] - (20 * np.log(0.999 + 0.001 / 3 * 3 * 1e-3))) < 1e-9
