@@ -218,9 +218,6 @@ extern "C" int cdg_create(int device, cdg_ctx **out) {
     for (int i = 0; i < EV_N; i++) { cudaEventCreate(&ctx->ev[i]); ctx->evValid[i] = false; }
     for (int i = 0; i < 2 * cdgsort::MAX_PASSES; i++) cudaEventCreate(&ctx->passEv[i]);
     if (ctx->dScalars.reserve(SC_N * 8) != cudaSuccess) { delete ctx; return CDG_ERR_CUDA; }
-    cudaFuncSetAttribute(cdgkmer::extract_short_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cdgkmer::EX_WARPS * 2048 * 4);
-    cudaFuncSetAttribute(cdgkmer::extract_short_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cdgkmer::EX_WARPS * 2048 * 4);
-    cudaFuncSetAttribute(cdgkmer::extract_short_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cdgkmer::EX_WARPS * 2048 * 4);
     cudaFuncSetAttribute(cdgalign::correct_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(cdgalign::CorrSmem));
     cudaFuncSetAttribute(cdgkmer::extract_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (32768 + 128) * 4);
     if (ctx->dPow31.reserve(cdgkmer::POW31_TABLE * 8) != cudaSuccess) { delete ctx; return CDG_ERR_CUDA; }
@@ -392,16 +389,24 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
     if ((rc = read_scalar(ctx, SC_NLONG, &nLong64))) return rc;
     if ((rc = read_scalar(ctx, SC_LONGSCR, &longScr))) return rc;
     const u32 nLong = (u32) nLong64;
-    const int shortBlocks = ctx->smCount * 3;
+    int perSm = 3;   // persistent grid: as many resident blocks as the registers allow
+    {
+        const u32 maxW0 = ctx->maxLen >= (u32) p->k ? ctx->maxLen - p->k + 1 : 0;
+        if (maxW0 <= 64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, extract_short_kernel<2>, EX_WARPS * 32, 0);
+        else if (maxW0 <= 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, extract_short_kernel<4>, EX_WARPS * 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, extract_short_kernel<8>, EX_WARPS * 32, 0);
+        if (perSm < 1) perSm = 1;
+    }
+    const int shortBlocks = ctx->smCount * perSm;
     const u64 gridWarps = (u64) shortBlocks * EX_WARPS;
     CK(ctx->dShortScratch.reserve(gridWarps * 2 * EX_MAXW * sizeof(WinRec)));
     CK(ctx->dShortKeep.reserve(gridWarps * EX_MAXW));
     {
         const u32 maxW = ctx->maxLen >= (u32) p->k ? ctx->maxLen - p->k + 1 : 0;   // short sequences have <= 256 windows
 #define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dPow31.as<u64>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT)
-        if (maxW <= 64) extract_short_kernel<2><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
-        else if (maxW <= 128) extract_short_kernel<4><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
-        else extract_short_kernel<8><<<shortBlocks, EX_WARPS * 32, EX_WARPS * 2048 * 4, ctx->st>>> CDG_EXTRACT_ARGS;
+        if (maxW <= 64) extract_short_kernel<2><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
+        else if (maxW <= 128) extract_short_kernel<4><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
+        else extract_short_kernel<8><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
 #undef CDG_EXTRACT_ARGS
     }
     ctx->launches++;

@@ -178,6 +178,7 @@ CDG_D void emit_identity(u64 seqHash, u64 seq, const ExtractParams &P, u64 *idKe
 
 static constexpr int EX_WARPS = 8;
 static constexpr int EX_MAXW = 256;   // windows per short sequence
+static constexpr int EX_BM_WORDS = 256;   // per-warp repeat-hint bitmap (8192 bits, indexed by the low 13 bits of the 16-bit hash)
 
 // ---- short sequences: one warp per sequence ------------------------------------------------------------
 // Fast path (no repeated k-mer inside the sequence): every valid window is emitted.  A per-warp bitmap over
@@ -191,10 +192,10 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
     u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow, const u32 *__restrict__ rankOf, const u64 *__restrict__ pow31tab,
     WinRec *__restrict__ scratch /*[gridWarps][2*EX_MAXW]*/,
     u8 *__restrict__ scratchKeep /*[gridWarps][EX_MAXW]*/, unsigned long long *__restrict__ emitted) {
-    extern __shared__ u32 bitmapAll[];   // [EX_WARPS][2048] : 65536 bits per warp
+    __shared__ u32 bitmapAll[EX_WARPS * EX_BM_WORDS];   // 8192 bits per warp: small, so that registers bound the occupancy
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u32 *bitmap = bitmapAll + warp * 2048;
-    for (int i = lane; i < 2048; i += 32) bitmap[i] = 0;
+    u32 *bitmap = bitmapAll + warp * EX_BM_WORDS;
+    for (int i = lane; i < EX_BM_WORDS; i += 32) bitmap[i] = 0;
     __syncwarp();
     const u64 gwarp = (u64) blockIdx.x * EX_WARPS + warp, nwarps = (u64) gridDim.x * EX_WARPS;
     WinRec *myScratch = scratch + gwarp * (2 * EX_MAXW);
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
         // windows: lane handles p = lane + 32*it
         WinRec rec[ITERS];
         u32 validMask = 0;   // bit it
-        u32 collide = 0;
+        u32 flagged = 0;     // bit it: the window's bitmap bit was already set (possible repeat)
 #pragma unroll
         for (int it = 0; it < ITERS; it++) {
             u32 p = lane + 32 * it;
@@ -237,17 +238,36 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
             if (p < W) ok = make_window(w, xm, p, L, P, rec[it]);
             if (ok) {
                 validMask |= 1u << it;
-                u32 bit = 1u << (rec[it].score & 31);
-                u32 old = atomicOr(&bitmap[rec[it].score >> 5], bit);
-                collide |= old & bit;
+                const u32 h = rec[it].score & (EX_BM_WORDS * 32 - 1);
+                u32 bit = 1u << (h & 31);
+                u32 old = atomicOr(&bitmap[h >> 5], bit);
+                if (old & bit) flagged |= 1u << it;
             }
         }
         __syncwarp();
-        // clear the bits again (cheaper than wiping 8 KB per sequence)
+        // clear the bits again (cheaper than wiping the bitmap per sequence)
 #pragma unroll
-        for (int it = 0; it < ITERS; it++) if (validMask & (1u << it)) bitmap[rec[it].score >> 5] = 0;
+        for (int it = 0; it < ITERS; it++) if (validMask & (1u << it)) bitmap[(rec[it].score & (EX_BM_WORDS * 32 - 1)) >> 5] = 0;
         __syncwarp();
-        collide = __any_sync(0xffffffffu, collide);
+        // a set bit is only a hint (the bitmap index is 13 bits of the hash): confirm by comparing the flagged window's
+        // k-mer with every other window of the sequence; only a true repeat takes the exact path
+        u32 collide = 0;
+        if (__any_sync(0xffffffffu, flagged)) {
+#pragma unroll
+            for (int it = 0; it < ITERS; it++) {
+                u32 fl = __ballot_sync(0xffffffffu, (flagged >> it) & 1u);
+                while (fl) {
+                    const int src = __ffs(fl) - 1; fl &= fl - 1;
+                    const u64 km = __shfl_sync(0xffffffffu, rec[it].kmer | CDG_B63, src);
+                    bool eq = false;
+#pragma unroll
+                    for (int i2 = 0; i2 < ITERS; i2++)
+                        eq |= ((validMask >> i2) & 1u) && (rec[i2].kmer | CDG_B63) == km && !(i2 == it && lane == src);
+                    collide |= eq ? 1u : 0u;
+                }
+            }
+            collide = __any_sync(0xffffffffu, collide);
+        }
 
         const u64 slot0 = slotAbs - P.slotBase;
         const u32 cap = kmer_capacity(L, P.k, P.kmersPerSeq, P.scale);
