@@ -343,7 +343,8 @@ static constexpr int CF_WARPS = 8;
 static constexpr int CF_CACHE = 32;
 using ::SeqMeta; using ::META_EXC; using ::META_EXT; using ::META_LEN;
 struct LineCache { u64 tOff[CF_CACHE]; u32 dL[CF_CACHE]; i32 qs[CF_CACHE]; i32 aln[CF_CACHE]; i32 ds[CF_CACHE]; u32 rev[CF_CACHE]; };
-struct CorrSmem { DamageTables T; u32 cnt[CF_WARPS][44][32]; LineCache lc[CF_WARPS]; u8 lut[256]; };   // lut: bits 0-1 forward base index, 2-3 reverse-complement base index
+static constexpr u32 CF_COMPACT_LEN = 96;   // queries up to this length evaluate only the columns where some counted target disagrees
+struct CorrSmem { DamageTables T; u32 cnt[CF_WARPS][44][32]; LineCache lc[CF_WARPS]; u8 lut[256]; u8 colList[CF_WARPS][CF_COMPACT_LEN]; int domOK; };   // lut: bits 0-1 forward base index, 2-3 reverse-complement base index
 
 __global__ void __launch_bounds__(256) meta_kernel(const u64 *__restrict__ off, const u64 *__restrict__ wordOff, const u32 *__restrict__ len,
                                                    const u8 *__restrict__ flags, const u8 *__restrict__ ext, u64 n, SeqMeta *__restrict__ meta) {
@@ -363,6 +364,29 @@ CDG_D u32 ry_dist_packed(const u64 *__restrict__ qw, u32 qs, const u64 *__restri
         u64 x = a ^ b;
         dist += __popcll((x ^ (x >> 1)) & 0x5555555555555555ull);
     }
+    return dist;
+}
+
+// RY distance (getRYSeqId) and, per 32-column query word, the columns where the oriented target differs from the query:
+// bit 62-2j of m<w> = column 32w+j mismatches (words beyond the third are not recorded; the caller only uses the masks
+// for queries of at most CF_COMPACT_LEN bases).  Same popcounts as ry_dist_packed, chunked by query word.
+CDG_D u32 ry_dist_mismatch(const u64 *__restrict__ qw, u32 qs, const u64 *__restrict__ tw, u32 dL, bool rev, u32 ds, u32 aln, u64 &m0, u64 &m1, u64 &m2) {
+    u32 dist = 0;
+    const u32 qe = qs + aln;
+    auto word = [&](u32 w, u64 &m, bool record) {
+        const u32 lo = max(qs, w << 5), hi = min(qe, (w + 1) << 5), c = hi - lo;
+        const u64 a = get_bases(qw, lo, c);
+        const u32 tp = ds + (lo - qs);
+        const u64 b = rev ? get_bases_rc(tw, dL, tp, c) : get_bases(tw, tp, c);
+        const u64 x = a ^ b;
+        dist += __popcll((x ^ (x >> 1)) & 0x5555555555555555ull);
+        if (record) m = ((x | (x >> 1)) & 0x5555555555555555ull) >> (2 * (lo & 31));
+    };
+    u64 unused = 0;
+    if (qs < 32 && qe > 0) word(0, m0, true);
+    if (qs < 64 && qe > 32) word(1, m1, true);
+    if (qs < 96 && qe > 64) word(2, m2, true);
+    for (u32 w = max(3u, qs >> 5); (w << 5) < qe; w++) word(w, unused, false);
     return dist;
 }
 
@@ -391,7 +415,7 @@ __global__ void __launch_bounds__(256) multi_line_queries_kernel(const u64 *__re
     if (multi) list[base + __popc(b & ((1u << lane) - 1))] = (u32) q;
 }
 
-__global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
+__global__ void __launch_bounds__(CF_WARPS * 32, 4) correct_fast_kernel(
     const u32 *__restrict__ qList, const u32 *__restrict__ qCount,
     const u8 *__restrict__ data, const SeqMeta *__restrict__ meta, const u64 *__restrict__ words, u64 qLo, u64 n,
     const u64 *__restrict__ lineOff, const u32 *__restrict__ lineT, const u8 *__restrict__ keep, const float *__restrict__ seqId,
@@ -407,6 +431,24 @@ __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
         const int fwd = nuc_map((unsigned char) i);
         const int rvi = nuc_map(t_char((const u8 *) &i, 1, true, 0));   // little-endian: the low byte of i is the character
         S.lut[i] = (u8) (fwd | (rvi << 2));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // A column whose counted target bases all equal the query base b keeps b whenever, for every other candidate x, each
+        // term of lik[b] is >= the matching term of lik[x] and the query term is larger by a margin far above the rounding
+        // error of the sums (mostLikeliBaseRead, correction.cpp:61-117; the :56-60 early return keeps b as well).  The tables
+        // decide whether that holds (it fails only for substitution rates above 0.5); if not, every column is evaluated.
+        bool ok = true;
+        for (int b = 0; b < 4; b++)
+            for (int x = 0; x < 4; x++) {
+                if (x == b) continue;
+                if (!(S.T.logSE[b][b] - S.T.logSE[x][b] >= 1e-6)) ok = false;
+                for (int l = 0; l < 11; l++) {
+                    if (!(S.T.logD[l][b][b] - S.T.logD[l][x][b] >= 1e-6)) ok = false;
+                    if (!(S.T.logDrev[l][b][b] >= S.T.logDrev[l][x][b])) ok = false;
+                }
+            }
+        S.domOK = ok ? 1 : 0;
     }
     __syncthreads();
     const DamageTables &T = S.T;
@@ -451,6 +493,8 @@ __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
         avCov = avCov / (float) qLen;
         // pass 2 (:273-323, :353-359), one line per lane
         u32 nSel = 0;
+        u64 mm0 = 0, mm1 = 0, mm2 = 0;   // columns where one of this lane's counted targets differs from the query
+        bool compact = S.domOK && likOut == nullptr && !qExc && qLen <= CF_COMPACT_LEN;
         for (u64 lb = l0; lb < l1; lb += 32) {
             const u64 l = lb + lane;
             u8 sel = 0;
@@ -466,7 +510,9 @@ __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
                     bool rev = false;
                     if (qs > qe) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; rev = true; }
                     u32 dist = 0;
-                    if (!qExc && !(tm.lenFlags & META_EXC)) dist = ry_dist_packed(qw, (u32) qs, words + tm.wordOff, dL, rev, (u32) ds, (u32) aln);
+                    u64 lm0 = 0, lm1 = 0, lm2 = 0;
+                    const bool packed = !qExc && !(tm.lenFlags & META_EXC);
+                    if (packed) dist = ry_dist_mismatch(qw, (u32) qs, words + tm.wordOff, dL, rev, (u32) ds, (u32) aln, lm0, lm1, lm2);
                     else {
                         const u8 *ts = data + tOff;
                         for (i32 p = 0; p < aln; p++) dist += (ry_map(q[qs + p]) != ry_map(t_char(ts, dL, rev, (u32) (ds + p)))) ? 1u : 0u;
@@ -477,9 +523,14 @@ __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
                     const bool pick = (ry >= thr && ds == 0 && (u32) qe == qLen - 1) || (ry >= thr && qs == 0 && de == (i32) dL - 1) ||
                                       (ry >= thr && avCov < 50);
                     const float sid = P.roundSeqId ? seqid_text_roundtrip(seqId[l]) : seqId[l];
-                    if (pick && ry >= thr && sid >= P.seqIdThr && aln >= 30) sel = rev ? 2 : 1;
+                    if (pick && ry >= thr && sid >= P.seqIdThr && aln >= 30) {
+                        sel = rev ? 2 : 1;
+                        if (packed) { mm0 |= lm0; mm1 |= lm1; mm2 |= lm2; } else sel |= 4;   // 4: a counted target needs the byte path
+                    }
                 }
             }
+            if (__any_sync(0xffffffffu, sel & 4)) compact = false;
+            sel &= 3;
             if (l < l1) lineSel[l] = sel;
             const u32 b = __ballot_sync(0xffffffffu, sel != 0);
             if (sel) {
@@ -495,14 +546,33 @@ __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
         }
         __syncwarp();
         u8 *o = out + qm.off;
-        for (u32 c0 = 0; c0 < qLen; c0 += 32) {
-            const u32 col = c0 + lane;
+        // columns to evaluate: all of them, or (short plain queries, dominance holds) only those where a counted target disagrees
+        u32 nCols = qLen;
+        u8 *colList = S.colList[warp];
+        if (compact) {
+            nCols = 0;
+#pragma unroll
+            for (int w = 0; w < 3; w++) {
+                const u64 mine = w == 0 ? mm0 : (w == 1 ? mm1 : mm2);
+                const u32 lo32 = __reduce_or_sync(0xffffffffu, (u32) mine), hi32 = __reduce_or_sync(0xffffffffu, (u32) (mine >> 32));
+                const u64 need = ((u64) hi32 << 32) | lo32;
+                const u32 c = 32 * w + lane;
+                const bool bit = ((need >> (62 - 2 * lane)) & 1ull) && c < qLen;
+                const u32 b = __ballot_sync(0xffffffffu, bit);
+                if (bit) colList[nCols + __popc(b & ((1u << lane) - 1))] = (u8) c;
+                nCols += __popc(b);
+            }
+            __syncwarp();
+        }
+        for (u32 c0 = 0; c0 < nCols; c0 += 32) {
+            const bool valid = c0 + lane < nCols;
+            const u32 col = compact ? (valid ? colList[c0 + lane] : 0u) : c0 + lane;
             unsigned long long mask = 0;
             if (nSel <= CF_CACHE) {
 #pragma unroll 4
                 for (u32 i = 0; i < nSel; i++) {
                     const i32 qs = LC.qs[i], aln = LC.aln[i];
-                    if (col < qLen && (i32) col >= qs && (i32) col < qs + aln)
+                    if (valid && (i32) col >= qs && (i32) col < qs + aln)
                         count_column(data, LC.tOff[i], LC.dL[i], LC.rev[i] != 0, (u32) LC.ds[i] + (col - (u32) qs), cnt, lane, lut, mask);
                 }
             } else {
@@ -515,7 +585,7 @@ __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
                     const bool rev = sel == 2;
                     if (rev) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; }
                     const i32 aln = max(abs(qe - qs), abs(de - ds)) + 1;
-                    if (col < qLen && (i32) col >= qs && (i32) col < qs + aln)
+                    if (valid && (i32) col >= qs && (i32) col < qs + aln)
                         count_column(data, tm.off, dL, rev, (u32) ds + (col - (u32) qs), cnt, lane, lut, mask);
                 }
             }
@@ -531,7 +601,7 @@ __global__ void __launch_bounds__(CF_WARPS * 32) correct_fast_kernel(
                 }
             }
             const u32 tot = cov0 + cov1 + cov2 + cov3;
-            if (col < qLen && tot > 1) {
+            if (valid && tot > 1) {
                 const unsigned char orig = q[col];
                 const int b = nuc_map(orig);
                 int nb = b;

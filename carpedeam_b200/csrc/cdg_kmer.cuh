@@ -185,7 +185,7 @@ static constexpr int EX_BM_WORDS = 256;   // per-warp repeat-hint bitmap (8192 b
 // the 16-bit hash detects possible repeats (equal k-mers have equal hashes); on a hit the warp ranks its
 // windows in shared... global scratch and lane 0 replays the reference's sequential loop.
 template <int ITERS>
-__global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
+__global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_short_kernel(
     const u64 *__restrict__ words, const u32 *__restrict__ xmask, const SeqMeta *__restrict__ meta,
     u64 n, ExtractParams P, const u64 *__restrict__ slotOff /*[n] first main slot of seq*/,
     u64 *__restrict__ mainKeys, u64 *__restrict__ mainVals, u64 *__restrict__ idKeys, u64 *__restrict__ idVals,
@@ -202,10 +202,14 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
     u8 *myKeep = scratchKeep + gwarp * EX_MAXW;
     unsigned long long localEmitted = 0;
 
+    // the loads that start a sequence (meta, rank, slot) are issued one sequence ahead
+    SeqMeta smN; smN.off = 0; smN.wordOff = 0; smN.lenFlags = 0; u32 rankN = 0; u64 slotN = 0;
+    if (gwarp < n) { smN = meta[gwarp]; rankN = rankOf[gwarp]; slotN = slotOff[gwarp]; }
     for (u64 seq = gwarp; seq < n; seq += nwarps) {
-        const SeqMeta sm = meta[seq];   // one 16-byte load: length and first word
-        const u32 myRank = rankOf[seq];
-        const u64 slotAbs = slotOff[seq];
+        const SeqMeta sm = smN;   // one 16-byte load: length and first word
+        const u32 myRank = rankN;
+        const u64 slotAbs = slotN;
+        if (seq + nwarps < n) { smN = meta[seq + nwarps]; rankN = rankOf[seq + nwarps]; slotN = slotOff[seq + nwarps]; }
         const u32 L = sm.lenFlags & META_LEN;
         if (!is_short_seq(L, P.k, P.kmersPerSeq, P.scale)) continue;   // handled by extract_long_kernel
         if (myRank < P.posLo || myRank >= P.posHi) continue;            // not in this rank's slice
@@ -219,7 +223,13 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
             const u32 b0 = lane * c, b1 = min(b0 + c, L);
             if (b0 < L) {
                 u64 h = 0;
-                for (u32 p = b0; p < b1; p++) h = h * 31 + (u64) base_code(w, xm, p);
+                u32 curW = 0xFFFFFFFFu, xx = 0; u64 ww = 0;   // the chunk's words are loaded once, not per base
+                for (u32 p = b0; p < b1; p++) {
+                    const u32 wi = p >> 5, o = p & 31;
+                    if (wi != curW) { ww = w[wi]; xx = xm[wi]; curW = wi; }
+                    const u64 code = ((xx >> (31 - o)) & 1u) ? 4ull : ((ww >> (62 - 2 * o)) & 3ull);
+                    h = h * 31 + code;
+                }
                 part = h * pow31tab[L - b1];   // L - b1 < 288 for short sequences
             }
         }
@@ -325,6 +335,11 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_short_kernel(
         }
         for (u32 s = written + lane; s < cap; s += 32) { mainKeys[slot0 + s] = CDG_SENTINEL; mainVals[slot0 + s] = 0; }
         localEmitted += written;
+        // next sequence's packed words towards L1 while this one's records drain
+        if (lane < 2 && seq + nwarps < n) {
+            const void *pw = lane == 0 ? (const void *) (words + smN.wordOff) : (const void *) (xmask + smN.wordOff);
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(pw));
+        }
     }
     if (lane == 0 && localEmitted) atomicAdd(emitted, localEmitted);
 }

@@ -347,3 +347,31 @@ def test_pair_likelihood_argument_errors(ctx):
         ctx.pair_loglik([0], [1], [0], [0], [9], [0], [8], [10])          # not an ungapped alignment
     a, b = ctx.pair_loglik([0], [1], [0], [0], [19], [0], [19], [20])     # no damage, identical columns
     assert abs(a[0] - (20 * np.log(0.999 + 0.001 / 3 * 3 * 1e-3))) < 1e-9
+
+
+@pytest.mark.parametrize("ct0,ga0", [(0.7, 0.65), (0.0, 0.0)])
+def test_correction_with_unusual_damage_profiles(ctx, oracle, tmp_path, ct0, ga0):
+    """The correction kernel skips columns where every counted target agrees with the query only when the damage tables
+    make that provably safe; rates above 0.5 (first case) switch the shortcut off, an all-zero profile (second case,
+    nuclassembleUtil.cpp:824-832 semantics through explicit zero rows) keeps it on.  Both must equal the oracle."""
+    import carpedeam_b200 as cd
+    hdr = "A>C\tA>G\tA>T\tC>A\tC>G\tC>T\tG>A\tG>C\tG>T\tT>A\tT>C\tT>G\n"
+    rows5 = [[0.0] * 12 for _ in range(5)]; rows3 = [[0.0] * 12 for _ in range(5)]
+    for i, f in enumerate((1.0, 0.6, 0.4, 0.3, 0.2)):
+        rows5[i][5] = ct0 * f; rows3[4 - i][6] = ga0 * f
+    pfx = str(tmp_path / "odd")
+    for name, rows in (("5p.prof", rows5), ("3p.prof", rows3)):
+        with open(pfx + name, "w") as f:
+            f.write(hdr + "".join("\t".join("%g" % v for v in r) + "\n" for r in rows))
+    s = SeqSet(synth_reads(6000, 30000, 21))
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_damage(cd.load_damage(pfx))
+    oracle.load_damage(pfx)
+    hits, alns, out, changed = ctx.iteration(fetch_hits=True)
+    ohits, r, line_off, oout = _oracle_iteration(oracle, s)
+    assert np.array_equal(out, oout)
+    assert changed == int((out != s.blob).sum())
+    if ct0 > 0:
+        assert changed > 0
+    lik = ctx.correct_likelihoods(s.total)     # the likelihood export evaluates every covered column
+    assert np.isfinite(lik).any()
