@@ -77,7 +77,10 @@ struct cdg_ctx {
     u64 nHits = 0, nRecords = 0, nGrouped = 0; bool hitsValid = false;
     u32 sort1Passes = 0, sort2Passes = 0; u64 sort1Records = 0;
     u64 *sortedMainK = nullptr, *sortedMainV = nullptr, *sortedIdK = nullptr, *sortedIdV = nullptr, *sortedKey2 = nullptr;
-    KmPlanFwd plan; u64 qLo = 0, nQ = 0; u64 mgRecv = 0, mgR2 = 0; u64 nIdent = 0; bool identCompacted = false;
+    KmPlanFwd plan; u64 qLo = 0, nQ = 0; u64 mgRecv = 0, mgR2 = 0; u64 nIdent = 0;
+    const u64 *ordV = nullptr;   // sequence index by (length desc, id asc) rank (km_prepare)
+    u64 *idSrcK = nullptr, *idSrcV = nullptr, *idAltK = nullptr, *idAltV = nullptr;   // identity records to sort (nIdent) and their ping-pong partner
+    DevBuf dRecvIdK, dRecvIdV;
     // lines / alignments
     DevBuf dLineOff, dLineQ, dLineT, dLinePref, dLineDiag, dKeep, dScore, dBits, dEvalue, dSeqId, dQS, dQE, dDS, dDE, dLineSel;
     HostBuf hLineOff, hLineT, hKeep, hScore, hBits, hEvalue, hSeqId, hQS, hQE, hDS, hDE;
@@ -238,7 +241,7 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
                    &ctx->dHitScore, &ctx->dHitDiag, &ctx->dLineOff, &ctx->dLineQ, &ctx->dLineT, &ctx->dLinePref, &ctx->dLineDiag, &ctx->dKeep,
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
                    &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2, &ctx->dQList, &ctx->dPow31,
-                   &ctx->dPairModel, &ctx->dPairIn, &ctx->dPairCons, &ctx->dPairOut};
+                   &ctx->dPairModel, &ctx->dPairIn, &ctx->dPairCons, &ctx->dPairOut, &ctx->dRecvIdK, &ctx->dRecvIdV};
     for (DevBuf *b : d) b->release();
     HostBuf *h[] = {&ctx->hHitRep, &ctx->hHitTgt, &ctx->hHitScore, &ctx->hHitDiag, &ctx->hHitDiag16, &ctx->hLineOff, &ctx->hLineT, &ctx->hKeep,
                     &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE};
@@ -341,6 +344,7 @@ static int km_prepare(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlan &K) {
                                  cdgsort::make_plan(0, 0, 0, std::max(1, ceil_log2((u64) ctx->maxLen + 1))), &ordK, &ordV, ctx->smCount);
     if (lo < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "length-order sort failed");
     ctx->launches += lo + 1;
+    ctx->ordV = ordV;
     if ((rc = scan_to(ctx, OrderedCapacityF{ordV, ctx->dLen.as<u32>(), p->k, p->kmers_per_seq, p->kmers_per_seq_scale}, n, ctx->dSlotRank.as<u64>(), true))) return rc;
     order_scatter_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ordV, ctx->dSlotRank.as<u64>(), n, ctx->dSlotOff.as<u64>(), ctx->dRankOf.as<u32>());
     ctx->launches++;
@@ -373,12 +377,12 @@ static int km_prepare(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlan &K) {
 
 // extraction of the slice into (keys, vals)[0, K.slots); extras (identity hashes inside the k-mer key range) at extraBase
 static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64 *keys, u64 *vals, u64 *idKeys, u64 *idVals, u64 extraBase,
-                      bool identityInline, u32 hashLo, u32 hashHi) {
+                      int identityMode /*ExtractParams::identity*/, u32 hashLo, u32 hashHi) {
     using namespace cdgkmer;
     const u64 n = ctx->n;
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
     ExtractParams E; E.k = p->k; E.kmersPerSeq = p->kmers_per_seq; E.scale = p->kmers_per_seq_scale; E.seed = p->hash_shift;
-    E.hashLo = hashLo; E.hashHi = hashHi; E.world = K.world; E.posLo = K.posLo; E.posHi = K.posHi; E.slotBase = K.slotBase; E.identity = identityInline ? 1 : 0;
+    E.hashLo = hashLo; E.hashHi = hashHi; E.world = K.world; E.posLo = K.posLo; E.posHi = K.posHi; E.slotBase = K.slotBase; E.identity = identityMode;
     int rc;
     CK(ctx->dLongList.reserve(n * 4)); CK(ctx->dScratchOff.reserve(n * 8));
     long_list_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dLen.as<u32>(), n, p->k, p->kmers_per_seq, p->kmers_per_seq_scale,
@@ -403,7 +407,7 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
     CK(ctx->dShortKeep.reserve(gridWarps * EX_MAXW));
     {
         const u32 maxW = ctx->maxLen >= (u32) p->k ? ctx->maxLen - p->k + 1 : 0;   // short sequences have <= 256 windows
-#define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dPow31.as<u64>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT)
+#define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dPow31.as<u64>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT, identityMode == 2 ? ctx->ordV : (const u64 *) nullptr, ctx->dSlotRank.as<u64>())
         if (maxW <= 64) extract_short_kernel<2><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
         else if (maxW <= 128) extract_short_kernel<4><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
         else extract_short_kernel<8><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
@@ -437,12 +441,7 @@ static int km_sort_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K
     int l1 = cdgsort::radix_sort(ctx->st, ws, ka, kb, va, vb, Rtot, plan1, &ctx->sortedMainK, &ctx->sortedMainV, ctx->smCount, -1, ctx->passEv);
     ctx->passEvN = plan1.n; ctx->sort1Records = Rtot;
     cdgsort::Plan planI = cdgsort::make_plan(0, 0, 0, 63);
-    const u64 nId = ctx->identCompacted ? ctx->nIdent : n;
-    int l2 = ctx->identCompacted
-                 ? cdgsort::radix_sort(ctx->st, ws, ctx->dIdKeysB.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsB.as<u64>(), ctx->dIdValsA.as<u64>(), nId, planI,
-                                       &ctx->sortedIdK, &ctx->sortedIdV, ctx->smCount)
-                 : cdgsort::radix_sort(ctx->st, ws, ctx->dIdKeysA.as<u64>(), ctx->dIdKeysB.as<u64>(), ctx->dIdValsA.as<u64>(), ctx->dIdValsB.as<u64>(), nId, planI,
-                                       &ctx->sortedIdK, &ctx->sortedIdV, ctx->smCount);
+    int l2 = cdgsort::radix_sort(ctx->st, ws, ctx->idSrcK, ctx->idAltK, ctx->idSrcV, ctx->idAltV, ctx->nIdent, planI, &ctx->sortedIdK, &ctx->sortedIdV, ctx->smCount);
     if (l1 < 0 || l2 < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "radix sort: input too large for one pass set");
     ctx->launches += l1 + l2; ctx->sort1Passes = plan1.n;
     CKL();
@@ -471,7 +470,7 @@ static int km_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64
     if (Rtot) group_kernel<<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedMainK, ctx->sortedMainV, Rtot, ctx->dLen.as<u32>(), G,
                                                                                                       ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
     GroupParams GI = G; GI.firstRunQuirk = idHasGlobalFirstRun ? 1 : 0;
-    const u64 nId = ctx->identCompacted ? ctx->nIdent : n;
+    const u64 nId = ctx->nIdent;
     if (nId) group_kernel<<<(unsigned) ((nId + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedIdK, ctx->sortedIdV, nId, ctx->dLen.as<u32>(), GI,
                                                                                                     ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
     ctx->launches += 2;
@@ -535,16 +534,17 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     CK(cudaMemsetAsync(sc, 0, SC_N * 8, ctx->st));
     rec(ctx, EV_START);
     if ((rc = km_prepare(ctx, p, K))) return rc;
-    ctx->plan = K; ctx->qLo = 0; ctx->nQ = n; ctx->identCompacted = false; ctx->nIdent = n;
+    ctx->plan = K; ctx->qLo = 0; ctx->nQ = n; ctx->nIdent = n;
     const u64 Rtot = K.slots + K.extraCap;
     if (Rtot > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "%llu k-mer records exceed one sort (2^30): use hash ranges", (unsigned long long) Rtot);
     CK(ctx->dKeysA.reserve(Rtot * 8)); CK(ctx->dKeysB.reserve(Rtot * 8)); CK(ctx->dValsA.reserve(Rtot * 8)); CK(ctx->dValsB.reserve(Rtot * 8));
     CK(ctx->dIdKeysA.reserve(n * 8)); CK(ctx->dIdKeysB.reserve(n * 8)); CK(ctx->dIdValsA.reserve(n * 8)); CK(ctx->dIdValsB.reserve(n * 8));
     CK(cudaMemsetAsync(ctx->dKeysA.as<u64>() + K.slots, 0xFF, (size_t) K.extraCap * 8, ctx->st));
     CK(cudaMemsetAsync(ctx->dValsA.as<u64>() + K.slots, 0, (size_t) K.extraCap * 8, ctx->st));
-    if ((rc = km_extract(ctx, p, K, ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), K.slots, true, p->hash_lo,
+    if ((rc = km_extract(ctx, p, K, ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), K.slots, 1, p->hash_lo,
                          p->hash_hi))) return rc;
     rec(ctx, EV_EXTRACT);
+    ctx->idSrcK = ctx->dIdKeysA.as<u64>(); ctx->idSrcV = ctx->dIdValsA.as<u64>(); ctx->idAltK = ctx->dIdKeysB.as<u64>(); ctx->idAltV = ctx->dIdValsB.as<u64>();
     u64 minKey = 0;
     if ((rc = km_sort_group(ctx, p, K, ctx->dKeysA.as<u64>(), ctx->dKeysB.as<u64>(), ctx->dValsA.as<u64>(), ctx->dValsB.as<u64>(), Rtot, 0, &minKey, nullptr))) return rc;
     u64 emitted = 0, extra = 0, R2 = 0;
@@ -927,8 +927,9 @@ extern "C" int cdg_get_stats(cdg_ctx *ctx, cdg_stats *out) {
 //            -> all-to-all of 8-byte grouped records (replaces the reference's host k-way merge of split files)
 //   phase 4  cdg_mg_sort2      sort 2; the first records (same target id) go to the previous rank for the rep-boundary bleed
 //   phase 5  cdg_mg_finish     reduce, rescore, correct for the rank's query range
-extern "C" int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world, int rank, uint64_t *send_counts, void **send_keys, void **send_vals) {
-    if (!ctx || !p || !send_counts || world < 1 || world > CDG_MAX_WORLD || rank < 0 || rank >= world) return CDG_ERR_ARG;
+extern "C" int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world, int rank, uint64_t *send_counts, void **send_keys, void **send_vals,
+                              uint64_t *id_send_counts, void **id_send_keys, void **id_send_vals) {
+    if (!ctx || !p || !send_counts || !id_send_counts || world < 1 || world > CDG_MAX_WORLD || rank < 0 || rank >= world) return CDG_ERR_ARG;
     if (ctx->n == 0) return fail(ctx, CDG_ERR_ARG, "cdg_mg_extract: no sequence set uploaded");
     CK(cudaSetDevice(ctx->device));
     KmPlan K; K.world = (u32) world; K.rank = (u32) rank;
@@ -938,43 +939,53 @@ extern "C" int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world,
     CK(cudaMemsetAsync(sc, 0, SC_N * 8, ctx->st));
     if ((rc = km_prepare(ctx, p, K))) return rc;
     ctx->plan = K; ctx->qLo = K.qLo; ctx->nQ = K.nQ;
-    const u64 R = K.slots;
+    const u64 R = K.slots + K.extraCap;          // slice slots + spare slots for identity hashes inside the k-mer key range
+    const u64 nSlice = (u64) K.posHi - K.posLo;  // sequences of the slice = identity records produced here
     if (R > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "slice has too many k-mer records for one sort");
     CK(ctx->dKeysA.reserve((R + 1) * 8)); CK(ctx->dKeysB.reserve((R + 1) * 8)); CK(ctx->dValsA.reserve((R + 1) * 8)); CK(ctx->dValsB.reserve((R + 1) * 8));
-    CK(ctx->dIdKeysA.reserve(ctx->n * 8)); CK(ctx->dIdKeysB.reserve(ctx->n * 8)); CK(ctx->dIdValsA.reserve(ctx->n * 8)); CK(ctx->dIdValsB.reserve(ctx->n * 8));
-    // all hash values of the slice's sequences; identity records are produced locally in phase 2
-    if ((rc = km_extract(ctx, p, K, ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), 0, false, 0, 65535))) return rc;
+    CK(ctx->dIdKeysA.reserve((nSlice + 1) * 8)); CK(ctx->dIdKeysB.reserve((nSlice + 1) * 8)); CK(ctx->dIdValsA.reserve((nSlice + 1) * 8)); CK(ctx->dIdValsB.reserve((nSlice + 1) * 8));
+    CK(cudaMemsetAsync(ctx->dKeysA.as<u64>() + K.slots, 0xFF, (size_t) K.extraCap * 8, ctx->st));
+    CK(cudaMemsetAsync(ctx->dValsA.as<u64>() + K.slots, 0, (size_t) K.extraCap * 8, ctx->st));
+    // all hash values of the slice's sequences and one identity record per sequence of the slice, each tagged with its owner
+    if ((rc = km_extract(ctx, p, K, ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), K.slots, 2, 0, 65535))) return rc;
     // partition by owner: one stable radix pass over the owner bits of the VALUE word (roles of the arrays swapped)
-    u64 *pv = ctx->dValsA.as<u64>(), *pk = ctx->dKeysA.as<u64>();
-    for (int o = 0; o < world; o++) send_counts[o] = 0;
-    if (R) {
-        cdgsort::Workspace ws;
-        if ((rc = sort_ws(ctx, std::max<u64>(R, ctx->n), ws))) return rc;
-        const int ownerBits = std::max(1, ceil_log2((u64) world));
-        cdgsort::Plan plan = cdgsort::make_plan(0, 0, CDG_OWNER_SHIFT, CDG_OWNER_SHIFT + ownerBits);
-        int l = cdgsort::radix_sort(ctx->st, ws, ctx->dValsA.as<u64>(), ctx->dValsB.as<u64>(), ctx->dKeysA.as<u64>(), ctx->dKeysB.as<u64>(), R, plan, &pv, &pk, ctx->smCount);
+    u64 *pv = ctx->dValsA.as<u64>(), *pk = ctx->dKeysA.as<u64>(), *iv = ctx->dIdValsA.as<u64>(), *ik = ctx->dIdKeysA.as<u64>();
+    for (int o = 0; o < world; o++) { send_counts[o] = 0; id_send_counts[o] = 0; }
+    cdgsort::Workspace ws;
+    if ((rc = sort_ws(ctx, std::max<u64>(R, ctx->n), ws))) return rc;
+    const int ownerBits = std::max(1, ceil_log2((u64) world));
+    cdgsort::Plan plan = cdgsort::make_plan(0, 0, CDG_OWNER_SHIFT, CDG_OWNER_SHIFT + ownerBits);
+    auto partition = [&](u64 *va, u64 *vb, u64 *ka, u64 *kb, u64 cnt, u64 **outV, u64 **outK, uint64_t *counts) -> int {
+        if (!cnt) return 0;
+        int l = cdgsort::radix_sort(ctx->st, ws, va, vb, ka, kb, cnt, plan, outV, outK, ctx->smCount);
         if (l < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "owner partition failed");
         ctx->launches += l;
         unsigned long long hoff[cdgsort::RADIX];
         CK(cudaMemcpyAsync(hoff, ws.hist, sizeof hoff, cudaMemcpyDeviceToHost, ctx->st));   // exclusive bin offsets of the single pass
         CK(cudaStreamSynchronize(ctx->st));
-        for (int o = 0; o < world; o++) send_counts[o] = (o + 1 < cdgsort::RADIX ? hoff[o + 1] : R) - hoff[o];
-        u64 acc = 0; for (int o = 0; o < world - 1; o++) acc += send_counts[o];
-        send_counts[world - 1] = R - acc;
-    }
+        u64 acc = 0;
+        for (int o = 0; o < world - 1; o++) { counts[o] = hoff[o + 1] - hoff[o]; acc += counts[o]; }
+        counts[world - 1] = cnt - acc;
+        return 0;
+    };
+    if ((rc = partition(ctx->dValsA.as<u64>(), ctx->dValsB.as<u64>(), ctx->dKeysA.as<u64>(), ctx->dKeysB.as<u64>(), R, &pv, &pk, send_counts))) return rc;
+    if ((rc = partition(ctx->dIdValsA.as<u64>(), ctx->dIdValsB.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdKeysB.as<u64>(), nSlice, &iv, &ik, id_send_counts))) return rc;
     CKL();
     *send_keys = pk; *send_vals = pv;
+    if (id_send_keys) *id_send_keys = ik;
+    if (id_send_vals) *id_send_vals = iv;
     return CDG_OK;
 }
 
-// receive area for `total` routed records; returns device pointers the exchange writes into
-extern "C" int cdg_mg_recv_records(cdg_ctx *ctx, uint64_t total, void **recv_keys, void **recv_vals) {
-    if (!ctx || !recv_keys || !recv_vals) return CDG_ERR_ARG;
+// receive areas for `total` routed k-mer records and `id_total` identity records; returns device pointers the exchange writes into
+extern "C" int cdg_mg_recv_records(cdg_ctx *ctx, uint64_t total, uint64_t id_total, void **recv_keys, void **recv_vals, void **id_recv_keys,
+                                   void **id_recv_vals) {
+    if (!ctx || !recv_keys || !recv_vals || !id_recv_keys || !id_recv_vals) return CDG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    const u64 cap = total + ctx->plan.extraCap + 1;
-    CK(ctx->dRecvK.reserve(cap * 8)); CK(ctx->dRecvV.reserve(cap * 8));
-    ctx->mgRecv = total;
-    *recv_keys = ctx->dRecvK.p; *recv_vals = ctx->dRecvV.p;
+    CK(ctx->dRecvK.reserve((total + 1) * 8)); CK(ctx->dRecvV.reserve((total + 1) * 8));
+    CK(ctx->dRecvIdK.reserve((id_total + 1) * 8)); CK(ctx->dRecvIdV.reserve((id_total + 1) * 8));
+    ctx->mgRecv = total; ctx->nIdent = id_total;
+    *recv_keys = ctx->dRecvK.p; *recv_vals = ctx->dRecvV.p; *id_recv_keys = ctx->dRecvIdK.p; *id_recv_vals = ctx->dRecvIdV.p;
     return CDG_OK;
 }
 
@@ -983,29 +994,14 @@ extern "C" int cdg_mg_sort(cdg_ctx *ctx, const cdg_kmer_params *p, uint64_t *min
     CK(cudaSetDevice(ctx->device));
     using namespace cdgkmer;
     const KmPlan &K = ctx->plan;
-    const u64 total = ctx->mgRecv, Rtot = total + K.extraCap, n = ctx->n;
+    const u64 Rtot = ctx->mgRecv;
     if (Rtot > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "too many routed records for one sort");
-    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
     int rc;
-    // the send buffers of phase 1 are free now: they become the ping-pong partners of the receive area
-    CK(ctx->dKeysB.reserve(Rtot * 8)); CK(ctx->dValsB.reserve(Rtot * 8));
-    CK(cudaMemsetAsync(ctx->dRecvK.as<u64>() + total, 0xFF, (size_t) K.extraCap * 8, ctx->st));
-    CK(cudaMemsetAsync(ctx->dRecvV.as<u64>() + total, 0, (size_t) K.extraCap * 8, ctx->st));
-    ExtractParams E; E.k = p->k; E.kmersPerSeq = p->kmers_per_seq; E.scale = p->kmers_per_seq_scale; E.seed = p->hash_shift;
-    E.hashLo = K.hashLo; E.hashHi = K.hashHi; E.world = K.world; E.posLo = 0; E.posHi = (u32) n; E.slotBase = 0; E.identity = 1;
-    identity_kernel<<<ctx->smCount * 16, 256, 0, ctx->st>>>(ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), n, E,
-                                                         ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), ctx->dRecvK.as<u64>(), ctx->dRecvV.as<u64>(), total,
-                                                         K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>());
-    ctx->launches++;
-    CKL();
-    // keep only the owned identity records (1/world of the slots), in slot order
-    if ((rc = scan_to(ctx, NonSentinelF{ctx->dIdKeysA.as<u64>()}, n, ctx->dSlotRank.as<u64>(), false))) return rc;
-    compact_pairs_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), ctx->dSlotRank.as<u64>(), n,
-                                                                         ctx->dIdKeysB.as<u64>(), ctx->dIdValsB.as<u64>());
-    ctx->launches++;
-    u64 nOwnedId = 0;
-    if ((rc = read_scalar(ctx, SC_SCAN, &nOwnedId))) return rc;
-    ctx->nIdent = nOwnedId; ctx->identCompacted = true;
+    // the send buffers of phase 1 are free now: they become the ping-pong partners of the receive areas
+    CK(ctx->dKeysB.reserve((Rtot + 1) * 8)); CK(ctx->dValsB.reserve((Rtot + 1) * 8));
+    CK(ctx->dIdKeysA.reserve((ctx->nIdent + 1) * 8)); CK(ctx->dIdValsA.reserve((ctx->nIdent + 1) * 8));
+    // identity records arrived ordered by source rank = (length desc, id asc) order: the stable sort keeps the representative first
+    ctx->idSrcK = ctx->dRecvIdK.as<u64>(); ctx->idSrcV = ctx->dRecvIdV.as<u64>(); ctx->idAltK = ctx->dIdKeysA.as<u64>(); ctx->idAltV = ctx->dIdValsA.as<u64>();
     u64 mk = 0;
     if ((rc = km_sort_group(ctx, p, K, ctx->dRecvK.as<u64>(), ctx->dKeysB.as<u64>(), ctx->dRecvV.as<u64>(), ctx->dValsB.as<u64>(), Rtot, -1, &mk, nullptr))) return rc;
     *min_key = mk;
@@ -1018,7 +1014,7 @@ extern "C" int cdg_mg_group(cdg_ctx *ctx, const cdg_kmer_params *p, int has_glob
     CK(cudaSetDevice(ctx->device));
     using namespace cdgkmer;
     const KmPlan &K = ctx->plan;
-    const u64 Rtot = ctx->mgRecv + K.extraCap;
+    const u64 Rtot = ctx->mgRecv;
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
     int rc;
     u64 R2 = 0;

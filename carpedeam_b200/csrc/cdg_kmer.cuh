@@ -75,8 +75,10 @@ CDG_D int base_code(const u64 *__restrict__ w, const u32 *__restrict__ xm, u32 p
 struct ExtractParams {
     int k; int kmersPerSeq; float scale; u64 seed; u32 hashLo, hashHi;
     // multi-GPU slice: this call extracts the sequences whose (length desc, id asc) rank lies in [posLo, posHi), tags
-    // every record with the owner of its hash (hash16 * world >> 16), writes slots relative to slotBase and leaves the
-    // identity records to identity_kernel.  Single GPU: world = 1, posLo = 0, posHi = n, slotBase = 0, identity = 1.
+    // every record with the owner of its hash (hash16 * world >> 16) and writes slots relative to slotBase.
+    // identity: 1 = single GPU (world = 1, posLo = 0, posHi = n, slotBase = 0): records of the owned hash range at slot
+    // rankOf[seq]; 2 = slice mode: one identity record per sequence of the slice at slot rank - posLo, tagged with its owner
+    // (routed with the k-mer records); 0 = none.
     u32 world, posLo, posHi; u64 slotBase; int identity;
 };
 CDG_D u32 owner_of(u32 score, u32 world) { return (score * world) >> 16; }
@@ -163,16 +165,17 @@ CDG_D void select_sequential(const WinRec *sorted, u32 cnt, u32 considered, u32 
 CDG_D void emit_identity(u64 seqHash, u64 seq, const ExtractParams &P, u64 *idKeys, u64 *idVals, u64 *mainKeys, u64 *mainVals,
                          u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow, const u32 *__restrict__ rankOf) {
     u32 h16 = (u32) (seqHash & 0xFFFFu);
-    bool owned = h16 >= P.hashLo && h16 <= P.hashHi;
+    const bool slice = P.identity == 2;
+    bool owned = slice || (h16 >= P.hashLo && h16 <= P.hashHi);
     u64 key = CDG_SENTINEL, val = 0;
-    if (owned) { key = seqHash; val = cdg_pack_val((u32) seq, 0); }
+    if (owned) { key = seqHash; val = cdg_pack_val((u32) seq, 0, slice ? owner_of(h16, P.world) : 0u); }
     if (owned && (seqHash & ~CDG_B63) < (1ull << (2 * P.k))) {
         u32 slot = atomicAdd(extraCount, 1u);
         if (slot < extraCap) { mainKeys[extraBase + slot] = key; mainVals[extraBase + slot] = val; }
         else atomicExch(overflow, 1u);
         key = CDG_SENTINEL; val = 0;
     }
-    const u32 slot = rankOf[seq];   // (length desc, id asc) order: after the stable sort the representative comes first
+    const u32 slot = rankOf[seq] - (slice ? P.posLo : 0u);   // (length desc, id asc) order: after the stable sort the representative comes first
     idKeys[slot] = key; idVals[slot] = val;
 }
 
@@ -191,7 +194,9 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
     u64 *__restrict__ mainKeys, u64 *__restrict__ mainVals, u64 *__restrict__ idKeys, u64 *__restrict__ idVals,
     u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow, const u32 *__restrict__ rankOf, const u64 *__restrict__ pow31tab,
     WinRec *__restrict__ scratch /*[gridWarps][2*EX_MAXW]*/,
-    u8 *__restrict__ scratchKeep /*[gridWarps][EX_MAXW]*/, unsigned long long *__restrict__ emitted) {
+    u8 *__restrict__ scratchKeep /*[gridWarps][EX_MAXW]*/, unsigned long long *__restrict__ emitted,
+    const u64 *__restrict__ order /*slice mode: sequence index by (length desc, id asc) rank, else null*/,
+    const u64 *__restrict__ prefix /*slice mode: first slot by rank*/) {
     __shared__ u32 bitmapAll[EX_WARPS * EX_BM_WORDS];   // 8192 bits per warp: small, so that registers bound the occupancy
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u32 *bitmap = bitmapAll + warp * EX_BM_WORDS;
@@ -202,14 +207,24 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
     u8 *myKeep = scratchKeep + gwarp * EX_MAXW;
     unsigned long long localEmitted = 0;
 
-    // the loads that start a sequence (meta, rank, slot) are issued one sequence ahead
-    SeqMeta smN; smN.off = 0; smN.wordOff = 0; smN.lenFlags = 0; u32 rankN = 0; u64 slotN = 0;
-    if (gwarp < n) { smN = meta[gwarp]; rankN = rankOf[gwarp]; slotN = slotOff[gwarp]; }
-    for (u64 seq = gwarp; seq < n; seq += nwarps) {
+    // Iteration space: all sequences in index order (single GPU), or the ranks [posLo, posHi) of this GPU's slice through
+    // `order` (multi-GPU: the per-rank work does not grow with the number of ranks).  The loads that start a sequence
+    // (index, meta, rank, slot) are issued one sequence ahead.
+    const bool byRank = order != nullptr;
+    const u64 itLo = byRank ? (u64) P.posLo : 0ull, itHi = byRank ? (u64) P.posHi : n;
+    SeqMeta smN; smN.off = 0; smN.wordOff = 0; smN.lenFlags = 0; u32 rankN = 0; u64 slotN = 0, seqN = 0;
+    auto fetch = [&](u64 it) {
+        if (byRank) { seqN = (u32) order[it]; rankN = (u32) it; slotN = prefix[it]; }
+        else { seqN = it; rankN = rankOf[it]; slotN = slotOff[it]; }
+        smN = meta[seqN];
+    };
+    if (itLo + gwarp < itHi) fetch(itLo + gwarp);
+    for (u64 it = itLo + gwarp; it < itHi; it += nwarps) {
         const SeqMeta sm = smN;   // one 16-byte load: length and first word
         const u32 myRank = rankN;
         const u64 slotAbs = slotN;
-        if (seq + nwarps < n) { smN = meta[seq + nwarps]; rankN = rankOf[seq + nwarps]; slotN = slotOff[seq + nwarps]; }
+        const u64 seq = seqN;
+        if (it + nwarps < itHi) fetch(it + nwarps);
         const u32 L = sm.lenFlags & META_LEN;
         if (!is_short_seq(L, P.k, P.kmersPerSeq, P.scale)) continue;   // handled by extract_long_kernel
         if (myRank < P.posLo || myRank >= P.posHi) continue;            // not in this rank's slice
@@ -336,7 +351,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
         for (u32 s = written + lane; s < cap; s += 32) { mainKeys[slot0 + s] = CDG_SENTINEL; mainVals[slot0 + s] = 0; }
         localEmitted += written;
         // next sequence's packed words towards L1 while this one's records drain
-        if (lane < 2 && seq + nwarps < n) {
+        if (lane < 2 && it + nwarps < itHi) {
             const void *pw = lane == 0 ? (const void *) (words + smN.wordOff) : (const void *) (xmask + smN.wordOff);
             asm volatile("prefetch.global.L1 [%0];" :: "l"(pw));
         }

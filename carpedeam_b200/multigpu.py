@@ -6,7 +6,7 @@ Plumbing only — every kernel lives in libcarpedeam_gpu.so (cdg_mg_* phases).  
 decision) is testable on CPU with gloo (tests/test_multigpu_host.py).
 
 Per iteration:
-  1. cdg_mg_extract      -> all_to_all of (key, value) records             [the data all-to-all north_star names]
+  1. cdg_mg_extract      -> all_to_all of (key, value) records + the slice's identity records  [the data all-to-all north_star names]
   2. cdg_mg_sort         -> all_gather of one u64 per rank (smallest key)  [first-run quirk, kmermatcher.cpp:466]
   3. cdg_mg_group        -> all_to_all of 8-byte grouped records to the rank owning the representative
                             (on-device replacement of the reference's host k-way merge of split files, :953-1111)
@@ -53,7 +53,11 @@ class TorchComm:
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
 
     def exchange_counts(self, send_counts):
-        t = self.torch.tensor([int(c) for c in send_counts], dtype=self.torch.int64, device=self.device)
+        """send_counts: k*world values, [a_0..a_{w-1}, b_0..b_{w-1}, ...] (k count vectors); returns what every peer sends to this
+        rank, interleaved per peer: [a from 0, b from 0, a from 1, b from 1, ...] (k = 1: the plain received counts)."""
+        k = len(send_counts) // self.world
+        t = self.torch.tensor([int(send_counts[j * self.world + o]) for o in range(self.world) for j in range(k)], dtype=self.torch.int64,
+                              device=self.device)
         r = self.torch.empty_like(t)
         self.dist.all_to_all_single(r, t)
         return [int(x) for x in r.tolist()]
@@ -101,8 +105,10 @@ class ShardedIteration:
     def __init__(self, ctx, comm):
         self.ctx, self.comm = ctx, comm
         L = lib()
-        L.cdg_mg_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
-        L.cdg_mg_recv_records.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.cdg_mg_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.cdg_mg_recv_records.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_void_p)]
         L.cdg_mg_sort.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.cdg_mg_group.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
         L.cdg_mg_recv_grouped.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
@@ -134,19 +140,24 @@ class ShardedIteration:
             tm[name] = tm.get(name, 0.0) + (now - t_last[0]) * 1e3
             t_last[0] = now
         # phase 1
-        sc = (C.c_uint64 * world)()
-        sk, sv = C.c_void_p(), C.c_void_p()
-        ctx._ck(L.cdg_mg_extract(ctx._h, C.byref(kp), world, rank, sc, C.byref(sk), C.byref(sv)), "cdg_mg_extract")
-        send_counts = list(sc)
+        sc = (C.c_uint64 * world)(); isc = (C.c_uint64 * world)()
+        sk, sv, ik, iv = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ctx._ck(L.cdg_mg_extract(ctx._h, C.byref(kp), world, rank, sc, C.byref(sk), C.byref(sv), isc, C.byref(ik), C.byref(iv)), "cdg_mg_extract")
+        send_counts = list(sc); id_send = list(isc)
         lap("extract+partition")
-        recv_counts = comm.exchange_counts(send_counts)
-        total = sum(recv_counts)
-        rk, rv = C.c_void_p(), C.c_void_p()
-        ctx._ck(L.cdg_mg_recv_records(ctx._h, total, C.byref(rk), C.byref(rv)), "cdg_mg_recv_records")
-        nsend = sum(send_counts)
-        w1 = comm.all_to_all(self._t(rk.value, total), self._t(sk.value, nsend), recv_counts, send_counts, async_op=True)
-        w2 = comm.all_to_all(self._t(rv.value, total), self._t(sv.value, nsend), recv_counts, send_counts, async_op=True)
-        w1.wait(); w2.wait()
+        both = comm.exchange_counts(send_counts + id_send)      # [counts of rank 0, ids of rank 0, counts of rank 1, ...] see exchange_counts
+        recv_counts, id_recv = both[0::2], both[1::2]
+        total, id_total = sum(recv_counts), sum(id_recv)
+        rk, rv, irk, irv = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ctx._ck(L.cdg_mg_recv_records(ctx._h, total, id_total, C.byref(rk), C.byref(rv), C.byref(irk), C.byref(irv)), "cdg_mg_recv_records")
+        nsend, id_nsend = sum(send_counts), sum(id_send)
+        # one exchange: k-mer records and the identity records of the slice (keys and values of each, issued together)
+        ws = [comm.all_to_all(self._t(rk.value, total), self._t(sk.value, nsend), recv_counts, send_counts, async_op=True),
+              comm.all_to_all(self._t(rv.value, total), self._t(sv.value, nsend), recv_counts, send_counts, async_op=True),
+              comm.all_to_all(self._t(irk.value, id_total), self._t(ik.value, id_nsend), id_recv, id_send, async_op=True),
+              comm.all_to_all(self._t(irv.value, id_total), self._t(iv.value, id_nsend), id_recv, id_send, async_op=True)]
+        for w in ws:
+            w.wait()
         lap("all_to_all records")
         # phase 2
         mk = C.c_uint64()

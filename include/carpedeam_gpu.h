@@ -191,13 +191,17 @@ int cdg_iteration(cdg_ctx *ctx, const cdg_iter_params *p, cdg_hits *hits, cdg_al
  * One context per rank, the whole sequence set uploaded on every rank.  K-mer records are owned by hash range like
  * kmermatcher's split passes (kmermatcher.cpp:742-784): rank r owns hash16 in [r*65536/world, (r+1)*65536/world).
  * The caller exchanges the device buffers between the phases (carpedeam_b200/multigpu.py, NCCL through torch.distributed):
- *   cdg_mg_extract  -> all-to-all of the 16-byte records (send_counts[o] records for rank o, contiguous, in rank order)
+ *   cdg_mg_extract  -> all-to-all of the 16-byte records (send_counts[o] records for rank o, contiguous, in rank order); the identity
+ *                      records of the rank's slice of sequences (one per sequence, kmermatcher.cpp:244-262) travel in the same exchange
+ *                      (id_send_counts / id_send_keys / id_send_vals), so no rank hashes sequences outside its slice
  *   cdg_mg_recv_records / cdg_mg_sort -> min key of the rank (the ranks compare 8 bytes each: first-run quirk, :466)
  *   cdg_mg_group    -> all-to-all of the 8-byte grouped records to the rank owning the representative's index range
  *   cdg_mg_recv_grouped / cdg_mg_sort2 -> the leading records with one target id go to rank-1 (rep-boundary bleed, :886-888)
  *   cdg_mg_finish   -> hits, alignments and corrected bytes of the rank's query range [rank*ceil(n/world), ...) */
-int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world, int rank, uint64_t *send_counts, void **send_keys, void **send_vals);
-int cdg_mg_recv_records(cdg_ctx *ctx, uint64_t total, void **recv_keys, void **recv_vals);
+int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world, int rank, uint64_t *send_counts, void **send_keys, void **send_vals,
+                   uint64_t *id_send_counts, void **id_send_keys, void **id_send_vals);
+int cdg_mg_recv_records(cdg_ctx *ctx, uint64_t total, uint64_t id_total, void **recv_keys, void **recv_vals, void **id_recv_keys,
+                        void **id_recv_vals);
 int cdg_mg_sort(cdg_ctx *ctx, const cdg_kmer_params *p, uint64_t *min_key);
 int cdg_mg_group(cdg_ctx *ctx, const cdg_kmer_params *p, int has_global_first_run, uint64_t *send_counts, void **send_key2);
 int cdg_mg_recv_grouped(cdg_ctx *ctx, uint64_t total, void **recv_key2);
