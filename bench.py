@@ -290,6 +290,8 @@ def main():
     ap.add_argument("--genome", type=int, default=50_000_000)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU record exchange: sender-side partition kernel writing into peer memory over NVLink (p2p) or NCCL all-to-all")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     workload = "synthetic %d merged reads, 35-70 bp, dhigh damage, %d bp genome (BASELINE configs[1])" % (args.reads, args.genome)
@@ -336,7 +338,7 @@ def main():
     ctx.set_damage(cd.load_damage(os.path.join(ROOT, "tests", "golden", "dhigh")))
     ip = cd.IterParams(cd.kmer_params(), cd.RescoreParams(0.9, 0.001, 0), cd.CorrParams(0.9, 0.99))
     stream = torch.cuda.ExternalStream(ctx.stream)
-    sharded = ShardedIteration(ctx, TorchComm(dev)) if world > 1 else None
+    sharded = ShardedIteration(ctx, TorchComm(dev), exchange=args.exchange) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -410,7 +412,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int64 (+f64 likelihoods)", "data": data_note,
             "config": {"workload": workload, "l2": "inputs larger than L2 (k-mer records of one pass: GBs)",
-                       "parallelism": "single GPU" if world == 1 else "k-mer records owned by hash range, %d ranks, NCCL all-to-all" % world},
+                       "parallelism": "single GPU" if world == 1 else "k-mer records owned by hash range, %d ranks, %s" % (
+                           world, "partition kernel writes into peer memory over NVLink (CUDA IPC)" if args.exchange == "p2p" else "NCCL all-to-all")},
             "e2e": {"value": e2e_val, "unit": "Mreads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_step},
             "gpu_launches": int(launches), "clocks": clocks_summary(samples)}
     if world == 1:
@@ -442,6 +445,8 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "Mreads/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % str(ex)[:200]}
     if rank == 0:
         print(json.dumps(line))
+    if sharded is not None:
+        sharded.release()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

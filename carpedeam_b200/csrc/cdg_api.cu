@@ -50,6 +50,8 @@ enum { EV_START, EV_EXTRACT, EV_SORT1, EV_GROUP, EV_SORT2, EV_REDUCE, EV_RS0, EV
 }   // namespace
 
 static constexpr int CDG_MAX_WORLD = 16;
+static constexpr int CDG_IPC_BUFFERS = 5;   // recvK, recvV, recvIdK, recvIdV, recv2
+static constexpr int CDG_IPC_HANDLE_BYTES = 64 + 8;   // cudaIpcMemHandle_t + byte offset of the buffer inside its allocation
 static constexpr u64 CDG_HEAD_RUN = 4096;   // records of the next rank's head run appended before the reduction
 struct KmPlanFwd {
     int idBits, diagBits; u32 world, rank; u32 posLo, posHi; u64 slotBase, slots; u32 extraCap; u32 hashLo, hashHi; u32 repChunk; u64 qLo, nQ;
@@ -80,7 +82,11 @@ struct cdg_ctx {
     KmPlanFwd plan; u64 qLo = 0, nQ = 0; u64 mgRecv = 0, mgR2 = 0; u64 nIdent = 0;
     const u64 *ordV = nullptr;   // sequence index by (length desc, id asc) rank (km_prepare)
     u64 *idSrcK = nullptr, *idSrcV = nullptr, *idAltK = nullptr, *idAltV = nullptr;   // identity records to sort (nIdent) and their ping-pong partner
-    DevBuf dRecvIdK, dRecvIdV;
+    DevBuf dRecvIdK, dRecvIdV, dRouteTab;
+    // peer-mapped receive buffers (CUDA IPC): [which][peer] base pointers as opened in this process, and the handle they came from
+    void *peerPtr[CDG_IPC_BUFFERS][CDG_MAX_WORLD] = {}; void *peerBase[CDG_IPC_BUFFERS][CDG_MAX_WORLD] = {};
+    unsigned char peerHandle[CDG_IPC_BUFFERS][CDG_MAX_WORLD][CDG_IPC_HANDLE_BYTES] = {};
+    u64 mgSlice = 0; u64 *mgMainK = nullptr, *mgMainV = nullptr, *mgIdK = nullptr, *mgIdV = nullptr;   // phase-1 arrays awaiting the scatter
     // lines / alignments
     DevBuf dLineOff, dLineQ, dLineT, dLinePref, dLineDiag, dKeep, dScore, dBits, dEvalue, dSeqId, dQS, dQE, dDS, dDE, dLineSel;
     HostBuf hLineOff, hLineT, hKeep, hScore, hBits, hEvalue, hSeqId, hQS, hQE, hDS, hDE;
@@ -234,6 +240,7 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
+    for (int w = 0; w < CDG_IPC_BUFFERS; w++) for (int pe = 0; pe < CDG_MAX_WORLD; pe++) if (ctx->peerBase[w][pe]) cudaIpcCloseMemHandle(ctx->peerBase[w][pe]);
     DevBuf *d[] = {&ctx->dMeta, &ctx->dData, &ctx->dOff, &ctx->dLen, &ctx->dExt, &ctx->dWordOff, &ctx->dWords, &ctx->dXmask, &ctx->dFlags, &ctx->dLikOff,
                    &ctx->dTileSums, &ctx->dScalars, &ctx->dHist, &ctx->dTileState, &ctx->dSlotOff, &ctx->dKeysA, &ctx->dKeysB, &ctx->dValsA,
                    &ctx->dValsB, &ctx->dIdKeysA, &ctx->dIdKeysB, &ctx->dIdValsA, &ctx->dIdValsB, &ctx->dKey2A, &ctx->dKey2B, &ctx->dLongList,
@@ -241,7 +248,7 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
                    &ctx->dHitScore, &ctx->dHitDiag, &ctx->dLineOff, &ctx->dLineQ, &ctx->dLineT, &ctx->dLinePref, &ctx->dLineDiag, &ctx->dKeep,
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
                    &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2, &ctx->dQList, &ctx->dPow31,
-                   &ctx->dPairModel, &ctx->dPairIn, &ctx->dPairCons, &ctx->dPairOut, &ctx->dRecvIdK, &ctx->dRecvIdV};
+                   &ctx->dPairModel, &ctx->dPairIn, &ctx->dPairCons, &ctx->dPairOut, &ctx->dRecvIdK, &ctx->dRecvIdV, &ctx->dRouteTab};
     for (DevBuf *b : d) b->release();
     HostBuf *h[] = {&ctx->hHitRep, &ctx->hHitTgt, &ctx->hHitScore, &ctx->hHitDiag, &ctx->hHitDiag16, &ctx->hLineOff, &ctx->hLineT, &ctx->hKeep,
                     &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE};
@@ -927,8 +934,8 @@ extern "C" int cdg_get_stats(cdg_ctx *ctx, cdg_stats *out) {
 //            -> all-to-all of 8-byte grouped records (replaces the reference's host k-way merge of split files)
 //   phase 4  cdg_mg_sort2      sort 2; the first records (same target id) go to the previous rank for the rep-boundary bleed
 //   phase 5  cdg_mg_finish     reduce, rescore, correct for the rank's query range
-extern "C" int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world, int rank, uint64_t *send_counts, void **send_keys, void **send_vals,
-                              uint64_t *id_send_counts, void **id_send_keys, void **id_send_vals) {
+extern "C" int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world, int rank, int partition, uint64_t *send_counts, void **send_keys,
+                              void **send_vals, uint64_t *id_send_counts, void **id_send_keys, void **id_send_vals) {
     if (!ctx || !p || !send_counts || !id_send_counts || world < 1 || world > CDG_MAX_WORLD || rank < 0 || rank >= world) return CDG_ERR_ARG;
     if (ctx->n == 0) return fail(ctx, CDG_ERR_ARG, "cdg_mg_extract: no sequence set uploaded");
     CK(cudaSetDevice(ctx->device));
@@ -955,8 +962,19 @@ extern "C" int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world,
     if ((rc = sort_ws(ctx, std::max<u64>(R, ctx->n), ws))) return rc;
     const int ownerBits = std::max(1, ceil_log2((u64) world));
     cdgsort::Plan plan = cdgsort::make_plan(0, 0, CDG_OWNER_SHIFT, CDG_OWNER_SHIFT + ownerBits);
-    auto partition = [&](u64 *va, u64 *vb, u64 *ka, u64 *kb, u64 cnt, u64 **outV, u64 **outK, uint64_t *counts) -> int {
+    auto partitionPass = [&](u64 *va, u64 *vb, u64 *ka, u64 *kb, u64 cnt, u64 **outV, u64 **outK, uint64_t *counts) -> int {
         if (!cnt) return 0;
+        if (!partition) {   // peer-memory exchange: only the per-owner counts now, cdg_mg_scatter_records writes straight into the peers
+            CK(cudaMemsetAsync(ws.hist, 0, sizeof(unsigned long long) * cdgsort::RADIX, ctx->st));
+            int hb = (int) std::min<u64>((cnt + cdgsort::BLOCK - 1) / cdgsort::BLOCK, (u64) ctx->smCount * 8);
+            cdgsort::hist_kernel<<<hb, cdgsort::BLOCK, cdgsort::RADIX * sizeof(u32), ctx->st>>>(va, nullptr, cnt, plan, ws.hist);
+            ctx->launches++;
+            unsigned long long hc[cdgsort::RADIX];
+            CK(cudaMemcpyAsync(hc, ws.hist, sizeof hc, cudaMemcpyDeviceToHost, ctx->st));
+            CK(cudaStreamSynchronize(ctx->st));
+            for (int o = 0; o < world; o++) counts[o] = hc[o];
+            return 0;
+        }
         int l = cdgsort::radix_sort(ctx->st, ws, va, vb, ka, kb, cnt, plan, outV, outK, ctx->smCount);
         if (l < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "owner partition failed");
         ctx->launches += l;
@@ -968,10 +986,12 @@ extern "C" int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world,
         counts[world - 1] = cnt - acc;
         return 0;
     };
-    if ((rc = partition(ctx->dValsA.as<u64>(), ctx->dValsB.as<u64>(), ctx->dKeysA.as<u64>(), ctx->dKeysB.as<u64>(), R, &pv, &pk, send_counts))) return rc;
-    if ((rc = partition(ctx->dIdValsA.as<u64>(), ctx->dIdValsB.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdKeysB.as<u64>(), nSlice, &iv, &ik, id_send_counts))) return rc;
+    ctx->mgSlice = nSlice; ctx->mgMainK = ctx->dKeysA.as<u64>(); ctx->mgMainV = ctx->dValsA.as<u64>(); ctx->mgIdK = ctx->dIdKeysA.as<u64>(); ctx->mgIdV = ctx->dIdValsA.as<u64>();
+    if ((rc = partitionPass(ctx->dValsA.as<u64>(), ctx->dValsB.as<u64>(), ctx->dKeysA.as<u64>(), ctx->dKeysB.as<u64>(), R, &pv, &pk, send_counts))) return rc;
+    if ((rc = partitionPass(ctx->dIdValsA.as<u64>(), ctx->dIdValsB.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdKeysB.as<u64>(), nSlice, &iv, &ik, id_send_counts))) return rc;
     CKL();
-    *send_keys = pk; *send_vals = pv;
+    if (send_keys) *send_keys = pk;
+    if (send_vals) *send_vals = pv;
     if (id_send_keys) *id_send_keys = ik;
     if (id_send_vals) *id_send_vals = iv;
     return CDG_OK;
@@ -982,8 +1002,9 @@ extern "C" int cdg_mg_recv_records(cdg_ctx *ctx, uint64_t total, uint64_t id_tot
                                    void **id_recv_vals) {
     if (!ctx || !recv_keys || !recv_vals || !id_recv_keys || !id_recv_vals) return CDG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    CK(ctx->dRecvK.reserve((total + 1) * 8)); CK(ctx->dRecvV.reserve((total + 1) * 8));
-    CK(ctx->dRecvIdK.reserve((id_total + 1) * 8)); CK(ctx->dRecvIdV.reserve((id_total + 1) * 8));
+    const u64 minBytes = 8ull << 20;   // own allocation block each (IPC maps whole blocks)
+    CK(ctx->dRecvK.reserve(std::max<u64>((total + 1) * 8, minBytes))); CK(ctx->dRecvV.reserve(std::max<u64>((total + 1) * 8, minBytes)));
+    CK(ctx->dRecvIdK.reserve(std::max<u64>((id_total + 1) * 8, minBytes))); CK(ctx->dRecvIdV.reserve(std::max<u64>((id_total + 1) * 8, minBytes)));
     ctx->mgRecv = total; ctx->nIdent = id_total;
     *recv_keys = ctx->dRecvK.p; *recv_vals = ctx->dRecvV.p; *id_recv_keys = ctx->dRecvIdK.p; *id_recv_vals = ctx->dRecvIdV.p;
     return CDG_OK;
@@ -1009,8 +1030,8 @@ extern "C" int cdg_mg_sort(cdg_ctx *ctx, const cdg_kmer_params *p, uint64_t *min
 }
 
 // has_global_first_run: this rank's smallest key is the smallest of all ranks (ties: lowest rank)
-extern "C" int cdg_mg_group(cdg_ctx *ctx, const cdg_kmer_params *p, int has_global_first_run, uint64_t *send_counts, void **send_key2) {
-    if (!ctx || !p || !send_counts || !send_key2) return CDG_ERR_ARG;
+extern "C" int cdg_mg_group(cdg_ctx *ctx, const cdg_kmer_params *p, int has_global_first_run, int partition, uint64_t *send_counts, void **send_key2) {
+    if (!ctx || !p || !send_counts) return CDG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     using namespace cdgkmer;
     const KmPlan &K = ctx->plan;
@@ -1031,16 +1052,19 @@ extern "C" int cdg_mg_group(cdg_ctx *ctx, const cdg_kmer_params *p, int has_glob
         route_count_kernel<<<blocks, 256, 0, ctx->st>>>(ctx->dKey2A.as<u64>(), R2, repShift, K.repChunk, K.world, counts);
         CK(cudaMemcpyAsync(hc, counts, 16 * 8, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
-        unsigned long long cur[16], acc = 0;
-        for (u32 o = 0; o < 16; o++) { cur[o] = acc; acc += o < K.world ? hc[o] : 0; }
-        CK(cudaMemcpyAsync(counts, cur, 16 * 8, cudaMemcpyHostToDevice, ctx->st));
-        route_scatter_kernel<<<blocks, 256, 0, ctx->st>>>(ctx->dKey2A.as<u64>(), R2, repShift, K.repChunk, K.world, counts, ctx->dKey2B.as<u64>());
-        ctx->launches += 2;
+        ctx->launches++;
+        if (partition) {
+            unsigned long long cur[16], acc = 0;
+            for (u32 o = 0; o < 16; o++) { cur[o] = acc; acc += o < K.world ? hc[o] : 0; }
+            CK(cudaMemcpyAsync(counts, cur, 16 * 8, cudaMemcpyHostToDevice, ctx->st));
+            route_scatter_kernel<<<blocks, 256, 0, ctx->st>>>(ctx->dKey2A.as<u64>(), R2, repShift, K.repChunk, K.world, counts, ctx->dKey2B.as<u64>());
+            ctx->launches++;
+        }
         CKL();
     }
     for (u32 o = 0; o < K.world; o++) send_counts[o] = hc[o];
     CK(cudaStreamSynchronize(ctx->st));
-    *send_key2 = ctx->dKey2B.p;
+    if (send_key2) *send_key2 = ctx->dKey2B.p;
     return CDG_OK;
 }
 
@@ -1048,9 +1072,144 @@ extern "C" int cdg_mg_recv_grouped(cdg_ctx *ctx, uint64_t total, void **recv_key
     if (!ctx || !recv_key2) return CDG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     // dKey2A (group output, already scattered to dKey2B) is reused as the receive area; the exchange reads dKey2B
-    CK(ctx->dRecv2.reserve((total + CDG_HEAD_RUN + 1) * 8));
+    CK(ctx->dRecv2.reserve(std::max<u64>((total + CDG_HEAD_RUN + 1) * 8, 8ull << 20)));
     ctx->mgR2 = total;
     *recv_key2 = ctx->dRecv2.p;
+    return CDG_OK;
+}
+
+// ---- peer-memory exchange (NVLink, CUDA IPC): the partition pass of the sender writes straight into the receivers ----------
+static DevBuf *ipc_buffer(cdg_ctx *ctx, int which) {
+    switch (which) {
+        case 0: return &ctx->dRecvK; case 1: return &ctx->dRecvV; case 2: return &ctx->dRecvIdK; case 3: return &ctx->dRecvIdV; case 4: return &ctx->dRecv2;
+        default: return nullptr;
+    }
+}
+// handle of receive buffer `which` (after cdg_mg_recv_records / cdg_mg_recv_grouped reserved it): 64-byte cudaIpcMemHandle_t
+// followed by the buffer's byte offset inside its allocation
+extern "C" int cdg_mg_ipc_export(cdg_ctx *ctx, int which, void *handle_out) {
+    DevBuf *b = ctx ? ipc_buffer(ctx, which) : nullptr;
+    if (!b || !handle_out || !b->p) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, b->p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    u64 offset = 0;
+    {   // allocation base through the driver entry point (no link-time dependency on libcuda)
+        typedef int (*GetRange)(unsigned long long *, size_t *, unsigned long long);
+        void *fn = nullptr; cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn) {
+            unsigned long long base = 0; size_t sz = 0;
+            if (((GetRange) fn)(&base, &sz, (unsigned long long) (uintptr_t) b->p) == 0 && base) offset = (u64) (uintptr_t) b->p - base;
+        }
+    }
+    memcpy(handle_out, &h, 64); memcpy((unsigned char *) handle_out + 64, &offset, 8);
+    return CDG_OK;
+}
+// bytes receive buffer `which` can hold without being reallocated (0 = not allocated yet).  A buffer must not be freed while a
+// peer still maps it: before a rank grows a buffer every peer drops its mapping (cdg_mg_ipc_close) — see multigpu.py.
+extern "C" int cdg_mg_ipc_capacity(cdg_ctx *ctx, int which, uint64_t *bytes) {
+    DevBuf *b = ctx ? ipc_buffer(ctx, which) : nullptr;
+    if (!b || !bytes) return CDG_ERR_ARG;
+    *bytes = b->cap;
+    return CDG_OK;
+}
+extern "C" int cdg_mg_ipc_close(cdg_ctx *ctx, int which, int peer) {
+    if (!ctx || which < 0 || which >= CDG_IPC_BUFFERS || peer < 0 || peer >= CDG_MAX_WORLD) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->peerBase[which][peer]) {
+        CK(cudaStreamSynchronize(ctx->st));
+        CK(cudaIpcCloseMemHandle(ctx->peerBase[which][peer]));
+        ctx->peerBase[which][peer] = nullptr; ctx->peerPtr[which][peer] = nullptr;
+        memset(ctx->peerHandle[which][peer], 0, CDG_IPC_HANDLE_BYTES);
+    }
+    return CDG_OK;
+}
+// maps peer `peer`'s receive buffer `which` into this process (cached while the peer's handle stays the same)
+extern "C" int cdg_mg_ipc_open(cdg_ctx *ctx, int which, int peer, const void *handle) {
+    if (!ctx || !handle || which < 0 || which >= CDG_IPC_BUFFERS || peer < 0 || peer >= CDG_MAX_WORLD) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->peerBase[which][peer] && memcmp(ctx->peerHandle[which][peer], handle, CDG_IPC_HANDLE_BYTES) == 0) return CDG_OK;
+    if (ctx->peerBase[which][peer]) { CK(cudaIpcCloseMemHandle(ctx->peerBase[which][peer])); ctx->peerBase[which][peer] = nullptr; ctx->peerPtr[which][peer] = nullptr; }
+    cudaIpcMemHandle_t h; u64 offset = 0;
+    memcpy(&h, handle, 64); memcpy(&offset, (const unsigned char *) handle + 64, 8);
+    void *base = nullptr;
+    CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peerBase[which][peer] = base; ctx->peerPtr[which][peer] = (unsigned char *) base + offset;
+    memcpy(ctx->peerHandle[which][peer], handle, CDG_IPC_HANDLE_BYTES);
+    return CDG_OK;
+}
+
+// Send side of the record all-to-all: ONE stable partition pass per array pair whose per-owner outputs are the peers' receive
+// buffers.  dst_off[o] / id_dst_off[o] = first record index of this rank's segment in rank o's k-mer / identity receive area
+// (= records the lower ranks send to o).  Own segment: the local buffer.  The caller synchronises the ranks afterwards.
+extern "C" int cdg_mg_scatter_records(cdg_ctx *ctx, const uint64_t *dst_off, const uint64_t *id_dst_off) {
+    if (!ctx || !dst_off || !id_dst_off) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const KmPlan &K = ctx->plan;
+    const u32 world = K.world, rank = K.rank;
+    const u64 R = K.slots + K.extraCap, nSlice = ctx->mgSlice;
+    int rc;
+    cdgsort::Workspace ws;
+    if ((rc = sort_ws(ctx, std::max<u64>(R, ctx->n), ws))) return rc;
+    CK(ctx->dRouteTab.reserve(4 * cdgsort::ROUTE_MAX * sizeof(void *)));
+    u64 *tab[4][cdgsort::ROUTE_MAX] = {};
+    for (u32 o = 0; o < world; o++) {
+        DevBuf *own[4] = {&ctx->dRecvV, &ctx->dRecvK, &ctx->dRecvIdV, &ctx->dRecvIdK};   // digit word = value (owner bits), payload = key
+        const int which[4] = {1, 0, 3, 2};
+        for (int a = 0; a < 4; a++) {
+            u64 *base = o == rank ? own[a]->as<u64>() : (u64 *) ctx->peerPtr[which[a]][o];
+            if (!base) return fail(ctx, CDG_ERR_ARG, "cdg_mg_scatter_records: receive buffer %d of rank %u is not mapped (cdg_mg_ipc_open)", which[a], o);
+            tab[a][o] = base + (a < 2 ? dst_off[o] : id_dst_off[o]);
+        }
+    }
+    CK(cudaMemcpyAsync(ctx->dRouteTab.p, tab, sizeof tab, cudaMemcpyHostToDevice, ctx->st));
+    u64 *const *dtab = ctx->dRouteTab.as<u64 *>();
+    const int ownerBits = std::max(1, ceil_log2((u64) world));
+    const cdgsort::Pass pass{0, CDG_OWNER_SHIFT, (1u << ownerBits) - 1};
+    auto route = [&](const u64 *digitWords, const u64 *payload, u64 cnt, u64 *const *tV, u64 *const *tK) -> int {
+        if (!cnt) return 0;
+        CK(cudaMemsetAsync(ws.hist, 0, sizeof(unsigned long long) * cdgsort::RADIX, ctx->st));
+        CK(cudaMemsetAsync(ws.tileState, 0, cdgsort::tiles_for(cnt) * cdgsort::RADIX * sizeof(u32), ctx->st));
+        CK(cudaMemsetAsync(ws.ticket, 0, sizeof(u32), ctx->st));
+        cdgsort::launch_route_pass(ctx->st, digitWords, payload, cnt, pass, ws.hist, ws.tileState, ws.ticket, tV, tK);
+        ctx->launches++;
+        return 0;
+    };
+    if ((rc = route(ctx->mgMainV, ctx->mgMainK, R, dtab, dtab + cdgsort::ROUTE_MAX))) return rc;
+    if ((rc = route(ctx->mgIdV, ctx->mgIdK, nSlice, dtab + 2 * cdgsort::ROUTE_MAX, dtab + 3 * cdgsort::ROUTE_MAX))) return rc;
+    CKL();
+    CK(cudaStreamSynchronize(ctx->st));
+    return CDG_OK;
+}
+
+// Send side of the grouped-record all-to-all: block-aggregated append into the peers' receive buffers (order is irrelevant,
+// sort 2 follows).  dst_off[o] = first record index of this rank's segment in rank o's receive area.
+extern "C" int cdg_mg_scatter_grouped(cdg_ctx *ctx, const uint64_t *dst_off) {
+    if (!ctx || !dst_off) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    using namespace cdgkmer;
+    const KmPlan &K = ctx->plan;
+    const u64 R2 = ctx->nGrouped;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    CK(ctx->dRouteTab.reserve(4 * cdgsort::ROUTE_MAX * sizeof(void *)));
+    u64 *tab[cdgsort::ROUTE_MAX] = {};
+    for (u32 o = 0; o < K.world; o++) {
+        u64 *base = o == K.rank ? ctx->dRecv2.as<u64>() : (u64 *) ctx->peerPtr[4][o];
+        if (!base) return fail(ctx, CDG_ERR_ARG, "cdg_mg_scatter_grouped: receive buffer of rank %u is not mapped (cdg_mg_ipc_open)", o);
+        tab[o] = base + dst_off[o];
+    }
+    CK(cudaMemcpyAsync(ctx->dRouteTab.p, tab, sizeof tab, cudaMemcpyHostToDevice, ctx->st));
+    if (R2) {
+        unsigned long long *cursors = sc + SC_ROUTE;
+        CK(cudaMemsetAsync(cursors, 0, 16 * 8, ctx->st));
+        const int blocks = (int) std::min<u64>((R2 + 255) / 256, (u64) ctx->smCount * 16);
+        route_scatter_kernel<<<blocks, 256, 0, ctx->st>>>(ctx->dKey2A.as<u64>(), R2, K.idBits + K.diagBits + 1, K.repChunk, K.world, cursors, nullptr,
+                                                          ctx->dRouteTab.as<u64 *>());
+        ctx->launches++;
+        CKL();
+    }
+    CK(cudaStreamSynchronize(ctx->st));
     return CDG_OK;
 }
 

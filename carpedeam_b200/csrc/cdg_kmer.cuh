@@ -525,9 +525,12 @@ __global__ void __launch_bounds__(256) route_count_kernel(const u64 *__restrict_
     __syncthreads();
     if (threadIdx.x < world && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long) sc[threadIdx.x]);
 }
+// outTab == nullptr: one local output array, cursors start at the segment offsets.  outTab != nullptr: the send side of the
+// grouped-record all-to-all — outTab[o] is this rank's segment of rank o's receive buffer (peer memory over NVLink, CUDA IPC),
+// cursors start at 0; a block's records for one owner are appended as one burst.
 __global__ void __launch_bounds__(256) route_scatter_kernel(const u64 *__restrict__ key2, u64 n, int repShift, u32 repChunk, u32 world,
-                                                            unsigned long long *__restrict__ cursors /*[world], start = segment offsets*/,
-                                                            u64 *__restrict__ out) {
+                                                            unsigned long long *__restrict__ cursors /*[world]*/,
+                                                            u64 *__restrict__ out, u64 *const *__restrict__ outTab = nullptr) {
     // block-aggregated append: per-owner counts of a 2048-record tile in shared memory, one global atomic per owner and block
     constexpr int ITEMS = 8;
     __shared__ u32 sCnt[16];
@@ -557,7 +560,7 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(const u64 *__restric
         if (threadIdx.x < world && sCnt[threadIdx.x]) sBase[threadIdx.x] = atomicAdd(&cursors[threadIdx.x], (unsigned long long) sCnt[threadIdx.x]);
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < ITEMS; j++) if (o[j] != 0xFFFFFFFFu) out[sBase[o[j]] + r[j]] = k[j];
+        for (int j = 0; j < ITEMS; j++) if (o[j] != 0xFFFFFFFFu) (outTab ? outTab[o[j]] : out)[sBase[o[j]] + r[j]] = k[j];
         __syncthreads();
     }
 }

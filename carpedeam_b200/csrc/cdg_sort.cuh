@@ -17,6 +17,7 @@ static constexpr int BLOCK = 256;                 // histogram kernel block
 static constexpr int MAX_PASSES = 16;
 static constexpr u32 FLAG_AGG = 1u << 30, FLAG_INC = 2u << 30, FLAG_MASK = 3u << 30, VAL_MASK = ~FLAG_MASK;
 static constexpr u64 MAX_N = (1ull << 30) - 1;    // 30-bit tile-state counters
+static constexpr int ROUTE_MAX = 16;              // digits of a routing pass (= ranks)
 
 struct Pass { int word; int shift; u32 mask; };   // word: 0 = key, 1 = val
 struct Plan { int n; Pass p[MAX_PASSES]; };
@@ -81,6 +82,7 @@ struct SweepSmem {
     unsigned long long delta[RADIX];
     u32 warpSum[8];
     u32 sTile;
+    u64 *routeK[ROUTE_MAX]; u64 *routeV[ROUTE_MAX];   // ROUTE: per-digit output bases (peer-mapped receive buffers)
     u8 digitAt[HAS_VAL ? TILE_T : 4];
 };
 
@@ -97,16 +99,22 @@ CDG_D u32 digit_peers(u32 d) {
     return m;
 }
 
-template <int BLOCK_T, int ITEMS_T, bool HAS_VAL>
+// ROUTE: the pass is the send side of an all-to-all.  Digit d (< ROUTE_MAX) is a destination rank and its records go, in
+// stable order, to routeK[d] / routeV[d] — the rank's segment of peer d's receive buffer, mapped into this process over
+// NVLink (CUDA IPC) — instead of one local output array: the partition and the transfer are one kernel, the tile's run
+// of each digit is written as one coalesced burst into peer memory.  binBase must be all zero (offsets are per segment).
+template <int BLOCK_T, int ITEMS_T, bool HAS_VAL, bool ROUTE = false>
 __global__ void __launch_bounds__(BLOCK_T) onesweep_kernel(const u64 *__restrict__ keysIn, u64 *__restrict__ keysOut,
                                                            const u64 *__restrict__ valsIn, u64 *__restrict__ valsOut, u64 n,
                                                            Pass pass, const unsigned long long *__restrict__ binBase,
-                                                           u32 *tileState /*[tiles][RADIX]*/, u32 *ticket) {
+                                                           u32 *tileState /*[tiles][RADIX]*/, u32 *ticket,
+                                                           u64 *const *__restrict__ routeK = nullptr, u64 *const *__restrict__ routeV = nullptr) {
     constexpr int TILE_T = BLOCK_T * ITEMS_T, WARPS_T = BLOCK_T / 32;
     extern __shared__ __align__(16) unsigned char sweepRaw[];
     SweepSmem<BLOCK_T, ITEMS_T, HAS_VAL> &S = *reinterpret_cast<SweepSmem<BLOCK_T, ITEMS_T, HAS_VAL> *>(sweepRaw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (ROUTE && tid < ROUTE_MAX) { S.routeK[tid] = routeK[tid]; if (HAS_VAL) S.routeV[tid] = routeV[tid]; }
     if (tid == 0) S.sTile = atomicAdd(ticket, 1u);
     for (int i = tid; i < WARPS_T * RADIX; i += BLOCK_T) (&S.warpHist[0][0])[i] = 0;
     __syncthreads();
@@ -217,13 +225,18 @@ __global__ void __launch_bounds__(BLOCK_T) onesweep_kernel(const u64 *__restrict
         for (int i = 0; i < ITEMS_T; i++) {
             const u32 j = tid + i * BLOCK_T;
             const u64 k = S.exch[j];
-            keysOut[S.delta[digit_of(k, pass.shift, pass.mask)] + j] = k;
+            const u32 dg = digit_of(k, pass.shift, pass.mask);
+            (ROUTE ? S.routeK[dg & (ROUTE_MAX - 1)] : keysOut)[S.delta[dg] + j] = k;
         }
     } else {
 #pragma unroll
         for (int i = 0; i < ITEMS_T; i++) {
             const u32 j = tid + i * BLOCK_T;
-            if (j < tileValid) { const u64 k = S.exch[j]; keysOut[S.delta[digit_of(k, pass.shift, pass.mask)] + j] = k; }
+            if (j < tileValid) {
+                const u64 k = S.exch[j];
+                const u32 dg = digit_of(k, pass.shift, pass.mask);
+                (ROUTE ? S.routeK[dg & (ROUTE_MAX - 1)] : keysOut)[S.delta[dg] + j] = k;
+            }
         }
     }
     if (HAS_VAL) {
@@ -234,7 +247,7 @@ __global__ void __launch_bounds__(BLOCK_T) onesweep_kernel(const u64 *__restrict
 #pragma unroll
         for (int i = 0; i < ITEMS_T; i++) {
             const u32 j = tid + i * BLOCK_T;
-            if (full || j < tileValid) valsOut[S.delta[S.digitAt[j]] + j] = S.exch[j];
+            if (full || j < tileValid) { const u32 dg = S.digitAt[j]; (ROUTE ? S.routeV[dg & (ROUTE_MAX - 1)] : valsOut)[S.delta[dg] + j] = S.exch[j]; }
         }
     }
 }
@@ -437,6 +450,16 @@ inline void launch_pass(cudaStream_t st, const u64 *ki, u64 *ko, const u64 *vi, 
     if (!attrSet) { cudaFuncSetAttribute(onesweep_kernel<BLOCK_T, ITEMS_T, HAS_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(SM)); attrSet = true; }
     const u64 tiles = (n + SM::TILE_T - 1) / SM::TILE_T;
     onesweep_kernel<BLOCK_T, ITEMS_T, HAS_VAL><<<(unsigned) tiles, BLOCK_T, sizeof(SM), st>>>(ki, ko, vi, vo, n, p, binBase, tileState, ticket);
+}
+
+// routing pass (send side of the all-to-all): digits = destination ranks, outputs = peer-mapped segment bases (device tables)
+inline void launch_route_pass(cudaStream_t st, const u64 *ki, const u64 *vi, u64 n, const Pass &p, const unsigned long long *zeroBase,
+                              u32 *tileState, u32 *ticket, u64 *const *routeK, u64 *const *routeV) {
+    typedef SweepSmem<256, 16, true> SM;
+    static bool attrSet = false;
+    if (!attrSet) { cudaFuncSetAttribute(onesweep_kernel<256, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(SM)); attrSet = true; }
+    const u64 tiles = (n + SM::TILE_T - 1) / SM::TILE_T;
+    onesweep_kernel<256, 16, true, true><<<(unsigned) tiles, 256, sizeof(SM), st>>>(ki, nullptr, vi, nullptr, n, p, zeroBase, tileState, ticket, routeK, routeV);
 }
 
 // variant: 0 = 256 threads x 16 keys, 1 = 256 x 8, 2 = 512 x 8, 3 = 384... (tuning knob; default chosen by measurements)

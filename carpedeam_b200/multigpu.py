@@ -1,6 +1,11 @@
 """Multi-GPU iteration: one process per GPU, k-mer records owned by hash range (kmermatcher's split scheme,
 kmermatcher.cpp:742-784), exchanged with NCCL all-to-all over NVLink through torch.distributed.
 
+Two exchange modes.  "p2p" (default): every rank maps its peers' receive buffers (CUDA IPC over NVLink) and the SENDER's
+partition kernel writes each record straight into its owner's memory — the partition pass and the all-to-all are one kernel
+(cdg_mg_scatter_records / cdg_mg_scatter_grouped); torch.distributed only moves counts, handles and barriers.  "nccl": partition
+locally, then all_to_all_single (the baseline the fused path is measured against).
+
 Plumbing only — every kernel lives in libcarpedeam_gpu.so (cdg_mg_* phases).  The exchange plan is written against a tiny
 `Comm` interface so that the host logic (split sizes, ordering by source rank, ring shift of the head run, first-run
 decision) is testable on CPU with gloo (tests/test_multigpu_host.py).
@@ -66,6 +71,25 @@ class TorchComm:
         return self.dist.all_to_all_single(recv, send, output_split_sizes=[int(c) for c in recv_counts],
                                            input_split_sizes=[int(c) for c in send_counts], async_op=async_op)
 
+    def all_gather_rows(self, row):
+        """row: list of ints (int64 range) -> list over ranks of such rows"""
+        t = self.torch.tensor([int(x) for x in row], dtype=self.torch.int64, device=self.device)
+        out = self.torch.empty(self.world * len(row), dtype=self.torch.int64, device=self.device)
+        self.dist.all_gather_into_tensor(out, t)
+        flat = out.tolist()
+        return [flat[r * len(row):(r + 1) * len(row)] for r in range(self.world)]
+
+    def all_gather_bytes(self, payload):
+        """payload: bytes of equal length on every rank -> list of bytes per rank"""
+        t = self.torch.frombuffer(bytearray(payload), dtype=self.torch.uint8).to(self.device)
+        out = self.torch.empty(self.world * len(payload), dtype=self.torch.uint8, device=self.device)
+        self.dist.all_gather_into_tensor(out, t)
+        b = out.cpu().numpy().tobytes()
+        return [b[r * len(payload):(r + 1) * len(payload)] for r in range(self.world)]
+
+    def barrier(self):
+        self.dist.barrier()
+
     def all_gather_u64(self, value):
         t = self.torch.tensor([np.uint64(value).astype(np.int64)], dtype=self.torch.int64, device=self.device)
         out = [self.torch.empty_like(t) for _ in range(self.world)]
@@ -88,6 +112,15 @@ class TorchComm:
         return n_recv
 
 
+def segment_offsets(matrix, rank):
+    """matrix[r][o] = records rank r sends to rank o.  Returns (dst_off, totals): dst_off[o] = first index of `rank`'s segment in
+    o's receive area (segments are ordered by source rank, like an all-to-all's output), totals[o] = records o receives."""
+    world = len(matrix)
+    dst_off = [sum(int(matrix[r][o]) for r in range(rank)) for o in range(world)]
+    totals = [sum(int(matrix[r][o]) for r in range(world)) for o in range(world)]
+    return dst_off, totals
+
+
 def first_run_owner(min_keys):
     """rank holding the globally smallest k-mer key (ties: lowest rank); None if no rank has a record."""
     best, who = None, None
@@ -102,15 +135,24 @@ def first_run_owner(min_keys):
 class ShardedIteration:
     """Drives one context (= one GPU) through the five phases."""
 
-    def __init__(self, ctx, comm):
-        self.ctx, self.comm = ctx, comm
+    HANDLE_BYTES = 72
+
+    def __init__(self, ctx, comm, exchange="p2p"):
+        assert exchange in ("p2p", "nccl")
+        self.ctx, self.comm, self.exchange = ctx, comm, exchange
         L = lib()
-        L.cdg_mg_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+        L.cdg_mg_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.cdg_mg_ipc_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.cdg_mg_ipc_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.cdg_mg_ipc_capacity.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+        L.cdg_mg_ipc_close.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.cdg_mg_scatter_records.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.cdg_mg_scatter_grouped.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.cdg_mg_recv_records.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                           C.POINTER(C.c_void_p)]
         L.cdg_mg_sort.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
-        L.cdg_mg_group.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
+        L.cdg_mg_group.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
         L.cdg_mg_recv_grouped.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
         L.cdg_mg_sort2.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.cdg_mg_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
@@ -122,6 +164,54 @@ class ShardedIteration:
         if n == 0:
             return torch.empty(0, dtype=torch.int64, device=self.comm.device)
         return torch.as_tensor(DevArray(ptr, n), device=self.comm.device)
+
+    MIN_BYTES = 8 << 20
+    HEAD_RUN = 4096
+
+    def _capacities(self, buffers):
+        out = []
+        for which in buffers:
+            c = C.c_uint64()
+            self.ctx._ck(self.L.cdg_mg_ipc_capacity(self.ctx._h, which, C.byref(c)), "cdg_mg_ipc_capacity")
+            out.append(int(c.value))
+        return out
+
+    def _release_if_growing(self, buffers, needs_by_rank, caps_by_rank):
+        """A receive buffer may only be reallocated after every peer dropped its mapping.  All ranks see the same numbers, so they
+        take the same branch: if any rank is about to grow a buffer of this group, everyone closes the group and meets at a barrier."""
+        grow = any(need > cap for needs, caps in zip(needs_by_rank, caps_by_rank) for need, cap in zip(needs, caps))
+        if grow:
+            for which in buffers:
+                for peer in range(self.comm.world):
+                    if peer != self.comm.rank:
+                        self.ctx._ck(self.L.cdg_mg_ipc_close(self.ctx._h, which, peer), "cdg_mg_ipc_close")
+            self.comm.barrier()
+        return grow
+
+    def release(self):
+        """drop every peer mapping (collective): call before the contexts are destroyed or the receive buffers are reused elsewhere"""
+        if self.exchange != "p2p":
+            return
+        for which in range(5):
+            for peer in range(self.comm.world):
+                if peer != self.comm.rank:
+                    self.ctx._ck(self.L.cdg_mg_ipc_close(self.ctx._h, which, peer), "cdg_mg_ipc_close")
+        self.comm.barrier()
+
+    def _map_peers(self, buffers):
+        """exchange the IPC handles of this rank's receive buffers `buffers` and map every peer's (cached inside the library)"""
+        ctx, comm, L = self.ctx, self.comm, self.L
+        mine = b""
+        for which in buffers:
+            h = C.create_string_buffer(self.HANDLE_BYTES)
+            ctx._ck(L.cdg_mg_ipc_export(ctx._h, which, h), "cdg_mg_ipc_export")
+            mine += h.raw
+        for peer, blob in enumerate(comm.all_gather_bytes(mine)):
+            if peer == comm.rank:
+                continue
+            for i, which in enumerate(buffers):
+                hb = C.create_string_buffer(blob[i * self.HANDLE_BYTES:(i + 1) * self.HANDLE_BYTES], self.HANDLE_BYTES)
+                ctx._ck(L.cdg_mg_ipc_open(ctx._h, which, peer, hb), "cdg_mg_ipc_open")
 
     def run(self, kmer=None, rescore=None, corr=None, fetch_hits=False, fetch_alns=False, out_range=None):
         ctx, comm, L = self.ctx, self.comm, self.L
@@ -140,24 +230,41 @@ class ShardedIteration:
             tm[name] = tm.get(name, 0.0) + (now - t_last[0]) * 1e3
             t_last[0] = now
         # phase 1
+        p2p = self.exchange == "p2p"
         sc = (C.c_uint64 * world)(); isc = (C.c_uint64 * world)()
         sk, sv, ik, iv = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-        ctx._ck(L.cdg_mg_extract(ctx._h, C.byref(kp), world, rank, sc, C.byref(sk), C.byref(sv), isc, C.byref(ik), C.byref(iv)), "cdg_mg_extract")
+        ctx._ck(L.cdg_mg_extract(ctx._h, C.byref(kp), world, rank, 0 if p2p else 1, sc, C.byref(sk), C.byref(sv), isc, C.byref(ik), C.byref(iv)),
+                "cdg_mg_extract")
         send_counts = list(sc); id_send = list(isc)
-        lap("extract+partition")
-        both = comm.exchange_counts(send_counts + id_send)      # [counts of rank 0, ids of rank 0, counts of rank 1, ...] see exchange_counts
-        recv_counts, id_recv = both[0::2], both[1::2]
-        total, id_total = sum(recv_counts), sum(id_recv)
-        rk, rv, irk, irv = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-        ctx._ck(L.cdg_mg_recv_records(ctx._h, total, id_total, C.byref(rk), C.byref(rv), C.byref(irk), C.byref(irv)), "cdg_mg_recv_records")
         nsend, id_nsend = sum(send_counts), sum(id_send)
-        # one exchange: k-mer records and the identity records of the slice (keys and values of each, issued together)
-        ws = [comm.all_to_all(self._t(rk.value, total), self._t(sk.value, nsend), recv_counts, send_counts, async_op=True),
-              comm.all_to_all(self._t(rv.value, total), self._t(sv.value, nsend), recv_counts, send_counts, async_op=True),
-              comm.all_to_all(self._t(irk.value, id_total), self._t(ik.value, id_nsend), id_recv, id_send, async_op=True),
-              comm.all_to_all(self._t(irv.value, id_total), self._t(iv.value, id_nsend), id_recv, id_send, async_op=True)]
-        for w in ws:
-            w.wait()
+        lap("extract+partition" if not p2p else "extract+count")
+        rk, rv, irk, irv = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        if p2p:
+            # every rank learns the whole count matrix; this all-gather is also the barrier that says every peer is done with
+            # the receive buffers of the previous iteration
+            rows = comm.all_gather_rows(send_counts + id_send + self._capacities((0, 1, 2, 3)))
+            dst, totals = segment_offsets([r[:world] for r in rows], rank)
+            id_dst, id_totals = segment_offsets([r[world:2 * world] for r in rows], rank)
+            total, id_total = totals[rank], id_totals[rank]
+            need = lambda t: max((t + 1) * 8, self.MIN_BYTES)
+            self._release_if_growing((0, 1, 2, 3), [[need(totals[r])] * 2 + [need(id_totals[r])] * 2 for r in range(world)],
+                                     [r[2 * world:] for r in rows])
+            ctx._ck(L.cdg_mg_recv_records(ctx._h, total, id_total, C.byref(rk), C.byref(rv), C.byref(irk), C.byref(irv)), "cdg_mg_recv_records")
+            self._map_peers((0, 1, 2, 3))
+            ctx._ck(L.cdg_mg_scatter_records(ctx._h, (C.c_uint64 * world)(*dst), (C.c_uint64 * world)(*id_dst)), "cdg_mg_scatter_records")
+            comm.barrier()      # all partitions have landed
+        else:
+            both = comm.exchange_counts(send_counts + id_send)
+            recv_counts, id_recv = both[0::2], both[1::2]
+            total, id_total = sum(recv_counts), sum(id_recv)
+            ctx._ck(L.cdg_mg_recv_records(ctx._h, total, id_total, C.byref(rk), C.byref(rv), C.byref(irk), C.byref(irv)), "cdg_mg_recv_records")
+            # one exchange: k-mer records and the identity records of the slice (keys and values of each, issued together)
+            ws = [comm.all_to_all(self._t(rk.value, total), self._t(sk.value, nsend), recv_counts, send_counts, async_op=True),
+                  comm.all_to_all(self._t(rv.value, total), self._t(sv.value, nsend), recv_counts, send_counts, async_op=True),
+                  comm.all_to_all(self._t(irk.value, id_total), self._t(ik.value, id_nsend), id_recv, id_send, async_op=True),
+                  comm.all_to_all(self._t(irv.value, id_total), self._t(iv.value, id_nsend), id_recv, id_send, async_op=True)]
+            for w in ws:
+                w.wait()
         lap("all_to_all records")
         # phase 2
         mk = C.c_uint64()
@@ -167,14 +274,25 @@ class ShardedIteration:
         # phase 3
         sc2 = (C.c_uint64 * world)()
         s2 = C.c_void_p()
-        ctx._ck(L.cdg_mg_group(ctx._h, C.byref(kp), 1 if owner == rank else 0, sc2, C.byref(s2)), "cdg_mg_group")
+        ctx._ck(L.cdg_mg_group(ctx._h, C.byref(kp), 1 if owner == rank else 0, 0 if p2p else 1, sc2, C.byref(s2)), "cdg_mg_group")
         send2 = list(sc2)
-        lap("group+route")
-        recv2 = comm.exchange_counts(send2)
-        total2 = sum(recv2)
+        lap("group+route" if not p2p else "group+count")
         r2 = C.c_void_p()
-        ctx._ck(L.cdg_mg_recv_grouped(ctx._h, total2, C.byref(r2)), "cdg_mg_recv_grouped")
-        comm.all_to_all(self._t(r2.value, total2), self._t(s2.value, sum(send2)), recv2, send2)
+        if p2p:
+            rows2 = comm.all_gather_rows(send2 + self._capacities((4,)))
+            dst2, totals2 = segment_offsets([r[:world] for r in rows2], rank)
+            total2 = totals2[rank]
+            self._release_if_growing((4,), [[max((totals2[r] + self.HEAD_RUN + 1) * 8, self.MIN_BYTES)] for r in range(world)],
+                                     [r[world:] for r in rows2])
+            ctx._ck(L.cdg_mg_recv_grouped(ctx._h, total2, C.byref(r2)), "cdg_mg_recv_grouped")
+            self._map_peers((4,))
+            ctx._ck(L.cdg_mg_scatter_grouped(ctx._h, (C.c_uint64 * world)(*dst2)), "cdg_mg_scatter_grouped")
+            comm.barrier()
+        else:
+            recv2 = comm.exchange_counts(send2)
+            total2 = sum(recv2)
+            ctx._ck(L.cdg_mg_recv_grouped(ctx._h, total2, C.byref(r2)), "cdg_mg_recv_grouped")
+            comm.all_to_all(self._t(r2.value, total2), self._t(s2.value, sum(send2)), recv2, send2)
         lap("all_to_all grouped")
         # phase 4
         sorted_ptr, head_n, head_cap = C.c_void_p(), C.c_uint64(), C.c_uint64()

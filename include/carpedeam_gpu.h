@@ -198,12 +198,24 @@ int cdg_iteration(cdg_ctx *ctx, const cdg_iter_params *p, cdg_hits *hits, cdg_al
  *   cdg_mg_group    -> all-to-all of the 8-byte grouped records to the rank owning the representative's index range
  *   cdg_mg_recv_grouped / cdg_mg_sort2 -> the leading records with one target id go to rank-1 (rep-boundary bleed, :886-888)
  *   cdg_mg_finish   -> hits, alignments and corrected bytes of the rank's query range [rank*ceil(n/world), ...) */
-int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world, int rank, uint64_t *send_counts, void **send_keys, void **send_vals,
-                   uint64_t *id_send_counts, void **id_send_keys, void **id_send_vals);
+/* partition != 0: the records are partitioned by owner into contiguous send buffers for an NCCL all-to-all (baseline exchange).
+ * partition == 0: only the per-owner counts are returned; cdg_mg_scatter_records then writes the partition straight into the
+ * peers' receive buffers over NVLink (CUDA IPC mappings from cdg_mg_ipc_export / cdg_mg_ipc_open) — partition pass and transfer
+ * are one kernel. */
+int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world, int rank, int partition, uint64_t *send_counts, void **send_keys,
+                   void **send_vals, uint64_t *id_send_counts, void **id_send_keys, void **id_send_vals);
 int cdg_mg_recv_records(cdg_ctx *ctx, uint64_t total, uint64_t id_total, void **recv_keys, void **recv_vals, void **id_recv_keys,
                         void **id_recv_vals);
+/* receive buffer `which`: 0 k-mer keys, 1 k-mer values, 2 identity keys, 3 identity values, 4 grouped records.  handle = 72 bytes. */
+int cdg_mg_ipc_export(cdg_ctx *ctx, int which, void *handle_out);
+int cdg_mg_ipc_open(cdg_ctx *ctx, int which, int peer, const void *handle);
+/* a receive buffer must not be reallocated while a peer maps it: capacity (bytes) so that the ranks can agree to close first */
+int cdg_mg_ipc_capacity(cdg_ctx *ctx, int which, uint64_t *bytes);
+int cdg_mg_ipc_close(cdg_ctx *ctx, int which, int peer);
+int cdg_mg_scatter_records(cdg_ctx *ctx, const uint64_t *dst_off, const uint64_t *id_dst_off);
+int cdg_mg_scatter_grouped(cdg_ctx *ctx, const uint64_t *dst_off);
 int cdg_mg_sort(cdg_ctx *ctx, const cdg_kmer_params *p, uint64_t *min_key);
-int cdg_mg_group(cdg_ctx *ctx, const cdg_kmer_params *p, int has_global_first_run, uint64_t *send_counts, void **send_key2);
+int cdg_mg_group(cdg_ctx *ctx, const cdg_kmer_params *p, int has_global_first_run, int partition, uint64_t *send_counts, void **send_key2);
 int cdg_mg_recv_grouped(cdg_ctx *ctx, uint64_t total, void **recv_key2);
 int cdg_mg_sort2(cdg_ctx *ctx, void **sorted, uint64_t *head_count, uint64_t *head_capacity);
 int cdg_mg_finish(cdg_ctx *ctx, const cdg_rescore_params *rp, const cdg_corr_params *cp, uint64_t n_appended, cdg_hits *hits, cdg_alns *alns,

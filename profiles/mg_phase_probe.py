@@ -43,7 +43,7 @@ def main():
         t0 = time.perf_counter()
         sc = (C.c_uint64 * a.world)(); isc = (C.c_uint64 * a.world)()
         sk, sv, ik, iv = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-        ctx._ck(L.cdg_mg_extract(ctx._h, C.byref(kp), a.world, 0, sc, C.byref(sk), C.byref(sv), isc, C.byref(ik), C.byref(iv)), "cdg_mg_extract")
+        ctx._ck(L.cdg_mg_extract(ctx._h, C.byref(kp), a.world, 0, 1, sc, C.byref(sk), C.byref(sv), isc, C.byref(ik), C.byref(iv)), "cdg_mg_extract")
         lap("extract+partition", t0)
         total, id_total = sum(sc), sum(isc)
         rk, rv, irk, irv = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -57,7 +57,7 @@ def main():
         lap("identity+sort1", t0)
         t0 = time.perf_counter()
         sc2 = (C.c_uint64 * a.world)(); s2 = C.c_void_p()
-        ctx._ck(L.cdg_mg_group(ctx._h, C.byref(kp), 1, sc2, C.byref(s2)), "cdg_mg_group")
+        ctx._ck(L.cdg_mg_group(ctx._h, C.byref(kp), 1, 1, sc2, C.byref(s2)), "cdg_mg_group")
         lap("group+route", t0)
         print("iteration %d: records %d  " % (it, total) + "  ".join("%s %.1f ms" % kv for kv in t.items()), flush=True)
     ctx.close()

@@ -27,10 +27,12 @@ def main():
              ("golden contigs k=22 ext", SeqSet.from_golden("assembly_contigs_8_noneCycle"), cd.kmer_params(k=22, include_only_extendable=1)),
              ("synthetic 60k", SeqSet(synth_reads(60000, 300000, 21, n_frac=0.001)), cd.kmer_params())]
     ok = True
-    for name, s, kp in cases:
+    modes = os.environ.get("CDG_MG_EXCHANGE", "p2p,nccl").split(",")
+    sharded = {m: ShardedIteration(ctx, comm, exchange=m) for m in modes}
+    for name, s, kp in [(n + " [" + m + "]", s_, k_) for (n, s_, k_) in cases for m in modes]:
         ctx.upload(s.blob, s.off, s.len, s.ext)
         out_range = np.zeros(len(s.blob), np.uint8)
-        res = ShardedIteration(ctx, comm).run(kmer=kp, fetch_hits=True, fetch_alns=True, out_range=out_range)
+        res = sharded[name[name.rindex("[") + 1:-1]].run(kmer=kp, fetch_hits=True, fetch_alns=True, out_range=out_range)
         parts = [None] * world
         dist.all_gather_object(parts, dict(hits=res["hits"], alns=res["alns"], off=res["range_offset"], nbytes=res["range_bytes"],
                                            out=out_range[:res["range_bytes"]].copy(), changed=res["changed"],
@@ -50,9 +52,11 @@ def main():
                 merged[p["off"]:p["off"] + p["nbytes"]] = p["out"]
             if not np.array_equal(merged, out) or sum(p["changed"] for p in parts) != changed:
                 ok = False; print("MISMATCH", name, "corrected bytes")
-            print("case %-28s world=%d hits=%d changed=%d %s" % (name, world, len(hits["rep"]), changed, [p["stats"] for p in parts]))
+            print("case %-36s world=%d hits=%d changed=%d %s" % (name, world, len(hits["rep"]), changed, [p["stats"] for p in parts]))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
+    for sh in sharded.values():
+        sh.release()
     ctx.close()
     dist.destroy_process_group()
     if rank == 0:

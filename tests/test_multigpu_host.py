@@ -13,7 +13,7 @@ WORKER = r'''
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, %r)
-from carpedeam_b200.multigpu import TorchComm, first_run_owner, owner_hash_range, split_offsets, SENTINEL
+from carpedeam_b200.multigpu import TorchComm, first_run_owner, owner_hash_range, segment_offsets, split_offsets, SENTINEL
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 comm = TorchComm(torch.device("cpu"))
@@ -35,6 +35,16 @@ for src in range(world):
     assert np.all(seg %% world == rank), "every record reached its owner"
     assert np.all(np.diff(seg) > 0), "order inside a source segment is preserved"
 assert sum(recv_counts) == sum(int(((np.arange(1000 + 37 * r) + r * 1_000_000) %% world == rank).sum()) for r in range(world))
+# peer-memory exchange plan: the count matrix every rank gathers gives the same segment layout an all-to-all produces
+rows = comm.all_gather_rows(send_counts + [n, rank])
+assert [r[-1] for r in rows] == list(range(world)) and rows[rank][:world] == send_counts
+dst, totals = segment_offsets([r[:world] for r in rows], rank)
+assert totals[rank] == sum(recv_counts)
+assert dst[rank] == off[rank], "own segment starts where the all-to-all put it"
+for o in range(world):
+    assert dst[o] == sum(rows[r][o] for r in range(rank))
+blobs = comm.all_gather_bytes(bytes([rank]) * 72)
+assert [b[0] for b in blobs] == list(range(world)) and all(len(b) == 72 for b in blobs)
 # u64 all-gather incl. values above 2^63, and the first-run decision
 mine = SENTINEL if rank == 1 else (1 << 63) | 12345
 keys = comm.all_gather_u64(mine)
