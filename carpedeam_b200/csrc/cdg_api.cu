@@ -353,8 +353,12 @@ static int km_prepare(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlan &K) {
     ctx->launches += lo + 1;
     ctx->ordV = ordV;
     if ((rc = scan_to(ctx, OrderedCapacityF{ordV, ctx->dLen.as<u32>(), p->k, p->kmers_per_seq, p->kmers_per_seq_scale}, n, ctx->dSlotRank.as<u64>(), true))) return rc;
-    order_scatter_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ordV, ctx->dSlotRank.as<u64>(), n, ctx->dSlotOff.as<u64>(), ctx->dRankOf.as<u32>());
-    ctx->launches++;
+    // per-sequence views of the order (slot offset, rank): the single-GPU extraction walks the sequences in index order, and the
+    // block-per-sequence kernel for long sequences looks them up; a multi-GPU slice of short reads walks the order itself
+    if (K.world == 1 || !cdgkmer::is_short_seq(ctx->maxLen, p->k, p->kmers_per_seq, p->kmers_per_seq_scale)) {
+        order_scatter_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ordV, ctx->dSlotRank.as<u64>(), n, ctx->dSlotOff.as<u64>(), ctx->dRankOf.as<u32>());
+        ctx->launches++;
+    }
     u64 total = 0;
     if ((rc = read_scalar(ctx, SC_SCAN, &total))) return rc;
     K.posLo = 0; K.posHi = (u32) n; K.slotBase = 0; K.slots = total;
@@ -391,14 +395,16 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
     ExtractParams E; E.k = p->k; E.kmersPerSeq = p->kmers_per_seq; E.scale = p->kmers_per_seq_scale; E.seed = p->hash_shift;
     E.hashLo = hashLo; E.hashHi = hashHi; E.world = K.world; E.posLo = K.posLo; E.posHi = K.posHi; E.slotBase = K.slotBase; E.identity = identityMode;
     int rc;
-    CK(ctx->dLongList.reserve(n * 4)); CK(ctx->dScratchOff.reserve(n * 8));
-    long_list_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dLen.as<u32>(), n, p->k, p->kmers_per_seq, p->kmers_per_seq_scale,
-                                                                        ctx->dLongList.as<u32>(), ctx->dScratchOff.as<u64>(), (u32 *) (sc + SC_NLONG),
-                                                                        sc + SC_LONGSCR);
-    ctx->launches++;
     u64 nLong64 = 0, longScr = 0;
-    if ((rc = read_scalar(ctx, SC_NLONG, &nLong64))) return rc;
-    if ((rc = read_scalar(ctx, SC_LONGSCR, &longScr))) return rc;
+    if (!is_short_seq(ctx->maxLen, p->k, p->kmers_per_seq, p->kmers_per_seq_scale)) {   // (monotonic in the length: the longest sequence decides)
+        CK(ctx->dLongList.reserve(n * 4)); CK(ctx->dScratchOff.reserve(n * 8));
+        long_list_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dLen.as<u32>(), n, p->k, p->kmers_per_seq, p->kmers_per_seq_scale,
+                                                                            ctx->dLongList.as<u32>(), ctx->dScratchOff.as<u64>(), (u32 *) (sc + SC_NLONG),
+                                                                            sc + SC_LONGSCR);
+        ctx->launches++;
+        if ((rc = read_scalar(ctx, SC_NLONG, &nLong64))) return rc;
+        if ((rc = read_scalar(ctx, SC_LONGSCR, &longScr))) return rc;
+    }
     const u32 nLong = (u32) nLong64;
     int perSm = 3;   // persistent grid: as many resident blocks as the registers allow
     {
@@ -488,14 +494,15 @@ static int km_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64
 }
 
 // sort 2 of R2 records in dKey2A (partner dKey2B); result pointer in ctx->sortedKey2
-static int km_sort2(cdg_ctx *ctx, const KmPlan &K, u64 R2) {
+static int km_sort2(cdg_ctx *ctx, const KmPlan &K, u64 R2, u64 *src = nullptr, u64 *alt = nullptr) {
     int rc;
     cdgsort::Workspace ws;
     if (R2 > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "grouped records exceed one sort");
     if ((rc = sort_ws(ctx, std::max<u64>(R2, ctx->n), ws))) return rc;
     u64 *dummy = nullptr;
     cdgsort::Plan plan2 = cdgsort::make_plan(0, 0, 1, 2 * K.idBits + K.diagBits + 1);   // bit 0 (needRev) is not an ordering key
-    int l3 = cdgsort::radix_sort(ctx->st, ws, ctx->dKey2A.as<u64>(), ctx->dKey2B.as<u64>(), nullptr, nullptr, R2, plan2, &ctx->sortedKey2, &dummy, ctx->smCount);
+    if (!src) { src = ctx->dKey2A.as<u64>(); alt = ctx->dKey2B.as<u64>(); }
+    int l3 = cdgsort::radix_sort(ctx->st, ws, src, alt, nullptr, nullptr, R2, plan2, &ctx->sortedKey2, &dummy, ctx->smCount);
     if (l3 < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "radix sort 2 failed");
     ctx->launches += l3; ctx->sort2Passes = plan2.n;
     CKL();
@@ -1221,9 +1228,8 @@ extern "C" int cdg_mg_sort2(cdg_ctx *ctx, void **sorted, uint64_t *head_count, u
     const KmPlan &K = ctx->plan;
     const u64 R2 = ctx->mgR2;
     int rc;
-    CK(ctx->dKey2A.reserve((R2 + CDG_HEAD_RUN + 1) * 8)); CK(ctx->dKey2B.reserve((R2 + CDG_HEAD_RUN + 1) * 8));
-    CK(cudaMemcpyAsync(ctx->dKey2A.p, ctx->dRecv2.p, R2 * 8, cudaMemcpyDeviceToDevice, ctx->st));
-    if ((rc = km_sort2(ctx, K, R2))) return rc;
+    CK(ctx->dKey2A.reserve((R2 + CDG_HEAD_RUN + 1) * 8));
+    if ((rc = km_sort2(ctx, K, R2, ctx->dRecv2.as<u64>(), ctx->dKey2A.as<u64>()))) return rc;   // sorted in place of the receive area and its partner
     // head run on the host: first min(R2, CDG_HEAD_RUN) keys, count the prefix with the first record's target id
     std::vector<u64> head(std::min<u64>(R2, CDG_HEAD_RUN));
     if (!head.empty()) CK(cudaMemcpyAsync(head.data(), ctx->sortedKey2, head.size() * 8, cudaMemcpyDeviceToHost, ctx->st));

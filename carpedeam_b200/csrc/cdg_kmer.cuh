@@ -163,7 +163,7 @@ CDG_D void select_sequential(const WinRec *sorted, u32 cnt, u32 considered, u32 
 // Goes to idKeys/idVals[seq] unless its value (bit 63 masked) lies inside the k-mer key range, in
 // which case it must be sorted among the k-mers: those go to the `extra` slots of the main array.
 CDG_D void emit_identity(u64 seqHash, u64 seq, const ExtractParams &P, u64 *idKeys, u64 *idVals, u64 *mainKeys, u64 *mainVals,
-                         u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow, const u32 *__restrict__ rankOf) {
+                         u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow, u32 myRank /*(length desc, id asc) rank of seq*/) {
     u32 h16 = (u32) (seqHash & 0xFFFFu);
     const bool slice = P.identity == 2;
     bool owned = slice || (h16 >= P.hashLo && h16 <= P.hashHi);
@@ -175,7 +175,7 @@ CDG_D void emit_identity(u64 seqHash, u64 seq, const ExtractParams &P, u64 *idKe
         else atomicExch(overflow, 1u);
         key = CDG_SENTINEL; val = 0;
     }
-    const u32 slot = rankOf[seq] - (slice ? P.posLo : 0u);   // (length desc, id asc) order: after the stable sort the representative comes first
+    const u32 slot = myRank - (slice ? P.posLo : 0u);   // (length desc, id asc) order: after the stable sort the representative comes first
     idKeys[slot] = key; idVals[slot] = val;
 }
 
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0 && P.identity) emit_identity(cdg_xxh64_u64(part, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow, rankOf);
+        if (lane == 0 && P.identity) emit_identity(cdg_xxh64_u64(part, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow, myRank);
 
         // windows: lane handles p = lane + 32*it
         WinRec rec[ITERS];
@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(EXL_BLOCK) extract_long_kernel(
 
     for (u32 li = blockIdx.x; li < nLong; li += gridDim.x) {
         const u64 seq = longList[li];
-        { const u32 r = rankOf[seq]; if (r < P.posLo || r >= P.posHi) continue; }   // block-uniform
+        const u32 myRank = rankOf[seq];
+        if (myRank < P.posLo || myRank >= P.posHi) continue;   // block-uniform
         const u32 L = len[seq];
         const u64 *w = words + wordOff[seq];
         const u32 *xm = xmask + wordOff[seq];
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(EXL_BLOCK) extract_long_kernel(
         if (tid == 0) {
             u64 h = 0;
             for (int i = 0; i < EXL_BLOCK / 32; i++) h += sHash[i];
-            if (P.identity) emit_identity(cdg_xxh64_u64(h, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow, rankOf);
+            if (P.identity) emit_identity(cdg_xxh64_u64(h, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow, myRank);
             u32 cnt = sCnt;
             float consF = (float) (P.kmersPerSeq - 1) + P.scale * (float) L;
             u64 cons64 = consF > 0.f ? (u64) consF : 0;
@@ -482,32 +483,6 @@ __global__ void __launch_bounds__(EXL_BLOCK) extract_long_kernel(
         for (u32 s = written + tid; s < cap; s += EXL_BLOCK) { mainKeys[slot0 + s] = CDG_SENTINEL; mainVals[slot0 + s] = 0; }
         if (tid == 0 && written) atomicAdd(emitted, (unsigned long long) written);
         __syncthreads();
-    }
-}
-
-// identity records of ALL sequences whose hash falls into [hashLo, hashHi] (multi-GPU: every rank holds the whole
-// sequence set, so no exchange is needed for them); one warp per sequence.
-__global__ void __launch_bounds__(256) identity_kernel(const u64 *__restrict__ words, const u32 *__restrict__ xmask, const u64 *__restrict__ wordOff,
-                                                       const u32 *__restrict__ len, u64 n, ExtractParams P, u64 *__restrict__ idKeys,
-                                                       u64 *__restrict__ idVals, u64 *__restrict__ mainKeys, u64 *__restrict__ mainVals, u64 extraBase,
-                                                       u32 extraCap, u32 *extraCount, u32 *overflow, const u32 *__restrict__ rankOf) {
-    const int lane = threadIdx.x & 31;
-    const u64 gwarp = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64) gridDim.x * blockDim.x) >> 5;
-    for (u64 seq = gwarp; seq < n; seq += nwarps) {
-        const u32 L = len[seq];
-        const u64 *w = words + wordOff[seq];
-        const u32 *xm = xmask + wordOff[seq];
-        u64 part = 0;
-        const u32 c = (L + 31) >> 5;
-        const u32 b0 = lane * c, b1 = min(b0 + c, L);
-        if (b0 < L) {
-            u64 h = 0;
-            for (u32 p = b0; p < b1; p++) h = h * 31 + (u64) base_code(w, xm, p);
-            part = h * pow31(L - b1);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) emit_identity(cdg_xxh64_u64(part, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow, rankOf);
     }
 }
 
