@@ -358,7 +358,10 @@ def main():
     last = {}
 
     def step_e2e():
-        upload()
+        if world == 1:
+            upload()
+        else:   # every rank copies 1/world of the host arrays, NVLink all-gather, pack from device memory
+            last["h2d"] = sharded.upload_sharded(h_blob, h_off, h_len)
         if world == 1:
             ctx.iteration_raw(ip, None, alns, h_out.data_ptr())
             last["M"] = alns.n_lines; last["d2h_seq"] = h_blob.numel()
@@ -397,7 +400,7 @@ def main():
     wall_e2e = (time.perf_counter() - t0) * 1e3
     stop.set(); th.join()
     M = last["M"]
-    h2d = int(h_blob.numel() + n * 8 + n * 4)
+    h2d = int(h_blob.numel() + n * 8 + n * 4) if world == 1 else int(last["h2d"])   # per rank
     d2h = int(last["d2h_seq"] + (st["n_seqs"] // world + 1) * 8 + M * (4 + 1 + 4 + 4 + 8 + 4 + 16))
     if world > 1:
         t = torch.tensor([ms, ms_e2e, wall_e2e], device="cuda", dtype=torch.float64)

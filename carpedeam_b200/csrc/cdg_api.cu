@@ -274,10 +274,10 @@ extern "C" int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_
     CK(ctx->dData.reserve(data_bytes + 64));
     CK(ctx->dOff.reserve(n * 8)); CK(ctx->dLen.reserve(n * 4)); CK(ctx->dExt.reserve(n)); CK(ctx->dFlags.reserve(n));
     CK(ctx->dWordOff.reserve((n + 1) * 8)); CK(ctx->dLikOff.reserve((n + 1) * 8));
-    CK(cudaMemcpyAsync(ctx->dData.p, data, data_bytes, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(ctx->dOff.p, offsets, n * 8, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(ctx->dLen.p, lens, n * 4, cudaMemcpyHostToDevice, ctx->st));
-    if (ext) CK(cudaMemcpyAsync(ctx->dExt.p, ext, n, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->dData.p, data, data_bytes, cudaMemcpyDefault, ctx->st));
+    CK(cudaMemcpyAsync(ctx->dOff.p, offsets, n * 8, cudaMemcpyDefault, ctx->st));
+    CK(cudaMemcpyAsync(ctx->dLen.p, lens, n * 4, cudaMemcpyDefault, ctx->st));
+    if (ext) CK(cudaMemcpyAsync(ctx->dExt.p, ext, n, cudaMemcpyDefault, ctx->st));
     else CK(cudaMemsetAsync(ctx->dExt.p, 0, n, ctx->st));
     // facts needed for sizing: total bases, longest sequence, packed words (all reduced on the device)
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();

@@ -188,6 +188,31 @@ class ShardedIteration:
             self.comm.barrier()
         return grow
 
+    def upload_sharded(self, blob, off, lens, ext=None):
+        """Every rank holds the same pinned host arrays (the mapped DB).  Instead of `world` full host-to-device copies, rank r
+        copies the r-th 1/world of each array and the ranks all-gather the pieces over NVLink; the library packs from device
+        memory.  blob: uint8, off: int64, lens: int32, ext: uint8 or None (torch CPU tensors)."""
+        torch, dist, comm = self.comm.torch, self.comm.dist, self.comm
+        world, rank, dev = comm.world, comm.rank, comm.device
+        full, h2d = [], 0
+        for a in (blob, off, lens, ext):
+            if a is None:
+                full.append(None)
+                continue
+            n = a.numel()
+            per = (n + world - 1) // world
+            lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+            shard = torch.zeros(per, dtype=a.dtype, device=dev)
+            shard[:hi - lo].copy_(a[lo:hi], non_blocking=True)
+            h2d += (hi - lo) * a.element_size()
+            out = torch.empty(per * world, dtype=a.dtype, device=dev)
+            dist.all_gather_into_tensor(out, shard)
+            full.append(out[:n])
+        torch.cuda.current_stream().synchronize()
+        self.ctx.upload_raw(full[0].data_ptr(), full[0].numel(), full[1].data_ptr(), full[2].data_ptr(),
+                            full[3].data_ptr() if full[3] is not None else 0, lens.numel())     # synchronous: `full` may go afterwards
+        return h2d      # bytes this rank copied from the host
+
     def release(self):
         """drop every peer mapping (collective): call before the contexts are destroyed or the receive buffers are reused elsewhere"""
         if self.exchange != "p2p":

@@ -50,7 +50,9 @@ void *cdg_stream(cdg_ctx *ctx);
  * data   : the DB data file bytes; entry i is data[offsets[i] .. offsets[i]+lens[i]) (then "\n\0")
  * lens   : sequence lengths without the trailing "\n\0"  (DBReader::getSeqLen)
  * ext    : CarpeDeam's 4th index column, "was extended" (DBReader::getExtData, DBReader.cpp:807-817)
- * The set stays resident on the device until the next upload.  Packs the bases to 2 bit + N mask. */
+ * The set stays resident on the device until the next upload.  Packs the bases to 2 bit + N mask.
+ * The four arrays may live in host memory (pinned memory makes the copy asynchronous) or in device memory of this GPU
+ * (multi-GPU: every rank reads 1/world of the DB from the host and the ranks all-gather over NVLink, multigpu.py). */
 int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, const uint64_t *offsets,
                     const uint32_t *lens, const uint8_t *ext, uint64_t n);
 
