@@ -169,9 +169,10 @@ def alg_bytes(st, k):
         H * (8 + 2 * Lbar / 4 + 32) + A * (32 + Lbar / 4) + S / 4 * 2
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of onesweep_kernel<true> over its algorithmic 2*16*records bytes, measured with
-# ncu --set full (profiles/r01c_ncu_full_raw_2Mreads.csv: 1.079 GB + 1.043 GB per launch for 68.998M+ records)
-ONESWEEP_TRAFFIC_RATIO = 0.961
+# dram__bytes_read.sum + dram__bytes_write.sum of onesweep_kernel<256,16,true> over its algorithmic 2*16*records bytes, measured with
+# ncu --set full (profiles/r01j_onesweep_full_raw_2Mreads.csv: 1.088 GB read + 1.044 GB written per launch of 16358 tiles x 4096
+# records = 2.144 GB algorithmic)
+ONESWEEP_TRAFFIC_RATIO = 0.995
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) correct_wide_kernel(
 static constexpr int CF_WARPS = 8;
 static constexpr int CF_CACHE = 32;
 using ::SeqMeta; using ::META_EXC; using ::META_EXT; using ::META_LEN;
-struct LineCache { u64 tOff[CF_CACHE]; u32 dL[CF_CACHE]; i32 qs[CF_CACHE]; i32 aln[CF_CACHE]; i32 ds[CF_CACHE]; u32 rev[CF_CACHE]; };
+struct LineCache { u64 tOff[CF_CACHE]; u32 wOff[CF_CACHE]; u32 dL[CF_CACHE]; i32 qs[CF_CACHE]; i32 aln[CF_CACHE]; i32 ds[CF_CACHE]; u32 rev[CF_CACHE]; };   // rev: bit 0 reverse strand, bit 1 target is plain ACGT (packed words usable)
 static constexpr u32 CF_COMPACT_LEN = 96;   // queries up to this length evaluate only the columns where some counted target disagrees
 struct CorrSmem { DamageTables T; u32 cnt[CF_WARPS][44][32]; LineCache lc[CF_WARPS]; u8 lut[256]; u8 colList[CF_WARPS][CF_COMPACT_LEN]; int domOK; };   // lut: bits 0-1 forward base index, 2-3 reverse-complement base index
 
@@ -398,6 +398,19 @@ CDG_D void count_column(const u8 *__restrict__ data, u64 tOff, u32 dL, bool rev,
     const u32 e = lut[data[tOff + (rev ? dL - 1 - tp : tp)]];
     const int bse = rev ? (int) (e >> 2) : (int) (e & 3u);
     const int idx = bse * 11 + cl;
+    cnt[idx][lane] += rev ? 0x10001u : 1u;
+    mask |= 1ull << idx;
+}
+
+// same from the 2-bit words (plain ACGT targets): the words were just read for the RY distance, so this load hits L1 while the
+// byte of the raw DB would come from DRAM.  Packed codes A0 C1 T2 G3 -> counter index A0 C1 G2 T3 = code ^ (code >> 1);
+// complement = code ^ 2.
+CDG_D void count_column_packed(const u64 *__restrict__ tw, u32 dL, bool rev, u32 tp, u32 (*cnt)[32], int lane, unsigned long long &mask) {
+    const int cl = ((i32) tp >= (i32) dL - 5) ? 6 + (int) (tp - (dL - 5)) : (tp < 5 ? (int) tp : 5);   // correction.cpp:361-371
+    const u32 sp = rev ? dL - 1 - tp : tp;
+    u32 code = (u32) (tw[sp >> 5] >> (62 - 2 * (sp & 31))) & 3u;
+    if (rev) code ^= 2u;
+    const int idx = (int) (code ^ (code >> 1)) * 11 + cl;
     cnt[idx][lane] += rev ? 0x10001u : 1u;
     mask |= 1ull << idx;
 }
@@ -498,12 +511,12 @@ __global__ void __launch_bounds__(CF_WARPS * 32, 4) correct_fast_kernel(
         for (u64 lb = l0; lb < l1; lb += 32) {
             const u64 l = lb + lane;
             u8 sel = 0;
-            u64 tOff = 0; u32 dL = 0; i32 qs = 0, aln = 0, ds = 0;
+            u64 tOff = 0; u32 dL = 0, tWOff = 0, tPlain = 0; i32 qs = 0, aln = 0, ds = 0;
             if (!single && l < l1) { myKeep = keep[l]; if (myKeep) { myT = lineT[l]; mqs = qS_[l]; mqe = qE_[l]; mds = dS_[l]; mde = dE_[l]; } }
             if (l < l1 && myKeep) {
                 const SeqMeta tm = meta[myT];
                 if (!(tm.lenFlags & META_EXT)) {
-                    dL = tm.lenFlags & META_LEN; tOff = tm.off;
+                    dL = tm.lenFlags & META_LEN; tOff = tm.off; tWOff = tm.wordOff; tPlain = (tm.lenFlags & META_EXC) ? 0u : 2u;
                     i32 qe = mqe, de = mde;
                     qs = mqs; ds = mds;
                     aln = max(abs(qe - qs), abs(de - ds)) + 1;
@@ -535,7 +548,7 @@ __global__ void __launch_bounds__(CF_WARPS * 32, 4) correct_fast_kernel(
             const u32 b = __ballot_sync(0xffffffffu, sel != 0);
             if (sel) {
                 const u32 slot = nSel + __popc(b & ((1u << lane) - 1));
-                if (slot < CF_CACHE) { LC.tOff[slot] = tOff; LC.dL[slot] = dL; LC.qs[slot] = qs; LC.aln[slot] = aln; LC.ds[slot] = ds; LC.rev[slot] = sel == 2; }
+                if (slot < CF_CACHE) { LC.tOff[slot] = tOff; LC.dL[slot] = dL; LC.qs[slot] = qs; LC.aln[slot] = aln; LC.ds[slot] = ds; LC.rev[slot] = (sel == 2 ? 1u : 0u) | tPlain; LC.wOff[slot] = tWOff; }
             }
             nSel += __popc(b);
         }
@@ -572,8 +585,11 @@ __global__ void __launch_bounds__(CF_WARPS * 32, 4) correct_fast_kernel(
 #pragma unroll 4
                 for (u32 i = 0; i < nSel; i++) {
                     const i32 qs = LC.qs[i], aln = LC.aln[i];
-                    if (valid && (i32) col >= qs && (i32) col < qs + aln)
-                        count_column(data, LC.tOff[i], LC.dL[i], LC.rev[i] != 0, (u32) LC.ds[i] + (col - (u32) qs), cnt, lane, lut, mask);
+                    if (valid && (i32) col >= qs && (i32) col < qs + aln) {
+                        const u32 rv = LC.rev[i];
+                        if (rv & 2u) count_column_packed(words + LC.wOff[i], LC.dL[i], (rv & 1u) != 0, (u32) LC.ds[i] + (col - (u32) qs), cnt, lane, mask);
+                        else count_column(data, LC.tOff[i], LC.dL[i], (rv & 1u) != 0, (u32) LC.ds[i] + (col - (u32) qs), cnt, lane, lut, mask);
+                    }
                 }
             } else {
                 for (u64 l = l0; l < l1; l++) {

@@ -111,3 +111,34 @@ CDG_HD u32 cdg_val_pos(u64 v) { return (u32) v & ((1u << CDG_OWNER_SHIFT) - 1); 
 // per-sequence metadata in one 16-byte load: byte offset in the DB data, first packed word, length and flags
 struct SeqMeta { u64 off; u32 wordOff; u32 lenFlags; };   // lenFlags: len | exception << 30 | ext << 31
 static constexpr u32 META_EXC = 1u << 30, META_EXT = 1u << 31, META_LEN = (1u << 30) - 1;
+
+// ---- TMA (bulk async copy engine): contiguous global -> shared tile loads ------------------------------------------
+// One thread arms an mbarrier with the byte count and issues cp.async.bulk; the copy engine moves the tile while no LSU
+// instruction is spent on it, every thread then waits on the barrier phase.  Source, destination and size must be
+// multiples of 16 bytes (callers fall back to a plain loop otherwise).
+CDG_D u32 cdg_smem_u32(const void *p) { return (u32) __cvta_generic_to_shared(p); }
+CDG_D void cdg_mbar_init(u64 *bar, u32 arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(cdg_smem_u32(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+CDG_D void cdg_mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(cdg_smem_u32(bar)), "r"(bytes) : "memory");
+}
+CDG_D void cdg_tma_load_1d(void *dstSmem, const void *srcGlobal, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(cdg_smem_u32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(cdg_smem_u32(bar)) : "memory");
+}
+CDG_D void cdg_mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "CDG_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra CDG_MBAR_DONE;\n"
+        "bra CDG_MBAR_WAIT;\n"
+        "CDG_MBAR_DONE:\n"
+        "}\n" :: "r"(cdg_smem_u32(bar)), "r"(parity) : "memory");
+}
+CDG_D bool cdg_tma_ok(const void *src, u32 bytes) { return (((unsigned long long) src) & 15ull) == 0 && (bytes & 15u) == 0 && bytes > 0; }
+

@@ -573,8 +573,9 @@ static constexpr int GROUP_TILE = GROUP_BLOCK * GROUP_ITEMS;
 __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, u64 n,
                                                             const u32 *__restrict__ len, GroupParams G, u64 *__restrict__ out,
                                                             unsigned long long *__restrict__ outCount) {
-    __shared__ u64 sKey[GROUP_TILE + 1];   // +1: the record after the tile (singleton test)
-    __shared__ u64 sVal[GROUP_TILE];
+    __shared__ __align__(16) u64 sKey[GROUP_TILE + 2];   // +1: the record after the tile (singleton test)
+    __shared__ __align__(16) u64 sVal[GROUP_TILE];
+    __shared__ __align__(8) u64 sBar;                    // mbarrier of the TMA tile load
     __shared__ u32 shWarp[GROUP_BLOCK / 32 + 1];
     __shared__ u32 sWarpMax[GROUP_BLOCK / 32];
     __shared__ unsigned long long sBase;
@@ -582,8 +583,20 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u64 tileBase = (u64) blockIdx.x * GROUP_TILE;
     const u32 tileN = (u32) (n - tileBase < (u64) GROUP_TILE ? n - tileBase : (u64) GROUP_TILE);
-    for (u32 i = tid; i < tileN; i += GROUP_BLOCK) { sKey[i] = keys[tileBase + i]; sVal[i] = vals[tileBase + i]; }
-    if (tid == 0) {
+    // tile load: keys and values of the tile are two contiguous 16 KB runs -> two TMA bulk copies into shared memory
+    const bool tma = cdg_tma_ok(keys + tileBase, tileN * 8) && cdg_tma_ok(vals + tileBase, tileN * 8);
+    if (tma) {
+        if (tid == 0) cdg_mbar_init(&sBar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            cdg_mbar_expect_tx(&sBar, 2 * tileN * 8);
+            cdg_tma_load_1d(sKey, keys + tileBase, tileN * 8, &sBar);
+            cdg_tma_load_1d(sVal, vals + tileBase, tileN * 8, &sBar);
+        }
+    } else {
+        for (u32 i = tid; i < tileN; i += GROUP_BLOCK) { sKey[i] = keys[tileBase + i]; sVal[i] = vals[tileBase + i]; }
+    }
+    if (tid == 32) {   // (not the thread that drives the TMA copy: the walk below is a chain of dependent loads)
         sKey[tileN] = tileBase + tileN < n ? keys[tileBase + tileN] : CDG_SENTINEL;
         // run open at the tile start: walk back to its head (one thread per tile, runs are short)
         u64 h = tileBase;
@@ -593,6 +606,7 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
         }
         sTileHead = h;
     }
+    if (tma) cdg_mbar_wait(&sBar, 0);
     __syncthreads();
     // head flags and run-head index by max-scan (blocked arrangement: thread t owns records [t*ITEMS, (t+1)*ITEMS))
     const u32 first = tid * GROUP_ITEMS;
@@ -758,7 +772,9 @@ struct OpMax { CDG_D u64 operator()(u64 a, u64 b) const { return a > b ? a : b; 
 __global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(PairEndFlag f, ReduceParams R, const unsigned long long *__restrict__ tileSums,
                                                            u32 *__restrict__ hitRep, u32 *__restrict__ hitTgt,
                                                            i32 *__restrict__ hitScore, i32 *__restrict__ hitDiag) {
-    __shared__ u64 sKey[RED_TILE + 2];   // [0] = record before the tile, [tileN+1] = record after it
+    __shared__ __align__(16) u64 sKeyRaw[RED_TILE + 4];
+    u64 *sKey = sKeyRaw + 1;             // [0] = record before the tile, [1..tileN] = the tile (16-byte aligned), [tileN+1] = record after it
+    __shared__ __align__(8) u64 sBar;
     __shared__ u64 shVal[RED_BLOCK / 32];
     __shared__ u32 shFlag[RED_BLOCK / 32];
     __shared__ u32 shWarp[RED_BLOCK / 32 + 1];
@@ -767,8 +783,16 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(PairEndFlag f, Reduce
     const u64 base = (u64) blockIdx.x * RED_TILE;
     const u32 tileN = (u32) (f.n - base < (u64) RED_TILE ? f.n - base : (u64) RED_TILE);
     const u64 NONE = ~0ull;   // pair field of "no record": real pairs have at most 2*idBits < 64 bits
-    for (u32 i = tid; i < tileN; i += RED_BLOCK) sKey[i + 1] = f.keys[base + i];
+    const bool tma = cdg_tma_ok(f.keys + base, tileN * 8);
+    if (tma) {   // the tile is one contiguous run: one TMA bulk copy
+        if (tid == 0) cdg_mbar_init(&sBar, 1);
+        __syncthreads();
+        if (tid == 0) { cdg_mbar_expect_tx(&sBar, tileN * 8); cdg_tma_load_1d(sKey + 1, f.keys + base, tileN * 8, &sBar); }
+    } else {
+        for (u32 i = tid; i < tileN; i += RED_BLOCK) sKey[i + 1] = f.keys[base + i];
+    }
     if (tid == 0) { sKey[0] = base > 0 ? f.keys[base - 1] : NONE; sKey[tileN + 1] = base + tileN < f.n ? f.keys[base + tileN] : NONE; }
+    if (tma) cdg_mbar_wait(&sBar, 0);
     __syncthreads();
     const int pairShift = R.diagBits + 1;
     const u64 idMask = (1ull << R.idBits) - 1, diagMask = (1ull << R.diagBits) - 1;
