@@ -573,9 +573,8 @@ static constexpr int GROUP_TILE = GROUP_BLOCK * GROUP_ITEMS;
 __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, u64 n,
                                                             const u32 *__restrict__ len, GroupParams G, u64 *__restrict__ out,
                                                             unsigned long long *__restrict__ outCount) {
-    __shared__ __align__(16) u64 sKey[GROUP_TILE + 2];   // +1: the record after the tile (singleton test)
-    __shared__ __align__(16) u64 sVal[GROUP_TILE];
-    __shared__ __align__(8) u64 sBar;                    // mbarrier of the TMA tile load
+    __shared__ u64 sKey[GROUP_TILE + 1];   // +1: the record after the tile (singleton test)
+    __shared__ u64 sVal[GROUP_TILE];
     __shared__ u32 shWarp[GROUP_BLOCK / 32 + 1];
     __shared__ u32 sWarpMax[GROUP_BLOCK / 32];
     __shared__ unsigned long long sBase;
@@ -583,20 +582,8 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u64 tileBase = (u64) blockIdx.x * GROUP_TILE;
     const u32 tileN = (u32) (n - tileBase < (u64) GROUP_TILE ? n - tileBase : (u64) GROUP_TILE);
-    // tile load: keys and values of the tile are two contiguous 16 KB runs -> two TMA bulk copies into shared memory
-    const bool tma = cdg_tma_ok(keys + tileBase, tileN * 8) && cdg_tma_ok(vals + tileBase, tileN * 8);
-    if (tma) {
-        if (tid == 0) cdg_mbar_init(&sBar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            cdg_mbar_expect_tx(&sBar, 2 * tileN * 8);
-            cdg_tma_load_1d(sKey, keys + tileBase, tileN * 8, &sBar);
-            cdg_tma_load_1d(sVal, vals + tileBase, tileN * 8, &sBar);
-        }
-    } else {
-        for (u32 i = tid; i < tileN; i += GROUP_BLOCK) { sKey[i] = keys[tileBase + i]; sVal[i] = vals[tileBase + i]; }
-    }
-    if (tid == 32) {   // (not the thread that drives the TMA copy: the walk below is a chain of dependent loads)
+    for (u32 i = tid; i < tileN; i += GROUP_BLOCK) { sKey[i] = keys[tileBase + i]; sVal[i] = vals[tileBase + i]; }
+    if (tid == 0) {
         sKey[tileN] = tileBase + tileN < n ? keys[tileBase + tileN] : CDG_SENTINEL;
         // run open at the tile start: walk back to its head (one thread per tile, runs are short)
         u64 h = tileBase;
@@ -606,7 +593,6 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
         }
         sTileHead = h;
     }
-    if (tma) cdg_mbar_wait(&sBar, 0);
     __syncthreads();
     // head flags and run-head index by max-scan (blocked arrangement: thread t owns records [t*ITEMS, (t+1)*ITEMS))
     const u32 first = tid * GROUP_ITEMS;

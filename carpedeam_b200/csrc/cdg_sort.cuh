@@ -119,7 +119,7 @@ CDG_D u32 digit_peers(u32 d) {
 // NVLink (CUDA IPC) — instead of one local output array: the partition and the transfer are one kernel, the tile's run
 // of each digit is written as one coalesced burst into peer memory.  binBase must be all zero (offsets are per segment).
 template <int BLOCK_T, int ITEMS_T, bool HAS_VAL, bool ROUTE = false>
-__global__ void __launch_bounds__(BLOCK_T) onesweep_kernel(const u64 *__restrict__ keysIn, u64 *__restrict__ keysOut,
+__global__ void __launch_bounds__(BLOCK_T, (BLOCK_T == 256 && ITEMS_T == 16) ? 4 : 1) onesweep_kernel(const u64 *__restrict__ keysIn, u64 *__restrict__ keysOut,
                                                            const u64 *__restrict__ valsIn, u64 *__restrict__ valsOut, u64 n,
                                                            Pass pass, const unsigned long long *__restrict__ binBase,
                                                            u32 *tileState /*[tiles][RADIX]*/, u32 *ticket,
