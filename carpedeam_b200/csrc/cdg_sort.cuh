@@ -17,6 +17,13 @@ static constexpr int BLOCK = 256;                 // histogram kernel block
 static constexpr int MAX_PASSES = 16;
 static constexpr u32 FLAG_AGG = 1u << 30, FLAG_INC = 2u << 30, FLAG_MASK = 3u << 30, VAL_MASK = ~FLAG_MASK;
 static constexpr u64 MAX_N = (1ull << 30) - 1;    // 30-bit tile-state counters
+// resident blocks per SM the 256x16 digit pass is compiled for (64 registers, no spills, at 4; measured on B200)
+#ifndef CDG_SWEEP_MB_PAIRS
+#define CDG_SWEEP_MB_PAIRS 4
+#endif
+#ifndef CDG_SWEEP_MB_KEYS
+#define CDG_SWEEP_MB_KEYS 4
+#endif
 static constexpr int ROUTE_MAX = 16;              // digits of a routing pass (= ranks)
 
 struct Pass { int word; int shift; u32 mask; };   // word: 0 = key, 1 = val
@@ -119,7 +126,7 @@ CDG_D u32 digit_peers(u32 d) {
 // NVLink (CUDA IPC) — instead of one local output array: the partition and the transfer are one kernel, the tile's run
 // of each digit is written as one coalesced burst into peer memory.  binBase must be all zero (offsets are per segment).
 template <int BLOCK_T, int ITEMS_T, bool HAS_VAL, bool ROUTE = false>
-__global__ void __launch_bounds__(BLOCK_T, (BLOCK_T == 256 && ITEMS_T == 16) ? 4 : 1) onesweep_kernel(const u64 *__restrict__ keysIn, u64 *__restrict__ keysOut,
+__global__ void __launch_bounds__(BLOCK_T, (BLOCK_T == 256 && ITEMS_T == 16) ? (HAS_VAL ? CDG_SWEEP_MB_PAIRS : CDG_SWEEP_MB_KEYS) : 1) onesweep_kernel(const u64 *__restrict__ keysIn, u64 *__restrict__ keysOut,
                                                            const u64 *__restrict__ valsIn, u64 *__restrict__ valsOut, u64 n,
                                                            Pass pass, const unsigned long long *__restrict__ binBase,
                                                            u32 *tileState /*[tiles][RADIX]*/, u32 *ticket,

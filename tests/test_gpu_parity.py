@@ -375,3 +375,67 @@ def test_correction_with_unusual_damage_profiles(ctx, oracle, tmp_path, ct0, ga0
         assert changed > 0
     lik = ctx.correct_likelihoods(s.total)     # the likelihood export evaluates every covered column
     assert np.isfinite(lik).any()
+
+
+def _metagenome_reads(n, n_genomes, seed, rates5, rates3, interior, mu=44.0, sigma=0.2, lmin=30, lmax=150):
+    """BASELINE configs[2]/[3] shape at test size: log-normal read lengths clipped to [30,150], several genomes at
+    log-normal relative abundance (mixed coverage), terminal C->T / G->A damage with the given rates."""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    comp = np.zeros(256, np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    sizes = np.exp(rng.uniform(np.log(4000), np.log(40000), n_genomes)).astype(int)
+    genomes = [acgt[rng.integers(0, 4, s)] for s in sizes]
+    ab = rng.lognormal(0, 1, n_genomes) * sizes
+    which = rng.choice(n_genomes, n, p=ab / ab.sum())
+    lens = np.clip(np.round(rng.lognormal(np.log(mu), sigma, n)), lmin, lmax).astype(int)
+    seqs = []
+    for i in range(n):
+        g = genomes[which[i]]; L = int(lens[i])
+        st = int(rng.integers(0, len(g) - L))
+        r = g[st:st + L].copy()
+        if rng.random() < 0.5:
+            r = comp[r[::-1]]
+        u = rng.random(L)
+        p_ct = np.full(L, interior); p_ct[:5] = rates5
+        p_ga = np.full(L, interior); p_ga[L - 5:] = rates3[::-1]
+        ct = (r == ord("C")) & (u < p_ct); ga = (r == ord("G")) & (u < p_ga)
+        r[ct] = ord("T"); r[ga] = ord("A")
+        e = rng.random(L) < 0.001
+        if e.any():
+            r[e] = acgt[rng.integers(0, 4, int(e.sum()))]
+        seqs.append(r.tobytes())
+    return seqs
+
+
+@pytest.mark.parametrize("name,rates,interior", [
+    ("config 3 (dhigh damage)", (.329405, .221745, .187678, .161196, .144011), 0.01),
+    ("config 4 (low damage)", (.05, .03, .02, .015, .01), 0.002)])
+def test_metagenome_shaped_reads_vs_oracle(ctx, oracle, tmp_path, name, rates, interior):
+    """BASELINE configs[2] and [3] at test size: reads of 30-150 bp (the 4- and 8-windows-per-lane extraction kernels, queries
+    longer than the compact-column limit of the correction), mixed coverage from 1x to >100x, dhigh and low-damage profiles."""
+    import carpedeam_b200 as cd
+    hdr = "A>C\tA>G\tA>T\tC>A\tC>G\tC>T\tG>A\tG>C\tG>T\tT>A\tT>C\tT>G\n"
+    rows5 = [[0.0] * 12 for _ in range(5)]; rows3 = [[0.0] * 12 for _ in range(5)]
+    for i in range(5):
+        rows5[i][5] = rates[i]; rows3[4 - i][6] = rates[i]
+    pfx = str(tmp_path / "prof")
+    for fn, rows in (("5p.prof", rows5), ("3p.prof", rows3)):
+        with open(pfx + fn, "w") as f:
+            f.write(hdr + "".join("\t".join("%g" % v for v in r) + "\n" for r in rows))
+    # sigma 0.5 instead of the config's 0.2: at 12 k reads the 0.2 tail stops at ~90 bp, the wider one reaches the 150 bp clip
+    s = SeqSet(_metagenome_reads(12000, 12, 31, np.array(rates), np.array(rates), interior, sigma=0.5))
+    assert s.len.max() >= 140 and s.len.min() <= 32 and (s.len > 96).sum() > 100
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_damage(cd.load_damage(pfx))
+    oracle.load_damage(pfx)
+    hits, alns, out, changed = ctx.iteration(fetch_hits=True)
+    ohits, r, line_off, oout = _oracle_iteration(oracle, s)
+    _hits_equal(hits, ohits)
+    for f in ("keep", "score", "bits", "qs", "qe", "ds", "de"):
+        assert np.array_equal(alns[f], r[f]), f
+    assert np.array_equal(out, oout)
+    assert changed == int((out != s.blob).sum()) and changed > 0
+    cover = np.bincount(hits["rep"], minlength=s.n)
+    assert cover.max() > 50 and (cover == 0).sum() > 0      # deep and shallow genomes in one set
