@@ -274,6 +274,12 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) correct_wide_kernel(
                     if (qs > qe) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; rev = true; }
                     const u8 *ts = data + off[t];
                     u32 dist = 0;
+                    // A target counts only with aln >= 30 (:359), so shorter alignments need no RY distance; that also covers the
+                    // records of score-0 alignments (all-N self hits: start = end = -1, DistanceCalculator.h:204-220), where the
+                    // reference reads the byte in front of the sequence.  Coordinates outside the sequences (possible only in
+                    // caller-provided alignments; undefined behaviour in the reference) never reach a load here.
+                    const bool usable = aln >= 30 && qs >= 0 && ds >= 0 && (u32) (qs + aln) <= qLen && (u32) (ds + aln) <= dL;
+                    if (usable)
                     for (i32 p = lane; p < aln; p += 32) dist += (ry_map(q[qs + p]) != ry_map(t_char(ts, dL, rev, (u32) (ds + p)))) ? 1u : 0u;
 #pragma unroll
                     for (int s = 16; s > 0; s >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, s);
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) correct_wide_kernel(
                     const bool pick = (ry >= thr && ds == 0 && (u32) qe == qLen - 1) || (ry >= thr && qs == 0 && de == (i32) dL - 1) ||
                                       (ry >= thr && avCov < 50);
                     const float sid = P.roundSeqId ? seqid_text_roundtrip(seqId[l]) : seqId[l];
-                    if (pick && ry >= thr && sid >= P.seqIdThr && aln >= 30) sel = rev ? 2 : 1;
+                    if (usable && pick && ry >= thr && sid >= P.seqIdThr) sel = rev ? 2 : 1;
                 }
             }
             if (lane == 0) lineSel[l] = sel;
@@ -525,7 +531,10 @@ __global__ void __launch_bounds__(CF_WARPS * 32, 4) correct_fast_kernel(
                     u32 dist = 0;
                     u64 lm0 = 0, lm1 = 0, lm2 = 0;
                     const bool packed = !qExc && !(tm.lenFlags & META_EXC);
-                    if (packed) dist = ry_dist_mismatch(qw, (u32) qs, words + tm.wordOff, dL, rev, (u32) ds, (u32) aln, lm0, lm1, lm2);
+                    // (see correct_wide_kernel: alignments shorter than 30 never count, out-of-sequence coordinates never load)
+                    const bool usable = aln >= 30 && qs >= 0 && ds >= 0 && (u32) (qs + aln) <= qLen && (u32) (ds + aln) <= dL;
+                    if (!usable) {}
+                    else if (packed) dist = ry_dist_mismatch(qw, (u32) qs, words + tm.wordOff, dL, rev, (u32) ds, (u32) aln, lm0, lm1, lm2);
                     else {
                         const u8 *ts = data + tOff;
                         for (i32 p = 0; p < aln; p++) dist += (ry_map(q[qs + p]) != ry_map(t_char(ts, dL, rev, (u32) (ds + p)))) ? 1u : 0u;
@@ -536,7 +545,7 @@ __global__ void __launch_bounds__(CF_WARPS * 32, 4) correct_fast_kernel(
                     const bool pick = (ry >= thr && ds == 0 && (u32) qe == qLen - 1) || (ry >= thr && qs == 0 && de == (i32) dL - 1) ||
                                       (ry >= thr && avCov < 50);
                     const float sid = P.roundSeqId ? seqid_text_roundtrip(seqId[l]) : seqId[l];
-                    if (pick && ry >= thr && sid >= P.seqIdThr && aln >= 30) {
+                    if (usable && pick && ry >= thr && sid >= P.seqIdThr) {
                         sel = rev ? 2 : 1;
                         if (packed) { mm0 |= lm0; mm1 |= lm1; mm2 |= lm2; } else sel |= 4;   // 4: a counted target needs the byte path
                     }

@@ -110,7 +110,15 @@ int fail(cdg_ctx *c, int code, const char *fmt, ...) {
         cudaError_t e_ = (call);                                                                             \
         if (e_ != cudaSuccess) return fail(ctx, CDG_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
     } while (0)
-#define CKL() CK(cudaGetLastError())
+// launch check; with CDG_SYNC_DEBUG=1 in the environment every check also waits for the stream, so that an asynchronous kernel
+// fault is reported at the launch site that caused it (compute-sanitizer is not always available)
+static cudaError_t cdg_launch_check(cdg_ctx *ctx) {
+    static const bool dbg = getenv("CDG_SYNC_DEBUG") != nullptr;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && dbg && ctx) e = cudaStreamSynchronize(ctx->st);
+    return e;
+}
+#define CKL() CK(cdg_launch_check(ctx))
 
 // scalars block on the device: [0] scan total, [1] emitted records, [2] grouped count, [3] kept lines,
 // [4] changed bases, [5] (u32) extraCount, [6] (u32) overflow, [7] (u32) long count, [8] long scratch total, [9] (u32) sort ticket
@@ -792,12 +800,14 @@ static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data
     CK(cudaMemsetAsync(sc + SC_QLIST, 0, 8, ctx->st));
     if (n) cdgalign::multi_line_queries_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dLineOff.as<u64>(), n, ctx->dQList.as<u32>(), (u32 *) (sc + SC_QLIST));
     ctx->launches++;
+    CKL();
     const int blocks = ctx->smCount * 4;
     cdgalign::correct_fast_kernel<<<blocks, cdgalign::CF_WARPS * 32, sizeof(cdgalign::CorrSmem), ctx->st>>>(
         ctx->dQList.as<u32>(), (const u32 *) (sc + SC_QLIST), ctx->dData.as<u8>(), ctx->dMeta.as<cdgalign::SeqMeta>(), ctx->dWords.as<u64>(), qLo, n, ctx->dLineOff.as<u64>(), ctx->dLineT.as<u32>(), ctx->dKeep.as<u8>(), ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(),
         ctx->dQE.as<i32>(), ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), C, ctx->dTables.as<cdgalign::DamageTables>(), ctx->dLineSel.as<u8>(),
         ctx->dOut.as<u8>(), sc + SC_CHANGED, ctx->dLikOff.as<u64>(), dLik, ctx->dWideList.as<u32>(), (u32 *) (sc + SC_WIDE));
     ctx->launches++;
+    CKL();
     // queries with more than 65535 counted targets (16-bit counters): generic kernel, usually an empty list
     cdgalign::correct_wide_kernel<<<ctx->smCount, cdgalign::CORR_WARPS * 32, 0, ctx->st>>>(
         ctx->dWideList.as<u32>(), (const u32 *) (sc + SC_WIDE),

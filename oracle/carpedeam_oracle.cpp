@@ -504,7 +504,10 @@ extern "C" void orc_correct(const char *blob, const u64 *off, const u32 *len, co
                 ts = trev.data();
             }
             unsigned dist = 0;
-            for (int p = 0; p < x.aln; p++) if (ry_map(q[x.qS + p]) != ry_map(ts[x.dS + p])) dist++;   // getRYSeqId :78-92
+            // getRYSeqId :78-92.  Its result only matters for aln >= 30 (:359); score-0 alignments (start = end = -1) make the
+            // reference read the byte in front of the sequence here, which the restatement does not imitate.
+            if (x.aln >= 30)
+            for (int p = 0; p < x.aln; p++) if (ry_map(q[x.qS + p]) != ry_map(ts[x.dS + p])) dist++;
             float ry = (float) ((unsigned) x.aln - dist) / (float) x.aln;
             float thr = ryThr;
             if (x.aln <= 100) { thr = ((float) x.aln - 1) / (float) x.aln; thr = std::floor(thr * 1000) / 1000; }

@@ -439,3 +439,72 @@ def test_metagenome_shaped_reads_vs_oracle(ctx, oracle, tmp_path, name, rates, i
     assert changed == int((out != s.blob).sum()) and changed > 0
     cover = np.bincount(hits["rep"], minlength=s.n)
     assert cover.max() > 50 and (cover == 0).sum() > 0      # deep and shallow genomes in one set
+
+
+def _run_both(ctx, oracle, seqs, k=20):
+    import carpedeam_b200 as cd
+    s = SeqSet(seqs)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+    oracle.load_damage(os.path.join(GOLD, "dhigh"))
+    hits, alns, out, changed = ctx.iteration(kmer=cd.kmer_params(k=k), fetch_hits=True)
+    ohits, r, line_off, oout = _oracle_iteration(oracle, s, k=k)
+    _hits_equal(hits, ohits)
+    assert np.array_equal(alns["line_off"], line_off)
+    for f in ("keep", "score", "bits", "qs", "qe", "ds", "de"):
+        assert np.array_equal(alns[f], r[f]), f
+    assert np.array_equal(out, oout)
+    return s, hits, alns, out, changed
+
+
+def test_degenerate_sets(ctx, oracle):
+    """edge cases: one sequence; every sequence shorter than k (no k-mer records at all, only identity records); reads that are
+    all N; exact duplicates and reverse-complement duplicates only (identity-record groups, kmermatcher.cpp:244-262)."""
+    rng = np.random.default_rng(3)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    one = acgt[rng.integers(0, 4, 61)].tobytes()
+    s, hits, alns, out, changed = _run_both(ctx, oracle, [one])
+    assert len(hits["rep"]) == 0 and changed == 0 and alns["keep"].tolist() == [1]
+    short = [acgt[rng.integers(0, 4, int(L))].tobytes() for L in rng.integers(1, 20, 300)]
+    s, hits, alns, out, changed = _run_both(ctx, oracle, short)
+    assert hits["R1"] == 300 and changed == 0                      # identity records only
+    s, hits, alns, out, changed = _run_both(ctx, oracle, [b"N" * 40, b"N" * 40, one, b"NNNNNNNNNNNNNNNNNNNNNNNNA"])
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    dup = [one] * 7 + [one.translate(comp)[::-1]] * 5 + [one[:40]] * 3
+    s, hits, alns, out, changed = _run_both(ctx, oracle, dup)
+    assert len(hits["rep"]) > 0
+
+
+def test_deep_pileup_uses_wide_counters(ctx, oracle):
+    """70 000 copies of one locus with damage: the representative's columns see more than 65 535 counted targets, so the
+    16-bit counters of the fast correction kernel hand the query to the generic kernel (no test knob involved)."""
+    rng = np.random.default_rng(8)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    locus = acgt[rng.integers(0, 4, 64)]
+    seqs = []
+    for i in range(70000):
+        r = locus.copy()
+        u = rng.random(64)
+        r[(r == ord("C")) & (u < 0.02)] = ord("T")
+        if i % 9 == 0:
+            r = r[: 50 + i % 14]
+        seqs.append(r.tobytes())
+    s, hits, alns, out, changed = _run_both(ctx, oracle, seqs)
+    lo = alns["line_off"].astype(np.int64)
+    assert (np.diff(lo)).max() > 65536
+
+
+def test_empty_set_is_an_error_or_empty_result():
+    """an empty sequence DB must not crash or hang: either a clean CdgError (with a message) or empty outputs"""
+    import carpedeam_b200 as cd
+    c = cd.Context(0)
+    try:
+        c.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+        try:
+            c.upload(np.zeros(0, np.uint8), np.zeros(0, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint8))
+            hits, alns, out, changed = c.iteration(fetch_hits=True)
+            assert len(hits["rep"]) == 0 and changed == 0 and len(alns["tgt"]) == 0
+        except cd.CdgError as e:
+            assert len(str(e)) > 10
+    finally:
+        c.close()
