@@ -269,7 +269,8 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) correct_wide_kernel(
                 if (!ext[t]) {
                     const u32 dL = len[t];
                     i32 qs = qS_[l], qe = qE_[l], ds = dS_[l], de = dE_[l];
-                    const i32 aln = max(abs(qe - qs), abs(de - ds)) + 1;
+                    const bool sane = (((u32) qs | (u32) qe | (u32) ds | (u32) de) >> 30) == 0;   // no negative / overflowing coordinate
+                    const i32 aln = sane ? max(abs(qe - qs), abs(de - ds)) + 1 : 0;
                     bool rev = false;
                     if (qs > qe) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; rev = true; }
                     const u8 *ts = data + off[t];
@@ -525,7 +526,8 @@ __global__ void __launch_bounds__(CF_WARPS * 32, 4) correct_fast_kernel(
                     dL = tm.lenFlags & META_LEN; tOff = tm.off; tWOff = tm.wordOff; tPlain = (tm.lenFlags & META_EXC) ? 0u : 2u;
                     i32 qe = mqe, de = mde;
                     qs = mqs; ds = mds;
-                    aln = max(abs(qe - qs), abs(de - ds)) + 1;
+                    const bool sane = (((u32) qs | (u32) qe | (u32) ds | (u32) de) >> 30) == 0;   // no negative / overflowing coordinate
+                    aln = sane ? max(abs(qe - qs), abs(de - ds)) + 1 : 0;
                     bool rev = false;
                     if (qs > qe) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; rev = true; }
                     u32 dist = 0;

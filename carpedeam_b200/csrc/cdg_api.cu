@@ -644,12 +644,26 @@ static int build_lines_from_hits(cdg_ctx *ctx) {
     return 0;
 }
 
+// caller-provided CSR lists (parsed from a pref / aln DB): offsets must be monotone and end at n_lines, targets must be
+// indices of the resident set — the kernels index with them
+static int validate_csr(cdg_ctx *ctx, const char *what, const uint64_t *off, uint64_t nq, const uint32_t *target, uint64_t n_lines) {
+    if (off[0] != 0 || off[nq] != n_lines) return fail(ctx, CDG_ERR_ARG, "%s: offsets must start at 0 and end at the number of lines", what);
+    for (uint64_t q = 0; q < nq; q++)
+        if (off[q + 1] < off[q]) return fail(ctx, CDG_ERR_ARG, "%s: offsets decrease at query %llu", what, (unsigned long long) q);
+    if (n_lines && !target) return fail(ctx, CDG_ERR_ARG, "%s: no target array", what);
+    for (uint64_t l = 0; l < n_lines; l++)
+        if (target[l] >= ctx->n) return fail(ctx, CDG_ERR_ARG, "%s: line %llu: target index %u outside the resident set (%llu sequences)", what,
+                                             (unsigned long long) l, target[l], (unsigned long long) ctx->n);
+    return 0;
+}
+
 extern "C" int cdg_set_pref_lines(cdg_ctx *ctx, const uint64_t *line_off, uint64_t n_queries, const uint32_t *target, const int32_t *pref_score,
                                   const uint16_t *diag, uint64_t n_lines) {
     if (!ctx || !line_off) return CDG_ERR_ARG;
     if (n_queries != ctx->n) return fail(ctx, CDG_ERR_ARG, "cdg_set_pref_lines: %llu queries, resident set has %llu", (unsigned long long) n_queries,
                                          (unsigned long long) ctx->n);
     CK(cudaSetDevice(ctx->device));
+    if (int v = validate_csr(ctx, "cdg_set_pref_lines", line_off, n_queries, target, n_lines)) return v;
     int rc = reserve_lines(ctx, n_lines);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->dLineOff.p, line_off, (n_queries + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
@@ -755,6 +769,7 @@ extern "C" int cdg_set_alignments(cdg_ctx *ctx, const uint64_t *aln_off, uint64_
     if (n_queries != ctx->n) return fail(ctx, CDG_ERR_ARG, "cdg_set_alignments: %llu queries, resident set has %llu", (unsigned long long) n_queries,
                                          (unsigned long long) ctx->n);
     CK(cudaSetDevice(ctx->device));
+    if (int v = validate_csr(ctx, "cdg_set_alignments", aln_off, n_queries, target, n_alns)) return v;
     int rc = reserve_lines(ctx, n_alns);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->dLineOff.p, aln_off, (n_queries + 1) * 8, cudaMemcpyHostToDevice, ctx->st));

@@ -508,3 +508,31 @@ def test_empty_set_is_an_error_or_empty_result():
             assert len(str(e)) > 10
     finally:
         c.close()
+
+
+def test_caller_provided_lists_are_validated(ctx):
+    """stand-alone rescorediagonal / ancient_correction take lists parsed from text DBs: indices outside the resident set, broken
+    offsets and alignments whose coordinates lie outside the sequences must be rejected or ignored, never dereferenced"""
+    import carpedeam_b200 as cd
+    s = SeqSet(synth_reads(50, 2000, 4))
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+    off = np.arange(s.n + 1, dtype=np.uint64)
+    tgt = np.arange(s.n, dtype=np.uint32)
+    bad = tgt.copy(); bad[7] = 1 << 30
+    with pytest.raises(cd.CdgError):
+        ctx.set_pref_lines(off, bad, np.zeros(s.n, np.int32), np.zeros(s.n, np.uint16))
+    boff = off.copy(); boff[5] = 99
+    with pytest.raises(cd.CdgError):
+        ctx.set_pref_lines(boff, tgt, np.zeros(s.n, np.int32), np.zeros(s.n, np.uint16))
+    with pytest.raises(cd.CdgError):
+        ctx.set_alignments(off, bad, np.ones(s.n, np.float32), np.zeros(s.n, np.int32), s.len.astype(np.int32) - 1, np.zeros(s.n, np.int32),
+                           s.len.astype(np.int32) - 1)
+    # coordinates far outside the sequences: accepted as records, but never counted and never loaded
+    two = np.repeat(np.arange(s.n + 1, dtype=np.uint64) * 2, 1)
+    t2 = np.repeat(tgt, 2); t2[1::2] = (t2[1::2] + 1) % s.n
+    qs = np.zeros(2 * s.n, np.int32); qe = np.repeat(s.len.astype(np.int32) - 1, 2); ds = qs.copy(); de = qe.copy()
+    qs[1::2] = -5000; qe[1::2] = 100000; ds[1::2] = -7; de[1::2] = 2_000_000_000
+    ctx.set_alignments(two, t2, np.ones(2 * s.n, np.float32), qs, qe, ds, de)
+    out, changed = ctx.correct()
+    assert changed == 0 and np.array_equal(out, s.blob)
