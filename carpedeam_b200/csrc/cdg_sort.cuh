@@ -126,7 +126,7 @@ CDG_D u32 digit_peers(u32 d) {
 // NVLink (CUDA IPC) — instead of one local output array: the partition and the transfer are one kernel, the tile's run
 // of each digit is written as one coalesced burst into peer memory.  binBase must be all zero (offsets are per segment).
 template <int BLOCK_T, int ITEMS_T, bool HAS_VAL, bool ROUTE = false>
-__global__ void __launch_bounds__(BLOCK_T, (BLOCK_T == 256 && ITEMS_T == 16) ? (HAS_VAL ? CDG_SWEEP_MB_PAIRS : CDG_SWEEP_MB_KEYS) : 1) onesweep_kernel(const u64 *__restrict__ keysIn, u64 *__restrict__ keysOut,
+__global__ void __launch_bounds__(BLOCK_T, (BLOCK_T == 256 && ITEMS_T == 16) ? (HAS_VAL ? CDG_SWEEP_MB_PAIRS : CDG_SWEEP_MB_KEYS) : (BLOCK_T == 512 && ITEMS_T == 16) ? 2 : 1) onesweep_kernel(const u64 *__restrict__ keysIn, u64 *__restrict__ keysOut,
                                                            const u64 *__restrict__ valsIn, u64 *__restrict__ valsOut, u64 n,
                                                            Pass pass, const unsigned long long *__restrict__ binBase,
                                                            u32 *tileState /*[tiles][RADIX]*/, u32 *ticket,
@@ -496,6 +496,8 @@ inline void launch_variant(int variant, bool hasVal, cudaStream_t st, const u64 
         case 13: launch_persistent<512, 8, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket, smCount); break;
         case 14: launch_persistent<384, 8, false>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket, smCount); break;
         case 15: launch_persistent<384, 8, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket, smCount); break;
+        case 16: launch_pass<512, 16, false>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;   // 8192-record tiles
+        case 17: launch_pass<512, 16, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
         case 0: launch_pass<256, 16, false>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
         case 1: launch_pass<256, 16, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
         case 2: launch_pass<256, 8, false>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
@@ -506,7 +508,7 @@ inline void launch_variant(int variant, bool hasVal, cudaStream_t st, const u64 
         default: launch_pass<512, 4, true>(st, ki, ko, vi, vo, n, p, binBase, tileState, ticket); break;
     }
 }
-inline int &default_variant(bool hasVal) { static int v[2] = {0, 0}; return v[hasVal ? 1 : 0]; }   // 256 threads x 16 keys: best measured on B200
+inline int &default_variant(bool hasVal) { static int v[2] = {8, 0}; return v[hasVal ? 1 : 0]; }   // measured on B200 (profiles/sortbench_tiles.py): keys only 512 x 16 (40.2 % of the HBM peak vs 38.3 %), pairs 256 x 16 (64.7 %)
 
 // Input in (keysA, valsA); result pointer pair returned through outKeys/outVals (A or B, depending on the number
 // of passes).  Returns number of kernels launched, <0 on error.  passMs (optional): per-pass event timing sink.

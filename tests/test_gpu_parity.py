@@ -53,7 +53,7 @@ def test_radix_sort(ctx, n, pairs):
             assert np.array_equal(v2, vals[order])   # stability
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_radix_sort_all_tile_shapes(ctx, variant):
     import carpedeam_b200 as cd
     L = cd.lib()
@@ -71,7 +71,7 @@ def test_radix_sort_all_tile_shapes(ctx, variant):
                 if pairs:
                     assert np.array_equal(v2, vals[order])
     finally:
-        L.cdg_test_set_sort_variant(0, 0)
+        L.cdg_test_set_sort_variant(8, 0)     # the library defaults
 
 
 def _hits_equal(a, b):
