@@ -359,8 +359,8 @@ def main():
     last = {}
 
     def step_e2e():
-        if world == 1:
-            upload()
+        if world == 1:   # asynchronous upload: the iteration packs and extracts piece c while piece c+1 is still on the bus
+            ctx.upload_raw_async(h_blob.data_ptr(), h_blob.numel(), h_off.data_ptr(), h_len.data_ptr(), 0, n)
         else:   # every rank copies 1/world of the host arrays, NVLink all-gather, pack from device memory
             last["h2d"] = sharded.upload_sharded(h_blob, h_off, h_len)
         if world == 1:

@@ -114,6 +114,7 @@ def lib():
         L.cdg_last_error.argtypes = [C.c_void_p]; L.cdg_last_error.restype = C.c_char_p
         L.cdg_stream.argtypes = [C.c_void_p]; L.cdg_stream.restype = C.c_void_p
         L.cdg_upload_seqs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.cdg_upload_seqs_async.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.cdg_kmermatch.argtypes = [C.c_void_p, C.POINTER(KmerParams), C.POINTER(Hits)]
         L.cdg_set_pref_lines.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.cdg_rescore.argtypes = [C.c_void_p, C.POINTER(RescoreParams), C.POINTER(Alns)]
@@ -221,6 +222,13 @@ class Context:
         self.n = n; self.data_bytes = nbytes
         self._ck(lib().cdg_upload_seqs(self._h, C.c_void_p(blob_ptr), nbytes, C.c_void_p(off_ptr), C.c_void_p(len_ptr),
                                        C.c_void_p(ext_ptr) if ext_ptr else None, n), "cdg_upload_seqs")
+
+    def upload_raw_async(self, blob_ptr, nbytes, off_ptr, len_ptr, ext_ptr, n):
+        """cdg_upload_seqs_async: returns once the copies are queued; the (pinned) host buffers must stay valid until the next call
+        on this context has returned (kmermatch / iteration consume the pieces as they arrive)"""
+        self.n = n; self.data_bytes = nbytes
+        self._ck(lib().cdg_upload_seqs_async(self._h, C.c_void_p(blob_ptr), nbytes, C.c_void_p(off_ptr), C.c_void_p(len_ptr),
+                                             C.c_void_p(ext_ptr) if ext_ptr else None, n), "cdg_upload_seqs_async")
 
     @staticmethod
     def _hits(h):

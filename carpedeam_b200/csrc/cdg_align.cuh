@@ -354,9 +354,9 @@ static constexpr u32 CF_COMPACT_LEN = 96;   // queries up to this length evaluat
 struct CorrSmem { DamageTables T; u32 cnt[CF_WARPS][44][32]; LineCache lc[CF_WARPS]; u8 lut[256]; u8 colList[CF_WARPS][CF_COMPACT_LEN]; int domOK; };   // lut: bits 0-1 forward base index, 2-3 reverse-complement base index
 
 __global__ void __launch_bounds__(256) meta_kernel(const u64 *__restrict__ off, const u64 *__restrict__ wordOff, const u32 *__restrict__ len,
-                                                   const u8 *__restrict__ flags, const u8 *__restrict__ ext, u64 n, SeqMeta *__restrict__ meta) {
-    u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                                                   const u8 *__restrict__ flags, const u8 *__restrict__ ext, u64 seqLo, u64 seqHi, SeqMeta *__restrict__ meta) {
+    u64 i = seqLo + (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= seqHi) return;
     SeqMeta m; m.off = off[i]; m.wordOff = (u32) wordOff[i];
     m.lenFlags = (len[i] & META_LEN) | (flags[i] ? META_EXC : 0u) | (ext[i] ? META_EXT : 0u);
     meta[i] = m;

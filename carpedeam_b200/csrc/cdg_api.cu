@@ -50,6 +50,7 @@ enum { EV_START, EV_EXTRACT, EV_SORT1, EV_GROUP, EV_SORT2, EV_REDUCE, EV_RS0, EV
 }   // namespace
 
 static constexpr int CDG_MAX_WORLD = 16;
+static constexpr int CDG_UPLOAD_CHUNKS = 8;   // pieces of an asynchronous upload (copy of piece c+1 overlaps pack + extraction of piece c)
 static constexpr int CDG_IPC_BUFFERS = 5;   // recvK, recvV, recvIdK, recvIdV, recv2
 static constexpr int CDG_IPC_HANDLE_BYTES = 64 + 8;   // cudaIpcMemHandle_t + byte offset of the buffer inside its allocation
 static constexpr u64 CDG_HEAD_RUN = 4096;   // records of the next rank's head run appended before the reduction
@@ -80,6 +81,9 @@ struct cdg_ctx {
     u32 sort1Passes = 0, sort2Passes = 0; u64 sort1Records = 0;
     u64 *sortedMainK = nullptr, *sortedMainV = nullptr, *sortedIdK = nullptr, *sortedIdV = nullptr, *sortedKey2 = nullptr;
     KmPlanFwd plan; u64 qLo = 0, nQ = 0; u64 mgRecv = 0, mgR2 = 0; u64 nIdent = 0;
+    // chunked upload: the DB bytes arrive in chunks on copySt; the chunks that are not packed yet (sequence ranges + events)
+    struct UploadChunk { u64 seqLo, seqHi; cudaEvent_t ev; };
+    std::vector<UploadChunk> pending; cudaEvent_t chunkEv[CDG_UPLOAD_CHUNKS]; cudaEvent_t evUploadStart = nullptr;
     const u64 *ordV = nullptr;   // sequence index by (length desc, id asc) rank (km_prepare)
     u64 *idSrcK = nullptr, *idSrcV = nullptr, *idAltK = nullptr, *idAltV = nullptr;   // identity records to sort (nIdent) and their ping-pong partner
     DevBuf dRecvIdK, dRecvIdV, dRouteTab;
@@ -234,6 +238,8 @@ extern "C" int cdg_create(int device, cdg_ctx **out) {
     cudaEventCreateWithFlags(&ctx->evReady, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->evCopied, cudaEventDisableTiming);
     for (int i = 0; i < EV_N; i++) { cudaEventCreate(&ctx->ev[i]); ctx->evValid[i] = false; }
     for (int i = 0; i < 2 * cdgsort::MAX_PASSES; i++) cudaEventCreate(&ctx->passEv[i]);
+    for (int i = 0; i < CDG_UPLOAD_CHUNKS; i++) cudaEventCreateWithFlags(&ctx->chunkEv[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->evUploadStart, cudaEventDisableTiming);
     if (ctx->dScalars.reserve(SC_N * 8) != cudaSuccess) { delete ctx; return CDG_ERR_CUDA; }
     cudaFuncSetAttribute(cdgalign::correct_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(cdgalign::CorrSmem));
     cudaFuncSetAttribute(cdgkmer::extract_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (32768 + 128) * 4);
@@ -263,6 +269,9 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
     for (HostBuf *b : h) b->release();
     for (int i = 0; i < EV_N; i++) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2 * cdgsort::MAX_PASSES; i++) cudaEventDestroy(ctx->passEv[i]);
+    cudaStreamSynchronize(ctx->copySt);
+    for (int i = 0; i < CDG_UPLOAD_CHUNKS; i++) cudaEventDestroy(ctx->chunkEv[i]);
+    cudaEventDestroy(ctx->evUploadStart);
     cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->copySt); cudaEventDestroy(ctx->evReady); cudaEventDestroy(ctx->evCopied);
     delete ctx;
 }
@@ -271,23 +280,71 @@ extern "C" const char *cdg_last_error(const cdg_ctx *ctx) { return ctx ? ctx->er
 extern "C" void *cdg_stream(cdg_ctx *ctx) { return ctx ? (void *) ctx->st : nullptr; }
 
 // ------------------------------------------------------------------------------------------------------
-extern "C" int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, const uint64_t *offsets, const uint32_t *lens,
-                               const uint8_t *ext, uint64_t n) {
+// pack + meta of the chunks whose bytes have arrived but are not packed yet (every consumer of the packed set calls this;
+// the k-mer extraction interleaves it with its own per-chunk launches instead, see km_extract)
+static int pack_chunk(cdg_ctx *ctx, u64 seqLo, u64 seqHi) {
+    if (seqHi <= seqLo) return 0;
+    const u64 cnt = seqHi - seqLo;
+    const unsigned pb = (unsigned) std::min<u64>((cnt * 32 + 255) / 256, (u64) ctx->smCount * 16);
+    cdgkmer::pack_kernel<<<pb, 256, 0, ctx->st>>>(ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dWordOff.as<u64>(), seqLo, seqHi,
+                                                  ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dFlags.as<u8>());
+    cdgalign::meta_kernel<<<(unsigned) ((cnt + 255) / 256), 256, 0, ctx->st>>>(ctx->dOff.as<u64>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dFlags.as<u8>(),
+                                                                           ctx->dExt.as<u8>(), seqLo, seqHi, ctx->dMeta.as<cdgalign::SeqMeta>());
+    ctx->launches += 2;
+    CKL();
+    return 0;
+}
+static int ensure_packed(cdg_ctx *ctx) {
+    for (const cdg_ctx::UploadChunk &c : ctx->pending) {
+        CK(cudaStreamWaitEvent(ctx->st, c.ev, 0));
+        if (int rc = pack_chunk(ctx, c.seqLo, c.seqHi)) return rc;
+    }
+    ctx->pending.clear();
+    return 0;
+}
+
+// chunks > 1: `data` and `offsets` are host memory; the DB bytes are copied in `chunks` pieces on the copy stream and the set is
+// packed lazily (ensure_packed / km_extract), so that the copy of one piece overlaps pack + extraction of the previous one
+static int upload_impl(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, const uint64_t *offsets, const uint32_t *lens, const uint8_t *ext,
+                       uint64_t n, int chunks) {
     if (!ctx) return CDG_ERR_ARG;
     if (n == 0 || !data || !offsets || !lens) return fail(ctx, CDG_ERR_ARG, "cdg_upload_seqs: empty or NULL input");
     if (n >= (1ull << 31)) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_upload_seqs: more than 2^31 sequences per context");
     CK(cudaSetDevice(ctx->device));
+    if (!ctx->pending.empty()) { CK(cudaStreamSynchronize(ctx->copySt)); ctx->pending.clear(); }   // an upload nobody consumed
     ctx->hitsValid = ctx->linesValid = ctx->alnsValid = false;
     ctx->n = n; ctx->dataBytes = data_bytes; ctx->qLo = 0; ctx->nQ = n;
     CK(ctx->dData.reserve(data_bytes + 64));
     CK(ctx->dOff.reserve(n * 8)); CK(ctx->dLen.reserve(n * 4)); CK(ctx->dExt.reserve(n)); CK(ctx->dFlags.reserve(n));
     CK(ctx->dWordOff.reserve((n + 1) * 8)); CK(ctx->dLikOff.reserve((n + 1) * 8));
-    CK(cudaMemcpyAsync(ctx->dData.p, data, data_bytes, cudaMemcpyDefault, ctx->st));
     CK(cudaMemcpyAsync(ctx->dOff.p, offsets, n * 8, cudaMemcpyDefault, ctx->st));
     CK(cudaMemcpyAsync(ctx->dLen.p, lens, n * 4, cudaMemcpyDefault, ctx->st));
     if (ext) CK(cudaMemcpyAsync(ctx->dExt.p, ext, n, cudaMemcpyDefault, ctx->st));
     else CK(cudaMemsetAsync(ctx->dExt.p, 0, n, ctx->st));
-    // facts needed for sizing: total bases, longest sequence, packed words (all reduced on the device)
+    if (chunks > CDG_UPLOAD_CHUNKS) chunks = CDG_UPLOAD_CHUNKS;
+    if (chunks <= 1 || n < 4096) {
+        CK(cudaMemcpyAsync(ctx->dData.p, data, data_bytes, cudaMemcpyDefault, ctx->st));
+        CK(cudaEventRecord(ctx->chunkEv[0], ctx->st));
+        ctx->pending.push_back(cdg_ctx::UploadChunk{0, n, ctx->chunkEv[0]});
+    } else {
+        // the copy stream starts once everything queued on the main stream (which may still read the old set) is done
+        CK(cudaEventRecord(ctx->evUploadStart, ctx->st));
+        CK(cudaStreamWaitEvent(ctx->copySt, ctx->evUploadStart, 0));
+        u64 s0 = 0;
+        for (int c = 0; c < chunks; c++) {
+            u64 s1 = n;
+            if (c + 1 < chunks) {   // first sequence whose offset reaches the next byte target
+                const u64 target = data_bytes / chunks * (c + 1);
+                s1 = (u64) (std::lower_bound(offsets + s0, offsets + n, target) - offsets);
+            }
+            const u64 b0 = c == 0 ? 0 : offsets[s0], b1 = s1 < n ? offsets[s1] : data_bytes;
+            if (b1 > b0) CK(cudaMemcpyAsync(ctx->dData.as<u8>() + b0, data + b0, b1 - b0, cudaMemcpyDefault, ctx->copySt));
+            CK(cudaEventRecord(ctx->chunkEv[c], ctx->copySt));
+            ctx->pending.push_back(cdg_ctx::UploadChunk{s0, s1, ctx->chunkEv[c]});
+            s0 = s1;
+        }
+    }
+    // facts needed for sizing: total bases, longest sequence, packed words (all reduced on the device, from the lengths alone)
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
     CK(cudaMemsetAsync(sc + SC_WIDE, 0, 8, ctx->st));
     max_len_kernel<<<ctx->smCount * 4, 256, 0, ctx->st>>>(ctx->dLen.as<u32>(), n, (u32 *) (sc + SC_WIDE));
@@ -302,18 +359,24 @@ extern "C" int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_
     u64 words = 0;
     if ((rc = read_scalar(ctx, SC_SCAN, &words))) return rc;
     ctx->totalWords = words;
-    CK(ctx->dWords.reserve((words + 2) * 8)); CK(ctx->dXmask.reserve((words + 2) * 4));
-    cdgkmer::pack_kernel<<<ctx->smCount * 16, 256, 0, ctx->st>>>(ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(),
-                                                                                    ctx->dWordOff.as<u64>(), n, ctx->dWords.as<u64>(),
-                                                                                    ctx->dXmask.as<u32>(), ctx->dFlags.as<u8>());
     if (words >= (1ull << 32)) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_upload_seqs: more than 2^32 packed words per context");
+    CK(ctx->dWords.reserve((words + 2) * 8)); CK(ctx->dXmask.reserve((words + 2) * 4));
     CK(ctx->dMeta.reserve(n * sizeof(cdgalign::SeqMeta)));
-    cdgalign::meta_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dOff.as<u64>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(),
-                                                                           ctx->dFlags.as<u8>(), ctx->dExt.as<u8>(), n, ctx->dMeta.as<cdgalign::SeqMeta>());
-    ctx->launches += 2;
-    CKL();
+    return CDG_OK;
+}
+
+extern "C" int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, const uint64_t *offsets, const uint32_t *lens,
+                               const uint8_t *ext, uint64_t n) {
+    int rc = upload_impl(ctx, data, data_bytes, offsets, lens, ext, n, 1);
+    if (rc) return rc;
+    if ((rc = ensure_packed(ctx))) return rc;
     CK(cudaStreamSynchronize(ctx->st));
     return CDG_OK;
+}
+
+extern "C" int cdg_upload_seqs_async(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, const uint64_t *offsets, const uint32_t *lens,
+                                     const uint8_t *ext, uint64_t n) {
+    return upload_impl(ctx, data, data_bytes, offsets, lens, ext, n, CDG_UPLOAD_CHUNKS);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -426,16 +489,23 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
     const u64 gridWarps = (u64) shortBlocks * EX_WARPS;
     CK(ctx->dShortScratch.reserve(gridWarps * 2 * EX_MAXW * sizeof(WinRec)));
     CK(ctx->dShortKeep.reserve(gridWarps * EX_MAXW));
-    {
+    // Index-order extraction of a set whose bytes are still arriving (asynchronous upload): per chunk wait for its bytes, pack it,
+    // extract it — the copy of the next chunk runs meanwhile.  Otherwise (resident set, or a rank-order slice) one launch.
+    std::vector<cdg_ctx::UploadChunk> pieces;
+    if (identityMode != 2 && ctx->pending.size() > 1) { pieces = ctx->pending; ctx->pending.clear(); }
+    else { if ((rc = ensure_packed(ctx))) return rc; pieces.push_back(cdg_ctx::UploadChunk{0, n, nullptr}); }
+    for (const cdg_ctx::UploadChunk &piece : pieces) {
+        if (piece.ev) { CK(cudaStreamWaitEvent(ctx->st, piece.ev, 0)); if ((rc = pack_chunk(ctx, piece.seqLo, piece.seqHi))) return rc; }
+        E.seqLo = piece.seqLo; E.seqHi = piece.seqHi;
         const u32 maxW = ctx->maxLen >= (u32) p->k ? ctx->maxLen - p->k + 1 : 0;   // short sequences have <= 256 windows
 #define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dPow31.as<u64>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT, identityMode == 2 ? ctx->ordV : (const u64 *) nullptr, ctx->dSlotRank.as<u64>())
         if (maxW <= 64) extract_short_kernel<2><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
         else if (maxW <= 128) extract_short_kernel<4><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
         else extract_short_kernel<8><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
 #undef CDG_EXTRACT_ARGS
+        ctx->launches++;
+        CKL();
     }
-    ctx->launches++;
-    CKL();
     if (nLong) {
         CK(ctx->dScratch.reserve((longScr + 1) * sizeof(WinRec))); CK(ctx->dScratchKeep.reserve(longScr + 1));
         unsigned lb = nLong < (u32) ctx->smCount ? nLong : (u32) ctx->smCount;
@@ -681,6 +751,7 @@ extern "C" int cdg_set_pref_lines(cdg_ctx *ctx, const uint64_t *line_off, uint64
 }
 
 static int run_rescore(cdg_ctx *ctx, const cdg_rescore_params *p) {
+    if (int rcp = ensure_packed(ctx)) return rcp;
     if (!ctx->linesValid) {
         if (!ctx->hitsValid) return fail(ctx, CDG_ERR_ARG, "cdg_rescore: no prefilter lines (run cdg_kmermatch or cdg_set_pref_lines)");
         int rc = build_lines_from_hits(ctx);
@@ -793,6 +864,7 @@ static int wait_exports(cdg_ctx *ctx) {
 }
 
 static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data, uint64_t *n_changed, double *lik) {
+    if (int rcp = ensure_packed(ctx)) return rcp;
     if (!ctx->alnsValid) return fail(ctx, CDG_ERR_ARG, "cdg_correct: no alignments (run cdg_rescore or cdg_set_alignments)");
     if (!ctx->damageSet) return fail(ctx, CDG_ERR_ARG, "cdg_correct: cdg_set_damage not called");
     const u64 n = ctx->nQ, qLo = ctx->qLo;
@@ -888,6 +960,7 @@ static int run_pair_loglik(cdg_ctx *ctx, const cdg_pairs *P, const uint8_t *cons
     const u64 n = P->n;
     if (n == 0) return CDG_OK;
     CK(cudaSetDevice(ctx->device));
+    if (int rcp = ensure_packed(ctx)) return rcp;
     // validate on the host what would otherwise be an out-of-bounds device read
     for (u64 i = 0; i < n; i++) {
         if (P->query[i] >= ctx->n || P->target[i] >= ctx->n)

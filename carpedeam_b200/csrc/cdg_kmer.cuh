@@ -27,11 +27,11 @@ CDG_D u64 interleave32(u32 hi, u32 lo) {   // bit j of hi -> bit 2j+1, bit j of 
     return (a << 1) | b;
 }
 __global__ void __launch_bounds__(256) pack_kernel(const u8 *__restrict__ data, const u64 *__restrict__ off, const u32 *__restrict__ len,
-                                                   const u64 *__restrict__ wordOff, u64 n, u64 *__restrict__ words,
+                                                   const u64 *__restrict__ wordOff, u64 seqLo, u64 seqHi, u64 *__restrict__ words,
                                                    u32 *__restrict__ xmask, u8 *__restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const u64 gwarp = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64) gridDim.x * blockDim.x) >> 5;
-    for (u64 seq = gwarp; seq < n; seq += nwarps) {
+    for (u64 seq = seqLo + gwarp; seq < seqHi; seq += nwarps) {
         const u8 *s = data + off[seq];
         const u32 L = len[seq];
         const u64 w0 = wordOff[seq];
@@ -80,6 +80,7 @@ struct ExtractParams {
     // rankOf[seq]; 2 = slice mode: one identity record per sequence of the slice at slot rank - posLo, tagged with its owner
     // (routed with the k-mer records); 0 = none.
     u32 world, posLo, posHi; u64 slotBase; int identity;
+    u64 seqLo, seqHi;   // index-order iteration (single GPU): sequences [seqLo, seqHi) of this launch (chunked upload pipeline)
 };
 CDG_D u32 owner_of(u32 score, u32 world) { return (score * world) >> 16; }
 // slots reserved for sequence of length L: upper bound of selected k-mers (kmermatcher.cpp:226)
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
     // `order` (multi-GPU: the per-rank work does not grow with the number of ranks).  The loads that start a sequence
     // (index, meta, rank, slot) are issued one sequence ahead.
     const bool byRank = order != nullptr;
-    const u64 itLo = byRank ? (u64) P.posLo : 0ull, itHi = byRank ? (u64) P.posHi : n;
+    const u64 itLo = byRank ? (u64) P.posLo : P.seqLo, itHi = byRank ? (u64) P.posHi : (P.seqHi < n ? P.seqHi : n);
     SeqMeta smN; smN.off = 0; smN.wordOff = 0; smN.lenFlags = 0; u32 rankN = 0; u64 slotN = 0, seqN = 0;
     auto fetch = [&](u64 it) {
         if (byRank) { seqN = (u32) order[it]; rankN = (u32) it; slotN = prefix[it]; }

@@ -55,6 +55,11 @@ void *cdg_stream(cdg_ctx *ctx);
  * (multi-GPU: every rank reads 1/world of the DB from the host and the ranks all-gather over NVLink, multigpu.py). */
 int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, const uint64_t *offsets,
                     const uint32_t *lens, const uint8_t *ext, uint64_t n);
+/* Same, but returns as soon as the copies are queued: the DB bytes travel in pieces on a copy stream and the next call on the
+ * context consumes them as they arrive (cdg_kmermatch / cdg_iteration pack and extract piece c while piece c+1 is still on the
+ * PCIe bus).  The four arrays must be HOST memory (pinned for real overlap) and stay valid until that next call has returned. */
+int cdg_upload_seqs_async(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, const uint64_t *offsets,
+                          const uint32_t *lens, const uint8_t *ext, uint64_t n);
 
 /* ---- kmermatcher ----------------------------------------------------------------------------- */
 typedef struct {

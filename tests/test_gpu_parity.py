@@ -536,3 +536,41 @@ def test_caller_provided_lists_are_validated(ctx):
     ctx.set_alignments(two, t2, np.ones(2 * s.n, np.float32), qs, qe, ds, de)
     out, changed = ctx.correct()
     assert changed == 0 and np.array_equal(out, s.blob)
+
+
+def test_async_upload_pipeline_equals_synchronous_upload(oracle):
+    """cdg_upload_seqs_async + cdg_iteration (chunked copy, per-chunk pack and extraction) must give exactly what the synchronous
+    upload gives; also when the first consumer is not the extraction (stand-alone rescore on caller-provided lines)."""
+    import torch
+    import carpedeam_b200 as cd
+    seqs = synth_reads(30000, 150000, 77, n_frac=0.001)
+    seqs[5] = seqs[5].lower()
+    s = SeqSet(seqs)
+    c = cd.Context(0)
+    try:
+        c.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+        c.upload(s.blob, s.off, s.len, s.ext)
+        hits, alns, out, changed = c.iteration(fetch_hits=True)
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        hb, ho, hl, he = pin(s.blob), pin(s.off.view(np.int64)), pin(s.len.view(np.int32)), pin(s.ext)
+        for rep in range(2):
+            c.upload_raw_async(hb.data_ptr(), hb.numel(), ho.data_ptr(), hl.data_ptr(), he.data_ptr(), s.n)
+            hits2, alns2, out2, changed2 = c.iteration(fetch_hits=True)
+            for f in ("rep", "tgt", "score", "diag"):
+                assert np.array_equal(hits[f], hits2[f]), f
+            for f in ("keep", "score", "bits", "qs", "qe", "ds", "de", "seqid"):
+                assert np.array_equal(alns[f], alns2[f]), f
+            assert np.array_equal(out, out2) and changed == changed2
+        # first consumer = rescore on provided lines
+        c.upload_raw_async(hb.data_ptr(), hb.numel(), ho.data_ptr(), hl.data_ptr(), he.data_ptr(), s.n)
+        lo = alns["line_off"]
+        q = np.repeat(np.arange(s.n), np.diff(lo.astype(np.int64)))
+        pref = np.zeros(len(q), np.int32); dg = np.zeros(len(q), np.uint16)
+        hp = np.arange(len(hits["rep"])) + hits["rep"].astype(np.int64) + 1
+        pref[hp] = hits["score"]; dg[hp] = hits["diag"].astype(np.uint16)
+        c.set_pref_lines(lo, alns["tgt"], pref, dg)
+        alns3 = c.rescore()
+        for f in ("keep", "score", "qs", "qe", "ds", "de"):
+            assert np.array_equal(alns[f], alns3[f]), f
+    finally:
+        c.close()
