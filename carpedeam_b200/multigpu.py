@@ -112,6 +112,130 @@ class TorchComm:
         return n_recv
 
 
+class LocalWorld:
+    """shared state of `world` virtual ranks that run as threads of ONE process on ONE GPU (see ThreadComm)"""
+
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+
+
+class ThreadComm:
+    """Comm adapter for virtual ranks: every rank is a host thread with its own library context on the same device, the
+    "collectives" are device-to-device copies between the contexts' buffers.  Two uses: (1) hash-range passes on a single GPU —
+    the reference's split mode (kmermatcher.cpp:665-675, setupKmerSplits :742-784) with unsplit results: each virtual rank sorts
+    and groups one hash range, so no sort sees more than 1/world of the k-mer records; (2) the multi-rank logic runs in the
+    single-GPU test-suite.  Use with ShardedIteration(..., exchange="nccl") (the IPC exchange needs separate processes)."""
+
+    def __init__(self, local_world, rank, device):
+        import torch
+        self.torch, self.dist, self.device = torch, None, device
+        self.lw, self.rank, self.world = local_world, rank, local_world.world
+
+    def _gather(self, obj):
+        """every rank contributes `obj`; returns the list over ranks (two barriers: publish, then everybody has read)"""
+        self.lw.slots[self.rank] = obj
+        self.lw.barrier.wait()
+        out = list(self.lw.slots)
+        self.lw.barrier.wait()
+        return out
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            self.torch.cuda.synchronize()
+
+    def barrier(self):
+        self._sync()
+        self.lw.barrier.wait()
+
+    def exchange_counts(self, send_counts):
+        k = len(send_counts) // self.world
+        rows = self._gather([int(c) for c in send_counts])
+        return [rows[src][j * self.world + self.rank] for src in range(self.world) for j in range(k)]
+
+    def all_gather_rows(self, row):
+        return self._gather([int(x) for x in row])
+
+    def all_gather_bytes(self, payload):
+        return self._gather(bytes(payload))
+
+    def all_gather_u64(self, value):
+        return self._gather(int(value))
+
+    class _Done:
+        def wait(self):
+            return None
+
+    def all_to_all(self, recv, send, recv_counts, send_counts, async_op=False):
+        sends = self._gather((send, split_offsets(send_counts)))     # peers' send tensors (same device) and their segment offsets
+        pos = 0
+        for src in range(self.world):
+            t, off = sends[src]
+            c = int(recv_counts[src])
+            if c:
+                recv[pos:pos + c].copy_(t[off[self.rank]:off[self.rank] + c])
+            pos += c
+        self._sync()
+        self.lw.barrier.wait()          # nobody reuses a send buffer before every peer has copied from it
+        return self._Done()
+
+    def shift_to_prev(self, send, n_send, recv_capacity_tensor):
+        items = self._gather((send, int(n_send)))
+        n_recv = 0
+        if self.rank + 1 < self.world:
+            t, n_recv = items[self.rank + 1]
+            if n_recv:
+                recv_capacity_tensor[:n_recv].copy_(t[:n_recv])
+        self._sync()
+        self.lw.barrier.wait()
+        return n_recv
+
+
+def run_virtual_ranks(device_index, world, blob, off, lens, ext, damage, kmer=None, rescore=None, corr=None):
+    """Hash-range passes on one GPU: `world` virtual ranks (threads, one context each) run the sharded iteration with unsplit
+    results.  Returns the per-rank result dicts of ShardedIteration.run (hits, alns, corrected bytes of the rank's query range
+    in res["out"])."""
+    import threading
+
+    import torch
+
+    from . import Context
+    lw = LocalWorld(world)
+    results, errors = [None] * world, []
+    dev = torch.device("cuda", device_index)
+
+    def worker(rank):
+        ctx = None
+        try:
+            torch.cuda.set_device(device_index)
+            ctx = Context(device_index)
+            ctx.set_damage(damage)
+            ctx.upload(blob, off, lens, ext)
+            out = np.zeros(len(blob), np.uint8)
+            res = ShardedIteration(ctx, ThreadComm(lw, rank, dev), exchange="nccl").run(kmer=kmer, rescore=rescore, corr=corr, fetch_hits=True,
+                                                                                    fetch_alns=True, out_range=out)
+            res["out"] = out[:res["range_bytes"]].copy()
+            results[rank] = res
+        except Exception as e:      # a failed rank must not leave the others waiting at a barrier
+            errors.append((rank, e))
+            lw.barrier.abort()
+        finally:
+            if ctx is not None:
+                ctx.close()
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        real = [e for e in errors if "BrokenBarrier" not in type(e[1]).__name__] or errors
+        raise RuntimeError("virtual rank %d failed: %r" % real[0])
+    return results
+
+
 def segment_offsets(matrix, rank):
     """matrix[r][o] = records rank r sends to rank o.  Returns (dst_off, totals): dst_off[o] = first index of `rank`'s segment in
     o's receive area (segments are ordered by source rank, like an all-to-all's output), totals[o] = records o receives."""

@@ -574,3 +574,34 @@ def test_async_upload_pipeline_equals_synchronous_upload(oracle):
             assert np.array_equal(alns[f], alns3[f]), f
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", ["golden reads k=20", "golden contigs k=22 ext", "synthetic with N"])
+def test_virtual_ranks_equal_unsplit_run(ctx, world, case):
+    """hash-range passes on one GPU (virtual ranks = threads with one context each, multigpu.run_virtual_ranks): every rank sorts and
+    groups one hash range, grouped records go to the rank owning the representative, the head run crosses rank boundaries —
+    hits, alignment records and corrected bytes must equal the unsplit single-context run bit for bit.  This is the multi-GPU
+    algorithm (tests/mg_worker.py runs it over NCCL / peer memory on 2-8 GPUs) inside the single-GPU suite."""
+    import carpedeam_b200 as cd
+    from carpedeam_b200.multigpu import run_virtual_ranks
+    if case == "golden reads k=20":
+        s, kp = SeqSet.from_golden("nucl_reads"), cd.kmer_params()
+    elif case == "golden contigs k=22 ext":
+        s, kp = SeqSet.from_golden("assembly_contigs_8_noneCycle"), cd.kmer_params(k=22, include_only_extendable=1)
+    else:
+        s, kp = SeqSet(synth_reads(20000, 100000, 21, n_frac=0.001)), cd.kmer_params()
+    dmg = cd.load_damage(os.path.join(GOLD, "dhigh"))
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_damage(dmg)
+    hits, alns, out, changed = ctx.iteration(kmer=kp, fetch_hits=True)
+    parts = run_virtual_ranks(0, world, s.blob, s.off, s.len, s.ext, dmg, kmer=kp)
+    for f in ("rep", "tgt", "score", "diag"):
+        assert np.array_equal(np.concatenate([p["hits"][f] for p in parts]), hits[f]), f
+    for f in ("tgt", "keep", "score", "bits", "qs", "qe", "ds", "de", "seqid"):
+        assert np.array_equal(np.concatenate([p["alns"][f] for p in parts]), alns[f]), f
+    merged = s.blob.copy()
+    for p in parts:
+        merged[p["range_offset"]:p["range_offset"] + p["range_bytes"]] = p["out"]
+    assert np.array_equal(merged, out) and sum(p["changed"] for p in parts) == changed
+    assert max(p["records_received"] for p in parts) < 0.75 * hits["R1"] or world == 1      # no rank sorted the whole record set

@@ -86,3 +86,60 @@ def test_hash_ownership_partitions_the_16bit_space():
             assert not covered[lo:hi + 1].any()
             covered[lo:hi + 1] = True
         assert covered.all()
+
+
+def test_thread_comm_virtual_ranks_cpu():
+    """ThreadComm (virtual ranks as threads, used for hash-range passes on one GPU) must behave like the torch.distributed
+    adapter: all-to-all segments ordered by source rank with per-source order preserved, interleaved count exchange, row/bytes
+    all-gathers, ring shift of the head run."""
+    import threading
+
+    import torch
+
+    from carpedeam_b200.multigpu import LocalWorld, ThreadComm, segment_offsets, split_offsets
+    world = 3
+    lw = LocalWorld(world)
+    errors = []
+
+    def worker(rank):
+        try:
+            comm = ThreadComm(lw, rank, torch.device("cpu"))
+            n = 500 + 11 * rank
+            vals = np.arange(n, dtype=np.int64) + rank * 1_000_000
+            owner = vals % world
+            order = np.argsort(owner, kind="stable")
+            send = torch.from_numpy(vals[order].copy())
+            send_counts = [int((owner == o).sum()) for o in range(world)]
+            ids = [rank * 10 + o for o in range(world)]
+            both = comm.exchange_counts(send_counts + ids)
+            recv_counts, id_recv = both[0::2], both[1::2]
+            assert id_recv == [src * 10 + rank for src in range(world)]
+            recv = torch.empty(sum(recv_counts), dtype=torch.int64)
+            comm.all_to_all(recv, send, recv_counts, send_counts, async_op=True).wait()
+            got = recv.numpy(); off = split_offsets(recv_counts)
+            for src in range(world):
+                seg = got[off[src]:off[src + 1]]
+                assert np.all(seg // 1_000_000 == src) and np.all(seg % world == rank) and np.all(np.diff(seg) > 0)
+            rows = comm.all_gather_rows(send_counts)
+            dst, totals = segment_offsets(rows, rank)
+            assert totals[rank] == sum(recv_counts) and dst[rank] == off[rank]
+            assert comm.all_gather_u64((1 << 63) + rank) == [(1 << 63) + r for r in range(world)]
+            assert comm.all_gather_bytes(bytes([rank]) * 5) == [bytes([r]) * 5 for r in range(world)]
+            buf = torch.arange(10, dtype=torch.int64) + 100 * rank
+            tail = torch.zeros(8, dtype=torch.int64)
+            n_recv = comm.shift_to_prev(buf, 2 + rank, tail)
+            if rank + 1 < world:
+                assert n_recv == 3 + rank and torch.equal(tail[:n_recv], torch.arange(n_recv) + 100 * (rank + 1))
+            else:
+                assert n_recv == 0
+            comm.barrier()
+        except Exception as e:
+            errors.append((rank, repr(e)))
+            lw.barrier.abort()
+
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(60)
+    assert not errors, errors
