@@ -367,7 +367,11 @@ def main():
             ctx.iteration_raw(ip, None, alns, h_out.data_ptr())
             last["M"] = alns.n_lines; last["d2h_seq"] = h_blob.numel()
         else:
+            t_up = time.perf_counter()
             r = sharded.run(fetch_alns="raw", out_range=h_out.data_ptr())
+            if os.environ.get("CDG_MG_TRACE") is not None and rank == 0:
+                print("e2e run (incl. exports) %.1f ms  phases %s" % ((time.perf_counter() - t_up) * 1e3, {k: round(v, 1) for k, v in r["phase_ms"].items()}),
+                      file=sys.stderr, flush=True)
             last["M"] = int(r["alns_raw"].n_lines); last["d2h_seq"] = r["range_bytes"]; last["sent"] = r["records_sent"]; last["sent2"] = r["grouped_sent"]
 
     # ---- resident-input timing ----

@@ -318,6 +318,10 @@ class ShardedIteration:
         memory.  blob: uint8, off: int64, lens: int32, ext: uint8 or None (torch CPU tensors)."""
         torch, dist, comm = self.comm.torch, self.comm.dist, self.comm
         world, rank, dev = comm.world, comm.rank, comm.device
+        import os
+        import time
+        trace = os.environ.get("CDG_MG_TRACE") is not None
+        t0 = time.perf_counter()
         full, h2d = [], 0
         for a in (blob, off, lens, ext):
             if a is None:
@@ -333,8 +337,11 @@ class ShardedIteration:
             dist.all_gather_into_tensor(out, shard)
             full.append(out[:n])
         torch.cuda.current_stream().synchronize()
+        t1 = time.perf_counter()
         self.ctx.upload_raw(full[0].data_ptr(), full[0].numel(), full[1].data_ptr(), full[2].data_ptr(),
                             full[3].data_ptr() if full[3] is not None else 0, lens.numel())     # synchronous: `full` may go afterwards
+        if trace and rank == 0:
+            print("upload_sharded: shards+all_gather %.1f ms, pack from device memory %.1f ms" % ((t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3), flush=True)
         return h2d      # bytes this rank copied from the host
 
     def release(self):
