@@ -66,3 +66,32 @@ void parse_aln_entry(const char *data, std::vector<AlnLine> &out) {
 }
 
 }   // namespace cdh
+
+// ---- C entry points for the CPU test-suite (ctypes): round trips of whole DB entries through the parsers / formatters ----
+extern "C" size_t cdh_pref_roundtrip(const char *entry, char *out, size_t cap) {
+    std::vector<cdh::PrefLine> lines;
+    cdh::parse_pref_entry(entry, lines);
+    size_t n = 0;
+    char buf[64];
+    for (const cdh::PrefLine &l : lines) {
+        const size_t k = cdh::format_pref_line(buf, l.targetKey, l.score, (int16_t) l.diag);
+        if (n + k >= cap) return 0;
+        memcpy(out + n, buf, k); n += k;
+    }
+    out[n] = '\0';
+    return n;
+}
+extern "C" size_t cdh_format_aln_line(char *buf, uint32_t targetKey, int32_t bits, float seqId, double evalue, int32_t qStart, int32_t qEnd,
+                                      int32_t qLen, int32_t dbStart, int32_t dbEnd, int32_t dbLen) {
+    return cdh::format_aln_line(buf, targetKey, bits, seqId, evalue, qStart, qEnd, qLen, dbStart, dbEnd, dbLen);
+}
+// fields of line `index` of an alignment entry as the correction stage reads them; returns the number of lines
+extern "C" size_t cdh_parse_aln_entry(const char *entry, size_t index, uint32_t *targetKey, float *seqId, int32_t *coords4) {
+    std::vector<cdh::AlnLine> lines;
+    cdh::parse_aln_entry(entry, lines);
+    if (index < lines.size()) {
+        const cdh::AlnLine &a = lines[index];
+        *targetKey = a.targetKey; *seqId = a.seqId; coords4[0] = a.qStart; coords4[1] = a.qEnd; coords4[2] = a.dbStart; coords4[3] = a.dbEnd;
+    }
+    return lines.size();
+}

@@ -1,0 +1,60 @@
+"""CPU tests of the C++ host side (carpedeam_b200/host/formats.cpp): the text formats between the stages
+(QueryMatcher::prefilterHitToBuffer / parsePrefilterHits, Matcher::resultToBuffer / parseAlignmentRecord) against the
+reference's own pref / aln databases (tests/golden)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from support import load_golden
+
+
+@pytest.fixture(scope="module")
+def host():
+    import carpedeam_b200 as cd
+    cd.build()
+    H = C.CDLL(cd.HOST_LIB_PATH)
+    H.cdh_pref_roundtrip.restype = C.c_size_t
+    H.cdh_pref_roundtrip.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+    H.cdh_format_aln_line.restype = C.c_size_t
+    H.cdh_format_aln_line.argtypes = [C.c_char_p, C.c_uint32, C.c_int32, C.c_float, C.c_double] + [C.c_int32] * 6
+    H.cdh_parse_aln_entry.restype = C.c_size_t
+    H.cdh_parse_aln_entry.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    return H
+
+
+@pytest.mark.parametrize("name", ["pref_0", "pref_asm_5", "pref_asm_9"])
+def test_pref_entries_round_trip(host, name):
+    """parse (diagonal read back as unsigned short) + format (written as signed short) reproduces every entry byte for byte"""
+    keys, payloads, _ = load_golden(name)
+    out = C.create_string_buffer(1 << 22)
+    neg = 0
+    for p in payloads:
+        n = host.cdh_pref_roundtrip(p, out, len(out))
+        assert out.raw[:n] == p
+        neg += p.count(b"\t-")
+    assert neg > 100      # negative scores (reverse strand) and negative diagonals occur
+
+
+@pytest.mark.parametrize("name", ["aln_0", "aln_asm_5"])
+def test_aln_lines_format_and_parse(host, name):
+    """every alignment line of the reference re-formatted by the host formatter from its own fields (seqId quirks: "1.00",
+    truncation to three decimals, %.3E E-values), and the parser returns the fields ancient_correction reads"""
+    keys, payloads, _ = load_golden(name)
+    buf = C.create_string_buffer(256)
+    checked = 0
+    for p in payloads[:4000]:
+        lines = [l for l in p.split(b"\n") if l]
+        for i, line in enumerate(lines):
+            f = line.split(b"\t")
+            sid_txt = f[2]
+            sid = 1.0 if sid_txt == b"1.00" else float(sid_txt) + 0.0004      # any value that truncates to the printed decimals
+            n = host.cdh_format_aln_line(buf, int(f[0]), int(f[1]), sid, float(f[3]), *[int(x) for x in f[4:10]])
+            assert buf.raw[:n] == line + b"\n", (buf.raw[:n], line)
+            if i == len(lines) - 1 and i < 3:
+                t = C.c_uint32(); s = C.c_float(); c4 = (C.c_int32 * 4)()
+                cnt = host.cdh_parse_aln_entry(p, i, C.byref(t), C.byref(s), c4)
+                assert cnt == len(lines) and t.value == int(f[0]) and list(c4) == [int(f[4]), int(f[5]), int(f[7]), int(f[8])]
+                assert s.value == np.float32(float(sid_txt))
+            checked += 1
+    assert checked > 5000
