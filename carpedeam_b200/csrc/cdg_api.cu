@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/carpedeam_gpu.h"
@@ -342,6 +343,31 @@ static int upload_impl(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, c
             CK(cudaEventRecord(ctx->chunkEv[c], ctx->copySt));
             ctx->pending.push_back(cdg_ctx::UploadChunk{s0, s1, ctx->chunkEv[c]});
             s0 = s1;
+        }
+        // The pieces assume that the entries lie in the data file in index order without overlap (what createdb and the stages'
+        // single-threaded writers produce).  Checked here, on the host, while the copies are already in flight; any other layout
+        // (index sorted by key over a multi-threaded writer's data file) gets one plain copy behind the pieces instead.
+        bool ordered = true;
+        {
+            const int T = 8;
+            bool ok[T];
+            std::vector<std::thread> th;
+            for (int t = 0; t < T; t++)
+                th.emplace_back([&, t]() {
+                    const u64 lo = (n - 1) * t / T, hi = (n - 1) * (t + 1) / T;
+                    bool o = true;
+                    for (u64 i = lo; i < hi; i++) o &= offsets[i] + lens[i] <= offsets[i + 1];
+                    ok[t] = o;
+                });
+            for (int t = 0; t < T; t++) { th[t].join(); ordered = ordered && ok[t]; }
+        }
+        if (!ordered || offsets[n - 1] + lens[n - 1] > data_bytes) {
+            if (n && offsets[n - 1] + lens[n - 1] > data_bytes && ordered)
+                return fail(ctx, CDG_ERR_ARG, "cdg_upload_seqs_async: the last entry ends beyond data_bytes");
+            CK(cudaMemcpyAsync(ctx->dData.p, data, data_bytes, cudaMemcpyDefault, ctx->copySt));
+            CK(cudaEventRecord(ctx->chunkEv[0], ctx->copySt));
+            ctx->pending.clear();
+            ctx->pending.push_back(cdg_ctx::UploadChunk{0, n, ctx->chunkEv[0]});
         }
     }
     // facts needed for sizing: total bases, longest sequence, packed words (all reduced on the device, from the lengths alone)

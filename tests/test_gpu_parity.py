@@ -561,6 +561,21 @@ def test_async_upload_pipeline_equals_synchronous_upload(oracle):
             for f in ("keep", "score", "bits", "qs", "qe", "ds", "de", "seqid"):
                 assert np.array_equal(alns[f], alns2[f]), f
             assert np.array_equal(out, out2) and changed == changed2
+        # entries NOT in index order in the data file (index sorted by key over a shuffled data file): same set, same answers
+        perm = np.random.default_rng(1).permutation(s.n)
+        blob2 = np.zeros_like(s.blob); off2 = np.zeros_like(s.off)
+        pos = 0
+        for i in perm.tolist():
+            L = int(s.len[i]) + 2
+            blob2[pos:pos + L] = s.blob[int(s.off[i]):int(s.off[i]) + L]; off2[i] = pos; pos += L
+        hb2, ho2 = pin(blob2), pin(off2.view(np.int64))
+        c.upload_raw_async(hb2.data_ptr(), hb2.numel(), ho2.data_ptr(), hl.data_ptr(), he.data_ptr(), s.n)
+        hits4, alns4, out4, changed4 = c.iteration(fetch_hits=True)
+        for f in ("rep", "tgt", "score", "diag"):
+            assert np.array_equal(hits[f], hits4[f]), f
+        assert changed4 == changed
+        for i in range(0, s.n, 97):
+            assert np.array_equal(out4[int(off2[i]):int(off2[i]) + int(s.len[i])], out[int(s.off[i]):int(s.off[i]) + int(s.len[i])])
         # first consumer = rescore on provided lines
         c.upload_raw_async(hb.data_ptr(), hb.numel(), ho.data_ptr(), hl.data_ptr(), he.data_ptr(), s.n)
         lo = alns["line_off"]
