@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) long_list_kernel(const u32 *__restrict__ 
 int ceil_log2(u64 x) { int b = 0; while ((1ull << b) < x) b++; return b; }
 
 int sort_ws(cdg_ctx *ctx, u64 n, cdgsort::Workspace &ws) {
-    u64 tiles = cdgsort::tiles_for(n) + 1;
+    u64 tiles = (cdgsort::tiles_for(n) + 1) * (n > cdgsort::SMALL_N ? 2 : 1);   // 64-bit tile states above 2^30 records
     CK(ctx->dHist.reserve(sizeof(unsigned long long) * cdgsort::MAX_PASSES * cdgsort::RADIX));
     CK(ctx->dTileState.reserve(tiles * cdgsort::RADIX * sizeof(u32)));
     ws.hist = ctx->dHist.as<unsigned long long>();
@@ -654,7 +654,7 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     if ((rc = km_prepare(ctx, p, K))) return rc;
     ctx->plan = K; ctx->qLo = 0; ctx->nQ = n; ctx->nIdent = n;
     const u64 Rtot = K.slots + K.extraCap;
-    if (Rtot > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "%llu k-mer records exceed one sort (2^30): use hash ranges", (unsigned long long) Rtot);
+    if (Rtot > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "%llu k-mer records exceed one sort (2^32): use hash ranges (multigpu.run_virtual_ranks)", (unsigned long long) Rtot);
     CK(ctx->dKeysA.reserve(Rtot * 8)); CK(ctx->dKeysB.reserve(Rtot * 8)); CK(ctx->dValsA.reserve(Rtot * 8)); CK(ctx->dValsB.reserve(Rtot * 8));
     CK(ctx->dIdKeysA.reserve(n * 8)); CK(ctx->dIdKeysB.reserve(n * 8)); CK(ctx->dIdValsA.reserve(n * 8)); CK(ctx->dIdValsB.reserve(n * 8));
     CK(cudaMemsetAsync(ctx->dKeysA.as<u64>() + K.slots, 0xFF, (size_t) K.extraCap * 8, ctx->st));
@@ -1079,7 +1079,7 @@ extern "C" int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world,
     ctx->plan = K; ctx->qLo = K.qLo; ctx->nQ = K.nQ;
     const u64 R = K.slots + K.extraCap;          // slice slots + spare slots for identity hashes inside the k-mer key range
     const u64 nSlice = (u64) K.posHi - K.posLo;  // sequences of the slice = identity records produced here
-    if (R > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "slice has too many k-mer records for one sort");
+    if (R > cdgsort::SMALL_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "slice has too many k-mer records for one routing pass (2^30)");
     CK(ctx->dKeysA.reserve((R + 1) * 8)); CK(ctx->dKeysB.reserve((R + 1) * 8)); CK(ctx->dValsA.reserve((R + 1) * 8)); CK(ctx->dValsB.reserve((R + 1) * 8));
     CK(ctx->dIdKeysA.reserve((nSlice + 1) * 8)); CK(ctx->dIdKeysB.reserve((nSlice + 1) * 8)); CK(ctx->dIdValsA.reserve((nSlice + 1) * 8)); CK(ctx->dIdValsB.reserve((nSlice + 1) * 8));
     CK(cudaMemsetAsync(ctx->dKeysA.as<u64>() + K.slots, 0xFF, (size_t) K.extraCap * 8, ctx->st));
@@ -1449,6 +1449,25 @@ __global__ void fill_random_kernel(u64 *k, u64 *v, u64 n, u64 seed) {
     u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { k[i] = cdg_xxh64_u64(i, seed); if (v) v[i] = i; }
 }
+// order check of a sort result: adjacent pairs out of order on the sorted bits (and, with values = original indices, unstable
+// ties), plus wrapping sums of keys and values to compare with the input (keys xxh64(i), values i: sums are known in closed form
+// only for the values, the key sum is taken before the sort)
+__global__ void sort_check_kernel(const u64 *__restrict__ k, const u64 *__restrict__ v, u64 n, u64 mask, unsigned long long *out /*[3]: bad, sumK, sumV*/) {
+    unsigned long long bad = 0, sk = 0, sv = 0;
+    for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) {
+        const u64 a = k[i];
+        sk += a;
+        if (v) sv += v[i];
+        if (i + 1 < n) {
+            const u64 b = k[i + 1];
+            if ((a & mask) > (b & mask)) bad++;
+            else if (v && (a & mask) == (b & mask) && v[i] > v[i + 1]) bad++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { bad += __shfl_xor_sync(0xffffffffu, bad, o); sk += __shfl_xor_sync(0xffffffffu, sk, o); sv += __shfl_xor_sync(0xffffffffu, sv, o); }
+    if ((threadIdx.x & 31) == 0) { if (bad) atomicAdd(out, bad); atomicAdd(out + 1, sk); atomicAdd(out + 2, sv); }
+}
 // sort micro-benchmark on device-generated random keys: average milliseconds per full sort (histogram + all passes)
 extern "C" int cdg_test_sort_bench(cdg_ctx *ctx, uint64_t n, int bit_lo, int bit_hi, int has_val, int variant, int reps, float *ms_per_sort,
                                    int *passes) {
@@ -1467,12 +1486,27 @@ extern "C" int cdg_test_sort_bench(cdg_ctx *ctx, uint64_t n, int bit_lo, int bit
     float total = 0.f;
     for (int r = 0; r < reps + 1; r++) {
         fill_random_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ka.as<u64>(), has_val ? va.as<u64>() : nullptr, n, 1234 + r);
+        unsigned long long *chk = ctx->dScalars.as<unsigned long long>() + SC_ROUTE;   // 6 scratch words: input sums, output check
+        const u64 sortMask = (bit_hi >= 64 ? ~0ull : ((1ull << bit_hi) - 1)) & ~((1ull << bit_lo) - 1);
+        if (r == reps) {
+            CK(cudaMemsetAsync(chk, 0, 6 * 8, ctx->st));
+            sort_check_kernel<<<ctx->smCount * 8, 256, 0, ctx->st>>>(ka.as<u64>(), has_val ? va.as<u64>() : nullptr, n, 0, chk);
+        }
         cudaEventRecord(e0, ctx->st);
         u64 *ok, *ov;
         int l = cdgsort::radix_sort(ctx->st, ws, ka.as<u64>(), kb.as<u64>(), has_val ? va.as<u64>() : nullptr, has_val ? vb.as<u64>() : nullptr, n, plan,
                                     &ok, &ov, ctx->smCount, variant);
         if (l < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_test_sort_bench: sort refused");
         cudaEventRecord(e1, ctx->st);
+        if (r == reps) {   // last repetition: the result must be a stable sorted permutation of the input
+            sort_check_kernel<<<ctx->smCount * 8, 256, 0, ctx->st>>>(ok, has_val ? ov : nullptr, n, sortMask, chk + 3);
+            unsigned long long h[6];
+            CK(cudaMemcpyAsync(h, chk, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
+            CK(cudaStreamSynchronize(ctx->st));
+            if (h[3] != 0 || h[4] != h[1] || h[5] != h[2])
+                return fail(ctx, CDG_ERR_CUDA, "cdg_test_sort_bench: result is not a stable sorted permutation (%llu inversions, key sum %s, value sum %s)", h[3],
+                            h[4] == h[1] ? "ok" : "differs", h[5] == h[2] ? "ok" : "differs");
+        }
         CK(cudaStreamSynchronize(ctx->st));
         CKL();
         float ms = 0.f;

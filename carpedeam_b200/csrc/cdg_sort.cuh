@@ -15,8 +15,13 @@ static constexpr int RADIX_BITS = 8;
 static constexpr int RADIX = 1 << RADIX_BITS;
 static constexpr int BLOCK = 256;                 // histogram kernel block
 static constexpr int MAX_PASSES = 16;
-static constexpr u32 FLAG_AGG = 1u << 30, FLAG_INC = 2u << 30, FLAG_MASK = 3u << 30, VAL_MASK = ~FLAG_MASK;
-static constexpr u64 MAX_N = (1ull << 30) - 1;    // 30-bit tile-state counters
+// tile state = flag (2 bits) | digit count: one 32-bit word for passes below 2^30 records (the fast case: 64-bit states
+// measured 64.7 % -> 53 % of the HBM peak on the 16-byte pass), one 64-bit word above
+template <class ST> struct State;
+template <> struct State<u32> { static constexpr u32 AGG = 1u << 30, INC = 2u << 30, FLAGS = 3u << 30, VAL = ~(3u << 30); };
+template <> struct State<u64> { static constexpr u64 AGG = 1ull << 62, INC = 2ull << 62, FLAGS = 3ull << 62, VAL = ~(3ull << 62); };
+static constexpr u64 SMALL_N = (1ull << 30) - 1;  // 30-bit tile-state counters
+static constexpr u64 MAX_N = (1ull << 32) - 8192; // 32-bit tile ids and per-block counters
 // resident blocks per SM the 256x16 digit pass is compiled for (64 registers, no spills, at 4; measured on B200)
 #ifndef CDG_SWEEP_MB_PAIRS
 #define CDG_SWEEP_MB_PAIRS 4
@@ -34,6 +39,8 @@ CDG_D u32 digit_of(u64 w, int shift, u32 mask) { return (u32) (w >> shift) & mas
 // than the system-scope accesses `volatile` compiles to
 CDG_D u32 ld_state(const u32 *p) { u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 CDG_D void st_state(u32 *p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+CDG_D u64 ld_state(const u64 *p) { u64 v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+CDG_D void st_state(u64 *p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
 
 // ---- kernel 1: histograms of every pass in one read of the digit words --------------------------
 __global__ void __launch_bounds__(BLOCK) hist_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, u64 n,
@@ -125,11 +132,11 @@ CDG_D u32 digit_peers(u32 d) {
 // stable order, to routeK[d] / routeV[d] — the rank's segment of peer d's receive buffer, mapped into this process over
 // NVLink (CUDA IPC) — instead of one local output array: the partition and the transfer are one kernel, the tile's run
 // of each digit is written as one coalesced burst into peer memory.  binBase must be all zero (offsets are per segment).
-template <int BLOCK_T, int ITEMS_T, bool HAS_VAL, bool ROUTE = false>
+template <int BLOCK_T, int ITEMS_T, bool HAS_VAL, bool ROUTE = false, class ST = u32>
 __global__ void __launch_bounds__(BLOCK_T, (BLOCK_T == 256 && ITEMS_T == 16) ? (HAS_VAL ? CDG_SWEEP_MB_PAIRS : CDG_SWEEP_MB_KEYS) : (BLOCK_T == 512 && ITEMS_T == 16) ? 2 : 1) onesweep_kernel(const u64 *__restrict__ keysIn, u64 *__restrict__ keysOut,
                                                            const u64 *__restrict__ valsIn, u64 *__restrict__ valsOut, u64 n,
                                                            Pass pass, const unsigned long long *__restrict__ binBase,
-                                                           u32 *tileState /*[tiles][RADIX]*/, u32 *ticket,
+                                                           ST *tileState /*[tiles][RADIX]*/, u32 *ticket,
                                                            u64 *const *__restrict__ routeK = nullptr, u64 *const *__restrict__ routeV = nullptr) {
     constexpr int TILE_T = BLOCK_T * ITEMS_T, WARPS_T = BLOCK_T / 32;
     extern __shared__ __align__(16) unsigned char sweepRaw[];
@@ -180,31 +187,31 @@ __global__ void __launch_bounds__(BLOCK_T, (BLOCK_T == 256 && ITEMS_T == 16) ? (
         const int d = tid;
 #pragma unroll
         for (int w = 0; w < WARPS_T; w++) run += S.warpHist[w][d];
-        u32 *state = tileState;
+        ST *state = tileState;
         u64 excl = 0;
         if (tile == 0) {
-            st_state(state + d, FLAG_INC | run);
+            st_state(state + d, (ST) (State<ST>::INC | run));
         } else {
-            st_state(state + (u64) tile * RADIX + d, FLAG_AGG | run);
+            st_state(state + (u64) tile * RADIX + d, (ST) (State<ST>::AGG | run));
             // decoupled look-back, LOOK predecessors per round trip (independent loads), consumed nearest first
             constexpr int LOOK = 4;
             i64 p = (i64) tile - 1;
             bool done = false;
             while (!done) {
-                u32 sv[LOOK];
+                ST sv[LOOK];
 #pragma unroll
-                for (int j = 0; j < LOOK; j++) sv[j] = (p - j) >= 0 ? ld_state(state + (u64) (p - j) * RADIX + d) : 0x80000000u /* FLAG_INC, value 0: nothing before tile 0 */;
+                for (int j = 0; j < LOOK; j++) sv[j] = (p - j) >= 0 ? ld_state(state + (u64) (p - j) * RADIX + d) : State<ST>::INC /* value 0: nothing before tile 0 */;
                 int used = 0;
 #pragma unroll
                 for (int j = 0; j < LOOK; j++) {
                     if (!done && used == j) {
-                        const u32 f = sv[j] & FLAG_MASK;
-                        if (f != 0) { excl += sv[j] & VAL_MASK; used = j + 1; if (f == FLAG_INC) done = true; }
+                        const ST f = sv[j] & State<ST>::FLAGS;
+                        if (f != 0) { excl += sv[j] & State<ST>::VAL; used = j + 1; if (f == State<ST>::INC) done = true; }
                     }
                 }
                 p -= used;   // first predecessor that had not published yet is polled again
             }
-            st_state(state + (u64) tile * RADIX + d, FLAG_INC | (u32) (excl + run));
+            st_state(state + (u64) tile * RADIX + d, (ST) (State<ST>::INC | (ST) (excl + run)));
         }
         // exclusive scan of the tile's digit counts over d (8 warps of 32 digits)
         incl = run;
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(BLOCK_T) onesweep_persistent_kernel(const u64 
             const int d = tid;
 #pragma unroll
             for (int w = 0; w < WARPS_T; w++) run += S.warpHist[w][d];
-            st_state(tileState + (u64) tile * RADIX + d, (tile == 0 ? FLAG_INC : FLAG_AGG) | run);
+            st_state(tileState + (u64) tile * RADIX + d, (tile == 0 ? State<u32>::INC : State<u32>::AGG) | run);
             incl = run;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
@@ -396,13 +403,13 @@ __global__ void __launch_bounds__(BLOCK_T) onesweep_persistent_kernel(const u64 
 #pragma unroll
                     for (int j = 0; j < LOOK; j++) {
                         if (!done && used == j) {
-                            const u32 f = sv[j] & FLAG_MASK;
-                            if (f != 0) { excl += sv[j] & VAL_MASK; used = j + 1; if (f == FLAG_INC) done = true; }
+                            const u32 f = sv[j] & State<u32>::FLAGS;
+                            if (f != 0) { excl += sv[j] & State<u32>::VAL; used = j + 1; if (f == State<u32>::INC) done = true; }
                         }
                     }
                     p -= used;
                 }
-                st_state(state + (u64) tile * RADIX + d, FLAG_INC | (u32) (excl + run));
+                st_state(state + (u64) tile * RADIX + d, State<u32>::INC | (u32) (excl + run));
             }
             S.delta[d] = binBase[d] + excl - tileOff;
         }
@@ -473,6 +480,16 @@ inline void launch_pass(cudaStream_t st, const u64 *ki, u64 *ko, const u64 *vi, 
     const u64 tiles = (n + SM::TILE_T - 1) / SM::TILE_T;
     onesweep_kernel<BLOCK_T, ITEMS_T, HAS_VAL><<<(unsigned) tiles, BLOCK_T, sizeof(SM), st>>>(ki, ko, vi, vo, n, p, binBase, tileState, ticket);
 }
+// same pass with 64-bit tile states: 2^30 records and more (the workspace holds twice the state bytes then)
+template <int BLOCK_T, int ITEMS_T, bool HAS_VAL>
+inline void launch_pass_wide(cudaStream_t st, const u64 *ki, u64 *ko, const u64 *vi, u64 *vo, u64 n, const Pass &p, const unsigned long long *binBase,
+                             u32 *tileState, u32 *ticket) {
+    typedef SweepSmem<BLOCK_T, ITEMS_T, HAS_VAL> SM;
+    static bool attrSet = false;
+    if (!attrSet) { cudaFuncSetAttribute(onesweep_kernel<BLOCK_T, ITEMS_T, HAS_VAL, false, u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(SM)); attrSet = true; }
+    const u64 tiles = (n + SM::TILE_T - 1) / SM::TILE_T;
+    onesweep_kernel<BLOCK_T, ITEMS_T, HAS_VAL, false, u64><<<(unsigned) tiles, BLOCK_T, sizeof(SM), st>>>(ki, ko, vi, vo, n, p, binBase, (u64 *) tileState, ticket);
+}
 
 // routing pass (send side of the all-to-all): digits = destination ranks, outputs = peer-mapped segment bases (device tables)
 inline void launch_route_pass(cudaStream_t st, const u64 *ki, const u64 *vi, u64 n, const Pass &p, const unsigned long long *zeroBase,
@@ -516,9 +533,10 @@ inline int radix_sort(cudaStream_t st, Workspace &ws, u64 *keysA, u64 *keysB, u6
                       u64 **outKeys, u64 **outVals, int smCount, int variant = -1, cudaEvent_t *passEvents = nullptr /*[2*plan.n]*/) {
     *outKeys = keysA; *outVals = valsA;
     if (n == 0 || plan.n == 0) return 0;
-    if (n > MAX_N || tiles_for(n) > ws.tilesCap || plan.n > MAX_PASSES) return -1;
+    const bool wide = n > SMALL_N;   // 64-bit tile states: only the two default tile shapes are built for them
+    if (n > MAX_N || tiles_for(n) * (wide ? 2 : 1) > ws.tilesCap || plan.n > MAX_PASSES) return -1;
     for (int p = 0; p < plan.n; p++) if (plan.p[p].word != 0) return -1;   // digits come from the key word
-    if (variant < 0) variant = default_variant(valsA != nullptr);
+    if (variant < 0 || wide) variant = default_variant(valsA != nullptr);
     int launches = 0;
     cudaMemsetAsync(ws.hist, 0, sizeof(unsigned long long) * MAX_PASSES * RADIX, st);
     int hb = smCount * 8;
@@ -529,10 +547,12 @@ inline int radix_sort(cudaStream_t st, Workspace &ws, u64 *keysA, u64 *keysB, u6
     launches += 2;
     u64 *ki = keysA, *ko = keysB, *vi = valsA, *vo = valsB;
     for (int p = 0; p < plan.n; p++) {
-        cudaMemsetAsync(ws.tileState, 0, tiles_for(n) * RADIX * sizeof(u32), st);
+        cudaMemsetAsync(ws.tileState, 0, tiles_for(n) * RADIX * sizeof(u32) * (wide ? 2 : 1), st);
         cudaMemsetAsync(ws.ticket, 0, sizeof(u32), st);
         if (passEvents) cudaEventRecord(passEvents[2 * p], st);
-        launch_variant(variant, valsA != nullptr, st, ki, ko, vi, vo, n, plan.p[p], ws.hist + p * RADIX, ws.tileState, ws.ticket, smCount);
+        if (!wide) launch_variant(variant, valsA != nullptr, st, ki, ko, vi, vo, n, plan.p[p], ws.hist + p * RADIX, ws.tileState, ws.ticket, smCount);
+        else if (valsA) launch_pass_wide<256, 16, true>(st, ki, ko, vi, vo, n, plan.p[p], ws.hist + p * RADIX, ws.tileState, ws.ticket);
+        else launch_pass_wide<512, 16, false>(st, ki, ko, vi, vo, n, plan.p[p], ws.hist + p * RADIX, ws.tileState, ws.ticket);
         if (passEvents) cudaEventRecord(passEvents[2 * p + 1], st);
         launches++;
         u64 *t = ki; ki = ko; ko = t;
