@@ -440,8 +440,15 @@ def main():
         line["stage_ms"] = {k: st[k] for k in st if k.startswith("ms_")}
         line["counters"] = {k: st[k] for k in ("n_seqs", "n_bases", "n_records", "n_grouped", "n_hits", "n_alns", "sort1_passes", "sort2_passes")}
     else:
-        line["roofline"] = {"bound": "hbm", "kernel": "see the n_gpus=1 line (same kernels per rank)", "achieved": None, "peak": peak, "unit": "GB/s",
-                            "frac": None, "traffic": None, "peak_source": peak_src}
+        # same dominant kernel per rank: the sort-1 passes over the records this rank received (rank 0's launches of the last step)
+        launches1 = max(1, st["n_sort1_pass_launches"])
+        per_launch_bytes = 2 * 16 * st["sort1_records"]
+        per_launch_ms = st["ms_sort1_passes"] / launches1
+        ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None
+        line["roofline"] = {"bound": "hbm", "kernel": "cdgsort::onesweep_kernel<256,16,true> on rank 0 (sort 1 of the received records, %d launches per step, %.3f ms each, "
+                                      "%d records x 32 B)" % (launches1, per_launch_ms, st["sort1_records"]),
+                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                            "traffic": ONESWEEP_TRAFFIC_RATIO * per_launch_bytes if ach else None, "peak_source": peak_src}
         line["phase_ms_rank0"] = {k: round(v, 2) for k, v in last.get("phase_ms", {}).items()}
         line["exchange"] = {"records_sent_per_rank": last.get("sent"), "grouped_sent_per_rank": last.get("sent2"),
                             "nvlink_bytes_per_rank_per_step": int(16 * (last.get("sent") or 0) + 8 * (last.get("sent2") or 0))}
