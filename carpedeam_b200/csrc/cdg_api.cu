@@ -151,14 +151,6 @@ __global__ void __launch_bounds__(256) max_len_kernel(const u32 *__restrict__ le
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
-struct NonSentinelF { const u64 *keys; __device__ u32 operator()(u64 i) const { return keys[i] != CDG_SENTINEL ? 1u : 0u; } };
-__global__ void __launch_bounds__(256) compact_pairs_kernel(const u64 *__restrict__ k, const u64 *__restrict__ v, const u64 *__restrict__ prefix, u64 n,
-                                                            u64 *__restrict__ ko, u64 *__restrict__ vo) {
-    u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && k[i] != CDG_SENTINEL) { ko[prefix[i]] = k[i]; vo[prefix[i]] = v[i]; }
-}
-struct CapacityF { const u32 *len; int k, kps; float scale; __device__ u32 operator()(u64 i) const { return cdgkmer::kmer_capacity(len[i], k, kps, scale); } };
-
 template <class F>
 __global__ void __launch_bounds__(cdgscan::BLOCK) prefix_write_kernel(F f, u64 n, const unsigned long long *__restrict__ tileSums, u64 *__restrict__ out) {
     __shared__ u32 shWarp[cdgscan::BLOCK / 32 + 1];

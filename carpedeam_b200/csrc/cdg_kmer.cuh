@@ -220,12 +220,12 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
         smN = meta[seqN];
     };
     if (itLo + gwarp < itHi) fetch(itLo + gwarp);
-    for (u64 it = itLo + gwarp; it < itHi; it += nwarps) {
+    for (u64 cur = itLo + gwarp; cur < itHi; cur += nwarps) {
         const SeqMeta sm = smN;   // one 16-byte load: length and first word
         const u32 myRank = rankN;
         const u64 slotAbs = slotN;
         const u64 seq = seqN;
-        if (it + nwarps < itHi) fetch(it + nwarps);
+        if (cur + nwarps < itHi) fetch(cur + nwarps);
         const u32 L = sm.lenFlags & META_LEN;
         if (!is_short_seq(L, P.k, P.kmersPerSeq, P.scale)) continue;   // handled by extract_long_kernel
         if (myRank < P.posLo || myRank >= P.posHi) continue;            // not in this rank's slice
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
         for (u32 s = written + lane; s < cap; s += 32) { mainKeys[slot0 + s] = CDG_SENTINEL; mainVals[slot0 + s] = 0; }
         localEmitted += written;
         // next sequence's packed words towards L1 while this one's records drain
-        if (lane < 2 && it + nwarps < itHi) {
+        if (lane < 2 && cur + nwarps < itHi) {
             const void *pw = lane == 0 ? (const void *) (words + smN.wordOff) : (const void *) (xmask + smN.wordOff);
             asm volatile("prefetch.global.L1 [%0];" :: "l"(pw));
         }
