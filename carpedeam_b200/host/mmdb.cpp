@@ -89,3 +89,15 @@ void DbWriter::close() {
 }
 
 }   // namespace cdh
+
+// ---- C entry point for the CPU test-suite: read a database, write it again through DbWriter, return the entry count ----
+extern "C" long cdh_db_roundtrip(const char *inPath, const char *outPath, int *dbtypeOut) {
+    cdh::Db db;
+    cdh::open_db(inPath, db);
+    cdh::DbWriter w(outPath, db.dbtype);
+    for (size_t i = 0; i < db.size(); i++)
+        w.write((const char *) db.data.data() + db.offsets[i], db.lengths[i] ? db.lengths[i] - 1 : 0, db.keys[i], db.ext[i]);
+    w.close();
+    if (dbtypeOut) *dbtypeOut = db.dbtype;
+    return (long) db.size();
+}

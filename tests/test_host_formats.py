@@ -58,3 +58,65 @@ def test_aln_lines_format_and_parse(host, name):
                 assert s.value == np.float32(float(sid_txt))
             checked += 1
     assert checked > 5000
+
+
+def _write_db(path, keys, payloads, exts, dbtype, split=1, shuffle=False):
+    """an MMseqs2 database as the reference's DBWriter leaves it: data file(s) (`split` > 1: per-thread files db.0, db.1, ...
+    with offsets over their concatenation), 4-column index, 4-byte dbtype"""
+    import struct
+    order = list(range(len(keys)))
+    if shuffle:
+        np.random.default_rng(0).shuffle(order)
+    blobs = [b""] * split
+    rows = {}
+    per = (len(order) + split - 1) // split
+    offset_base = [0] * split
+    for j, i in enumerate(order):
+        f = min(j // per, split - 1)
+        rows[keys[i]] = (f, len(blobs[f]), len(payloads[i]) + 1, exts[i])
+        blobs[f] += payloads[i] + b"\0"
+    for f in range(1, split):
+        offset_base[f] = offset_base[f - 1] + len(blobs[f - 1])
+    for f in range(split):
+        with open(path if split == 1 else "%s.%d" % (path, f), "wb") as fh:
+            fh.write(blobs[f])
+    with open(path + ".index", "w") as fh:
+        for k in (sorted(rows) if not shuffle else list(rows)):
+            f, off, ln, e = rows[k]
+            fh.write("%d\t%d\t%d\t%d\n" % (k, offset_base[f] + off, ln, e))
+    with open(path + ".dbtype", "wb") as fh:
+        fh.write(struct.pack("<i", dbtype))
+
+
+def _read_db(path):
+    data = open(path, "rb").read()
+    out = {}
+    for line in open(path + ".index"):
+        k, off, ln, e = [int(x) for x in line.split()]
+        out[k] = (data[off:off + ln - 1], e)
+    return out
+
+
+@pytest.mark.parametrize("split,shuffle", [(1, False), (3, False), (1, True)])
+def test_db_reader_writer_round_trip(tmp_path, split, shuffle):
+    """mmdb.cpp reads what the reference writes (single or per-thread data files, index in any order, CarpeDeam's ext column)
+    and writes what the reference reads: same keys, payloads, ext flags and dbtype after a read -> write round trip"""
+    import carpedeam_b200 as cd
+    cd.build()
+    H = C.CDLL(cd.HOST_LIB_PATH)
+    H.cdh_db_roundtrip.restype = C.c_long
+    H.cdh_db_roundtrip.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+    keys, payloads, exts = load_golden("assembly_reads_4")      # reads and ext-flagged contigs
+    keys, payloads, exts = keys[:3000], payloads[:3000], exts[:3000]
+    src = str(tmp_path / "in"); dst = str(tmp_path / "out")
+    _write_db(src, keys, payloads, exts, 1, split=split, shuffle=shuffle)
+    t = C.c_int()
+    n = H.cdh_db_roundtrip(src.encode(), dst.encode(), C.byref(t))
+    assert n == len(keys) and t.value == 1
+    got = _read_db(dst)
+    assert sorted(got) == keys
+    assert any(exts) and not all(exts)
+    for k, p, e in zip(keys, payloads, exts):
+        assert got[k] == (p, e)
+    idx_keys = [int(l.split()[0]) for l in open(dst + ".index")]
+    assert idx_keys == sorted(idx_keys)          # DBWriter::close sorts the index by key
