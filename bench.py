@@ -421,7 +421,7 @@ def main():
             "dtype": "u8/int64 (+f64 likelihoods)", "data": data_note,
             "config": {"workload": workload, "l2": "inputs larger than L2 (k-mer records of one pass: GBs)",
                        "parallelism": "single GPU" if world == 1 else "k-mer records owned by hash range, %d ranks, %s" % (
-                           world, "partition kernel writes into peer memory over NVLink (CUDA IPC)" if args.exchange == "p2p" else "NCCL all-to-all")},
+                           world, "partition kernel writes into peer memory over NVLink (CUDA IPC)" if (sharded.exchange if sharded else args.exchange) == "p2p" else "NCCL all-to-all")},
             "e2e": {"value": e2e_val, "unit": "Mreads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_step},
             "gpu_launches": int(launches), "clocks": clocks_summary(samples)}
     if world == 1:

@@ -282,6 +282,30 @@ class ShardedIteration:
         L.cdg_mg_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         self.L = L
+        if exchange == "p2p" and comm.world > 1:
+            self._probe_peer_memory()
+
+    def _probe_peer_memory(self):
+        """Collective start-up check: can every rank map every peer's receive buffer (CUDA IPC needs all GPUs visible to all
+        processes and a shared IPC namespace)?  If any rank cannot, ALL ranks switch to the NCCL exchange — loudly — instead of
+        failing in the middle of the first iteration."""
+        import sys
+        ok = 1
+        try:
+            r2 = C.c_void_p()
+            self.ctx._ck(self.L.cdg_mg_recv_grouped(self.ctx._h, 1, C.byref(r2)), "cdg_mg_recv_grouped")      # allocates the buffer
+            self._map_peers((4,))
+        except Exception as e:      # noqa: BLE001 - any failure means "no peer memory here"
+            ok = 0
+            print("carpedeam_b200.multigpu: rank %d cannot map peer memory (%s)" % (self.comm.rank, e), file=sys.stderr, flush=True)
+        flags = self.comm.all_gather_rows([ok])
+        if not all(f[0] for f in flags):
+            for peer in range(self.comm.world):
+                if peer != self.comm.rank:
+                    self.L.cdg_mg_ipc_close(self.ctx._h, 4, peer)
+            self.exchange = "nccl"
+            if self.comm.rank == 0:
+                print("carpedeam_b200.multigpu: peer-memory exchange unavailable, using the NCCL all-to-all exchange", file=sys.stderr, flush=True)
 
     def _t(self, ptr, n):
         torch = self.comm.torch
