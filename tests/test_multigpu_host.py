@@ -143,3 +143,60 @@ def test_thread_comm_virtual_ranks_cpu():
     for t in ts:
         t.join(60)
     assert not errors, errors
+
+
+def test_peer_memory_probe_falls_back_collectively():
+    """if ONE rank cannot map its peers (CUDA IPC unavailable), EVERY rank must switch to the NCCL exchange: the decision is an
+    all-gather of the per-rank outcome.  Driven here with two thread ranks and a stub library in which rank 1 fails."""
+    import threading
+
+    import torch
+
+    from carpedeam_b200.multigpu import LocalWorld, ShardedIteration, ThreadComm
+    lw = LocalWorld(2)
+    out, errors = {}, []
+
+    class StubCtx:
+        _h = None
+
+        def _ck(self, rc, what):
+            if rc != 0:
+                raise RuntimeError(what + " failed")
+
+    class StubLib:
+        def __init__(self, rank, fail):
+            self.rank, self.fail, self.closed = rank, fail, []
+
+        def cdg_mg_recv_grouped(self, h, total, ptr):
+            return 0
+
+        def cdg_mg_ipc_export(self, h, which, buf):
+            return 0
+
+        def cdg_mg_ipc_open(self, h, which, peer, buf):
+            return -1 if self.fail else 0
+
+        def cdg_mg_ipc_close(self, h, which, peer):
+            self.closed.append((which, peer))
+            return 0
+
+    def worker(rank, fail_rank):
+        try:
+            sh = ShardedIteration.__new__(ShardedIteration)
+            sh.ctx, sh.comm, sh.exchange = StubCtx(), ThreadComm(lw, rank, torch.device("cpu")), "p2p"
+            sh.L = StubLib(rank, fail=(rank == fail_rank))
+            sh._probe_peer_memory()
+            out[(fail_rank, rank)] = (sh.exchange, sh.L.closed)
+        except Exception as e:
+            errors.append(repr(e)); lw.barrier.abort()
+
+    for fail_rank in (1, None):
+        ts = [threading.Thread(target=worker, args=(r, fail_rank)) for r in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(60)
+    assert not errors, errors
+    assert out[(1, 0)][0] == "nccl" and out[(1, 1)][0] == "nccl"          # both ranks, although only rank 1 failed
+    assert out[(1, 0)][1] == [(4, 1)] and out[(1, 1)][1] == [(4, 0)]      # mappings dropped
+    assert out[(None, 0)][0] == "p2p" and out[(None, 1)][0] == "p2p" and out[(None, 0)][1] == []
