@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
         msrc = os.path.join(hsrc_dir, "main_stages.cpp")
         if os.path.exists(msrc) and (force or not os.path.exists(STAGE_BIN) or any(os.path.getmtime(d) > os.path.getmtime(STAGE_BIN) for d in hdeps + [LIB_PATH])):
             os.makedirs(os.path.dirname(STAGE_BIN), exist_ok=True)
-            subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", STAGE_BIN, msrc] + hsrc +
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-o", STAGE_BIN, msrc] + hsrc +
                            ["-L" + HERE, "-lcarpedeam_gpu", "-Wl,-rpath," + HERE], check=True)
     return LIB_PATH
 
@@ -91,6 +91,16 @@ class Pairs(C.Structure):
                 ("q_end", C.c_void_p), ("db_start", C.c_void_p), ("db_end", C.c_void_p), ("max_aln", C.c_void_p)]
 
 
+class AlnsCompact(C.Structure):
+    _fields_ = [("n_queries", C.c_uint64), ("n_alns", C.c_uint64), ("first_query", C.c_uint64), ("count", C.POINTER(C.c_uint32)),
+                ("target", C.POINTER(C.c_uint32)), ("width", C.c_int32), ("score", C.c_void_p), ("id_cnt", C.c_void_p), ("q_start", C.c_void_p),
+                ("db_start", C.c_void_p), ("aln_len_rev", C.c_void_p), ("db_residues", C.c_uint64)]
+
+
+class Patches(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("entry", C.POINTER(C.c_uint64))]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_seqs", C.c_uint64), ("n_bases", C.c_uint64), ("n_records", C.c_uint64), ("n_grouped", C.c_uint64),
                 ("n_hits", C.c_uint64), ("n_alns", C.c_uint64), ("sort1_passes", C.c_uint32), ("sort2_passes", C.c_uint32),
@@ -126,6 +136,10 @@ def lib():
         L.cdg_set_pair_model.argtypes = [C.c_void_p, C.POINTER(PairModel)]
         L.cdg_pair_loglik.argtypes = [C.c_void_p, C.POINTER(Pairs), C.c_void_p, C.c_void_p]
         L.cdg_pair_loglik_consensus.argtypes = [C.c_void_p, C.POINTER(Pairs), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.cdg_upload_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
+        L.cdg_iteration_compact.argtypes = [C.c_void_p, C.POINTER(IterParams), C.POINTER(AlnsCompact), C.POINTER(Patches), C.POINTER(C.c_uint64)]
+        L.cdg_export_alns_compact.argtypes = [C.c_void_p, C.POINTER(AlnsCompact)]
+        L.cdg_export_patches.argtypes = [C.c_void_p, C.POINTER(Patches)]
         L.cdg_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.cdg_test_radix_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
         L.cdg_test_hash_revcomp.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -144,8 +158,53 @@ def hostlib():
         H.cdh_build_damage.restype = C.c_int
         H.cdh_build_pair_model.argtypes = [C.c_char_p, C.c_double, C.c_float, C.c_float, C.POINTER(PairModel), C.c_char_p, C.c_size_t]
         H.cdh_build_pair_model.restype = C.c_int
+        H.cdh_packed_words.argtypes = [C.c_void_p, C.c_uint64]; H.cdh_packed_words.restype = C.c_uint64
+        H.cdh_pack_seqs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
+        H.cdh_pack_seqs.restype = C.c_int
+        H.cdh_expanded_lines.argtypes = [C.POINTER(AlnsCompact)]; H.cdh_expanded_lines.restype = C.c_uint64
+        H.cdh_expand_alns.argtypes = [C.POINTER(AlnsCompact)] + [C.c_void_p] * 12; H.cdh_expand_alns.restype = C.c_int
+        H.cdh_apply_patches.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(Patches)]; H.cdh_apply_patches.restype = C.c_int
         _hostlib = H
     return _hostlib
+
+
+def pack_seqs(blob, off, lens, with_mask=True):
+    """DB bytes -> (words u64, nmask u32 or None, has_n): the 2-bit packed set cdg_upload_packed takes (host/pack.cpp).
+    Raises CdgError when a letter other than upper-case A,C,G,T,N occurs."""
+    blob = np.ascontiguousarray(blob, np.uint8); off = np.ascontiguousarray(off, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+    H = hostlib()
+    nw = int(H.cdh_packed_words(_ptr(lens), len(lens)))
+    words = np.zeros(nw, np.uint64)
+    nmask = np.zeros(nw, np.uint32) if with_mask else None
+    has_n = C.c_int(0)
+    err = C.create_string_buffer(512)
+    if H.cdh_pack_seqs(_ptr(blob), _ptr(off), _ptr(lens), len(lens), _ptr(words), _ptr(nmask), C.byref(has_n), err, 512) != 0:
+        raise CdgError("pack_seqs: " + err.value.decode())
+    return words, nmask, bool(has_n.value)
+
+
+def expand_alns(compact, lens):
+    """cdg_alns_compact -> the dict Context._alns gives for the same alignments restricted to keep == 1 (host/pack.cpp)."""
+    lens = np.ascontiguousarray(lens, np.uint32)
+    H = hostlib()
+    M = int(H.cdh_expanded_lines(C.byref(compact)))
+    nq = int(compact.n_queries)
+    out = dict(line_off=np.zeros(nq + 1, np.uint64), tgt=np.zeros(M, np.uint32), keep=np.zeros(M, np.uint8), score=np.zeros(M, np.int32),
+               bits=np.zeros(M, np.int32), evalue=np.zeros(M, np.float64), seqid=np.zeros(M, np.float32), qs=np.zeros(M, np.int32),
+               qe=np.zeros(M, np.int32), ds=np.zeros(M, np.int32), de=np.zeros(M, np.int32))
+    rc = H.cdh_expand_alns(C.byref(compact), _ptr(lens), *[_ptr(out[k]) for k in ("line_off", "tgt", "keep", "score", "bits", "evalue", "seqid", "qs",
+                                                                                   "qe", "ds", "de")])
+    if rc != 0:
+        raise CdgError("cdh_expand_alns failed (%d)" % rc)
+    return out
+
+
+def apply_patches(blob, patches):
+    """corrected reads = the input bytes with the patches applied (host/pack.cpp)"""
+    out = np.ascontiguousarray(blob, np.uint8).copy()
+    if hostlib().cdh_apply_patches(_ptr(out), out.nbytes, C.byref(patches)) != 0:
+        raise CdgError("cdh_apply_patches: offset outside the data")
+    return out
 
 
 def _ptr(a):
@@ -229,6 +288,37 @@ class Context:
         self.n = n; self.data_bytes = nbytes
         self._ck(lib().cdg_upload_seqs_async(self._h, C.c_void_p(blob_ptr), nbytes, C.c_void_p(off_ptr), C.c_void_p(len_ptr),
                                              C.c_void_p(ext_ptr) if ext_ptr else None, n), "cdg_upload_seqs_async")
+
+    def upload_packed(self, words, nmask, lens, ext=None):
+        """cdg_upload_packed from numpy arrays (kept alive on the context until the next upload)"""
+        words = np.ascontiguousarray(words, np.uint64); lens = np.ascontiguousarray(lens, np.uint32)
+        nmask = None if nmask is None else np.ascontiguousarray(nmask, np.uint32)
+        ext = None if ext is None else np.ascontiguousarray(ext, np.uint8)
+        self._keep = [words, nmask, lens, ext]
+        self.n = len(lens); self.data_bytes = int(lens.astype(np.uint64).sum()) + 2 * len(lens)
+        self._ck(lib().cdg_upload_packed(self._h, _ptr(words), _ptr(nmask), _ptr(lens), _ptr(ext), len(lens), len(words)), "cdg_upload_packed")
+
+    def upload_packed_raw(self, words_ptr, nmask_ptr, len_ptr, ext_ptr, n, n_words):
+        self.n = n
+        self._ck(lib().cdg_upload_packed(self._h, C.c_void_p(words_ptr), C.c_void_p(nmask_ptr) if nmask_ptr else None, C.c_void_p(len_ptr),
+                                         C.c_void_p(ext_ptr) if ext_ptr else None, n, n_words), "cdg_upload_packed")
+
+    def iteration_compact(self, ip, alns=None, patches=None):
+        """cdg_iteration_compact; alns / patches are AlnsCompact / Patches structures filled with views of the library's pinned buffers"""
+        ch = C.c_uint64()
+        self._ck(lib().cdg_iteration_compact(self._h, C.byref(ip), C.byref(alns) if alns is not None else None,
+                                             C.byref(patches) if patches is not None else None, C.byref(ch)), "cdg_iteration_compact")
+        return ch.value
+
+    def export_alns_compact(self):
+        a = AlnsCompact()
+        self._ck(lib().cdg_export_alns_compact(self._h, C.byref(a)), "cdg_export_alns_compact")
+        return a
+
+    def export_patches(self):
+        p = Patches()
+        self._ck(lib().cdg_export_patches(self._h, C.byref(p)), "cdg_export_patches")
+        return p
 
     @staticmethod
     def _hits(h):

@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(256) rescore_kernel(
     const u32 *__restrict__ lineQ, const u32 *__restrict__ lineT, const i32 *__restrict__ linePref, const u16 *__restrict__ lineDiag,
     u64 M, RescoreParams P,
     u8 *__restrict__ keep, i32 *__restrict__ score, i32 *__restrict__ bits, double *__restrict__ evalue, float *__restrict__ seqId,
-    i32 *__restrict__ qS, i32 *__restrict__ qE, i32 *__restrict__ dS, i32 *__restrict__ dE, unsigned long long *__restrict__ keptCount) {
+    i32 *__restrict__ qS, i32 *__restrict__ qE, i32 *__restrict__ dS, i32 *__restrict__ dE, u32 *__restrict__ idCnt,
+    unsigned long long *__restrict__ keptCount) {
     u64 l = (u64) blockIdx.x * blockDim.x + threadIdx.x;
     u32 kept = 0;
     if (l < M) {
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(
         const bool hasEvalue = ev <= P.evalThr;
         const bool k = isIdentity || (hasSeqId && hasEvalue);   // rescorediagonal.cpp:304-314 with -c 0, --min-aln-len 0
         keep[l] = k ? 1 : 0; score[l] = distance; bits[l] = bitScore; evalue[l] = ev; seqId[l] = sid;
-        qS[l] = qs; qE[l] = qe; dS[l] = ds; dE[l] = de;
+        qS[l] = qs; qE[l] = qe; dS[l] = ds; dE[l] = de; idCnt[l] = mx.idCnt;
         kept = k ? 1u : 0u;
     }
     u32 b = __ballot_sync(0xffffffffu, kept);

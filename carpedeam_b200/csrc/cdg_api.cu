@@ -11,6 +11,7 @@
 #include "../../include/carpedeam_gpu.h"
 #include "cdg_align.cuh"
 #include "cdg_common.cuh"
+#include "cdg_export.cuh"
 #include "cdg_kmer.cuh"
 #include "cdg_pairlik.cuh"
 #include "cdg_sort.cuh"
@@ -93,11 +94,16 @@ struct cdg_ctx {
     unsigned char peerHandle[CDG_IPC_BUFFERS][CDG_MAX_WORLD][CDG_IPC_HANDLE_BYTES] = {};
     u64 mgSlice = 0; u64 *mgMainK = nullptr, *mgMainV = nullptr, *mgIdK = nullptr, *mgIdV = nullptr;   // phase-1 arrays awaiting the scatter
     // lines / alignments
-    DevBuf dLineOff, dLineQ, dLineT, dLinePref, dLineDiag, dKeep, dScore, dBits, dEvalue, dSeqId, dQS, dQE, dDS, dDE, dLineSel;
+    DevBuf dLineOff, dLineQ, dLineT, dLinePref, dLineDiag, dKeep, dScore, dBits, dEvalue, dSeqId, dQS, dQE, dDS, dDE, dLineSel, dIdCnt;
     HostBuf hLineOff, hLineT, hKeep, hScore, hBits, hEvalue, hSeqId, hQS, hQE, hDS, hDE;
+    // compact exports (cdg_alns_compact / cdg_patches): device staging + pinned host copies
+    DevBuf dCmpCount, dCmpTarget, dCmpFields, dPatches;
+    HostBuf hCmpCount, hCmpTarget, hCmpFields, hPatches;
+    u64 nCompact = 0, nChangedLast = 0; bool correctedValid = false; double dbResUsed = 0; bool monotoneOffsets = true; bool packedUpload = false;
     u64 nLines = 0, nKept = 0; bool linesValid = false, alnsValid = false, alnsFromText = false;
     // correction
-    DevBuf dTables, dOut, dLik, dWideList, dRecvK, dRecvV, dRecv2, dQList, dPow31; bool damageSet = false;
+    DevBuf dTables, dOut, dLik, dWideList, dRecvK, dRecvV, dRecv2, dQList, dPow31, dKey2Big; bool damageSet = false;
+    u64 headCap = 0;   // records of a neighbour's head run that fit behind sortedKey2 (cdg_mg_sort2 / cdg_mg_head_area)
     // pair likelihood (a19)
     DevBuf dPairModel, dPairIn, dPairCons, dPairOut; bool pairModelSet = false;
 };
@@ -113,7 +119,10 @@ int fail(cdg_ctx *c, int code, const char *fmt, ...) {
 #define CK(call)                                                                                             \
     do {                                                                                                     \
         cudaError_t e_ = (call);                                                                             \
-        if (e_ != cudaSuccess) return fail(ctx, CDG_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+        if (e_ != cudaSuccess) {                                                                             \
+            (void) cudaGetLastError(); /* a recovered failure (IPC probe, OOM + retry) must not poison the next launch check */ \
+            return fail(ctx, CDG_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+        }                                                                                                    \
     } while (0)
 // launch check; with CDG_SYNC_DEBUG=1 in the environment every check also waits for the stream, so that an asynchronous kernel
 // fault is reported at the launch site that caused it (compute-sanitizer is not always available)
@@ -133,6 +142,7 @@ void rec(cdg_ctx *ctx, int e) { cudaEventRecord(ctx->ev[e], ctx->st); ctx->evVal
 
 struct LenWordsF { const u32 *len; __device__ u32 operator()(u64 i) const { return (len[i] + 31) >> 5; } };
 struct LenBasesF { const u32 *len; __device__ u32 operator()(u64 i) const { return len[i]; } };
+struct LenEntryF { const u32 *len; __device__ u32 operator()(u64 i) const { return len[i] + 2; } };   // BASES + "\n\0"
 struct OrderedCapacityF { const u64 *order; const u32 *len; int k, kps; float scale;
     __device__ u32 operator()(u64 r) const { return cdgkmer::kmer_capacity(len[(u32) order[r]], k, kps, scale); } };
 __global__ void __launch_bounds__(256) order_init_kernel(const u32 *__restrict__ len, u64 n, u32 maxLen, u64 *__restrict__ k, u64 *__restrict__ v) {
@@ -150,6 +160,17 @@ __global__ void __launch_bounds__(256) max_len_kernel(const u32 *__restrict__ le
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+// bit 0: an entry ends beyond the data, bit 1: entries are not laid out in index order
+__global__ void __launch_bounds__(256) layout_check_kernel(const u64 *__restrict__ off, const u32 *__restrict__ len, u64 n, u64 dataBytes, u32 *__restrict__ out) {
+    u32 f = 0;
+    for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) {
+        const u64 e = off[i] + len[i];
+        if (e > dataBytes || e < off[i]) f |= 1u;
+        if (i + 1 < n && off[i + 1] < e) f |= 2u;
+    }
+    f = __reduce_or_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0 && f) atomicOr(out, f);
 }
 template <class F>
 __global__ void __launch_bounds__(cdgscan::BLOCK) prefix_write_kernel(F f, u64 n, const unsigned long long *__restrict__ tileSums, u64 *__restrict__ out) {
@@ -255,10 +276,12 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
                    &ctx->dHitScore, &ctx->dHitDiag, &ctx->dLineOff, &ctx->dLineQ, &ctx->dLineT, &ctx->dLinePref, &ctx->dLineDiag, &ctx->dKeep,
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
                    &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2, &ctx->dQList, &ctx->dPow31,
-                   &ctx->dPairModel, &ctx->dPairIn, &ctx->dPairCons, &ctx->dPairOut, &ctx->dRecvIdK, &ctx->dRecvIdV, &ctx->dRouteTab};
+                   &ctx->dPairModel, &ctx->dPairIn, &ctx->dPairCons, &ctx->dPairOut, &ctx->dRecvIdK, &ctx->dRecvIdV, &ctx->dRouteTab,
+                   &ctx->dIdCnt, &ctx->dCmpCount, &ctx->dCmpTarget, &ctx->dCmpFields, &ctx->dPatches, &ctx->dKey2Big};
     for (DevBuf *b : d) b->release();
     HostBuf *h[] = {&ctx->hHitRep, &ctx->hHitTgt, &ctx->hHitScore, &ctx->hHitDiag, &ctx->hHitDiag16, &ctx->hLineOff, &ctx->hLineT, &ctx->hKeep,
-                    &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE};
+                    &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE,
+                    &ctx->hCmpCount, &ctx->hCmpTarget, &ctx->hCmpFields, &ctx->hPatches};
     for (HostBuf *b : h) b->release();
     for (int i = 0; i < EV_N; i++) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2 * cdgsort::MAX_PASSES; i++) cudaEventDestroy(ctx->passEv[i]);
@@ -279,6 +302,10 @@ static int pack_chunk(cdg_ctx *ctx, u64 seqLo, u64 seqHi) {
     if (seqHi <= seqLo) return 0;
     const u64 cnt = seqHi - seqLo;
     const unsigned pb = (unsigned) std::min<u64>((cnt * 32 + 255) / 256, (u64) ctx->smCount * 16);
+    if (ctx->packedUpload)   // cdg_upload_packed: the words are the input, the DB bytes are rebuilt from them
+        cdgexp::unpack_kernel<<<pb, 256, 0, ctx->st>>>(ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dWordOff.as<u64>(),
+                                                       seqLo, seqHi, ctx->dData.as<u8>(), ctx->dFlags.as<u8>());
+    else
     cdgkmer::pack_kernel<<<pb, 256, 0, ctx->st>>>(ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dWordOff.as<u64>(), seqLo, seqHi,
                                                   ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dFlags.as<u8>());
     cdgalign::meta_kernel<<<(unsigned) ((cnt + 255) / 256), 256, 0, ctx->st>>>(ctx->dOff.as<u64>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dFlags.as<u8>(),
@@ -305,7 +332,7 @@ static int upload_impl(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, c
     if (n >= (1ull << 31)) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_upload_seqs: more than 2^31 sequences per context");
     CK(cudaSetDevice(ctx->device));
     if (!ctx->pending.empty()) { CK(cudaStreamSynchronize(ctx->copySt)); ctx->pending.clear(); }   // an upload nobody consumed
-    ctx->hitsValid = ctx->linesValid = ctx->alnsValid = false;
+    ctx->hitsValid = ctx->linesValid = ctx->alnsValid = false; ctx->packedUpload = false; ctx->correctedValid = false;
     ctx->n = n; ctx->dataBytes = data_bytes; ctx->qLo = 0; ctx->nQ = n;
     CK(ctx->dData.reserve(data_bytes + 64));
     CK(ctx->dOff.reserve(n * 8)); CK(ctx->dLen.reserve(n * 4)); CK(ctx->dExt.reserve(n)); CK(ctx->dFlags.reserve(n));
@@ -365,13 +392,20 @@ static int upload_impl(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, c
     // facts needed for sizing: total bases, longest sequence, packed words (all reduced on the device, from the lengths alone)
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
     CK(cudaMemsetAsync(sc + SC_WIDE, 0, 8, ctx->st));
+    CK(cudaMemsetAsync(sc + SC_QLIST, 0, 8, ctx->st));
     max_len_kernel<<<ctx->smCount * 4, 256, 0, ctx->st>>>(ctx->dLen.as<u32>(), n, (u32 *) (sc + SC_WIDE));
-    ctx->launches++;
+    // entries must lie inside the data (the kernels index with them); entries that are not in index order are fine for
+    // everything except the per-range exports of the multi-GPU phases (cdg_mg_finish)
+    layout_check_kernel<<<ctx->smCount * 4, 256, 0, ctx->st>>>(ctx->dOff.as<u64>(), ctx->dLen.as<u32>(), n, data_bytes, (u32 *) (sc + SC_QLIST));
+    ctx->launches += 2;
     int rc;
     if ((rc = scan_to(ctx, LenBasesF{ctx->dLen.as<u32>()}, n, ctx->dLikOff.as<u64>(), true))) return rc;
-    u64 total = 0, mx64 = 0;
+    u64 total = 0, mx64 = 0, layout = 0;
     if ((rc = read_scalar(ctx, SC_SCAN, &total))) return rc;
     if ((rc = read_scalar(ctx, SC_WIDE, &mx64))) return rc;
+    if ((rc = read_scalar(ctx, SC_QLIST, &layout))) return rc;
+    if ((u32) layout & 1u) { ctx->n = 0; ctx->pending.clear(); cudaStreamSynchronize(ctx->copySt); return fail(ctx, CDG_ERR_ARG, "cdg_upload_seqs: an entry (offset + length) ends beyond data_bytes"); }
+    ctx->monotoneOffsets = ((u32) layout & 2u) == 0;
     ctx->totalBases = total; ctx->maxLen = (u32) mx64;
     if ((rc = scan_to(ctx, LenWordsF{ctx->dLen.as<u32>()}, n, ctx->dWordOff.as<u64>(), true))) return rc;
     u64 words = 0;
@@ -395,6 +429,54 @@ extern "C" int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_
 extern "C" int cdg_upload_seqs_async(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, const uint64_t *offsets, const uint32_t *lens,
                                      const uint8_t *ext, uint64_t n) {
     return upload_impl(ctx, data, data_bytes, offsets, lens, ext, n, CDG_UPLOAD_CHUNKS);
+}
+
+// 2-bit packed input: the words (and the N mask) travel on the copy stream while the layout scans run; the DB bytes are rebuilt
+// on the device by unpack_kernel when the first consumer needs them (pack_chunk)
+extern "C" int cdg_upload_packed(cdg_ctx *ctx, const uint64_t *words, const uint32_t *nmask, const uint32_t *lens, const uint8_t *ext, uint64_t n,
+                                 uint64_t n_words) {
+    if (!ctx) return CDG_ERR_ARG;
+    if (n == 0 || !words || !lens) return fail(ctx, CDG_ERR_ARG, "cdg_upload_packed: empty or NULL input");
+    if (n >= (1ull << 31)) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_upload_packed: more than 2^31 sequences per context");
+    if (n_words >= (1ull << 32)) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_upload_packed: more than 2^32 packed words per context");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->pending.empty()) { CK(cudaStreamSynchronize(ctx->copySt)); ctx->pending.clear(); }
+    ctx->hitsValid = ctx->linesValid = ctx->alnsValid = false; ctx->packedUpload = true; ctx->monotoneOffsets = true; ctx->correctedValid = false;
+    ctx->n = n; ctx->qLo = 0; ctx->nQ = n;
+    CK(ctx->dOff.reserve(n * 8)); CK(ctx->dLen.reserve(n * 4)); CK(ctx->dExt.reserve(n)); CK(ctx->dFlags.reserve(n));
+    CK(ctx->dWordOff.reserve((n + 1) * 8)); CK(ctx->dLikOff.reserve((n + 1) * 8));
+    CK(ctx->dWords.reserve((n_words + 2) * 8)); CK(ctx->dXmask.reserve((n_words + 2) * 4));
+    CK(ctx->dMeta.reserve(n * sizeof(cdgalign::SeqMeta)));
+    CK(cudaMemcpyAsync(ctx->dLen.p, lens, n * 4, cudaMemcpyDefault, ctx->st));
+    if (ext) CK(cudaMemcpyAsync(ctx->dExt.p, ext, n, cudaMemcpyDefault, ctx->st));
+    else CK(cudaMemsetAsync(ctx->dExt.p, 0, n, ctx->st));
+    CK(cudaEventRecord(ctx->evUploadStart, ctx->st));   // work queued earlier may still read the old set
+    CK(cudaStreamWaitEvent(ctx->copySt, ctx->evUploadStart, 0));
+    CK(cudaMemcpyAsync(ctx->dWords.p, words, n_words * 8, cudaMemcpyDefault, ctx->copySt));
+    if (nmask) CK(cudaMemcpyAsync(ctx->dXmask.p, nmask, n_words * 4, cudaMemcpyDefault, ctx->copySt));
+    else CK(cudaMemsetAsync(ctx->dXmask.p, 0, n_words * 4, ctx->copySt));
+    CK(cudaEventRecord(ctx->chunkEv[0], ctx->copySt));
+    ctx->pending.push_back(cdg_ctx::UploadChunk{0, n, ctx->chunkEv[0]});
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    CK(cudaMemsetAsync(sc + SC_WIDE, 0, 8, ctx->st));
+    max_len_kernel<<<ctx->smCount * 4, 256, 0, ctx->st>>>(ctx->dLen.as<u32>(), n, (u32 *) (sc + SC_WIDE));
+    ctx->launches++;
+    int rc;
+    u64 total = 0, mx64 = 0, wordsNeeded = 0, bytes = 0;
+    if ((rc = scan_to(ctx, LenBasesF{ctx->dLen.as<u32>()}, n, ctx->dLikOff.as<u64>(), true))) return rc;
+    if ((rc = read_scalar(ctx, SC_SCAN, &total))) return rc;
+    if ((rc = read_scalar(ctx, SC_WIDE, &mx64))) return rc;
+    if ((rc = scan_to(ctx, LenWordsF{ctx->dLen.as<u32>()}, n, ctx->dWordOff.as<u64>(), true))) return rc;
+    if ((rc = read_scalar(ctx, SC_SCAN, &wordsNeeded))) return rc;
+    if ((rc = scan_to(ctx, LenEntryF{ctx->dLen.as<u32>()}, n, ctx->dOff.as<u64>(), false))) return rc;
+    if ((rc = read_scalar(ctx, SC_SCAN, &bytes))) return rc;
+    if (wordsNeeded != n_words) {
+        cudaStreamSynchronize(ctx->copySt); ctx->pending.clear(); ctx->n = 0;
+        return fail(ctx, CDG_ERR_ARG, "cdg_upload_packed: lens need %llu words, n_words = %llu", (unsigned long long) wordsNeeded, (unsigned long long) n_words);
+    }
+    ctx->totalBases = total; ctx->maxLen = (u32) mx64; ctx->totalWords = n_words; ctx->dataBytes = bytes;
+    CK(ctx->dData.reserve(bytes + 64));
+    return CDG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -709,7 +791,7 @@ static int reserve_lines(cdg_ctx *ctx, u64 M) {
     CK(ctx->dLinePref.reserve((M + 1) * 4)); CK(ctx->dLineDiag.reserve((M + 1) * 2));
     CK(ctx->dKeep.reserve(M + 1)); CK(ctx->dScore.reserve((M + 1) * 4)); CK(ctx->dBits.reserve((M + 1) * 4)); CK(ctx->dEvalue.reserve((M + 1) * 8));
     CK(ctx->dSeqId.reserve((M + 1) * 4)); CK(ctx->dQS.reserve((M + 1) * 4)); CK(ctx->dQE.reserve((M + 1) * 4)); CK(ctx->dDS.reserve((M + 1) * 4));
-    CK(ctx->dDE.reserve((M + 1) * 4)); CK(ctx->dLineSel.reserve(M + 1));
+    CK(ctx->dDE.reserve((M + 1) * 4)); CK(ctx->dLineSel.reserve(M + 1)); CK(ctx->dIdCnt.reserve((M + 1) * 4));
     return 0;
 }
 
@@ -786,10 +868,11 @@ static int run_rescore(cdg_ctx *ctx, const cdg_rescore_params *p) {
             ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dWords.as<u64>(), ctx->dWordOff.as<u64>(), ctx->dFlags.as<u8>(),
             ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(), ctx->dLinePref.as<i32>(), ctx->dLineDiag.as<u16>(), M, R, ctx->dKeep.as<u8>(),
             ctx->dScore.as<i32>(), ctx->dBits.as<i32>(), ctx->dEvalue.as<double>(), ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(), ctx->dQE.as<i32>(),
-            ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), sc + SC_KEPT);
+            ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), ctx->dIdCnt.as<u32>(), sc + SC_KEPT);
         ctx->launches++;
         CKL();
     }
+    ctx->dbResUsed = R.dbRes;
     rec(ctx, EV_RS1);
     ctx->alnsValid = true; ctx->alnsFromText = false;
     return CDG_OK;
@@ -825,6 +908,92 @@ static int export_alns(cdg_ctx *ctx, cdg_alns *out, bool overlap = false) {
     out->score = ctx->hScore.as<i32>(); out->bits = ctx->hBits.as<i32>(); out->evalue = ctx->hEvalue.as<double>(); out->seq_id = ctx->hSeqId.as<float>();
     out->q_start = ctx->hQS.as<i32>(); out->q_end = ctx->hQE.as<i32>(); out->db_start = ctx->hDS.as<i32>(); out->db_end = ctx->hDE.as<i32>();
     return CDG_OK;
+}
+
+
+// ---- compact exports -------------------------------------------------------------------------------------------------------
+// Alignments the reference writes (keep == 1), 14 bytes each when every sequence is shorter than 32768, implicit self lines
+// dropped.  overlap: the device-to-host copies run on the copy stream (the caller finishes with wait_exports()).
+static int export_alns_compact(cdg_ctx *ctx, cdg_alns_compact *out, bool overlap) {
+    if (!ctx->alnsValid || ctx->alnsFromText) return fail(ctx, CDG_ERR_ARG, "compact alignment export needs the alignments of cdg_rescore on this context");
+    const u64 M = ctx->nLines, nQ = ctx->nQ;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    cdgexp::ExportFlag f;
+    f.A = cdgexp::LineArrays{ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(), ctx->dLinePref.as<i32>(), ctx->dKeep.as<u8>(), ctx->dScore.as<i32>(), ctx->dIdCnt.as<u32>(),
+                             ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(), ctx->dQE.as<i32>(), ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), ctx->dMeta.as<SeqMeta>()};
+    const u64 tiles = cdgscan::tiles_for(M);
+    CK(ctx->dTileSums.reserve((tiles + 1) * 8));
+    unsigned long long *ts = ctx->dTileSums.as<unsigned long long>();
+    u64 A = 0, kept = 0;
+    if (M) {
+        cdgscan::tile_sum_kernel<<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, M, ts);
+        cdgscan::tile_scan_kernel<<<1, 1024, 0, ctx->st>>>(ts, tiles, sc + SC_SCAN);
+        ctx->launches += 2;
+        CKL();
+        u64 h[2];
+        CK(cudaMemcpyAsync(&h[0], sc + SC_SCAN, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(&h[1], sc + SC_KEPT, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        A = h[0]; kept = h[1];
+    }
+    ctx->nKept = kept; ctx->nCompact = A;
+    const int width = ctx->maxLen < 32768 ? 2 : 4;
+    const u64 fieldBytes = (A + 8) * (u64) width;   // 5 arrays of A elements, each padded to 16 bytes
+    const u64 stride = (fieldBytes + 15) & ~15ull;
+    CK(ctx->dCmpCount.reserve((nQ + 1) * 4)); CK(ctx->dCmpTarget.reserve((A + 1) * 4)); CK(ctx->dCmpFields.reserve(5 * stride));
+    CK(ctx->hCmpCount.reserve((nQ + 1) * 4)); CK(ctx->hCmpTarget.reserve((A + 1) * 4)); CK(ctx->hCmpFields.reserve(5 * stride));
+    u8 *df = ctx->dCmpFields.as<u8>();
+    if (M) {
+        if (width == 2)
+            cdgexp::compact_write_kernel<u16, short><<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, M, ts, ctx->dCmpTarget.as<u32>(), (u16 *) df, (u16 *) (df + stride),
+                                                                                                     (short *) (df + 2 * stride), (short *) (df + 3 * stride), (u16 *) (df + 4 * stride));
+        else
+            cdgexp::compact_write_kernel<u32, i32><<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, M, ts, ctx->dCmpTarget.as<u32>(), (u32 *) df, (u32 *) (df + stride),
+                                                                                                   (i32 *) (df + 2 * stride), (i32 *) (df + 3 * stride), (u32 *) (df + 4 * stride));
+        ctx->launches++;
+    }
+    if (nQ) { cdgexp::compact_count_kernel<<<(unsigned) ((nQ + 255) / 256), 256, 0, ctx->st>>>(f, ctx->dLineOff.as<u64>(), nQ, ctx->dCmpCount.as<u32>()); ctx->launches++; }
+    CKL();
+    cudaStream_t cs = ctx->st;
+    if (overlap) { CK(cudaEventRecord(ctx->evReady, ctx->st)); CK(cudaStreamWaitEvent(ctx->copySt, ctx->evReady, 0)); cs = ctx->copySt; }
+    if (nQ) CK(cudaMemcpyAsync(ctx->hCmpCount.p, ctx->dCmpCount.p, nQ * 4, cudaMemcpyDeviceToHost, cs));
+    if (A) {
+        CK(cudaMemcpyAsync(ctx->hCmpTarget.p, ctx->dCmpTarget.p, A * 4, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(ctx->hCmpFields.p, ctx->dCmpFields.p, 4 * stride + A * (u64) width, cudaMemcpyDeviceToHost, cs));
+    }
+    if (overlap) { CK(cudaEventRecord(ctx->evCopied, cs)); ctx->copyPending = true; } else CK(cudaStreamSynchronize(cs));
+    const u8 *hf = ctx->hCmpFields.as<u8>();
+    out->n_queries = nQ; out->n_alns = A; out->first_query = ctx->qLo; out->count = ctx->hCmpCount.as<u32>(); out->target = ctx->hCmpTarget.as<u32>();
+    out->width = width; out->score = hf; out->id_cnt = hf + stride; out->q_start = hf + 2 * stride; out->db_start = hf + 3 * stride;
+    out->aln_len_rev = hf + 4 * stride; out->db_residues = (u64) ctx->dbResUsed;
+    return CDG_OK;
+}
+
+// corrected reads of the byte range [b0, b1) as patches (the last cdg_correct's output against the resident input)
+static int export_patches(cdg_ctx *ctx, u64 b0, u64 b1, u64 nChanged, cdg_patches *out) {
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    CK(ctx->dPatches.reserve((nChanged + 1) * 8)); CK(ctx->hPatches.reserve((nChanged + 1) * 8));
+    u64 got = 0;
+    if (nChanged && b1 > b0) {
+        CK(cudaMemsetAsync(sc + SC_SCAN, 0, 8, ctx->st));
+        const u64 chunks = ((b1 + 15) >> 4) - (b0 >> 4);
+        const unsigned blocks = (unsigned) std::min<u64>((chunks + 255) / 256, (u64) ctx->smCount * 16);
+        cdgexp::patch_kernel<<<blocks, 256, 0, ctx->st>>>(ctx->dData.as<u8>(), ctx->dOut.as<u8>(), b0, b1, ctx->dPatches.as<u64>(), nChanged, sc + SC_SCAN);
+        ctx->launches++;
+        CKL();
+        CK(cudaMemcpyAsync(ctx->hPatches.p, ctx->dPatches.p, nChanged * 8, cudaMemcpyDeviceToHost, ctx->st));
+        int rc = read_scalar(ctx, SC_SCAN, &got);
+        if (rc) return rc;
+        if (got != nChanged) return fail(ctx, CDG_ERR_CUDA, "patch export: %llu differing bytes, the correction counted %llu", (unsigned long long) got, (unsigned long long) nChanged);
+    }
+    out->n = got; out->entry = ctx->hPatches.as<u64>();
+    return CDG_OK;
+}
+
+extern "C" int cdg_export_alns_compact(cdg_ctx *ctx, cdg_alns_compact *out) {
+    if (!ctx || !out) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return export_alns_compact(ctx, out, false);
 }
 
 extern "C" int cdg_rescore(cdg_ctx *ctx, const cdg_rescore_params *p, cdg_alns *out) {
@@ -928,7 +1097,32 @@ static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data
     int rc = read_scalar(ctx, SC_CHANGED, &ch);
     if (rc) return rc;
     if (n_changed) *n_changed = ch;
+    ctx->nChangedLast = ch; ctx->correctedValid = true;
     return CDG_OK;
+}
+
+extern "C" int cdg_export_patches(cdg_ctx *ctx, cdg_patches *out) {
+    if (!ctx || !out) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->correctedValid) return fail(ctx, CDG_ERR_ARG, "cdg_export_patches: no cdg_correct result on this context");
+    return export_patches(ctx, 0, ctx->dataBytes, ctx->nChangedLast, out);
+}
+
+extern "C" int cdg_iteration_compact(cdg_ctx *ctx, const cdg_iter_params *p, cdg_alns_compact *alns, cdg_patches *patches, uint64_t *n_changed) {
+    if (!ctx || !p) return CDG_ERR_ARG;
+    if (ctx->n == 0) return fail(ctx, CDG_ERR_ARG, "cdg_iteration_compact: no sequence set uploaded");
+    CK(cudaSetDevice(ctx->device));
+    int rc = run_kmermatch(ctx, &p->kmer);
+    if (rc) return rc;
+    if ((rc = run_rescore(ctx, &p->rescore))) return rc;
+    if (alns && (rc = export_alns_compact(ctx, alns, true))) return rc;   // the export overlaps the correction kernel
+    if (!alns) { u64 kept = 0; if ((rc = read_scalar(ctx, SC_KEPT, &kept))) return rc; ctx->nKept = kept; }
+    u64 ch = 0;
+    rc = run_correct(ctx, &p->corr, nullptr, &ch, nullptr);
+    if (!rc && patches) rc = export_patches(ctx, 0, ctx->dataBytes, ch, patches);
+    if (n_changed) *n_changed = ch;
+    int rc2 = wait_exports(ctx);
+    return rc ? rc : rc2;
 }
 
 extern "C" int cdg_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data, uint64_t *n_changed) {
@@ -1336,8 +1530,26 @@ extern "C" int cdg_mg_scatter_grouped(cdg_ctx *ctx, const uint64_t *dst_off) {
     return CDG_OK;
 }
 
-// sorts the received grouped records; *sorted points at the sorted array, which has CDG_HEAD_RUN spare records after
-// `total` for the next rank's head run; *head_count = number of leading records that share the first record's target id
+// leading records of the sorted grouped array that share the first record's target id (exact, any length: one block gallops
+// over the array until the first record with another id)
+__global__ void __launch_bounds__(1024) head_run_kernel(const u64 *__restrict__ keys, u64 n, int idShift, u64 idMask, unsigned long long *__restrict__ out) {
+    __shared__ unsigned long long firstOther;
+    if (threadIdx.x == 0) firstOther = ~0ull;
+    __syncthreads();
+    if (n == 0) { if (threadIdx.x == 0) *out = 0; return; }
+    const u64 id0 = (keys[0] >> idShift) & idMask;
+    for (u64 base = 0; base < n; base += 1024) {
+        const u64 i = base + threadIdx.x;
+        if (i < n && ((keys[i] >> idShift) & idMask) != id0) atomicMin(&firstOther, (unsigned long long) i);
+        __syncthreads();
+        if (firstOther != ~0ull) break;
+    }
+    if (threadIdx.x == 0) *out = firstOther == ~0ull ? n : firstOther;
+}
+
+// sorts the received grouped records; *sorted points at the sorted array; *head_count = number of leading records that share
+// the first record's target id (they go to the previous rank: rep-boundary bleed, kmermatcher.cpp:886-888); *head_capacity =
+// records of a neighbour's head run that fit behind the sorted array without moving it (cdg_mg_head_area handles more)
 extern "C" int cdg_mg_sort2(cdg_ctx *ctx, void **sorted, uint64_t *head_count, uint64_t *head_capacity) {
     if (!ctx || !sorted || !head_count) return CDG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -1346,37 +1558,57 @@ extern "C" int cdg_mg_sort2(cdg_ctx *ctx, void **sorted, uint64_t *head_count, u
     int rc;
     CK(ctx->dKey2A.reserve((R2 + CDG_HEAD_RUN + 1) * 8));
     if ((rc = km_sort2(ctx, K, R2, ctx->dRecv2.as<u64>(), ctx->dKey2A.as<u64>()))) return rc;   // sorted in place of the receive area and its partner
-    // head run on the host: first min(R2, CDG_HEAD_RUN) keys, count the prefix with the first record's target id
-    std::vector<u64> head(std::min<u64>(R2, CDG_HEAD_RUN));
-    if (!head.empty()) CK(cudaMemcpyAsync(head.data(), ctx->sortedKey2, head.size() * 8, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    head_run_kernel<<<1, 1024, 0, ctx->st>>>(ctx->sortedKey2, R2, K.diagBits + 1, (1ull << K.idBits) - 1, sc + SC_SCAN);
+    ctx->launches++;
+    CKL();
     u64 hcnt = 0;
-    if (!head.empty()) {
-        const u64 idMask = (1ull << K.idBits) - 1;
-        const u32 id0 = (u32) ((head[0] >> (K.diagBits + 1)) & idMask);
-        while (hcnt < head.size() && (u32) ((head[hcnt] >> (K.diagBits + 1)) & idMask) == id0) hcnt++;
-    }
+    if ((rc = read_scalar(ctx, SC_SCAN, &hcnt))) return rc;
+    ctx->headCap = CDG_HEAD_RUN;
     *sorted = ctx->sortedKey2; *head_count = hcnt;
     if (head_capacity) *head_capacity = CDG_HEAD_RUN;
     return CDG_OK;
 }
 
+// where the next rank's head run of n_incoming records goes: directly behind the sorted records.  Runs longer than the spare
+// area (deep pile-ups, overlapping contigs) move the sorted array into a larger buffer first — no run is ever cut.
+extern "C" int cdg_mg_head_area(cdg_ctx *ctx, uint64_t n_incoming, void **dst) {
+    if (!ctx || !dst) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const u64 R2 = ctx->mgR2;
+    if (n_incoming > ctx->headCap) {
+        CK(ctx->dKey2Big.reserve((R2 + n_incoming + 1) * 8));
+        CK(cudaMemcpyAsync(ctx->dKey2Big.p, ctx->sortedKey2, R2 * 8, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        ctx->sortedKey2 = ctx->dKey2Big.as<u64>();
+        ctx->headCap = n_incoming;
+    }
+    *dst = ctx->sortedKey2 + R2;
+    return CDG_OK;
+}
+
 // n_appended records of the next rank's head run have been written behind the rank's own sorted records
-extern "C" int cdg_mg_finish(cdg_ctx *ctx, const cdg_rescore_params *rp, const cdg_corr_params *cp, uint64_t n_appended, cdg_hits *hits, cdg_alns *alns,
-                             uint8_t *out_range, uint64_t *range_offset, uint64_t *range_bytes, uint64_t *n_changed) {
+static int mg_finish_core(cdg_ctx *ctx, const cdg_rescore_params *rp, const cdg_corr_params *cp, uint64_t n_appended, cdg_hits *hits, cdg_alns *alns,
+                          cdg_alns_compact *compact, cdg_patches *patches, uint8_t *out_range, uint64_t *range_offset, uint64_t *range_bytes,
+                          uint64_t *n_changed) {
     if (!ctx || !rp || !cp) return CDG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     const KmPlan &K = ctx->plan;
     const u64 R2 = ctx->mgR2;
-    if (n_appended > CDG_HEAD_RUN) return fail(ctx, CDG_ERR_ARG, "cdg_mg_finish: head run longer than the reserved area");
+    if (n_appended > ctx->headCap) return fail(ctx, CDG_ERR_ARG, "cdg_mg_finish: head run longer than the reserved area (call cdg_mg_head_area first)");
+    if (!ctx->monotoneOffsets && (out_range || patches))
+        return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_mg_finish: the DB entries are not laid out in index order, so a query range is not a byte range; "
+                                              "rewrite the DB in index order (single-threaded writer) for the multi-GPU phases");
     int rc;
     if ((rc = km_reduce(ctx, K, R2, R2 + n_appended))) return rc;
     if (hits && (rc = export_hits(ctx, hits))) return rc;
     if ((rc = run_rescore(ctx, rp))) return rc;
     if (alns && (rc = export_alns(ctx, alns, true))) return rc;
-    if (!alns) { u64 kept = 0; if ((rc = read_scalar(ctx, SC_KEPT, &kept))) return rc; ctx->nKept = kept; }
-    if ((rc = run_correct(ctx, cp, nullptr, n_changed, nullptr))) return rc;
-    if ((rc = wait_exports(ctx))) return rc;
+    else if (compact && (rc = export_alns_compact(ctx, compact, true))) return rc;
+    if (!alns && !compact) { u64 kept = 0; if ((rc = read_scalar(ctx, SC_KEPT, &kept))) return rc; ctx->nKept = kept; }
+    u64 ch = 0;
+    if ((rc = run_correct(ctx, cp, nullptr, &ch, nullptr))) return rc;
+    if (n_changed) *n_changed = ch;
     // corrected bytes of the rank's query range
     u64 b0 = 0, b1 = ctx->dataBytes;
     if (K.nQ) {
@@ -1386,9 +1618,19 @@ extern "C" int cdg_mg_finish(cdg_ctx *ctx, const cdg_rescore_params *rp, const c
     } else b0 = b1 = 0;
     if (range_offset) *range_offset = b0;
     if (range_bytes) *range_bytes = b1 - b0;
+    if (patches && (rc = export_patches(ctx, b0, b1, ch, patches))) return rc;
     if (out_range && b1 > b0) CK(cudaMemcpyAsync(out_range, ctx->dOut.as<u8>() + b0, b1 - b0, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    return CDG_OK;
+    return wait_exports(ctx);
+}
+extern "C" int cdg_mg_finish(cdg_ctx *ctx, const cdg_rescore_params *rp, const cdg_corr_params *cp, uint64_t n_appended, cdg_hits *hits, cdg_alns *alns,
+                             uint8_t *out_range, uint64_t *range_offset, uint64_t *range_bytes, uint64_t *n_changed) {
+    return mg_finish_core(ctx, rp, cp, n_appended, hits, alns, nullptr, nullptr, out_range, range_offset, range_bytes, n_changed);
+}
+// same with the compact outputs of cdg_iteration_compact for the rank's query range (patch offsets are offsets into the whole DB)
+extern "C" int cdg_mg_finish_compact(cdg_ctx *ctx, const cdg_rescore_params *rp, const cdg_corr_params *cp, uint64_t n_appended, cdg_alns_compact *alns,
+                                     cdg_patches *patches, uint64_t *range_offset, uint64_t *range_bytes, uint64_t *n_changed) {
+    return mg_finish_core(ctx, rp, cp, n_appended, nullptr, nullptr, alns, patches, nullptr, range_offset, range_bytes, n_changed);
 }
 
 // ------------------------------------------------------------------------------------------------------

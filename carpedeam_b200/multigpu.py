@@ -67,9 +67,29 @@ class TorchComm:
         self.dist.all_to_all_single(r, t)
         return [int(x) for x in r.tolist()]
 
+    class _Synced:
+        """wait() of a data collective returns only when the data is in place for EVERY stream: Work.wait() alone orders torch's
+        current stream, but the library works on its own non-blocking stream (cdg_stream) — so the host waits for the device."""
+
+        def __init__(self, work, comm):
+            self.work, self.comm = work, comm
+
+        def wait(self):
+            if self.work is not None:
+                self.work.wait()
+            self.comm._sync()
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            self.torch.cuda.current_stream(self.device).synchronize()
+
     def all_to_all(self, recv, send, recv_counts, send_counts, async_op=False):
-        return self.dist.all_to_all_single(recv, send, output_split_sizes=[int(c) for c in recv_counts],
-                                           input_split_sizes=[int(c) for c in send_counts], async_op=async_op)
+        w = self.dist.all_to_all_single(recv, send, output_split_sizes=[int(c) for c in recv_counts],
+                                        input_split_sizes=[int(c) for c in send_counts], async_op=async_op)
+        if async_op:
+            return self._Synced(w, self)
+        self._sync()
+        return None
 
     def all_gather_rows(self, row):
         """row: list of ints (int64 range) -> list over ranks of such rows"""
@@ -96,8 +116,9 @@ class TorchComm:
         self.dist.all_gather(out, t)
         return [int(np.int64(o.item()).astype(np.uint64)) for o in out]
 
-    def shift_to_prev(self, send, n_send, recv_capacity_tensor):
-        """rank r sends `send[:n_send]` to rank r-1 and receives from rank r+1; returns the received count."""
+    def shift_to_prev(self, send, n_send, recv_area):
+        """rank r sends `send[:n_send]` to rank r-1 and receives from rank r+1; returns the received count.  recv_area: a tensor
+        with room for the incoming records, or a callable n -> tensor of n elements (the receiver learns n first)."""
         torch, dist = self.torch, self.dist
         cnt = self.all_gather_u64(n_send)
         n_recv = cnt[self.rank + 1] if self.rank + 1 < self.world else 0
@@ -105,10 +126,12 @@ class TorchComm:
         if self.rank > 0 and n_send > 0:
             ops.append(dist.P2POp(dist.isend, send[:n_send], self.rank - 1))
         if n_recv > 0:
-            ops.append(dist.P2POp(dist.irecv, recv_capacity_tensor[:n_recv], self.rank + 1))
+            area = recv_area(n_recv) if callable(recv_area) else recv_area
+            ops.append(dist.P2POp(dist.irecv, area[:n_recv], self.rank + 1))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
+            self._sync()
         return n_recv
 
 
@@ -181,13 +204,14 @@ class ThreadComm:
         self.lw.barrier.wait()          # nobody reuses a send buffer before every peer has copied from it
         return self._Done()
 
-    def shift_to_prev(self, send, n_send, recv_capacity_tensor):
+    def shift_to_prev(self, send, n_send, recv_area):
         items = self._gather((send, int(n_send)))
         n_recv = 0
         if self.rank + 1 < self.world:
             t, n_recv = items[self.rank + 1]
             if n_recv:
-                recv_capacity_tensor[:n_recv].copy_(t[:n_recv])
+                area = recv_area(n_recv) if callable(recv_area) else recv_area
+                area[:n_recv].copy_(t[:n_recv])
         self._sync()
         self.lw.barrier.wait()
         return n_recv
@@ -281,23 +305,42 @@ class ShardedIteration:
         L.cdg_mg_sort2.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.cdg_mg_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.cdg_mg_head_area.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        L.cdg_mg_finish_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
+                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         self.L = L
+        self._up = None      # persistent device staging of upload_sharded_packed
         if exchange == "p2p" and comm.world > 1:
             self._probe_peer_memory()
 
     def _probe_peer_memory(self):
         """Collective start-up check: can every rank map every peer's receive buffer (CUDA IPC needs all GPUs visible to all
         processes and a shared IPC namespace)?  If any rank cannot, ALL ranks switch to the NCCL exchange — loudly — instead of
-        failing in the middle of the first iteration."""
+        failing in the middle of the first iteration.  Local steps (allocation, handle export, opening the peers' handles) may
+        fail on any rank; the two collectives (handle all-gather, outcome all-gather) are entered by every rank regardless, so a
+        failing rank can never leave its peers in a different collective."""
         import sys
-        ok = 1
+        ok, why = 1, ""
+        mine = bytes(self.HANDLE_BYTES)
         try:
             r2 = C.c_void_p()
             self.ctx._ck(self.L.cdg_mg_recv_grouped(self.ctx._h, 1, C.byref(r2)), "cdg_mg_recv_grouped")      # allocates the buffer
-            self._map_peers((4,))
+            h = C.create_string_buffer(self.HANDLE_BYTES)
+            self.ctx._ck(self.L.cdg_mg_ipc_export(self.ctx._h, 4, h), "cdg_mg_ipc_export")
+            mine = h.raw
         except Exception as e:      # noqa: BLE001 - any failure means "no peer memory here"
-            ok = 0
-            print("carpedeam_b200.multigpu: rank %d cannot map peer memory (%s)" % (self.comm.rank, e), file=sys.stderr, flush=True)
+            ok, why = 0, str(e)
+        handles = self.comm.all_gather_bytes(mine)
+        if ok:
+            try:
+                for peer, blob in enumerate(handles):
+                    if peer != self.comm.rank and any(blob):
+                        hb = C.create_string_buffer(blob, self.HANDLE_BYTES)
+                        self.ctx._ck(self.L.cdg_mg_ipc_open(self.ctx._h, 4, peer, hb), "cdg_mg_ipc_open")
+            except Exception as e:      # noqa: BLE001
+                ok, why = 0, str(e)
+        if not ok:
+            print("carpedeam_b200.multigpu: rank %d cannot map peer memory (%s)" % (self.comm.rank, why), file=sys.stderr, flush=True)
         flags = self.comm.all_gather_rows([ok])
         if not all(f[0] for f in flags):
             for peer in range(self.comm.world):
@@ -367,6 +410,41 @@ class ShardedIteration:
         if trace and rank == 0:
             print("upload_sharded: shards+all_gather %.1f ms, pack from device memory %.1f ms" % ((t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3), flush=True)
         return h2d      # bytes this rank copied from the host
+
+    def upload_sharded_packed(self, words, nmask, lens, ext=None):
+        """cdg_upload_packed for `world` ranks that all hold the same pinned host arrays (torch CPU tensors: words int64, nmask
+        int32 or None, lens int32, ext uint8 or None): rank r copies the r-th 1/world of every array from the host, the ranks
+        all-gather the pieces over NVLink into persistent device buffers, the library reads device memory.  Per-rank host traffic
+        is 1/world of the packed set; the device buffers are allocated once."""
+        torch, dist, comm = self.comm.torch, self.comm.dist, self.comm
+        world, rank, dev = comm.world, comm.rank, comm.device
+        arrays = (words, nmask, lens, ext)
+        sig = tuple(None if a is None else (a.numel(), a.dtype) for a in arrays)
+        if self._up is None or self._up[0] != sig:
+            bufs = []
+            for a in arrays:
+                if a is None:
+                    bufs.append(None)
+                    continue
+                per = (a.numel() + world - 1) // world
+                bufs.append((per, torch.zeros(per, dtype=a.dtype, device=dev), torch.empty(per * world, dtype=a.dtype, device=dev)))
+            self._up = (sig, bufs)
+        h2d, full = 0, []
+        for a, b in zip(arrays, self._up[1]):
+            if a is None:
+                full.append(None)
+                continue
+            per, shard, out = b
+            n = a.numel()
+            lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+            shard[:hi - lo].copy_(a[lo:hi], non_blocking=True)
+            h2d += (hi - lo) * a.element_size()
+            dist.all_gather_into_tensor(out, shard)
+            full.append(out[:n])
+        torch.cuda.current_stream().synchronize()
+        self.ctx.upload_packed_raw(full[0].data_ptr(), full[1].data_ptr() if full[1] is not None else 0, full[2].data_ptr(),
+                                   full[3].data_ptr() if full[3] is not None else 0, lens.numel(), words.numel())
+        return h2d
 
     def release(self):
         """drop every peer mapping (collective): call before the contexts are destroyed or the receive buffers are reused elsewhere"""
@@ -478,8 +556,11 @@ class ShardedIteration:
         sorted_ptr, head_n, head_cap = C.c_void_p(), C.c_uint64(), C.c_uint64()
         ctx._ck(L.cdg_mg_sort2(ctx._h, C.byref(sorted_ptr), C.byref(head_n), C.byref(head_cap)), "cdg_mg_sort2")
         lap("sort2")
-        whole = self._t(sorted_ptr.value, total2 + head_cap.value)
-        n_app = comm.shift_to_prev(whole[:total2], int(head_n.value), whole[total2:])
+        def head_area(n_in):      # the library makes room behind its sorted records (any run length)
+            dst = C.c_void_p()
+            ctx._ck(L.cdg_mg_head_area(ctx._h, n_in, C.byref(dst)), "cdg_mg_head_area")
+            return self._t(dst.value, n_in)
+        n_app = comm.shift_to_prev(self._t(sorted_ptr.value, total2), int(head_n.value), head_area)
         lap("head shift")
         # phase 5
         hits, alns = Hits(), Alns()
@@ -487,14 +568,23 @@ class ShardedIteration:
         optr = None
         if out_range is not None:
             optr = C.c_void_p(out_range.ctypes.data) if hasattr(out_range, "ctypes") else C.c_void_p(int(out_range))
-        ctx._ck(L.cdg_mg_finish(ctx._h, C.byref(rp), C.byref(cp), n_app, C.byref(hits) if fetch_hits else None, C.byref(alns) if fetch_alns else None,
-                                optr, C.byref(off), C.byref(nbytes), C.byref(changed)), "cdg_mg_finish")
+        compact, patches = None, None
+        if fetch_alns == "compact":      # cdg_alns_compact + cdg_patches of the rank's query range (what crosses PCIe in the benchmark)
+            from . import AlnsCompact, Patches
+            compact, patches = AlnsCompact(), Patches()
+            ctx._ck(L.cdg_mg_finish_compact(ctx._h, C.byref(rp), C.byref(cp), n_app, C.byref(compact), C.byref(patches), C.byref(off), C.byref(nbytes),
+                                            C.byref(changed)), "cdg_mg_finish_compact")
+        else:
+            ctx._ck(L.cdg_mg_finish(ctx._h, C.byref(rp), C.byref(cp), n_app, C.byref(hits) if fetch_hits else None, C.byref(alns) if fetch_alns else None,
+                                    optr, C.byref(off), C.byref(nbytes), C.byref(changed)), "cdg_mg_finish")
         lap("reduce+rescore+correct")
         res = dict(phase_ms=tm, range_offset=off.value, range_bytes=nbytes.value, changed=changed.value, records_sent=nsend, records_received=total,
                    grouped_sent=sum(send2), grouped_received=total2, head_appended=n_app)
         if fetch_hits:
             res["hits"] = ctx._hits(hits)
-        if fetch_alns == "raw":
+        if fetch_alns == "compact":
+            res["alns_compact"], res["patches"] = compact, patches
+        elif fetch_alns == "raw":
             res["alns_raw"] = alns     # library-owned pinned arrays, no numpy copies (benchmark)
         elif fetch_alns:
             res["alns"] = ctx._alns(alns)

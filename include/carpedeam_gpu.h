@@ -61,6 +61,18 @@ int cdg_upload_seqs(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, cons
 int cdg_upload_seqs_async(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, const uint64_t *offsets,
                           const uint32_t *lens, const uint8_t *ext, uint64_t n);
 
+/* 2-bit packed upload (SURVEY §8(b) proposal `cdg_upload_seqs(packed2bit, nmask_words, ...)`; §8(d): the metric is quoted from
+ * PACKED sequences in pinned host memory).  For sets whose letters are upper-case A,C,G,T,N only (what createdb writes for
+ * FASTQ reads; carpedeam_b200/host/pack.cpp `cdh_pack_seqs` builds the arrays and refuses anything else):
+ *   words : u64, 32 bases per word, sequence i owns ceil(lens[i]/32) consecutive words in index order, first base in the most
+ *           significant bits (the order of Indexer::computeKmerIdx, Indexer.h:136-143), codes A0 C1 T2 G3, N and padding 0
+ *   nmask : u32 per word, bit 31-j set = base j of the word is N; NULL = the set holds no N
+ * The library rebuilds the DB byte layout (`BASES\n\0` per entry, offsets = prefix sum of lens+2) on the device, so every later
+ * call behaves exactly as after cdg_upload_seqs of that DB.  Asynchronous like cdg_upload_seqs_async (arrays: host memory that
+ * stays valid until the next call on the context returned, or device memory of this GPU). */
+int cdg_upload_packed(cdg_ctx *ctx, const uint64_t *words, const uint32_t *nmask, const uint32_t *lens, const uint8_t *ext,
+                      uint64_t n, uint64_t n_words);
+
 /* ---- kmermatcher ----------------------------------------------------------------------------- */
 typedef struct {
     int32_t k;                       /* -k (20 reads / 22 contigs) */
@@ -194,6 +206,37 @@ typedef struct {
 int cdg_iteration(cdg_ctx *ctx, const cdg_iter_params *p, cdg_hits *hits, cdg_alns *alns, uint8_t *out_data,
                   uint64_t *n_changed);
 
+/* ---- compact results (what has to cross PCIe; SURVEY §8(d): "corrected packed sequences + alignment SoA") ----------------
+ * Alignments: only what rescorediagonal WRITES (keep == 1), in pref order, grouped by query.  An ungapped alignment is fully
+ * described by (target, raw score, identical columns, first query / target column, length, strand):
+ *   q_end = reverse ? q_start - (aln_len-1) : q_start + (aln_len-1),  db_end = db_start + aln_len - 1,
+ *   seq_id = score ? (float) id_cnt / (float) aln_len : 0,  bits / evalue from (score, query length, db residues)
+ * (carpedeam_b200/host/expand.cpp `cdh_expand_alns` rebuilds the cdg_alns arrays / the alignment DB text from these with the
+ * reference's own formulas).  The self alignment of query q (always kept, rescorediagonal.cpp:304-314) is IMPLICIT when q is
+ * plain upper-case ACGT: target q, score 2*len, id_cnt len, columns 0..len-1; for any other query it is the first exported
+ * record of q (target == q).  width = 2: the five per-alignment arrays are int16/uint16 (longest sequence < 32768), else 4. */
+typedef struct {
+    uint64_t n_queries, n_alns;
+    uint64_t first_query;        /* index of the first query of this context's range (multi-GPU), else 0 */
+    const uint32_t *count;       /* n_queries: exported alignments of each query */
+    const uint32_t *target;      /* n_alns */
+    int32_t width;
+    const void *score, *id_cnt;  /* uint16 / uint32 */
+    const void *q_start, *db_start; /* int16 / int32 (a score-0 self alignment has start = -1, DistanceCalculator.h:42-55) */
+    const void *aln_len_rev;     /* uint16 / uint32: aln_len << 1 | reverse strand */
+    uint64_t db_residues;        /* the E-value's database size used on the device */
+} cdg_alns_compact;
+/* Corrected reads as a patch list: entry = byte offset in the DB data layout << 8 | new base letter; unordered, offsets distinct.
+ * (correction.cpp:465-470 rewrites the whole sequence; a caller that holds the input applies the patches to its copy.) */
+typedef struct { uint64_t n; const uint64_t *entry; } cdg_patches;
+
+/* cdg_iteration with compact outputs (either may be NULL).  Results are identical to cdg_iteration's (tests/test_gpu_parity.py
+ * test_compact_outputs_equal_full_outputs). */
+int cdg_iteration_compact(cdg_ctx *ctx, const cdg_iter_params *p, cdg_alns_compact *alns, cdg_patches *patches, uint64_t *n_changed);
+/* compact views of the last cdg_rescore / cdg_correct of the stand-alone stages */
+int cdg_export_alns_compact(cdg_ctx *ctx, cdg_alns_compact *out);
+int cdg_export_patches(cdg_ctx *ctx, cdg_patches *out);
+
 /* ---- multi-GPU phases ------------------------------------------------------------
  * One context per rank, the whole sequence set uploaded on every rank.  K-mer records are owned by hash range like
  * kmermatcher's split passes (kmermatcher.cpp:742-784): rank r owns hash16 in [r*65536/world, (r+1)*65536/world).
@@ -203,7 +246,8 @@ int cdg_iteration(cdg_ctx *ctx, const cdg_iter_params *p, cdg_hits *hits, cdg_al
  *                      (id_send_counts / id_send_keys / id_send_vals), so no rank hashes sequences outside its slice
  *   cdg_mg_recv_records / cdg_mg_sort -> min key of the rank (the ranks compare 8 bytes each: first-run quirk, :466)
  *   cdg_mg_group    -> all-to-all of the 8-byte grouped records to the rank owning the representative's index range
- *   cdg_mg_recv_grouped / cdg_mg_sort2 -> the leading records with one target id go to rank-1 (rep-boundary bleed, :886-888)
+ *   cdg_mg_recv_grouped / cdg_mg_sort2 / cdg_mg_head_area -> the leading records with one target id (any number) go to rank-1
+ *                      (rep-boundary bleed, :886-888)
  *   cdg_mg_finish   -> hits, alignments and corrected bytes of the rank's query range [rank*ceil(n/world), ...) */
 /* partition != 0: the records are partitioned by owner into contiguous send buffers for an NCCL all-to-all (baseline exchange).
  * partition == 0: only the per-owner counts are returned; cdg_mg_scatter_records then writes the partition straight into the
@@ -225,8 +269,15 @@ int cdg_mg_sort(cdg_ctx *ctx, const cdg_kmer_params *p, uint64_t *min_key);
 int cdg_mg_group(cdg_ctx *ctx, const cdg_kmer_params *p, int has_global_first_run, int partition, uint64_t *send_counts, void **send_key2);
 int cdg_mg_recv_grouped(cdg_ctx *ctx, uint64_t total, void **recv_key2);
 int cdg_mg_sort2(cdg_ctx *ctx, void **sorted, uint64_t *head_count, uint64_t *head_capacity);
+/* device address the next rank's head run of n_incoming records must be written to (directly behind this rank's sorted records;
+ * the array is moved to a larger buffer when the run does not fit the spare area — head runs are never cut) */
+int cdg_mg_head_area(cdg_ctx *ctx, uint64_t n_incoming, void **dst);
 int cdg_mg_finish(cdg_ctx *ctx, const cdg_rescore_params *rp, const cdg_corr_params *cp, uint64_t n_appended, cdg_hits *hits, cdg_alns *alns,
                   uint8_t *out_range, uint64_t *range_offset, uint64_t *range_bytes, uint64_t *n_changed);
+
+/* cdg_mg_finish with the compact outputs of cdg_iteration_compact for the rank's query range */
+int cdg_mg_finish_compact(cdg_ctx *ctx, const cdg_rescore_params *rp, const cdg_corr_params *cp, uint64_t n_appended, cdg_alns_compact *alns,
+                          cdg_patches *patches, uint64_t *range_offset, uint64_t *range_bytes, uint64_t *n_changed);
 
 /* ---- measurement ------------------------------------------------------------------------------ */
 typedef struct {

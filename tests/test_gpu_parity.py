@@ -620,3 +620,97 @@ def test_virtual_ranks_equal_unsplit_run(ctx, world, case):
         merged[p["range_offset"]:p["range_offset"] + p["range_bytes"]] = p["out"]
     assert np.array_equal(merged, out) and sum(p["changed"] for p in parts) == changed
     assert max(p["records_received"] for p in parts) < 0.75 * hits["R1"] or world == 1      # no rank sorted the whole record set
+
+
+def _kept(alns):
+    """the kept lines of a full alignment export, re-grouped by query (what cdh_expand_alns must reproduce)"""
+    k = alns["keep"].astype(bool)
+    lo = alns["line_off"].astype(np.int64)
+    csum = np.concatenate([[0], np.cumsum(k)])
+    out = {f: alns[f][k] for f in ("tgt", "score", "bits", "evalue", "seqid", "qs", "qe", "ds", "de")}
+    out["line_off"] = csum[lo].astype(np.uint64)
+    return out
+
+
+@pytest.mark.parametrize("case", ["golden reads", "golden contigs k=22", "synthetic with N and lower case", "long contigs (32-bit fields)"])
+def test_compact_outputs_equal_full_outputs(ctx, case):
+    """cdg_iteration_compact (kept alignments as 14-byte records with implicit self lines, corrected reads as patches) expanded
+    on the host == cdg_iteration's full-fidelity outputs, field for field; the packed upload (2-bit words + N mask in, DB bytes
+    rebuilt on the device) == the byte upload of the same set."""
+    import ctypes as C
+    import carpedeam_b200 as cd
+    kp = cd.kmer_params()
+    if case == "golden reads":
+        s = SeqSet.from_golden("nucl_reads")
+    elif case == "golden contigs k=22":
+        s, kp = SeqSet.from_golden("assembly_contigs_8_noneCycle"), cd.kmer_params(k=22, include_only_extendable=1)
+    elif case == "synthetic with N and lower case":
+        seqs = synth_reads(20000, 100000, 31, n_frac=0.002)
+        seqs[7] = seqs[7].lower(); seqs[11] = b"N" * 40; seqs[12] = seqs[13]
+        s = SeqSet(seqs)
+    else:
+        rng = np.random.default_rng(5)
+        g = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 120000)]
+        seqs = [g[a:a + L].tobytes() for a, L in ((0, 40000), (30000, 50000), (70000, 45000), (100, 39000))] + synth_reads(2000, 100000, 6)
+        s = SeqSet(seqs)
+    ctx.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    hits, alns, out, changed = ctx.iteration(kmer=kp, fetch_hits=True)
+    ip = cd.IterParams(kp, cd.RescoreParams(0.9, 0.001, 0), cd.CorrParams(0.9, 0.99))
+    uploads = [("bytes", lambda: ctx.upload(s.blob, s.off, s.len, s.ext))]
+    plain = all(set(s.seq(i)) <= set(b"ACGTN") for i in range(s.n))
+    if plain:
+        words, nmask, has_n = cd.pack_seqs(s.blob, s.off, s.len)
+        uploads.append(("packed", lambda: ctx.upload_packed(words, nmask, s.len, s.ext)))
+    else:
+        with pytest.raises(cd.CdgError):
+            cd.pack_seqs(s.blob, s.off, s.len)
+    want = _kept(alns)
+    for name, up in uploads:
+        up()
+        ca, pa = cd.AlnsCompact(), cd.Patches()
+        ch = ctx.iteration_compact(ip, ca, pa)
+        assert ca.width == (2 if s.len.max() < 32768 else 4)
+        got = cd.expand_alns(ca, s.len)
+        assert np.array_equal(got["line_off"], want["line_off"]), name
+        for f in ("tgt", "score", "bits", "seqid", "qs", "qe", "ds", "de"):
+            assert np.array_equal(got[f], want[f]), (name, f)
+        assert np.allclose(got["evalue"], want["evalue"], rtol=1e-12, atol=0), name      # glibc vs CUDA exp/erfc
+        assert ch == changed and pa.n == changed
+        assert np.array_equal(cd.apply_patches(s.blob, pa), out), name
+        # fewer bytes than the full export, and implicit self lines really are implied
+        assert ca.n_alns <= int(alns["keep"].sum())
+        if case == "golden reads":
+            assert ca.n_alns == int(alns["keep"].sum()) - s.n
+    # stand-alone stage exports after cdg_rescore / cdg_correct
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.kmermatch(kp, fetch=False)
+    ctx.rescore(fetch=False)
+    got = cd.expand_alns(ctx.export_alns_compact(), s.len)
+    # (the stand-alone stages do not round seqId through the alignment text, the kept lines are the same)
+    for f in ("tgt", "score", "qs", "qe", "ds", "de", "seqid"):
+        assert np.array_equal(got[f], want[f]), f
+    out2, ch2 = ctx.correct()
+    assert np.array_equal(cd.apply_patches(s.blob, ctx.export_patches()), out2)
+
+
+def test_packed_upload_rejects_inconsistent_arguments(ctx):
+    import carpedeam_b200 as cd
+    s = SeqSet(synth_reads(100, 2000, 3))
+    words, nmask, _ = cd.pack_seqs(s.blob, s.off, s.len)
+    with pytest.raises(cd.CdgError):
+        ctx.upload_packed(words[:-1], None, s.len)
+    # dirty padding / N positions in the words are sanitised on the device: results equal the clean upload
+    ctx.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+    ctx.upload_packed(words, nmask, s.len)
+    h1 = ctx.kmermatch()
+    dirty = words.copy()
+    wo = np.concatenate([[0], np.cumsum((s.len.astype(np.int64) + 31) // 32)])
+    for i in range(s.n):
+        L = int(s.len[i])
+        if L % 32:
+            dirty[wo[i + 1] - 1] |= np.uint64((1 << (2 * (32 - L % 32))) - 1)
+    ctx.upload_packed(dirty, nmask, s.len)
+    h2 = ctx.kmermatch()
+    for f in ("rep", "tgt", "score", "diag"):
+        assert np.array_equal(h1[f], h2[f])

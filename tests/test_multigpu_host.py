@@ -164,39 +164,47 @@ def test_peer_memory_probe_falls_back_collectively():
                 raise RuntimeError(what + " failed")
 
     class StubLib:
-        def __init__(self, rank, fail):
-            self.rank, self.fail, self.closed = rank, fail, []
+        def __init__(self, rank, fail, where="open"):
+            self.rank, self.fail, self.where, self.closed, self.opened = rank, fail, where, [], []
 
         def cdg_mg_recv_grouped(self, h, total, ptr):
-            return 0
+            return -1 if self.fail and self.where == "alloc" else 0
 
         def cdg_mg_ipc_export(self, h, which, buf):
+            if self.fail and self.where == "export":
+                return -1
+            buf.raw = bytes([self.rank + 1]) * len(buf.raw)
             return 0
 
         def cdg_mg_ipc_open(self, h, which, peer, buf):
-            return -1 if self.fail else 0
+            self.opened.append(peer)
+            return -1 if self.fail and self.where == "open" else 0
 
         def cdg_mg_ipc_close(self, h, which, peer):
             self.closed.append((which, peer))
             return 0
 
-    def worker(rank, fail_rank):
+    def worker(rank, fail_rank, where):
         try:
             sh = ShardedIteration.__new__(ShardedIteration)
             sh.ctx, sh.comm, sh.exchange = StubCtx(), ThreadComm(lw, rank, torch.device("cpu")), "p2p"
-            sh.L = StubLib(rank, fail=(rank == fail_rank))
+            sh.L = StubLib(rank, fail=(rank == fail_rank), where=where)
             sh._probe_peer_memory()
-            out[(fail_rank, rank)] = (sh.exchange, sh.L.closed)
+            out[(fail_rank, where, rank)] = (sh.exchange, sh.L.closed, sh.L.opened)
         except Exception as e:
             errors.append(repr(e)); lw.barrier.abort()
 
-    for fail_rank in (1, None):
-        ts = [threading.Thread(target=worker, args=(r, fail_rank)) for r in range(2)]
+    # the failure may hit before the handle all-gather (allocation, export) or after it (open): in every case both ranks must pass
+    # through the same two collectives and agree
+    for fail_rank, where in ((1, "open"), (1, "export"), (0, "alloc"), (None, "open")):
+        ts = [threading.Thread(target=worker, args=(r, fail_rank, where)) for r in range(2)]
         for t in ts:
             t.start()
         for t in ts:
             t.join(60)
-    assert not errors, errors
-    assert out[(1, 0)][0] == "nccl" and out[(1, 1)][0] == "nccl"          # both ranks, although only rank 1 failed
-    assert out[(1, 0)][1] == [(4, 1)] and out[(1, 1)][1] == [(4, 0)]      # mappings dropped
-    assert out[(None, 0)][0] == "p2p" and out[(None, 1)][0] == "p2p" and out[(None, 0)][1] == []
+        assert not errors, (fail_rank, where, errors)
+    for where, fr in (("open", 1), ("export", 1), ("alloc", 0)):
+        assert out[(fr, where, 0)][0] == "nccl" and out[(fr, where, 1)][0] == "nccl", where     # both ranks, although only one failed
+    assert out[(1, "open", 0)][1] == [(4, 1)] and out[(1, "open", 1)][1] == [(4, 0)]      # mappings dropped
+    assert out[(1, "export", 0)][2] == []       # a zeroed handle (the peer could not export) is never opened
+    assert out[(None, "open", 0)][0] == "p2p" and out[(None, "open", 1)][0] == "p2p" and out[(None, "open", 0)][1] == []
