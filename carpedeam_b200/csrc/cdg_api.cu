@@ -599,8 +599,13 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
         E.seqLo = piece.seqLo; E.seqHi = piece.seqHi;
         const u32 maxW = ctx->maxLen >= (u32) p->k ? ctx->maxLen - p->k + 1 : 0;   // short sequences have <= 256 windows
 #define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dPow31.as<u64>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT, identityMode == 2 ? ctx->ordV : (const u64 *) nullptr, ctx->dSlotRank.as<u64>())
-        if (maxW <= 64) extract_short_kernel<2><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
+        // the 16-bit XXH64 score of a window only matters for ownership (hash range, owner rank) and inside the exact replay
+        const bool noScore = hashLo == 0 && hashHi >= 65535 && K.world == 1;
+        if (maxW <= 64 && noScore) extract_short_kernel<2, false><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
+        else if (maxW <= 64) extract_short_kernel<2><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
+        else if (maxW <= 128 && noScore) extract_short_kernel<4, false><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
         else if (maxW <= 128) extract_short_kernel<4><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
+        else if (noScore) extract_short_kernel<8, false><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
         else extract_short_kernel<8><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
 #undef CDG_EXTRACT_ARGS
         ctx->launches++;
@@ -1661,7 +1666,7 @@ extern "C" int cdg_test_radix_sort(cdg_ctx *ctx, uint64_t *keys, uint64_t *vals,
 
 __global__ void hash_rc_kernel(const u64 *in, u64 n, int k, u64 seed, u64 *h, u64 *rc) {
     u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { h[i] = cdg_xxh64_u64(in[i], seed); rc[i] = cdg_revcomp_kmer(in[i], k); }
+    if (i < n) { h[i] = cdg_xxh64_u64(in[i], seed); rc[i] = cdgkmer::revcomp_kmer_dev(in[i], k); }   // the kernels' BREV form (oracle: the reference's)
 }
 extern "C" int cdg_test_hash_revcomp(cdg_ctx *ctx, const uint64_t *in, uint64_t n, int k, uint64_t seed, uint64_t *hash_out, uint64_t *rc_out) {
     if (!ctx || !in || !hash_out || !rc_out) return CDG_ERR_ARG;

@@ -108,15 +108,27 @@ CDG_D u64 pow31(u32 e) {
 
 struct WinRec { u64 kmer; u32 pos; u32 score; };   // kmer carries the strand bit 63
 
-// canonical k-mer of window p; returns false for windows the reference skips (X, palindromes)
+// reverse complement on the device: two BREV reverse the 64 bits, one swap of the bits inside every 2-bit group restores the codes
+CDG_D u64 revcomp_kmer_dev(u64 idx, int k) {
+    const u64 x = idx ^ 0xAAAAAAAAAAAAAAAAull;
+    u32 lo = __brev((u32) (x >> 32)), hi = __brev((u32) x);
+    lo = ((lo >> 1) & 0x55555555u) | ((lo & 0x55555555u) << 1);
+    hi = ((hi >> 1) & 0x55555555u) | ((hi & 0x55555555u) << 1);
+    return (((u64) hi << 32) | lo) >> (64 - 2 * k);
+}
+// canonical k-mer of window p; returns false for windows the reference skips (X, palindromes).
+// SCORE = false: the 16-bit XXH64 score is not needed by the caller's fast path (no hash threshold, the whole hash range owned,
+// one rank): r.score then holds a cheap 13-bit mixing of the k-mer (repeat-hint bitmap index only)
+template <bool SCORE = true>
 CDG_D bool make_window(const u64 *__restrict__ w, const u32 *__restrict__ xm, u32 p, u32 L, const ExtractParams &P, WinRec &r) {
     if (window_xmask(xm, p, P.k)) return false;                     // kmermatcher.cpp:146
     u64 idx = window_bits(w, p, P.k);
-    u64 rc = cdg_revcomp_kmer(idx, P.k);
+    u64 rc = revcomp_kmer_dev(idx, P.k);
     if (rc == idx) return false;                                    // :159
     bool useRc = rc < idx;
     u64 canon = useRc ? rc : idx;
-    r.score = (u32) (cdg_xxh64_u64(canon, P.seed) & 0xFFFFu);       // :164
+    if (SCORE) r.score = (u32) (cdg_xxh64_u64(canon, P.seed) & 0xFFFFu);       // :164
+    else r.score = (((u32) canon ^ (u32) (canon >> 21)) * 0x9E3779B1u) >> 19;
     r.kmer = useRc ? canon : (canon | CDG_B63);                     // :183
     r.pos = useRc ? (L - p - P.k) : p;                              // :185
     return true;
@@ -188,7 +200,7 @@ static constexpr int EX_BM_WORDS = 256;   // per-warp repeat-hint bitmap (8192 b
 // Fast path (no repeated k-mer inside the sequence): every valid window is emitted.  A per-warp bitmap over
 // the 16-bit hash detects possible repeats (equal k-mers have equal hashes); on a hit the warp ranks its
 // windows in shared... global scratch and lane 0 replays the reference's sequential loop.
-template <int ITERS>
+template <int ITERS, bool SCORE = true>
 __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_short_kernel(
     const u64 *__restrict__ words, const u32 *__restrict__ xmask, const SeqMeta *__restrict__ meta,
     u64 n, ExtractParams P, const u64 *__restrict__ slotOff /*[n] first main slot of seq*/,
@@ -261,7 +273,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
         for (int it = 0; it < ITERS; it++) {
             u32 p = lane + 32 * it;
             bool ok = false;
-            if (p < W) ok = make_window(w, xm, p, L, P, rec[it]);
+            if (p < W) ok = make_window<SCORE>(w, xm, p, L, P, rec[it]);
             if (ok) {
                 validMask |= 1u << it;
                 const u32 h = rec[it].score & (EX_BM_WORDS * 32 - 1);
@@ -302,12 +314,12 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
 #pragma unroll
             for (int it = 0; it < ITERS; it++) {
                 bool ok = (validMask >> it) & 1u;
-                bool own = ok && rec[it].score >= P.hashLo && rec[it].score <= P.hashHi;
+                bool own = ok && (!SCORE || (rec[it].score >= P.hashLo && rec[it].score <= P.hashHi));
                 u32 b = __ballot_sync(0xffffffffu, own);
                 if (own) {
                     u64 dst = slot0 + written + __popc(b & ((1u << lane) - 1));
                     mainKeys[dst] = rec[it].kmer;
-                    mainVals[dst] = cdg_pack_val((u32) seq, rec[it].pos, owner_of(rec[it].score, P.world));
+                    mainVals[dst] = cdg_pack_val((u32) seq, rec[it].pos, SCORE ? owner_of(rec[it].score, P.world) : 0u);
                 }
                 written += __popc(b);
             }
@@ -317,6 +329,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
 #pragma unroll
             for (int it = 0; it < ITERS; it++) {
                 bool ok = (validMask >> it) & 1u;
+                if (!SCORE && ok) rec[it].score = (u32) (cdg_xxh64_u64(rec[it].kmer & ~CDG_B63, P.seed) & 0xFFFFu);   // the replay orders by score
                 u32 b = __ballot_sync(0xffffffffu, ok);
                 if (ok) myScratch[cnt + __popc(b & ((1u << lane) - 1))] = rec[it];
                 cnt += __popc(b);

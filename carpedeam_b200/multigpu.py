@@ -310,6 +310,7 @@ class ShardedIteration:
                                             C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         self.L = L
         self._up = None      # persistent device staging of upload_sharded_packed
+        self._blk = None     # ... and of upload_packed_blocks
         if exchange == "p2p" and comm.world > 1:
             self._probe_peer_memory()
 
@@ -444,6 +445,57 @@ class ShardedIteration:
         torch.cuda.current_stream().synchronize()
         self.ctx.upload_packed_raw(full[0].data_ptr(), full[1].data_ptr() if full[1] is not None else 0, full[2].data_ptr(),
                                    full[3].data_ptr() if full[3] is not None else 0, lens.numel(), words.numel())
+        return h2d
+
+    def upload_packed_blocks(self, words, nmask, lens, ext=None):
+        """Reads block-partitioned over the ranks: every rank holds only ITS block of the packed set in pinned host
+        memory (torch CPU tensors: words int64, nmask int32 or None, lens int32, ext uint8 or None; blocks in rank order form the
+        set, block r = the rank's query range [r*ceil(n/world), ...)).  Each rank copies its block from the host once, the ranks
+        all-gather the blocks over NVLink into persistent device buffers and the library takes the device arrays
+        (cdg_upload_packed).  Returns the bytes this rank copied from the host."""
+        torch, dist, comm = self.comm.torch, self.comm.dist, self.comm
+        world, rank, dev = comm.world, comm.rank, comm.device
+        arrays = (words, nmask, lens, ext)
+        sig = tuple(None if a is None else (a.numel(), a.dtype) for a in arrays)
+        if self._blk is None or self._blk[0] != sig:
+            rows = comm.all_gather_rows([lens.numel(), words.numel()] + [0 if a is None else 1 for a in arrays])
+            if any(r[2:] != rows[0][2:] for r in rows):
+                raise ValueError("upload_packed_blocks: the ranks disagree about which optional arrays exist")
+            n_r, w_r = [r[0] for r in rows], [r[1] for r in rows]
+            n = sum(n_r)
+            per = (n + world - 1) // world
+            if any(n_r[r] != max(0, min(n, (r + 1) * per) - min(n, r * per)) for r in range(world)):
+                raise ValueError("upload_packed_blocks: block sizes %r are not the query ranges of %d sequences over %d ranks" % (n_r, n, world))
+            bufs = []
+            for a, cnt in zip(arrays, (w_r, w_r, n_r, n_r)):
+                if a is None:
+                    bufs.append(None)
+                    continue
+                mx = max(cnt)
+                uniform = all(c == mx for c in cnt)
+                gathered = torch.empty(mx * world, dtype=a.dtype, device=dev)
+                bufs.append((cnt, mx, torch.zeros(mx, dtype=a.dtype, device=dev), gathered,
+                             gathered if uniform else torch.empty(sum(cnt), dtype=a.dtype, device=dev)))
+            self._blk = (sig, bufs, n, sum(w_r))
+        _, bufs, n, n_words = self._blk
+        h2d, full = 0, []
+        for a, b in zip(arrays, bufs):
+            if a is None:
+                full.append(None)
+                continue
+            cnt, mx, shard, gathered, out = b
+            shard[:a.numel()].copy_(a, non_blocking=True)
+            h2d += a.numel() * a.element_size()
+            dist.all_gather_into_tensor(gathered, shard)
+            if out is not gathered:      # ragged blocks: close the gaps (device-to-device)
+                pos = 0
+                for r in range(world):
+                    out[pos:pos + cnt[r]].copy_(gathered[r * mx:r * mx + cnt[r]])
+                    pos += cnt[r]
+            full.append(out)
+        torch.cuda.current_stream().synchronize()
+        self.ctx.upload_packed_raw(full[0].data_ptr(), full[1].data_ptr() if full[1] is not None else 0, full[2].data_ptr(),
+                                   full[3].data_ptr() if full[3] is not None else 0, n, n_words)
         return h2d
 
     def release(self):

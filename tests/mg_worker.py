@@ -53,6 +53,36 @@ def main():
             if not np.array_equal(merged, out) or sum(p["changed"] for p in parts) != changed:
                 ok = False; print("MISMATCH", name, "corrected bytes")
             print("case %-36s world=%d hits=%d changed=%d %s" % (name, world, len(hits["rep"]), changed, [p["stats"] for p in parts]))
+    # reads block-partitioned over the ranks: every rank packs and uploads only its block (upload_packed_blocks), compact outputs
+    for mode in modes:
+        s = cases[2][1]
+        per = (s.n + world - 1) // world
+        lo, hi = min(s.n, rank * per), min(s.n, (rank + 1) * per)
+        words, nmask, _ = cd.pack_seqs(s.blob[int(s.off[lo]):int(s.off[hi - 1]) + int(s.len[hi - 1]) + 2], s.off[lo:hi] - s.off[lo], s.len[lo:hi])
+        pin = lambda a, dt: torch.from_numpy(a.view(dt)).pin_memory()
+        sharded[mode].upload_packed_blocks(pin(words, np.int64), pin(nmask, np.int32), pin(s.len[lo:hi].copy(), np.int32))
+        res = sharded[mode].run(kmer=cases[2][2], fetch_alns="compact")
+        ex = cd.expand_alns(res["alns_compact"], s.len)
+        pn = int(res["patches"].n)
+        pent = np.ctypeslib.as_array(res["patches"].entry, shape=(max(1, pn),))[:pn].copy()
+        parts = [None] * world
+        dist.all_gather_object(parts, dict(ex={k: v.copy() for k, v in ex.items()}, patches=pent, first=int(res["alns_compact"].first_query)))
+        if rank == 0:
+            ctx.upload(s.blob, s.off, s.len, s.ext)
+            hits, alns, out, changed = ctx.iteration(kmer=cases[2][2])
+            k = alns["keep"].astype(bool)
+            for f in ("tgt", "score", "bits", "qs", "qe", "ds", "de", "seqid"):
+                got = np.concatenate([p["ex"][f] for p in parts])
+                if not np.array_equal(got, alns[f][k]):
+                    ok = False; print("MISMATCH blocks+compact [%s] alns %s" % (mode, f))
+            patched = s.blob.copy()
+            for p in parts:
+                e = p["patches"]
+                patched[(e >> np.uint64(8)).astype(np.int64)] = (e & np.uint64(0xFF)).astype(np.uint8)
+            if not np.array_equal(patched, out):
+                ok = False; print("MISMATCH blocks+compact [%s] corrected bytes" % mode)
+            print("case %-36s world=%d kept=%d patches=%d first_query=%s" % ("packed blocks + compact [" + mode + "]", world, int(k.sum()),
+                                                                             sum(len(p["patches"]) for p in parts), [p["first"] for p in parts]))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     for sh in sharded.values():

@@ -714,3 +714,18 @@ def test_packed_upload_rejects_inconsistent_arguments(ctx):
     h2 = ctx.kmermatch()
     for f in ("rep", "tgt", "score", "diag"):
         assert np.array_equal(h1[f], h2[f])
+
+
+def test_multi_gpu_worker_under_torchrun():
+    """tests/mg_worker.py (one process per GPU, NCCL, peer-memory and NCCL exchanges, byte and packed-block uploads, full and
+    compact outputs == the single-GPU run) — runs whenever the box has at least two GPUs."""
+    import subprocess
+    import sys
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (the driver's 1-GPU box runs the same phases through ThreadComm: test_virtual_ranks_equal_unsplit_run)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+                        "--master-port", "29613", os.path.join(here, "mg_worker.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MULTIGPU PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
