@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(CF_WARPS * 32, 4) correct_fast_kernel(
     const i32 *__restrict__ qS_, const i32 *__restrict__ qE_, const i32 *__restrict__ dS_, const i32 *__restrict__ dE_,
     CorrParams P, const DamageTables *__restrict__ tablesG, u8 *__restrict__ lineSel, u8 *__restrict__ out,
     unsigned long long *__restrict__ changed, const u64 *__restrict__ likOff, double *__restrict__ likOut,
-    u32 *__restrict__ wideList, u32 *__restrict__ wideCount) {
+    u32 *__restrict__ wideList, u32 *__restrict__ wideCount,
+    u64 *__restrict__ patches /*out == nullptr: corrected bases go here as byte offset << 8 | letter*/, u64 patchCap, unsigned long long *__restrict__ patchCount) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     CorrSmem &S = *reinterpret_cast<CorrSmem *>(smemRaw);
     for (int i = threadIdx.x; i < (int) (sizeof(DamageTables) / sizeof(double)); i += blockDim.x) ((double *) &S.T)[i] = ((const double *) tablesG)[i];
@@ -613,8 +614,10 @@ __global__ void __launch_bounds__(CF_WARPS * 32, 4) correct_fast_kernel(
                     const bool rev = sel == 2;
                     if (rev) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; }
                     const i32 aln = max(abs(qe - qs), abs(de - ds)) + 1;
-                    if (valid && (i32) col >= qs && (i32) col < qs + aln)
-                        count_column(data, tm.off, dL, rev, (u32) ds + (col - (u32) qs), cnt, lane, lut, mask);
+                    if (valid && (i32) col >= qs && (i32) col < qs + aln) {
+                        if (tm.lenFlags & META_EXC) count_column(data, tm.off, dL, rev, (u32) ds + (col - (u32) qs), cnt, lane, lut, mask);
+                        else count_column_packed(words + tm.wordOff, dL, rev, (u32) ds + (col - (u32) qs), cnt, lane, mask);
+                    }
                 }
             }
             // coverage per target base from the non-zero counters
@@ -630,7 +633,8 @@ __global__ void __launch_bounds__(CF_WARPS * 32, 4) correct_fast_kernel(
             }
             const u32 tot = cov0 + cov1 + cov2 + cov3;
             if (valid && tot > 1) {
-                const unsigned char orig = q[col];
+                // plain queries: the letter comes from the 2-bit words already in cache (the DB bytes may not even exist: packed uploads)
+                const unsigned char orig = qExc ? q[col] : (unsigned char) cdg_num2aa((int) ((qw[col >> 5] >> (62 - 2 * (col & 31))) & 3ull));
                 const int b = nuc_map(orig);
                 int nb = b;
                 bool evaluate = true;
@@ -667,7 +671,11 @@ __global__ void __launch_bounds__(CF_WARPS * 32, 4) correct_fast_kernel(
                     if (likOut) { double *lo = likOut + (likOff[qi] + col) * 4; lo[0] = acc[0]; lo[1] = acc[1]; lo[2] = acc[2]; lo[3] = acc[3]; }
                 }
                 const unsigned char res = (unsigned char) "ACGT"[nb];
-                if (res != orig) { o[col] = res; nChanged++; }
+                if (res != orig) {
+                    nChanged++;
+                    if (out) o[col] = res;
+                    else { const u64 slot = atomicAdd(patchCount, 1ull); if (slot < patchCap) patches[slot] = ((qm.off + col) << 8) | (u64) res; }
+                }
             }
             while (mask) { const int idx = __ffsll((long long) mask) - 1; mask &= mask - 1; cnt[idx][lane] = 0; }
         }

@@ -100,6 +100,8 @@ struct cdg_ctx {
     DevBuf dCmpCount, dCmpTarget, dCmpFields, dPatches;
     HostBuf hCmpCount, hCmpTarget, hCmpFields, hPatches;
     u64 nCompact = 0, nChangedLast = 0; bool correctedValid = false; double dbResUsed = 0; bool monotoneOffsets = true; bool packedUpload = false;
+    // packed uploads rebuild the DB bytes only when something reads them (a sequence with N, or a byte-consuming entry point)
+    DevBuf dSetFacts; bool bytesValid = true; bool patchesDirect = false;
     u64 nLines = 0, nKept = 0; bool linesValid = false, alnsValid = false, alnsFromText = false;
     // correction
     DevBuf dTables, dOut, dLik, dWideList, dRecvK, dRecvV, dRecv2, dQList, dPow31, dKey2Big; bool damageSet = false;
@@ -136,7 +138,7 @@ static cudaError_t cdg_launch_check(cdg_ctx *ctx) {
 
 // scalars block on the device: [0] scan total, [1] emitted records, [2] grouped count, [3] kept lines,
 // [4] changed bases, [5] (u32) extraCount, [6] (u32) overflow, [7] (u32) long count, [8] long scratch total, [9] (u32) sort ticket
-enum { SC_SCAN = 0, SC_EMIT, SC_GROUPED, SC_KEPT, SC_CHANGED, SC_EXTRA, SC_OVERFLOW, SC_NLONG, SC_LONGSCR, SC_TICKET, SC_WIDE, SC_QLIST, SC_ROUTE /*16 counters*/, SC_BOUNDS = SC_ROUTE + 16 /*17 bounds*/, SC_N = SC_BOUNDS + 20 };
+enum { SC_SCAN = 0, SC_EMIT, SC_GROUPED, SC_KEPT, SC_CHANGED, SC_EXTRA, SC_OVERFLOW, SC_NLONG, SC_LONGSCR, SC_TICKET, SC_WIDE, SC_QLIST, SC_PATCH, SC_ROUTE /*16 counters*/, SC_BOUNDS = SC_ROUTE + 16 /*17 bounds*/, SC_N = SC_BOUNDS + 20 };
 
 void rec(cdg_ctx *ctx, int e) { cudaEventRecord(ctx->ev[e], ctx->st); ctx->evValid[e] = true; }
 
@@ -277,7 +279,7 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
                    &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2, &ctx->dQList, &ctx->dPow31,
                    &ctx->dPairModel, &ctx->dPairIn, &ctx->dPairCons, &ctx->dPairOut, &ctx->dRecvIdK, &ctx->dRecvIdV, &ctx->dRouteTab,
-                   &ctx->dIdCnt, &ctx->dCmpCount, &ctx->dCmpTarget, &ctx->dCmpFields, &ctx->dPatches, &ctx->dKey2Big};
+                   &ctx->dIdCnt, &ctx->dCmpCount, &ctx->dCmpTarget, &ctx->dCmpFields, &ctx->dPatches, &ctx->dKey2Big, &ctx->dSetFacts};
     for (DevBuf *b : d) b->release();
     HostBuf *h[] = {&ctx->hHitRep, &ctx->hHitTgt, &ctx->hHitScore, &ctx->hHitDiag, &ctx->hHitDiag16, &ctx->hLineOff, &ctx->hLineT, &ctx->hKeep,
                     &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE,
@@ -302,10 +304,14 @@ static int pack_chunk(cdg_ctx *ctx, u64 seqLo, u64 seqHi) {
     if (seqHi <= seqLo) return 0;
     const u64 cnt = seqHi - seqLo;
     const unsigned pb = (unsigned) std::min<u64>((cnt * 32 + 255) / 256, (u64) ctx->smCount * 16);
-    if (ctx->packedUpload)   // cdg_upload_packed: the words are the input, the DB bytes are rebuilt from them
+    if (ctx->packedUpload) {   // cdg_upload_packed: the words are the input; the DB bytes are rebuilt only if a sequence holds an N
+        unsigned long long *flagged = ctx->dSetFacts.as<unsigned long long>();
+        cdgexp::sanitize_packed_kernel<<<(unsigned) ((cnt + 255) / 256), 256, 0, ctx->st>>>(ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dLen.as<u32>(),
+                                                                                           ctx->dWordOff.as<u64>(), seqLo, seqHi, ctx->dFlags.as<u8>(), flagged);
         cdgexp::unpack_kernel<<<pb, 256, 0, ctx->st>>>(ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dWordOff.as<u64>(),
-                                                       seqLo, seqHi, ctx->dData.as<u8>(), ctx->dFlags.as<u8>());
-    else
+                                                       seqLo, seqHi, ctx->dData.as<u8>(), flagged);
+        ctx->launches++;
+    } else
     cdgkmer::pack_kernel<<<pb, 256, 0, ctx->st>>>(ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dWordOff.as<u64>(), seqLo, seqHi,
                                                   ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dFlags.as<u8>());
     cdgalign::meta_kernel<<<(unsigned) ((cnt + 255) / 256), 256, 0, ctx->st>>>(ctx->dOff.as<u64>(), ctx->dWordOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dFlags.as<u8>(),
@@ -322,6 +328,23 @@ static int ensure_packed(cdg_ctx *ctx) {
     ctx->pending.clear();
     return 0;
 }
+// the DB byte layout of a packed upload, for the entry points that read or return bytes (no-op after cdg_upload_seqs)
+static int ensure_bytes(cdg_ctx *ctx) {
+    if (ctx->bytesValid) return 0;
+    if (int rc = ensure_packed(ctx)) return rc;
+    u64 flagged = 0;
+    CK(cudaMemcpyAsync(&flagged, ctx->dSetFacts.p, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (flagged == 0 && ctx->n) {   // (otherwise pack_chunk's conditional unpack has already run)
+        const unsigned pb = (unsigned) std::min<u64>((ctx->n * 32 + 255) / 256, (u64) ctx->smCount * 16);
+        cdgexp::unpack_kernel<<<pb, 256, 0, ctx->st>>>(ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dWordOff.as<u64>(),
+                                                       0, ctx->n, ctx->dData.as<u8>(), nullptr);
+        ctx->launches++;
+        CKL();
+    }
+    ctx->bytesValid = true;
+    return 0;
+}
 
 // chunks > 1: `data` and `offsets` are host memory; the DB bytes are copied in `chunks` pieces on the copy stream and the set is
 // packed lazily (ensure_packed / km_extract), so that the copy of one piece overlaps pack + extraction of the previous one
@@ -332,7 +355,7 @@ static int upload_impl(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, c
     if (n >= (1ull << 31)) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_upload_seqs: more than 2^31 sequences per context");
     CK(cudaSetDevice(ctx->device));
     if (!ctx->pending.empty()) { CK(cudaStreamSynchronize(ctx->copySt)); ctx->pending.clear(); }   // an upload nobody consumed
-    ctx->hitsValid = ctx->linesValid = ctx->alnsValid = false; ctx->packedUpload = false; ctx->correctedValid = false;
+    ctx->hitsValid = ctx->linesValid = ctx->alnsValid = false; ctx->packedUpload = false; ctx->correctedValid = false; ctx->bytesValid = true;
     ctx->n = n; ctx->dataBytes = data_bytes; ctx->qLo = 0; ctx->nQ = n;
     CK(ctx->dData.reserve(data_bytes + 64));
     CK(ctx->dOff.reserve(n * 8)); CK(ctx->dLen.reserve(n * 4)); CK(ctx->dExt.reserve(n)); CK(ctx->dFlags.reserve(n));
@@ -441,7 +464,8 @@ extern "C" int cdg_upload_packed(cdg_ctx *ctx, const uint64_t *words, const uint
     if (n_words >= (1ull << 32)) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_upload_packed: more than 2^32 packed words per context");
     CK(cudaSetDevice(ctx->device));
     if (!ctx->pending.empty()) { CK(cudaStreamSynchronize(ctx->copySt)); ctx->pending.clear(); }
-    ctx->hitsValid = ctx->linesValid = ctx->alnsValid = false; ctx->packedUpload = true; ctx->monotoneOffsets = true; ctx->correctedValid = false;
+    ctx->hitsValid = ctx->linesValid = ctx->alnsValid = false; ctx->packedUpload = true; ctx->monotoneOffsets = true; ctx->correctedValid = false; ctx->bytesValid = false;
+    CK(ctx->dSetFacts.reserve(64)); CK(cudaMemsetAsync(ctx->dSetFacts.p, 0, 64, ctx->st));
     ctx->n = n; ctx->qLo = 0; ctx->nQ = n;
     CK(ctx->dOff.reserve(n * 8)); CK(ctx->dLen.reserve(n * 4)); CK(ctx->dExt.reserve(n)); CK(ctx->dFlags.reserve(n));
     CK(ctx->dWordOff.reserve((n + 1) * 8)); CK(ctx->dLikOff.reserve((n + 1) * 8));
@@ -979,7 +1003,11 @@ static int export_patches(cdg_ctx *ctx, u64 b0, u64 b1, u64 nChanged, cdg_patche
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
     CK(ctx->dPatches.reserve((nChanged + 1) * 8)); CK(ctx->hPatches.reserve((nChanged + 1) * 8));
     u64 got = 0;
-    if (nChanged && b1 > b0) {
+    if (ctx->patchesDirect) {   // the correction kernel wrote the list itself (all of it lies in the context's query range)
+        if (nChanged) CK(cudaMemcpyAsync(ctx->hPatches.p, ctx->dPatches.p, nChanged * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        got = nChanged;
+    } else if (nChanged && b1 > b0) {
         CK(cudaMemsetAsync(sc + SC_SCAN, 0, 8, ctx->st));
         const u64 chunks = ((b1 + 15) >> 4) - (b0 >> 4);
         const unsigned blocks = (unsigned) std::min<u64>((chunks + 255) / 256, (u64) ctx->smCount * 16);
@@ -1055,16 +1083,23 @@ static int wait_exports(cdg_ctx *ctx) {
     return 0;
 }
 
-static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data, uint64_t *n_changed, double *lik) {
+// patchMode: corrected bases are emitted as patches (byte offset << 8 | letter) straight from the kernel, no corrected copy of the
+// DB bytes exists (cdg_iteration_compact, cdg_mg_finish without a byte output); a packed upload then never materialises bytes.
+// Falls back to the byte mode when the generic wide-counter kernel is needed or the patch list overflows.
+static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data, uint64_t *n_changed, double *lik, bool patchMode = false) {
     if (int rcp = ensure_packed(ctx)) return rcp;
     if (!ctx->alnsValid) return fail(ctx, CDG_ERR_ARG, "cdg_correct: no alignments (run cdg_rescore or cdg_set_alignments)");
     if (!ctx->damageSet) return fail(ctx, CDG_ERR_ARG, "cdg_correct: cdg_set_damage not called");
+    if (out_data) patchMode = false;
+    if (!patchMode) if (int rcb = ensure_bytes(ctx)) return rcb;
     const u64 n = ctx->nQ, qLo = ctx->qLo;
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
-    CK(ctx->dOut.reserve(ctx->dataBytes + 64));
+    const u64 patchCap = patchMode ? std::max<u64>(1ull << 20, ctx->totalBases / 32) : 0;
+    if (patchMode) { CK(ctx->dPatches.reserve((patchCap + 1) * 8)); CK(cudaMemsetAsync(sc + SC_PATCH, 0, 8, ctx->st)); }
+    else CK(ctx->dOut.reserve(ctx->dataBytes + 64));
     CK(cudaMemsetAsync(sc + SC_CHANGED, 0, 8, ctx->st));
     rec(ctx, EV_CO0);
-    CK(cudaMemcpyAsync(ctx->dOut.p, ctx->dData.p, ctx->dataBytes, cudaMemcpyDeviceToDevice, ctx->st));
+    if (!patchMode) CK(cudaMemcpyAsync(ctx->dOut.p, ctx->dData.p, ctx->dataBytes, cudaMemcpyDeviceToDevice, ctx->st));
     double *dLik = nullptr;
     if (lik) {
         CK(ctx->dLik.reserve((ctx->totalBases + 1) * 4 * 8));
@@ -1084,9 +1119,23 @@ static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data
     cdgalign::correct_fast_kernel<<<blocks, cdgalign::CF_WARPS * 32, sizeof(cdgalign::CorrSmem), ctx->st>>>(
         ctx->dQList.as<u32>(), (const u32 *) (sc + SC_QLIST), ctx->dData.as<u8>(), ctx->dMeta.as<cdgalign::SeqMeta>(), ctx->dWords.as<u64>(), qLo, n, ctx->dLineOff.as<u64>(), ctx->dLineT.as<u32>(), ctx->dKeep.as<u8>(), ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(),
         ctx->dQE.as<i32>(), ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), C, ctx->dTables.as<cdgalign::DamageTables>(), ctx->dLineSel.as<u8>(),
-        ctx->dOut.as<u8>(), sc + SC_CHANGED, ctx->dLikOff.as<u64>(), dLik, ctx->dWideList.as<u32>(), (u32 *) (sc + SC_WIDE));
+        patchMode ? nullptr : ctx->dOut.as<u8>(), sc + SC_CHANGED, ctx->dLikOff.as<u64>(), dLik, ctx->dWideList.as<u32>(), (u32 *) (sc + SC_WIDE),
+        patchMode ? ctx->dPatches.as<u64>() : nullptr, patchCap, sc + SC_PATCH);
     ctx->launches++;
     CKL();
+    if (patchMode) {
+        u64 h[3];
+        CK(cudaMemcpyAsync(&h[0], sc + SC_WIDE, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(&h[1], sc + SC_PATCH, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(&h[2], sc + SC_CHANGED, 8, cudaMemcpyDeviceToHost, ctx->st));
+        rec(ctx, EV_CO1);
+        CK(cudaStreamSynchronize(ctx->st));
+        if ((u32) h[0] != 0 || h[1] > patchCap) return run_correct(ctx, p, nullptr, n_changed, lik, false);   // deep pile-ups / very many corrections: byte mode
+        if (lik) { CK(cudaMemcpyAsync(lik, ctx->dLik.p, ctx->totalBases * 4 * 8, cudaMemcpyDeviceToHost, ctx->st)); CK(cudaStreamSynchronize(ctx->st)); }
+        if (n_changed) *n_changed = h[2];
+        ctx->nChangedLast = h[2]; ctx->correctedValid = true; ctx->patchesDirect = true;
+        return CDG_OK;
+    }
     // queries with more than 65535 counted targets (16-bit counters): generic kernel, usually an empty list
     cdgalign::correct_wide_kernel<<<ctx->smCount, cdgalign::CORR_WARPS * 32, 0, ctx->st>>>(
         ctx->dWideList.as<u32>(), (const u32 *) (sc + SC_WIDE),
@@ -1102,7 +1151,7 @@ static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data
     int rc = read_scalar(ctx, SC_CHANGED, &ch);
     if (rc) return rc;
     if (n_changed) *n_changed = ch;
-    ctx->nChangedLast = ch; ctx->correctedValid = true;
+    ctx->nChangedLast = ch; ctx->correctedValid = true; ctx->patchesDirect = false;
     return CDG_OK;
 }
 
@@ -1123,7 +1172,7 @@ extern "C" int cdg_iteration_compact(cdg_ctx *ctx, const cdg_iter_params *p, cdg
     if (alns && (rc = export_alns_compact(ctx, alns, true))) return rc;   // the export overlaps the correction kernel
     if (!alns) { u64 kept = 0; if ((rc = read_scalar(ctx, SC_KEPT, &kept))) return rc; ctx->nKept = kept; }
     u64 ch = 0;
-    rc = run_correct(ctx, &p->corr, nullptr, &ch, nullptr);
+    rc = run_correct(ctx, &p->corr, nullptr, &ch, nullptr, true);
     if (!rc && patches) rc = export_patches(ctx, 0, ctx->dataBytes, ch, patches);
     if (n_changed) *n_changed = ch;
     int rc2 = wait_exports(ctx);
@@ -1177,7 +1226,7 @@ static int run_pair_loglik(cdg_ctx *ctx, const cdg_pairs *P, const uint8_t *cons
     const u64 n = P->n;
     if (n == 0) return CDG_OK;
     CK(cudaSetDevice(ctx->device));
-    if (int rcp = ensure_packed(ctx)) return rcp;
+    if (int rcp = ensure_bytes(ctx)) return rcp;   // (packs first) the pair kernels read the DB bytes
     // validate on the host what would otherwise be an out-of-bounds device read
     for (u64 i = 0; i < n; i++) {
         if (P->query[i] >= ctx->n || P->target[i] >= ctx->n)
@@ -1612,7 +1661,7 @@ static int mg_finish_core(cdg_ctx *ctx, const cdg_rescore_params *rp, const cdg_
     else if (compact && (rc = export_alns_compact(ctx, compact, true))) return rc;
     if (!alns && !compact) { u64 kept = 0; if ((rc = read_scalar(ctx, SC_KEPT, &kept))) return rc; ctx->nKept = kept; }
     u64 ch = 0;
-    if ((rc = run_correct(ctx, cp, nullptr, &ch, nullptr))) return rc;
+    if ((rc = run_correct(ctx, cp, nullptr, &ch, nullptr, out_range == nullptr))) return rc;
     if (n_changed) *n_changed = ch;
     // corrected bytes of the rank's query range
     u64 b0 = 0, b1 = ctx->dataBytes;

@@ -9,11 +9,44 @@
 
 namespace cdgexp {
 
-// One warp per sequence.  words / xmask are sanitised in place (N positions and the padding of the last word hold code 0, mask
-// bits beyond the sequence are cleared) so that they are bit-identical to what pack_kernel derives from the same bytes.
-__global__ void __launch_bounds__(256) unpack_kernel(u64 *__restrict__ words, u32 *__restrict__ xmask, const u64 *__restrict__ off,
+// cdg_upload_packed, first step (one thread per sequence): the words / N mask are sanitised in place (N positions and the padding
+// of the last word hold code 0, mask bits beyond the sequence are cleared) so that they are bit-identical to what pack_kernel
+// derives from the same bytes; flags[seq] = the sequence holds an N; *flagged counts those sequences.  The DB byte layout is only
+// rebuilt (unpack_kernel) when some sequence holds an N — the byte paths of rescore / correction are reached through flagged
+// sequences only — or when a caller asks for bytes (ensure_bytes in cdg_api.cu).
+__global__ void __launch_bounds__(256) sanitize_packed_kernel(u64 *__restrict__ words, u32 *__restrict__ xmask, const u32 *__restrict__ len,
+                                                              const u64 *__restrict__ wordOff, u64 seqLo, u64 seqHi, u8 *__restrict__ flags,
+                                                              unsigned long long *__restrict__ flagged) {
+    const u64 seq = seqLo + (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    u32 any = 0;
+    if (seq < seqHi) {
+        const u32 L = len[seq];
+        const u64 w0 = wordOff[seq];
+        const u32 nw = (L + 31) >> 5;
+        for (u32 w = 0; w < nw; w++) {
+            const u32 c = L - (w << 5) < 32 ? L - (w << 5) : 32;
+            const u64 word = words[w0 + w];
+            const u32 xm0 = xmask[w0 + w];
+            u32 xm = xm0;
+            if (c < 32) xm &= ~(0xFFFFFFFFu >> c);
+            const u64 valid = c == 32 ? ~0ull : ~(~0ull >> (2 * c));
+            const u64 clean = word & valid & ~cdgkmer::interleave32(xm, xm);
+            if (clean != word) words[w0 + w] = clean;
+            if (xm != xm0) xmask[w0 + w] = xm;
+            any |= xm;
+        }
+        flags[seq] = any ? 1 : 0;
+    }
+    const u32 b = __ballot_sync(0xffffffffu, any != 0);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(flagged, (unsigned long long) __popc(b));
+}
+
+// One warp per sequence: the DB byte layout from sanitised words.  onlyIfFlagged (device scalar, may be null): return at once when it
+// is zero (no sequence holds an N: nothing reads the bytes).
+__global__ void __launch_bounds__(256) unpack_kernel(const u64 *__restrict__ words, const u32 *__restrict__ xmask, const u64 *__restrict__ off,
                                                      const u32 *__restrict__ len, const u64 *__restrict__ wordOff, u64 seqLo, u64 seqHi,
-                                                     u8 *__restrict__ data, u8 *__restrict__ flags) {
+                                                     u8 *__restrict__ data, const unsigned long long *__restrict__ onlyIfFlagged) {
+    if (onlyIfFlagged && *onlyIfFlagged == 0) return;
     const int lane = threadIdx.x & 31;
     const u64 gwarp = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64) gridDim.x * blockDim.x) >> 5;
     for (u64 seq = seqLo + gwarp; seq < seqHi; seq += nwarps) {
@@ -21,23 +54,16 @@ __global__ void __launch_bounds__(256) unpack_kernel(u64 *__restrict__ words, u3
         const u64 w0 = wordOff[seq];
         u8 *d = data + off[seq];
         const u32 nw = (L + 31) >> 5;
-        u32 any = 0;
         for (u32 w = 0; w < nw; w++) {
             const u32 c = L - (w << 5) < 32 ? L - (w << 5) : 32;
-            u64 word = words[w0 + w];
-            u32 xm = xmask[w0 + w];
-            if (c < 32) xm &= ~(0xFFFFFFFFu >> c);
-            const u64 valid = c == 32 ? ~0ull : ~(~0ull >> (2 * c));
-            word &= valid & ~cdgkmer::interleave32(xm, xm);
-            any |= xm;
+            const u64 word = words[w0 + w];
+            const u32 xm = xmask[w0 + w];
             if ((u32) lane < c) {
                 const u32 code = (u32) (word >> (62 - 2 * lane)) & 3u;
                 d[(w << 5) + lane] = ((xm >> (31 - lane)) & 1u) ? (u8) 'N' : (u8) cdg_num2aa((int) code);
             }
-            __syncwarp();
-            if (lane == 0) { words[w0 + w] = word; xmask[w0 + w] = xm; }
         }
-        if (lane == 0) { d[L] = (u8) '\n'; d[L + 1] = 0; flags[seq] = any ? 1 : 0; }
+        if (lane == 0) { d[L] = (u8) '\n'; d[L + 1] = 0; }
     }
 }
 

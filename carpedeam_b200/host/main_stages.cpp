@@ -7,12 +7,16 @@
 //
 // Host side only: DBReader/DBWriter-compatible file access and the text formats; all arithmetic happens in
 // libcarpedeam_gpu.so through the C ABI.  Errors print a message and exit(EXIT_FAILURE), as the reference does.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../../include/carpedeam_gpu.h"
 #include "formats.h"
@@ -45,6 +49,74 @@ void ck(cdg_ctx *ctx, int rc, const char *what) {
     if (rc != 0) die(std::string(what) + " failed: " + cdg_last_error(ctx));
 }
 
+// The implementation is pinned to the values the assembler workflow passes (tests/golden/cfg1_stage_argv.log): a flag given with
+// any other value would silently change the reference's output, so it is an error here.  Flags that cannot affect the
+// output (--threads, -v, --db-load-mode, --split-memory-limit, ...) are accepted as they are.
+struct Pinned { const char *flag; const char *value; };
+void require_pinned(const Args &a, const char *stage, std::initializer_list<Pinned> table) {
+    for (const Pinned &p : table) {
+        auto it = a.opt.find(p.flag);
+        if (it == a.opt.end()) continue;
+        const bool numeric = p.value[0] == '-' || (p.value[0] >= '0' && p.value[0] <= '9');
+        const bool same = numeric ? atof(it->second.c_str()) == atof(p.value) : it->second.find(p.value) != std::string::npos;
+        if (!same) die(std::string(stage) + ": " + p.flag + " " + it->second + " is not supported by carpedeam_gpu (implemented: " + p.flag + " " + p.value + ")");
+    }
+}
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+int host_threads(const Args &a) {
+    int t = (int) a.num("--threads", 0);
+#ifdef _OPENMP
+    if (t <= 0) t = omp_get_max_threads();
+#else
+    t = 1;
+#endif
+    return t < 1 ? 1 : t;
+}
+
+// Entries of queries [0, n) built by `threads` host threads, each over a contiguous block of queries with its own writer (the
+// reference's per-thread DBWriter, rescorediagonal.cpp:125-146,340-352), merged in query order into one data file.
+template <class F>
+void write_entries_parallel(const std::string &path, int dbtype, size_t n, int threads, F entryOf) {
+    if (threads > (int) (n / 1024 + 1)) threads = (int) (n / 1024 + 1);
+    std::vector<DbWriter> parts;
+    for (int t = 0; t < threads; t++) parts.emplace_back(path, dbtype);
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+    for (int t = 0; t < threads; t++) {
+        const size_t lo = n * (size_t) t / (size_t) threads, hi = n * (size_t) (t + 1) / (size_t) threads;
+        std::string entry;
+        for (size_t q = lo; q < hi; q++) {
+            entry.clear();
+            uint32_t key = 0; uint8_t ext = 0;
+            entryOf(q, entry, key, ext);
+            parts[t].write(entry.data(), entry.size(), key, ext);
+        }
+    }
+    for (int t = 1; t < threads; t++) parts[0].append(parts[t]);
+    parts[0].close();
+}
+
+// per-query variable-length records parsed by `threads` host threads into one CSR: parseOf(q, push) calls push(record)
+template <class R, class F>
+void parse_entries_parallel(size_t n, int threads, std::vector<uint64_t> &off, std::vector<R> &records, F parseOf) {
+    if (threads > (int) (n / 1024 + 1)) threads = (int) (n / 1024 + 1);
+    std::vector<std::vector<R>> part(threads);
+    off.assign(n + 1, 0);
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+    for (int t = 0; t < threads; t++) {
+        const size_t lo = n * (size_t) t / (size_t) threads, hi = n * (size_t) (t + 1) / (size_t) threads;
+        for (size_t q = lo; q < hi; q++) {
+            const size_t before = part[t].size();
+            parseOf(q, part[t]);
+            off[q + 1] = part[t].size() - before;   // count, turned into an offset below
+        }
+    }
+    for (size_t q = 0; q < n; q++) off[q + 1] += off[q];
+    records.resize(off[n]);
+    size_t pos = 0;
+    for (int t = 0; t < threads; t++) { std::copy(part[t].begin(), part[t].end(), records.begin() + pos); pos += part[t].size(); }
+}
+
 cdg_ctx *make_ctx() {
     cdg_ctx *ctx = nullptr;
     const char *dev = getenv("CDG_DEVICE");
@@ -62,7 +134,14 @@ void upload(cdg_ctx *ctx, const Db &db, std::vector<uint32_t> &lens) {
 int kmermatcher(int argc, char **argv) {
     Args a = parse_args(argc, argv, 2);
     if (a.pos.size() < 2) die("Usage: kmermatcher <i:sequenceDB> <o:prefDB> [options]");
+    require_pinned(a, "kmermatcher", {{"--sub-mat", "nucleotide.out"}, {"--alph-size", "nucl:5"}, {"--spaced-kmer-mode", "0"}, {"--adjust-kmer-len", "0"},
+                                      {"--mask", "0"}, {"--mask-lower-case", "0"}, {"--ignore-multi-kmer", "1"}, {"--compressed", "0"}, {"-c", "0"}});
+    const double t0 = now_ms();
     Db seq; open_db(a.pos[0], seq);
+    if (a.opt.count("--max-seq-len"))
+        for (size_t i = 0; i < seq.size(); i++)
+            if (seq.lengths[i] >= 2 && (double) (seq.lengths[i] - 2) > a.num("--max-seq-len", 65535)) die("kmermatcher: a sequence is longer than --max-seq-len (truncation is not implemented)");
+    const double t1 = now_ms();
     cdg_ctx *ctx = make_ctx();
     std::vector<uint32_t> lens;
     upload(ctx, seq, lens);
@@ -77,18 +156,19 @@ int kmermatcher(int argc, char **argv) {
     if (a.num("-c", 0.0) != 0.0) die("kmermatcher: only -c 0 (the assembler's setting) is supported");
     cdg_hits h;
     ck(ctx, cdg_kmermatch(ctx, &p, &h), "cdg_kmermatch");
-    DbWriter w(a.pos[1], DBTYPE_PREFILTER_REV_RES);
-    std::string entry; char buf[64];
-    uint64_t hi = 0;
-    for (size_t q = 0; q < seq.size(); q++) {
-        entry.clear();
+    const double t2 = now_ms();
+    // first hit of every representative (the hit list is sorted by representative)
+    std::vector<uint64_t> first(seq.size() + 1, 0);
+    for (uint64_t i = 0; i < h.n_hits; i++) first[h.rep[i] + 1]++;
+    for (size_t q = 0; q < seq.size(); q++) first[q + 1] += first[q];
+    write_entries_parallel(a.pos[1], DBTYPE_PREFILTER_REV_RES, seq.size(), host_threads(a), [&](size_t q, std::string &entry, uint32_t &key, uint8_t &ext) {
+        char buf[64];
         entry.append(buf, format_pref_line(buf, seq.keys[q], 0, 0));   // `rep 0 0` / singleton `key 0 0` (kmermatcher.cpp:836, :710-730)
-        bool isRep = false;
-        while (hi < h.n_hits && h.rep[hi] == q) { entry.append(buf, format_pref_line(buf, seq.keys[h.target[hi]], h.score[hi], h.diag[hi])); hi++; isRep = true; }
+        for (uint64_t i = first[q]; i < first[q + 1]; i++) entry.append(buf, format_pref_line(buf, seq.keys[h.target[i]], h.score[i], h.diag[i]));
         // only the singleton fill carries the ext flag (kmermatcher.cpp:727); entries of representatives are written without (:860,:923)
-        w.write(entry.data(), entry.size(), seq.keys[q], isRep ? 0 : seq.ext[q]);
-    }
-    w.close();
+        key = seq.keys[q]; ext = first[q + 1] > first[q] ? 0 : seq.ext[q];
+    });
+    fprintf(stderr, "carpedeam_gpu kmermatcher: read DB %.1f ms, upload + GPU + export %.1f ms, format + write DB %.1f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
     cdg_destroy(ctx);
     return EXIT_SUCCESS;
 }
@@ -98,25 +178,31 @@ int rescorediagonal(int argc, char **argv) {
     if (a.pos.size() < 4) die("Usage: rescorediagonal <i:queryDB> <i:targetDB> <i:prefDB> <o:alnDB> [options]");
     if (a.pos[0] != a.pos[1]) die("rescorediagonal: query and target database must be the same (assembler usage)");
     if ((int) a.num("--rescore-mode", 0) != 3) die("rescorediagonal: only --rescore-mode 3 is implemented");
+    require_pinned(a, "rescorediagonal", {{"--sub-mat", "nucleotide.out"}, {"--wrapped-scoring", "0"}, {"--filter-hits", "0"}, {"-a", "0"}, {"-c", "0"},
+                                          {"--min-aln-len", "0"}, {"--seq-id-mode", "0"}, {"--add-self-matches", "0"}, {"--sort-results", "0"},
+                                          {"--compressed", "0"}});
+    const double t0 = now_ms();
     Db seq; open_db(a.pos[0], seq);
     Db pref; open_db(a.pos[2], pref);
+    const double t1 = now_ms();
     cdg_ctx *ctx = make_ctx();
     std::vector<uint32_t> lens;
     upload(ctx, seq, lens);
-    std::vector<uint64_t> lineOff(seq.size() + 1, 0);
-    std::vector<uint32_t> tgt; std::vector<int32_t> score; std::vector<uint16_t> diag;
-    std::vector<PrefLine> lines;
-    for (size_t q = 0; q < seq.size(); q++) {
+    std::vector<uint64_t> lineOff;
+    std::vector<PrefLine> all;   // targetKey replaced by the target's index
+    parse_entries_parallel(seq.size(), host_threads(a), lineOff, all, [&](size_t q, std::vector<PrefLine> &out) {
         long pi = pref.find(seq.keys[q]);
-        lines.clear();
-        if (pi >= 0) parse_pref_entry((const char *) pref.data.data() + pref.offsets[pi], lines);
-        for (const PrefLine &l : lines) {
-            long ti = seq.find(l.targetKey);
+        const size_t before = out.size();
+        if (pi >= 0) parse_pref_entry((const char *) pref.data.data() + pref.offsets[pi], out);
+        for (size_t i = before; i < out.size(); i++) {
+            long ti = seq.find(out[i].targetKey);
             if (ti < 0) die("Invalid database read for database data file=" + a.pos[1]);
-            tgt.push_back((uint32_t) ti); score.push_back(l.score); diag.push_back(l.diag);
+            out[i].targetKey = (uint32_t) ti;
         }
-        lineOff[q + 1] = tgt.size();
-    }
+    });
+    std::vector<uint32_t> tgt(all.size()); std::vector<int32_t> score(all.size()); std::vector<uint16_t> diag(all.size());
+    for (size_t i = 0; i < all.size(); i++) { tgt[i] = all[i].targetKey; score[i] = all[i].score; diag[i] = all[i].diag; }
+    const double t2 = now_ms();
     ck(ctx, cdg_set_pref_lines(ctx, lineOff.data(), seq.size(), tgt.data(), score.data(), diag.data(), tgt.size()), "cdg_set_pref_lines");
     cdg_rescore_params p;
     p.min_seq_id = (float) a.num("--min-seq-id", 0.0);
@@ -124,19 +210,19 @@ int rescorediagonal(int argc, char **argv) {
     p.db_residues = 0;   // same DB: getAminoAcidDBSize() = sum of sequence lengths
     cdg_alns r;
     ck(ctx, cdg_rescore(ctx, &p, &r), "cdg_rescore");
-    DbWriter w(a.pos[3], DBTYPE_ALIGNMENT_RES);
-    std::string entry; char buf[256];
-    for (size_t q = 0; q < seq.size(); q++) {
-        entry.clear();
+    const double t3 = now_ms();
+    write_entries_parallel(a.pos[3], DBTYPE_ALIGNMENT_RES, seq.size(), host_threads(a), [&](size_t q, std::string &entry, uint32_t &key, uint8_t &ext) {
+        char buf[256];
         for (uint64_t l = r.line_off[q]; l < r.line_off[q + 1]; l++) {
             if (!r.keep[l]) continue;
             uint32_t t = r.target[l];
             entry.append(buf, format_aln_line(buf, seq.keys[t], r.bits[l], r.seq_id[l], r.evalue[l], r.q_start[l], r.q_end[l], (int32_t) lens[q],
                                               r.db_start[l], r.db_end[l], (int32_t) lens[t]));
         }
-        w.write(entry.data(), entry.size(), seq.keys[q], 0);
-    }
-    w.close();
+        key = seq.keys[q]; ext = 0;
+    });
+    fprintf(stderr, "carpedeam_gpu rescorediagonal: read DBs %.1f ms, parse pref text %.1f ms, upload + GPU + export %.1f ms, format + write DB %.1f ms\n",
+            t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);
     cdg_destroy(ctx);
     return EXIT_SUCCESS;
 }
@@ -144,28 +230,33 @@ int rescorediagonal(int argc, char **argv) {
 int ancient_correction(int argc, char **argv) {
     Args a = parse_args(argc, argv, 2);
     if (a.pos.size() < 3) die("Usage: ancient_correction <i:sequenceDB> <i:alnDB> <o:correctedDB> [options]");
+    require_pinned(a, "ancient_correction", {{"--compressed", "0"}});
+    const double t0 = now_ms();
     Db seq; open_db(a.pos[0], seq);
     Db aln; open_db(a.pos[1], aln);
+    const double t1 = now_ms();
     cdg_ctx *ctx = make_ctx();
     std::vector<uint32_t> lens;
     upload(ctx, seq, lens);
     cdg_damage dmg; char err[512];
     if (cdh_build_damage(a.get("--ancient-damage", "").c_str(), 0.01, &dmg, err, sizeof err) != 0) die(err);   // correction.cpp:153-156,196
     ck(ctx, cdg_set_damage(ctx, &dmg), "cdg_set_damage");
-    std::vector<uint64_t> off(seq.size() + 1, 0);
-    std::vector<uint32_t> tgt; std::vector<float> sid; std::vector<int32_t> qs, qe, ds, de;
-    std::vector<AlnLine> lines;
-    for (size_t q = 0; q < seq.size(); q++) {
+    std::vector<uint64_t> off;
+    std::vector<AlnLine> all;   // targetKey replaced by the target's index
+    parse_entries_parallel(seq.size(), host_threads(a), off, all, [&](size_t q, std::vector<AlnLine> &out) {
         long ai = aln.find(seq.keys[q]);
-        lines.clear();
-        if (ai >= 0) parse_aln_entry((const char *) aln.data.data() + aln.offsets[ai], lines);
-        for (const AlnLine &l : lines) {
-            long ti = seq.find(l.targetKey);
+        const size_t before = out.size();
+        if (ai >= 0) parse_aln_entry((const char *) aln.data.data() + aln.offsets[ai], out);
+        for (size_t i = before; i < out.size(); i++) {
+            long ti = seq.find(out[i].targetKey);
             if (ti < 0) die("Invalid database read for database data file=" + a.pos[0]);
-            tgt.push_back((uint32_t) ti); sid.push_back(l.seqId); qs.push_back(l.qStart); qe.push_back(l.qEnd); ds.push_back(l.dbStart); de.push_back(l.dbEnd);
+            out[i].targetKey = (uint32_t) ti;
         }
-        off[q + 1] = tgt.size();
-    }
+    });
+    const size_t A = all.size();
+    std::vector<uint32_t> tgt(A); std::vector<float> sid(A); std::vector<int32_t> qs(A), qe(A), ds(A), de(A);
+    for (size_t i = 0; i < A; i++) { tgt[i] = all[i].targetKey; sid[i] = all[i].seqId; qs[i] = all[i].qStart; qe[i] = all[i].qEnd; ds[i] = all[i].dbStart; de[i] = all[i].dbEnd; }
+    const double t2 = now_ms();
     ck(ctx, cdg_set_alignments(ctx, off.data(), seq.size(), tgt.data(), sid.data(), qs.data(), qe.data(), ds.data(), de.data(), tgt.size()),
        "cdg_set_alignments");
     cdg_corr_params p;
@@ -174,15 +265,14 @@ int ancient_correction(int argc, char **argv) {
     std::vector<uint8_t> out(seq.data.size());
     uint64_t changed = 0;
     ck(ctx, cdg_correct(ctx, &p, out.data(), &changed), "cdg_correct");
-    DbWriter w(a.pos[2], seq.dbtype ? seq.dbtype : DBTYPE_NUCLEOTIDES);
-    std::string entry;
-    for (size_t q = 0; q < seq.size(); q++) {
+    const double t3 = now_ms();
+    write_entries_parallel(a.pos[2], seq.dbtype ? seq.dbtype : DBTYPE_NUCLEOTIDES, seq.size(), host_threads(a), [&](size_t q, std::string &entry, uint32_t &key, uint8_t &ext) {
         entry.assign((const char *) out.data() + seq.offsets[q], lens[q]);
         entry.push_back('\n');                                           // correction.cpp:465-470
-        w.write(entry.data(), entry.size(), seq.keys[q], seq.ext[q]);
-    }
-    w.close();
-    fprintf(stderr, "ancient_correction: %llu bases corrected\n", (unsigned long long) changed);
+        key = seq.keys[q]; ext = seq.ext[q];
+    });
+    fprintf(stderr, "carpedeam_gpu ancient_correction: %llu bases corrected; read DBs %.1f ms, parse aln text %.1f ms, upload + GPU + export %.1f ms, write DB %.1f ms\n",
+            (unsigned long long) changed, t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);
     cdg_destroy(ctx);
     return EXIT_SUCCESS;
 }

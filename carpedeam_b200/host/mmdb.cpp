@@ -71,6 +71,12 @@ void DbWriter::write(const char *payload, size_t len, uint32_t key, uint8_t extF
     entries.push_back(e);
 }
 
+void DbWriter::append(const DbWriter &other) {
+    const uint64_t shift = data.size();
+    data.insert(data.end(), other.data.begin(), other.data.end());
+    for (Entry e : other.entries) { e.off += shift; entries.push_back(e); }
+}
+
 void DbWriter::close() {
     FILE *f = fopen(path.c_str(), "wb");
     if (!f) die("Could not open " + path + " for writing!");

@@ -35,6 +35,7 @@ struct DbWriter {
     DbWriter(const std::string &p, int type) : path(p), dbtype(type) {}
     // appends payload + '\0' (DBWriter::writeData adds the null byte, DBWriter.cpp:360-407)
     void write(const char *payload, size_t len, uint32_t key, uint8_t extFlag);
+    void append(const DbWriter &other);   // entries of another (per-thread) writer behind this one's
     void close();   // data, .index (sorted by key, 4 columns), .dbtype
 };
 

@@ -83,7 +83,7 @@ def main():
                 f.write(blob)
     manifest.append("%s  out.fasta" % hashlib.sha256(open(work + "/out.fasta", "rb").read()).hexdigest())
     open(os.path.join(GOLD, "MANIFEST.sha256"), "w").write("\n".join(manifest) + "\n")
-    for p in ("dhigh5p.prof", "dhigh3p.prof"):
+    for p in ("dhigh5p.prof", "dhigh3p.prof", "test_data.fq.gz"):     # the run's inputs (example data), for the workflow test on the GPU box
         shutil.copy(REF + "/example/" + p, os.path.join(GOLD, p))
     # which kmermatcher input belongs to which pref: see the stage argv lines of run.log
     log = [l for l in open(work + "/run.log") if l.startswith(("kmermatcher ", "rescorediagonal ", "ancient_correction "))]

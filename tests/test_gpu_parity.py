@@ -492,6 +492,15 @@ def test_deep_pileup_uses_wide_counters(ctx, oracle):
     s, hits, alns, out, changed = _run_both(ctx, oracle, seqs)
     lo = alns["line_off"].astype(np.int64)
     assert (np.diff(lo)).max() > 65536
+    # the compact path emits patches straight from the fast kernel and never builds bytes for a packed upload; a query for the
+    # wide kernel makes it fall back to the byte mode — same result
+    import carpedeam_b200 as cd
+    words, nmask, _ = cd.pack_seqs(s.blob, s.off, s.len)
+    ctx.upload_packed(words, nmask, s.len, s.ext)
+    ip = cd.IterParams(cd.kmer_params(), cd.RescoreParams(0.9, 0.001, 0), cd.CorrParams(0.9, 0.99))
+    ca, pa = cd.AlnsCompact(), cd.Patches()
+    assert ctx.iteration_compact(ip, ca, pa) == changed
+    assert np.array_equal(cd.apply_patches(s.blob, pa), out)
 
 
 def test_empty_set_is_an_error_or_empty_result():
@@ -632,7 +641,7 @@ def _kept(alns):
     return out
 
 
-@pytest.mark.parametrize("case", ["golden reads", "golden contigs k=22", "synthetic with N and lower case", "long contigs (32-bit fields)"])
+@pytest.mark.parametrize("case", ["golden reads", "golden contigs k=22", "synthetic with N and lower case", "synthetic with N", "long contigs (32-bit fields)"])
 def test_compact_outputs_equal_full_outputs(ctx, case):
     """cdg_iteration_compact (kept alignments as 14-byte records with implicit self lines, corrected reads as patches) expanded
     on the host == cdg_iteration's full-fidelity outputs, field for field; the packed upload (2-bit words + N mask in, DB bytes
@@ -647,6 +656,10 @@ def test_compact_outputs_equal_full_outputs(ctx, case):
     elif case == "synthetic with N and lower case":
         seqs = synth_reads(20000, 100000, 31, n_frac=0.002)
         seqs[7] = seqs[7].lower(); seqs[11] = b"N" * 40; seqs[12] = seqs[13]
+        s = SeqSet(seqs)
+    elif case == "synthetic with N":      # packed upload of a set with N: the device rebuilds the DB bytes (byte paths of rescore / correction)
+        seqs = synth_reads(20000, 100000, 32, n_frac=0.003)
+        seqs[11] = b"N" * 40; seqs[12] = seqs[13]
         s = SeqSet(seqs)
     else:
         rng = np.random.default_rng(5)
@@ -682,6 +695,9 @@ def test_compact_outputs_equal_full_outputs(ctx, case):
         assert ca.n_alns <= int(alns["keep"].sum())
         if case == "golden reads":
             assert ca.n_alns == int(alns["keep"].sum()) - s.n
+        if name == "packed":      # a byte-returning call after the packed upload: the library rebuilds the DB bytes on demand
+            _, alns3, out3, ch3 = ctx.iteration(kmer=kp)
+            assert np.array_equal(out3, out) and ch3 == changed and np.array_equal(alns3["keep"], alns["keep"])
     # stand-alone stage exports after cdg_rescore / cdg_correct
     ctx.upload(s.blob, s.off, s.len, s.ext)
     ctx.kmermatch(kp, fetch=False)
