@@ -52,9 +52,15 @@ CDG_D u64 get_bases(const u64 *__restrict__ w, u32 p, u32 c) {
     return c == 32 ? v : (v & ~(~0ull >> (2 * c)));
 }
 // c bases of revcomp(seq) starting at revcomp position a
+CDG_D u64 rev2bit64_dev(u64 x) {   // reverse the 32 2-bit groups: two BREV + one swap inside every group (cdg_rev2bit64 is the portable form)
+    u32 lo = __brev((u32) (x >> 32)), hi = __brev((u32) x);
+    lo = ((lo >> 1) & 0x55555555u) | ((lo & 0x55555555u) << 1);
+    hi = ((hi >> 1) & 0x55555555u) | ((hi & 0x55555555u) << 1);
+    return ((u64) hi << 32) | lo;
+}
 CDG_D u64 get_bases_rc(const u64 *__restrict__ w, u32 L, u32 a, u32 c) {
     u64 x = get_bases(w, L - a - c, c);            // forward bases, left aligned
-    u64 r = cdg_rev2bit64(x) << (2 * (32 - c));    // reversed, left aligned again
+    u64 r = rev2bit64_dev(x) << (2 * (32 - c));    // reversed, left aligned again
     r ^= 0xAAAAAAAAAAAAAAAAull;
     return c == 32 ? r : (r & ~(~0ull >> (2 * c)));
 }
@@ -115,8 +121,7 @@ CDG_D LocalAln by_diagonal(bool fast, const u64 *qw, const u8 *qa, u32 qLen, boo
 }
 
 __global__ void __launch_bounds__(256) rescore_kernel(
-    const u8 *__restrict__ data, const u64 *__restrict__ off, const u32 *__restrict__ len, const u64 *__restrict__ words,
-    const u64 *__restrict__ wordOff, const u8 *__restrict__ flags,
+    const u8 *__restrict__ data, const SeqMeta *__restrict__ meta, const u64 *__restrict__ words,
     const u32 *__restrict__ lineQ, const u32 *__restrict__ lineT, const i32 *__restrict__ linePref, const u16 *__restrict__ lineDiag,
     u64 M, RescoreParams P,
     u8 *__restrict__ keep, i32 *__restrict__ score, i32 *__restrict__ bits, double *__restrict__ evalue, float *__restrict__ seqId,
@@ -126,12 +131,13 @@ __global__ void __launch_bounds__(256) rescore_kernel(
     u32 kept = 0;
     if (l < M) {
         const u32 q = lineQ[l], t = lineT[l];
-        const u32 qLen = len[q], tLen = len[t];
+        const SeqMeta qm = meta[q], tm = meta[t];   // one 16-byte load per sequence (offset, first word, length, flags)
+        const u32 qLen = qm.lenFlags & META_LEN, tLen = tm.lenFlags & META_LEN;
         const bool isRev = linePref[l] < 0;
         const bool isIdentity = q == t;
-        const bool fast = !(flags[q] | flags[t]);
-        const u64 *qw = words + wordOff[q], *tw = words + wordOff[t];
-        const u8 *qa = data + off[q], *ta = data + off[t];
+        const bool fast = !((qm.lenFlags | tm.lenFlags) & META_EXC);
+        const u64 *qw = words + qm.wordOff, *tw = words + tm.wordOff;
+        const u8 *qa = data + qm.off, *ta = data + tm.off;
         const u32 diag16 = lineDiag[l];
         LocalAln mx; mx.startPos = -1; mx.endPos = -1; mx.score = 0; mx.diagonalLen = 0; mx.dist = 0; mx.diagonal = 0; mx.idCnt = 0;
         if (qLen > 0 && tLen > 0) {
@@ -423,6 +429,63 @@ CDG_D void count_column_packed(const u64 *__restrict__ tw, u32 dL, bool rev, u32
     mask |= 1ull << idx;
 }
 
+// ---- per-line preparation of the correction (correction.cpp:273-323, :353-359), one thread per alignment line ------------
+// Everything of pass 2 that does not depend on the query's average coverage: the RY identity of the pair (getRYSeqId), the
+// thresholds, and — for plain ACGT pairs — the columns where the oriented target differs from the query.  The warp-per-query
+// kernel then only combines lines (it used to do this work with one lane per line, mostly idle lanes).
+//   prep[l]: bit 0 the line can be counted (usable, RY identity and sequence identity above their thresholds, target not
+//            ext-flagged), bit 1 it satisfies one of the two end conditions (:303-311), bit 2 reverse strand, bit 3 a sequence of
+//            the pair needs the byte path
+//   alnLen[l]: Matcher::computeAlnLength of a kept line (0 otherwise) for the average coverage of pass 1 (:220-245)
+//   mism[3l..3l+2]: mismatch columns of query words 0..2 (bit 62-2j = column 32w+j), plain pairs only
+static constexpr u8 PREP_CAND = 1, PREP_END = 2, PREP_REV = 4, PREP_BYTES = 8;
+__global__ void __launch_bounds__(256) corr_prep_kernel(
+    const u8 *__restrict__ data, const SeqMeta *__restrict__ meta, const u64 *__restrict__ words, u64 qLo, const u64 *__restrict__ lineOff,
+    const u32 *__restrict__ lineQ, const u32 *__restrict__ lineT, const u8 *__restrict__ keep, const float *__restrict__ seqId,
+    const i32 *__restrict__ qS_, const i32 *__restrict__ qE_, const i32 *__restrict__ dS_, const i32 *__restrict__ dE_, u64 M,
+    CorrParams P, u8 *__restrict__ prep, u32 *__restrict__ alnLen, u64 *__restrict__ mism) {
+    const u64 l = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= M) return;
+    u8 pr = 0; u32 al = 0;
+    if (keep[l]) {
+        i32 qs = qS_[l], qe = qE_[l], ds = dS_[l], de = dE_[l];
+        al = (u32) (max(abs(qe - qs), abs(de - ds)) + 1);
+        const u32 q = lineQ[l];
+        const u64 ql = q - qLo;
+        if (lineOff[ql + 1] - lineOff[ql] > 1) {   // a query with a single line is never touched (coverage <= 1)
+            const SeqMeta qm = meta[q], tm = meta[lineT[l]];
+            if (!(tm.lenFlags & META_EXT)) {
+                const u32 qLen = qm.lenFlags & META_LEN, dL = tm.lenFlags & META_LEN;
+                const bool sane = (((u32) qs | (u32) qe | (u32) ds | (u32) de) >> 30) == 0;   // no negative / overflowing coordinate
+                const i32 aln = sane ? (i32) al : 0;
+                bool rev = false;
+                if (qs > qe) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; rev = true; }
+                const bool packed = !((qm.lenFlags | tm.lenFlags) & META_EXC);
+                // (see correct_wide_kernel: alignments shorter than 30 never count, out-of-sequence coordinates never load)
+                const bool usable = aln >= 30 && qs >= 0 && ds >= 0 && (u32) (qs + aln) <= qLen && (u32) (ds + aln) <= dL;
+                u32 dist = 0;
+                u64 m0 = 0, m1 = 0, m2 = 0;
+                if (!usable) {}
+                else if (packed) dist = ry_dist_mismatch(words + qm.wordOff, (u32) qs, words + tm.wordOff, dL, rev, (u32) ds, (u32) aln, m0, m1, m2);
+                else {
+                    const u8 *qb = data + qm.off, *ts = data + tm.off;
+                    for (i32 p = 0; p < aln; p++) dist += (ry_map(qb[qs + p]) != ry_map(t_char(ts, dL, rev, (u32) (ds + p)))) ? 1u : 0u;
+                }
+                const float ry = (float) ((u32) aln - dist) / (float) aln;   // getRYSeqId (nuclassembleUtil.cpp:78-92)
+                float thr = P.ryThr;
+                if (aln <= 100) { thr = ((float) aln - 1) / (float) aln; thr = floorf(thr * 1000) / 1000; }
+                const float sid = P.roundSeqId ? seqid_text_roundtrip(seqId[l]) : seqId[l];
+                if (usable && ry >= thr && sid >= P.seqIdThr) {
+                    pr = PREP_CAND | (rev ? PREP_REV : 0) | (packed ? 0 : PREP_BYTES);
+                    if ((ds == 0 && (u32) qe == qLen - 1) || (qs == 0 && de == (i32) dL - 1)) pr |= PREP_END;
+                    if (packed) { mism[3 * l] = m0; mism[3 * l + 1] = m1; mism[3 * l + 2] = m2; }
+                }
+            }
+        }
+    }
+    prep[l] = pr; alnLen[l] = al;
+}
+
 // queries with more than one line (only those can change): compact list, order irrelevant
 __global__ void __launch_bounds__(256) multi_line_queries_kernel(const u64 *__restrict__ lineOff, u64 n, u32 *__restrict__ list, u32 *__restrict__ count) {
     const u64 q = (u64) blockIdx.x * blockDim.x + threadIdx.x;
@@ -444,7 +507,8 @@ __global__ void __launch_bounds__(CF_WARPS * 32, 4) correct_fast_kernel(
     CorrParams P, const DamageTables *__restrict__ tablesG, u8 *__restrict__ lineSel, u8 *__restrict__ out,
     unsigned long long *__restrict__ changed, const u64 *__restrict__ likOff, double *__restrict__ likOut,
     u32 *__restrict__ wideList, u32 *__restrict__ wideCount,
-    u64 *__restrict__ patches /*out == nullptr: corrected bases go here as byte offset << 8 | letter*/, u64 patchCap, unsigned long long *__restrict__ patchCount) {
+    u64 *__restrict__ patches /*out == nullptr: corrected bases go here as byte offset << 8 | letter*/, u64 patchCap, unsigned long long *__restrict__ patchCount,
+    const u8 *__restrict__ prep, const u32 *__restrict__ alnLen, const u64 *__restrict__ mism /*corr_prep_kernel*/) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     CorrSmem &S = *reinterpret_cast<CorrSmem *>(smemRaw);
     for (int i = threadIdx.x; i < (int) (sizeof(DamageTables) / sizeof(double)); i += blockDim.x) ((double *) &S.T)[i] = ((const double *) tablesG)[i];
@@ -492,79 +556,46 @@ __global__ void __launch_bounds__(CF_WARPS * 32, 4) correct_fast_kernel(
         const u64 *qw = words + qm.wordOff;
         const bool qExc = (qm.lenFlags & META_EXC) != 0;
         const bool qExt = (qm.lenFlags & META_EXT) != 0;
-        // pass 1 (correction.cpp:220-245): exact integer sum of the alignment lengths -> avCov
-        const bool single = (l1 - l0) <= 32;   // one line per lane: pass 1 and pass 2 share their loads
-        u8 myKeep = 0; u32 myT = 0; i32 mqs = 0, mqe = 0, mds = 0, mde = 0;
+        // pass 1 (correction.cpp:220-245): exact integer sum of the alignment lengths (corr_prep_kernel: 0 for lines not kept) -> avCov
         unsigned long long sum = 0;
-        if (single) {
-            const u64 l = l0 + lane;
-            if (l < l1) { myKeep = keep[l]; myT = lineT[l]; mqs = qS_[l]; mqe = qE_[l]; mds = dS_[l]; mde = dE_[l]; }
-            if (myKeep) sum = (unsigned long long) (max(abs(mqe - mqs), abs(mde - mds)) + 1);
-        } else {
-            for (u64 l = l0 + lane; l < l1; l += 32)
-                if (keep[l]) sum += (unsigned long long) (max(abs(qE_[l] - qS_[l]), abs(dE_[l] - dS_[l])) + 1);
-        }
+        for (u64 l = l0 + lane; l < l1; l += 32) sum += (unsigned long long) alnLen[l];
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
         float avCov;
         if (sum < (1ull << 24)) avCov = (float) sum;   // every partial sum of the reference's float accumulation is exact
         else {
             avCov = 0.f;
-            for (u64 l = l0; l < l1; l++) if (keep[l]) avCov += (float) (max(abs(qE_[l] - qS_[l]), abs(dE_[l] - dS_[l])) + 1);
+            for (u64 l = l0; l < l1; l++) if (keep[l]) avCov += (float) alnLen[l];
         }
         avCov = avCov / (float) qLen;
-        // pass 2 (:273-323, :353-359), one line per lane
+        // pass 2 (:273-323, :353-359), one line per lane: the per-line part comes from corr_prep_kernel, the coverage rule is applied here
         u32 nSel = 0;
         u64 mm0 = 0, mm1 = 0, mm2 = 0;   // columns where one of this lane's counted targets differs from the query
         bool compact = S.domOK && likOut == nullptr && !qExc && qLen <= CF_COMPACT_LEN;
         for (u64 lb = l0; lb < l1; lb += 32) {
             const u64 l = lb + lane;
             u8 sel = 0;
-            u64 tOff = 0; u32 dL = 0, tWOff = 0, tPlain = 0; i32 qs = 0, aln = 0, ds = 0;
-            if (!single && l < l1) { myKeep = keep[l]; if (myKeep) { myT = lineT[l]; mqs = qS_[l]; mqe = qE_[l]; mds = dS_[l]; mde = dE_[l]; } }
-            if (l < l1 && myKeep) {
-                const SeqMeta tm = meta[myT];
-                if (!(tm.lenFlags & META_EXT)) {
-                    dL = tm.lenFlags & META_LEN; tOff = tm.off; tWOff = tm.wordOff; tPlain = (tm.lenFlags & META_EXC) ? 0u : 2u;
-                    i32 qe = mqe, de = mde;
-                    qs = mqs; ds = mds;
-                    const bool sane = (((u32) qs | (u32) qe | (u32) ds | (u32) de) >> 30) == 0;   // no negative / overflowing coordinate
-                    aln = sane ? max(abs(qe - qs), abs(de - ds)) + 1 : 0;
-                    bool rev = false;
-                    if (qs > qe) { i32 x = qs; qs = qe; qe = x; i32 d0 = ds; ds = (i32) dL - de - 1; de = (i32) dL - d0 - 1; rev = true; }
-                    u32 dist = 0;
-                    u64 lm0 = 0, lm1 = 0, lm2 = 0;
-                    const bool packed = !qExc && !(tm.lenFlags & META_EXC);
-                    // (see correct_wide_kernel: alignments shorter than 30 never count, out-of-sequence coordinates never load)
-                    const bool usable = aln >= 30 && qs >= 0 && ds >= 0 && (u32) (qs + aln) <= qLen && (u32) (ds + aln) <= dL;
-                    if (!usable) {}
-                    else if (packed) dist = ry_dist_mismatch(qw, (u32) qs, words + tm.wordOff, dL, rev, (u32) ds, (u32) aln, lm0, lm1, lm2);
-                    else {
-                        const u8 *ts = data + tOff;
-                        for (i32 p = 0; p < aln; p++) dist += (ry_map(q[qs + p]) != ry_map(t_char(ts, dL, rev, (u32) (ds + p)))) ? 1u : 0u;
-                    }
-                    const float ry = (float) ((u32) aln - dist) / (float) aln;   // getRYSeqId (nuclassembleUtil.cpp:78-92)
-                    float thr = P.ryThr;
-                    if (aln <= 100) { thr = ((float) aln - 1) / (float) aln; thr = floorf(thr * 1000) / 1000; }
-                    const bool pick = (ry >= thr && ds == 0 && (u32) qe == qLen - 1) || (ry >= thr && qs == 0 && de == (i32) dL - 1) ||
-                                      (ry >= thr && avCov < 50);
-                    const float sid = P.roundSeqId ? seqid_text_roundtrip(seqId[l]) : seqId[l];
-                    if (usable && pick && ry >= thr && sid >= P.seqIdThr) {
-                        sel = rev ? 2 : 1;
-                        if (packed) { mm0 |= lm0; mm1 |= lm1; mm2 |= lm2; } else sel |= 4;   // 4: a counted target needs the byte path
-                    }
-                }
-            }
-            if (__any_sync(0xffffffffu, sel & 4)) compact = false;
-            sel &= 3;
+            const u8 pr = l < l1 ? prep[l] : (u8) 0;
+            if ((pr & PREP_CAND) && ((pr & PREP_END) || avCov < 50)) sel = (pr & PREP_REV) ? 2 : 1;
+            if (sel && (pr & PREP_BYTES)) compact = false;   // a counted target needs the byte path (made warp-uniform below)
             if (l < l1) lineSel[l] = sel;
             const u32 b = __ballot_sync(0xffffffffu, sel != 0);
             if (sel) {
+                if (!(pr & PREP_BYTES)) { mm0 |= mism[3 * l]; mm1 |= mism[3 * l + 1]; mm2 |= mism[3 * l + 2]; }
                 const u32 slot = nSel + __popc(b & ((1u << lane) - 1));
-                if (slot < CF_CACHE) { LC.tOff[slot] = tOff; LC.dL[slot] = dL; LC.qs[slot] = qs; LC.aln[slot] = aln; LC.ds[slot] = ds; LC.rev[slot] = (sel == 2 ? 1u : 0u) | tPlain; LC.wOff[slot] = tWOff; }
+                if (slot < CF_CACHE) {
+                    const SeqMeta tm = meta[lineT[l]];
+                    const u32 dL = tm.lenFlags & META_LEN;
+                    i32 qs = qS_[l], qe = qE_[l], ds = dS_[l], de = dE_[l];
+                    const i32 aln = max(abs(qe - qs), abs(de - ds)) + 1;
+                    if (sel == 2) { i32 x = qs; qs = qe; qe = x; ds = (i32) dL - de - 1; }
+                    LC.tOff[slot] = tm.off; LC.dL[slot] = dL; LC.qs[slot] = qs; LC.aln[slot] = aln; LC.ds[slot] = ds;
+                    LC.rev[slot] = (sel == 2 ? 1u : 0u) | ((tm.lenFlags & META_EXC) ? 0u : 2u); LC.wOff[slot] = tm.wordOff;
+                }
             }
             nSel += __popc(b);
         }
+        compact = __all_sync(0xffffffffu, compact);
         if (nSel <= 1) continue;
         if (nSel > P.wideThreshold) {   // 16-bit counters could overflow (> 65535): hand over to the generic kernel
             if (lane == 0) { u32 s = atomicAdd(wideCount, 1u); wideList[s] = (u32) qi; }

@@ -101,7 +101,7 @@ struct cdg_ctx {
     HostBuf hCmpCount, hCmpTarget, hCmpFields, hPatches;
     u64 nCompact = 0, nChangedLast = 0; bool correctedValid = false; double dbResUsed = 0; bool monotoneOffsets = true; bool packedUpload = false;
     // packed uploads rebuild the DB bytes only when something reads them (a sequence with N, or a byte-consuming entry point)
-    DevBuf dSetFacts; bool bytesValid = true; bool patchesDirect = false;
+    DevBuf dSetFacts, dSlowList, dPrep, dAlnLen, dMism; bool bytesValid = true; bool patchesDirect = false;
     u64 nLines = 0, nKept = 0; bool linesValid = false, alnsValid = false, alnsFromText = false;
     // correction
     DevBuf dTables, dOut, dLik, dWideList, dRecvK, dRecvV, dRecv2, dQList, dPow31, dKey2Big; bool damageSet = false;
@@ -138,7 +138,7 @@ static cudaError_t cdg_launch_check(cdg_ctx *ctx) {
 
 // scalars block on the device: [0] scan total, [1] emitted records, [2] grouped count, [3] kept lines,
 // [4] changed bases, [5] (u32) extraCount, [6] (u32) overflow, [7] (u32) long count, [8] long scratch total, [9] (u32) sort ticket
-enum { SC_SCAN = 0, SC_EMIT, SC_GROUPED, SC_KEPT, SC_CHANGED, SC_EXTRA, SC_OVERFLOW, SC_NLONG, SC_LONGSCR, SC_TICKET, SC_WIDE, SC_QLIST, SC_PATCH, SC_ROUTE /*16 counters*/, SC_BOUNDS = SC_ROUTE + 16 /*17 bounds*/, SC_N = SC_BOUNDS + 20 };
+enum { SC_SCAN = 0, SC_EMIT, SC_GROUPED, SC_KEPT, SC_CHANGED, SC_EXTRA, SC_OVERFLOW, SC_NLONG, SC_LONGSCR, SC_TICKET, SC_WIDE, SC_QLIST, SC_PATCH, SC_SLOW, SC_ROUTE /*16 counters*/, SC_BOUNDS = SC_ROUTE + 16 /*17 bounds*/, SC_N = SC_BOUNDS + 20 };
 
 void rec(cdg_ctx *ctx, int e) { cudaEventRecord(ctx->ev[e], ctx->st); ctx->evValid[e] = true; }
 
@@ -279,7 +279,7 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
                    &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2, &ctx->dQList, &ctx->dPow31,
                    &ctx->dPairModel, &ctx->dPairIn, &ctx->dPairCons, &ctx->dPairOut, &ctx->dRecvIdK, &ctx->dRecvIdV, &ctx->dRouteTab,
-                   &ctx->dIdCnt, &ctx->dCmpCount, &ctx->dCmpTarget, &ctx->dCmpFields, &ctx->dPatches, &ctx->dKey2Big, &ctx->dSetFacts};
+                   &ctx->dIdCnt, &ctx->dCmpCount, &ctx->dCmpTarget, &ctx->dCmpFields, &ctx->dPatches, &ctx->dKey2Big, &ctx->dSetFacts, &ctx->dSlowList, &ctx->dPrep, &ctx->dAlnLen, &ctx->dMism};
     for (DevBuf *b : d) b->release();
     HostBuf *h[] = {&ctx->hHitRep, &ctx->hHitTgt, &ctx->hHitScore, &ctx->hHitDiag, &ctx->hHitDiag16, &ctx->hLineOff, &ctx->hLineT, &ctx->hKeep,
                     &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE,
@@ -610,6 +610,16 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
         if (perSm < 1) perSm = 1;
     }
     const int shortBlocks = ctx->smCount * perSm;
+    static int groupPerSm[3] = {0, 0, 0};
+    if (!groupPerSm[0]) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&groupPerSm[0], extract_group_kernel<8, 8, true>, EX_WARPS * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&groupPerSm[1], extract_group_kernel<16, 8, true>, EX_WARPS * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&groupPerSm[2], extract_group_kernel<32, 8, true>, EX_WARPS * 32, 0);
+        for (int &g : groupPerSm) if (g < 1) g = 1;
+    }
+    const int groupBlocks[3] = {ctx->smCount * groupPerSm[0], ctx->smCount * groupPerSm[1], ctx->smCount * groupPerSm[2]};
+    CK(ctx->dSlowList.reserve((n + 1) * 4));
+    CK(cudaMemsetAsync(sc + SC_SLOW, 0, 8, ctx->st));
     const u64 gridWarps = (u64) shortBlocks * EX_WARPS;
     CK(ctx->dShortScratch.reserve(gridWarps * 2 * EX_MAXW * sizeof(WinRec)));
     CK(ctx->dShortKeep.reserve(gridWarps * EX_MAXW));
@@ -622,16 +632,30 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
         if (piece.ev) { CK(cudaStreamWaitEvent(ctx->st, piece.ev, 0)); if ((rc = pack_chunk(ctx, piece.seqLo, piece.seqHi))) return rc; }
         E.seqLo = piece.seqLo; E.seqHi = piece.seqHi;
         const u32 maxW = ctx->maxLen >= (u32) p->k ? ctx->maxLen - p->k + 1 : 0;   // short sequences have <= 256 windows
-#define CDG_EXTRACT_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dPow31.as<u64>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT, identityMode == 2 ? ctx->ordV : (const u64 *) nullptr, ctx->dSlotRank.as<u64>())
+#define CDG_EXTRACT_ARGS_(LIST, LISTN) (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dPow31.as<u64>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT, identityMode == 2 ? ctx->ordV : (const u64 *) nullptr, ctx->dSlotRank.as<u64>(), LIST, LISTN)
         // the 16-bit XXH64 score of a window only matters for ownership (hash range, owner rank) and inside the exact replay
         const bool noScore = hashLo == 0 && hashHi >= 65535 && K.world == 1;
-        if (maxW <= 64 && noScore) extract_short_kernel<2, false><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
-        else if (maxW <= 64) extract_short_kernel<2><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
-        else if (maxW <= 128 && noScore) extract_short_kernel<4, false><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
-        else if (maxW <= 128) extract_short_kernel<4><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
-        else if (noScore) extract_short_kernel<8, false><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
-        else extract_short_kernel<8><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_ARGS;
-#undef CDG_EXTRACT_ARGS
+        // fast path: GROUP lanes per sequence, possible repeats go to the slow list; then the exact warp-per-sequence kernel on the list
+        const u32 *slowList = ctx->dSlowList.as<u32>(); const u32 *slowCount = (const u32 *) (sc + SC_SLOW);
+#define CDG_GROUP_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dPow31.as<u64>(), sc + SC_EMIT, identityMode == 2 ? ctx->ordV : (const u64 *) nullptr, ctx->dSlotRank.as<u64>(), ctx->dSlowList.as<u32>(), (u32 *) (sc + SC_SLOW))
+        if (maxW <= 64) { if (noScore) extract_group_kernel<8, 8, false><<<groupBlocks[0], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; else extract_group_kernel<8, 8, true><<<groupBlocks[0], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; }
+        else if (maxW <= 128) { if (noScore) extract_group_kernel<16, 8, false><<<groupBlocks[1], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; else extract_group_kernel<16, 8, true><<<groupBlocks[1], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; }
+        else { if (noScore) extract_group_kernel<32, 8, false><<<groupBlocks[2], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; else extract_group_kernel<32, 8, true><<<groupBlocks[2], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; }
+#undef CDG_GROUP_ARGS
+        ctx->launches++;
+        CKL();
+        {
+            ExtractParams keepE = E;
+            E.identity = 0;   // the identity records of the listed sequences are already out
+#define CDG_EXTRACT_LIST_ARGS CDG_EXTRACT_ARGS_(slowList, slowCount)
+            if (maxW <= 64) extract_short_kernel<2><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_LIST_ARGS;
+            else if (maxW <= 128) extract_short_kernel<4><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_LIST_ARGS;
+            else extract_short_kernel<8><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_LIST_ARGS;
+#undef CDG_EXTRACT_LIST_ARGS
+            E = keepE;
+            CK(cudaMemsetAsync(sc + SC_SLOW, 0, 8, ctx->st));   // the next piece starts an empty list
+        }
+#undef CDG_EXTRACT_ARGS_
         ctx->launches++;
         CKL();
     }
@@ -894,7 +918,7 @@ static int run_rescore(cdg_ctx *ctx, const cdg_rescore_params *p) {
     R.dbRes = (double) (p->db_residues ? p->db_residues : ctx->totalBases);
     if (M) {
         cdgalign::rescore_kernel<<<(unsigned) ((M + 255) / 256), 256, 0, ctx->st>>>(
-            ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(), ctx->dWords.as<u64>(), ctx->dWordOff.as<u64>(), ctx->dFlags.as<u8>(),
+            ctx->dData.as<u8>(), ctx->dMeta.as<cdgalign::SeqMeta>(), ctx->dWords.as<u64>(),
             ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(), ctx->dLinePref.as<i32>(), ctx->dLineDiag.as<u16>(), M, R, ctx->dKeep.as<u8>(),
             ctx->dScore.as<i32>(), ctx->dBits.as<i32>(), ctx->dEvalue.as<double>(), ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(), ctx->dQE.as<i32>(),
             ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), ctx->dIdCnt.as<u32>(), sc + SC_KEPT);
@@ -1072,6 +1096,9 @@ extern "C" int cdg_set_alignments(cdg_ctx *ctx, const uint64_t *aln_off, uint64_
         CK(cudaMemcpyAsync(ctx->dDS.p, db_start, n_alns * 4, cudaMemcpyHostToDevice, ctx->st));
         CK(cudaMemcpyAsync(ctx->dDE.p, db_end, n_alns * 4, cudaMemcpyHostToDevice, ctx->st));
         CK(cudaMemsetAsync(ctx->dKeep.p, 1, n_alns, ctx->st));
+        cdgalign::lines_fillq_kernel<<<(unsigned) ((n_queries + 255) / 256), 256, 0, ctx->st>>>(ctx->dLineOff.as<u64>(), n_queries, ctx->dLineQ.as<u32>());
+        ctx->launches++;
+        CKL();
     }
     CK(cudaStreamSynchronize(ctx->st));
     ctx->nLines = n_alns; ctx->linesValid = false; ctx->hitsValid = false; ctx->alnsValid = true; ctx->alnsFromText = true; ctx->qLo = 0; ctx->nQ = ctx->n;
@@ -1115,12 +1142,23 @@ static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data
     if (n) cdgalign::multi_line_queries_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dLineOff.as<u64>(), n, ctx->dQList.as<u32>(), (u32 *) (sc + SC_QLIST));
     ctx->launches++;
     CKL();
+    // per-line part of pass 2 (RY identity, thresholds, mismatch columns): one thread per line
+    const u64 M = ctx->nLines;
+    CK(ctx->dPrep.reserve(M + 1)); CK(ctx->dAlnLen.reserve((M + 1) * 4)); CK(ctx->dMism.reserve((M + 1) * 24));
+    if (M) {
+        cdgalign::corr_prep_kernel<<<(unsigned) ((M + 255) / 256), 256, 0, ctx->st>>>(
+            ctx->dData.as<u8>(), ctx->dMeta.as<cdgalign::SeqMeta>(), ctx->dWords.as<u64>(), qLo, ctx->dLineOff.as<u64>(), ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(),
+            ctx->dKeep.as<u8>(), ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(), ctx->dQE.as<i32>(), ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), M, C,
+            ctx->dPrep.as<u8>(), ctx->dAlnLen.as<u32>(), ctx->dMism.as<u64>());
+        ctx->launches++;
+        CKL();
+    }
     const int blocks = ctx->smCount * 4;
     cdgalign::correct_fast_kernel<<<blocks, cdgalign::CF_WARPS * 32, sizeof(cdgalign::CorrSmem), ctx->st>>>(
         ctx->dQList.as<u32>(), (const u32 *) (sc + SC_QLIST), ctx->dData.as<u8>(), ctx->dMeta.as<cdgalign::SeqMeta>(), ctx->dWords.as<u64>(), qLo, n, ctx->dLineOff.as<u64>(), ctx->dLineT.as<u32>(), ctx->dKeep.as<u8>(), ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(),
         ctx->dQE.as<i32>(), ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), C, ctx->dTables.as<cdgalign::DamageTables>(), ctx->dLineSel.as<u8>(),
         patchMode ? nullptr : ctx->dOut.as<u8>(), sc + SC_CHANGED, ctx->dLikOff.as<u64>(), dLik, ctx->dWideList.as<u32>(), (u32 *) (sc + SC_WIDE),
-        patchMode ? ctx->dPatches.as<u64>() : nullptr, patchCap, sc + SC_PATCH);
+        patchMode ? ctx->dPatches.as<u64>() : nullptr, patchCap, sc + SC_PATCH, ctx->dPrep.as<u8>(), ctx->dAlnLen.as<u32>(), ctx->dMism.as<u64>());
     ctx->launches++;
     CKL();
     if (patchMode) {

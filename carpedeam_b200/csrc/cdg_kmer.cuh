@@ -209,7 +209,9 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
     WinRec *__restrict__ scratch /*[gridWarps][2*EX_MAXW]*/,
     u8 *__restrict__ scratchKeep /*[gridWarps][EX_MAXW]*/, unsigned long long *__restrict__ emitted,
     const u64 *__restrict__ order /*slice mode: sequence index by (length desc, id asc) rank, else null*/,
-    const u64 *__restrict__ prefix /*slice mode: first slot by rank*/) {
+    const u64 *__restrict__ prefix /*slice mode: first slot by rank*/,
+    const u32 *__restrict__ list = nullptr /*list mode: the iteration indices to process (extract_group_kernel's flagged sequences)*/,
+    const u32 *__restrict__ listCount = nullptr) {
     __shared__ u32 bitmapAll[EX_WARPS * EX_BM_WORDS];   // 8192 bits per warp: small, so that registers bound the occupancy
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u32 *bitmap = bitmapAll + warp * EX_BM_WORDS;
@@ -224,9 +226,10 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
     // `order` (multi-GPU: the per-rank work does not grow with the number of ranks).  The loads that start a sequence
     // (index, meta, rank, slot) are issued one sequence ahead.
     const bool byRank = order != nullptr;
-    const u64 itLo = byRank ? (u64) P.posLo : P.seqLo, itHi = byRank ? (u64) P.posHi : (P.seqHi < n ? P.seqHi : n);
+    const u64 itLo = list ? 0 : (byRank ? (u64) P.posLo : P.seqLo), itHi = list ? (u64) *listCount : (byRank ? (u64) P.posHi : (P.seqHi < n ? P.seqHi : n));
     SeqMeta smN; smN.off = 0; smN.wordOff = 0; smN.lenFlags = 0; u32 rankN = 0; u64 slotN = 0, seqN = 0;
     auto fetch = [&](u64 it) {
+        if (list) it = list[it];
         if (byRank) { seqN = (u32) order[it]; rankN = (u32) it; slotN = prefix[it]; }
         else { seqN = it; rankN = rankOf[it]; slotN = slotOff[it]; }
         smN = meta[seqN];
@@ -371,6 +374,115 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
         }
     }
     if (lane == 0 && localEmitted) atomicAdd(emitted, localEmitted);
+}
+
+// ---- short sequences, GROUP lanes per sequence (32/GROUP sequences per warp) ------------------------------------------
+// The fast path of extract_short_kernel for the common read lengths: a 35-70 bp read has 16-51 windows, so a full warp per read
+// leaves half of the lanes idle and pays the per-sequence work (meta fetch, identity hash, slot bookkeeping) once per read; with
+// 8 lanes per read four reads share every instruction.  Every valid window is emitted optimistically in window order; a blocked
+// Bloom filter per group (128 words of 64 bits, a window sets two bits of one word with ONE atomic, so of two equal k-mers —
+// even in the same instruction — the later one sees both bits set) flags a POSSIBLE repeated k-mer, and a flagged sequence is
+// appended to `slowList` for extract_short_kernel's exact path, which rewrites all of its slots (false positives: < 1 % of reads).  Iteration index `cur` as in extract_short_kernel (sequence index, or the
+// (length desc, id asc) rank in slice mode); slowList holds `cur`.
+template <int GROUP, int ITERS, bool SCORE>
+__global__ void __launch_bounds__(EX_WARPS * 32, GROUP == 8 ? 4 : 5) extract_group_kernel(
+    const u64 *__restrict__ words, const u32 *__restrict__ xmask, const SeqMeta *__restrict__ meta,
+    u64 n, ExtractParams P, const u64 *__restrict__ slotOff, u64 *__restrict__ mainKeys, u64 *__restrict__ mainVals,
+    u64 *__restrict__ idKeys, u64 *__restrict__ idVals, u64 extraBase, u32 extraCap, u32 *extraCount, u32 *overflow,
+    const u32 *__restrict__ rankOf, const u64 *__restrict__ pow31tab, unsigned long long *__restrict__ emitted,
+    const u64 *__restrict__ order, const u64 *__restrict__ prefix, u32 *__restrict__ slowList, u32 *__restrict__ slowCount) {
+    constexpr int GPW = 32 / GROUP;                   // groups (sequences) per warp
+    constexpr u32 BM_WORDS = 128;                     // 64-bit words of the group's filter
+    __shared__ unsigned long long bitmapAll[EX_WARPS * GPW * BM_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane / GROUP, gl = lane % GROUP;
+    unsigned long long *bm = bitmapAll + (warp * GPW + g) * BM_WORDS;
+    for (int i = gl; i < (int) BM_WORDS; i += GROUP) bm[i] = 0;
+    __syncwarp();
+    const u32 gmask = (GROUP == 32 ? 0xffffffffu : ((1u << GROUP) - 1u)) << (g * GROUP);
+    const u32 ltmask = gmask & ((1u << lane) - 1u);   // lanes of my group below me
+    const u64 ggroup = ((u64) blockIdx.x * EX_WARPS + warp) * GPW + g, ngroups = (u64) gridDim.x * EX_WARPS * GPW;
+    const bool byRank = order != nullptr;
+    const u64 itLo = byRank ? (u64) P.posLo : P.seqLo, itHi = byRank ? (u64) P.posHi : (P.seqHi < n ? P.seqHi : n);
+    unsigned long long localEmitted = 0;
+    // all groups of a warp run the same number of rounds (the last ones with an inactive group)
+    for (u64 base = itLo + (ggroup - g); base < itHi; base += ngroups) {
+        const u64 cur = base + g;
+        bool active = cur < itHi;
+        u64 seq = 0, slotAbs = 0; u32 myRank = 0;
+        SeqMeta sm; sm.off = 0; sm.wordOff = 0; sm.lenFlags = 0;
+        if (active) {
+            if (byRank) { seq = (u32) order[cur]; myRank = (u32) cur; slotAbs = prefix[cur]; }
+            else { seq = cur; myRank = rankOf[cur]; slotAbs = slotOff[cur]; }
+            sm = meta[seq];
+        }
+        const u32 L = sm.lenFlags & META_LEN;
+        active = active && is_short_seq(L, P.k, P.kmersPerSeq, P.scale) && myRank >= P.posLo && myRank < P.posHi;
+        const u64 *w = words + sm.wordOff;
+        const u32 *xm = xmask + sm.wordOff;
+        const u32 W = (active && L >= (u32) P.k) ? L - P.k + 1 : 0;
+        // identity hash (Util::hash, Util.h:337-346): sum of code_p * 31^(L-1-p), lane gl takes p = gl, gl+GROUP, ...
+        u64 part = 0;
+        if (active) {
+            u32 curW = 0xFFFFFFFFu, xx = 0; u64 ww = 0;
+            for (u32 p = gl; p < L; p += GROUP) {
+                const u32 wi = p >> 5, o = p & 31;
+                if (wi != curW) { ww = w[wi]; xx = xm[wi]; curW = wi; }
+                const u64 code = ((xx >> (31 - o)) & 1u) ? 4ull : ((ww >> (62 - 2 * o)) & 3ull);
+                part += code * pow31tab[L - 1 - p];   // L - 1 - p < 288 for short sequences
+            }
+        }
+#pragma unroll
+        for (int o = GROUP / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (active && gl == 0 && P.identity)
+            emit_identity(cdg_xxh64_u64(part, P.seed), seq, P, idKeys, idVals, mainKeys, mainVals, extraBase, extraCap, extraCount, overflow, myRank);
+        // windows
+        const u64 slot0 = slotAbs - P.slotBase;
+        u32 written = 0, flagged = 0;
+        u32 hh[ITERS];   // the window's filter word, 0xFFFFFFFF = no valid window in this iteration
+        u32 maxW = W;
+#pragma unroll
+        for (int o = 16; o >= GROUP; o >>= 1) maxW = max(maxW, __shfl_xor_sync(0xffffffffu, maxW, o));   // over the groups of the warp
+#pragma unroll
+        for (int it = 0; it < ITERS; it++) {
+            hh[it] = 0xFFFFFFFFu;
+            if ((u32) (it * GROUP) >= maxW) continue;     // warp-uniform
+            const u32 p = gl + GROUP * it;
+            WinRec r; bool ok = false;
+            if (p < W) ok = make_window<SCORE>(w, xm, p, L, P, r);
+            bool own = ok;
+            if (SCORE) own = ok && r.score >= P.hashLo && r.score <= P.hashHi;
+            if (ok) {
+                const u64 canon = r.kmer & ~CDG_B63;
+                const u32 mix = ((u32) canon ^ (u32) (canon >> 19)) * 0x9E3779B1u;
+                const unsigned long long bits = (1ull << ((mix >> 19) & 63u)) | (1ull << ((mix >> 13) & 63u));
+                hh[it] = mix >> 25;
+                const unsigned long long old = atomicOr(&bm[hh[it]], bits);
+                if ((old & bits) == bits) flagged = 1;
+            }
+            const u32 b = __ballot_sync(0xffffffffu, own) & gmask;
+            if (own) {
+                const u64 dst = slot0 + written + __popc(b & ltmask);
+                mainKeys[dst] = r.kmer;
+                mainVals[dst] = cdg_pack_val((u32) seq, r.pos, SCORE ? owner_of(r.score, P.world) : 0u);
+            }
+            written += __popc(b);
+        }
+        __syncwarp();
+        // clear the touched bitmap words (cheaper than wiping 1 KB per sequence)
+#pragma unroll
+        for (int it = 0; it < ITERS; it++) if (hh[it] != 0xFFFFFFFFu) bm[hh[it]] = 0;
+        const bool slow = (__ballot_sync(0xffffffffu, flagged) & gmask) != 0;
+        if (active) {
+            const u32 cap = kmer_capacity(L, P.k, P.kmersPerSeq, P.scale);
+            for (u32 sI = written + gl; sI < cap; sI += GROUP) { mainKeys[slot0 + sI] = CDG_SENTINEL; mainVals[slot0 + sI] = 0; }
+            if (gl == 0) {
+                if (slow) slowList[atomicAdd(slowCount, 1u)] = (u32) cur;   // the exact path rewrites the slots and counts the records
+                else localEmitted += written;
+            }
+        }
+        __syncwarp();
+    }
+    if (localEmitted) atomicAdd(emitted, localEmitted);
 }
 
 // ---- long sequences (hash threshold active or > 256 windows): one block per sequence -------------------
