@@ -57,6 +57,7 @@ static constexpr int CDG_IPC_BUFFERS = 5;   // recvK, recvV, recvIdK, recvIdV, r
 static constexpr int CDG_IPC_HANDLE_BYTES = 64 + 8;   // cudaIpcMemHandle_t + byte offset of the buffer inside its allocation
 static constexpr u64 CDG_HEAD_RUN = 4096;   // records of the next rank's head run appended before the reduction
 struct KmPlanFwd {
+    bool wide = false;   // grouped records need more than 64 bits: two-word records (single GPU only)
     int idBits, diagBits; u32 world, rank; u32 posLo, posHi; u64 slotBase, slots; u32 extraCap; u32 hashLo, hashHi; u32 repChunk; u64 qLo, nQ;
 };
 struct cdg_ctx {
@@ -101,7 +102,7 @@ struct cdg_ctx {
     HostBuf hCmpCount, hCmpTarget, hCmpFields, hPatches;
     u64 nCompact = 0, nChangedLast = 0; bool correctedValid = false; double dbResUsed = 0; bool monotoneOffsets = true; bool packedUpload = false;
     // packed uploads rebuild the DB bytes only when something reads them (a sequence with N, or a byte-consuming entry point)
-    DevBuf dSetFacts, dSlowList, dPrep, dAlnLen, dMism; bool bytesValid = true; bool patchesDirect = false;
+    DevBuf dSetFacts, dSlowList, dPrep, dAlnLen, dMism, dKey2HiA, dKey2HiB; u64 *sortedKey2Hi = nullptr; bool bytesValid = true; bool patchesDirect = false;
     u64 nLines = 0, nKept = 0; bool linesValid = false, alnsValid = false, alnsFromText = false;
     // correction
     DevBuf dTables, dOut, dLik, dWideList, dRecvK, dRecvV, dRecv2, dQList, dPow31, dKey2Big; bool damageSet = false;
@@ -279,7 +280,7 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
                    &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2, &ctx->dQList, &ctx->dPow31,
                    &ctx->dPairModel, &ctx->dPairIn, &ctx->dPairCons, &ctx->dPairOut, &ctx->dRecvIdK, &ctx->dRecvIdV, &ctx->dRouteTab,
-                   &ctx->dIdCnt, &ctx->dCmpCount, &ctx->dCmpTarget, &ctx->dCmpFields, &ctx->dPatches, &ctx->dKey2Big, &ctx->dSetFacts, &ctx->dSlowList, &ctx->dPrep, &ctx->dAlnLen, &ctx->dMism};
+                   &ctx->dIdCnt, &ctx->dCmpCount, &ctx->dCmpTarget, &ctx->dCmpFields, &ctx->dPatches, &ctx->dKey2Big, &ctx->dSetFacts, &ctx->dSlowList, &ctx->dPrep, &ctx->dAlnLen, &ctx->dMism, &ctx->dKey2HiA, &ctx->dKey2HiB};
     for (DevBuf *b : d) b->release();
     HostBuf *h[] = {&ctx->hHitRep, &ctx->hHitTgt, &ctx->hHitScore, &ctx->hHitDiag, &ctx->hHitDiag16, &ctx->hLineOff, &ctx->hLineT, &ctx->hKeep,
                     &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE,
@@ -525,9 +526,10 @@ static int km_bits(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlan &K) {
     if (ctx->maxLen >= (1u << CDG_OWNER_SHIFT)) return fail(ctx, CDG_ERR_UNSUPPORTED, "sequences longer than 2^28 are not supported");
     K.idBits = std::max(1, ceil_log2(ctx->n));
     K.diagBits = std::max(1, ceil_log2(2ull * ctx->maxLen + 1));
-    if (2 * K.idBits + K.diagBits + 1 > 64)
-        return fail(ctx, CDG_ERR_UNSUPPORTED, "n=%llu sequences x max length %u needs %d key bits (>64): split the set", (unsigned long long) ctx->n,
-                    ctx->maxLen, 2 * K.idBits + K.diagBits + 1);
+    K.wide = 2 * K.idBits + K.diagBits + 1 > 64 || getenv("CDG_FORCE_WIDE_KEY2") != nullptr;   // (test knob: the two-word path on any set)
+    if (K.wide && K.world > 1)
+        return fail(ctx, CDG_ERR_UNSUPPORTED, "n=%llu sequences x max length %u needs %d grouped-record bits (>64): the two-word records are "
+                    "implemented for the single-GPU path only", (unsigned long long) ctx->n, ctx->maxLen, 2 * K.idBits + K.diagBits + 1);
     return 0;
 }
 
@@ -708,14 +710,19 @@ static int km_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64
     int rc;
     const u64 key2Cap = Rtot + n + CDG_HEAD_RUN;
     CK(ctx->dKey2A.reserve(key2Cap * 8)); CK(ctx->dKey2B.reserve(key2Cap * 8));
+    if (K.wide) { CK(ctx->dKey2HiA.reserve(key2Cap * 8)); CK(ctx->dKey2HiB.reserve(key2Cap * 8)); }
     CK(cudaMemsetAsync(sc + SC_GROUPED, 0, 8, ctx->st));
     GroupParams G; G.idBits = K.idBits; G.diagBits = K.diagBits; G.diagBias = (i32) ctx->maxLen; G.onlyExtendable = p->include_only_extendable;
     G.firstRunQuirk = mainHasGlobalFirstRun ? 1 : 0;   // kmermatcher.cpp:466: only the globally first run
-    if (Rtot) group_kernel<<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedMainK, ctx->sortedMainV, Rtot, ctx->dLen.as<u32>(), G,
+    if (Rtot && K.wide) group_kernel<true><<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedMainK, ctx->sortedMainV, Rtot, ctx->dLen.as<u32>(), G,
+                                                                                                                    ctx->dKey2A.as<u64>(), sc + SC_GROUPED, ctx->dKey2HiA.as<u64>());
+    else if (Rtot) group_kernel<<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedMainK, ctx->sortedMainV, Rtot, ctx->dLen.as<u32>(), G,
                                                                                                       ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
     GroupParams GI = G; GI.firstRunQuirk = idHasGlobalFirstRun ? 1 : 0;
     const u64 nId = ctx->nIdent;
-    if (nId) group_kernel<<<(unsigned) ((nId + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedIdK, ctx->sortedIdV, nId, ctx->dLen.as<u32>(), GI,
+    if (nId && K.wide) group_kernel<true><<<(unsigned) ((nId + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedIdK, ctx->sortedIdV, nId, ctx->dLen.as<u32>(), GI,
+                                                                                                                  ctx->dKey2A.as<u64>(), sc + SC_GROUPED, ctx->dKey2HiA.as<u64>());
+    else if (nId) group_kernel<<<(unsigned) ((nId + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedIdK, ctx->sortedIdV, nId, ctx->dLen.as<u32>(), GI,
                                                                                                     ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
     ctx->launches += 2;
     CKL();
@@ -731,11 +738,26 @@ static int km_sort2(cdg_ctx *ctx, const KmPlan &K, u64 R2, u64 *src = nullptr, u
     if (R2 > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "grouped records exceed one sort");
     if ((rc = sort_ws(ctx, std::max<u64>(R2, ctx->n), ws))) return rc;
     u64 *dummy = nullptr;
+    ctx->sortedKey2Hi = nullptr;
+    int l3;
+    if (K.wide) {   // two-word records: pair sort by (id, diag) on the lo words carrying hi, then by rep on the hi words carrying lo (LSD, stable)
+        cdgsort::Plan planLo = cdgsort::make_plan(0, 0, 1, K.idBits + K.diagBits + 1), planHi = cdgsort::make_plan(0, 0, 0, K.idBits);
+        u64 *lo1, *hi1;
+        int la = cdgsort::radix_sort(ctx->st, ws, ctx->dKey2A.as<u64>(), ctx->dKey2B.as<u64>(), ctx->dKey2HiA.as<u64>(), ctx->dKey2HiB.as<u64>(), R2, planLo, &lo1, &hi1, ctx->smCount);
+        if (la < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "radix sort 2 failed");
+        u64 *loAlt = lo1 == ctx->dKey2A.as<u64>() ? ctx->dKey2B.as<u64>() : ctx->dKey2A.as<u64>();
+        u64 *hiAlt = hi1 == ctx->dKey2HiA.as<u64>() ? ctx->dKey2HiB.as<u64>() : ctx->dKey2HiA.as<u64>();
+        int lb = cdgsort::radix_sort(ctx->st, ws, hi1, hiAlt, lo1, loAlt, R2, planHi, &ctx->sortedKey2Hi, &ctx->sortedKey2, ctx->smCount);
+        if (lb < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "radix sort 2 failed");
+        l3 = la + lb; ctx->sort2Passes = planLo.n + planHi.n;
+    } else {
     cdgsort::Plan plan2 = cdgsort::make_plan(0, 0, 1, 2 * K.idBits + K.diagBits + 1);   // bit 0 (needRev) is not an ordering key
     if (!src) { src = ctx->dKey2A.as<u64>(); alt = ctx->dKey2B.as<u64>(); }
-    int l3 = cdgsort::radix_sort(ctx->st, ws, src, alt, nullptr, nullptr, R2, plan2, &ctx->sortedKey2, &dummy, ctx->smCount);
+    l3 = cdgsort::radix_sort(ctx->st, ws, src, alt, nullptr, nullptr, R2, plan2, &ctx->sortedKey2, &dummy, ctx->smCount);
     if (l3 < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "radix sort 2 failed");
-    ctx->launches += l3; ctx->sort2Passes = plan2.n;
+    ctx->sort2Passes = plan2.n;
+    }
+    ctx->launches += l3;
     CKL();
     rec(ctx, EV_SORT2);
     return 0;
@@ -748,7 +770,7 @@ static int km_reduce(cdg_ctx *ctx, const KmPlan &K, u64 nOwn, u64 nTotal) {
     int rc;
     u64 H = 0;
     if (nOwn > 0) {
-        PairEndFlag f; f.keys = ctx->sortedKey2; f.n = nTotal; f.idBits = K.idBits; f.diagBits = K.diagBits; f.nOwn = nOwn;
+        PairEndFlag f; f.keys = ctx->sortedKey2; f.n = nTotal; f.idBits = K.idBits; f.diagBits = K.diagBits; f.nOwn = nOwn; f.hi = K.wide ? ctx->sortedKey2Hi : nullptr;
         u64 tiles = cdgscan::tiles_for(nTotal);
         CK(ctx->dTileSums.reserve((tiles + 1) * 8));
         unsigned long long *ts = ctx->dTileSums.as<unsigned long long>();
@@ -758,7 +780,9 @@ static int km_reduce(cdg_ctx *ctx, const KmPlan &K, u64 nOwn, u64 nTotal) {
         if ((rc = read_scalar(ctx, SC_SCAN, &H))) return rc;
         CK(ctx->dHitRep.reserve((H + 1) * 4)); CK(ctx->dHitTgt.reserve((H + 1) * 4)); CK(ctx->dHitScore.reserve((H + 1) * 4)); CK(ctx->dHitDiag.reserve((H + 1) * 4));
         ReduceParams R; R.idBits = K.idBits; R.diagBits = K.diagBits; R.diagBias = (i32) ctx->maxLen;
-        reduce_kernel<<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, R, ts, ctx->dHitRep.as<u32>(), ctx->dHitTgt.as<u32>(), ctx->dHitScore.as<i32>(),
+        if (K.wide) reduce_kernel<true><<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, R, ts, ctx->dHitRep.as<u32>(), ctx->dHitTgt.as<u32>(), ctx->dHitScore.as<i32>(),
+                                                                                      ctx->dHitDiag.as<i32>());
+        else reduce_kernel<<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, R, ts, ctx->dHitRep.as<u32>(), ctx->dHitTgt.as<u32>(), ctx->dHitScore.as<i32>(),
                                                                       ctx->dHitDiag.as<i32>());
         ctx->launches++;
         CKL();

@@ -675,6 +675,9 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(const u64 *__restric
 struct GroupParams {
     int idBits, diagBits; i32 diagBias; int onlyExtendable; int firstRunQuirk;   // :466 first run: repIsReverse=false
 };
+// WIDE records (2*idBits + diagBits + 1 > 64, e.g. 5*10^7 sequences with contigs of 10 kb and more): two words per member,
+//   lo = id << (diagBits + 1) | (diag + diagBias) << 1 | needRev,   hi = rep
+// sorted as (lo bits, then hi bits) by two pair sorts; the (rep,id) pair = hi << idBits | lo >> (diagBits + 1) still fits 64 bits.
 CDG_D bool rep_better(u32 lenA, u32 idA, u32 posA, u64 keyA, u32 lenB, u32 idB, u32 posB, u64 keyB) {   // A before B ?
     if (lenA != lenB) return lenA > lenB;
     if (idA != idB) return idA < idB;
@@ -696,9 +699,10 @@ CDG_D void member_diag(bool repRev, u32 repLen, u32 repPos, bool tRev, u32 tLen,
 static constexpr int GROUP_BLOCK = 256;
 static constexpr int GROUP_ITEMS = 8;
 static constexpr int GROUP_TILE = GROUP_BLOCK * GROUP_ITEMS;
+template <bool WIDE = false>
 __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, u64 n,
                                                             const u32 *__restrict__ len, GroupParams G, u64 *__restrict__ out,
-                                                            unsigned long long *__restrict__ outCount) {
+                                                            unsigned long long *__restrict__ outCount, u64 *__restrict__ outHi = nullptr) {
     __shared__ u64 sKey[GROUP_TILE + 1];   // +1: the record after the tile (singleton test)
     __shared__ u64 sVal[GROUP_TILE];
     __shared__ u32 shWarp[GROUP_BLOCK / 32 + 1];
@@ -747,6 +751,7 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
     if (lane > 0) carry = max(carry, prevLane);
     // per record: representative, diagonal, keep flag
     u64 outKey[GROUP_ITEMS];
+    u32 outRep[WIDE ? GROUP_ITEMS : 1];
     u32 keep = 0;
     const int sh1 = G.diagBits + 1, sh2 = G.idBits + G.diagBits + 1;
 #pragma unroll
@@ -781,7 +786,8 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
         i32 d; bool need;
         member_diag(repRev, repLen, repPos, (k & CDG_B63) == 0, tl, cdg_val_pos(v), d, need);
         if (G.onlyExtendable && !(d < 0 || d > (i32) repLen - (i32) tl)) continue;   // :526-536
-        outKey[j] = ((u64) repId << sh2) | ((u64) id << sh1) | ((u64) (u32) (d + G.diagBias) << 1) | (need ? 1ull : 0ull);
+        outKey[j] = (WIDE ? 0ull : ((u64) repId << sh2)) | ((u64) id << sh1) | ((u64) (u32) (d + G.diagBias) << 1) | (need ? 1ull : 0ull);
+        if (WIDE) outRep[j] = repId;
         keep |= 1u << j;
     }
     // compaction: block scan of keep counts, one atomic per block
@@ -791,7 +797,7 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
     __syncthreads();
     u64 dst = sBase + myOff;
 #pragma unroll
-    for (int j = 0; j < GROUP_ITEMS; j++) if (keep & (1u << j)) out[dst++] = outKey[j];
+    for (int j = 0; j < GROUP_ITEMS; j++) if (keep & (1u << j)) { if (WIDE) outHi[dst] = outRep[j]; out[dst++] = outKey[j]; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -804,10 +810,12 @@ struct ReduceParams { int idBits, diagBits; i32 diagBias; };
 // flag = last record of a (rep,target) pair with target != rep: one hit each, in sorted (= pref DB) order
 struct PairEndFlag {
     const u64 *keys; u64 n; int idBits, diagBits; u64 nOwn;   // records [nOwn, n) are a neighbour's head run: walked, never emitted
+    const u64 *hi = nullptr;                                  // WIDE records: the representatives
+    CDG_D u64 pair_at(u64 i) const { return hi ? ((hi[i] << idBits) | (keys[i] >> (diagBits + 1))) : (keys[i] >> (diagBits + 1)); }
     CDG_D u32 operator()(u64 i) const {
         if (i >= nOwn) return 0;
-        const u64 pair = keys[i] >> (diagBits + 1);
-        if (i + 1 < n && (keys[i + 1] >> (diagBits + 1)) == pair) return 0;
+        const u64 pair = pair_at(i);
+        if (i + 1 < n && pair_at(i + 1) == pair) return 0;
         const u32 id = (u32) (pair & ((1ull << idBits) - 1)), rep = (u32) (pair >> idBits);
         return id != rep ? 1u : 0u;
     }
@@ -815,20 +823,22 @@ struct PairEndFlag {
 
 // sequential replay of the reference's walk (kmermatcher.cpp:886-905) from the first record `s` of a pair; used for
 // pairs that start before the tile and for pairs whose target-id run bleeds into the next representative
-CDG_D void reduce_walk(const u64 *__restrict__ keys, u64 n, u64 s, const ReduceParams &R, u32 &top, i32 &best, bool &brev) {
+CDG_D void reduce_walk(const PairEndFlag &f, u64 n, u64 s, const ReduceParams &R, u32 &top, i32 &best, bool &brev) {
+    const u64 *__restrict__ keys = f.keys;
     const u64 idMask = (1ull << R.idBits) - 1, diagMask = (1ull << R.diagBits) - 1;
-    const int pairShift = R.diagBits + 1;
     const u64 k = keys[s];
-    const u32 tgt = (u32) ((k >> pairShift) & idMask);
-    u32 prevRep = (u32) (k >> (pairShift + R.idBits));
+    const u64 p0 = f.pair_at(s);
+    const u32 tgt = (u32) (p0 & idMask);
+    u32 prevRep = (u32) (p0 >> R.idBits);
     i32 prev = (i32) ((k >> 1) & diagMask);
     best = prev; brev = false; top = 0;
     u32 dc = 0, mx = 0; bool runNeed = false;
     for (u64 e = s; e < n; e++) {
         const u64 ke = keys[e];
-        if ((u32) ((ke >> pairShift) & idMask) != tgt) break;   // the rep is deliberately not checked
+        const u64 pe = f.pair_at(e);
+        if ((u32) (pe & idMask) != tgt) break;   // the rep is deliberately not checked
         const i32 d = (i32) ((ke >> 1) & diagMask);
-        const u32 repE = (u32) (ke >> (pairShift + R.idBits));
+        const u32 repE = (u32) (pe >> R.idBits);
         const bool sameRun = prev == d;
         dc = sameRun ? dc + 1 : 1;
         // equal (rep,id,diag) records are unordered in the reference; our order puts needRev last -> OR over the run,
@@ -881,11 +891,14 @@ CDG_D void block_seg_scan(u64 (&val)[RED_ITEMS], u32 heads, Op op, u64 *shVal /*
 struct OpLenNeed { CDG_D u64 operator()(u64 a, u64 b) const { return (((a >> 1) + (b >> 1)) << 1) | ((a | b) & 1ull); } };
 struct OpMax { CDG_D u64 operator()(u64 a, u64 b) const { return a > b ? a : b; } };
 
+template <bool WIDE = false>
 __global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(PairEndFlag f, ReduceParams R, const unsigned long long *__restrict__ tileSums,
                                                            u32 *__restrict__ hitRep, u32 *__restrict__ hitTgt,
                                                            i32 *__restrict__ hitScore, i32 *__restrict__ hitDiag) {
     __shared__ __align__(16) u64 sKeyRaw[RED_TILE + 4];
+    __shared__ u64 sPairRaw[WIDE ? RED_TILE + 4 : 1];   // WIDE: the (rep,id) pair of every record of sKey (NONE outside the array)
     u64 *sKey = sKeyRaw + 1;             // [0] = record before the tile, [1..tileN] = the tile (16-byte aligned), [tileN+1] = record after it
+    u64 *sPair = sPairRaw + (WIDE ? 1 : 0);
     __shared__ __align__(8) u64 sBar;
     __shared__ u64 shVal[RED_BLOCK / 32];
     __shared__ u32 shFlag[RED_BLOCK / 32];
@@ -904,11 +917,16 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(PairEndFlag f, Reduce
         for (u32 i = tid; i < tileN; i += RED_BLOCK) sKey[i + 1] = f.keys[base + i];
     }
     if (tid == 0) { sKey[0] = base > 0 ? f.keys[base - 1] : NONE; sKey[tileN + 1] = base + tileN < f.n ? f.keys[base + tileN] : NONE; }
+    if (WIDE) {
+        for (u32 i = tid; i < tileN; i += RED_BLOCK) sPair[i + 1] = f.pair_at(base + i);
+        if (tid == 0) { sPair[0] = base > 0 ? f.pair_at(base - 1) : NONE; sPair[tileN + 1] = base + tileN < f.n ? f.pair_at(base + tileN) : NONE; }
+    }
     if (tma) cdg_mbar_wait(&sBar, 0);
     __syncthreads();
     const int pairShift = R.diagBits + 1;
     const u64 idMask = (1ull << R.idBits) - 1, diagMask = (1ull << R.diagBits) - 1;
-    auto pairOf = [&](u64 k) -> u64 { return k == NONE ? NONE : (k >> pairShift); };
+    // pair of the record at shared index x (0 = before the tile)
+    auto pairAt = [&](u32 x) -> u64 { if (WIDE) return sPair[x]; const u64 k = sKey[x]; return k == NONE ? NONE : (k >> pairShift); };
     const u32 first = tid * RED_ITEMS;
     u32 pairHeads = 0, runHeads = 0, pairEnds = 0, runEnds = 0;
     u64 v1[RED_ITEMS];
@@ -919,7 +937,7 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(PairEndFlag f, Reduce
         v1[j] = 0;
         if (li < tileN) {
             const u64 k = sKey[li + 1], kp = sKey[li], kn = sKey[li + 2];
-            const bool ph = pairOf(kp) != pairOf(k), pe = pairOf(kn) != pairOf(k);
+            const bool ph = pairAt(li) != pairAt(li + 1), pe = pairAt(li + 2) != pairAt(li + 1);
             const bool rh = ph || ((kp >> 1) & diagMask) != ((k >> 1) & diagMask);
             const bool re = pe || ((kn >> 1) & diagMask) != ((k >> 1) & diagMask);
             pairHeads |= ph ? 1u << j : 0; runHeads |= rh ? 1u << j : 0; pairEnds |= pe ? 1u << j : 0; runEnds |= re ? 1u << j : 0;
@@ -953,7 +971,7 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(PairEndFlag f, Reduce
     for (int j = 0; j < RED_ITEMS; j++) {
         const u32 li = first + j;
         if (li < tileN && (pairEnds & (1u << j)) && base + li < f.nOwn) {
-            const u64 pair = sKey[li + 1] >> pairShift;
+            const u64 pair = pairAt(li + 1);
             if ((u32) (pair & idMask) != (u32) (pair >> R.idBits)) flags |= 1u << j;
         }
     }
@@ -964,11 +982,11 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(PairEndFlag f, Reduce
     for (int j = 0; j < RED_ITEMS; j++) {
         if (!(flags & (1u << j))) continue;
         const u32 li = first + j;
-        const u64 k = sKey[li + 1];
-        const u32 tgt = (u32) ((k >> pairShift) & idMask), rep = (u32) (k >> (pairShift + R.idBits));
+        const u64 pr0 = pairAt(li + 1);
+        const u32 tgt = (u32) (pr0 & idMask), rep = (u32) (pr0 >> R.idBits);
         const u32 hl = max(headOf[j], carry);
-        const u64 kn = sKey[li + 2];
-        const bool bleeds = kn != NONE && (u32) ((kn >> pairShift) & idMask) == tgt;   // next rep's first target is the same id
+        const u64 pn = pairAt(li + 2);
+        const bool bleeds = pn != NONE && (u32) (pn & idMask) == tgt;   // next rep's first target is the same id
         u32 top; i32 best; bool brev;
         if (hl != 0 && !bleeds) {
             const u32 startLi = hl - 1;
@@ -979,8 +997,8 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(PairEndFlag f, Reduce
         } else {
             u64 s = base + li;
             if (hl != 0) s = base + hl - 1;
-            else { const u64 pr = k >> pairShift; while (s > 0 && (f.keys[s - 1] >> pairShift) == pr) s--; }
-            reduce_walk(f.keys, f.n, s, R, top, best, brev);
+            else { while (s > 0 && f.pair_at(s - 1) == pr0) s--; }
+            reduce_walk(f, f.n, s, R, top, best, brev);
         }
         hitRep[h] = rep; hitTgt[h] = tgt;
         hitScore[h] = brev ? -(i32) top : (i32) top;

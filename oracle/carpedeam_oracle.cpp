@@ -85,6 +85,10 @@ static void extract_seq(const char *s, int L, u32 id, int k, int kmersPerSeq, fl
     u64 h = 0;
     for (int i = 0; i < L; i++) h = h * 31 + num[i];
     u64 seqHash = xxh64_u64(h, seed);
+    if (L < k) {   // no window: only the identity record (:244); skips the 256 KB histogram below (sets with millions of such entries)
+        if ((unsigned short) seqHash >= hashLo && (unsigned short) seqHash <= hashHi) { KmerRec r; r.kmer = seqHash; r.id = id; r.pos = 0; r.seqLen = L; out.push_back(r); }
+        return;
+    }
     std::vector<SeqPos> km;
     std::vector<unsigned> scoreDist(65536, 0);
     unsigned hier[128] = {0};

@@ -745,3 +745,75 @@ def test_multi_gpu_worker_under_torchrun():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
                         "--master-port", "29613", os.path.join(here, "mg_worker.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MULTIGPU PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("seqdb,pref,aln,corr,k,only_ext", CASES)
+def test_two_word_grouped_records_forced_on_golden_sets(ctx, monkeypatch, seqdb, pref, aln, corr, k, only_ext):
+    """the two-word grouped records (rep in its own word: sets where 2*idBits + diagBits + 1 > 64) forced on the reference's own
+    iterations: same pref DB as the reference wrote, incl. the rep-boundary bleed of config 1"""
+    import carpedeam_b200 as cd
+    monkeypatch.setenv("CDG_FORCE_WIDE_KEY2", "1")
+    s = SeqSet.from_golden(seqdb)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    got = ctx.kmermatch(cd.kmer_params(k=k, include_only_extendable=only_ext))
+    keys, payloads, _ = load_golden(pref)
+    mine = format_pref(s, got)
+    assert all(mine[kk] == p for kk, p in zip(keys, payloads))
+    id_bits = int(np.ceil(np.log2(s.n))); diag_bits = int(np.ceil(np.log2(2 * int(s.len.max()) + 1)))
+    assert ctx.stats()["sort2_passes"] == -(-(id_bits + diag_bits) // 8) + -(-id_bits // 8)      # (id, diag) passes + rep passes of the two pair sorts
+
+
+def test_config4_shaped_set_needs_more_than_64_grouped_record_bits(ctx, oracle):
+    """BASELINE configs[3] shape (contig iterations of a 5*10^7-sequence set: k=22, include-only-extendable, ext-flagged contigs of
+    8 kb and more next to reads): 2^25 + sequences give 26-bit ids, 8-16 kb contigs 16-bit diagonals -> 2*26 + 16 + 1 = 69 bits,
+    the single-word grouped record does not exist.  Most of the 3.4*10^7 entries are 1-base fillers (no k-mers) so that the oracle
+    finishes in seconds (13-base fillers, all different: no k-mer, no identity group); hits are compared in full."""
+    import carpedeam_b200 as cd
+    rng = np.random.default_rng(44)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    contigs = [acgt[rng.integers(0, 4, L)].tobytes() for L in (16000, 9000, 8200, 12000)]
+    real, ext = [], []
+    for c in contigs:
+        real.append(c); ext.append(1)
+        for _ in range(600):
+            L = int(rng.integers(35, 120)); st = int(rng.integers(-20, len(c) - L + 20))
+            r = c[max(0, st):st + L]
+            if st < 0:
+                r = acgt[rng.integers(0, 4, -st)].tobytes() + r        # overhanging reads stay extendable
+            if st + L > len(c):
+                r = r + acgt[rng.integers(0, 4, st + L - len(c))].tobytes()
+            if rng.random() < 0.5:
+                r = r.translate(comp)[::-1]
+            real.append(r); ext.append(0)
+    # two overlapping contigs (long shared diagonal run) and the fillers in between: real sequences sit at both ends of the id range
+    real.append(contigs[0][-3000:] + acgt[rng.integers(0, 4, 6000)].tobytes()); ext.append(1)
+    half = len(real) // 2
+    n_fill = (1 << 25) + 5
+    head, tail = SeqSet(real[:half], ext=ext[:half]), SeqSet(real[half:], ext=ext[half:])
+    s = SeqSet.__new__(SeqSet)
+    s.n = head.n + n_fill + tail.n
+    fill = np.zeros((n_fill, 15), np.uint8)
+    idx = np.arange(n_fill, dtype=np.uint64)
+    for j in range(13):
+        fill[:, j] = acgt[((idx >> np.uint64(2 * j)) & np.uint64(3)).astype(np.int64)]
+    fill[:, 13] = ord("\n")
+    s.blob = np.concatenate([head.blob, fill.ravel(), tail.blob])
+    s.len = np.concatenate([head.len, np.full(n_fill, 13, np.uint32), tail.len])
+    s.off = np.zeros(s.n, np.uint64); s.off[1:] = np.cumsum(s.len[:-1].astype(np.uint64) + 2)
+    s.ext = np.concatenate([head.ext, np.zeros(n_fill, np.uint8), tail.ext])
+    s.keys = np.arange(s.n, dtype=np.uint32); s.total = int(s.len.sum())
+    assert 2 * 26 + int(np.ceil(np.log2(2 * int(s.len.max()) + 1))) + 1 > 64
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    got = ctx.kmermatch(cd.kmer_params(k=22, include_only_extendable=1))
+    want = oracle.kmermatch(s, k=22, only_ext=1)
+    _hits_equal(got, want)
+    assert len(got["rep"]) > 1000 and got["rep"].max() > n_fill and got["rep"].min() < half
+    # the rest of the iteration on the same context (rescore + correction of 3.4*10^7 entries): the alignments of the real sequences
+    ctx.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+    a = ctx.rescore()
+    q = np.repeat(np.arange(s.n, dtype=np.uint32), np.diff(a["line_off"].astype(np.int64)))
+    sel = q != a["tgt"]
+    r = oracle.rescore(s, q[sel], a["tgt"][sel], got["score"], (got["diag"].astype(np.int64) & 0xFFFF).astype(np.uint16))
+    for f in ("keep", "score", "qs", "qe", "ds", "de"):
+        assert np.array_equal(a[f][sel], r[f]), f
