@@ -51,7 +51,7 @@ class CdgError(RuntimeError):
 
 class KmerParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("kmers_per_seq", C.c_int32), ("kmers_per_seq_scale", C.c_float), ("hash_shift", C.c_uint64),
-                ("include_only_extendable", C.c_int32), ("hash_lo", C.c_uint32), ("hash_hi", C.c_uint32)]
+                ("include_only_extendable", C.c_int32), ("hash_lo", C.c_uint32), ("hash_hi", C.c_uint32), ("split_passes", C.c_int32)]
 
 
 class Hits(C.Structure):
@@ -106,7 +106,7 @@ class Stats(C.Structure):
                 ("n_hits", C.c_uint64), ("n_alns", C.c_uint64), ("sort1_passes", C.c_uint32), ("sort2_passes", C.c_uint32),
                 ("kernel_launches", C.c_uint64), ("ms_extract", C.c_float), ("ms_sort1", C.c_float), ("ms_group", C.c_float),
                 ("ms_sort2", C.c_float), ("ms_reduce", C.c_float), ("ms_rescore", C.c_float), ("ms_correct", C.c_float),
-                ("ms_sort1_passes", C.c_float), ("n_sort1_pass_launches", C.c_uint32), ("sort1_records", C.c_uint64)]
+                ("ms_sort1_passes", C.c_float), ("n_sort1_pass_launches", C.c_uint32), ("sort1_records", C.c_uint64), ("split_passes", C.c_uint32)]
 
 
 _lib = None
@@ -217,8 +217,8 @@ def _view(ptr, n, dtype):
     return np.ctypeslib.as_array(ptr, shape=(int(n),)).view(dtype).copy()
 
 
-def kmer_params(k=20, kmers_per_seq=200, scale=0.2, hash_shift=67, include_only_extendable=0, hash_lo=0, hash_hi=65535):
-    return KmerParams(k, kmers_per_seq, scale, hash_shift, include_only_extendable, hash_lo, hash_hi)
+def kmer_params(k=20, kmers_per_seq=200, scale=0.2, hash_shift=67, include_only_extendable=0, hash_lo=0, hash_hi=65535, split_passes=0):
+    return KmerParams(k, kmers_per_seq, scale, hash_shift, include_only_extendable, hash_lo, hash_hi, split_passes)
 
 
 def load_damage(prefix, seq_err=0.01):
@@ -250,6 +250,7 @@ class Context:
         if rc != 0:
             raise CdgError("cdg_create(device=%d) failed (%d): CUDA device required, no CPU fallback" % (device, rc))
         self._keep = []
+        self._stream_mapped = None      # multigpu.ShardedIteration: sizes of the peer-mapped receive areas
 
     def close(self):
         if self._h:

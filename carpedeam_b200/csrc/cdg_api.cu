@@ -58,6 +58,7 @@ static constexpr int CDG_IPC_HANDLE_BYTES = 64 + 8;   // cudaIpcMemHandle_t + by
 static constexpr u64 CDG_HEAD_RUN = 4096;   // records of the next rank's head run appended before the reduction
 struct KmPlanFwd {
     bool wide = false;   // grouped records need more than 64 bits: two-word records (single GPU only)
+    u64 totalSlots = 0;  // k-mer slots of the whole set (every rank computes the same number)
     int idBits, diagBits; u32 world, rank; u32 posLo, posHi; u64 slotBase, slots; u32 extraCap; u32 hashLo, hashHi; u32 repChunk; u64 qLo, nQ;
 };
 struct cdg_ctx {
@@ -102,6 +103,7 @@ struct cdg_ctx {
     HostBuf hCmpCount, hCmpTarget, hCmpFields, hPatches;
     u64 nCompact = 0, nChangedLast = 0; bool correctedValid = false; double dbResUsed = 0; bool monotoneOffsets = true; bool packedUpload = false;
     // packed uploads rebuild the DB bytes only when something reads them (a sequence with N, or a byte-consuming entry point)
+    bool planReady = false; std::vector<cudaEvent_t> chunkDone; u32 splitPasses = 1; DevBuf dHashHist, dChunkK, dChunkV, dRouteBase;
     DevBuf dSetFacts, dSlowList, dPrep, dAlnLen, dMism, dKey2HiA, dKey2HiB; u64 *sortedKey2Hi = nullptr; bool bytesValid = true; bool patchesDirect = false;
     u64 nLines = 0, nKept = 0; bool linesValid = false, alnsValid = false, alnsFromText = false;
     // correction
@@ -139,7 +141,7 @@ static cudaError_t cdg_launch_check(cdg_ctx *ctx) {
 
 // scalars block on the device: [0] scan total, [1] emitted records, [2] grouped count, [3] kept lines,
 // [4] changed bases, [5] (u32) extraCount, [6] (u32) overflow, [7] (u32) long count, [8] long scratch total, [9] (u32) sort ticket
-enum { SC_SCAN = 0, SC_EMIT, SC_GROUPED, SC_KEPT, SC_CHANGED, SC_EXTRA, SC_OVERFLOW, SC_NLONG, SC_LONGSCR, SC_TICKET, SC_WIDE, SC_QLIST, SC_PATCH, SC_SLOW, SC_ROUTE /*16 counters*/, SC_BOUNDS = SC_ROUTE + 16 /*17 bounds*/, SC_N = SC_BOUNDS + 20 };
+enum { SC_SCAN = 0, SC_EMIT, SC_GROUPED, SC_KEPT, SC_CHANGED, SC_EXTRA, SC_OVERFLOW, SC_NLONG, SC_LONGSCR, SC_TICKET, SC_WIDE, SC_QLIST, SC_PATCH, SC_SLOW, SC_RTOVF, SC_ROUTE /*16 counters*/, SC_BOUNDS = SC_ROUTE + 16 /*17 bounds*/, SC_N = SC_BOUNDS + 20 };
 
 void rec(cdg_ctx *ctx, int e) { cudaEventRecord(ctx->ev[e], ctx->st); ctx->evValid[e] = true; }
 
@@ -280,13 +282,14 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
                    &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2, &ctx->dQList, &ctx->dPow31,
                    &ctx->dPairModel, &ctx->dPairIn, &ctx->dPairCons, &ctx->dPairOut, &ctx->dRecvIdK, &ctx->dRecvIdV, &ctx->dRouteTab,
-                   &ctx->dIdCnt, &ctx->dCmpCount, &ctx->dCmpTarget, &ctx->dCmpFields, &ctx->dPatches, &ctx->dKey2Big, &ctx->dSetFacts, &ctx->dSlowList, &ctx->dPrep, &ctx->dAlnLen, &ctx->dMism, &ctx->dKey2HiA, &ctx->dKey2HiB};
+                   &ctx->dIdCnt, &ctx->dCmpCount, &ctx->dCmpTarget, &ctx->dCmpFields, &ctx->dPatches, &ctx->dKey2Big, &ctx->dSetFacts, &ctx->dSlowList, &ctx->dPrep, &ctx->dAlnLen, &ctx->dMism, &ctx->dKey2HiA, &ctx->dKey2HiB, &ctx->dHashHist, &ctx->dChunkK, &ctx->dChunkV, &ctx->dRouteBase};
     for (DevBuf *b : d) b->release();
     HostBuf *h[] = {&ctx->hHitRep, &ctx->hHitTgt, &ctx->hHitScore, &ctx->hHitDiag, &ctx->hHitDiag16, &ctx->hLineOff, &ctx->hLineT, &ctx->hKeep,
                     &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE,
                     &ctx->hCmpCount, &ctx->hCmpTarget, &ctx->hCmpFields, &ctx->hPatches};
     for (HostBuf *b : h) b->release();
     for (int i = 0; i < EV_N; i++) cudaEventDestroy(ctx->ev[i]);
+    for (cudaEvent_t e : ctx->chunkDone) cudaEventDestroy(e);
     for (int i = 0; i < 2 * cdgsort::MAX_PASSES; i++) cudaEventDestroy(ctx->passEv[i]);
     cudaStreamSynchronize(ctx->copySt);
     for (int i = 0; i < CDG_UPLOAD_CHUNKS; i++) cudaEventDestroy(ctx->chunkEv[i]);
@@ -558,7 +561,7 @@ static int km_prepare(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlan &K) {
     }
     u64 total = 0;
     if ((rc = read_scalar(ctx, SC_SCAN, &total))) return rc;
-    K.posLo = 0; K.posHi = (u32) n; K.slotBase = 0; K.slots = total;
+    K.posLo = 0; K.posHi = (u32) n; K.slotBase = 0; K.slots = total; K.totalSlots = total;
     if (K.world > 1) {   // slot-balanced slices of the order
         u64 *bounds = (u64 *) (sc + SC_BOUNDS);
         slice_bounds_kernel<<<1, 32, 0, ctx->st>>>(ctx->dSlotRank.as<u64>(), n, total, K.world, bounds);
@@ -585,12 +588,13 @@ static int km_prepare(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlan &K) {
 
 // extraction of the slice into (keys, vals)[0, K.slots); extras (identity hashes inside the k-mer key range) at extraBase
 static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64 *keys, u64 *vals, u64 *idKeys, u64 *idVals, u64 extraBase,
-                      int identityMode /*ExtractParams::identity*/, u32 hashLo, u32 hashHi) {
+                      int identityMode /*ExtractParams::identity*/, u32 hashLo, u32 hashHi, u32 sentinelOwner = 0, bool byRank = false) {
+    byRank = byRank || identityMode == 2;
     using namespace cdgkmer;
     const u64 n = ctx->n;
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
     ExtractParams E; E.k = p->k; E.kmersPerSeq = p->kmers_per_seq; E.scale = p->kmers_per_seq_scale; E.seed = p->hash_shift;
-    E.hashLo = hashLo; E.hashHi = hashHi; E.world = K.world; E.posLo = K.posLo; E.posHi = K.posHi; E.slotBase = K.slotBase; E.identity = identityMode;
+    E.hashLo = hashLo; E.hashHi = hashHi; E.world = K.world; E.posLo = K.posLo; E.posHi = K.posHi; E.slotBase = K.slotBase; E.identity = identityMode; E.sentinelOwner = sentinelOwner;
     int rc;
     u64 nLong64 = 0, longScr = 0;
     if (!is_short_seq(ctx->maxLen, p->k, p->kmers_per_seq, p->kmers_per_seq_scale)) {   // (monotonic in the length: the longest sequence decides)
@@ -628,24 +632,34 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
     // Index-order extraction of a set whose bytes are still arriving (asynchronous upload): per chunk wait for its bytes, pack it,
     // extract it — the copy of the next chunk runs meanwhile.  Otherwise (resident set, or a rank-order slice) one launch.
     std::vector<cdg_ctx::UploadChunk> pieces;
-    if (identityMode != 2 && ctx->pending.size() > 1) { pieces = ctx->pending; ctx->pending.clear(); }
+    if (!byRank && ctx->pending.size() > 1) { pieces = ctx->pending; ctx->pending.clear(); }
     else { if ((rc = ensure_packed(ctx))) return rc; pieces.push_back(cdg_ctx::UploadChunk{0, n, nullptr}); }
     for (const cdg_ctx::UploadChunk &piece : pieces) {
         if (piece.ev) { CK(cudaStreamWaitEvent(ctx->st, piece.ev, 0)); if ((rc = pack_chunk(ctx, piece.seqLo, piece.seqHi))) return rc; }
         E.seqLo = piece.seqLo; E.seqHi = piece.seqHi;
         const u32 maxW = ctx->maxLen >= (u32) p->k ? ctx->maxLen - p->k + 1 : 0;   // short sequences have <= 256 windows
-#define CDG_EXTRACT_ARGS_(LIST, LISTN) (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dPow31.as<u64>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT, identityMode == 2 ? ctx->ordV : (const u64 *) nullptr, ctx->dSlotRank.as<u64>(), LIST, LISTN)
+#define CDG_EXTRACT_ARGS_(LIST, LISTN) (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dPow31.as<u64>(), ctx->dShortScratch.as<WinRec>(), ctx->dShortKeep.as<u8>(), sc + SC_EMIT, byRank ? ctx->ordV : (const u64 *) nullptr, ctx->dSlotRank.as<u64>(), LIST, LISTN)
         // the 16-bit XXH64 score of a window only matters for ownership (hash range, owner rank) and inside the exact replay
         const bool noScore = hashLo == 0 && hashHi >= 65535 && K.world == 1;
         // fast path: GROUP lanes per sequence, possible repeats go to the slow list; then the exact warp-per-sequence kernel on the list
         const u32 *slowList = ctx->dSlowList.as<u32>(); const u32 *slowCount = (const u32 *) (sc + SC_SLOW);
-#define CDG_GROUP_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dPow31.as<u64>(), sc + SC_EMIT, identityMode == 2 ? ctx->ordV : (const u64 *) nullptr, ctx->dSlotRank.as<u64>(), ctx->dSlowList.as<u32>(), (u32 *) (sc + SC_SLOW))
-        if (maxW <= 64) { if (noScore) extract_group_kernel<8, 8, false><<<groupBlocks[0], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; else extract_group_kernel<8, 8, true><<<groupBlocks[0], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; }
-        else if (maxW <= 128) { if (noScore) extract_group_kernel<16, 8, false><<<groupBlocks[1], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; else extract_group_kernel<16, 8, true><<<groupBlocks[1], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; }
+#define CDG_GROUP_ARGS (ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E, ctx->dSlotOff.as<u64>(), keys, vals, idKeys, idVals, extraBase, K.extraCap, (u32 *) (sc + SC_EXTRA), (u32 *) (sc + SC_OVERFLOW), ctx->dRankOf.as<u32>(), ctx->dPow31.as<u64>(), sc + SC_EMIT, byRank ? ctx->ordV : (const u64 *) nullptr, ctx->dSlotRank.as<u64>(), ctx->dSlowList.as<u32>(), (u32 *) (sc + SC_SLOW))
+        // group size from the mean length: 8 lanes cover reads of up to 64 windows (L <= 63 + k), longer short sequences are rare in read
+        // sets (config 3: < 0.1 %) and go through the slow list; sets of mostly longer sequences take 16 or 32 lanes
+        const u32 meanW = (u32) (ctx->totalBases / std::max<u64>(1, n)) >= (u32) p->k ? (u32) (ctx->totalBases / std::max<u64>(1, n)) - p->k + 1 : 0;
+        int gsel = (maxW <= 64 || meanW <= 40) ? 0 : ((maxW <= 128 || meanW <= 80) ? 1 : 2);
+        if (const char *e = getenv("CDG_EXTRACT_GROUP")) { const int v = atoi(e); if (v >= 0 && v <= 2) gsel = v; }   // test knob
+        if (gsel == 0) { if (noScore) extract_group_kernel<8, 8, false><<<groupBlocks[0], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; else extract_group_kernel<8, 8, true><<<groupBlocks[0], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; }
+        else if (gsel == 1) { if (noScore) extract_group_kernel<16, 8, false><<<groupBlocks[1], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; else extract_group_kernel<16, 8, true><<<groupBlocks[1], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; }
         else { if (noScore) extract_group_kernel<32, 8, false><<<groupBlocks[2], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; else extract_group_kernel<32, 8, true><<<groupBlocks[2], EX_WARPS * 32, 0, ctx->st>>> CDG_GROUP_ARGS; }
 #undef CDG_GROUP_ARGS
         ctx->launches++;
         CKL();
+        if (getenv("CDG_DEBUG_EXTRACT")) {
+            u64 a = 0, b = 0;
+            read_scalar(ctx, SC_SLOW, &a); read_scalar(ctx, SC_EMIT, &b);
+            fprintf(stderr, "[extract] gsel %d n %llu pos [%u,%u) after group kernel: slow list %u, emitted %llu\n", gsel, (unsigned long long) n, E.posLo, E.posHi, (u32) a, (unsigned long long) b);
+        }
         {
             ExtractParams keepE = E;
             E.identity = 0;   // the identity records of the listed sequences are already out
@@ -655,6 +669,7 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
             else extract_short_kernel<8><<<shortBlocks, EX_WARPS * 32, 0, ctx->st>>> CDG_EXTRACT_LIST_ARGS;
 #undef CDG_EXTRACT_LIST_ARGS
             E = keepE;
+            if (getenv("CDG_DEBUG_EXTRACT")) { u64 b = 0; read_scalar(ctx, SC_EMIT, &b); fprintf(stderr, "[extract] after the list kernel: emitted %llu\n", (unsigned long long) b); }
             CK(cudaMemsetAsync(sc + SC_SLOW, 0, 8, ctx->st));   // the next piece starts an empty list
         }
 #undef CDG_EXTRACT_ARGS_
@@ -703,20 +718,25 @@ static int km_sort_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K
     return 0;
 }
 
-static int km_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64 Rtot, bool mainHasGlobalFirstRun, bool idHasGlobalFirstRun, u64 *R2out) {
+// append: the grouped records go behind the ones already counted in SC_GROUPED (hash-range passes); mainSkip: leading records of
+// the sorted main array that are grouped separately (the first run of a hash range, see run_kmermatch_split)
+static int km_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64 Rtot, bool mainHasGlobalFirstRun, bool idHasGlobalFirstRun, u64 *R2out,
+                    bool append = false, u64 mainSkip = 0, u64 key2CapOverride = 0) {
     using namespace cdgkmer;
     const u64 n = ctx->n;
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
     int rc;
-    const u64 key2Cap = Rtot + n + CDG_HEAD_RUN;
+    const u64 key2Cap = key2CapOverride ? key2CapOverride : Rtot + n + CDG_HEAD_RUN;
     CK(ctx->dKey2A.reserve(key2Cap * 8)); CK(ctx->dKey2B.reserve(key2Cap * 8));
     if (K.wide) { CK(ctx->dKey2HiA.reserve(key2Cap * 8)); CK(ctx->dKey2HiB.reserve(key2Cap * 8)); }
-    CK(cudaMemsetAsync(sc + SC_GROUPED, 0, 8, ctx->st));
+    if (!append) CK(cudaMemsetAsync(sc + SC_GROUPED, 0, 8, ctx->st));
+    const u64 *mainK = ctx->sortedMainK + mainSkip, *mainV = ctx->sortedMainV + mainSkip;
+    Rtot -= mainSkip;
     GroupParams G; G.idBits = K.idBits; G.diagBits = K.diagBits; G.diagBias = (i32) ctx->maxLen; G.onlyExtendable = p->include_only_extendable;
     G.firstRunQuirk = mainHasGlobalFirstRun ? 1 : 0;   // kmermatcher.cpp:466: only the globally first run
-    if (Rtot && K.wide) group_kernel<true><<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedMainK, ctx->sortedMainV, Rtot, ctx->dLen.as<u32>(), G,
+    if (Rtot && K.wide) group_kernel<true><<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(mainK, mainV, Rtot, ctx->dLen.as<u32>(), G,
                                                                                                                     ctx->dKey2A.as<u64>(), sc + SC_GROUPED, ctx->dKey2HiA.as<u64>());
-    else if (Rtot) group_kernel<<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedMainK, ctx->sortedMainV, Rtot, ctx->dLen.as<u32>(), G,
+    else if (Rtot) group_kernel<<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(mainK, mainV, Rtot, ctx->dLen.as<u32>(), G,
                                                                                                       ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
     GroupParams GI = G; GI.firstRunQuirk = idHasGlobalFirstRun ? 1 : 0;
     const u64 nId = ctx->nIdent;
@@ -794,6 +814,138 @@ static int km_reduce(cdg_ctx *ctx, const KmPlan &K, u64 nOwn, u64 nTotal) {
     return 0;
 }
 
+// ---- hash-range passes on one context (kmermatcher.cpp:615-627 memory sizing, :742-784 setupKmerSplits, :665-675 the split loop) ----
+// The k-mer records of the set do not fit (or `passes` is forced): the 16-bit hash space is cut into `M` contiguous ranges of about
+// equal record count from a 65536-bin histogram, and per range the sequences are extracted chunk by chunk with the range as hash
+// filter, compacted into the range's record array, sorted and grouped; the grouped records of all ranges accumulate and the second
+// sort + reduction run once over all of them, so the result is the UNSPLIT one (the reference's split mode applies the first-run
+// quirk per split and merges unsigned-char scores on the host, :953-1111).  One resident copy of the sequences; peak memory =
+// 4 arrays of the largest range + a chunk buffer + the grouped records.  The first run of every range is grouped at the end,
+// when the range holding the globally smallest k-mer (first-run quirk, :466) is known.
+static int run_kmermatch_split(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, int M) {
+    using namespace cdgkmer;
+    const u64 n = ctx->n;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    int rc;
+    if ((rc = ensure_packed(ctx))) return rc;
+    // 1. histogram of the window hashes -> ranges
+    CK(ctx->dHashHist.reserve(65536 * 8));
+    CK(cudaMemsetAsync(ctx->dHashHist.p, 0, 65536 * 8, ctx->st));
+    ExtractParams E0; E0.k = p->k; E0.kmersPerSeq = p->kmers_per_seq; E0.scale = p->kmers_per_seq_scale; E0.seed = p->hash_shift;
+    E0.hashLo = 0; E0.hashHi = 65535; E0.world = 1; E0.posLo = 0; E0.posHi = (u32) n; E0.slotBase = 0; E0.identity = 0; E0.seqLo = 0; E0.seqHi = n;
+    hash_hist_kernel<<<ctx->smCount * 8, 256, 0, ctx->st>>>(ctx->dWords.as<u64>(), ctx->dXmask.as<u32>(), ctx->dMeta.as<SeqMeta>(), n, E0, ctx->dHashHist.as<unsigned long long>());
+    ctx->launches++;
+    CKL();
+    std::vector<u64> hist(65536);
+    CK(cudaMemcpyAsync(hist.data(), ctx->dHashHist.p, 65536 * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    u64 totalWin = 0;
+    for (u64 v : hist) totalWin += v;
+    if (totalWin == 0) return -100;   // no k-mer at all: the caller runs the unsplit path (nothing to split)
+    std::vector<u32> lo, hi; std::vector<u64> cnt;
+    {
+        const u64 target = (totalWin + (u64) M - 1) / (u64) M;
+        u64 acc = 0, accAll = 0; u32 start = 0;
+        for (u32 b = 0; b < 65536; b++) {
+            acc += hist[b]; accAll += hist[b];
+            if (b == 65535 || (accAll >= target * (lo.size() + 1) && (int) lo.size() < M - 1)) { lo.push_back(start); hi.push_back(b); cnt.push_back(acc); acc = 0; start = b + 1; }
+        }
+    }
+    M = (int) lo.size();
+    u64 rangeCap = 0;
+    for (u64 c : cnt) rangeCap = std::max(rangeCap, c);
+    rangeCap += K.extraCap + 1;
+    if (rangeCap > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "a hash range still holds %llu records (> 2^32): more passes needed", (unsigned long long) rangeCap);
+    // 2. chunks of the (length desc, id asc) order with about half a range of slots each
+    const u64 chunkTarget = std::max<u64>(K.slots / (2ull * (u64) M) + 1, 1ull << 20);
+    const int C = (int) std::min<u64>((K.slots + chunkTarget - 1) / chunkTarget, 4096);
+    std::vector<u32> cpos(C + 1); std::vector<u64> cslot(C + 1);
+    for (int c = 0; c <= C; c++) cpos[c] = (u32) (n * (u64) c / (u64) C);
+    for (int c = 0; c < C; c++) CK(cudaMemcpyAsync(&cslot[c], ctx->dSlotRank.as<u64>() + cpos[c], 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    cslot[C] = K.slots;
+    u64 chunkCap = 0;
+    for (int c = 0; c < C; c++) chunkCap = std::max(chunkCap, cslot[c + 1] - cslot[c]);
+    CK(ctx->dChunkK.reserve((chunkCap + K.extraCap + 1) * 8)); CK(ctx->dChunkV.reserve((chunkCap + K.extraCap + 1) * 8));
+    CK(ctx->dKeysA.reserve(rangeCap * 8)); CK(ctx->dKeysB.reserve(rangeCap * 8)); CK(ctx->dValsA.reserve(rangeCap * 8)); CK(ctx->dValsB.reserve(rangeCap * 8));
+    CK(ctx->dIdKeysA.reserve(n * 8)); CK(ctx->dIdKeysB.reserve(n * 8)); CK(ctx->dIdValsA.reserve(n * 8)); CK(ctx->dIdValsB.reserve(n * 8));
+    const u64 key2Cap = std::min<u64>(totalWin, K.slots) + n + CDG_HEAD_RUN;
+    CK(cudaMemsetAsync(sc + SC_GROUPED, 0, 8, ctx->st));
+    unsigned long long *cursor = sc + SC_ROUTE;   // records of the current range so far
+    std::vector<DevBuf> side(M); std::vector<u64> runLen(M, 0), minKey(M, CDG_SENTINEL);
+    auto releaseSide = [&]() { for (DevBuf &b : side) b.release(); };
+    auto compactInto = [&](const u64 *ck, const u64 *cv, u64 cntSlots) -> int {   // chunk buffer -> behind the range's records (stable)
+        if (!cntSlots) return 0;
+        const u64 tiles = cdgscan::tiles_for(cntSlots);
+        CK(ctx->dTileSums.reserve((tiles + 1) * 8));
+        unsigned long long *ts = ctx->dTileSums.as<unsigned long long>();
+        NotSentinelF f{ck};
+        cdgscan::tile_sum_kernel<<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, cntSlots, ts);
+        cdgscan::tile_scan_kernel<<<1, 1024, 0, ctx->st>>>(ts, tiles, sc + SC_SCAN);
+        compact_records_kernel<<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, cv, cntSlots, ts, cursor, ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>());
+        add_u64_kernel<<<1, 1, 0, ctx->st>>>(cursor, sc + SC_SCAN);
+        ctx->launches += 4;
+        return 0;
+    };
+    ctx->nIdent = n;
+    for (int r = 0; r < M; r++) {
+        CK(cudaMemsetAsync(cursor, 0, 8, ctx->st));
+        CK(cudaMemsetAsync(sc + SC_EXTRA, 0, 8, ctx->st));
+        CK(cudaMemsetAsync(ctx->dChunkK.as<u64>() + chunkCap, 0xFF, (size_t) K.extraCap * 8, ctx->st));
+        CK(cudaMemsetAsync(ctx->dChunkV.as<u64>() + chunkCap, 0, (size_t) K.extraCap * 8, ctx->st));
+        for (int c = 0; c < C; c++) {
+            KmPlan Kc = K; Kc.posLo = cpos[c]; Kc.posHi = cpos[c + 1]; Kc.slotBase = cslot[c]; Kc.slots = cslot[c + 1] - cslot[c];
+            if (Kc.posHi <= Kc.posLo) continue;
+            if ((rc = km_extract(ctx, p, Kc, ctx->dChunkK.as<u64>(), ctx->dChunkV.as<u64>(), ctx->dIdKeysA.as<u64>(), ctx->dIdValsA.as<u64>(), chunkCap, 1, lo[r], hi[r], 0,
+                                 true))) { releaseSide(); return rc; }
+            if ((rc = compactInto(ctx->dChunkK.as<u64>(), ctx->dChunkV.as<u64>(), Kc.slots))) { releaseSide(); return rc; }
+        }
+        if ((rc = compactInto(ctx->dChunkK.as<u64>() + chunkCap, ctx->dChunkV.as<u64>() + chunkCap, K.extraCap))) { releaseSide(); return rc; }
+        CKL();
+        if (r == 0) rec(ctx, EV_EXTRACT);
+        u64 Rr = 0;
+        if ((rc = read_scalar(ctx, SC_ROUTE, &Rr))) { releaseSide(); return rc; }
+        if (Rr > rangeCap) { releaseSide(); return fail(ctx, CDG_ERR_CUDA, "hash range %d holds %llu records, the histogram bound was %llu", r, (unsigned long long) Rr, (unsigned long long) rangeCap); }
+        ctx->idSrcK = ctx->dIdKeysA.as<u64>(); ctx->idSrcV = ctx->dIdValsA.as<u64>(); ctx->idAltK = ctx->dIdKeysB.as<u64>(); ctx->idAltV = ctx->dIdValsB.as<u64>();
+        if ((rc = km_sort_group(ctx, p, K, ctx->dKeysA.as<u64>(), ctx->dKeysB.as<u64>(), ctx->dValsA.as<u64>(), ctx->dValsB.as<u64>(), Rr, 0, &minKey[r], nullptr))) { releaseSide(); return rc; }
+        if (Rr) {
+            first_run_kernel<<<1, 1024, 0, ctx->st>>>(ctx->sortedMainK, Rr, sc + SC_SCAN);
+            ctx->launches++;
+            if ((rc = read_scalar(ctx, SC_SCAN, &runLen[r]))) { releaseSide(); return rc; }
+        }
+        if (runLen[r]) {   // the first run waits in a side buffer until the range with the globally smallest k-mer is known
+            if (side[r].reserve(runLen[r] * 16) != cudaSuccess) { releaseSide(); return fail(ctx, CDG_ERR_CUDA, "out of memory (first run of a hash range)"); }
+            CK(cudaMemcpyAsync(side[r].p, ctx->sortedMainK, runLen[r] * 8, cudaMemcpyDeviceToDevice, ctx->st));
+            CK(cudaMemcpyAsync(side[r].as<u64>() + runLen[r], ctx->sortedMainV, runLen[r] * 8, cudaMemcpyDeviceToDevice, ctx->st));
+        }
+        u64 r2 = 0;
+        if ((rc = km_group(ctx, p, K, Rr, false, false, &r2, true, runLen[r], key2Cap))) { releaseSide(); return rc; }
+    }
+    // 3. the first runs; the quirk goes to the range with the smallest key (ties cannot happen: a k-mer has one hash)
+    int rStar = -1;
+    for (int r = 0; r < M; r++) if (minKey[r] != CDG_SENTINEL && (rStar < 0 || minKey[r] < minKey[rStar])) rStar = r;
+    GroupParams G; G.idBits = K.idBits; G.diagBits = K.diagBits; G.diagBias = (i32) ctx->maxLen; G.onlyExtendable = p->include_only_extendable;
+    for (int r = 0; r < M; r++) {
+        if (!runLen[r]) continue;
+        G.firstRunQuirk = r == rStar ? 1 : 0;
+        const unsigned gb = (unsigned) ((runLen[r] + GROUP_TILE - 1) / GROUP_TILE);
+        if (K.wide) group_kernel<true><<<gb, GROUP_BLOCK, 0, ctx->st>>>(side[r].as<u64>(), side[r].as<u64>() + runLen[r], runLen[r], ctx->dLen.as<u32>(), G, ctx->dKey2A.as<u64>(), sc + SC_GROUPED,
+                                                                      ctx->dKey2HiA.as<u64>());
+        else group_kernel<<<gb, GROUP_BLOCK, 0, ctx->st>>>(side[r].as<u64>(), side[r].as<u64>() + runLen[r], runLen[r], ctx->dLen.as<u32>(), G, ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
+        ctx->launches++;
+    }
+    CKL();
+    u64 R2 = 0, emitted = 0;
+    rc = read_scalar(ctx, SC_GROUPED, &R2);
+    releaseSide();
+    if (rc) return rc;
+    if ((rc = read_scalar(ctx, SC_EMIT, &emitted))) return rc;
+    rec(ctx, EV_GROUP);
+    ctx->nRecords = emitted + n; ctx->nGrouped = R2; ctx->splitPasses = (u32) M;
+    if ((rc = km_sort2(ctx, K, R2))) return rc;
+    return km_reduce(ctx, K, R2, R2);
+}
+
 static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     const u64 n = ctx->n;
     KmPlan K; K.world = 1; K.rank = 0;
@@ -803,9 +955,28 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     CK(cudaMemsetAsync(sc, 0, SC_N * 8, ctx->st));
     rec(ctx, EV_START);
     if ((rc = km_prepare(ctx, p, K))) return rc;
-    ctx->plan = K; ctx->qLo = 0; ctx->nQ = n; ctx->nIdent = n;
+    ctx->plan = K; ctx->qLo = 0; ctx->nQ = n; ctx->nIdent = n; ctx->splitPasses = 1;
     const u64 Rtot = K.slots + K.extraCap;
-    if (Rtot > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "%llu k-mer records exceed one sort (2^32): use hash ranges (multigpu.run_virtual_ranks)", (unsigned long long) Rtot);
+    {   // number of hash-range passes: forced, or from the memory the unsplit arrays would need (kmermatcher.cpp:615-627)
+        int M = p->split_passes;
+        if (const char *e = getenv("CDG_FORCE_SPLITS")) { const int v = atoi(e); if (v > 0) M = v; }   // test knob
+        if (M <= 0) {
+            size_t freeB = 0, totalB = 0;
+            CK(cudaMemGetInfo(&freeB, &totalB));
+            const u64 have = ctx->dKeysA.cap + ctx->dKeysB.cap + ctx->dValsA.cap + ctx->dValsB.cap + ctx->dKey2A.cap + ctx->dKey2B.cap;
+            const u64 needMain = 4 * Rtot * 8, needKey2 = 2 * (Rtot + n + CDG_HEAD_RUN) * 8 * (K.wide ? 2 : 1);
+            const u64 budget = (u64) ((double) (freeB + have) * 0.85);
+            if (Rtot <= cdgsort::MAX_N && needMain + needKey2 <= budget) M = 1;
+            else if (needKey2 >= budget) return fail(ctx, CDG_ERR_UNSUPPORTED, "the grouped records alone (%llu bytes) exceed the free device memory: shard the set over more GPUs", (unsigned long long) needKey2);
+            else M = (int) std::min<u64>(64, std::max<u64>(2, (needMain + needMain / 2 + (budget - needKey2) - 1) / (budget - needKey2)));
+            if (Rtot > cdgsort::MAX_N) M = std::max<int>(M, (int) (Rtot / (cdgsort::MAX_N / 2)) + 1);
+        }
+        if (M > 1 && p->hash_lo == 0 && p->hash_hi >= 65535) {
+            rc = run_kmermatch_split(ctx, p, K, M);
+            if (rc != -100) return rc;
+        }
+    }
+    if (Rtot > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "%llu k-mer records exceed one sort (2^32) and no hash-range split applies", (unsigned long long) Rtot);
     CK(ctx->dKeysA.reserve(Rtot * 8)); CK(ctx->dKeysB.reserve(Rtot * 8)); CK(ctx->dValsA.reserve(Rtot * 8)); CK(ctx->dValsB.reserve(Rtot * 8));
     CK(ctx->dIdKeysA.reserve(n * 8)); CK(ctx->dIdKeysB.reserve(n * 8)); CK(ctx->dIdValsA.reserve(n * 8)); CK(ctx->dIdValsB.reserve(n * 8));
     CK(cudaMemsetAsync(ctx->dKeysA.as<u64>() + K.slots, 0xFF, (size_t) K.extraCap * 8, ctx->st));
@@ -1351,7 +1522,7 @@ extern "C" int cdg_get_stats(cdg_ctx *ctx, cdg_stats *out) {
     cudaStreamSynchronize(ctx->st);
     out->ms_extract = el(EV_START, EV_EXTRACT); out->ms_sort1 = el(EV_EXTRACT, EV_SORT1); out->ms_group = el(EV_SORT1, EV_GROUP);
     out->ms_sort2 = el(EV_GROUP, EV_SORT2);
-    out->ms_sort1_passes = 0.f; out->n_sort1_pass_launches = 0; out->sort1_records = ctx->sort1Records;
+    out->ms_sort1_passes = 0.f; out->n_sort1_pass_launches = 0; out->sort1_records = ctx->sort1Records; out->split_passes = ctx->splitPasses;
     for (int i = 0; i < ctx->passEvN; i++) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ctx->passEv[2 * i], ctx->passEv[2 * i + 1]) == cudaSuccess) { out->ms_sort1_passes += ms; out->n_sort1_pass_launches++; } } out->ms_reduce = el(EV_SORT2, EV_REDUCE); out->ms_rescore = el(EV_RS0, EV_RS1); out->ms_correct = el(EV_CO0, EV_CO1);
     return CDG_OK;
 }
@@ -1427,6 +1598,163 @@ extern "C" int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world,
     if (send_vals) *send_vals = pv;
     if (id_send_keys) *id_send_keys = ik;
     if (id_send_vals) *id_send_vals = iv;
+    return CDG_OK;
+}
+
+// ---- streamed record exchange: extraction and routing overlap ------------------------------------------------------------
+// Every owner's receive area is split into `world` regions of cap_per_source records, one per source rank (in rank order, so the
+// receiver's stable sort still sees the sources in (length desc, id asc) order).  A source extracts its slice in chunks and, while
+// chunk c+1 is being extracted, the routing pass of chunk c writes each owner's records behind the ones already sent (running
+// per-owner counts on the device) — no count matrix is needed before the transfer starts.  The unused tail of every region is
+// filled with sentinels by the receiver (cdg_mg_recv_fill).  Hash ownership is uniform, so a region holds 1/world^2 of the set's
+// k-mer slots plus a few per cent; a source that would overrun a region (degenerate sets) reports *overflow and the caller falls
+// back to the counted exchange (cdg_mg_extract / cdg_mg_scatter_records).
+extern "C" int cdg_mg_plan(cdg_ctx *ctx, const cdg_kmer_params *p, int world, int rank, uint64_t *cap_per_source) {
+    if (!ctx || !p || !cap_per_source || world < 1 || world > CDG_MAX_WORLD || rank < 0 || rank >= world) return CDG_ERR_ARG;
+    if (ctx->n == 0) return fail(ctx, CDG_ERR_ARG, "cdg_mg_plan: no sequence set uploaded");
+    CK(cudaSetDevice(ctx->device));
+    KmPlan K; K.world = (u32) world; K.rank = (u32) rank;
+    int rc = km_bits(ctx, p, K);
+    if (rc) return rc;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    CK(cudaMemsetAsync(sc, 0, SC_N * 8, ctx->st));
+    if ((rc = km_prepare(ctx, p, K))) return rc;
+    ctx->plan = K; ctx->qLo = K.qLo; ctx->nQ = K.nQ; ctx->planReady = true;
+    const u64 perPair = K.totalSlots / ((u64) world * (u64) world);
+    *cap_per_source = ((perPair + perPair / 64 + K.extraCap + 65536 + 4095) / 4096) * 4096;   // + 1.5 % and the spare identity slots
+    return CDG_OK;
+}
+
+extern "C" int cdg_mg_extract_stream(cdg_ctx *ctx, const cdg_kmer_params *p, int chunks, uint64_t cap_per_source, uint64_t *send_counts,
+                                     uint64_t *id_send_counts, int *overflow) {
+    if (!ctx || !p || !send_counts || !id_send_counts || !overflow || chunks < 1) return CDG_ERR_ARG;
+    if (!ctx->planReady) return fail(ctx, CDG_ERR_ARG, "cdg_mg_extract_stream: call cdg_mg_plan first");
+    CK(cudaSetDevice(ctx->device));
+    ctx->planReady = false;
+    const KmPlan K = ctx->plan;
+    const u32 world = K.world, rank = K.rank;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    int rc;
+    const u64 R = K.slots + K.extraCap;
+    const u64 nSlice = (u64) K.posHi - K.posLo;
+    if (R > cdgsort::SMALL_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "slice has too many k-mer records for one routing pass (2^30)");
+    CK(ctx->dKeysA.reserve((R + 1) * 8)); CK(ctx->dValsA.reserve((R + 1) * 8)); CK(ctx->dKeysB.reserve((R + 1) * 8)); CK(ctx->dValsB.reserve((R + 1) * 8));
+    CK(ctx->dIdKeysA.reserve((nSlice + 1) * 8)); CK(ctx->dIdKeysB.reserve((nSlice + 1) * 8)); CK(ctx->dIdValsA.reserve((nSlice + 1) * 8)); CK(ctx->dIdValsB.reserve((nSlice + 1) * 8));
+    const u32 discard = world < (u32) cdgsort::ROUTE_MAX ? (u32) cdgsort::ROUTE_MAX - 1 : 0u;   // unused slots: a local trash area, not rank 0
+    CK(cudaMemsetAsync(ctx->dKeysA.as<u64>() + K.slots, 0xFF, (size_t) K.extraCap * 8, ctx->st));
+    {   // (value words of the spare slots carry the discard tag)
+        std::vector<u64> fillv(K.extraCap, cdg_pack_val(0, 0, discard));
+        CK(cudaMemcpyAsync(ctx->dValsA.as<u64>() + K.slots, fillv.data(), (size_t) K.extraCap * 8, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+    }
+    // routing tables: region `rank` of every owner's receive area; the discard destination is the local partner buffer
+    cdgsort::Workspace ws;
+    if ((rc = sort_ws(ctx, std::max<u64>(R, ctx->n), ws))) return rc;
+    CK(ctx->dRouteTab.reserve(6 * cdgsort::ROUTE_MAX * sizeof(void *)));
+    struct { u64 *v[cdgsort::ROUTE_MAX]; u64 *k[cdgsort::ROUTE_MAX]; u64 cap[cdgsort::ROUTE_MAX]; } tab = {};
+    for (u32 o = 0; o < world; o++) {
+        u64 *bk = o == rank ? ctx->dRecvK.as<u64>() : (u64 *) ctx->peerPtr[0][o], *bv = o == rank ? ctx->dRecvV.as<u64>() : (u64 *) ctx->peerPtr[1][o];
+        if (!bk || !bv) return fail(ctx, CDG_ERR_ARG, "cdg_mg_extract_stream: receive buffers of rank %u are not mapped (cdg_mg_ipc_open)", o);
+        tab.k[o] = bk + (u64) rank * cap_per_source; tab.v[o] = bv + (u64) rank * cap_per_source; tab.cap[o] = cap_per_source;
+    }
+    if (discard) { tab.k[discard] = ctx->dKeysB.as<u64>(); tab.v[discard] = ctx->dValsB.as<u64>(); tab.cap[discard] = R + 1; }
+    CK(cudaMemcpyAsync(ctx->dRouteTab.p, &tab, sizeof tab, cudaMemcpyHostToDevice, ctx->st));
+    u64 *const *dV = ctx->dRouteTab.as<u64 *>(), *const *dK = dV + cdgsort::ROUTE_MAX;
+    const u64 *dCap = (const u64 *) (dK + cdgsort::ROUTE_MAX);
+    CK(ctx->dRouteBase.reserve(cdgsort::RADIX * 8));
+    unsigned long long *cursor = ctx->dRouteBase.as<unsigned long long>();      // records already sent per destination (one entry per digit of the pass)
+    CK(cudaMemsetAsync(cursor, 0, cdgsort::RADIX * 8, ctx->st));
+    CK(cudaMemsetAsync(sc + SC_RTOVF, 0, 8, ctx->st));
+    // chunk boundaries: equal shares of the slice's ranks; their first slots from the prefix array
+    std::vector<u32> cpos(chunks + 1); std::vector<u64> cslot(chunks + 1);
+    for (int c = 0; c <= chunks; c++) cpos[c] = (u32) (K.posLo + nSlice * (u64) c / (u64) chunks);
+    for (int c = 0; c <= chunks; c++) {
+        if (cpos[c] >= ctx->n) cslot[c] = K.slotBase + K.slots;
+        else CK(cudaMemcpyAsync(&cslot[c], ctx->dSlotRank.as<u64>() + cpos[c], 8, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CK(cudaStreamSynchronize(ctx->st));
+    cslot[chunks] = K.slotBase + K.slots;
+    const int ownerBits = 4;   // all 16 destinations: the ranks and the discard bin
+    const cdgsort::Pass pass{0, CDG_OWNER_SHIFT, (1u << ownerBits) - 1};
+    if ((int) ctx->chunkDone.size() < chunks + 1) {
+        const size_t old = ctx->chunkDone.size();
+        ctx->chunkDone.resize(chunks + 1);
+        for (size_t i = old; i < ctx->chunkDone.size(); i++) CK(cudaEventCreateWithFlags(&ctx->chunkDone[i], cudaEventDisableTiming));
+    }
+    auto routeRange = [&](u64 slotLo, u64 slotHi) -> int {   // on the copy stream: digit words = values (owner tag), payload = keys
+        const u64 cnt = slotHi - slotLo;
+        if (!cnt) return 0;
+        const u64 tiles = cdgsort::route_tiles(cnt);
+        CK(cudaMemsetAsync(ws.tileState, 0, tiles * cdgsort::RADIX * sizeof(u32), ctx->copySt));
+        CK(cudaMemsetAsync(ws.ticket, 0, sizeof(u32), ctx->copySt));
+        cdgsort::launch_route_pass(ctx->copySt, ctx->dValsA.as<u64>() + slotLo, ctx->dKeysA.as<u64>() + slotLo, cnt, pass, cursor, ws.tileState, ws.ticket, dV, dK, dCap,
+                                   (u32 *) (sc + SC_RTOVF));
+        cdgsort::route_advance_kernel<<<1, 32, 0, ctx->copySt>>>(ws.tileState, tiles, cursor);
+        ctx->launches += 2;
+        return 0;
+    };
+    CK(cudaEventRecord(ctx->evReady, ctx->st));
+    CK(cudaStreamWaitEvent(ctx->copySt, ctx->evReady, 0));   // tables, cursors and the spare slots are in place
+    for (int c = 0; c < chunks; c++) {
+        KmPlan Kc = K; Kc.posLo = cpos[c]; Kc.posHi = cpos[c + 1];
+        if (Kc.posHi > Kc.posLo) {
+            // identity records of the chunk land at their slice position (the kernels index them relative to the chunk's first rank)
+            if ((rc = km_extract(ctx, p, Kc, ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>(), ctx->dIdKeysA.as<u64>() + (cpos[c] - K.posLo),
+                                 ctx->dIdValsA.as<u64>() + (cpos[c] - K.posLo), K.slots, 2, 0, 65535, discard))) return rc;
+        }
+        CK(cudaEventRecord(ctx->chunkDone[c], ctx->st));
+        CK(cudaStreamWaitEvent(ctx->copySt, ctx->chunkDone[c], 0));
+        if ((rc = routeRange(cslot[c] - K.slotBase, cslot[c + 1] - K.slotBase))) return rc;
+    }
+    if ((rc = routeRange(K.slots, R))) return rc;     // the spare slots (identity hashes inside the k-mer key range)
+    CKL();
+    unsigned long long hc[17];
+    CK(cudaMemcpyAsync(hc, cursor, 16 * 8, cudaMemcpyDeviceToHost, ctx->copySt));
+    CK(cudaMemcpyAsync(hc + 16, sc + SC_RTOVF, 8, cudaMemcpyDeviceToHost, ctx->copySt));
+    CK(cudaStreamSynchronize(ctx->copySt));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (u32 o = 0; o < world; o++) send_counts[o] = hc[o];
+    *overflow = (u32) hc[16] ? 1 : 0;
+    // identity records: counted here, sent by cdg_mg_scatter_records(NULL, id offsets) once the ranks know each other's counts
+    for (u32 o = 0; o < world; o++) id_send_counts[o] = 0;
+    if (nSlice) {
+        const int ob = std::max(1, ceil_log2((u64) world));
+        cdgsort::Plan plan = cdgsort::make_plan(0, 0, CDG_OWNER_SHIFT, CDG_OWNER_SHIFT + ob);
+        CK(cudaMemsetAsync(ws.hist, 0, sizeof(unsigned long long) * cdgsort::RADIX, ctx->st));
+        int hb = (int) std::min<u64>((nSlice + cdgsort::BLOCK - 1) / cdgsort::BLOCK, (u64) ctx->smCount * 8);
+        cdgsort::hist_kernel<<<hb, cdgsort::BLOCK, cdgsort::RADIX * sizeof(u32), ctx->st>>>(ctx->dIdValsA.as<u64>(), nullptr, nSlice, plan, ws.hist);
+        ctx->launches++;
+        unsigned long long hh[cdgsort::RADIX];
+        CK(cudaMemcpyAsync(hh, ws.hist, sizeof hh, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        for (u32 o = 0; o < world; o++) id_send_counts[o] = hh[o];
+    }
+    ctx->mgSlice = nSlice; ctx->mgMainK = ctx->dKeysA.as<u64>(); ctx->mgMainV = ctx->dValsA.as<u64>(); ctx->mgIdK = ctx->dIdKeysA.as<u64>(); ctx->mgIdV = ctx->dIdValsA.as<u64>();
+    return CDG_OK;
+}
+
+// receiver side of the streamed exchange: region r of the receive area holds counts[r] records, the rest becomes sentinels
+__global__ void __launch_bounds__(256) region_fill_kernel(u64 *__restrict__ keys, u64 *__restrict__ vals, const unsigned long long *__restrict__ counts, u32 world,
+                                                          u64 cap) {
+    const u32 r = blockIdx.y;
+    if (r >= world) return;
+    for (u64 i = counts[r] + (u64) blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64) gridDim.x * blockDim.x) {
+        keys[(u64) r * cap + i] = CDG_SENTINEL; vals[(u64) r * cap + i] = 0;
+    }
+}
+extern "C" int cdg_mg_recv_fill(cdg_ctx *ctx, const uint64_t *counts, uint64_t cap_per_source) {
+    if (!ctx || !counts) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const u32 world = ctx->plan.world;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    unsigned long long hc[16] = {};
+    for (u32 r = 0; r < world; r++) { if (counts[r] > cap_per_source) return fail(ctx, CDG_ERR_ARG, "cdg_mg_recv_fill: a source sent more than a region holds"); hc[r] = counts[r]; }
+    CK(cudaMemcpyAsync(sc + SC_ROUTE, hc, sizeof hc, cudaMemcpyHostToDevice, ctx->st));
+    region_fill_kernel<<<dim3(64, world), 256, 0, ctx->st>>>(ctx->dRecvK.as<u64>(), ctx->dRecvV.as<u64>(), sc + SC_ROUTE, world, cap_per_source);
+    ctx->launches++;
+    CKL();
+    CK(cudaStreamSynchronize(ctx->st));   // (hc is a stack array)
+    ctx->mgRecv = (u64) world * cap_per_source;
     return CDG_OK;
 }
 
@@ -1577,7 +1905,7 @@ extern "C" int cdg_mg_ipc_open(cdg_ctx *ctx, int which, int peer, const void *ha
 // buffers.  dst_off[o] / id_dst_off[o] = first record index of this rank's segment in rank o's k-mer / identity receive area
 // (= records the lower ranks send to o).  Own segment: the local buffer.  The caller synchronises the ranks afterwards.
 extern "C" int cdg_mg_scatter_records(cdg_ctx *ctx, const uint64_t *dst_off, const uint64_t *id_dst_off) {
-    if (!ctx || !dst_off || !id_dst_off) return CDG_ERR_ARG;
+    if (!ctx || !id_dst_off) return CDG_ERR_ARG;   // dst_off == NULL: identity records only (the k-mer records went with cdg_mg_extract_stream)
     CK(cudaSetDevice(ctx->device));
     const KmPlan &K = ctx->plan;
     const u32 world = K.world, rank = K.rank;
@@ -1591,6 +1919,7 @@ extern "C" int cdg_mg_scatter_records(cdg_ctx *ctx, const uint64_t *dst_off, con
         DevBuf *own[4] = {&ctx->dRecvV, &ctx->dRecvK, &ctx->dRecvIdV, &ctx->dRecvIdK};   // digit word = value (owner bits), payload = key
         const int which[4] = {1, 0, 3, 2};
         for (int a = 0; a < 4; a++) {
+            if (a < 2 && !dst_off) continue;
             u64 *base = o == rank ? own[a]->as<u64>() : (u64 *) ctx->peerPtr[which[a]][o];
             if (!base) return fail(ctx, CDG_ERR_ARG, "cdg_mg_scatter_records: receive buffer %d of rank %u is not mapped (cdg_mg_ipc_open)", which[a], o);
             tab[a][o] = base + (a < 2 ? dst_off[o] : id_dst_off[o]);
@@ -1609,7 +1938,7 @@ extern "C" int cdg_mg_scatter_records(cdg_ctx *ctx, const uint64_t *dst_off, con
         ctx->launches++;
         return 0;
     };
-    if ((rc = route(ctx->mgMainV, ctx->mgMainK, R, dtab, dtab + cdgsort::ROUTE_MAX))) return rc;
+    if (dst_off && (rc = route(ctx->mgMainV, ctx->mgMainK, R, dtab, dtab + cdgsort::ROUTE_MAX))) return rc;
     if ((rc = route(ctx->mgIdV, ctx->mgIdK, nSlice, dtab + 2 * cdgsort::ROUTE_MAX, dtab + 3 * cdgsort::ROUTE_MAX))) return rc;
     CKL();
     CK(cudaStreamSynchronize(ctx->st));

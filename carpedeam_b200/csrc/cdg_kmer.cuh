@@ -81,6 +81,7 @@ struct ExtractParams {
     // (routed with the k-mer records); 0 = none.
     u32 world, posLo, posHi; u64 slotBase; int identity;
     u64 seqLo, seqHi;   // index-order iteration (single GPU): sequences [seqLo, seqHi) of this launch (chunked upload pipeline)
+    u32 sentinelOwner = 0;   // owner tag of unused slots (streamed multi-GPU exchange: a discard destination instead of rank 0)
 };
 CDG_D u32 owner_of(u32 score, u32 world) { return (score * world) >> 16; }
 // slots reserved for sequence of length L: upper bound of selected k-mers (kmermatcher.cpp:226)
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, ITERS <= 2 ? 5 : 1) extract_sho
             }
             __syncwarp();
         }
-        for (u32 s = written + lane; s < cap; s += 32) { mainKeys[slot0 + s] = CDG_SENTINEL; mainVals[slot0 + s] = 0; }
+        for (u32 s = written + lane; s < cap; s += 32) { mainKeys[slot0 + s] = CDG_SENTINEL; mainVals[slot0 + s] = cdg_pack_val(0, 0, P.sentinelOwner); }
         localEmitted += written;
         // next sequence's packed words towards L1 while this one's records drain
         if (lane < 2 && cur + nwarps < itHi) {
@@ -419,7 +420,11 @@ __global__ void __launch_bounds__(EX_WARPS * 32, GROUP == 8 ? 4 : 5) extract_gro
         active = active && is_short_seq(L, P.k, P.kmersPerSeq, P.scale) && myRank >= P.posLo && myRank < P.posHi;
         const u64 *w = words + sm.wordOff;
         const u32 *xm = xmask + sm.wordOff;
-        const u32 W = (active && L >= (u32) P.k) ? L - P.k + 1 : 0;
+        u32 W = (active && L >= (u32) P.k) ? L - P.k + 1 : 0;
+        // a short sequence with more windows than GROUP * ITERS (the group size follows the typical read, not the longest one): its
+        // identity record is written here, its windows by the exact kernel through the slow list
+        const bool tooLong = W > (u32) (GROUP * ITERS);
+        if (tooLong) W = 0;
         // identity hash (Util::hash, Util.h:337-346): sum of code_p * 31^(L-1-p), lane gl takes p = gl, gl+GROUP, ...
         u64 part = 0;
         if (active) {
@@ -438,14 +443,10 @@ __global__ void __launch_bounds__(EX_WARPS * 32, GROUP == 8 ? 4 : 5) extract_gro
         // windows
         const u64 slot0 = slotAbs - P.slotBase;
         u32 written = 0, flagged = 0;
-        u32 hh[ITERS];   // the window's filter word, 0xFFFFFFFF = no valid window in this iteration
-        u32 maxW = W;
-#pragma unroll
-        for (int o = 16; o >= GROUP; o >>= 1) maxW = max(maxW, __shfl_xor_sync(0xffffffffu, maxW, o));   // over the groups of the warp
-#pragma unroll
-        for (int it = 0; it < ITERS; it++) {
-            hh[it] = 0xFFFFFFFFu;
-            if ((u32) (it * GROUP) >= maxW) continue;     // warp-uniform
+        u64 touched = 0;      // filter words this lane set a bit in: 7 bits per iteration, bit 7 of each byte = valid
+        const u32 maxW = __reduce_max_sync(0xffffffffu, W);   // over the groups of the warp: every lane runs the same number of iterations
+        const int nIt = (int) ((maxW + GROUP - 1) / GROUP);   // <= ITERS
+        for (int it = 0; it < nIt; it++) {
             const u32 p = gl + GROUP * it;
             WinRec r; bool ok = false;
             if (p < W) ok = make_window<SCORE>(w, xm, p, L, P, r);
@@ -455,8 +456,9 @@ __global__ void __launch_bounds__(EX_WARPS * 32, GROUP == 8 ? 4 : 5) extract_gro
                 const u64 canon = r.kmer & ~CDG_B63;
                 const u32 mix = ((u32) canon ^ (u32) (canon >> 19)) * 0x9E3779B1u;
                 const unsigned long long bits = (1ull << ((mix >> 19) & 63u)) | (1ull << ((mix >> 13) & 63u));
-                hh[it] = mix >> 25;
-                const unsigned long long old = atomicOr(&bm[hh[it]], bits);
+                const u32 word = mix >> 25;
+                touched |= (u64) (0x80u | word) << (8 * it);
+                const unsigned long long old = atomicOr(&bm[word], bits);
                 if ((old & bits) == bits) flagged = 1;
             }
             const u32 b = __ballot_sync(0xffffffffu, own) & gmask;
@@ -468,13 +470,13 @@ __global__ void __launch_bounds__(EX_WARPS * 32, GROUP == 8 ? 4 : 5) extract_gro
             written += __popc(b);
         }
         __syncwarp();
-        // clear the touched bitmap words (cheaper than wiping 1 KB per sequence)
-#pragma unroll
-        for (int it = 0; it < ITERS; it++) if (hh[it] != 0xFFFFFFFFu) bm[hh[it]] = 0;
-        const bool slow = (__ballot_sync(0xffffffffu, flagged) & gmask) != 0;
+        // clear the touched filter words (cheaper than wiping 1 KB per sequence)
+        for (u64 t = touched; t; t >>= 8) if (t & 0x80u) bm[t & 0x7Fu] = 0;
+        const u32 flaggedLanes = __ballot_sync(0xffffffffu, flagged) & gmask;   // (taken by every lane: no short-circuit in front of a warp collective)
+        const bool slow = tooLong || flaggedLanes != 0;
         if (active) {
             const u32 cap = kmer_capacity(L, P.k, P.kmersPerSeq, P.scale);
-            for (u32 sI = written + gl; sI < cap; sI += GROUP) { mainKeys[slot0 + sI] = CDG_SENTINEL; mainVals[slot0 + sI] = 0; }
+            if (!tooLong) for (u32 sI = written + gl; sI < cap; sI += GROUP) { mainKeys[slot0 + sI] = CDG_SENTINEL; mainVals[slot0 + sI] = cdg_pack_val(0, 0, P.sentinelOwner); }
             if (gl == 0) {
                 if (slow) slowList[atomicAdd(slowCount, 1u)] = (u32) cur;   // the exact path rewrites the slots and counts the records
                 else localEmitted += written;
@@ -483,6 +485,57 @@ __global__ void __launch_bounds__(EX_WARPS * 32, GROUP == 8 ? 4 : 5) extract_gro
         __syncwarp();
     }
     if (localEmitted) atomicAdd(emitted, localEmitted);
+}
+
+// ---- hash-range passes (kmermatcher.cpp:742-784 setupKmerSplits) ------------------------------------------------------------
+// 65536-bin histogram of the 16-bit hashes of every valid window of the set: an upper bound of the records a hash range will hold
+// (repeated k-mers and the per-sequence hash threshold only remove records), from which the host cuts contiguous ranges of about
+// equal size.  One warp per sequence.
+__global__ void __launch_bounds__(256) hash_hist_kernel(const u64 *__restrict__ words, const u32 *__restrict__ xmask, const SeqMeta *__restrict__ meta, u64 n,
+                                                        ExtractParams P, unsigned long long *__restrict__ hist /*[65536]*/) {
+    const int lane = threadIdx.x & 31;
+    const u64 gwarp = ((u64) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64) gridDim.x * blockDim.x) >> 5;
+    for (u64 seq = gwarp; seq < n; seq += nwarps) {
+        const SeqMeta sm = meta[seq];
+        const u32 L = sm.lenFlags & META_LEN;
+        if (L < (u32) P.k) continue;
+        const u64 *w = words + sm.wordOff;
+        const u32 *xm = xmask + sm.wordOff;
+        for (u32 p = lane; p + P.k <= L; p += 32) {
+            WinRec r;
+            if (make_window<true>(w, xm, p, L, P, r)) atomicAdd(&hist[r.score], 1ull);
+        }
+    }
+}
+// records of a chunk buffer that are not sentinels, appended in order behind *base records of (outK, outV)
+struct NotSentinelF { const u64 *keys; CDG_D u32 operator()(u64 i) const { return keys[i] != CDG_SENTINEL ? 1u : 0u; } };
+__global__ void __launch_bounds__(cdgscan::BLOCK) compact_records_kernel(NotSentinelF f, const u64 *__restrict__ vals, u64 n, const unsigned long long *__restrict__ tileSums,
+                                                                         const unsigned long long *__restrict__ base, u64 *__restrict__ outK, u64 *__restrict__ outV) {
+    __shared__ u32 shWarp[cdgscan::BLOCK / 32 + 1];
+    u64 prefix[cdgscan::ITEMS]; u32 val[cdgscan::ITEMS];
+    cdgscan::tile_prefix(f, n, tileSums, shWarp, prefix, val);
+    const u64 b = *base, tb = (u64) blockIdx.x * cdgscan::TILE;
+#pragma unroll
+    for (int i = 0; i < cdgscan::ITEMS; i++) {
+        const u64 idx = tb + (u64) i * cdgscan::BLOCK + threadIdx.x;
+        if (idx < n && val[i]) { outK[b + prefix[i]] = f.keys[idx]; outV[b + prefix[i]] = vals[idx]; }
+    }
+}
+__global__ void add_u64_kernel(unsigned long long *dst, const unsigned long long *src) { *dst += *src; }
+// length of the first run of equal k-mers of a sorted key array (strand bit ignored); sentinels never start a run
+__global__ void __launch_bounds__(1024) first_run_kernel(const u64 *__restrict__ keys, u64 n, unsigned long long *__restrict__ out) {
+    __shared__ unsigned long long firstOther;
+    if (threadIdx.x == 0) firstOther = ~0ull;
+    __syncthreads();
+    if (n == 0 || keys[0] == CDG_SENTINEL) { if (threadIdx.x == 0) *out = 0; return; }
+    const u64 k0 = keys[0] | CDG_B63;
+    for (u64 b = 0; b < n; b += 1024) {
+        const u64 i = b + threadIdx.x;
+        if (i < n && (keys[i] == CDG_SENTINEL || (keys[i] | CDG_B63) != k0)) atomicMin(&firstOther, (unsigned long long) i);
+        __syncthreads();
+        if (firstOther != ~0ull) break;
+    }
+    if (threadIdx.x == 0) *out = firstOther == ~0ull ? n : firstOther;
 }
 
 // ---- long sequences (hash threshold active or > 256 windows): one block per sequence -------------------
@@ -606,7 +659,7 @@ __global__ void __launch_bounds__(EXL_BLOCK) extract_long_kernel(
         }
         __syncthreads();
         const u32 written = sWritten;
-        for (u32 s = written + tid; s < cap; s += EXL_BLOCK) { mainKeys[slot0 + s] = CDG_SENTINEL; mainVals[slot0 + s] = 0; }
+        for (u32 s = written + tid; s < cap; s += EXL_BLOCK) { mainKeys[slot0 + s] = CDG_SENTINEL; mainVals[slot0 + s] = cdg_pack_val(0, 0, P.sentinelOwner); }
         if (tid == 0 && written) atomicAdd(emitted, (unsigned long long) written);
         __syncthreads();
     }

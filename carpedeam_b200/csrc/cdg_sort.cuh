@@ -112,6 +112,7 @@ struct SweepSmem {
     u32 warpSum[8];
     u32 sTile;
     u64 *routeK[ROUTE_MAX]; u64 *routeV[ROUTE_MAX];   // ROUTE: per-digit output bases (peer-mapped receive buffers)
+    u64 routeCap[ROUTE_MAX];                          // ... and how many records each may take (a record beyond is dropped and flagged)
     u8 digitAt[HAS_VAL ? TILE_T : 4];
 };
 
@@ -137,13 +138,14 @@ __global__ void __launch_bounds__(BLOCK_T, (BLOCK_T == 256 && ITEMS_T == 16) ? (
                                                            const u64 *__restrict__ valsIn, u64 *__restrict__ valsOut, u64 n,
                                                            Pass pass, const unsigned long long *__restrict__ binBase,
                                                            ST *tileState /*[tiles][RADIX]*/, u32 *ticket,
-                                                           u64 *const *__restrict__ routeK = nullptr, u64 *const *__restrict__ routeV = nullptr) {
+                                                           u64 *const *__restrict__ routeK = nullptr, u64 *const *__restrict__ routeV = nullptr,
+                                                           const u64 *__restrict__ routeCap = nullptr /*ROUTE: records destination d can take*/, u32 *routeOverflow = nullptr) {
     constexpr int TILE_T = BLOCK_T * ITEMS_T, WARPS_T = BLOCK_T / 32;
     extern __shared__ __align__(16) unsigned char sweepRaw[];
     SweepSmem<BLOCK_T, ITEMS_T, HAS_VAL> &S = *reinterpret_cast<SweepSmem<BLOCK_T, ITEMS_T, HAS_VAL> *>(sweepRaw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (ROUTE && tid < ROUTE_MAX) { S.routeK[tid] = routeK[tid]; if (HAS_VAL) S.routeV[tid] = routeV[tid]; }
+    if (ROUTE && tid < ROUTE_MAX) { S.routeK[tid] = routeK[tid]; if (HAS_VAL) S.routeV[tid] = routeV[tid]; S.routeCap[tid] = routeCap ? routeCap[tid] : ~0ull; }
     if (tid == 0) S.sTile = atomicAdd(ticket, 1u);
     for (int i = tid; i < WARPS_T * RADIX; i += BLOCK_T) (&S.warpHist[0][0])[i] = 0;
     __syncthreads();
@@ -255,7 +257,8 @@ __global__ void __launch_bounds__(BLOCK_T, (BLOCK_T == 256 && ITEMS_T == 16) ? (
             const u32 j = tid + i * BLOCK_T;
             const u64 k = S.exch[j];
             const u32 dg = digit_of(k, pass.shift, pass.mask);
-            (ROUTE ? S.routeK[dg & (ROUTE_MAX - 1)] : keysOut)[S.delta[dg] + j] = k;
+            if (ROUTE) { const u64 idx = S.delta[dg] + j; if (idx < S.routeCap[dg & (ROUTE_MAX - 1)]) S.routeK[dg & (ROUTE_MAX - 1)][idx] = k; else *routeOverflow = 1u; }
+            else keysOut[S.delta[dg] + j] = k;
         }
     } else {
 #pragma unroll
@@ -264,7 +267,8 @@ __global__ void __launch_bounds__(BLOCK_T, (BLOCK_T == 256 && ITEMS_T == 16) ? (
             if (j < tileValid) {
                 const u64 k = S.exch[j];
                 const u32 dg = digit_of(k, pass.shift, pass.mask);
-                (ROUTE ? S.routeK[dg & (ROUTE_MAX - 1)] : keysOut)[S.delta[dg] + j] = k;
+                if (ROUTE) { const u64 idx = S.delta[dg] + j; if (idx < S.routeCap[dg & (ROUTE_MAX - 1)]) S.routeK[dg & (ROUTE_MAX - 1)][idx] = k; else *routeOverflow = 1u; }
+                else keysOut[S.delta[dg] + j] = k;
             }
         }
     }
@@ -276,7 +280,11 @@ __global__ void __launch_bounds__(BLOCK_T, (BLOCK_T == 256 && ITEMS_T == 16) ? (
 #pragma unroll
         for (int i = 0; i < ITEMS_T; i++) {
             const u32 j = tid + i * BLOCK_T;
-            if (full || j < tileValid) { const u32 dg = S.digitAt[j]; (ROUTE ? S.routeV[dg & (ROUTE_MAX - 1)] : valsOut)[S.delta[dg] + j] = S.exch[j]; }
+            if (full || j < tileValid) {
+                const u32 dg = S.digitAt[j];
+                if (ROUTE) { const u64 idx = S.delta[dg] + j; if (idx < S.routeCap[dg & (ROUTE_MAX - 1)]) S.routeV[dg & (ROUTE_MAX - 1)][idx] = S.exch[j]; }
+                else valsOut[S.delta[dg] + j] = S.exch[j];
+            }
         }
     }
 }
@@ -492,13 +500,21 @@ inline void launch_pass_wide(cudaStream_t st, const u64 *ki, u64 *ko, const u64 
 }
 
 // routing pass (send side of the all-to-all): digits = destination ranks, outputs = peer-mapped segment bases (device tables)
+// base: per-destination index of the first record of this launch (all zero, or the running counts of a chunked exchange)
 inline void launch_route_pass(cudaStream_t st, const u64 *ki, const u64 *vi, u64 n, const Pass &p, const unsigned long long *zeroBase,
-                              u32 *tileState, u32 *ticket, u64 *const *routeK, u64 *const *routeV) {
+                              u32 *tileState, u32 *ticket, u64 *const *routeK, u64 *const *routeV, const u64 *routeCap = nullptr, u32 *routeOverflow = nullptr) {
     typedef SweepSmem<256, 16, true> SM;
     static bool attrSet = false;
     if (!attrSet) { cudaFuncSetAttribute(onesweep_kernel<256, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(SM)); attrSet = true; }
     const u64 tiles = (n + SM::TILE_T - 1) / SM::TILE_T;
-    onesweep_kernel<256, 16, true, true><<<(unsigned) tiles, 256, sizeof(SM), st>>>(ki, nullptr, vi, nullptr, n, p, zeroBase, tileState, ticket, routeK, routeV);
+    onesweep_kernel<256, 16, true, true><<<(unsigned) tiles, 256, sizeof(SM), st>>>(ki, nullptr, vi, nullptr, n, p, zeroBase, tileState, ticket, routeK, routeV, routeCap, routeOverflow);
+}
+// after a routing pass over n records: base[d] += records of digit d (the inclusive state of the pass's last tile)
+__global__ void route_advance_kernel(const u32 *__restrict__ tileState, u64 tiles, unsigned long long *__restrict__ base) {
+    const int d = threadIdx.x;
+    if (d < ROUTE_MAX && tiles) base[d] += (unsigned long long) (tileState[(tiles - 1) * RADIX + d] & State<u32>::VAL);
+}
+inline u64 route_tiles(u64 n) { return (n + SweepSmem<256, 16, true>::TILE_T - 1) / SweepSmem<256, 16, true>::TILE_T;
 }
 
 // variant: 0 = 256 threads x 16 keys, 1 = 256 x 8, 2 = 512 x 8, 3 = 384... (tuning knob; default chosen by measurements)

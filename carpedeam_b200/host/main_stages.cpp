@@ -153,6 +153,7 @@ int kmermatcher(int argc, char **argv) {
     p.hash_shift = (uint64_t) a.num("--hash-shift", 67);
     p.include_only_extendable = (int) a.num("--include-only-extendable", 0);
     p.hash_lo = 0; p.hash_hi = 65535;
+    p.split_passes = 0;   // --split-memory-limit 0: as many hash-range passes as the free device memory asks for (usually one)
     if (a.num("-c", 0.0) != 0.0) die("kmermatcher: only -c 0 (the assembler's setting) is supported");
     cdg_hits h;
     ck(ctx, cdg_kmermatch(ctx, &p, &h), "cdg_kmermatch");

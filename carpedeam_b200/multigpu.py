@@ -27,6 +27,10 @@ from . import Alns, CorrParams, Hits, RescoreParams, lib, kmer_params
 SENTINEL = 0xFFFFFFFFFFFFFFFF
 
 
+class CdgErrorLocal(RuntimeError):
+    pass
+
+
 class DevArray:
     """zero-copy view of library-owned device memory for torch (`torch.as_tensor(DevArray(...), device='cuda')`)."""
 
@@ -306,11 +310,17 @@ class ShardedIteration:
         L.cdg_mg_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.cdg_mg_head_area.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        L.cdg_mg_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+        L.cdg_mg_extract_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+        L.cdg_mg_recv_fill.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64]
         L.cdg_mg_finish_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
                                             C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         self.L = L
         self._up = None      # persistent device staging of upload_sharded_packed
         self._blk = None     # ... and of upload_packed_blocks
+        # (records, identity records) the mapped receive areas of the streamed exchange hold: ctx._stream_mapped, shared by every
+        # driver object of the context
+        self.stream_chunks = 4       # pieces of the slice whose routing overlaps the extraction of the next piece (0: counted exchange)
         if exchange == "p2p" and comm.world > 1:
             self._probe_peer_memory()
 
@@ -502,6 +512,7 @@ class ShardedIteration:
         """drop every peer mapping (collective): call before the contexts are destroyed or the receive buffers are reused elsewhere"""
         if self.exchange != "p2p":
             return
+        self.ctx._stream_mapped = None
         for which in range(5):
             for peer in range(self.comm.world):
                 if peer != self.comm.rank:
@@ -523,6 +534,65 @@ class ShardedIteration:
                 hb = C.create_string_buffer(blob[i * self.HANDLE_BYTES:(i + 1) * self.HANDLE_BYTES], self.HANDLE_BYTES)
                 ctx._ck(L.cdg_mg_ipc_open(ctx._h, which, peer, hb), "cdg_mg_ipc_open")
 
+    def _phase1_counted(self, send_counts, id_send, rk, rv, irk, irv):
+        """counted peer-memory exchange: count matrix first, then one partition pass per rank writes its segments into the peers"""
+        ctx, comm, L = self.ctx, self.comm, self.L
+        world, rank = comm.world, comm.rank
+        # every rank learns the whole count matrix; this all-gather is also the barrier that says every peer is done with
+        # the receive buffers of the previous iteration
+        rows = comm.all_gather_rows(send_counts + id_send + self._capacities((0, 1, 2, 3)))
+        dst, totals = segment_offsets([r[:world] for r in rows], rank)
+        id_dst, id_totals = segment_offsets([r[world:2 * world] for r in rows], rank)
+        total, id_total = totals[rank], id_totals[rank]
+        need = lambda t: max((t + 1) * 8, self.MIN_BYTES)
+        if self._release_if_growing((0, 1, 2, 3), [[need(totals[r])] * 2 + [need(id_totals[r])] * 2 for r in range(world)], [r[2 * world:] for r in rows]):
+            self.ctx._stream_mapped = None
+        ctx._ck(L.cdg_mg_recv_records(ctx._h, total, id_total, C.byref(rk), C.byref(rv), C.byref(irk), C.byref(irv)), "cdg_mg_recv_records")
+        self._map_peers((0, 1, 2, 3))
+        ctx._ck(L.cdg_mg_scatter_records(ctx._h, (C.c_uint64 * world)(*dst), (C.c_uint64 * world)(*id_dst)), "cdg_mg_scatter_records")
+        comm.barrier()      # all partitions have landed
+        return total, id_total
+
+    def _phase1_streamed(self, kp, rk, rv, irk, irv, lap):
+        """streamed peer-memory exchange (cdg_mg_extract_stream).  Returns (records sent, records in the receive area) or None when
+        some rank reported a region overflow (every rank takes the same branch: the flags travel with the counts)."""
+        ctx, comm, L = self.ctx, self.comm, self.L
+        world, rank = comm.world, comm.rank
+        cap = C.c_uint64()
+        ctx._ck(L.cdg_mg_plan(ctx._h, C.byref(kp), world, rank, C.byref(cap)), "cdg_mg_plan")
+        cap = cap.value
+        n = ctx.n
+        S, id_cap = world * cap, min(n, 2 * ((n + world - 1) // world) + (1 << 20))
+        # the sizes follow from the resident set alone, so every rank sees the same numbers and takes the same branch
+        if self.ctx._stream_mapped is None or S > self.ctx._stream_mapped[0] or id_cap > self.ctx._stream_mapped[1]:
+            for which in (0, 1, 2, 3):
+                for peer in range(world):
+                    if peer != rank:
+                        ctx._ck(L.cdg_mg_ipc_close(ctx._h, which, peer), "cdg_mg_ipc_close")
+            comm.barrier()
+            ctx._ck(L.cdg_mg_recv_records(ctx._h, S, id_cap, C.byref(rk), C.byref(rv), C.byref(irk), C.byref(irv)), "cdg_mg_recv_records")
+            self._map_peers((0, 1, 2, 3))
+            self.ctx._stream_mapped = (S, id_cap)
+        else:
+            ctx._ck(L.cdg_mg_recv_records(ctx._h, S, id_cap, C.byref(rk), C.byref(rv), C.byref(irk), C.byref(irv)), "cdg_mg_recv_records")
+        sc = (C.c_uint64 * world)(); isc = (C.c_uint64 * world)(); ovf = C.c_int()
+        ctx._ck(L.cdg_mg_extract_stream(ctx._h, C.byref(kp), self.stream_chunks, cap, sc, isc, C.byref(ovf)), "cdg_mg_extract_stream")
+        lap("extract+route (streamed)")
+        rows = comm.all_gather_rows(list(sc) + list(isc) + [ovf.value])      # also: every rank's routing kernels have finished
+        if any(r[2 * world] for r in rows):
+            if rank == 0:
+                import sys
+                print("carpedeam_b200.multigpu: a receive region would overflow (skewed hash ownership), using the counted exchange", file=sys.stderr, flush=True)
+            return None
+        ctx._ck(L.cdg_mg_recv_fill(ctx._h, (C.c_uint64 * world)(*[rows[r][rank] for r in range(world)]), cap), "cdg_mg_recv_fill")
+        id_dst, id_totals = segment_offsets([r[world:2 * world] for r in rows], rank)
+        if id_totals[rank] > id_cap:
+            raise CdgErrorLocal("identity receive area too small")      # 2 n / world + 2^20 records: hash ownership is uniform
+        ctx._ck(L.cdg_mg_recv_records(ctx._h, S, id_totals[rank], C.byref(rk), C.byref(rv), C.byref(irk), C.byref(irv)), "cdg_mg_recv_records")
+        ctx._ck(L.cdg_mg_scatter_records(ctx._h, None, (C.c_uint64 * world)(*id_dst)), "cdg_mg_scatter_records")
+        comm.barrier()      # identity records have landed
+        return sum(sc), S
+
     def run(self, kmer=None, rescore=None, corr=None, fetch_hits=False, fetch_alns=False, out_range=None):
         ctx, comm, L = self.ctx, self.comm, self.L
         world, rank = comm.world, comm.rank
@@ -543,26 +613,27 @@ class ShardedIteration:
         p2p = self.exchange == "p2p"
         sc = (C.c_uint64 * world)(); isc = (C.c_uint64 * world)()
         sk, sv, ik, iv = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-        ctx._ck(L.cdg_mg_extract(ctx._h, C.byref(kp), world, rank, 0 if p2p else 1, sc, C.byref(sk), C.byref(sv), isc, C.byref(ik), C.byref(iv)),
-                "cdg_mg_extract")
-        send_counts = list(sc); id_send = list(isc)
-        nsend, id_nsend = sum(send_counts), sum(id_send)
-        lap("extract+partition" if not p2p else "extract+count")
+        streamed = p2p and self.stream_chunks > 0 and world > 1
         rk, rv, irk, irv = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-        if p2p:
-            # every rank learns the whole count matrix; this all-gather is also the barrier that says every peer is done with
-            # the receive buffers of the previous iteration
-            rows = comm.all_gather_rows(send_counts + id_send + self._capacities((0, 1, 2, 3)))
-            dst, totals = segment_offsets([r[:world] for r in rows], rank)
-            id_dst, id_totals = segment_offsets([r[world:2 * world] for r in rows], rank)
-            total, id_total = totals[rank], id_totals[rank]
-            need = lambda t: max((t + 1) * 8, self.MIN_BYTES)
-            self._release_if_growing((0, 1, 2, 3), [[need(totals[r])] * 2 + [need(id_totals[r])] * 2 for r in range(world)],
-                                     [r[2 * world:] for r in rows])
-            ctx._ck(L.cdg_mg_recv_records(ctx._h, total, id_total, C.byref(rk), C.byref(rv), C.byref(irk), C.byref(irv)), "cdg_mg_recv_records")
-            self._map_peers((0, 1, 2, 3))
-            ctx._ck(L.cdg_mg_scatter_records(ctx._h, (C.c_uint64 * world)(*dst), (C.c_uint64 * world)(*id_dst)), "cdg_mg_scatter_records")
-            comm.barrier()      # all partitions have landed
+        send_counts, id_send, nsend, id_nsend = [], [], 0, 0
+        if not streamed:
+            ctx._ck(L.cdg_mg_extract(ctx._h, C.byref(kp), world, rank, 0 if p2p else 1, sc, C.byref(sk), C.byref(sv), isc, C.byref(ik), C.byref(iv)),
+                    "cdg_mg_extract")
+            send_counts = list(sc); id_send = list(isc)
+            nsend, id_nsend = sum(send_counts), sum(id_send)
+            lap("extract+partition" if not p2p else "extract+count")
+        if p2p and self.stream_chunks > 0 and world > 1:
+            # streamed exchange: fixed regions per source in every owner's receive area, routing overlaps the extraction
+            done = self._phase1_streamed(kp, rk, rv, irk, irv, lap)
+            if done is None:      # a region would have overflowed somewhere (degenerate hash ownership): counted exchange instead
+                ctx._ck(L.cdg_mg_extract(ctx._h, C.byref(kp), world, rank, 0, sc, C.byref(sk), C.byref(sv), isc, C.byref(ik), C.byref(iv)), "cdg_mg_extract")
+                send_counts = list(sc); id_send = list(isc)
+                nsend, id_nsend = sum(send_counts), sum(id_send)
+                total, id_total = self._phase1_counted(send_counts, id_send, rk, rv, irk, irv)
+            else:
+                nsend, total = done
+        elif p2p:
+            total, id_total = self._phase1_counted(send_counts, id_send, rk, rv, irk, irv)
         else:
             both = comm.exchange_counts(send_counts + id_send)
             recv_counts, id_recv = both[0::2], both[1::2]

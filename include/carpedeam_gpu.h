@@ -80,8 +80,11 @@ typedef struct {
     float kmers_per_seq_scale;       /* --kmer-per-seq-scale 0.2 */
     uint64_t hash_shift;             /* --hash-shift 67 (XXH64 seed) */
     int32_t include_only_extendable; /* --include-only-extendable */
-    uint32_t hash_lo, hash_hi;       /* 16-bit hash range owned by this call (0..65535 = unsplit;
-                                        kmermatcher.cpp:742-784 splits, multi-GPU owner ranges) */
+    uint32_t hash_lo, hash_hi;       /* 16-bit hash range owned by this call (0..65535 = all; a sub-range yields that range's
+                                        partial result like one split of the reference, kmermatcher.cpp:665-675) */
+    int32_t split_passes;            /* hash-range passes INSIDE the call with unsplit results (--split-memory-limit): 0 = as many as
+                                        the free device memory asks for (kmermatcher.cpp:615-627), 1 = never split, M > 1 = M ranges
+                                        cut from the 65536-bin hash histogram (setupKmerSplits, :742-784) */
 } cdg_kmer_params;
 
 /* prefilter hits in pref-DB order: for rep index ascending, target index ascending
@@ -255,6 +258,17 @@ int cdg_export_patches(cdg_ctx *ctx, cdg_patches *out);
  * are one kernel. */
 int cdg_mg_extract(cdg_ctx *ctx, const cdg_kmer_params *p, int world, int rank, int partition, uint64_t *send_counts, void **send_keys,
                    void **send_vals, uint64_t *id_send_counts, void **id_send_keys, void **id_send_vals);
+/* Streamed record exchange (peer-memory mode): extraction in `chunks` pieces, the routing pass of piece c writes into the peers'
+ * receive areas while piece c+1 is extracted.  Every owner's area = world regions of cap_per_source records (one per source, rank
+ * order); cdg_mg_plan returns the region size every rank derives from the same resident set.  Order of calls per iteration:
+ *   cdg_mg_plan -> cdg_mg_recv_records(world * cap, ...) + handle exchange when the areas had to grow -> cdg_mg_extract_stream
+ *   -> the ranks all-gather send_counts / id_send_counts / overflow -> cdg_mg_recv_fill(counts of every source for this rank)
+ *   -> cdg_mg_scatter_records(NULL, id offsets) -> barrier -> cdg_mg_sort ...  (overflow on any rank: redo the phase with the
+ *   counted exchange, cdg_mg_extract + cdg_mg_scatter_records) */
+int cdg_mg_plan(cdg_ctx *ctx, const cdg_kmer_params *p, int world, int rank, uint64_t *cap_per_source);
+int cdg_mg_extract_stream(cdg_ctx *ctx, const cdg_kmer_params *p, int chunks, uint64_t cap_per_source, uint64_t *send_counts,
+                          uint64_t *id_send_counts, int *overflow);
+int cdg_mg_recv_fill(cdg_ctx *ctx, const uint64_t *counts_from_source, uint64_t cap_per_source);
 int cdg_mg_recv_records(cdg_ctx *ctx, uint64_t total, uint64_t id_total, void **recv_keys, void **recv_vals, void **id_recv_keys,
                         void **id_recv_vals);
 /* receive buffer `which`: 0 k-mer keys, 1 k-mer values, 2 identity keys, 3 identity values, 4 grouped records.  handle = 72 bytes. */
@@ -289,6 +303,7 @@ typedef struct {
     float ms_extract, ms_sort1, ms_group, ms_sort2, ms_reduce, ms_rescore, ms_correct; /* last run, CUDA events */
     /* dominant kernel: the LSD passes of sort 1 alone (events around every onesweep launch), records per launch */
     float ms_sort1_passes; uint32_t n_sort1_pass_launches; uint64_t sort1_records;
+    uint32_t split_passes;              /* hash-range passes of the last cdg_kmermatch (1 = unsplit) */
 } cdg_stats;
 int cdg_get_stats(cdg_ctx *ctx, cdg_stats *out);
 

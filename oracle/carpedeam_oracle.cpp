@@ -158,12 +158,20 @@ static void extract_seq(const char *s, int L, u32 id, int k, int kmersPerSeq, fl
 
 // a5..a8.  ids are sequence indices; the caller guarantees keys ascend with the index, so
 // ordering by index == ordering by dbKey (KmerPosition.id is the dbKey, kmermatcher.cpp:143).
+// hashLo/hashHi: one split of the reference's split loop (kmermatcher.cpp:665-675): only records whose 16-bit hash lies in the range
+// (:244, :315), grouped and written like a whole run (the first-run quirk applies to the split's first run)
+extern "C" long orc_kmermatch_range(const char *blob, const u64 *off, const u32 *len, size_t n, int k, int kmersPerSeq,
+                                    float scale, u64 seed, int onlyExtendable, int keepRecords, unsigned hashLo, unsigned hashHi);
 extern "C" long orc_kmermatch(const char *blob, const u64 *off, const u32 *len, size_t n, int k, int kmersPerSeq,
                               float scale, u64 seed, int onlyExtendable, int keepRecords) {
+    return orc_kmermatch_range(blob, off, len, n, k, kmersPerSeq, scale, seed, onlyExtendable, keepRecords, 0, 65535);
+}
+extern "C" long orc_kmermatch_range(const char *blob, const u64 *off, const u32 *len, size_t n, int k, int kmersPerSeq,
+                                    float scale, u64 seed, int onlyExtendable, int keepRecords, unsigned hashLo, unsigned hashHi) {
     KmOut &o = g_km;
     o = KmOut();
     std::vector<KmerRec> recs;
-    for (size_t i = 0; i < n; i++) extract_seq(blob + off[i], (int) len[i], (u32) i, k, kmersPerSeq, scale, seed, 0, 65535, recs);
+    for (size_t i = 0; i < n; i++) extract_seq(blob + off[i], (int) len[i], (u32) i, k, kmersPerSeq, scale, seed, hashLo, hashHi, recs);
     o.nR1 = recs.size();
     // a5 sort 1: compareRepSequenceAndIdAndPosReverse (kmermatcher.h:76-96); bit 63 breaks full ties here
     std::sort(recs.begin(), recs.end(), [](const KmerRec &a, const KmerRec &b) {

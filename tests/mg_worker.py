@@ -27,8 +27,12 @@ def main():
              ("golden contigs k=22 ext", SeqSet.from_golden("assembly_contigs_8_noneCycle"), cd.kmer_params(k=22, include_only_extendable=1)),
              ("synthetic 60k", SeqSet(synth_reads(60000, 300000, 21, n_frac=0.001)), cd.kmer_params())]
     ok = True
-    modes = os.environ.get("CDG_MG_EXCHANGE", "p2p,nccl").split(",")
-    sharded = {m: ShardedIteration(ctx, comm, exchange=m) for m in modes}
+    # p2p: streamed peer-memory exchange (routing overlaps the extraction), p2p-counted: count matrix first, nccl: NCCL all-to-all
+    modes = os.environ.get("CDG_MG_EXCHANGE", "p2p,p2p-counted,nccl").split(",")
+    sharded = {m: ShardedIteration(ctx, comm, exchange=m.split("-")[0]) for m in modes}
+    for m in modes:
+        if m == "p2p-counted":
+            sharded[m].stream_chunks = 0
     for name, s, kp in [(n + " [" + m + "]", s_, k_) for (n, s_, k_) in cases for m in modes]:
         ctx.upload(s.blob, s.off, s.len, s.ext)
         out_range = np.zeros(len(s.blob), np.uint8)

@@ -102,9 +102,13 @@ class Oracle:
         L.orc_load_damage.argtypes = [C.c_char_p, C.c_char_p]
         self.L = L
 
-    def kmermatch(self, s, k=20, kmers_per_seq=200, scale=0.2, seed=67, only_ext=0, keep_records=False):
-        H = self.L.orc_kmermatch(s.blob.ctypes.data, s.off.ctypes.data, s.len.ctypes.data, s.n, k, kmers_per_seq, scale,
-                                 seed, only_ext, 1 if keep_records else 0)
+    def kmermatch(self, s, k=20, kmers_per_seq=200, scale=0.2, seed=67, only_ext=0, keep_records=False, hash_lo=0, hash_hi=65535):
+        """hash_lo / hash_hi: one split of the reference's split loop (kmermatcher.cpp:665-675)"""
+        self.L.orc_kmermatch_range.restype = C.c_long
+        self.L.orc_kmermatch_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_int, C.c_int,
+                                               C.c_uint, C.c_uint]
+        H = self.L.orc_kmermatch_range(s.blob.ctypes.data, s.off.ctypes.data, s.len.ctypes.data, s.n, k, kmers_per_seq, scale,
+                                       seed, only_ext, 1 if keep_records else 0, hash_lo, hash_hi)
         rep = np.zeros(H, np.uint32); tgt = np.zeros(H, np.uint32); sc = np.zeros(H, np.int32); dg = np.zeros(H, np.int16)
         self.L.orc_km_hits(rep.ctypes.data, tgt.ctypes.data, sc.ctypes.data, dg.ctypes.data)
         r1 = C.c_uint64(); r2 = C.c_uint64()

@@ -817,3 +817,83 @@ def test_config4_shaped_set_needs_more_than_64_grouped_record_bits(ctx, oracle):
     r = oracle.rescore(s, q[sel], a["tgt"][sel], got["score"], (got["diag"].astype(np.int64) & 0xFFFF).astype(np.uint16))
     for f in ("keep", "score", "qs", "qe", "ds", "de"):
         assert np.array_equal(a[f][sel], r[f]), f
+
+
+@pytest.mark.parametrize("seqdb,pref,aln,corr,k,only_ext", CASES)
+@pytest.mark.parametrize("passes", [3, 7])
+def test_hash_range_passes_inside_the_call_equal_the_unsplit_result(ctx, seqdb, pref, aln, corr, k, only_ext, passes):
+    """cdg_kmermatch with split_passes = M cuts the 16-bit hash space into M ranges from the 65536-bin histogram
+    (setupKmerSplits, kmermatcher.cpp:742-784), extracts / sorts / groups range by range on ONE resident copy of the set and reduces
+    once: the pref DB must be the one the reference wrote without splitting (its own forced 3-way split gives the same DBs on
+    config 1)."""
+    import carpedeam_b200 as cd
+    s = SeqSet.from_golden(seqdb)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    got = ctx.kmermatch(cd.kmer_params(k=k, include_only_extendable=only_ext, split_passes=passes))
+    assert ctx.stats()["split_passes"] == passes
+    keys, payloads, _ = load_golden(pref)
+    mine = format_pref(s, got)
+    assert all(mine[kk] == p for kk, p in zip(keys, payloads))
+    whole = ctx.kmermatch(cd.kmer_params(k=k, include_only_extendable=only_ext, split_passes=1))
+    _hits_equal(got, whole)
+
+
+def test_hash_range_passes_on_repeats_long_contigs_and_wide_records(ctx, oracle, monkeypatch):
+    """the split loop on the awkward inputs: reads with repeated k-mers (exact replay path), contigs with an active hash threshold,
+    sequences shorter than k, N; once more with the two-word grouped records"""
+    import carpedeam_b200 as cd
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    contig = acgt[rng.integers(0, 4, 30000)].tobytes()
+    seqs = synth_reads(6000, 30000, 78, n_frac=0.002) + [contig, contig[1000:9000], b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT", b"A" * 60, b"ACGT", b"N" * 50]
+    seqs += [contig[i:i + 90] for i in range(0, 28000, 37)] + [(b"ACGGT" * 20)[:77], (b"ACGGT" * 20)[:77]]
+    s = SeqSet(seqs)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    want = oracle.kmermatch(s)
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("CDG_FORCE_WIDE_KEY2", env)
+        got = ctx.kmermatch(cd.kmer_params(split_passes=4))
+        assert ctx.stats()["split_passes"] == 4
+        _hits_equal(got, want)
+
+
+@pytest.mark.parametrize("seqdb,k,only_ext", [("nucl_reads", 20, 0), ("assembly_contigs_8_noneCycle", 22, 1)])
+def test_sub_range_call_is_one_split_of_the_reference(ctx, oracle, seqdb, k, only_ext):
+    """hash_lo / hash_hi: the partial result of one split (kmermatcher.cpp:665-675; records filtered at :244 and :315)"""
+    import carpedeam_b200 as cd
+    s = SeqSet.from_golden(seqdb)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    union = 0
+    for lo, hi in ((0, 21845), (21846, 43690), (43691, 65535)):
+        got = ctx.kmermatch(cd.kmer_params(k=k, include_only_extendable=only_ext, hash_lo=lo, hash_hi=hi))
+        want = oracle.kmermatch(s, k=k, only_ext=only_ext, hash_lo=lo, hash_hi=hi)
+        _hits_equal(got, want)
+        union += len(got["rep"])
+    assert union >= len(oracle.kmermatch(s, k=k, only_ext=only_ext)["rep"])      # a pair's k-mers are spread over the splits
+
+
+def test_memory_driven_number_of_hash_range_passes(ctx):
+    """split_passes = 0: the number of passes follows from the free device memory (kmermatcher.cpp:615-627).  With most of the HBM
+    taken by someone else the call must split by itself and still return the unsplit result."""
+    import torch
+    import carpedeam_b200 as cd
+    from bench import synth_reads_fast
+    s = synth_reads_fast(2_000_000, 10_000_000, 5)
+    ctx.upload(s["blob"], s["off"], s["len"], None)
+    whole = ctx.kmermatch(cd.kmer_params(split_passes=1))
+    assert ctx.stats()["split_passes"] == 1
+    c2 = cd.Context(0)        # a fresh context: nothing reserved yet, so the free memory decides
+    hog = None
+    try:
+        c2.upload(s["blob"], s["off"], s["len"], None)
+        torch.cuda.synchronize()
+        free, _ = torch.cuda.mem_get_info()
+        hog = torch.empty(max(0, free - (2600 << 20)), dtype=torch.uint8, device="cuda")      # the unsplit arrays need ~3.3 GB
+        got = c2.kmermatch(cd.kmer_params())
+        assert c2.stats()["split_passes"] > 1
+    finally:
+        del hog
+        c2.close()
+        torch.cuda.empty_cache()
+    _hits_equal(got, whole)
