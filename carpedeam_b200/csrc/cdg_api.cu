@@ -599,6 +599,7 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
     u64 nLong64 = 0, longScr = 0;
     if (!is_short_seq(ctx->maxLen, p->k, p->kmers_per_seq, p->kmers_per_seq_scale)) {   // (monotonic in the length: the longest sequence decides)
         CK(ctx->dLongList.reserve(n * 4)); CK(ctx->dScratchOff.reserve(n * 8));
+        CK(cudaMemsetAsync(sc + SC_NLONG, 0, 8, ctx->st)); CK(cudaMemsetAsync(sc + SC_LONGSCR, 0, 8, ctx->st));   // (km_extract runs once per chunk / hash range)
         long_list_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dLen.as<u32>(), n, p->k, p->kmers_per_seq, p->kmers_per_seq_scale,
                                                                             ctx->dLongList.as<u32>(), ctx->dScratchOff.as<u64>(), (u32 *) (sc + SC_NLONG),
                                                                             sc + SC_LONGSCR);
@@ -992,7 +993,18 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     if ((rc = read_scalar(ctx, SC_EXTRA, &extra))) return rc;
     const bool mainNonEmpty = minKey != CDG_SENTINEL;
     if ((rc = km_group(ctx, p, K, Rtot, mainNonEmpty, !mainNonEmpty, &R2))) return rc;
-    ctx->nRecords = emitted + n;   // every sequence owns one identity record when the hash range is full
+    u64 ownedIds = n;   // every sequence owns one identity record when the hash range is full
+    if (!(p->hash_lo == 0 && p->hash_hi >= 65535) && n) {   // a sub-range call: the identity records whose hash lies in the range (:244)
+        const u64 tiles = cdgscan::tiles_for(n);
+        CK(ctx->dTileSums.reserve((tiles + 1) * 8));
+        cdgkmer::NotSentinelF f{ctx->sortedIdK};
+        cdgscan::tile_sum_kernel<<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, n, ctx->dTileSums.as<unsigned long long>());
+        cdgscan::tile_scan_kernel<<<1, 1024, 0, ctx->st>>>(ctx->dTileSums.as<unsigned long long>(), tiles, sc + SC_SCAN);
+        ctx->launches += 2;
+        if ((rc = read_scalar(ctx, SC_SCAN, &ownedIds))) return rc;
+        ownedIds += (u32) extra;   // identity hashes inside the k-mer key range live in the main array
+    }
+    ctx->nRecords = emitted + ownedIds;
     ctx->nGrouped = R2;
     if ((rc = km_sort2(ctx, K, R2))) return rc;
     return km_reduce(ctx, K, R2, R2);
