@@ -103,7 +103,10 @@ struct cdg_ctx {
     HostBuf hCmpCount, hCmpTarget, hCmpFields, hPatches;
     u64 nCompact = 0, nChangedLast = 0; bool correctedValid = false; double dbResUsed = 0; bool monotoneOffsets = true; bool packedUpload = false;
     // packed uploads rebuild the DB bytes only when something reads them (a sequence with N, or a byte-consuming entry point)
-    bool planReady = false; std::vector<cudaEvent_t> chunkDone; u32 splitPasses = 1; DevBuf dHashHist, dChunkK, dChunkV, dRouteBase;
+    bool planReady = false; std::vector<cudaEvent_t> chunkDone;
+    // km_prepare's result ((length desc, id asc) order, slot prefix, slice bounds) is a property of the resident set and of
+    // (k, kmers per sequence, world, rank): kept until the next upload
+    u64 uploadGen = 0, prepGen = ~0ull; int prepK = 0, prepKps = 0; float prepScale = 0.f; u32 prepWorld = 0, prepRank = 0; KmPlanFwd prepPlan; u32 splitPasses = 1; DevBuf dHashHist, dChunkK, dChunkV, dRouteBase;
     DevBuf dSetFacts, dSlowList, dPrep, dAlnLen, dMism, dKey2HiA, dKey2HiB; u64 *sortedKey2Hi = nullptr; bool bytesValid = true; bool patchesDirect = false;
     u64 nLines = 0, nKept = 0; bool linesValid = false, alnsValid = false, alnsFromText = false;
     // correction
@@ -360,7 +363,7 @@ static int upload_impl(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, c
     CK(cudaSetDevice(ctx->device));
     if (!ctx->pending.empty()) { CK(cudaStreamSynchronize(ctx->copySt)); ctx->pending.clear(); }   // an upload nobody consumed
     ctx->hitsValid = ctx->linesValid = ctx->alnsValid = false; ctx->packedUpload = false; ctx->correctedValid = false; ctx->bytesValid = true;
-    ctx->n = n; ctx->dataBytes = data_bytes; ctx->qLo = 0; ctx->nQ = n;
+    ctx->n = n; ctx->dataBytes = data_bytes; ctx->qLo = 0; ctx->nQ = n; ctx->uploadGen++;
     CK(ctx->dData.reserve(data_bytes + 64));
     CK(ctx->dOff.reserve(n * 8)); CK(ctx->dLen.reserve(n * 4)); CK(ctx->dExt.reserve(n)); CK(ctx->dFlags.reserve(n));
     CK(ctx->dWordOff.reserve((n + 1) * 8)); CK(ctx->dLikOff.reserve((n + 1) * 8));
@@ -470,7 +473,7 @@ extern "C" int cdg_upload_packed(cdg_ctx *ctx, const uint64_t *words, const uint
     if (!ctx->pending.empty()) { CK(cudaStreamSynchronize(ctx->copySt)); ctx->pending.clear(); }
     ctx->hitsValid = ctx->linesValid = ctx->alnsValid = false; ctx->packedUpload = true; ctx->monotoneOffsets = true; ctx->correctedValid = false; ctx->bytesValid = false;
     CK(ctx->dSetFacts.reserve(64)); CK(cudaMemsetAsync(ctx->dSetFacts.p, 0, 64, ctx->st));
-    ctx->n = n; ctx->qLo = 0; ctx->nQ = n;
+    ctx->n = n; ctx->qLo = 0; ctx->nQ = n; ctx->uploadGen++;
     CK(ctx->dOff.reserve(n * 8)); CK(ctx->dLen.reserve(n * 4)); CK(ctx->dExt.reserve(n)); CK(ctx->dFlags.reserve(n));
     CK(ctx->dWordOff.reserve((n + 1) * 8)); CK(ctx->dLikOff.reserve((n + 1) * 8));
     CK(ctx->dWords.reserve((n_words + 2) * 8)); CK(ctx->dXmask.reserve((n_words + 2) * 4));
@@ -537,7 +540,22 @@ static int km_bits(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlan &K) {
 }
 
 // (length desc, id asc) order, slot prefix in that order, rankOf, slice of this rank
+static int km_prepare_compute(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlanFwd &K);
 static int km_prepare(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlan &K) {
+    const u64 n = ctx->n;
+    if (ctx->prepGen == ctx->uploadGen && ctx->prepK == p->k && ctx->prepKps == p->kmers_per_seq && ctx->prepScale == p->kmers_per_seq_scale &&
+        ctx->prepWorld == K.world && ctx->prepRank == K.rank) {   // same resident set, same parameters: nothing to recompute
+        const bool wide = K.wide; const int idBits = K.idBits, diagBits = K.diagBits;
+        K = ctx->prepPlan; K.wide = wide; K.idBits = idBits; K.diagBits = diagBits;
+        return 0;
+    }
+    int rcPrep = km_prepare_compute(ctx, p, K);
+    if (rcPrep) return rcPrep;
+    ctx->prepGen = ctx->uploadGen; ctx->prepK = p->k; ctx->prepKps = p->kmers_per_seq; ctx->prepScale = p->kmers_per_seq_scale; ctx->prepWorld = K.world; ctx->prepRank = K.rank;
+    ctx->prepPlan = K;
+    return 0;
+}
+static int km_prepare_compute(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlan &K) {
     const u64 n = ctx->n;
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
     CK(ctx->dSlotOff.reserve((n + 1) * 8)); CK(ctx->dSlotRank.reserve((n + 1) * 8)); CK(ctx->dRankOf.reserve(n * 4));

@@ -443,10 +443,12 @@ __global__ void __launch_bounds__(EX_WARPS * 32, GROUP == 8 ? 4 : 5) extract_gro
         // windows
         const u64 slot0 = slotAbs - P.slotBase;
         u32 written = 0, flagged = 0;
-        u64 touched = 0;      // filter words this lane set a bit in: 7 bits per iteration, bit 7 of each byte = valid
-        const u32 maxW = __reduce_max_sync(0xffffffffu, W);   // over the groups of the warp: every lane runs the same number of iterations
-        const int nIt = (int) ((maxW + GROUP - 1) / GROUP);   // <= ITERS
-        for (int it = 0; it < nIt; it++) {
+        u32 hh[ITERS];   // the window's filter word, 0xFFFFFFFF = no valid window in this iteration
+        const u32 maxW = __reduce_max_sync(0xffffffffu, W);   // over the groups of the warp: every lane skips the same iterations
+#pragma unroll
+        for (int it = 0; it < ITERS; it++) {   // unrolled: the loads and hashes of several iterations overlap
+            hh[it] = 0xFFFFFFFFu;
+            if ((u32) (it * GROUP) >= maxW) continue;     // warp-uniform
             const u32 p = gl + GROUP * it;
             WinRec r; bool ok = false;
             if (p < W) ok = make_window<SCORE>(w, xm, p, L, P, r);
@@ -456,9 +458,8 @@ __global__ void __launch_bounds__(EX_WARPS * 32, GROUP == 8 ? 4 : 5) extract_gro
                 const u64 canon = r.kmer & ~CDG_B63;
                 const u32 mix = ((u32) canon ^ (u32) (canon >> 19)) * 0x9E3779B1u;
                 const unsigned long long bits = (1ull << ((mix >> 19) & 63u)) | (1ull << ((mix >> 13) & 63u));
-                const u32 word = mix >> 25;
-                touched |= (u64) (0x80u | word) << (8 * it);
-                const unsigned long long old = atomicOr(&bm[word], bits);
+                hh[it] = mix >> 25;
+                const unsigned long long old = atomicOr(&bm[hh[it]], bits);
                 if ((old & bits) == bits) flagged = 1;
             }
             const u32 b = __ballot_sync(0xffffffffu, own) & gmask;
@@ -471,7 +472,8 @@ __global__ void __launch_bounds__(EX_WARPS * 32, GROUP == 8 ? 4 : 5) extract_gro
         }
         __syncwarp();
         // clear the touched filter words (cheaper than wiping 1 KB per sequence)
-        for (u64 t = touched; t; t >>= 8) if (t & 0x80u) bm[t & 0x7Fu] = 0;
+#pragma unroll
+        for (int it = 0; it < ITERS; it++) if (hh[it] != 0xFFFFFFFFu) bm[hh[it]] = 0;
         const u32 flaggedLanes = __ballot_sync(0xffffffffu, flagged) & gmask;   // (taken by every lane: no short-circuit in front of a warp collective)
         const bool slow = tooLong || flaggedLanes != 0;
         if (active) {

@@ -614,27 +614,42 @@ __global__ void __launch_bounds__(BLOCK) tile_sum_kernel(F f, u64 n, unsigned lo
     block_excl_scan(s, &tot, shWarp);
     if (threadIdx.x == 0) tileSums[blockIdx.x] = tot;
 }
-// phase 2: single-block exclusive scan of the tile sums (sequential over chunks of BLOCK)
+// phase 2: single-block exclusive scan of the tile sums: 4096 sums per round staged through shared memory (coalesced global
+// accesses), 4 consecutive sums per thread, warp-shuffle scans
 __global__ void __launch_bounds__(1024) tile_scan_kernel(unsigned long long *__restrict__ tileSums, u64 nTiles, unsigned long long *__restrict__ total) {
-    __shared__ unsigned long long sh[1024];
+    constexpr int PER = 4;
+    __shared__ unsigned long long stage[1024 * PER];
+    __shared__ unsigned long long shWarp[32];
     __shared__ unsigned long long carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (u64 base = 0; base < nTiles; base += 1024) {
-        u64 idx = base + threadIdx.x;
-        unsigned long long v = idx < nTiles ? tileSums[idx] : 0;
-        sh[threadIdx.x] = v;
+    for (u64 base = 0; base < nTiles; base += 1024ull * PER) {
+#pragma unroll
+        for (int j = 0; j < PER; j++) { const u64 i = base + (u64) j * 1024 + threadIdx.x; stage[j * 1024 + threadIdx.x] = i < nTiles ? tileSums[i] : 0ull; }
         __syncthreads();
-        for (int off = 1; off < 1024; off <<= 1) {
-            unsigned long long t = threadIdx.x >= (unsigned) off ? sh[threadIdx.x - off] : 0;
-            __syncthreads();
-            sh[threadIdx.x] += t;
-            __syncthreads();
+        unsigned long long v[PER], sum = 0;
+#pragma unroll
+        for (int j = 0; j < PER; j++) { v[j] = stage[threadIdx.x * PER + j]; sum += v[j]; }
+        unsigned long long incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+        if (lane == 31) shWarp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = shWarp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned long long x = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += x; }
+            shWarp[lane] = wi - w;   // exclusive over the warps
         }
-        unsigned long long c = carry;
-        if (idx < nTiles) tileSums[idx] = c + sh[threadIdx.x] - v;
         __syncthreads();
-        if (threadIdx.x == 1023) carry = c + sh[1023];
+        unsigned long long run = carry + shWarp[warp] + incl - sum;
+#pragma unroll
+        for (int j = 0; j < PER; j++) { stage[threadIdx.x * PER + j] = run; run += v[j]; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = run;
+#pragma unroll
+        for (int j = 0; j < PER; j++) { const u64 i = base + (u64) j * 1024 + threadIdx.x; if (i < nTiles) tileSums[i] = stage[j * 1024 + threadIdx.x]; }
         __syncthreads();
     }
     if (threadIdx.x == 0 && total) *total = carry;

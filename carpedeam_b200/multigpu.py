@@ -320,7 +320,7 @@ class ShardedIteration:
         self._blk = None     # ... and of upload_packed_blocks
         # (records, identity records) the mapped receive areas of the streamed exchange hold: ctx._stream_mapped, shared by every
         # driver object of the context
-        self.stream_chunks = 4       # pieces of the slice whose routing overlaps the extraction of the next piece (0: counted exchange)
+        self.stream_chunks = 8       # pieces of the slice whose routing overlaps the extraction of the next piece (0: counted exchange)
         if exchange == "p2p" and comm.world > 1:
             self._probe_peer_memory()
 
