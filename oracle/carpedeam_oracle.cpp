@@ -616,3 +616,138 @@ extern "C" void orc_pair_loglik_consensus(const char *consensus, unsigned qLen, 
     }
     finish_pair(likMod, maxAln, counted, randAlnPenal, excessPenal, sLen, sRatio);
 }
+
+// ---- scoring front half of ancient_read_assemble ------------------------------------------------------------
+// Per query, over the alignment lines of its aln DB entry (Matcher::readAlignmentResults: alnLength = max(|qE-qS|,|dbE-dbS|)+1):
+//   orientation                       src/assembler/ancientReadsResults.cpp:200-236
+//   identity / RY identity recompute  :247-293   (target index compared with the query KEY, as the reference does)
+//   extension candidates (notContig)  :294-315
+//   consensusCaller                   src/assembler/nuclassembleUtil.cpp:570-702 (+ calculateConsensus :533-568)
+//   updateSeqIdConsensusReads         :377-470
+//   final filter + r_s_pair           ancientReadsResults.cpp:330-365, :48-70 -> calcLikelihoodConsensus
+// flags out: bit 0 candidate, bit 1 isRevToAlignment, bit 2 scored.  Coordinates out: the oriented frame.
+static void call_consensus(std::string &consensus, const std::vector<std::vector<unsigned>> &cov, unsigned minCov) {   // :533-568
+    for (size_t i = 0; i < cov.size(); i++) {
+        unsigned total = cov[i][0] + cov[i][1] + cov[i][2] + cov[i][3];
+        if (total >= minCov) {
+            unsigned mx = 0; char nuc = 'N'; int nMax = 0;
+            for (int j = 0; j < 4; j++) {
+                if (cov[i][j] > mx) { mx = cov[i][j]; nuc = "ACGT"[j]; nMax = 1; }
+                else if (cov[i][j] == mx && mx > 0) nMax++;
+            }
+            if (nMax > 1) nuc = 'N';
+            consensus[i] = nuc;
+        }
+    }
+}
+extern "C" void orc_extension(const char *blob, const u64 *off, const u32 *len, const uint8_t *ext, const u32 *keys, size_t n, const u64 *lineOff,
+                              const u32 *tgt, const int32_t *qS, const int32_t *qE, const int32_t *dS, const int32_t *dE, const float *seqIdIn,
+                              float seqIdThr, float rySeqIdThr, int unsafe, unsigned minCovSafe, double seqErrRate, float randAlnPenal, float excessPenal,
+                              uint8_t *flags, int32_t *oqS, int32_t *oqE, int32_t *odS, int32_t *odE, float *seqIdOut, float *ryOut, double *sLenOut,
+                              double *sRatioOut, u32 *maxLeftOut, u32 *maxRightOut, char *consOut /*3 * sum(len), query q at 3 * (sum of len before q)*/) {
+    u64 consOff = 0;
+    for (size_t q = 0; q < n; q++) {
+        const unsigned qLen = len[q];
+        const char *query = blob + off[q];
+        const u64 l0 = lineOff[q], l1 = lineOff[q + 1];
+        struct Aln { u32 t; int qs, qe, ds, de; unsigned dbLen, alnLen; float seqId, ry; bool rev; };
+        std::vector<Aln> a(l1 - l0);
+        for (u64 l = l0; l < l1; l++) {
+            Aln &x = a[l - l0];
+            x.t = tgt[l]; x.qs = qS[l]; x.qe = qE[l]; x.ds = dS[l]; x.de = dE[l]; x.dbLen = len[x.t];
+            x.alnLen = (unsigned) (std::max(std::abs(x.qe - x.qs), std::abs(x.de - x.ds)) + 1);
+            x.seqId = seqIdIn[l]; x.ry = 0.f; x.rev = false;
+        }
+        auto ends = [&](const Aln &x, bool &right, bool &left) {
+            right = (unsigned) x.ds == 0 && (unsigned) x.qe == qLen - 1;
+            left = (unsigned) x.qs == 0 && (unsigned) x.de == x.dbLen - 1;
+        };
+        for (Aln &x : a) {   // orientation
+            bool r, l; ends(x, r, l);
+            if (!r && !l) continue;
+            if (x.qs > x.qe) { std::swap(x.qs, x.qe); int d0 = x.ds; x.ds = (int) x.dbLen - x.de - 1; x.de = (int) x.dbLen - d0 - 1; x.rev = true; }
+            else x.rev = false;
+        }
+        std::string tSeq;
+        for (Aln &x : a) {   // identities against the query
+            bool r, l; ends(x, r, l);
+            if (!r && !l) continue;
+            if (x.t == keys[q]) continue;   // (sic) target INDEX against query KEY
+            oriented_target(blob + off[x.t], x.dbLen, x.rev, tSeq);
+            int idCnt = 0, idRy = 0;
+            for (int i = x.qs; i <= x.qe; i++) {
+                char qc = query[i], tc = tSeq[x.ds + (i - x.qs)];
+                idCnt += qc == tc; idRy += ry_map(qc) == ry_map(tc);
+            }
+            x.seqId = (float) idCnt / x.alnLen; x.ry = (float) idRy / x.alnLen;
+        }
+        std::vector<size_t> cand;
+        for (size_t i = 0; i < a.size(); i++) {   // candidates
+            bool r, l; ends(a[i], r, l);
+            if (!r && !l) continue;
+            bool noOffset = (a[i].dbLen - a[i].alnLen) == 0;
+            if (!ext[a[i].t] && a[i].alnLen >= 30 && a[i].seqId >= seqIdThr && !noOffset) cand.push_back(i);
+        }
+        std::string consensus(3 * (size_t) qLen, 'N');
+        if (!unsafe) { for (unsigned p = 0; p < qLen; p++) consensus[qLen + p] = query[p]; }
+        else {
+            std::vector<std::vector<unsigned>> cov(3 * (size_t) qLen, std::vector<unsigned>(4, 0));
+            for (size_t ci : cand) {
+                const Aln &x = a[ci];
+                const bool rightStart = x.ds == 0 && x.de != (int) x.dbLen - 1;
+                const bool leftStart = x.qs == 0 && x.qe != (int) qLen - 1;
+                const bool notId = keys[x.t] != keys[q];
+                if (!((rightStart || leftStart) && notId)) continue;
+                oriented_target(blob + off[x.t], x.dbLen, x.rev, tSeq);
+                if ((unsigned) x.ds == 0 && (unsigned) x.qe == qLen - 1) { for (unsigned p = 0; p < x.dbLen; p++) cov[qLen + x.qs + p][nuc_map(tSeq[p])]++; }
+                else if ((unsigned) x.qs == 0 && (unsigned) x.de == x.dbLen - 1) { for (unsigned p = 0; p < x.dbLen; p++) cov[qLen - (x.dbLen - x.alnLen) + p][nuc_map(tSeq[p])]++; }
+            }
+            call_consensus(consensus, cov, minCovSafe);
+            for (unsigned p = 0; p < qLen; p++) consensus[qLen + p] = query[p];
+        }
+        unsigned maxLeft = 0, maxRight = 0;
+        for (size_t ci : cand) {   // updateSeqIdConsensusReads
+            Aln &x = a[ci];
+            oriented_target(blob + off[x.t], x.dbLen, x.rev, tSeq);
+            const bool rightStart = (unsigned) x.ds == 0 && (unsigned) x.qe == qLen - 1;
+            const bool leftStart = (unsigned) x.qs == 0 && (unsigned) x.de == x.dbLen - 1;
+            int idCnt = 0, idRy = 0; unsigned tot = 0;
+            const unsigned pad = qLen - (x.dbLen - x.alnLen);
+            if (leftStart) {
+                for (unsigned i = 0; i < x.dbLen; i++) {   // the padded target starts at consensus[pad]
+                    char c = consensus[pad + i], t = tSeq[i];
+                    if (!(c == 'N' || t == 'N')) { idCnt += c == t; idRy += ry_map(c) == ry_map(t); tot++; }
+                }
+            } else if (rightStart) {
+                const size_t base = consensus.size() - (x.dbLen + pad);
+                for (unsigned i = 0; i < x.dbLen; i++) {
+                    char c = consensus[base + i], t = tSeq[i];
+                    if (!(c == 'N' || t == 'N')) { idCnt += c == t; idRy += ry_map(c) == ry_map(t); tot++; }
+                }
+            }
+            if (tot != 0) { x.seqId = (float) idCnt / tot; x.ry = (float) idRy / tot; }
+            if (leftStart && tot > maxLeft) maxLeft = tot;
+            else if (rightStart && tot > maxRight) maxRight = tot;
+        }
+        maxLeftOut[q] = maxLeft; maxRightOut[q] = maxRight;
+        memcpy(consOut + consOff, consensus.data(), consensus.size());
+        for (u64 l = l0; l < l1; l++) {
+            const Aln &x = a[l - l0];
+            flags[l] = x.rev ? 2 : 0; oqS[l] = x.qs; oqE[l] = x.qe; odS[l] = x.ds; odE[l] = x.de; seqIdOut[l] = x.seqId; ryOut[l] = x.ry; sLenOut[l] = 0; sRatioOut[l] = 0;
+        }
+        for (size_t ci : cand) {   // scores
+            const Aln &x = a[ci];
+            const u64 l = l0 + ci;
+            flags[l] |= 1;
+            const bool notInside = x.dbLen != x.alnLen, rightStart = x.ds == 0, leftStart = x.qs == 0, notId = keys[x.t] != keys[q];
+            if ((rightStart || leftStart) && notInside && notId && x.ry >= rySeqIdThr && x.seqId >= seqIdThr) {
+                unsigned maxOverlap = maxRight;
+                if ((unsigned) x.qs == 0 && (unsigned) x.de == x.dbLen - 1) maxOverlap = maxLeft;
+                orc_pair_loglik_consensus(consensus.data(), qLen, blob + off[x.t], x.dbLen, x.rev ? 1 : 0, x.qs, x.qe, x.ds, x.de, x.alnLen, maxOverlap, seqErrRate,
+                                          randAlnPenal, excessPenal, &sLenOut[l], &sRatioOut[l]);
+                flags[l] |= 4;
+            }
+        }
+        consOff += 3 * (u64) qLen;
+    }
+}

@@ -62,6 +62,43 @@ class SeqSet:
         return {int(k): i for i, k in enumerate(self.keys)}
 
 
+def load_extension_kat(tag):
+    """tests/golden/extension_kat_<tag>.txt.gz (oracle/ref_extension.cpp): per query with >= 2 alignment lines what the reference's
+    consensusCaller / updateSeqIdConsensusReads / r_s_pair return -> {query index: dict}"""
+    out = {}
+    cur = None
+    for line in gzip.open(os.path.join(GOLD, "extension_kat_%s.txt.gz" % tag), "rt"):
+        f = line.rstrip("\n").split("\t")
+        if f[0] == "Q":
+            cur = dict(max_left=int(f[3]), max_right=int(f[4]), consensus=f[5].encode(), lines=[])
+            out[int(f[1])] = cur
+        else:
+            cur["lines"].append(dict(cand=int(f[2]), rev=int(f[3]), qs=int(f[4]), qe=int(f[5]), ds=int(f[6]), de=int(f[7]), seqid=np.float32(f[8]), ry=np.float32(f[9]),
+                                     scored=int(f[10]), slen=float(f[11]), sratio=float(f[12])))
+    return out
+
+
+def check_extension_against_kat(s, aln_off, got, kat, rtol):
+    """got: dict of per-line arrays (flags, qs, qe, ds, de, seqid, ry, slen, sratio) + per-query max_left / max_right / consensus"""
+    cons_off = np.concatenate([[0], np.cumsum(3 * s.len.astype(np.int64))])
+    n_scored = 0
+    for q, k in kat.items():
+        l0 = int(aln_off[q])
+        assert int(aln_off[q + 1]) - l0 == len(k["lines"]), q
+        assert got["max_left"][q] == k["max_left"] and got["max_right"][q] == k["max_right"], q
+        assert got["consensus"][cons_off[q]:cons_off[q + 1]].tobytes() == k["consensus"], q
+        for i, a in enumerate(k["lines"]):
+            l = l0 + i
+            fl = int(got["flags"][l])
+            assert (fl & 1) == a["cand"] and ((fl >> 1) & 1) == a["rev"] and ((fl >> 2) & 1) == a["scored"], (q, i, fl, a)
+            assert (got["qs"][l], got["qe"][l], got["ds"][l], got["de"][l]) == (a["qs"], a["qe"], a["ds"], a["de"]), (q, i)
+            assert got["seqid"][l] == a["seqid"] and got["ry"][l] == a["ry"], (q, i, got["seqid"][l], a["seqid"], got["ry"][l], a["ry"])
+            if a["scored"]:
+                n_scored += 1
+                assert np.isclose(got["slen"][l], a["slen"], rtol=rtol, atol=0) and np.isclose(got["sratio"][l], a["sratio"], rtol=rtol, atol=1e-300), (q, i)
+    return n_scored
+
+
 def load_pairlik_kat():
     """tests/golden/pairlik_kat.txt (oracle/ref_pairlik.cpp): outputs of the reference's calcLikelihood[Consensus]."""
     out = []
@@ -172,6 +209,26 @@ class Oracle:
                                          C.c_uint(max_aln), C.c_double(seq_err), C.c_float(rand), C.c_float(excess),
                                          C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def extension(self, s, aln_off, t_idx, seqid, qs, qe, ds, de, unsafe=0, seqid_thr=0.9, ry_thr=0.99, min_cov_safe=5, seq_err=0.001, rand=0.85,
+                  excess=0.0625):
+        """scoring front half of ancient_read_assemble (orc_extension) over all queries; arrays per alignment line"""
+        aln_off = np.ascontiguousarray(aln_off, np.uint64); t_idx = np.ascontiguousarray(t_idx, np.uint32); seqid = np.ascontiguousarray(seqid, np.float32)
+        qs, qe, ds, de = [np.ascontiguousarray(x, np.int32) for x in (qs, qe, ds, de)]
+        M = len(t_idx)
+        out = dict(flags=np.zeros(M, np.uint8), qs=np.zeros(M, np.int32), qe=np.zeros(M, np.int32), ds=np.zeros(M, np.int32), de=np.zeros(M, np.int32),
+                   seqid=np.zeros(M, np.float32), ry=np.zeros(M, np.float32), slen=np.zeros(M, np.float64), sratio=np.zeros(M, np.float64),
+                   max_left=np.zeros(s.n, np.uint32), max_right=np.zeros(s.n, np.uint32), consensus=np.zeros(3 * s.total, np.uint8))
+        keys = np.ascontiguousarray(s.keys, np.uint32)
+        self.L.orc_extension.restype = None
+        self.L.orc_extension(C.c_void_p(s.blob.ctypes.data), C.c_void_p(s.off.ctypes.data), C.c_void_p(s.len.ctypes.data), C.c_void_p(s.ext.ctypes.data),
+                             C.c_void_p(keys.ctypes.data), C.c_size_t(s.n), C.c_void_p(aln_off.ctypes.data), C.c_void_p(t_idx.ctypes.data),
+                             C.c_void_p(qs.ctypes.data), C.c_void_p(qe.ctypes.data), C.c_void_p(ds.ctypes.data), C.c_void_p(de.ctypes.data),
+                             C.c_void_p(seqid.ctypes.data), C.c_float(seqid_thr), C.c_float(ry_thr), C.c_int(unsafe), C.c_uint(min_cov_safe),
+                             C.c_double(seq_err), C.c_float(rand), C.c_float(excess),
+                             *[C.c_void_p(out[k].ctypes.data) for k in ("flags", "qs", "qe", "ds", "de", "seqid", "ry", "slen", "sratio", "max_left", "max_right",
+                                                                        "consensus")])
+        return out
 
     def correct(self, s, aln_off, t_idx, seqid, qs, qe, ds, de, seqid_thr=0.9, ry_thr=0.99, seq_err=0.01, want_lik=False):
         aln_off = np.ascontiguousarray(aln_off, np.uint64); t_idx = np.ascontiguousarray(t_idx, np.uint32)
