@@ -101,6 +101,18 @@ class Patches(C.Structure):
     _fields_ = [("n", C.c_uint64), ("entry", C.POINTER(C.c_uint64))]
 
 
+class ExtParams(C.Structure):
+    _fields_ = [("min_seq_id", C.c_float), ("min_ryseq_id", C.c_float), ("unsafe", C.c_int32), ("min_cov_safe", C.c_uint32), ("keys", C.c_void_p)]
+
+
+class ExtScores(C.Structure):
+    _fields_ = [("n_lines", C.c_uint64), ("n_queries", C.c_uint64), ("flags", C.POINTER(C.c_uint8)), ("q_start", C.POINTER(C.c_int32)),
+                ("q_end", C.POINTER(C.c_int32)), ("db_start", C.POINTER(C.c_int32)), ("db_end", C.POINTER(C.c_int32)), ("seq_id", C.POINTER(C.c_float)),
+                ("ry_seq_id", C.POINTER(C.c_float)), ("s_len_norm", C.POINTER(C.c_double)), ("s_ratio", C.POINTER(C.c_double)),
+                ("max_aln_left", C.POINTER(C.c_uint32)), ("max_aln_right", C.POINTER(C.c_uint32)), ("consensus", C.POINTER(C.c_uint8)),
+                ("consensus_off", C.POINTER(C.c_uint64))]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_seqs", C.c_uint64), ("n_bases", C.c_uint64), ("n_records", C.c_uint64), ("n_grouped", C.c_uint64),
                 ("n_hits", C.c_uint64), ("n_alns", C.c_uint64), ("sort1_passes", C.c_uint32), ("sort2_passes", C.c_uint32),
@@ -140,6 +152,7 @@ def lib():
         L.cdg_iteration_compact.argtypes = [C.c_void_p, C.POINTER(IterParams), C.POINTER(AlnsCompact), C.POINTER(Patches), C.POINTER(C.c_uint64)]
         L.cdg_export_alns_compact.argtypes = [C.c_void_p, C.POINTER(AlnsCompact)]
         L.cdg_export_patches.argtypes = [C.c_void_p, C.POINTER(Patches)]
+        L.cdg_extension_scores.argtypes = [C.c_void_p, C.POINTER(ExtParams), C.POINTER(ExtScores)]
         L.cdg_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.cdg_test_radix_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
         L.cdg_test_hash_revcomp.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -413,6 +426,19 @@ class Context:
             self._ck(lib().cdg_pair_loglik_consensus(self._h, C.byref(P), _ptr(consensus), consensus.nbytes, _ptr(cons_off), _ptr(a), _ptr(b)),
                      "cdg_pair_loglik_consensus")
         return a, b
+
+    def extension_scores(self, min_seq_id=0.9, min_ryseq_id=0.99, unsafe=0, min_cov_safe=5, keys=None):
+        """cdg_extension_scores on the context's alignments -> dict of numpy arrays (copies), same names as Oracle.extension"""
+        keys = None if keys is None else np.ascontiguousarray(keys, np.uint32)
+        p = ExtParams(min_seq_id, min_ryseq_id, unsafe, min_cov_safe, keys.ctypes.data if keys is not None else None)
+        o = ExtScores()
+        self._ck(lib().cdg_extension_scores(self._h, C.byref(p), C.byref(o)), "cdg_extension_scores")
+        M, n = o.n_lines, o.n_queries
+        cons_off = _view(o.consensus_off, n + 1, np.uint64)
+        return dict(flags=_view(o.flags, M, np.uint8), qs=_view(o.q_start, M, np.int32), qe=_view(o.q_end, M, np.int32), ds=_view(o.db_start, M, np.int32),
+                    de=_view(o.db_end, M, np.int32), seqid=_view(o.seq_id, M, np.float32), ry=_view(o.ry_seq_id, M, np.float32),
+                    slen=_view(o.s_len_norm, M, np.float64), sratio=_view(o.s_ratio, M, np.float64), max_left=_view(o.max_aln_left, n, np.uint32),
+                    max_right=_view(o.max_aln_right, n, np.uint32), consensus=_view(o.consensus, int(cons_off[-1]), np.uint8), consensus_off=cons_off)
 
     def stats(self):
         s = Stats()

@@ -12,6 +12,7 @@
 #include "cdg_align.cuh"
 #include "cdg_common.cuh"
 #include "cdg_export.cuh"
+#include "cdg_ext.cuh"
 #include "cdg_kmer.cuh"
 #include "cdg_pairlik.cuh"
 #include "cdg_sort.cuh"
@@ -107,6 +108,7 @@ struct cdg_ctx {
     // km_prepare's result ((length desc, id asc) order, slot prefix, slice bounds) is a property of the resident set and of
     // (k, kmers per sequence, world, rank): kept until the next upload
     u64 uploadGen = 0, prepGen = ~0ull; int prepK = 0, prepKps = 0; float prepScale = 0.f; u32 prepWorld = 0, prepRank = 0; KmPlanFwd prepPlan; u32 splitPasses = 1; DevBuf dHashHist, dChunkK, dChunkV, dRouteBase;
+    DevBuf dExtI32, dExtF32, dExtF64, dExtU8, dExtU32, dExtU64, dExtCons, dExtKeys; HostBuf hExt;   // cdg_extension_scores
     DevBuf dSetFacts, dSlowList, dPrep, dAlnLen, dMism, dKey2HiA, dKey2HiB; u64 *sortedKey2Hi = nullptr; bool bytesValid = true; bool patchesDirect = false;
     u64 nLines = 0, nKept = 0; bool linesValid = false, alnsValid = false, alnsFromText = false;
     // correction
@@ -285,11 +287,12 @@ extern "C" void cdg_destroy(cdg_ctx *ctx) {
                    &ctx->dScore, &ctx->dBits, &ctx->dEvalue, &ctx->dSeqId, &ctx->dQS, &ctx->dQE, &ctx->dDS, &ctx->dDE, &ctx->dLineSel,
                    &ctx->dTables, &ctx->dOut, &ctx->dLik, &ctx->dWideList, &ctx->dRecvK, &ctx->dRecvV, &ctx->dRecv2, &ctx->dQList, &ctx->dPow31,
                    &ctx->dPairModel, &ctx->dPairIn, &ctx->dPairCons, &ctx->dPairOut, &ctx->dRecvIdK, &ctx->dRecvIdV, &ctx->dRouteTab,
-                   &ctx->dIdCnt, &ctx->dCmpCount, &ctx->dCmpTarget, &ctx->dCmpFields, &ctx->dPatches, &ctx->dKey2Big, &ctx->dSetFacts, &ctx->dSlowList, &ctx->dPrep, &ctx->dAlnLen, &ctx->dMism, &ctx->dKey2HiA, &ctx->dKey2HiB, &ctx->dHashHist, &ctx->dChunkK, &ctx->dChunkV, &ctx->dRouteBase};
+                   &ctx->dIdCnt, &ctx->dCmpCount, &ctx->dCmpTarget, &ctx->dCmpFields, &ctx->dPatches, &ctx->dKey2Big, &ctx->dSetFacts, &ctx->dSlowList, &ctx->dPrep, &ctx->dAlnLen, &ctx->dMism, &ctx->dKey2HiA, &ctx->dKey2HiB, &ctx->dHashHist, &ctx->dChunkK, &ctx->dChunkV, &ctx->dRouteBase, &ctx->dExtI32, &ctx->dExtF32, &ctx->dExtF64, &ctx->dExtU8, &ctx->dExtU32, &ctx->dExtU64,
+                   &ctx->dExtCons, &ctx->dExtKeys};
     for (DevBuf *b : d) b->release();
     HostBuf *h[] = {&ctx->hHitRep, &ctx->hHitTgt, &ctx->hHitScore, &ctx->hHitDiag, &ctx->hHitDiag16, &ctx->hLineOff, &ctx->hLineT, &ctx->hKeep,
                     &ctx->hScore, &ctx->hBits, &ctx->hEvalue, &ctx->hSeqId, &ctx->hQS, &ctx->hQE, &ctx->hDS, &ctx->hDE,
-                    &ctx->hCmpCount, &ctx->hCmpTarget, &ctx->hCmpFields, &ctx->hPatches};
+                    &ctx->hCmpCount, &ctx->hCmpTarget, &ctx->hCmpFields, &ctx->hPatches, &ctx->hExt};
     for (HostBuf *b : h) b->release();
     for (int i = 0; i < EV_N; i++) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->chunkDone) cudaEventDestroy(e);
@@ -542,7 +545,6 @@ static int km_bits(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlan &K) {
 // (length desc, id asc) order, slot prefix in that order, rankOf, slice of this rank
 static int km_prepare_compute(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlanFwd &K);
 static int km_prepare(cdg_ctx *ctx, const cdg_kmer_params *p, KmPlan &K) {
-    const u64 n = ctx->n;
     if (ctx->prepGen == ctx->uploadGen && ctx->prepK == p->k && ctx->prepKps == p->kmers_per_seq && ctx->prepScale == p->kmers_per_seq_scale &&
         ctx->prepWorld == K.world && ctx->prepRank == K.rank) {   // same resident set, same parameters: nothing to recompute
         const bool wide = K.wide; const int idBits = K.idBits, diagBits = K.diagBits;
@@ -1537,6 +1539,81 @@ extern "C" int cdg_pair_loglik_consensus(cdg_ctx *ctx, const cdg_pairs *pairs, c
                                          const uint64_t *cons_off, double *s_len_norm, double *s_ratio) {
     if (!consensus || !cons_off) return CDG_ERR_ARG;
     return run_pair_loglik(ctx, pairs, consensus, consensus_bytes, cons_off, s_len_norm, s_ratio);
+}
+
+// ---- scoring front half of ancient_read_assemble on the alignments of the context ----------------------------
+extern "C" int cdg_extension_scores(cdg_ctx *ctx, const cdg_ext_params *p, cdg_ext_scores *out) {
+    if (!ctx || !p || !out) return CDG_ERR_ARG;
+    if (ctx->n == 0) return fail(ctx, CDG_ERR_ARG, "cdg_extension_scores: no resident sequence set");
+    if (!ctx->alnsValid) return fail(ctx, CDG_ERR_ARG, "cdg_extension_scores: no alignments (cdg_rescore or cdg_set_alignments)");
+    if (!ctx->pairModelSet) return fail(ctx, CDG_ERR_ARG, "cdg_extension_scores: cdg_set_pair_model not called");
+    if (ctx->qLo != 0 || ctx->nQ != ctx->n) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_extension_scores: the alignments must cover all queries of the context");
+    CK(cudaSetDevice(ctx->device));
+    if (int rcb = ensure_bytes(ctx)) return rcb;
+    using namespace cdgext;
+    const u64 M = ctx->nLines, n = ctx->n, consBytes = 3 * ctx->totalBases;
+    // device arrays: 4 x i32 coordinates | 2 x f32 identities | 2 x f64 scores | flags + rev (u8) | maxAln per line + maxLeft/Right per query (u32) | consOff (u64)
+    CK(ctx->dExtI32.reserve((4 * M + 4) * 4)); CK(ctx->dExtF32.reserve((2 * M + 2) * 4)); CK(ctx->dExtF64.reserve((2 * M + 2) * 8)); CK(ctx->dExtU8.reserve(2 * M + 2));
+    CK(ctx->dExtU32.reserve((M + 2 * n + 4) * 4)); CK(ctx->dExtU64.reserve((M + 1) * 8)); CK(ctx->dExtCons.reserve(consBytes + 16));
+    i32 *oqS = ctx->dExtI32.as<i32>(), *oqE = oqS + M, *odS = oqE + M, *odE = odS + M;
+    float *sid = ctx->dExtF32.as<float>(), *ry = sid + M;
+    double *sLen = ctx->dExtF64.as<double>(), *sRatio = sLen + M;
+    u8 *flags = ctx->dExtU8.as<u8>(), *revLine = flags + M;
+    u32 *maxAlnLine = ctx->dExtU32.as<u32>(), *maxLeft = maxAlnLine + M, *maxRight = maxLeft + n;
+    u64 *consOffLine = ctx->dExtU64.as<u64>();
+    const u32 *dKeys = nullptr;
+    if (p->keys) { CK(ctx->dExtKeys.reserve(n * 4)); CK(cudaMemcpyAsync(ctx->dExtKeys.p, p->keys, n * 4, cudaMemcpyHostToDevice, ctx->st)); dKeys = ctx->dExtKeys.as<u32>(); }
+    CK(cudaMemsetAsync(maxLeft, 0, 2 * n * 4, ctx->st));
+    ExtParams E; E.seqIdThr = p->min_seq_id; E.ryThr = p->min_ryseq_id; E.unsafe = p->unsafe; E.minCovSafe = p->min_cov_safe; E.roundSeqId = ctx->alnsFromText ? 0 : 1;
+    const SeqMeta *meta = ctx->dMeta.as<SeqMeta>();
+    const unsigned lb = (unsigned) ((M + 255) / 256);
+    if (M) {
+        ext_lines_kernel<<<lb, 256, 0, ctx->st>>>(ctx->dData.as<u8>(), meta, dKeys, ctx->dLikOff.as<u64>(), ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(), ctx->dKeep.as<u8>(),
+                                                 ctx->dSeqId.as<float>(), ctx->dQS.as<i32>(), ctx->dQE.as<i32>(), ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), M, E, flags, oqS, oqE,
+                                                 odS, odE, sid, ry, consOffLine);
+        ctx->launches++;
+    }
+    ext_consensus_kernel<<<(unsigned) std::min<u64>((n * 32 + 255) / 256, (u64) ctx->smCount * 16), 256, 0, ctx->st>>>(
+        ctx->dData.as<u8>(), meta, dKeys, ctx->dLikOff.as<u64>(), ctx->dLineOff.as<u64>(), n, ctx->dLineT.as<u32>(), flags, oqS, oqE, odS, odE, E, ctx->dExtCons.as<u8>());
+    ctx->launches++;
+    if (M) {
+        ext_update_kernel<<<lb, 256, 0, ctx->st>>>(ctx->dData.as<u8>(), meta, ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(), flags, oqS, oqE, odS, odE, consOffLine,
+                                                  ctx->dExtCons.as<u8>(), M, sid, ry, maxLeft, maxRight);
+        ext_select_kernel<<<lb, 256, 0, ctx->st>>>(meta, dKeys, ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(), flags, oqS, odS, odE, sid, ry, maxLeft, maxRight, M, E, maxAlnLine,
+                                                  revLine);
+        const unsigned grid = (unsigned) std::min<u64>((M + cdgpair::PL_WARPS - 1) / cdgpair::PL_WARPS, (u64) ctx->smCount * 8);
+        cdgpair::pair_loglik_kernel<1><<<grid, cdgpair::PL_WARPS * 32, 0, ctx->st>>>(
+            ctx->dData.as<u8>(), meta, M, ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(), revLine, oqS, oqE, odS, odE, maxAlnLine, ctx->dExtCons.as<u8>(), consOffLine,
+            ctx->dPairModel.as<cdgpair::PairModel>(), sLen, sRatio, flags, EXT_SCORED);
+        ctx->launches += 3;
+    }
+    CKL();
+    // one pinned block: flags | 4 coordinates | 2 identities | 2 scores | maxLeft | maxRight | consensus | consensus offsets per query
+    auto al = [](u64 x) { return (x + 15) & ~15ull; };
+    const u64 oFlags = 0, oI = al(M), oF = oI + al(16 * M), oD = oF + al(8 * M), oML = oD + al(16 * M), oMR = oML + al(4 * n), oC = oMR + al(4 * n), oCO = oC + al(consBytes),
+              total = oCO + al(8 * (n + 1));
+    CK(ctx->hExt.reserve(total + 16));
+    u8 *h = ctx->hExt.as<u8>();
+    if (M) {
+        CK(cudaMemcpyAsync(h + oFlags, flags, M, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(h + oI, oqS, 16 * M, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(h + oF, sid, 8 * M, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(h + oD, sLen, 16 * M, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CK(cudaMemcpyAsync(h + oML, maxLeft, 4 * n, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(h + oMR, maxRight, 4 * n, cudaMemcpyDeviceToHost, ctx->st));
+    if (consBytes) CK(cudaMemcpyAsync(h + oC, ctx->dExtCons.p, consBytes, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(h + oCO, ctx->dLikOff.p, 8 * (n + 1), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    u64 *co = (u64 *) (h + oCO);
+    for (u64 i = 0; i <= n; i++) co[i] *= 3;
+    out->n_lines = M; out->n_queries = n; out->flags = h + oFlags;
+    out->q_start = (const int32_t *) (h + oI); out->q_end = out->q_start + M; out->db_start = out->q_end + M; out->db_end = out->db_start + M;
+    out->seq_id = (const float *) (h + oF); out->ry_seq_id = out->seq_id + M;
+    out->s_len_norm = (const double *) (h + oD); out->s_ratio = out->s_len_norm + M;
+    out->max_aln_left = (const uint32_t *) (h + oML); out->max_aln_right = (const uint32_t *) (h + oMR);
+    out->consensus = h + oC; out->consensus_off = co;
+    return CDG_OK;
 }
 
 extern "C" int cdg_get_stats(cdg_ctx *ctx, cdg_stats *out) {

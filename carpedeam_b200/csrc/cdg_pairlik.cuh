@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(PL_WARPS * 32) pair_loglik_kernel(
     const u32 *__restrict__ qIdx, const u32 *__restrict__ tIdx, const u8 *__restrict__ revFlag,
     const i32 *__restrict__ qS_, const i32 *__restrict__ qE_, const i32 *__restrict__ dS_, const i32 *__restrict__ dE_,
     const u32 *__restrict__ maxAln_, const u8 *__restrict__ cons, const u64 *__restrict__ consOff,
-    const PairModel *__restrict__ modelG, double *__restrict__ sLen, double *__restrict__ sRatio) {
+    const PairModel *__restrict__ modelG, double *__restrict__ sLen, double *__restrict__ sRatio,
+    const u8 *__restrict__ selFlags = nullptr /*not null: only pairs with (selFlags[i] & selMask) are evaluated, the others get 0*/, u8 selMask = 0) {
     __shared__ PairModel M;
     {
         const u32 *src = (const u32 *) modelG; u32 *dst = (u32 *) &M;
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32) pair_loglik_kernel(
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (u64 i = (u64) blockIdx.x * PL_WARPS + warp; i < nPairs; i += (u64) gridDim.x * PL_WARPS) {
+        if (selFlags && !(selFlags[i] & selMask)) { if (lane == 0) { sLen[i] = 0.0; sRatio[i] = 0.0; } continue; }
         const SeqMeta tm = meta[tIdx[i]];
         const u32 dbLen = tm.lenFlags & META_LEN;
         const u8 *t = data + tm.off;

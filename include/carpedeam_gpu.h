@@ -240,6 +240,34 @@ int cdg_iteration_compact(cdg_ctx *ctx, const cdg_iter_params *p, cdg_alns_compa
 int cdg_export_alns_compact(cdg_ctx *ctx, cdg_alns_compact *out);
 int cdg_export_patches(cdg_ctx *ctx, cdg_patches *out);
 
+/* ---- scoring front half of ancient_read_assemble ---------------------------------------------------------
+ * For the alignment lines of the context (cdg_set_alignments with the aln DB of the iteration, or the fused cdg_rescore) and
+ * the resident — corrected — sequences: everything doNuclAssembly1 computes per query before the greedy extension
+ * (src/assembler/ancientReadsResults.cpp:200-370): orientation of reverse alignments (:200-236), identity / RY identity against
+ * the query (:247-293), the extension candidates `notContig` (:294-315), consensusCaller (nuclassembleUtil.cpp:570-702; --unsafe 0
+ * copies the query between two N flanks, --unsafe 1 calls the flanks from the candidates with --min-cov-safe),
+ * updateSeqIdConsensusReads (:377-470: identities against the consensus, longest left / right overlap per query) and the scores
+ * of r_s_pair / calcLikelihoodConsensus (:48-70, :203-374) for the lines that pass the final filter (:351-352).  Needs
+ * cdg_set_pair_model.  The host keeps the priority queue: push line l when flags[l] & 4 and s_ratio[l] > --likelihood-ratio-threshold. */
+typedef struct {
+    float min_seq_id;          /* --min-seq-id (par.seqIdThr, 0.9 in the assembler workflow) */
+    float min_ryseq_id;        /* --min-ryseq-id (par.rySeqIdThr, 0.99) */
+    int32_t unsafe;            /* --unsafe */
+    uint32_t min_cov_safe;     /* --min-cov-safe (5) */
+    const uint32_t *keys;      /* DB keys of the sequences (n entries, host) or NULL when key == index: the reference compares a
+                                  target INDEX with the query KEY at ancientReadsResults.cpp:263 */
+} cdg_ext_params;
+typedef struct {               /* pinned host memory owned by the context, valid until the next call */
+    uint64_t n_lines, n_queries;
+    const uint8_t *flags;      /* bit 0 extension candidate, bit 1 isRevToAlignment, bit 2 scored */
+    const int32_t *q_start, *q_end, *db_start, *db_end;   /* oriented frame */
+    const float *seq_id, *ry_seq_id;
+    const double *s_len_norm, *s_ratio;                   /* 0 unless scored */
+    const uint32_t *max_aln_left, *max_aln_right;         /* per query */
+    const uint8_t *consensus; const uint64_t *consensus_off;   /* query q: 3*len letters at consensus + consensus_off[q] */
+} cdg_ext_scores;
+int cdg_extension_scores(cdg_ctx *ctx, const cdg_ext_params *p, cdg_ext_scores *out);
+
 /* ---- multi-GPU phases ------------------------------------------------------------
  * One context per rank, the whole sequence set uploaded on every rank.  K-mer records are owned by hash range like
  * kmermatcher's split passes (kmermatcher.cpp:742-784): rank r owns hash16 in [r*65536/world, (r+1)*65536/world).

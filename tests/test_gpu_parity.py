@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from support import GOLD, SeqSet, format_aln, format_pref, load_golden, parse_aln, parse_pref, synth_reads
+from support import seqid_text as seqid_text_bytes
 
 pytestmark = pytest.mark.gpu
 
@@ -897,3 +898,56 @@ def test_memory_driven_number_of_hash_range_passes(ctx):
         c2.close()
         torch.cuda.empty_cache()
     _hits_equal(got, whole)
+
+
+@pytest.mark.parametrize("tag,unsafe", [("safe", 0), ("unsafe", 1)])
+def test_extension_scores_vs_reference_functions(ctx, tag, unsafe):
+    """cdg_extension_scores (orientation, identity recompute, candidates, consensusCaller,
+    updateSeqIdConsensusReads, r_s_pair) against what the reference's own functions returned on config 1's second iteration
+    (tests/golden/extension_kat_*.txt.gz, oracle/ref_extension.cpp): flags, oriented coordinates, float identities and consensus
+    strings bit-exact, likelihood scores within 1e-5 relative (north_star; measured ~1e-13)."""
+    import carpedeam_b200 as cd
+    from support import check_extension_against_kat, load_extension_kat
+    s = SeqSet.from_golden("correction_1")
+    akeys, apay, _ = load_golden("aln_1")
+    off, t, sid, qs, qe, ds, de = parse_aln(s, apay)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_alignments(off, t, sid, qs, qe, ds, de)
+    ctx.set_pair_model(cd.load_pair_model(os.path.join(GOLD, "dhigh")))
+    got = ctx.extension_scores(unsafe=unsafe, keys=s.keys)
+    assert np.array_equal(got["consensus_off"], np.concatenate([[0], np.cumsum(3 * s.len.astype(np.uint64))]).astype(np.uint64))
+    n_scored = check_extension_against_kat(s, off, got, load_extension_kat(tag), rtol=1e-5)
+    assert n_scored > 4000
+
+
+def test_extension_scores_vs_oracle_on_synthetic_sets(ctx, oracle):
+    """same against the oracle on a synthetic iteration (reads with N, ext-flagged contigs as targets and queries, unsafe consensus
+    with enough coverage to call flank bases): every line of every query"""
+    import carpedeam_b200 as cd
+    rng = np.random.default_rng(91)
+    seqs = synth_reads(6000, 12000, 92, n_frac=0.001)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    seqs += [acgt[rng.integers(0, 4, 900)].tobytes(), acgt[rng.integers(0, 4, 400)].tobytes()]
+    ext = [0] * 6000 + [1, 1]
+    s = SeqSet(seqs, ext=ext)
+    ctx.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    hits, alns, out, changed = ctx.iteration(fetch_hits=True)
+    k = alns["keep"].astype(bool)
+    lo = alns["line_off"].astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(k)])[lo].astype(np.uint64)
+    # the aln DB text rounds the identity to three decimals (Util.cpp:278-307): what ancient_read_assemble reads back
+    sid = np.array([np.float32(float(seqid_text_bytes(x))) for x in alns["seqid"][k]], np.float32)
+    args = (off, alns["tgt"][k], sid, alns["qs"][k], alns["qe"][k], alns["ds"][k], alns["de"][k])
+    oracle.load_damage(os.path.join(GOLD, "dhigh"))
+    ctx.set_alignments(*args)
+    ctx.set_pair_model(cd.load_pair_model(os.path.join(GOLD, "dhigh")))
+    for unsafe, min_cov in ((0, 5), (1, 2)):
+        want = oracle.extension(s, *args, unsafe=unsafe, min_cov_safe=min_cov)
+        got = ctx.extension_scores(unsafe=unsafe, min_cov_safe=min_cov)
+        for f in ("flags", "qs", "qe", "ds", "de", "seqid", "ry", "max_left", "max_right", "consensus"):
+            assert np.array_equal(got[f], want[f]), (unsafe, f)
+        sc = (want["flags"] & 4) != 0
+        assert sc.sum() > 1000
+        assert np.allclose(got["slen"][sc], want["slen"][sc], rtol=1e-5, atol=0) and np.allclose(got["sratio"], want["sratio"], rtol=1e-5, atol=1e-300)
+    assert (want["consensus"] != ord("N")).sum() > s.total      # the unsafe run called bases in the flanks
