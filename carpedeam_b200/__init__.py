@@ -113,6 +113,21 @@ class ExtScores(C.Structure):
                 ("consensus_off", C.POINTER(C.c_uint64))]
 
 
+class MergeModel(C.Structure):
+    _fields_ = [("match_lik", C.c_double * 32)]
+
+
+class MergeParams(C.Structure):
+    _fields_ = [("min_merge_seq_id", C.c_float), ("min_ryseq_id", C.c_float), ("unsafe", C.c_int32), ("min_cov_safe", C.c_uint32), ("keys", C.c_void_p)]
+
+
+class MergeOut(C.Structure):
+    _fields_ = [("n_lines", C.c_uint64), ("flags", C.POINTER(C.c_uint8)), ("q_start", C.POINTER(C.c_int32)), ("q_end", C.POINTER(C.c_int32)),
+                ("db_start", C.POINTER(C.c_int32)), ("db_end", C.POINTER(C.c_int32)), ("seq_id_query", C.POINTER(C.c_float)),
+                ("ry_seq_id_query", C.POINTER(C.c_float)), ("seq_id", C.POINTER(C.c_float)), ("ry_seq_id", C.POINTER(C.c_float)),
+                ("deam_match", C.POINTER(C.c_float)), ("aln_len_cons", C.POINTER(C.c_uint32))]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_seqs", C.c_uint64), ("n_bases", C.c_uint64), ("n_records", C.c_uint64), ("n_grouped", C.c_uint64),
                 ("n_hits", C.c_uint64), ("n_alns", C.c_uint64), ("sort1_passes", C.c_uint32), ("sort2_passes", C.c_uint32),
@@ -171,6 +186,10 @@ def hostlib():
         H.cdh_build_damage.restype = C.c_int
         H.cdh_build_pair_model.argtypes = [C.c_char_p, C.c_double, C.c_float, C.c_float, C.POINTER(PairModel), C.c_char_p, C.c_size_t]
         H.cdh_build_pair_model.restype = C.c_int
+        H.cdh_build_merge_model.argtypes = [C.c_char_p, C.POINTER(MergeModel), C.c_char_p, C.c_size_t]
+        H.cdh_build_merge_model.restype = C.c_int
+        H.cdh_merge_less.argtypes = [C.c_uint32, C.c_float, C.c_uint32, C.c_float]; H.cdh_merge_less.restype = C.c_int
+        H.cdh_merge_queue_order.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]; H.cdh_merge_queue_order.restype = None
         H.cdh_packed_words.argtypes = [C.c_void_p, C.c_uint64]; H.cdh_packed_words.restype = C.c_uint64
         H.cdh_pack_seqs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
         H.cdh_pack_seqs.restype = C.c_int
@@ -252,6 +271,23 @@ def load_pair_model(prefix, seq_err=0.001, rand_align_penal=0.85, excess_penal=0
     if rc != 0:
         raise CdgError("damage profile: " + err.value.decode())
     return m
+
+
+def load_merge_model(prefix):
+    """--ancient-damage PFX -> cdg_merge_model (carpedeam_b200/host/merge.cpp)."""
+    m = MergeModel()
+    err = C.create_string_buffer(512)
+    if hostlib().cdh_build_merge_model((prefix or "").encode(), C.byref(m), err, 512) != 0:
+        raise CdgError("damage profile: " + err.value.decode())
+    return m
+
+
+def merge_queue_order(aln_len_cons, deam_match):
+    """order in which the reference's priority queue (CompareNuclResultByScoreContigs) pops lines pushed in the given order"""
+    alc = np.ascontiguousarray(aln_len_cons, np.uint32); d = np.ascontiguousarray(deam_match, np.float32)
+    order = np.zeros(len(alc), np.uint32)
+    hostlib().cdh_merge_queue_order(_ptr(alc), _ptr(d), len(alc), _ptr(order))
+    return order
 
 
 class Context:
@@ -439,6 +475,21 @@ class Context:
                     de=_view(o.db_end, M, np.int32), seqid=_view(o.seq_id, M, np.float32), ry=_view(o.ry_seq_id, M, np.float32),
                     slen=_view(o.s_len_norm, M, np.float64), sratio=_view(o.s_ratio, M, np.float64), max_left=_view(o.max_aln_left, n, np.uint32),
                     max_right=_view(o.max_aln_right, n, np.uint32), consensus=_view(o.consensus, int(cons_off[-1]), np.uint8), consensus_off=cons_off)
+
+    def set_merge_model(self, model):
+        self._ck(lib().cdg_set_merge_model(self._h, C.byref(model)), "cdg_set_merge_model")
+
+    def merge_scores(self, min_merge_seq_id=0.99, min_ryseq_id=0.99, unsafe=0, min_cov_safe=5, keys=None):
+        """cdg_merge_scores on the context's alignments -> dict of numpy arrays (copies), same names as Oracle.merge"""
+        keys = None if keys is None else np.ascontiguousarray(keys, np.uint32)
+        p = MergeParams(min_merge_seq_id, min_ryseq_id, unsafe, min_cov_safe, keys.ctypes.data if keys is not None else None)
+        o = MergeOut()
+        self._ck(lib().cdg_merge_scores(self._h, C.byref(p), C.byref(o)), "cdg_merge_scores")
+        M = o.n_lines
+        return dict(flags=_view(o.flags, M, np.uint8), qs=_view(o.q_start, M, np.int32), qe=_view(o.q_end, M, np.int32), ds=_view(o.db_start, M, np.int32),
+                    de=_view(o.db_end, M, np.int32), seqid0=_view(o.seq_id_query, M, np.float32), ry0=_view(o.ry_seq_id_query, M, np.float32),
+                    seqid=_view(o.seq_id, M, np.float32), ry=_view(o.ry_seq_id, M, np.float32), deam=_view(o.deam_match, M, np.float32),
+                    aln_len_cons=_view(o.aln_len_cons, M, np.uint32))
 
     def stats(self):
         s = Stats()

@@ -14,6 +14,7 @@
 #include "cdg_export.cuh"
 #include "cdg_ext.cuh"
 #include "cdg_kmer.cuh"
+#include "cdg_merge.cuh"
 #include "cdg_pairlik.cuh"
 #include "cdg_sort.cuh"
 
@@ -116,6 +117,8 @@ struct cdg_ctx {
     u64 headCap = 0;   // records of a neighbour's head run that fit behind sortedKey2 (cdg_mg_sort2 / cdg_mg_head_area)
     // pair likelihood (a19)
     DevBuf dPairModel, dPairIn, dPairCons, dPairOut; bool pairModelSet = false;
+    // contig-merge scores (N3)
+    DevBuf dMergeLog; cdgmerge::MergeModel mergeModel; bool mergeModelSet = false;
 };
 
 namespace {
@@ -1613,6 +1616,82 @@ extern "C" int cdg_extension_scores(cdg_ctx *ctx, const cdg_ext_params *p, cdg_e
     out->s_len_norm = (const double *) (h + oD); out->s_ratio = out->s_len_norm + M;
     out->max_aln_left = (const uint32_t *) (h + oML); out->max_aln_right = (const uint32_t *) (h + oMR);
     out->consensus = h + oC; out->consensus_off = co;
+    return CDG_OK;
+}
+
+// ---- N3: scoring front half of ancient_contig_merge (cdg_merge.cuh) ----------------------------------------------------------
+extern "C" int cdg_set_merge_model(cdg_ctx *ctx, const cdg_merge_model *m) {
+    if (!ctx || !m) return CDG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    // deamMatches' length prior (nuclassembleUtil.cpp:1017-1030) needs log(): tabulated here with the host libm the reference uses
+    const u32 nTab = cdgmerge::MRG_MAX_LOG_LEN + 1;
+    std::vector<double> tab(nTab);
+    const double logAdj = std::log(1.4e-9);
+    for (u32 len = 0; len < nTab; len++) tab[len] = logAdj - 3.0 * std::log(len);
+    CK(ctx->dMergeLog.reserve(nTab * 8));
+    CK(cudaMemcpyAsync(ctx->dMergeLog.p, tab.data(), nTab * 8, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (int r = 0; r < 2; r++) { ctx->mergeModel.matchLik[r][0] = m->match_lik[r][1][3]; ctx->mergeModel.matchLik[r][1] = m->match_lik[r][2][0]; }
+    ctx->mergeModel.absLogMin = std::abs(tab[10]); ctx->mergeModel.absLogMax = std::abs(tab[cdgmerge::MRG_MAX_LOG_LEN]);
+    ctx->mergeModelSet = true;
+    return CDG_OK;
+}
+
+extern "C" int cdg_merge_scores(cdg_ctx *ctx, const cdg_merge_params *p, cdg_merge_out *out) {
+    if (!ctx || !p || !out) return CDG_ERR_ARG;
+    if (ctx->n == 0) return fail(ctx, CDG_ERR_ARG, "cdg_merge_scores: no resident sequence set");
+    if (!ctx->alnsValid) return fail(ctx, CDG_ERR_ARG, "cdg_merge_scores: no alignments (cdg_rescore or cdg_set_alignments)");
+    if (!ctx->mergeModelSet) return fail(ctx, CDG_ERR_ARG, "cdg_merge_scores: cdg_set_merge_model not called");
+    if (ctx->qLo != 0 || ctx->nQ != ctx->n) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_merge_scores: the alignments must cover all queries of the context");
+    CK(cudaSetDevice(ctx->device));
+    if (int rcb = ensure_bytes(ctx)) return rcb;
+    using namespace cdgmerge;
+    const u64 M = ctx->nLines, n = ctx->n, consBytes = p->unsafe ? 3 * ctx->totalBases : 0;
+    // device arrays: 4 x i32 coordinates | 5 x f32 (seqId0, ry0, seqId, ry, deamMatch) | flags (u8) | alnLengthCons (u32)
+    CK(ctx->dExtI32.reserve((4 * M + 4) * 4)); CK(ctx->dExtF32.reserve((5 * M + 5) * 4)); CK(ctx->dExtU8.reserve(M + 2)); CK(ctx->dExtU32.reserve((M + 4) * 4));
+    if (consBytes) CK(ctx->dExtCons.reserve(consBytes + 16));
+    i32 *oqS = ctx->dExtI32.as<i32>(), *oqE = oqS + M, *odS = oqE + M, *odE = odS + M;
+    float *sid0 = ctx->dExtF32.as<float>(), *ry0 = sid0 + M, *sid = ry0 + M, *ry = sid + M, *deam = ry + M;
+    u8 *flags = ctx->dExtU8.as<u8>();
+    u32 *alc = ctx->dExtU32.as<u32>();
+    const u32 *dKeys = nullptr;
+    if (p->keys) { CK(ctx->dExtKeys.reserve(n * 4)); CK(cudaMemcpyAsync(ctx->dExtKeys.p, p->keys, n * 4, cudaMemcpyHostToDevice, ctx->st)); dKeys = ctx->dExtKeys.as<u32>(); }
+    MergeParams P; P.mergeThr = p->min_merge_seq_id; P.ryThr = p->min_ryseq_id; P.unsafe = p->unsafe;
+    const SeqMeta *meta = ctx->dMeta.as<SeqMeta>();
+    if (M) {
+        const unsigned wgrid = (unsigned) std::min<u64>((M * 32 + 255) / 256, (u64) ctx->smCount * 16);
+        merge_lines_kernel<<<wgrid, 256, 0, ctx->st>>>(ctx->dData.as<u8>(), meta, dKeys, ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(), ctx->dKeep.as<u8>(), ctx->dQS.as<i32>(),
+                                                      ctx->dQE.as<i32>(), ctx->dDS.as<i32>(), ctx->dDE.as<i32>(), M, P, flags, oqS, oqE, odS, odE, sid0, ry0);
+        ctx->launches++;
+        if (p->unsafe) {
+            ExtParams E; E.seqIdThr = p->min_merge_seq_id; E.ryThr = p->min_ryseq_id; E.unsafe = 1; E.minCovSafe = p->min_cov_safe; E.roundSeqId = 0;
+            ext_consensus_kernel<<<(unsigned) std::min<u64>((n * 32 + 255) / 256, (u64) ctx->smCount * 16), 256, 0, ctx->st>>>(
+                ctx->dData.as<u8>(), meta, dKeys, ctx->dLikOff.as<u64>(), ctx->dLineOff.as<u64>(), n, ctx->dLineT.as<u32>(), flags, oqS, oqE, odS, odE, E, ctx->dExtCons.as<u8>());
+            ctx->launches++;
+        }
+        merge_score_kernel<<<wgrid, 256, 0, ctx->st>>>(ctx->dData.as<u8>(), meta, ctx->dLikOff.as<u64>(), ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(), flags, oqS, oqE, odS, odE,
+                                                      sid0, ry0, p->unsafe ? ctx->dExtCons.as<u8>() : nullptr, ctx->dMergeLog.as<double>(), ctx->mergeModel, M, P, sid, ry,
+                                                      alc, deam);
+        ctx->launches++;
+    }
+    CKL();
+    // one pinned block: flags | 4 coordinates | 5 floats | alnLengthCons
+    auto al = [](u64 x) { return (x + 15) & ~15ull; };
+    const u64 oFlags = 0, oI = al(M), oF = oI + al(16 * M), oU = oF + al(20 * M), total = oU + al(4 * M);
+    CK(ctx->hExt.reserve(total + 16));
+    u8 *h = ctx->hExt.as<u8>();
+    if (M) {
+        CK(cudaMemcpyAsync(h + oFlags, flags, M, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(h + oI, oqS, 16 * M, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(h + oF, sid0, 20 * M, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(h + oU, alc, 4 * M, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CK(cudaStreamSynchronize(ctx->st));
+    out->n_lines = M; out->flags = h + oFlags;
+    out->q_start = (const int32_t *) (h + oI); out->q_end = out->q_start + M; out->db_start = out->q_end + M; out->db_end = out->db_start + M;
+    out->seq_id_query = (const float *) (h + oF); out->ry_seq_id_query = out->seq_id_query + M; out->seq_id = out->ry_seq_id_query + M; out->ry_seq_id = out->seq_id + M;
+    out->deam_match = out->ry_seq_id + M;
+    out->aln_len_cons = (const uint32_t *) (h + oU);
     return CDG_OK;
 }
 

@@ -150,3 +150,16 @@ extern "C" int cdh_build_pair_model(const char *prefix, double seq_err, float ra
     out->log_rand = logf(rand_align_penal);
     return 0;
 }
+
+// D[11] / Drev[11] narrowed to double, [class][from][to] (inspection, and the entries the contig-merge scores read: host/merge.cpp)
+extern "C" int cdh_damage_matrices(const char *prefix, double *D_out, double *Drev_out, char *errbuf, size_t errlen) {
+    Matrix4 D[11], Drev[11];
+    if (build_matrices(prefix, D, Drev, errbuf, errlen)) return -1;
+    for (int l = 0; l < 11; l++)
+        for (int q = 0; q < 4; q++)
+            for (int t = 0; t < 4; t++) {
+                D_out[l * 16 + q * 4 + t] = (double) D[l].p[q][t];
+                Drev_out[l * 16 + q * 4 + t] = (double) Drev[l].p[q][t];
+            }
+    return 0;
+}

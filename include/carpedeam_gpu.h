@@ -268,6 +268,40 @@ typedef struct {               /* pinned host memory owned by the context, valid
 } cdg_ext_scores;
 int cdg_extension_scores(cdg_ctx *ctx, const cdg_ext_params *p, cdg_ext_scores *out);
 
+/* ---- scoring front half of ancient_contig_merge -----------------------------------------------------------
+ * For the alignment lines of the context (the aln DB of a contig iteration through cdg_set_alignments, or the fused cdg_rescore) and the
+ * resident — corrected — sequences: everything doNuclAssembly2 computes per query before the greedy merge
+ * (src/assembler/ancientContigsResults.cpp:187-262): orientation of reverse alignments and identity / RY identity against the query for
+ * every line (:195-222), the merge candidates `contigs` (:224-229: both identities above their thresholds, not the query itself),
+ * consensusCaller (nuclassembleUtil.cpp:570-702, as in cdg_extension_scores), updateSeqIdConsensus (:704-790: identities over the non-N
+ * columns of the padded target against the consensus, alnLengthCons), the queue filter (:246-250: overlaps shorter than 500 need
+ * min(500, 0.2 * dbLen)) and ancientMatchCount (:1050-1180: expected matches from the consensus identity plus the posterior-weighted
+ * C->T / G->A columns of deamMatches :1011-1047, interior damage class, D or Drev by strand).
+ * The host keeps the priority queue: push line l when flags[l] & 4, ordered by cdh_merge_less (carpedeam_b200/host/merge.cpp =
+ * CompareNuclResultByScoreContigs, ancientContigsResults.cpp:24-70) over (aln_len_cons, deam_match). */
+typedef struct {
+    double match_lik[2][4][4];   /* [isRevToAlignment][consensus base][target base], A0 C1 G2 T3: D[5] / Drev[5] of initDeamProbabilities as
+                                    doubles (carpedeam_b200/host/merge.cpp: cdh_build_merge_model); only C->T and G->A are read */
+} cdg_merge_model;
+int cdg_set_merge_model(cdg_ctx *ctx, const cdg_merge_model *m);
+typedef struct {
+    float min_merge_seq_id;    /* --min-merge-seq-id (par.mergeSeqIdThr, 0.99) */
+    float min_ryseq_id;        /* --min-ryseq-id (par.rySeqIdThr, 0.99) */
+    int32_t unsafe;            /* --unsafe */
+    uint32_t min_cov_safe;     /* --min-cov-safe (5) */
+    const uint32_t *keys;      /* DB keys of the sequences (n entries, host) or NULL when key == index */
+} cdg_merge_params;
+typedef struct {               /* pinned host memory owned by the context, valid until the next call */
+    uint64_t n_lines;
+    const uint8_t *flags;      /* bit 0 merge candidate, bit 1 isRevToAlignment, bit 2 queued */
+    const int32_t *q_start, *q_end, *db_start, *db_end;   /* oriented frame */
+    const float *seq_id_query, *ry_seq_id_query;          /* identities against the query (:213-222), every line */
+    const float *seq_id, *ry_seq_id;                      /* after updateSeqIdConsensus (= the former unless a candidate touches an end) */
+    const float *deam_match;                              /* ancientMatchCount, 0 unless queued */
+    const uint32_t *aln_len_cons;                         /* alnLengthCons, 0 unless candidate */
+} cdg_merge_out;
+int cdg_merge_scores(cdg_ctx *ctx, const cdg_merge_params *p, cdg_merge_out *out);
+
 /* ---- multi-GPU phases ------------------------------------------------------------
  * One context per rank, the whole sequence set uploaded on every rank.  K-mer records are owned by hash range like
  * kmermatcher's split passes (kmermatcher.cpp:742-784): rank r owns hash16 in [r*65536/world, (r+1)*65536/world).

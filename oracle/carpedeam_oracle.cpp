@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <queue>
 #include <string>
 #include <vector>
 
@@ -750,4 +751,146 @@ extern "C" void orc_extension(const char *blob, const u64 *off, const u32 *len, 
         }
         consOff += 3 * (u64) qLen;
     }
+}
+
+// ---- scoring front half of ancient_contig_merge --------------------------------------------------------------
+// Per query, over the alignment lines of its aln DB entry (doNuclAssembly2, src/assembler/ancientContigsResults.cpp):
+//   orientation + identity / RY identity against the query + merge candidates ("contigs")   :187-236
+//   consensusCaller                   src/assembler/nuclassembleUtil.cpp:570-702 (the same function N1 uses)
+//   updateSeqIdConsensus              :704-790   (identities over the non-N columns, alnLengthCons)
+//   queue filter                      ancientContigsResults.cpp:246-262 (minAlnLen = 500, or min(500, 0.2*dbLen) for shorter overlaps)
+//   ancientMatchCount / deamMatches   nuclassembleUtil.cpp:1050-1180, :1011-1047 (D or Drev by isRevToAlignment, interior class 5)
+//   queue order                       CompareNuclResultByScoreContigs, ancientContigsResults.cpp:24-70 (std::priority_queue)
+// Pinned by tests/golden/merge_kat_*.txt.gz (outputs of the reference's own functions, oracle/ref_merge.cpp).
+// flags out: bit 0 merge candidate, bit 1 isRevToAlignment, bit 2 queued.  seqId0/ry0 = identities against the query.
+static double deam_posterior(unsigned alnLength, unsigned scoreAln, double matchLik) {   // deamMatches :1011-1047
+    const double logAdj = std::log(1.4e-9);
+    const unsigned maxLength = 100000;
+    auto logPower = [logAdj](unsigned length) { return logAdj - 3.0 * std::log(length); };
+    const double logMin = logPower(10), logMax = logPower(maxLength);
+    const double logLength = logPower(std::min(alnLength, maxLength));
+    const double fractionLength = (std::abs(logLength) - std::abs(logMax)) / (std::abs(logMin) - std::abs(logMax));
+    const double priorAln = 1 - fractionLength;
+    const double pMatch = 0.5f * ((((static_cast<double>(scoreAln) + 3.0f * alnLength) / 5.0f) + 0.9f) / (alnLength + 1)) + 0.5f * priorAln;
+    const double likNoMatch = 1 - pMatch;
+    const double oddsRatio = likNoMatch / matchLik;
+    const double odds = (1 - pMatch) / pMatch;
+    return 1 / (1 + oddsRatio * odds);
+}
+extern "C" int orc_merge_less(unsigned alnLenCons1, float deam1, unsigned alnLenCons2, float deam2) {   // ancientContigsResults.cpp:24-70
+    float mm1 = alnLenCons1 - deam1, mm2 = alnLenCons2 - deam2;
+    float alpha1 = mm1 + 1, alpha2 = mm2 + 1, beta1 = deam1 + 1, beta2 = deam2 + 1;
+    double log_c = (std::lgamma(beta1 + beta2) + std::lgamma(alpha1 + beta1)) - (std::lgamma(alpha1 + beta1 + beta2) + std::lgamma(beta1));
+    double log_r = 0.0, p = 0.0;
+    for (size_t idx = 0; idx < alpha2; idx++) {
+        p += exp(log_r + log_c);
+        log_r = log(alpha1 + idx) + log(beta2 + idx) - (log(idx + 1) + log(idx + alpha1 + beta1 + beta2)) + log_r;
+    }
+    if (p < 0.45) return 1;
+    if (p > 0.55) return 0;
+    if (alnLenCons1 < alnLenCons2) return 1;
+    if (alnLenCons1 > alnLenCons2) return 0;
+    return 1;
+}
+extern "C" void orc_merge(const char *blob, const u64 *off, const u32 *len, const u32 *keys, size_t n, const u64 *lineOff, const u32 *tgt,
+                          const int32_t *qS, const int32_t *qE, const int32_t *dS, const int32_t *dE, float mergeSeqIdThr, float rySeqIdThr, int unsafe,
+                          unsigned minCovSafe, uint8_t *flags, int32_t *oqS, int32_t *oqE, int32_t *odS, int32_t *odE, float *seqId0, float *ry0,
+                          float *seqIdOut, float *ryOut, u32 *alnLenConsOut, float *deamOut, u64 *consHash /*per query, FNV-1a 64*/) {
+    for (size_t q = 0; q < n; q++) {
+        const unsigned qLen = len[q];
+        const char *query = blob + off[q];
+        const u64 l0 = lineOff[q], l1 = lineOff[q + 1];
+        struct Aln { u32 t; int qs, qe, ds, de; unsigned dbLen, alnLen, alnLenCons; float seqId, ry; bool rev; };
+        std::vector<Aln> a(l1 - l0);
+        std::vector<size_t> cand;
+        std::string tSeq;
+        for (u64 l = l0; l < l1; l++) {
+            Aln &x = a[l - l0];
+            x.t = tgt[l]; x.qs = qS[l]; x.qe = qE[l]; x.ds = dS[l]; x.de = dE[l]; x.dbLen = len[x.t]; x.alnLenCons = 0;
+            x.alnLen = (unsigned) (std::max(std::abs(x.qe - x.qs), std::abs(x.de - x.ds)) + 1);
+            x.rev = x.qs > x.qe;
+            if (x.rev) { std::swap(x.qs, x.qe); int d0 = x.ds; x.ds = (int) x.dbLen - x.de - 1; x.de = (int) x.dbLen - d0 - 1; }
+            oriented_target(blob + off[x.t], x.dbLen, x.rev, tSeq);
+            int idCnt = 0, idRy = 0;
+            for (int i = x.qs; i <= x.qe; i++) {
+                char qc = query[i], tc = tSeq[x.ds + (i - x.qs)];
+                idCnt += qc == tc; idRy += ry_map(qc) == ry_map(tc);
+            }
+            x.seqId = (float) idCnt / x.alnLen; x.ry = (float) idRy / x.alnLen;
+            seqId0[l] = x.seqId; ry0[l] = x.ry;
+            if (x.seqId >= mergeSeqIdThr && x.ry >= rySeqIdThr && keys[q] != keys[x.t]) cand.push_back(l - l0);
+        }
+        std::string consensus(3 * (size_t) qLen, 'N');
+        if (!unsafe) { for (unsigned p = 0; p < qLen; p++) consensus[qLen + p] = query[p]; }
+        else {
+            std::vector<std::vector<unsigned>> cov(3 * (size_t) qLen, std::vector<unsigned>(4, 0));
+            for (size_t ci : cand) {
+                const Aln &x = a[ci];
+                const bool rightStart = x.ds == 0 && x.de != (int) x.dbLen - 1;
+                const bool leftStart = x.qs == 0 && x.qe != (int) qLen - 1;
+                if (!(rightStart || leftStart)) continue;
+                oriented_target(blob + off[x.t], x.dbLen, x.rev, tSeq);
+                if ((unsigned) x.ds == 0 && (unsigned) x.qe == qLen - 1) { for (unsigned p = 0; p < x.dbLen; p++) cov[qLen + x.qs + p][nuc_map(tSeq[p])]++; }
+                else if ((unsigned) x.qs == 0 && (unsigned) x.de == x.dbLen - 1) { for (unsigned p = 0; p < x.dbLen; p++) cov[qLen - (x.dbLen - x.alnLen) + p][nuc_map(tSeq[p])]++; }
+            }
+            call_consensus(consensus, cov, minCovSafe);
+            for (unsigned p = 0; p < qLen; p++) consensus[qLen + p] = query[p];
+        }
+        u64 h = 1469598103934665603ull;
+        for (unsigned char c : consensus) { h ^= c; h *= 1099511628211ull; }
+        consHash[q] = h;
+        for (u64 l = l0; l < l1; l++) {
+            const Aln &x = a[l - l0];
+            flags[l] = x.rev ? 2 : 0; oqS[l] = x.qs; oqE[l] = x.qe; odS[l] = x.ds; odE[l] = x.de; alnLenConsOut[l] = 0; deamOut[l] = 0.f;
+        }
+        for (size_t ci : cand) {
+            Aln &x = a[ci];
+            const u64 l = l0 + ci;
+            flags[l] |= 1;
+            oriented_target(blob + off[x.t], x.dbLen, x.rev, tSeq);
+            const bool rightStart = (unsigned) x.ds == 0 && (unsigned) x.qe == qLen - 1;
+            const bool leftStart = (unsigned) x.qs == 0 && (unsigned) x.de == x.dbLen - 1;
+            const unsigned pad = qLen - (x.dbLen - x.alnLen);
+            // the padded target lies at consensus[base ..): left = pad, right = 3*qLen - (dbLen + pad)
+            const size_t base = leftStart ? pad : consensus.size() - (x.dbLen + pad);
+            int idCnt = 0, idRy = 0; unsigned tot = 0, nCT = 0, nGA = 0;
+            if (leftStart || rightStart) {
+                for (unsigned i = 0; i < x.dbLen; i++) {
+                    char c = consensus[base + i], t = tSeq[i];
+                    if (!(c == 'N' || t == 'N')) {
+                        idCnt += c == t; idRy += ry_map(c) == ry_map(t); tot++;
+                        const int dimer = 4 * nuc_map(c) + nuc_map(t);
+                        nCT += dimer == 7; nGA += dimer == 8;
+                    }
+                }
+            }
+            if (tot != 0) { x.seqId = (float) idCnt / tot; x.ry = (float) idRy / tot; }   // updateSeqIdConsensus
+            x.alnLenCons = tot;
+            alnLenConsOut[l] = tot;
+            unsigned minAlnLen = 500;
+            minAlnLen = (x.alnLen < minAlnLen) ? std::min(minAlnLen, static_cast<unsigned>(0.2 * x.dbLen)) : minAlnLen;
+            if (x.seqId >= mergeSeqIdThr && x.ry >= rySeqIdThr && x.alnLen >= minAlnLen) {   // ancientMatchCount
+                const std::vector<DiNuc> &tab = x.rev ? g_Drev : g_D;
+                float mCT = 0, mGA = 0;
+                unsigned mmCons = (1 - x.seqId) * x.alnLenCons + 0.5;
+                unsigned mCons = x.alnLenCons - mmCons;
+                unsigned scoreAln = mCons * 2 + mmCons * (-3);
+                const double likCT = tab[5].p[1][3], likGA = tab[5].p[2][0];
+                if (likCT > 0) for (unsigned i = 0; i < nCT; i++) mCT += deam_posterior(x.alnLen, scoreAln, likCT);
+                if (likGA > 0) for (unsigned i = 0; i < nGA; i++) mGA += deam_posterior(x.alnLen, scoreAln, likGA);
+                deamOut[l] = ((static_cast<float>(scoreAln) + 3.0f * x.alnLenCons) / 5.0f) + mCT + mGA;
+                flags[l] |= 4;
+            }
+        }
+        for (u64 l = l0; l < l1; l++) { seqIdOut[l] = a[l - l0].seqId; ryOut[l] = a[l - l0].ry; }
+    }
+}
+// the order in which std::priority_queue<…, CompareNuclResultByScoreContigs> hands out the queued lines (pushed in line order)
+extern "C" void orc_merge_queue_order(const u32 *alnLenCons, const float *deam, size_t m, u32 *order) {
+    struct Item { u32 i, alc; float d; };
+    struct Less { bool operator()(const Item &a, const Item &b) const { return orc_merge_less(a.alc, a.d, b.alc, b.d) != 0; } };
+    std::priority_queue<Item, std::vector<Item>, Less> pq;
+    for (size_t i = 0; i < m; i++) pq.push(Item{(u32) i, alnLenCons[i], deam[i]});
+    size_t k = 0;
+    while (!pq.empty()) { order[k++] = pq.top().i; pq.pop(); }
 }

@@ -18,9 +18,9 @@ ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libcarpedeam_oracle.so")
 
 # ------------------------------------------------------------------------------------------------
 # canonical golden DBs  (format: oracle/make_golden.py)
-def load_golden(name):
+def load_golden(name, prefix="cfg1_"):
     """-> (keys[int], payloads[bytes], exts[int]) sorted by key."""
-    blob = gzip.open(os.path.join(GOLD, "cfg1_%s.gz" % name), "rb").read()
+    blob = gzip.open(os.path.join(GOLD, "%s%s.gz" % (prefix, name)), "rb").read()
     keys, payloads, exts = [], [], []
     pos = 0
     while pos < len(blob):
@@ -49,8 +49,8 @@ class SeqSet:
         self.total = int(self.len.sum())
 
     @classmethod
-    def from_golden(cls, name):
-        keys, payloads, exts = load_golden(name)
+    def from_golden(cls, name, prefix="cfg1_"):
+        keys, payloads, exts = load_golden(name, prefix)
         assert keys == sorted(keys)
         return cls([p.rstrip(b"\n") for p in payloads], keys, exts)
 
@@ -97,6 +97,63 @@ def check_extension_against_kat(s, aln_off, got, kat, rtol):
                 n_scored += 1
                 assert np.isclose(got["slen"][l], a["slen"], rtol=rtol, atol=0) and np.isclose(got["sratio"][l], a["sratio"], rtol=rtol, atol=1e-300), (q, i)
     return n_scored
+
+
+MERGE_SETS = {"asm5": ("correction_5", "aln_asm_5", "cfg1_"), "asm9": ("correction_9", "aln_asm_9", "cfg1_"), "synth": ("synth_contigs", "synth_contigs_aln", "")}
+
+
+def load_merge_kat(tag):
+    """tests/golden/merge_kat_<tag>.txt.gz (oracle/ref_merge.cpp): per run (unsafe, --min-merge-seq-id) and per query with >= 2 alignment lines what the
+    reference's consensusCaller / updateSeqIdConsensus / ancientMatchCount return and the order its priority queue pops the queued lines in
+    -> {(unsafe, thr): {query index: dict}}"""
+    out = {}
+    run = cur = None
+    for line in gzip.open(os.path.join(GOLD, "merge_kat_%s.txt.gz" % tag), "rt"):
+        f = line.rstrip("\n").split("\t")
+        if f[0] == "H":
+            run = out.setdefault((int(f[1]), float(f[2])), {})
+        elif f[0] == "Q":
+            cur = dict(cons_hash=int(f[3], 16), lines=[], pops=[])
+            run[int(f[1])] = cur
+        elif f[0] == "A":
+            cur["lines"].append(dict(cand=int(f[2]), rev=int(f[3]), qs=int(f[4]), qe=int(f[5]), ds=int(f[6]), de=int(f[7]), seqid0=np.float32(f[8]), ry0=np.float32(f[9]),
+                                     seqid=np.float32(f[10]), ry=np.float32(f[11]), aln_len_cons=int(f[12]), queued=int(f[13]), deam=np.float32(f[14])))
+        else:
+            cur["pops"] = [int(x) for x in f[1:]]
+    return out
+
+
+def load_merge_set(tag):
+    """sequence set + alignment CSR arrays (parse_aln) of one merge_kat set"""
+    seqname, alnname, prefix = MERGE_SETS[tag]
+    s = SeqSet.from_golden(seqname, prefix)
+    akeys, apay, _ = load_golden(alnname, prefix)
+    amap = dict(zip(akeys, apay))
+    return s, parse_aln(s, [amap.get(int(k), b"") for k in s.keys])
+
+
+def check_merge_against_kat(aln_off, got, kat, deam_rtol):
+    """got: per-line arrays flags, qs, qe, ds, de, seqid0, ry0, seqid, ry, aln_len_cons, deam (+ optional per-query cons_hash).
+    -> (queued lines, lines whose deamMatch is bit-equal)"""
+    n_queued = n_exact = 0
+    for q, k in kat.items():
+        l0 = int(aln_off[q])
+        assert int(aln_off[q + 1]) - l0 == len(k["lines"]), q
+        if "cons_hash" in got:
+            assert int(got["cons_hash"][q]) == k["cons_hash"], q
+        for i, a in enumerate(k["lines"]):
+            l = l0 + i
+            fl = int(got["flags"][l])
+            assert (fl & 1) == a["cand"] and ((fl >> 1) & 1) == a["rev"] and ((fl >> 2) & 1) == a["queued"], (q, i, fl, a)
+            assert (got["qs"][l], got["qe"][l], got["ds"][l], got["de"][l]) == (a["qs"], a["qe"], a["ds"], a["de"]), (q, i)
+            assert got["seqid0"][l] == a["seqid0"] and got["ry0"][l] == a["ry0"], (q, i, got["seqid0"][l], a["seqid0"])
+            assert got["seqid"][l] == a["seqid"] and got["ry"][l] == a["ry"], (q, i, got["seqid"][l], a["seqid"], got["ry"][l], a["ry"])
+            assert int(got["aln_len_cons"][l]) == a["aln_len_cons"], (q, i)
+            if a["queued"]:
+                n_queued += 1
+                n_exact += int(got["deam"][l] == a["deam"])
+                assert np.isclose(got["deam"][l], a["deam"], rtol=deam_rtol, atol=0), (q, i, got["deam"][l], a["deam"])
+    return n_queued, n_exact
 
 
 def load_pairlik_kat():
@@ -229,6 +286,30 @@ class Oracle:
                              *[C.c_void_p(out[k].ctypes.data) for k in ("flags", "qs", "qe", "ds", "de", "seqid", "ry", "slen", "sratio", "max_left", "max_right",
                                                                         "consensus")])
         return out
+
+    def merge(self, s, aln_off, t_idx, qs, qe, ds, de, unsafe=0, merge_thr=0.99, ry_thr=0.99, min_cov_safe=5):
+        """scoring front half of ancient_contig_merge (orc_merge) over all queries; arrays per alignment line"""
+        aln_off = np.ascontiguousarray(aln_off, np.uint64); t_idx = np.ascontiguousarray(t_idx, np.uint32)
+        qs, qe, ds, de = [np.ascontiguousarray(x, np.int32) for x in (qs, qe, ds, de)]
+        M = len(t_idx)
+        out = dict(flags=np.zeros(M, np.uint8), qs=np.zeros(M, np.int32), qe=np.zeros(M, np.int32), ds=np.zeros(M, np.int32), de=np.zeros(M, np.int32),
+                   seqid0=np.zeros(M, np.float32), ry0=np.zeros(M, np.float32), seqid=np.zeros(M, np.float32), ry=np.zeros(M, np.float32),
+                   aln_len_cons=np.zeros(M, np.uint32), deam=np.zeros(M, np.float32), cons_hash=np.zeros(s.n, np.uint64))
+        keys = np.ascontiguousarray(s.keys, np.uint32)
+        self.L.orc_merge.restype = None
+        self.L.orc_merge(C.c_void_p(s.blob.ctypes.data), C.c_void_p(s.off.ctypes.data), C.c_void_p(s.len.ctypes.data), C.c_void_p(keys.ctypes.data), C.c_size_t(s.n),
+                         C.c_void_p(aln_off.ctypes.data), C.c_void_p(t_idx.ctypes.data), C.c_void_p(qs.ctypes.data), C.c_void_p(qe.ctypes.data),
+                         C.c_void_p(ds.ctypes.data), C.c_void_p(de.ctypes.data), C.c_float(merge_thr), C.c_float(ry_thr), C.c_int(unsafe), C.c_uint(min_cov_safe),
+                         *[C.c_void_p(out[k].ctypes.data) for k in ("flags", "qs", "qe", "ds", "de", "seqid0", "ry0", "seqid", "ry", "aln_len_cons", "deam",
+                                                                    "cons_hash")])
+        return out
+
+    def merge_queue_order(self, aln_len_cons, deam):
+        alc = np.ascontiguousarray(aln_len_cons, np.uint32); d = np.ascontiguousarray(deam, np.float32)
+        order = np.zeros(len(alc), np.uint32)
+        self.L.orc_merge_queue_order.restype = None
+        self.L.orc_merge_queue_order(C.c_void_p(alc.ctypes.data), C.c_void_p(d.ctypes.data), C.c_size_t(len(alc)), C.c_void_p(order.ctypes.data))
+        return order
 
     def correct(self, s, aln_off, t_idx, seqid, qs, qe, ds, de, seqid_thr=0.9, ry_thr=0.99, seq_err=0.01, want_lik=False):
         aln_off = np.ascontiguousarray(aln_off, np.uint64); t_idx = np.ascontiguousarray(t_idx, np.uint32)

@@ -951,3 +951,88 @@ def test_extension_scores_vs_oracle_on_synthetic_sets(ctx, oracle):
         assert sc.sum() > 1000
         assert np.allclose(got["slen"][sc], want["slen"][sc], rtol=1e-5, atol=0) and np.allclose(got["sratio"], want["sratio"], rtol=1e-5, atol=1e-300)
     assert (want["consensus"] != ord("N")).sum() > s.total      # the unsafe run called bases in the flanks
+
+
+def _synth_contig_set(seed, n, genome_len, lmin=600, lmax=6000):
+    """overlapping contigs of one random genome, both strands, light residual damage and errors, a few N (cf. oracle/make_merge_kat.py)"""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    comp = np.zeros(256, np.uint8)
+    for a, b in zip(b"ACGTN", b"TGCAN"):
+        comp[a] = b
+    genome = acgt[rng.integers(0, 4, genome_len)]
+    seqs = []
+    for _ in range(n):
+        L = int(rng.integers(lmin, lmax + 1))
+        st = int(rng.integers(0, genome_len - L))
+        r = genome[st:st + L].copy()
+        if rng.random() < 0.5:
+            r = comp[r[::-1]]
+        err = (0.0, 0.001, 0.004, 0.012)[int(rng.integers(0, 4))]
+        u = rng.random(L)
+        r[(r == ord("C")) & (u < 0.004)] = ord("T")
+        r[(r == ord("G")) & (u > 0.996)] = ord("A")
+        e = rng.random(L) < err
+        if e.any():
+            r[e] = acgt[rng.integers(0, 4, int(e.sum()))]
+        if rng.random() < 0.15:
+            r[rng.integers(0, L, 3)] = ord("N")
+        seqs.append(r.tobytes())
+    return seqs
+
+
+@pytest.mark.parametrize("tag", ["synth", "asm9", "asm5"])
+def test_merge_scores_vs_reference_functions(ctx, tag):
+    """cdg_merge_scores (orientation, identity recompute, merge candidates, consensusCaller, updateSeqIdConsensus,
+    queue filter, ancientMatchCount / deamMatches) against what the reference's own functions returned on the contig iterations of
+    config 1 and on a synthetic contig set (tests/golden/merge_kat_*.txt.gz, oracle/ref_merge.cpp), --unsafe 0 and 1 (and
+    --min-merge-seq-id 0.97 on the synthetic set): flags, oriented coordinates, float identities, alnLengthCons bit-exact; deamMatch (a
+    float built from double posteriors) bit-exact as well — the tolerance 1e-6 only guards the table-free parts of the arithmetic —
+    and the host-side queue order (cdh_merge_queue_order) equal to the order the reference's priority queue popped."""
+    import carpedeam_b200 as cd
+    from support import check_merge_against_kat, load_merge_kat, load_merge_set
+    s, (off, t, sid, qs, qe, ds, de) = load_merge_set(tag)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_alignments(off, t, sid, qs, qe, ds, de)
+    ctx.set_merge_model(cd.load_merge_model(os.path.join(GOLD, "dhigh")))
+    for (unsafe, thr), kat in load_merge_kat(tag).items():
+        got = ctx.merge_scores(min_merge_seq_id=thr, unsafe=unsafe, keys=s.keys)
+        n_queued, n_exact = check_merge_against_kat(off, got, kat, 1e-6)
+        assert n_queued > 100 and n_exact == n_queued, (tag, unsafe, thr, n_queued, n_exact)
+        for q, k in kat.items():
+            l0 = int(off[q])
+            idx = [i for i, a in enumerate(k["lines"]) if a["queued"]]
+            if idx:
+                order = cd.merge_queue_order(got["aln_len_cons"][l0:][idx], got["deam"][l0:][idx])
+                assert [idx[j] for j in order] == k["pops"], (tag, unsafe, thr, q)
+
+
+def test_merge_scores_vs_oracle_on_synthetic_contigs(ctx, oracle):
+    """same against the oracle on a larger synthetic contig iteration whose alignments come from the device's own k=22 kmermatch + rescore
+    (600 contigs of 0.6-6 kb, both strands, N, mixed error rates; unsafe consensus with --min-cov-safe 2 so that flank bases are called)"""
+    import carpedeam_b200 as cd
+    seqs = _synth_contig_set(20260119, 600, 150000)
+    s = SeqSet(seqs, ext=[1] * len(seqs))
+    ctx.set_damage(cd.load_damage(os.path.join(GOLD, "dhigh")))
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    hits, alns, out, changed = ctx.iteration(kmer=cd.kmer_params(k=22, include_only_extendable=1), fetch_hits=True)
+    k = alns["keep"].astype(bool)
+    lo = alns["line_off"].astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(k)])[lo].astype(np.uint64)
+    args = (off, alns["tgt"][k], alns["seqid"][k], alns["qs"][k], alns["qe"][k], alns["ds"][k], alns["de"][k])
+    # the merge reads the corrected sequences (correction_N): make them the resident set, as the workflow does
+    s2 = SeqSet([bytes(out[int(o):int(o) + int(l)]) for o, l in zip(s.off, s.len)], ext=[1] * len(seqs))
+    ctx.upload(s2.blob, s2.off, s2.len, s2.ext)
+    ctx.set_alignments(*args)
+    oracle.load_damage(os.path.join(GOLD, "dhigh"))
+    ctx.set_merge_model(cd.load_merge_model(os.path.join(GOLD, "dhigh")))
+    oargs = (args[0], args[1]) + args[3:]
+    for unsafe, min_cov, thr in ((0, 5, 0.99), (1, 2, 0.99), (1, 1, 0.97)):
+        want = oracle.merge(s2, *oargs, unsafe=unsafe, merge_thr=np.float32(thr), min_cov_safe=min_cov)
+        got = ctx.merge_scores(min_merge_seq_id=thr, unsafe=unsafe, min_cov_safe=min_cov)
+        for f in ("flags", "qs", "qe", "ds", "de", "seqid0", "ry0", "seqid", "ry", "aln_len_cons"):
+            assert np.array_equal(got[f], want[f]), (unsafe, f)
+        qd = (want["flags"] & 4) != 0
+        assert qd.sum() > 300
+        assert np.allclose(got["deam"], want["deam"], rtol=1e-6, atol=0)
+        assert (got["deam"] == want["deam"]).all()
