@@ -128,6 +128,16 @@ class MergeOut(C.Structure):
                 ("deam_match", C.POINTER(C.c_float)), ("aln_len_cons", C.POINTER(C.c_uint32))]
 
 
+class HammingParams(C.Structure):
+    _fields_ = [("cov_thr", C.c_float), ("cov_mode", C.c_int32), ("min_seq_id", C.c_float), ("seq_id_mode", C.c_int32), ("min_aln_len", C.c_int32),
+                ("wrapped_scoring", C.c_int32)]
+
+
+class HammingOut(C.Structure):
+    _fields_ = [("n_lines", C.c_uint64), ("n_queries", C.c_uint64), ("n_kept", C.c_uint64), ("line_off", C.POINTER(C.c_uint64)), ("target", C.POINTER(C.c_uint32)),
+                ("keep", C.POINTER(C.c_uint8)), ("pref_score", C.POINTER(C.c_int32)), ("diag", C.POINTER(C.c_int32)), ("seq_id", C.POINTER(C.c_float))]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_seqs", C.c_uint64), ("n_bases", C.c_uint64), ("n_records", C.c_uint64), ("n_grouped", C.c_uint64),
                 ("n_hits", C.c_uint64), ("n_alns", C.c_uint64), ("sort1_passes", C.c_uint32), ("sort2_passes", C.c_uint32),
@@ -475,6 +485,15 @@ class Context:
                     de=_view(o.db_end, M, np.int32), seqid=_view(o.seq_id, M, np.float32), ry=_view(o.ry_seq_id, M, np.float32),
                     slen=_view(o.s_len_norm, M, np.float64), sratio=_view(o.s_ratio, M, np.float64), max_left=_view(o.max_aln_left, n, np.uint32),
                     max_right=_view(o.max_aln_right, n, np.uint32), consensus=_view(o.consensus, int(cons_off[-1]), np.uint8), consensus_off=cons_off)
+
+    def rescore_hamming(self, cov_thr=0.8, cov_mode=0, min_seq_id=0.9, seq_id_mode=0, min_aln_len=0, wrapped=0):
+        """cdg_rescore_hamming (rescorediagonal --rescore-mode 0) on the context's prefilter lines -> dict of numpy arrays (copies)"""
+        p = HammingParams(cov_thr, cov_mode, min_seq_id, seq_id_mode, min_aln_len, wrapped)
+        o = HammingOut()
+        self._ck(lib().cdg_rescore_hamming(self._h, C.byref(p), C.byref(o)), "cdg_rescore_hamming")
+        M, n = o.n_lines, o.n_queries
+        return dict(line_off=_view(o.line_off, n + 1, np.uint64), tgt=_view(o.target, M, np.uint32), keep=_view(o.keep, M, np.uint8),
+                    score=_view(o.pref_score, M, np.int32), diag=_view(o.diag, M, np.int32), seqid=_view(o.seq_id, M, np.float32), n_kept=int(o.n_kept))
 
     def set_merge_model(self, model):
         self._ck(lib().cdg_set_merge_model(self._h, C.byref(model)), "cdg_set_merge_model")

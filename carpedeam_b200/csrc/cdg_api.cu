@@ -13,6 +13,7 @@
 #include "cdg_common.cuh"
 #include "cdg_export.cuh"
 #include "cdg_ext.cuh"
+#include "cdg_hamming.cuh"
 #include "cdg_kmer.cuh"
 #include "cdg_merge.cuh"
 #include "cdg_pairlik.cuh"
@@ -1294,6 +1295,49 @@ extern "C" int cdg_rescore(cdg_ctx *ctx, const cdg_rescore_params *p, cdg_alns *
     rc = read_scalar(ctx, SC_KEPT, &kept);
     ctx->nKept = kept;
     return rc;
+}
+
+// ---- N4: rescorediagonal --rescore-mode 0 (linclust's Hamming pre-clustering), cdg_hamming.cuh ------------------------------------
+extern "C" int cdg_rescore_hamming(cdg_ctx *ctx, const cdg_hamming_params *p, cdg_hamming_out *out) {
+    if (!ctx || !p || !out) return CDG_ERR_ARG;
+    if (ctx->n == 0) return fail(ctx, CDG_ERR_ARG, "cdg_rescore_hamming: no sequence set uploaded");
+    if (p->cov_mode < 0 || p->cov_mode > 5 || p->seq_id_mode < 0 || p->seq_id_mode > 2)
+        return fail(ctx, CDG_ERR_ARG, "cdg_rescore_hamming: --cov-mode %d / --seq-id-mode %d unknown", p->cov_mode, p->seq_id_mode);
+    CK(cudaSetDevice(ctx->device));
+    if (int rcp = ensure_packed(ctx)) return rcp;
+    if (!ctx->linesValid) {
+        if (!ctx->hitsValid) return fail(ctx, CDG_ERR_ARG, "cdg_rescore_hamming: no prefilter lines (run cdg_kmermatch or cdg_set_pref_lines)");
+        if (int rc = build_lines_from_hits(ctx)) return rc;
+    }
+    const u64 M = ctx->nLines, n = ctx->nQ;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    CK(cudaMemsetAsync(sc + SC_KEPT, 0, 8, ctx->st));
+    cdgham::HammingParams H; H.covThr = p->cov_thr; H.seqIdThr = p->min_seq_id; H.covMode = p->cov_mode; H.seqIdMode = p->seq_id_mode;
+    H.alnLenThr = p->min_aln_len; H.wrapped = p->wrapped_scoring;
+    if (M) {
+        cdgham::hamming_kernel<<<(unsigned) ((M + 255) / 256), 256, 0, ctx->st>>>(
+            ctx->dData.as<u8>(), ctx->dMeta.as<cdgalign::SeqMeta>(), ctx->dWords.as<u64>(), ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(), ctx->dLinePref.as<i32>(),
+            ctx->dLineDiag.as<u16>(), M, H, ctx->dKeep.as<u8>(), ctx->dScore.as<i32>(), ctx->dQS.as<i32>(), ctx->dSeqId.as<float>(), sc + SC_KEPT);
+        ctx->launches++;
+        CKL();
+    }
+    ctx->alnsValid = false;   // the alignment arrays now hold Hamming results
+    CK(ctx->hLineOff.reserve((n + 1) * 8)); CK(ctx->hLineT.reserve((M + 1) * 4)); CK(ctx->hKeep.reserve(M + 1)); CK(ctx->hScore.reserve((M + 1) * 4));
+    CK(ctx->hQS.reserve((M + 1) * 4)); CK(ctx->hSeqId.reserve((M + 1) * 4));
+    u64 kept = 0;
+    if (int rc = read_scalar(ctx, SC_KEPT, &kept)) return rc;
+    CK(cudaMemcpyAsync(ctx->hLineOff.p, ctx->dLineOff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->st));
+    if (M) {
+        CK(cudaMemcpyAsync(ctx->hLineT.p, ctx->dLineT.p, M * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(ctx->hKeep.p, ctx->dKeep.p, M, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(ctx->hScore.p, ctx->dScore.p, M * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(ctx->hQS.p, ctx->dQS.p, M * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(ctx->hSeqId.p, ctx->dSeqId.p, M * 4, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CK(cudaStreamSynchronize(ctx->st));
+    out->n_lines = M; out->n_queries = n; out->n_kept = kept; out->line_off = ctx->hLineOff.as<u64>(); out->target = ctx->hLineT.as<u32>();
+    out->keep = ctx->hKeep.as<u8>(); out->pref_score = ctx->hScore.as<i32>(); out->diag = ctx->hQS.as<i32>(); out->seq_id = ctx->hSeqId.as<float>();
+    return CDG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -302,6 +302,32 @@ typedef struct {               /* pinned host memory owned by the context, valid
 } cdg_merge_out;
 int cdg_merge_scores(cdg_ctx *ctx, const cdg_merge_params *p, cdg_merge_out *out);
 
+/* ---- rescorediagonal --rescore-mode 0 (linclust's Hamming pre-clustering) -------------------------------------
+ * The HAMMING branch of doRescorediagonal (lib/mmseqs/src/alignment/rescorediagonal.cpp:194-334, :251-254, :323-329) over the prefilter lines
+ * of the context (cdg_kmermatch, or cdg_set_pref_lines with a pref DB: lib/mmseqs/data/workflow/linclust.sh:28-32): number of equal
+ * bytes on the best real diagonal (DistanceCalculator.h:93-175, :275-295) or, with --wrapped-scoring, on the best rotation of the
+ * circular query (:57-91; targets longer than the query are skipped as in the reference), identity by --seq-id-mode, then the
+ * coverage / identity / length filters (Util.cpp:533-567).  Output per prefilter line in pref order: what the reference writes for
+ * kept lines — `target \t int(100*seqId) (negative on the reverse strand) \t diagonal (as short)` — and keep == 0 for dropped ones. */
+typedef struct {
+    float cov_thr;             /* -c (linclust: max(0.5, -c) = 0.8) */
+    int32_t cov_mode;          /* --cov-mode 0..5 */
+    float min_seq_id;          /* --min-seq-id (linclust: max(0.5, --min-seq-id) = 0.9) */
+    int32_t seq_id_mode;       /* --seq-id-mode 0 alignment length, 1 shorter, 2 longer sequence */
+    int32_t min_aln_len;       /* --min-aln-len */
+    int32_t wrapped_scoring;   /* --wrapped-scoring */
+} cdg_hamming_params;
+typedef struct {               /* pinned host memory owned by the context, valid until the next call */
+    uint64_t n_lines, n_queries, n_kept;
+    const uint64_t *line_off;  /* n_queries + 1 */
+    const uint32_t *target;
+    const uint8_t *keep;
+    const int32_t *pref_score; /* int(100 * seqId), negated for reverse-strand lines */
+    const int32_t *diag;       /* the value the pref line prints */
+    const float *seq_id;
+} cdg_hamming_out;
+int cdg_rescore_hamming(cdg_ctx *ctx, const cdg_hamming_params *p, cdg_hamming_out *out);
+
 /* ---- multi-GPU phases ------------------------------------------------------------
  * One context per rank, the whole sequence set uploaded on every rank.  K-mer records are owned by hash range like
  * kmermatcher's split passes (kmermatcher.cpp:742-784): rank r owns hash16 in [r*65536/world, (r+1)*65536/world).

@@ -894,3 +894,103 @@ extern "C" void orc_merge_queue_order(const u32 *alnLenCons, const float *deam, 
     size_t k = 0;
     while (!pq.empty()) { order[k++] = pq.top().i; pq.pop(); }
 }
+
+// ---- rescorediagonal --rescore-mode 0 (Hamming) with and without --wrapped-scoring -------------------------------
+// linclust's pre-clustering step (lib/mmseqs/data/workflow/linclust.sh:28-32, HAMMING_PAR of lib/mmseqs/src/workflow/Linclust.cpp:103-112).
+//   per-line body                        lib/mmseqs/src/alignment/rescorediagonal.cpp:194-334 (HAMMING branch :251-254, output :323-329)
+//   computeUngappedAlignment             lib/mmseqs/src/alignment/DistanceCalculator.h:93-113, ungappedAlignmentByDiagonal :115-175
+//   computeUngappedWrappedAlignment      :57-91 (query doubled, every start of the circular query against the whole target)
+//   computeInverseHammingDistance        :275-295 (number of equal bytes)
+//   Util::canBeCovered / hasCoverage / computeSeqId   lib/mmseqs/src/commons/Util.cpp:533-567, :588-598
+// Pinned by tests/golden/cfg1_lin_rescore_9.gz / cfg1_lin_rescore_wrapped_9.gz (outputs of the reference binary, oracle/make_hamming_golden.py).
+static unsigned inv_hamming(const char *a, const char *b, unsigned n) { unsigned s = 0; for (unsigned i = 0; i < n; i++) s += a[i] == b[i]; return s; }
+static LocalAln ham_by_diagonal(const char *q, unsigned qLen, const char *t, unsigned tLen, int diagonal) {
+    LocalAln res; unsigned ad = (unsigned) abs(diagonal);
+    res.dist = ad; res.diagonal = diagonal;
+    if (diagonal >= 0 && ad < qLen) { unsigned m = std::min(tLen, qLen - ad); res.diagonalLen = (int) m; res.score = inv_hamming(q + ad, t, m); }
+    else if (diagonal < 0 && ad < tLen) { unsigned m = std::min(tLen - ad, qLen); res.diagonalLen = (int) m; res.score = inv_hamming(q, t + ad, m); }
+    return res;
+}
+static bool can_be_covered(float covThr, int covMode, float q, float t) {
+    switch (covMode) {
+        case 0: return (q / t >= covThr) && (t / q >= covThr);
+        case 1: return (q / t) >= covThr;    // COV_MODE_TARGET
+        case 2: return (t / q) >= covThr;    // COV_MODE_QUERY
+        case 3: return ((t / q) >= covThr) && (t / q) <= 1.0;
+        case 4: return ((q / t) >= covThr) && (q / t) <= 1.0;
+        case 5: return (std::min(t, q) / std::max(t, q)) >= covThr;
+        default: return true;
+    }
+}
+static bool has_coverage(float covThr, int covMode, float qCov, float tCov) {
+    switch (covMode) {
+        case 0: return qCov >= covThr && tCov >= covThr;
+        case 2: return qCov >= covThr;
+        case 1: return tCov >= covThr;
+        default: return true;
+    }
+}
+// per prefilter line: keep (0 also for lines the reference skips), prefScore and diagonal as written (diagonal through unsigned short -> short)
+extern "C" void orc_rescore_hamming(const char *blob, const u64 *off, const u32 *len, const u32 *qIdx, const u32 *tIdx, const int32_t *prefScore,
+                                    const uint16_t *diag16, size_t M, int wrapped, float covThr, int covMode, float seqIdThr, int seqIdMode, int alnLenThr,
+                                    uint8_t *keep, int32_t *scoreOut, int32_t *diagOut, float *seqIdOut) {
+    std::string rev, dbl;
+    for (size_t h = 0; h < M; h++) {
+        const char *q = blob + off[qIdx[h]]; const int origQLen = (int) len[qIdx[h]];
+        const char *t = blob + off[tIdx[h]]; const int dbLen = (int) len[tIdx[h]];
+        keep[h] = 0; scoreOut[h] = 0; diagOut[h] = 0; seqIdOut[h] = 0.f;
+        int qLen = origQLen;
+        if (wrapped) { dbl.assign(q, origQLen); dbl += dbl; q = dbl.data(); qLen = 2 * origQLen; }
+        const bool isRev = prefScore[h] < 0;
+        if (isRev) {
+            rev.resize(qLen);
+            for (int p = qLen - 1; p > -1; p--) rev[(qLen - 1) - p] = NUM2AA[rev_code(map_letter((unsigned char) q[p]))];
+            q = rev.data();
+        }
+        const bool isIdentity = qIdx[h] == tIdx[h];
+        if (!can_be_covered(covThr, covMode, (float) origQLen, (float) dbLen)) continue;
+        LocalAln a;
+        if (wrapped) {
+            if (dbLen > origQLen) continue;
+            const unsigned half = (unsigned) qLen / 2, dbSeqLen = (unsigned) dbLen;
+            for (unsigned d = 1; (-d * 65536 + diag16[h]) > -dbSeqLen; d++) {
+                int realDiagonal = (int) (-d * 65536 + diag16[h]) + (int) half;
+                LocalAln tmp = ham_by_diagonal(q + realDiagonal, half, t, dbSeqLen, 0);
+                tmp.diagonal += realDiagonal; tmp.dist = (unsigned) abs(realDiagonal);
+                if (tmp.score > a.score) a = tmp;
+            }
+            for (unsigned d = 0; (d * 65536 + diag16[h]) < half; d++) {
+                int realDiagonal = (int) (d * 65536 + diag16[h]);
+                LocalAln tmp = ham_by_diagonal(q + realDiagonal, half, t, dbSeqLen, 0);
+                tmp.diagonal += realDiagonal; tmp.dist = (unsigned) abs(realDiagonal);
+                if (tmp.score > a.score) a = tmp;
+            }
+            a.diagonalLen = (int) std::min(dbSeqLen, half);
+        } else {
+            for (unsigned d = 1; d <= 1 + (unsigned) dbLen / 32768; d++) {
+                LocalAln tmp = ham_by_diagonal(q, (unsigned) qLen, t, (unsigned) dbLen, (int) (-d * 65536 + diag16[h]));
+                if (tmp.score > a.score) a = tmp;
+            }
+            for (unsigned d = 0; d <= (unsigned) qLen / 65536; d++) {
+                LocalAln tmp = ham_by_diagonal(q, (unsigned) qLen, t, (unsigned) dbLen, (int) (d * 65536 + diag16[h]));
+                if (tmp.score > a.score) a = tmp;
+            }
+        }
+        const int diagonalLen = a.diagonalLen, distance = (int) a.score;
+        const float targetCov = (float) diagonalLen / (float) dbLen, queryCov = (float) diagonalLen / (float) origQLen;
+        const int idCnt = (int) (float) distance;
+        float sidf;   // Util::computeSeqId
+        if (seqIdMode == 1) sidf = (float) idCnt / (float) std::min(origQLen, dbLen);
+        else if (seqIdMode == 2) sidf = (float) idCnt / (float) std::max(origQLen, dbLen);
+        else sidf = (float) idCnt / (float) diagonalLen;
+        const double seqId = sidf;
+        const int alnLen = diagonalLen;
+        const bool hasCov = has_coverage(covThr, covMode, queryCov, targetCov);
+        const bool hasSeqId = seqId >= (seqIdThr - FLT_EPSILON);
+        const bool hasAlnLen = alnLen >= alnLenThr;
+        if (isIdentity || (hasAlnLen && hasCov && hasSeqId)) {
+            int ps = (int) (100 * seqId);
+            keep[h] = 1; scoreOut[h] = isRev ? -ps : ps; diagOut[h] = (int) (short) (unsigned short) a.diagonal; seqIdOut[h] = sidf;
+        }
+    }
+}

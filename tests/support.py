@@ -238,6 +238,19 @@ class Oracle:
                              ("keep", "score", "bits", "evalue", "seqid", "qs", "qe", "ds", "de", "idcnt", "alnlen")])
         return out
 
+    def rescore_hamming(self, s, q_idx, t_idx, pref_score, diag16, wrapped=0, cov_thr=0.8, cov_mode=0, seqid_thr=0.9, seqid_mode=0, aln_len_thr=0):
+        """rescorediagonal --rescore-mode 0 per prefilter line (orc_rescore_hamming)"""
+        M = len(q_idx)
+        q_idx = np.ascontiguousarray(q_idx, np.uint32); t_idx = np.ascontiguousarray(t_idx, np.uint32)
+        pref_score = np.ascontiguousarray(pref_score, np.int32); diag16 = np.ascontiguousarray(diag16, np.uint16)
+        out = dict(keep=np.zeros(M, np.uint8), score=np.zeros(M, np.int32), diag=np.zeros(M, np.int32), seqid=np.zeros(M, np.float32))
+        self.L.orc_rescore_hamming.restype = None
+        self.L.orc_rescore_hamming(C.c_void_p(s.blob.ctypes.data), C.c_void_p(s.off.ctypes.data), C.c_void_p(s.len.ctypes.data), C.c_void_p(q_idx.ctypes.data),
+                                   C.c_void_p(t_idx.ctypes.data), C.c_void_p(pref_score.ctypes.data), C.c_void_p(diag16.ctypes.data), C.c_size_t(M),
+                                   C.c_int(wrapped), C.c_float(cov_thr), C.c_int(cov_mode), C.c_float(seqid_thr), C.c_int(seqid_mode), C.c_int(aln_len_thr),
+                                   *[C.c_void_p(out[k].ctypes.data) for k in ("keep", "score", "diag", "seqid")])
+        return out
+
     def load_damage(self, prefix):
         if prefix:
             self.L.orc_load_damage((prefix + "5p.prof").encode(), (prefix + "3p.prof").encode())
@@ -356,6 +369,30 @@ def format_pref(s, hits):
         k = int(keys[i])
         out[k] = b"%d\t0\t0\n" % k + b"".join(lines.get(i, []))
     return out
+
+
+def load_hamming_golden():
+    """sequence set, prefilter lines of the first 6000 queries (linclust's kmermatcher) and what the reference's rescorediagonal --rescore-mode 0
+    wrote for them without / with --wrapped-scoring (oracle/make_hamming_golden.py) -> (s, (q, t, score, diag16, off), {wrapped: {query key: payload}})"""
+    s = SeqSet.from_golden("correction_9")
+    pk, pp, _ = load_golden("lin_pref_9")
+    pmap = dict(zip(pk, pp))
+    lines = parse_pref(s, [pmap.get(int(k), b"") for k in s.keys])
+    want = {}
+    for w, name in ((0, "lin_rescore_9"), (1, "lin_rescore_wrapped_9")):
+        k, p, _ = load_golden(name)
+        want[w] = dict(zip(k, p))
+    return s, lines, want
+
+
+def format_hamming(s, q, t, keep, score, diag):
+    """kept lines -> {query key: pref-format payload} (QueryMatcher::prefilterHitToBuffer) for the queries that have prefilter lines"""
+    out = {}
+    for qi, ti, k, sc, dg in zip(q, t, keep, score, diag):
+        e = out.setdefault(int(s.keys[qi]), [])
+        if k:
+            e.append(b"%d\t%d\t%d\n" % (int(s.keys[ti]), int(sc), int(dg)))
+    return {k: b"".join(v) for k, v in out.items()}
 
 
 def seqid_text(x):

@@ -1036,3 +1036,59 @@ def test_merge_scores_vs_oracle_on_synthetic_contigs(ctx, oracle):
         assert qd.sum() > 300
         assert np.allclose(got["deam"], want["deam"], rtol=1e-6, atol=0)
         assert (got["deam"] == want["deam"]).all()
+
+
+@pytest.mark.parametrize("wrapped", [0, 1])
+def test_hamming_rescore_vs_reference(ctx, oracle, wrapped):
+    """cdg_rescore_hamming (rescorediagonal --rescore-mode 0, linclust's pre-clustering step, with and without
+    --wrapped-scoring) on the prefilter lines the reference's linclust kmermatcher wrote for config 1's last sequence set: every entry
+    equals what the reference binary wrote (tests/golden/cfg1_lin_rescore[_wrapped]_9.gz), every line equals the oracle."""
+    from support import format_hamming, load_hamming_golden
+    s, (q, t, sc, dg, off), want = load_hamming_golden()
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    ctx.set_pref_lines(off, t, sc, dg)
+    got = ctx.rescore_hamming(wrapped=wrapped)
+    ref = oracle.rescore_hamming(s, q, t, sc, dg, wrapped=wrapped)
+    for f in ("keep", "score", "diag"):
+        assert np.array_equal(got[f], ref[f]), f
+    k = ref["keep"].astype(bool)
+    assert np.array_equal(got["seqid"][k], ref["seqid"][k]) and got["n_kept"] == int(k.sum())
+    mine = format_hamming(s, q, got["tgt"], got["keep"], got["score"], got["diag"])
+    assert set(mine) == set(want[wrapped])
+    bad = [kk for kk in mine if mine[kk] != want[wrapped][kk]]
+    assert not bad, (len(bad), mine[bad[0]], want[wrapped][bad[0]])
+    assert int(k.sum()) > 9000 and (ref["score"] < 0).sum() > 500
+
+
+def test_hamming_rescore_on_ragged_sets_vs_oracle(ctx, oracle):
+    """same against the oracle on the device's own prefilter lines: reads with N and lower-case / IUPAC letters (byte path), a 70 kb and a
+    40 kb contig sharing a 30 kb overlap (diagonals beyond 16 bits), every coverage mode and identity mode, wrapped and not"""
+    import carpedeam_b200 as cd
+    rng = np.random.default_rng(77)
+    seqs = synth_reads(3000, 9000, 78, n_frac=0.002)
+    for i in range(0, 3000, 17):
+        b = bytearray(seqs[i]); b[len(b) // 2] = ord("acgtRYn"[i % 7]); seqs[i] = bytes(b)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    g = acgt[rng.integers(0, 4, 80000)]
+    seqs += [g[:70000].tobytes(), g[40000:80000].tobytes(), g[100:900].tobytes()]
+    s = SeqSet(seqs)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    hits = ctx.kmermatch(cd.kmer_params(k=17, kmers_per_seq=60))
+    assert len(hits["rep"]) > 3000
+    first = None
+    for wrapped in (0, 1):
+        for cov_mode, cov_thr, sid_mode, min_len in ((0, 0.8, 0, 0), (1, 0.5, 1, 0), (2, 0.5, 2, 40), (3, 0.6, 0, 0), (4, 0.6, 0, 0), (5, 0.7, 0, 0)):
+            got = ctx.rescore_hamming(cov_thr=cov_thr, cov_mode=cov_mode, min_seq_id=0.9, seq_id_mode=sid_mode, min_aln_len=min_len, wrapped=wrapped)
+            lo = got["line_off"].astype(np.int64)
+            q = np.repeat(np.arange(s.n, dtype=np.uint32), np.diff(lo))
+            if first is None:
+                first = (q, got["tgt"].copy())
+                # prefilter lines as cdg_rescore sees them: self line first, then the hits of the representative
+                sc = np.zeros(len(q), np.int32); dg = np.zeros(len(q), np.uint16)
+                hit_lines = q != got["tgt"]
+                assert hit_lines.sum() == len(hits["rep"])
+                sc[hit_lines] = hits["score"]; dg[hit_lines] = hits["diag"].astype(np.uint16)
+            ref = oracle.rescore_hamming(s, first[0], first[1], sc, dg, wrapped=wrapped, cov_thr=cov_thr, cov_mode=cov_mode, seqid_mode=sid_mode, aln_len_thr=min_len)
+            for f in ("keep", "score", "diag"):
+                assert np.array_equal(got[f], ref[f]), (wrapped, cov_mode, f)
+            assert ref["keep"].sum() > s.n
