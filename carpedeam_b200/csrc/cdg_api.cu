@@ -120,6 +120,7 @@ struct cdg_ctx {
     DevBuf dPairModel, dPairIn, dPairCons, dPairOut; bool pairModelSet = false;
     // contig-merge scores (N3)
     DevBuf dMergeLog; cdgmerge::MergeModel mergeModel; bool mergeModelSet = false;
+    u64 hScalars[64] = {0};   // host copy of the scalar block taken after sort 1 (km_sort_group)
 };
 
 namespace {
@@ -151,6 +152,7 @@ static cudaError_t cdg_launch_check(cdg_ctx *ctx) {
 // scalars block on the device: [0] scan total, [1] emitted records, [2] grouped count, [3] kept lines,
 // [4] changed bases, [5] (u32) extraCount, [6] (u32) overflow, [7] (u32) long count, [8] long scratch total, [9] (u32) sort ticket
 enum { SC_SCAN = 0, SC_EMIT, SC_GROUPED, SC_KEPT, SC_CHANGED, SC_EXTRA, SC_OVERFLOW, SC_NLONG, SC_LONGSCR, SC_TICKET, SC_WIDE, SC_QLIST, SC_PATCH, SC_SLOW, SC_RTOVF, SC_ROUTE /*16 counters*/, SC_BOUNDS = SC_ROUTE + 16 /*17 bounds*/, SC_N = SC_BOUNDS + 20 };
+static_assert(SC_N <= 64, "cdg_ctx::hScalars holds the scalar block");
 
 void rec(cdg_ctx *ctx, int e) { cudaEventRecord(ctx->ev[e], ctx->st); ctx->evValid[e] = true; }
 
@@ -632,13 +634,19 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
         if ((rc = read_scalar(ctx, SC_LONGSCR, &longScr))) return rc;
     }
     const u32 nLong = (u32) nLong64;
-    int perSm = 3;   // persistent grid: as many resident blocks as the registers allow
+    int perSm = 3;   // persistent grid: as many resident blocks as the registers allow (asked once per kernel variant)
     {
+        static int shortPerSm[3] = {0, 0, 0};
         const u32 maxW0 = ctx->maxLen >= (u32) p->k ? ctx->maxLen - p->k + 1 : 0;
-        if (maxW0 <= 64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, extract_short_kernel<2>, EX_WARPS * 32, 0);
-        else if (maxW0 <= 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, extract_short_kernel<4>, EX_WARPS * 32, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, extract_short_kernel<8>, EX_WARPS * 32, 0);
-        if (perSm < 1) perSm = 1;
+        const int v = maxW0 <= 64 ? 0 : (maxW0 <= 128 ? 1 : 2);
+        if (!shortPerSm[v]) {
+            int q = 0;
+            if (v == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, extract_short_kernel<2>, EX_WARPS * 32, 0);
+            else if (v == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, extract_short_kernel<4>, EX_WARPS * 32, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, extract_short_kernel<8>, EX_WARPS * 32, 0);
+            shortPerSm[v] = q < 1 ? 1 : q;
+        }
+        perSm = shortPerSm[v];
     }
     const int shortBlocks = ctx->smCount * perSm;
     static int groupPerSm[3] = {0, 0, 0};
@@ -732,12 +740,12 @@ static int km_sort_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K
     ctx->launches += l1 + l2; ctx->sort1Passes = plan1.n;
     CKL();
     rec(ctx, EV_SORT1);
-    u64 overflow = 0;
-    if ((rc = read_scalar(ctx, SC_OVERFLOW, &overflow))) return rc;
-    if ((u32) overflow) return fail(ctx, CDG_ERR_UNSUPPORTED, "identity-record overflow area exhausted");
+    // one host round trip for everything the host needs after sort 1: the scalar block (overflow flag, emitted / extra counts) and the smallest key
     u64 firstKey = CDG_SENTINEL;
+    CK(cudaMemcpyAsync(ctx->hScalars, sc, SC_N * 8, cudaMemcpyDeviceToHost, ctx->st));
     if (Rtot) CK(cudaMemcpyAsync(&firstKey, ctx->sortedMainK, 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
+    if ((u32) ctx->hScalars[SC_OVERFLOW]) return fail(ctx, CDG_ERR_UNSUPPORTED, "identity-record overflow area exhausted");
     if (minKeyOut) *minKeyOut = firstKey == CDG_SENTINEL ? CDG_SENTINEL : (firstKey | CDG_B63);
     if (quirkMode < 0) return 0;   // multi-GPU: the caller decides the first-run quirk after comparing the ranks' minima
     return 0;
@@ -985,6 +993,13 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     {   // number of hash-range passes: forced, or from the memory the unsplit arrays would need (kmermatcher.cpp:615-627)
         int M = p->split_passes;
         if (const char *e = getenv("CDG_FORCE_SPLITS")) { const int v = atoi(e); if (v > 0) M = v; }   // test knob
+        const u64 key2Each = (Rtot + n + CDG_HEAD_RUN) * 8;
+        // steady state (the same set again): every array the unsplit run needs is already allocated — no cudaMemGetInfo, which costs
+        // from a fraction of a millisecond to several milliseconds of host time per call depending on the box
+        if (M <= 0 && Rtot <= cdgsort::MAX_N && ctx->dKeysA.cap >= Rtot * 8 && ctx->dKeysB.cap >= Rtot * 8 && ctx->dValsA.cap >= Rtot * 8 &&
+            ctx->dValsB.cap >= Rtot * 8 && ctx->dKey2A.cap >= key2Each && ctx->dKey2B.cap >= key2Each &&
+            (!K.wide || (ctx->dKey2HiA.cap >= key2Each && ctx->dKey2HiB.cap >= key2Each)))
+            M = 1;
         if (M <= 0) {
             size_t freeB = 0, totalB = 0;
             CK(cudaMemGetInfo(&freeB, &totalB));
@@ -1012,9 +1027,8 @@ static int run_kmermatch(cdg_ctx *ctx, const cdg_kmer_params *p) {
     ctx->idSrcK = ctx->dIdKeysA.as<u64>(); ctx->idSrcV = ctx->dIdValsA.as<u64>(); ctx->idAltK = ctx->dIdKeysB.as<u64>(); ctx->idAltV = ctx->dIdValsB.as<u64>();
     u64 minKey = 0;
     if ((rc = km_sort_group(ctx, p, K, ctx->dKeysA.as<u64>(), ctx->dKeysB.as<u64>(), ctx->dValsA.as<u64>(), ctx->dValsB.as<u64>(), Rtot, 0, &minKey, nullptr))) return rc;
-    u64 emitted = 0, extra = 0, R2 = 0;
-    if ((rc = read_scalar(ctx, SC_EMIT, &emitted))) return rc;
-    if ((rc = read_scalar(ctx, SC_EXTRA, &extra))) return rc;
+    u64 R2 = 0;
+    const u64 emitted = ctx->hScalars[SC_EMIT], extra = ctx->hScalars[SC_EXTRA];   // (fetched by km_sort_group with the overflow flag)
     const bool mainNonEmpty = minKey != CDG_SENTINEL;
     if ((rc = km_group(ctx, p, K, Rtot, mainNonEmpty, !mainNonEmpty, &R2))) return rc;
     u64 ownedIds = n;   // every sequence owns one identity record when the hash range is full

@@ -754,12 +754,16 @@ CDG_D void member_diag(bool repRev, u32 repLen, u32 repPos, bool tRev, u32 tLen,
 static constexpr int GROUP_BLOCK = 256;
 static constexpr int GROUP_ITEMS = 8;
 static constexpr int GROUP_TILE = GROUP_BLOCK * GROUP_ITEMS;
+#define GP(i) ((i) + ((i) >> 3))   // shared-memory index of tile record i (one pad word per 8)
 template <bool WIDE = false>
 __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, u64 n,
                                                             const u32 *__restrict__ len, GroupParams G, u64 *__restrict__ out,
                                                             unsigned long long *__restrict__ outCount, u64 *__restrict__ outHi = nullptr) {
-    __shared__ u64 sKey[GROUP_TILE + 1];   // +1: the record after the tile (singleton test)
-    __shared__ u64 sVal[GROUP_TILE];
+    // blocked arrangement (thread t owns records [8t, 8t+8)) on 64-bit words: unpadded, the 32 lanes of a load hit 2 of the 16
+    // 8-byte bank pairs (16-way conflict, 3.7 x the ideal wavefronts in profiles/r01e_src_group_kernel.csv); one pad word per 8 records
+    // spreads them over all 16
+    __shared__ u64 sKey[GP(GROUP_TILE) + 2];   // + the record after the tile (singleton test)
+    __shared__ u64 sVal[GP(GROUP_TILE) + 2];
     __shared__ u32 shWarp[GROUP_BLOCK / 32 + 1];
     __shared__ u32 sWarpMax[GROUP_BLOCK / 32];
     __shared__ unsigned long long sBase;
@@ -767,9 +771,9 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u64 tileBase = (u64) blockIdx.x * GROUP_TILE;
     const u32 tileN = (u32) (n - tileBase < (u64) GROUP_TILE ? n - tileBase : (u64) GROUP_TILE);
-    for (u32 i = tid; i < tileN; i += GROUP_BLOCK) { sKey[i] = keys[tileBase + i]; sVal[i] = vals[tileBase + i]; }
+    for (u32 i = tid; i < tileN; i += GROUP_BLOCK) { sKey[GP(i)] = keys[tileBase + i]; sVal[GP(i)] = vals[tileBase + i]; }
     if (tid == 0) {
-        sKey[tileN] = tileBase + tileN < n ? keys[tileBase + tileN] : CDG_SENTINEL;
+        sKey[GP(tileN)] = tileBase + tileN < n ? keys[tileBase + tileN] : CDG_SENTINEL;
         // run open at the tile start: walk back to its head (one thread per tile, runs are short)
         u64 h = tileBase;
         if (tileBase > 0 && keys[tileBase] != CDG_SENTINEL) {   // (a tile inside the sentinel tail has nothing to find)
@@ -787,8 +791,8 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
     for (int j = 0; j < GROUP_ITEMS; j++) {
         const u32 li = first + j;
         if (li < tileN) {
-            const u64 k = sKey[li] | CDG_B63;
-            const bool head = li == 0 ? (sTileHead == tileBase) : ((sKey[li - 1] | CDG_B63) != k);
+            const u64 k = sKey[GP(li)] | CDG_B63;
+            const bool head = li == 0 ? (sTileHead == tileBase) : ((sKey[GP(li - 1)] | CDG_B63) != k);
             if (head) runMax = li + 1;
         }
         headOf[j] = runMax;
@@ -809,34 +813,41 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
     u32 outRep[WIDE ? GROUP_ITEMS : 1];
     u32 keep = 0;
     const int sh1 = G.diagBits + 1, sh2 = G.idBits + G.diagBits + 1;
+    u64 cHead = ~0ull, cRepKey = 0; u32 cRepId = 0, cRepPos = 0, cRepLen = 0;   // representative of the run of the previous record
 #pragma unroll
     for (int j = 0; j < GROUP_ITEMS; j++) {
         const u32 li = first + j;
         outKey[j] = 0;
         if (li >= tileN) continue;
-        const u64 k = sKey[li];
+        const u64 k = sKey[GP(li)];
         if (k == CDG_SENTINEL) continue;
         const u32 hl = max(headOf[j], carry);
         const u64 headIdx = hl ? tileBase + hl - 1 : sTileHead;
         const bool isHead = headIdx == tileBase + li;
-        if (isHead && (sKey[li + 1] == CDG_SENTINEL || (sKey[li + 1] | CDG_B63) != (k | CDG_B63))) continue;   // singleton (:476)
+        if (isHead && (sKey[GP(li + 1)] == CDG_SENTINEL || (sKey[GP(li + 1)] | CDG_B63) != (k | CDG_B63))) continue;   // singleton (:476)
         // representative = head record; repeats of the head's own sequence: smallest position (forward first)
-        auto keyAt = [&](u64 x) -> u64 { return (x >= tileBase && x < tileBase + tileN) ? sKey[x - tileBase] : (x < n ? keys[x] : CDG_SENTINEL); };
-        auto valAt = [&](u64 x) -> u64 { return (x >= tileBase && x < tileBase + tileN) ? sVal[x - tileBase] : vals[x]; };
-        u64 repKey = keyAt(headIdx), repVal = valAt(headIdx);
-        const u32 repId = cdg_val_id(repVal);
-        u32 repPos = cdg_val_pos(repVal);
-        for (u64 x = headIdx + 1; x < n; x++) {
-            const u64 kx = keyAt(x);
-            if (kx == CDG_SENTINEL || (kx | CDG_B63) != (k | CDG_B63)) break;
-            const u64 vx = valAt(x);
-            if (cdg_val_id(vx) != repId) break;
-            const u32 px = cdg_val_pos(vx);
-            if (px < repPos || (px == repPos && (kx & CDG_B63) > (repKey & CDG_B63))) { repPos = px; repKey = kx; }
+        auto keyAt = [&](u64 x) -> u64 { return (x >= tileBase && x < tileBase + tileN) ? sKey[GP((u32) (x - tileBase))] : (x < n ? keys[x] : CDG_SENTINEL); };
+        auto valAt = [&](u64 x) -> u64 { return (x >= tileBase && x < tileBase + tileN) ? sVal[GP((u32) (x - tileBase))] : vals[x]; };
+        // consecutive records of a thread mostly belong to the same run (coverage): the representative is looked up once per run
+        if (headIdx != cHead) {
+            cHead = headIdx;
+            cRepKey = keyAt(headIdx);
+            const u64 repVal = valAt(headIdx);
+            cRepId = cdg_val_id(repVal);
+            cRepPos = cdg_val_pos(repVal);
+            for (u64 x = headIdx + 1; x < n; x++) {
+                const u64 kx = keyAt(x);
+                if (kx == CDG_SENTINEL || (kx | CDG_B63) != (k | CDG_B63)) break;
+                const u64 vx = valAt(x);
+                if (cdg_val_id(vx) != cRepId) break;
+                const u32 px = cdg_val_pos(vx);
+                if (px < cRepPos || (px == cRepPos && (kx & CDG_B63) > (cRepKey & CDG_B63))) { cRepPos = px; cRepKey = kx; }
+            }
+            cRepLen = len[cRepId];
         }
-        const u32 repLen = len[repId];
+        const u64 repKey = cRepKey; const u32 repId = cRepId, repPos = cRepPos, repLen = cRepLen;
         const bool repRev = (G.firstRunQuirk && headIdx == 0) ? false : ((repKey & CDG_B63) == 0);
-        const u64 v = sVal[li];
+        const u64 v = sVal[GP(li)];
         const u32 id = cdg_val_id(v), tl = len[id];
         i32 d; bool need;
         member_diag(repRev, repLen, repPos, (k & CDG_B63) == 0, tl, cdg_val_pos(v), d, need);
@@ -849,10 +860,14 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
     u32 blockTotal;
     const u32 myOff = cdgscan::block_excl_scan((u32) __popc(keep), &blockTotal, shWarp);
     if (tid == 0) sBase = blockTotal ? atomicAdd(outCount, (unsigned long long) blockTotal) : 0ull;
-    __syncthreads();
-    u64 dst = sBase + myOff;
+    // the kept records go through shared memory (every thread is past its last read of the tile: the scan has barriers) so that the
+    // block writes one contiguous, coalesced run instead of 8-byte stores 64 bytes apart
+    u32 o = myOff;
 #pragma unroll
-    for (int j = 0; j < GROUP_ITEMS; j++) if (keep & (1u << j)) { if (WIDE) outHi[dst] = outRep[j]; out[dst++] = outKey[j]; }
+    for (int j = 0; j < GROUP_ITEMS; j++) if (keep & (1u << j)) { if (WIDE) sVal[GP(o)] = outRep[j]; sKey[GP(o)] = outKey[j]; o++; }
+    __syncthreads();
+    const u64 dst = sBase;
+    for (u32 i = tid; i < blockTotal; i += GROUP_BLOCK) { out[dst + i] = sKey[GP(i)]; if (WIDE) outHi[dst + i] = sVal[GP(i)]; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -986,13 +1001,27 @@ __global__ void __launch_bounds__(RED_BLOCK) reduce_kernel(PairEndFlag f, Reduce
     u32 pairHeads = 0, runHeads = 0, pairEnds = 0, runEnds = 0;
     u64 v1[RED_ITEMS];
     u32 headOf[RED_ITEMS]; u32 runMax = 0;   // tile-local index + 1 of the pair head, 0 = before the tile
+    // the thread's 8 consecutive records as four 128-bit loads (lane stride 64 B: 4-way conflicts per quarter warp, 16 wavefronts per
+    // load) instead of eight 64-bit loads with a 16-way conflict each (32 wavefronts per load: profiles/r01e_src_reduce_kernel.csv had
+    // 3 x the ideal shared-memory wavefronts); the neighbours' edge records come by shuffle
+    static_assert(RED_ITEMS == 8, "reduce_kernel loads 8 records per thread as 4 x 16 bytes");
+    u64 kk[RED_ITEMS + 2];   // kk[0] = record before the thread's first, kk[1..8] = its records, kk[9] = record after its last
+    {
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(sKey + 1 + first);
+#pragma unroll
+        for (int j = 0; j < RED_ITEMS / 2; j++) { const ulonglong2 t2 = src[j]; kk[1 + 2 * j] = t2.x; kk[2 + 2 * j] = t2.y; }
+        const u64 up = __shfl_up_sync(0xffffffffu, kk[RED_ITEMS], 1), down = __shfl_down_sync(0xffffffffu, kk[1], 1);
+        kk[0] = lane > 0 ? up : sKey[first];
+        kk[RED_ITEMS + 1] = lane < 31 ? down : sKey[first + RED_ITEMS + 1];
+    }
+    auto pairOf = [&](u64 k) -> u64 { return k == NONE ? NONE : (k >> pairShift); };
 #pragma unroll
     for (int j = 0; j < RED_ITEMS; j++) {
         const u32 li = first + j;
         v1[j] = 0;
         if (li < tileN) {
-            const u64 k = sKey[li + 1], kp = sKey[li], kn = sKey[li + 2];
-            const bool ph = pairAt(li) != pairAt(li + 1), pe = pairAt(li + 2) != pairAt(li + 1);
+            const u64 k = kk[j + 1], kp = kk[j], kn = kk[j + 2];
+            const bool ph = WIDE ? pairAt(li) != pairAt(li + 1) : pairOf(kp) != pairOf(k), pe = WIDE ? pairAt(li + 2) != pairAt(li + 1) : pairOf(kn) != pairOf(k);
             const bool rh = ph || ((kp >> 1) & diagMask) != ((k >> 1) & diagMask);
             const bool re = pe || ((kn >> 1) & diagMask) != ((k >> 1) & diagMask);
             pairHeads |= ph ? 1u << j : 0; runHeads |= rh ? 1u << j : 0; pairEnds |= pe ? 1u << j : 0; runEnds |= re ? 1u << j : 0;
