@@ -15,15 +15,28 @@ namespace cdgalign {
 // Queries [qLo, qLo+n) (multi-GPU: the rank's query range; single GPU: all); lineOff is indexed by q - qLo.
 __global__ void __launch_bounds__(256) lines_self_kernel(const u32 *__restrict__ hitRep, u64 H, u64 qLo, u64 n, u64 *__restrict__ lineOff,
                                                          u32 *__restrict__ lineQ, u32 *__restrict__ lineT, i32 *__restrict__ linePref,
-                                                         u16 *__restrict__ lineDiag) {
-    u64 ql = (u64) blockIdx.x * blockDim.x + threadIdx.x;
-    if (ql > n) return;
-    const u64 q = qLo + ql;
-    u64 lo = 0, hi = H;
-    while (lo < hi) { u64 mid = (lo + hi) >> 1; if (hitRep[mid] < q) lo = mid + 1; else hi = mid; }
-    u64 l = ql + lo;
-    lineOff[ql] = l;
-    if (ql < n) { lineQ[l] = (u32) q; lineT[l] = (u32) q; linePref[l] = 0; lineDiag[l] = 0; }
+                                                         u16 *__restrict__ lineDiag, u32 *__restrict__ multiList = nullptr, u32 *__restrict__ multiCount = nullptr) {
+    const u64 ql = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    bool multi = false;
+    if (ql <= n) {
+        const u64 q = qLo + ql;
+        u64 lo = 0, hi = H;
+        while (lo < hi) { u64 mid = (lo + hi) >> 1; if (hitRep[mid] < q) lo = mid + 1; else hi = mid; }
+        u64 l = ql + lo;
+        lineOff[ql] = l;
+        if (ql < n) { lineQ[l] = (u32) q; lineT[l] = (u32) q; linePref[l] = 0; lineDiag[l] = 0; multi = lo < H && hitRep[lo] == q; }
+    }
+    // the queries with more than one line (= at least one hit), for the correction: what multi_line_queries_kernel would list
+    if (multiList) {
+        const u32 b = __ballot_sync(0xffffffffu, multi);
+        if (b) {
+            const int lane = threadIdx.x & 31;
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(multiCount, (u32) __popc(b));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (multi) multiList[base + __popc(b & ((1u << lane) - 1))] = (u32) ql;
+        }
+    }
 }
 __global__ void __launch_bounds__(256) lines_hits_kernel(const u32 *__restrict__ hitRep, const u32 *__restrict__ hitTgt,
                                                          const i32 *__restrict__ hitScore, const i32 *__restrict__ hitDiag, u64 H, u64 qLo,

@@ -120,6 +120,7 @@ struct cdg_ctx {
     DevBuf dPairModel, dPairIn, dPairCons, dPairOut; bool pairModelSet = false;
     // contig-merge scores (N3)
     DevBuf dMergeLog; cdgmerge::MergeModel mergeModel; bool mergeModelSet = false;
+    bool qListValid = false;  // dQList / SC_QLIST hold the multi-line queries of the current lines
     u64 hScalars[64] = {0};   // host copy of the scalar block taken after sort 1 (km_sort_group)
 };
 
@@ -432,6 +433,7 @@ static int upload_impl(cdg_ctx *ctx, const uint8_t *data, uint64_t data_bytes, c
     unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
     CK(cudaMemsetAsync(sc + SC_WIDE, 0, 8, ctx->st));
     CK(cudaMemsetAsync(sc + SC_QLIST, 0, 8, ctx->st));
+    ctx->qListValid = false;
     max_len_kernel<<<ctx->smCount * 4, 256, 0, ctx->st>>>(ctx->dLen.as<u32>(), n, (u32 *) (sc + SC_WIDE));
     // entries must lie inside the data (the kernels index with them); entries that are not in index order are fine for
     // everything except the per-range exports of the multi-GPU phases (cdg_mg_finish)
@@ -722,6 +724,28 @@ static int km_extract(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u
     return 0;
 }
 
+// The identity array is sorted by key bits [ID_SORT_LO, 63) only; this orders what is left: one thread per run of records that agree in
+// those bits.  Runs of true duplicates (equal keys) are only read; a run that mixes keys (a 40-bit collision of two 64-bit hashes) is
+// insertion-sorted in place by the low bits — stable, like the radix passes, so the result is the full 63-bit stable sort.
+static constexpr int ID_SORT_LO = 23;
+__global__ void __launch_bounds__(256) id_fixup_kernel(u64 *__restrict__ keys, u64 *__restrict__ vals, u64 n, int lo) {
+    const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 lowMask = (1ull << lo) - 1, hiMask = ~lowMask & ~CDG_B63;
+    const u64 k = keys[i];
+    if (k == CDG_SENTINEL) return;   // the unowned tail (hash-range calls): one long run of equal keys
+    if (i > 0 && ((keys[i - 1] ^ k) & hiMask) == 0) return;   // not the head of its run
+    u64 j = i + 1; bool mixed = false;
+    while (j < n && ((keys[j] ^ k) & hiMask) == 0) { mixed = mixed || ((keys[j] ^ k) & lowMask) != 0; j++; }
+    if (!mixed) return;
+    for (u64 a = i + 1; a < j; a++) {
+        const u64 ka = keys[a], va = vals[a];
+        u64 b = a;
+        while (b > i && (keys[b - 1] & lowMask) > (ka & lowMask)) { keys[b] = keys[b - 1]; vals[b] = vals[b - 1]; b--; }
+        keys[b] = ka; vals[b] = va;
+    }
+}
+
 // sort 1 (main array of Rtot records in (ka,va) with partner (kb,vb); identity array of n records) + group -> key2 in dKey2A
 static int km_sort_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64 *ka, u64 *kb, u64 *va, u64 *vb, u64 Rtot, int quirkMode,
                          u64 *minKeyOut, u64 *R2out) {
@@ -734,9 +758,14 @@ static int km_sort_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K
     cdgsort::Plan plan1 = cdgsort::make_plan(0, 0, 0, 2 * p->k);
     int l1 = cdgsort::radix_sort(ctx->st, ws, ka, kb, va, vb, Rtot, plan1, &ctx->sortedMainK, &ctx->sortedMainV, ctx->smCount, -1, ctx->passEv);
     ctx->passEvN = plan1.n; ctx->sort1Records = Rtot;
-    cdgsort::Plan planI = cdgsort::make_plan(0, 0, 0, 63);
+    // identity records (64-bit hashes, one per sequence): five passes over key bits [23, 63) and a fix-up of the (expected: n^2 / 2^41)
+    // runs that agree in those 40 bits but not below, instead of eight passes over all 63 bits
+    int idLo = ID_SORT_LO;
+    if (const char *e = getenv("CDG_ID_SORT_LO")) { const int v = atoi(e); if (v >= 0 && v < 63) idLo = v; }   // test knob: a high value sends every run through the fix-up
+    cdgsort::Plan planI = cdgsort::make_plan(0, 0, idLo, 63);
     int l2 = cdgsort::radix_sort(ctx->st, ws, ctx->idSrcK, ctx->idAltK, ctx->idSrcV, ctx->idAltV, ctx->nIdent, planI, &ctx->sortedIdK, &ctx->sortedIdV, ctx->smCount);
     if (l1 < 0 || l2 < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "radix sort: input too large for one pass set");
+    if (ctx->nIdent) { id_fixup_kernel<<<(unsigned) ((ctx->nIdent + 255) / 256), 256, 0, ctx->st>>>(ctx->sortedIdK, ctx->sortedIdV, ctx->nIdent, idLo); l2++; }
     ctx->launches += l1 + l2; ctx->sort1Passes = plan1.n;
     CKL();
     rec(ctx, EV_SORT1);
@@ -827,7 +856,9 @@ static int km_reduce(cdg_ctx *ctx, const KmPlan &K, u64 nOwn, u64 nTotal) {
         u64 tiles = cdgscan::tiles_for(nTotal);
         CK(ctx->dTileSums.reserve((tiles + 1) * 8));
         unsigned long long *ts = ctx->dTileSums.as<unsigned long long>();
-        cdgscan::tile_sum_kernel<<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, nTotal, ts);
+        if (!K.wide && (((unsigned long long) f.keys) & 15ull) == 0)
+            pair_end_count_kernel<<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f.keys, nTotal, nOwn, K.idBits, K.diagBits, ts);
+        else cdgscan::tile_sum_kernel<<<(unsigned) tiles, cdgscan::BLOCK, 0, ctx->st>>>(f, nTotal, ts);
         cdgscan::tile_scan_kernel<<<1, 1024, 0, ctx->st>>>(ts, tiles, sc + SC_SCAN);
         ctx->launches += 2;
         if ((rc = read_scalar(ctx, SC_SCAN, &H))) return rc;
@@ -1097,9 +1128,14 @@ static int build_lines_from_hits(cdg_ctx *ctx) {
     const u64 nQ = ctx->nQ, qLo = ctx->qLo, H = ctx->nHits, M = nQ + H;
     int rc = reserve_lines(ctx, M);
     if (rc) return rc;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    CK(ctx->dQList.reserve((nQ + 1) * 4));
+    CK(cudaMemsetAsync(sc + SC_QLIST, 0, 8, ctx->st));
     cdgalign::lines_self_kernel<<<(unsigned) ((nQ + 1 + 255) / 256), 256, 0, ctx->st>>>(ctx->dHitRep.as<u32>(), H, qLo, nQ, ctx->dLineOff.as<u64>(),
                                                                                         ctx->dLineQ.as<u32>(), ctx->dLineT.as<u32>(),
-                                                                                        ctx->dLinePref.as<i32>(), ctx->dLineDiag.as<u16>());
+                                                                                        ctx->dLinePref.as<i32>(), ctx->dLineDiag.as<u16>(),
+                                                                                        ctx->dQList.as<u32>(), (u32 *) (sc + SC_QLIST));
+    ctx->qListValid = true;   // run_correct takes the list of multi-line queries from here
     ctx->launches++;
     if (H) {
         cdgalign::lines_hits_kernel<<<(unsigned) ((H + 255) / 256), 256, 0, ctx->st>>>(ctx->dHitRep.as<u32>(), ctx->dHitTgt.as<u32>(), ctx->dHitScore.as<i32>(),
@@ -1144,7 +1180,7 @@ extern "C" int cdg_set_pref_lines(cdg_ctx *ctx, const uint64_t *line_off, uint64
     ctx->launches++;
     CKL();
     CK(cudaStreamSynchronize(ctx->st));
-    ctx->nLines = n_lines; ctx->linesValid = true; ctx->alnsValid = false; ctx->qLo = 0; ctx->nQ = ctx->n;
+    ctx->nLines = n_lines; ctx->linesValid = true; ctx->alnsValid = false; ctx->qLo = 0; ctx->nQ = ctx->n; ctx->qListValid = false;
     return CDG_OK;
 }
 
@@ -1390,6 +1426,7 @@ extern "C" int cdg_set_alignments(cdg_ctx *ctx, const uint64_t *aln_off, uint64_
     }
     CK(cudaStreamSynchronize(ctx->st));
     ctx->nLines = n_alns; ctx->linesValid = false; ctx->hitsValid = false; ctx->alnsValid = true; ctx->alnsFromText = true; ctx->qLo = 0; ctx->nQ = ctx->n;
+    ctx->qListValid = false;
     return CDG_OK;
 }
 
@@ -1425,11 +1462,14 @@ static int run_correct(cdg_ctx *ctx, const cdg_corr_params *p, uint8_t *out_data
     const u64 wideCap = ctx->wideThreshold < 65535 ? ctx->n + 16 : (ctx->nLines >> 16) + 16;
     CK(ctx->dWideList.reserve(wideCap * 4));
     CK(cudaMemsetAsync(sc + SC_WIDE, 0, 8, ctx->st));
-    CK(ctx->dQList.reserve((n + 1) * 4));
-    CK(cudaMemsetAsync(sc + SC_QLIST, 0, 8, ctx->st));
-    if (n) cdgalign::multi_line_queries_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dLineOff.as<u64>(), n, ctx->dQList.as<u32>(), (u32 *) (sc + SC_QLIST));
-    ctx->launches++;
-    CKL();
+    if (!ctx->qListValid) {   // (lines built from the hit list come with their list: build_lines_from_hits)
+        CK(ctx->dQList.reserve((n + 1) * 4));
+        CK(cudaMemsetAsync(sc + SC_QLIST, 0, 8, ctx->st));
+        if (n) cdgalign::multi_line_queries_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->st>>>(ctx->dLineOff.as<u64>(), n, ctx->dQList.as<u32>(), (u32 *) (sc + SC_QLIST));
+        ctx->launches++;
+        CKL();
+    }
+    ctx->qListValid = false;   // consumed: SC_QLIST is shared scratch
     // per-line part of pass 2 (RY identity, thresholds, mismatch columns): one thread per line
     const u64 M = ctx->nLines;
     CK(ctx->dPrep.reserve(M + 1)); CK(ctx->dAlnLen.reserve((M + 1) * 4)); CK(ctx->dMism.reserve((M + 1) * 24));

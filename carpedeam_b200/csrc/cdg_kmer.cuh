@@ -891,6 +891,33 @@ struct PairEndFlag {
     }
 };
 
+// tile sums of PairEndFlag for one-word records: 128-bit loads (two records per thread and load), the record after the pair by shuffle
+// — the generic tile_sum_kernel evaluates the functor per record and loads every key twice
+__global__ void __launch_bounds__(cdgscan::BLOCK) pair_end_count_kernel(const u64 *__restrict__ keys /*16-byte aligned*/, u64 n, u64 nOwn, int idBits, int diagBits,
+                                                                        unsigned long long *__restrict__ tileSums) {
+    __shared__ u32 shWarp[cdgscan::BLOCK / 32 + 1];
+    const int lane = threadIdx.x & 31;
+    const u64 base = (u64) blockIdx.x * cdgscan::TILE;
+    const int sh = diagBits + 1;
+    const u64 idMask = (1ull << idBits) - 1;
+    u32 s = 0;
+#pragma unroll
+    for (int j = 0; j < cdgscan::ITEMS / 2; j++) {
+        const u64 i = base + 2ull * (u64) (j * cdgscan::BLOCK + threadIdx.x);   // records i, i + 1
+        u64 k0 = 0, k1 = 0;
+        if (i + 1 < n) { const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(keys + i); k0 = t.x; k1 = t.y; }
+        else if (i < n) k0 = keys[i];
+        u64 k2 = __shfl_down_sync(0xffffffffu, k0, 1);
+        if (lane == 31) k2 = i + 2 < n ? keys[i + 2] : 0;
+        const u64 p0 = k0 >> sh, p1 = k1 >> sh, p2 = k2 >> sh;
+        if (i < nOwn && !(i + 1 < n && p1 == p0) && (u32) (p0 & idMask) != (u32) (p0 >> idBits)) s++;
+        if (i + 1 < nOwn && !(i + 2 < n && p2 == p1) && (u32) (p1 & idMask) != (u32) (p1 >> idBits)) s++;
+    }
+    u32 tot;
+    cdgscan::block_excl_scan(s, &tot, shWarp);
+    if (threadIdx.x == 0) tileSums[blockIdx.x] = tot;
+}
+
 // sequential replay of the reference's walk (kmermatcher.cpp:886-905) from the first record `s` of a pair; used for
 // pairs that start before the tile and for pairs whose target-id run bleeds into the next representative
 CDG_D void reduce_walk(const PairEndFlag &f, u64 n, u64 s, const ReduceParams &R, u32 &top, i32 &best, bool &brev) {

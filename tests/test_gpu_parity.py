@@ -1092,3 +1092,20 @@ def test_hamming_rescore_on_ragged_sets_vs_oracle(ctx, oracle):
             for f in ("keep", "score", "diag"):
                 assert np.array_equal(got[f], ref[f]), (wrapped, cov_mode, f)
             assert ref["keep"].sum() > s.n
+
+
+@pytest.mark.parametrize("lo", [55, 40])
+def test_identity_sort_fixup_orders_mixed_runs(ctx, oracle, monkeypatch, lo):
+    """the identity records are radix-sorted by key bits [23, 63) and the runs that agree there but not below are ordered by a fix-up
+    kernel: with the test knob CDG_ID_SORT_LO the radix part shrinks to a few bits, so that every run is mixed and goes through the
+    fix-up (duplicated sequences included: equal full keys must keep their (length desc, id asc) order) — the hit list must not change"""
+    import carpedeam_b200 as cd
+    seqs = synth_reads(3000, 6000, 123)
+    seqs += seqs[100:400] + seqs[100:200]      # identical sequences: identity groups of 2 and 3
+    s = SeqSet(seqs)
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    monkeypatch.setenv("CDG_ID_SORT_LO", str(lo))
+    got = ctx.kmermatch()
+    monkeypatch.delenv("CDG_ID_SORT_LO")
+    _hits_equal(got, ctx.kmermatch())
+    _hits_equal(got, oracle.kmermatch(s))
