@@ -35,13 +35,13 @@ def build(force=False, verbose=False):
         hsrc = sorted(os.path.join(hsrc_dir, f) for f in os.listdir(hsrc_dir) if f.endswith(".cpp") and not f.startswith("main_"))
         hdeps = [os.path.join(hsrc_dir, f) for f in os.listdir(hsrc_dir)]
         if hsrc and (force or not os.path.exists(HOST_LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(HOST_LIB_PATH) for d in hdeps)):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-o", HOST_LIB_PATH] + hsrc, check=True)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-o", HOST_LIB_PATH] + hsrc + ["-lz"], check=True)
         # the drop-in stage binary (same sub-commands and DB arguments as the reference's modules)
         msrc = os.path.join(hsrc_dir, "main_stages.cpp")
         if os.path.exists(msrc) and (force or not os.path.exists(STAGE_BIN) or any(os.path.getmtime(d) > os.path.getmtime(STAGE_BIN) for d in hdeps + [LIB_PATH])):
             os.makedirs(os.path.dirname(STAGE_BIN), exist_ok=True)
             subprocess.run(["g++", "-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-o", STAGE_BIN, msrc] + hsrc +
-                           ["-L" + HERE, "-lcarpedeam_gpu", "-Wl,-rpath," + HERE], check=True)
+                           ["-L" + HERE, "-lcarpedeam_gpu", "-lz", "-Wl,-rpath," + HERE], check=True)
     return LIB_PATH
 
 
@@ -138,6 +138,11 @@ class HammingOut(C.Structure):
                 ("keep", C.POINTER(C.c_uint8)), ("pref_score", C.POINTER(C.c_int32)), ("diag", C.POINTER(C.c_int32)), ("seq_id", C.POINTER(C.c_float))]
 
 
+class SeqSetC(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("data_bytes", C.c_uint64), ("header_bytes", C.c_uint64), ("total_residues", C.c_uint64), ("data", C.POINTER(C.c_uint8)),
+                ("offsets", C.POINTER(C.c_uint64)), ("lengths", C.POINTER(C.c_uint32)), ("headers", C.POINTER(C.c_uint8)), ("header_offsets", C.POINTER(C.c_uint64))]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_seqs", C.c_uint64), ("n_bases", C.c_uint64), ("n_records", C.c_uint64), ("n_grouped", C.c_uint64),
                 ("n_hits", C.c_uint64), ("n_alns", C.c_uint64), ("sort1_passes", C.c_uint32), ("sort2_passes", C.c_uint32),
@@ -200,6 +205,8 @@ def hostlib():
         H.cdh_build_merge_model.restype = C.c_int
         H.cdh_merge_less.argtypes = [C.c_uint32, C.c_float, C.c_uint32, C.c_float]; H.cdh_merge_less.restype = C.c_int
         H.cdh_merge_queue_order.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]; H.cdh_merge_queue_order.restype = None
+        H.cdh_createdb.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_char_p, C.POINTER(SeqSetC), C.c_char_p, C.c_size_t]; H.cdh_createdb.restype = C.c_int
+        H.cdh_free_seqset.argtypes = [C.POINTER(SeqSetC)]; H.cdh_free_seqset.restype = None
         H.cdh_packed_words.argtypes = [C.c_void_p, C.c_uint64]; H.cdh_packed_words.restype = C.c_uint64
         H.cdh_pack_seqs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
         H.cdh_pack_seqs.restype = C.c_int
@@ -281,6 +288,24 @@ def load_pair_model(prefix, seq_err=0.001, rand_align_penal=0.85, excess_penal=0
     if rc != 0:
         raise CdgError("damage profile: " + err.value.decode())
     return m
+
+
+def createdb(files, shuffle=True, out_db=None):
+    """FASTA / FASTQ [.gz] files -> (data u8, offsets u64[n], lengths u32[n], headers [bytes]) in the reference's createdb key order
+    (carpedeam_b200/host/createdb.cpp); with out_db also written as MMseqs2 database files"""
+    arr = (C.c_char_p * len(files))(*[f.encode() for f in files])
+    s = SeqSetC()
+    err = C.create_string_buffer(512)
+    if hostlib().cdh_createdb(arr, len(files), 1 if shuffle else 0, out_db.encode() if out_db else None, C.byref(s), err, 512) != 0:
+        raise CdgError("createdb: " + err.value.decode())
+    try:
+        n = int(s.n)
+        data = _view(s.data, s.data_bytes, np.uint8); off = _view(s.offsets, n + 1, np.uint64); lens = _view(s.lengths, n, np.uint32)
+        hb = _view(s.headers, s.header_bytes, np.uint8).tobytes(); ho = _view(s.header_offsets, n + 1, np.uint64)
+        headers = [hb[int(ho[i]):int(ho[i + 1]) - 2] for i in range(n)]
+    finally:
+        hostlib().cdh_free_seqset(C.byref(s))
+    return data, off[:n].copy(), lens, headers
 
 
 def load_merge_model(prefix):
