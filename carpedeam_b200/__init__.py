@@ -143,6 +143,14 @@ class SeqSetC(C.Structure):
                 ("offsets", C.POINTER(C.c_uint64)), ("lengths", C.POINTER(C.c_uint32)), ("headers", C.POINTER(C.c_uint8)), ("header_offsets", C.POINTER(C.c_uint64))]
 
 
+class CycleParams(C.Structure):
+    _fields_ = [("k", C.c_int32), ("max_seq_len", C.c_uint32)]
+
+
+class CycleOut(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("n_cyclic", C.c_uint64), ("n_kmers", C.c_uint64), ("split_diagonal", C.POINTER(C.c_uint32))]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_seqs", C.c_uint64), ("n_bases", C.c_uint64), ("n_records", C.c_uint64), ("n_grouped", C.c_uint64),
                 ("n_hits", C.c_uint64), ("n_alns", C.c_uint64), ("sort1_passes", C.c_uint32), ("sort2_passes", C.c_uint32),
@@ -519,6 +527,13 @@ class Context:
         M, n = o.n_lines, o.n_queries
         return dict(line_off=_view(o.line_off, n + 1, np.uint64), tgt=_view(o.target, M, np.uint32), keep=_view(o.keep, M, np.uint8),
                     score=_view(o.pref_score, M, np.int32), diag=_view(o.diag, M, np.int32), seqid=_view(o.seq_id, M, np.float32), n_kept=int(o.n_kept))
+
+    def cyclecheck(self, k=22, max_seq_len=200000):
+        """cdg_cyclecheck on the resident set -> split diagonal per sequence (0 = not circular)"""
+        p = CycleParams(k, max_seq_len)
+        o = CycleOut()
+        self._ck(lib().cdg_cyclecheck(self._h, C.byref(p), C.byref(o)), "cdg_cyclecheck")
+        return _view(o.split_diagonal, o.n, np.uint32)
 
     def set_merge_model(self, model):
         self._ck(lib().cdg_set_merge_model(self._h, C.byref(model)), "cdg_set_merge_model")

@@ -11,6 +11,7 @@
 #include "../../include/carpedeam_gpu.h"
 #include "cdg_align.cuh"
 #include "cdg_common.cuh"
+#include "cdg_cycle.cuh"
 #include "cdg_export.cuh"
 #include "cdg_ext.cuh"
 #include "cdg_hamming.cuh"
@@ -120,6 +121,7 @@ struct cdg_ctx {
     DevBuf dPairModel, dPairIn, dPairCons, dPairOut; bool pairModelSet = false;
     // contig-merge scores (N3)
     DevBuf dMergeLog; cdgmerge::MergeModel mergeModel; bool mergeModelSet = false;
+    DevBuf dCycleRecOff, dCycleDiagOff, dCycleHits, dCycleSplit;   // cdg_cyclecheck
     bool qListValid = false;  // dQList / SC_QLIST hold the multi-line queries of the current lines
     u64 hScalars[64] = {0};   // host copy of the scalar block taken after sort 1 (km_sort_group)
 };
@@ -1345,6 +1347,63 @@ extern "C" int cdg_rescore(cdg_ctx *ctx, const cdg_rescore_params *p, cdg_alns *
     rc = read_scalar(ctx, SC_KEPT, &kept);
     ctx->nKept = kept;
     return rc;
+}
+
+// ---- N3: cyclecheck (cdg_cycle.cuh) ------------------------------------------------------------------------------------------
+struct CycleWindowsF { const u32 *len; int k; u32 maxSeqLen; __device__ u32 operator()(u64 i) const { const u32 L = len[i]; return (L < maxSeqLen && L >= (u32) k) ? L - (u32) k + 1u : 0u; } };
+struct CycleDiagsF { const u32 *len; __device__ u32 operator()(u64 i) const { return 2u * (len[i] / 3u) + 1u; } };
+
+extern "C" int cdg_cyclecheck(cdg_ctx *ctx, const cdg_cycle_params *p, cdg_cycle_out *out) {
+    if (!ctx || !p || !out) return CDG_ERR_ARG;
+    if (ctx->n == 0) return fail(ctx, CDG_ERR_ARG, "cdg_cyclecheck: no resident sequence set");
+    if (p->k < 1 || p->k > 31) return fail(ctx, CDG_ERR_ARG, "cdg_cyclecheck: k = %d (1..31; the reference pins 22)", p->k);
+    CK(cudaSetDevice(ctx->device));
+    if (int rcb = ensure_bytes(ctx)) return rcb;
+    const u64 n = ctx->n;
+    unsigned long long *sc = ctx->dScalars.as<unsigned long long>();
+    int rc;
+    // record and diagonal-counter offsets per sequence
+    CK(ctx->dCycleRecOff.reserve((n + 1) * 8)); CK(ctx->dCycleDiagOff.reserve((n + 1) * 8)); CK(ctx->dCycleSplit.reserve((n + 1) * 4));
+    u64 R = 0, D = 0;
+    if ((rc = scan_to(ctx, CycleWindowsF{ctx->dLen.as<u32>(), p->k, p->max_seq_len}, n, ctx->dCycleRecOff.as<u64>(), true))) return rc;
+    if ((rc = read_scalar(ctx, SC_SCAN, &R))) return rc;
+    if ((rc = scan_to(ctx, CycleDiagsF{ctx->dLen.as<u32>()}, n, ctx->dCycleDiagOff.as<u64>(), true))) return rc;
+    if ((rc = read_scalar(ctx, SC_SCAN, &D))) return rc;
+    if (R > cdgsort::MAX_N) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_cyclecheck: %llu k-mers exceed one sort (2^32): call it per block of sequences", (unsigned long long) R);
+    CK(ctx->dKeysA.reserve((R + 1) * 8)); CK(ctx->dKeysB.reserve((R + 1) * 8)); CK(ctx->dValsA.reserve((R + 1) * 8)); CK(ctx->dValsB.reserve((R + 1) * 8));
+    CK(ctx->dCycleHits.reserve((D + 1) * 4));
+    CK(cudaMemsetAsync(ctx->dCycleHits.p, 0, (D + 1) * 4, ctx->st));
+    const unsigned wgrid = (unsigned) std::min<u64>((n * 32 + 255) / 256, (u64) ctx->smCount * 16);
+    if (R) {
+        cdgcycle::cycle_emit_kernel<<<wgrid, 256, 0, ctx->st>>>(ctx->dData.as<u8>(), ctx->dOff.as<u64>(), ctx->dLen.as<u32>(), n, p->k, p->max_seq_len,
+                                                               ctx->dCycleRecOff.as<u64>(), ctx->dKeysA.as<u64>(), ctx->dValsA.as<u64>());
+        ctx->launches++;
+        CKL();
+        cdgsort::Workspace ws;
+        if ((rc = sort_ws(ctx, R, ws))) return rc;
+        // k-mer index < 5 * 4^k / 3 (letters 0..4): 2k + 1 key bits
+        cdgsort::Plan plan = cdgsort::make_plan(0, 0, 0, 2 * p->k + 1);
+        u64 *sk = nullptr, *sv = nullptr;
+        const int l = cdgsort::radix_sort(ctx->st, ws, ctx->dKeysA.as<u64>(), ctx->dKeysB.as<u64>(), ctx->dValsA.as<u64>(), ctx->dValsB.as<u64>(), R, plan, &sk, &sv, ctx->smCount);
+        if (l < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_cyclecheck: radix sort: input too large for one pass set");
+        ctx->launches += l;
+        cdgcycle::cycle_match_kernel<<<(unsigned) ((R + 255) / 256), 256, 0, ctx->st>>>(sk, sv, R, ctx->dLen.as<u32>(), ctx->dCycleDiagOff.as<u64>(), ctx->dCycleHits.as<u32>());
+        ctx->launches++;
+        CKL();
+    }
+    cdgcycle::cycle_band_kernel<<<wgrid, 256, 0, ctx->st>>>(ctx->dLen.as<u32>(), n, p->k, p->max_seq_len, ctx->dCycleDiagOff.as<u64>(), ctx->dCycleHits.as<u32>(),
+                                                           ctx->dCycleSplit.as<u32>());
+    ctx->launches++;
+    CKL();
+    CK(ctx->hExt.reserve(n * 4 + 16));
+    CK(cudaMemcpyAsync(ctx->hExt.p, ctx->dCycleSplit.p, n * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->hitsValid = false; ctx->linesValid = false;   // the record arrays of the k-mer matcher were reused
+    out->n = n; out->n_kmers = R; out->split_diagonal = ctx->hExt.as<u32>();
+    u64 nc = 0;
+    for (u64 i = 0; i < n; i++) nc += out->split_diagonal[i] != 0;
+    out->n_cyclic = nc;
+    return CDG_OK;
 }
 
 // ---- N4: rescorediagonal --rescore-mode 0 (linclust's Hamming pre-clustering), cdg_hamming.cuh ------------------------------------

@@ -302,6 +302,21 @@ typedef struct {               /* pinned host memory owned by the context, valid
 } cdg_merge_out;
 int cdg_merge_scores(cdg_ctx *ctx, const cdg_merge_params *p, cdg_merge_out *out);
 
+/* ---- cyclecheck (src/assembler/cyclecheck.cpp:31-269, called after every contig iteration: data/nuclassemble.sh:19-60) ----
+ * Per resident sequence shorter than max_seq_len: the diagonal at which it overlaps itself (a circular genome read past its start), or 0.
+ * k-mers (forward strand, windows with X included, Indexer.h:21-84) of the front / middle / back third are matched (first occurrence in the
+ * earlier part against all in the later part), hits counted per diagonal >= L/3, and the first diagonal whose 1 % band has more than 0.24
+ * hits per possible k-mer is reported (:212-236).  The host writes the reported entries (whole, or cut at the diagonal with --chop-cycle). */
+typedef struct {
+    int32_t k;                 /* 22 (setCycleCheckDefaults, cyclecheck.cpp:26-29) */
+    uint32_t max_seq_len;      /* --max-seq-len (200000 in the assembler workflow): longer sequences are skipped */
+} cdg_cycle_params;
+typedef struct {               /* pinned host memory owned by the context, valid until the next call */
+    uint64_t n, n_cyclic, n_kmers;
+    const uint32_t *split_diagonal;   /* per sequence, 0 = not reported */
+} cdg_cycle_out;
+int cdg_cyclecheck(cdg_ctx *ctx, const cdg_cycle_params *p, cdg_cycle_out *out);
+
 /* ---- rescorediagonal --rescore-mode 0 (linclust's Hamming pre-clustering) -------------------------------------
  * The HAMMING branch of doRescorediagonal (lib/mmseqs/src/alignment/rescorediagonal.cpp:194-334, :251-254, :323-329) over the prefilter lines
  * of the context (cdg_kmermatch, or cdg_set_pref_lines with a pref DB: lib/mmseqs/data/workflow/linclust.sh:28-32): number of equal

@@ -994,3 +994,84 @@ extern "C" void orc_rescore_hamming(const char *blob, const u64 *off, const u32 
         }
     }
 }
+
+// ---- cyclecheck (src/assembler/cyclecheck.cpp:31-269) ---------------------------------------------------------------
+// Per sequence: k-mers (k = 22, forward only, index = sum code_i * 4^i over the mapped letters, Indexer.h:21-84 — an X adds 4 * 4^i, so
+// windows with X are NOT skipped) in three parts by position, matches front x back, front x middle, middle x back of equal k-mers (first
+// occurrence of the k-mer in the earlier part against every occurrence in the later one) counted per diagonal >= L/3, and the first diagonal
+// whose 1 % band holds more than 0.24 hits per possible k-mer is where the sequence wraps around.
+// The part of a k-mer is decided with the iterator position BEFORE nextKmer() (:107-108: position - 1, UINT_MAX for the first k-mer, which
+// therefore lands in the back part), the stored position is the real one.
+// Pinned by tests/golden/cycle_kat.txt (chopped lengths written by the reference binary with --chop-cycle 1, oracle/make_cycle_golden.py).
+extern "C" void orc_cyclecheck(const char *blob, const u64 *off, const u32 *len, size_t n, int k, unsigned maxSeqLen, u32 *splitOut) {
+    struct KP { u64 kmer; unsigned pos; };
+    auto cmp = [](const KP &a, const KP &b) { return a.kmer != b.kmer ? a.kmer < b.kmer : a.pos < b.pos; };
+    std::vector<KP> front, middle, back;
+    std::vector<unsigned> diagHits;
+    for (size_t s = 0; s < n; s++) {
+        splitOut[s] = 0;
+        const unsigned seqLen = len[s];
+        if (seqLen >= maxSeqLen) continue;
+        const char *seq = blob + off[s];
+        front.clear(); middle.clear(); back.clear();
+        const unsigned third = seqLen / 3;
+        for (unsigned p = 0; p + (unsigned) k <= seqLen; p++) {
+            u64 idx = 0, pw = 1;
+            for (int i = 0; i < k; i++) { idx += (u64) map_letter((unsigned char) seq[p + i]) * pw; pw *= 4; }
+            const unsigned itPos = p - 1;   // getCurrentPosition() before nextKmer()
+            if (itPos < third + 1) front.push_back(KP{idx, p});
+            else if (itPos < 2 * third + 1) middle.push_back(KP{idx, p});
+            else back.push_back(KP{idx, p});
+        }
+        std::sort(front.begin(), front.end(), cmp); std::sort(middle.begin(), middle.end(), cmp); std::sort(back.begin(), back.end(), cmp);
+        unsigned kmermatches = 0;
+        diagHits.assign(2 * (size_t) third + 1, 0);
+        size_t idx = 0, jdx = 0, kdx = 0;
+        while (idx < front.size() && (jdx < back.size() || kdx < middle.size())) {
+            const u64 km = front[idx].kmer; const unsigned pos = front[idx].pos;
+            while (jdx < back.size() && back[jdx].kmer < km) jdx++;
+            while (kdx < middle.size() && middle[kdx].kmer < km) kdx++;
+            while (jdx < back.size() && km == back[jdx].kmer) {
+                int diag = (int) (back[jdx].pos - pos);
+                if (diag >= (int) (seqLen / 3)) { diagHits[diag - seqLen / 3]++; kmermatches++; }
+                jdx++;
+            }
+            while (kdx < middle.size() && km == middle[kdx].kmer) {
+                int diag = (int) (middle[kdx].pos - pos);
+                if (diag >= (int) (seqLen / 3)) { diagHits[diag - seqLen / 3]++; kmermatches++; }
+                kdx++;
+            }
+            idx++;
+            while (idx < front.size() && km == front[idx].kmer) idx++;
+        }
+        jdx = 0; kdx = 0;
+        while (kdx < middle.size() && jdx < back.size()) {
+            if (middle[kdx].kmer < back[jdx].kmer) kdx++;
+            else if (middle[kdx].kmer > back[jdx].kmer) jdx++;
+            else {
+                const u64 km = middle[kdx].kmer; const unsigned pos = middle[kdx].pos;
+                while (jdx < back.size() && km == back[jdx].kmer) {
+                    int diag = (int) (back[jdx].pos - pos);
+                    if (diag >= (int) (seqLen / 3)) { diagHits[diag - seqLen / 3]++; kmermatches++; }
+                    jdx++;
+                }
+                while (kdx < middle.size() && km == middle[kdx].kmer) kdx++;
+            }
+        }
+        unsigned split = 0;
+        if (kmermatches > 0) {
+            for (unsigned d = 0; d < 2 * third; d++) {
+                if (diagHits[d] == 0) continue;
+                const unsigned diag = d + third, diaglen = seqLen - diag;
+                const unsigned gapwindow = diaglen * 0.01;
+                const unsigned lower = std::max(0, static_cast<int>(d - gapwindow));
+                const unsigned upper = std::min(d + gapwindow, 2 * third);
+                unsigned band = 0;
+                for (size_t i = lower; i <= upper; i++) if (diagHits[i] <= diagHits[d]) band += diagHits[i];
+                const float rate = static_cast<float>(band) / (diaglen - (size_t) k + 1);
+                if (rate > 0.24) { split = diag; break; }
+            }
+        }
+        splitOut[s] = split;
+    }
+}

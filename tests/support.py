@@ -156,6 +156,17 @@ def check_merge_against_kat(aln_off, got, kat, deam_rtol):
     return n_queued, n_exact
 
 
+def load_cycle_kat():
+    """tests/golden/synth_cycle.gz + cycle_kat.txt (oracle/make_cycle_golden.py): sequence set and the split diagonal the reference's cyclecheck
+    reported per key (0 = not circular)"""
+    s = SeqSet.from_golden("synth_cycle", "")
+    want = np.zeros(s.n, np.uint32)
+    for line in open(os.path.join(GOLD, "cycle_kat.txt")):
+        k, d = line.split()
+        want[int(k)] = int(d)
+    return s, want
+
+
 def load_pairlik_kat():
     """tests/golden/pairlik_kat.txt (oracle/ref_pairlik.cpp): outputs of the reference's calcLikelihood[Consensus]."""
     out = []
@@ -249,6 +260,13 @@ class Oracle:
                                    C.c_void_p(t_idx.ctypes.data), C.c_void_p(pref_score.ctypes.data), C.c_void_p(diag16.ctypes.data), C.c_size_t(M),
                                    C.c_int(wrapped), C.c_float(cov_thr), C.c_int(cov_mode), C.c_float(seqid_thr), C.c_int(seqid_mode), C.c_int(aln_len_thr),
                                    *[C.c_void_p(out[k].ctypes.data) for k in ("keep", "score", "diag", "seqid")])
+        return out
+
+    def cyclecheck(self, s, k=22, max_seq_len=200000):
+        out = np.zeros(s.n, np.uint32)
+        self.L.orc_cyclecheck.restype = None
+        self.L.orc_cyclecheck(C.c_void_p(s.blob.ctypes.data), C.c_void_p(s.off.ctypes.data), C.c_void_p(s.len.ctypes.data), C.c_size_t(s.n), C.c_int(k),
+                              C.c_uint(max_seq_len), C.c_void_p(out.ctypes.data))
         return out
 
     def load_damage(self, prefix):

@@ -1109,3 +1109,19 @@ def test_identity_sort_fixup_orders_mixed_runs(ctx, oracle, monkeypatch, lo):
     monkeypatch.delenv("CDG_ID_SORT_LO")
     _hits_equal(got, ctx.kmermatch())
     _hits_equal(got, oracle.kmermatch(s))
+
+
+def test_cyclecheck_vs_reference(ctx, oracle):
+    """cdg_cyclecheck against the split diagonals the reference's cyclecheck reported (tests/golden/cycle_kat.txt, chopped entry
+    lengths of `carpedeam cyclecheck --chop-cycle 1`) on linear contigs, circular genomes read past their start (exact / mutated overlaps), tandem
+    repeats, homopolymers, N runs and sequences around the three-k-mer limit; and against the oracle with other k and a --max-seq-len that skips"""
+    from support import load_cycle_kat
+    s, want = load_cycle_kat()
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    got = ctx.cyclecheck()
+    assert np.array_equal(got, want), np.nonzero(got != want)[0][:10]
+    assert (want > 0).sum() > 50
+    for k, mx in ((22, 4000), (15, 200000), (27, 200000)):
+        assert np.array_equal(ctx.cyclecheck(k=k, max_seq_len=mx), oracle.cyclecheck(s, k=k, max_seq_len=mx)), (k, mx)
+    # the k-mer matcher still works on the same context afterwards (cyclecheck reuses its record arrays)
+    _hits_equal(ctx.kmermatch(), oracle.kmermatch(s))

@@ -57,3 +57,10 @@ def test_host_merge_model_matches_oracle_damage_tables(oracle):
     got = np.array(m.match_lik[:]).reshape(2, 4, 4)
     assert np.array_equal(got[0], np.asarray(D).reshape(11, 4, 4)[5]) and np.array_equal(got[1], np.asarray(Drev).reshape(11, 4, 4)[5])
     assert got[0][1][3] > 0 and got[0][2][0] > 0
+
+
+def test_oracle_cyclecheck_matches_reference_binary(oracle):
+    """the oracle's cyclecheck on the synthetic contig set == the split diagonals the reference binary reported (oracle/make_cycle_golden.py)"""
+    from support import load_cycle_kat
+    s, want = load_cycle_kat()
+    assert np.array_equal(oracle.cyclecheck(s), want) and (want > 0).sum() > 50
