@@ -51,7 +51,8 @@ class CdgError(RuntimeError):
 
 class KmerParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("kmers_per_seq", C.c_int32), ("kmers_per_seq_scale", C.c_float), ("hash_shift", C.c_uint64),
-                ("include_only_extendable", C.c_int32), ("hash_lo", C.c_uint32), ("hash_hi", C.c_uint32), ("split_passes", C.c_int32)]
+                ("include_only_extendable", C.c_int32), ("hash_lo", C.c_uint32), ("hash_hi", C.c_uint32), ("split_passes", C.c_int32),
+                ("cov_thr", C.c_float), ("cov_mode", C.c_int32)]
 
 
 class Hits(C.Structure):
@@ -274,8 +275,9 @@ def _view(ptr, n, dtype):
     return np.ctypeslib.as_array(ptr, shape=(int(n),)).view(dtype).copy()
 
 
-def kmer_params(k=20, kmers_per_seq=200, scale=0.2, hash_shift=67, include_only_extendable=0, hash_lo=0, hash_hi=65535, split_passes=0):
-    return KmerParams(k, kmers_per_seq, scale, hash_shift, include_only_extendable, hash_lo, hash_hi, split_passes)
+def kmer_params(k=20, kmers_per_seq=200, scale=0.2, hash_shift=67, include_only_extendable=0, hash_lo=0, hash_hi=65535, split_passes=0, cov_thr=0.0,
+                cov_mode=1):
+    return KmerParams(k, kmers_per_seq, scale, hash_shift, include_only_extendable, hash_lo, hash_hi, split_passes, cov_thr, cov_mode)
 
 
 def load_damage(prefix, seq_err=0.01):

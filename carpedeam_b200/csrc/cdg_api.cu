@@ -796,7 +796,7 @@ static int km_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64
     if (!append) CK(cudaMemsetAsync(sc + SC_GROUPED, 0, 8, ctx->st));
     const u64 *mainK = ctx->sortedMainK + mainSkip, *mainV = ctx->sortedMainV + mainSkip;
     Rtot -= mainSkip;
-    GroupParams G; G.idBits = K.idBits; G.diagBits = K.diagBits; G.diagBias = (i32) ctx->maxLen; G.onlyExtendable = p->include_only_extendable;
+    GroupParams G; G.idBits = K.idBits; G.diagBits = K.diagBits; G.diagBias = (i32) ctx->maxLen; G.onlyExtendable = p->include_only_extendable; G.covThr = p->cov_thr; G.covMode = p->cov_mode;
     G.firstRunQuirk = mainHasGlobalFirstRun ? 1 : 0;   // kmermatcher.cpp:466: only the globally first run
     if (Rtot && K.wide) group_kernel<true><<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(mainK, mainV, Rtot, ctx->dLen.as<u32>(), G,
                                                                                                                     ctx->dKey2A.as<u64>(), sc + SC_GROUPED, ctx->dKey2HiA.as<u64>());
@@ -990,7 +990,7 @@ static int run_kmermatch_split(cdg_ctx *ctx, const cdg_kmer_params *p, const KmP
     // 3. the first runs; the quirk goes to the range with the smallest key (ties cannot happen: a k-mer has one hash)
     int rStar = -1;
     for (int r = 0; r < M; r++) if (minKey[r] != CDG_SENTINEL && (rStar < 0 || minKey[r] < minKey[rStar])) rStar = r;
-    GroupParams G; G.idBits = K.idBits; G.diagBits = K.diagBits; G.diagBias = (i32) ctx->maxLen; G.onlyExtendable = p->include_only_extendable;
+    GroupParams G; G.idBits = K.idBits; G.diagBits = K.diagBits; G.diagBias = (i32) ctx->maxLen; G.onlyExtendable = p->include_only_extendable; G.covThr = p->cov_thr; G.covMode = p->cov_mode;
     for (int r = 0; r < M; r++) {
         if (!runLen[r]) continue;
         G.firstRunQuirk = r == rStar ? 1 : 0;

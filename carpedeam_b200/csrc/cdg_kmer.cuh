@@ -729,7 +729,20 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(const u64 *__restric
 //   key2 = rep << (idBits + diagBits + 1) | id << (diagBits + 1) | (diag + diagBias) << 1 | needRev
 struct GroupParams {
     int idBits, diagBits; i32 diagBias; int onlyExtendable; int firstRunQuirk;   // :466 first run: repIsReverse=false
+    float covThr; int covMode;   // Util::canBeCovered(covThr, covMode, repLen, memberLen), applied when !onlyExtendable (:526-529)
 };
+// Util::canBeCovered (lib/mmseqs/src/commons/Util.cpp:533-550)
+CDG_D bool can_be_covered(float covThr, int covMode, float q, float t) {
+    switch (covMode) {
+        case 0: return (q / t >= covThr) && (t / q >= covThr);
+        case 1: return (q / t) >= covThr;
+        case 2: return (t / q) >= covThr;
+        case 3: return ((t / q) >= covThr) && (t / q) <= 1.0f;
+        case 4: return ((q / t) >= covThr) && (q / t) <= 1.0f;
+        case 5: return (fminf(t, q) / fmaxf(t, q)) >= covThr;
+        default: return true;
+    }
+}
 // WIDE records (2*idBits + diagBits + 1 > 64, e.g. 5*10^7 sequences with contigs of 10 kb and more): two words per member,
 //   lo = id << (diagBits + 1) | (diag + diagBias) << 1 | needRev,   hi = rep
 // sorted as (lo bits, then hi bits) by two pair sorts; the (rep,id) pair = hi << idBits | lo >> (diagBits + 1) still fits 64 bits.
@@ -851,7 +864,7 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
         const u32 id = cdg_val_id(v), tl = len[id];
         i32 d; bool need;
         member_diag(repRev, repLen, repPos, (k & CDG_B63) == 0, tl, cdg_val_pos(v), d, need);
-        if (G.onlyExtendable && !(d < 0 || d > (i32) repLen - (i32) tl)) continue;   // :526-536
+        if (G.onlyExtendable ? !(d < 0 || d > (i32) repLen - (i32) tl) : !can_be_covered(G.covThr, G.covMode, (float) repLen, (float) tl)) continue;   // :526-536
         outKey[j] = (WIDE ? 0ull : ((u64) repId << sh2)) | ((u64) id << sh1) | ((u64) (u32) (d + G.diagBias) << 1) | (need ? 1ull : 0ull);
         if (WIDE) outRep[j] = repId;
         keep |= 1u << j;

@@ -1,8 +1,8 @@
 #!/bin/bash
-# Drop-in switch for the reference workflow (data/nuclassemble.sh:105-175): run the assembler with this script in place of the
-# reference binary and the three hot-path modules of the read/contig iterations go to the GPU stage binary, everything else
-# (createdb, ancient_read_assemble, ancient_contig_merge, cyclecheck, linclust's own kmermatcher/rescorediagonal calls, ...) stays
-# with the unmodified reference.  The reference exports MMSEQS=argv[0] for its workflow scripts (Application.cpp:198), so the
+# Drop-in switch for the reference workflow (data/nuclassemble.sh:85-200): run the assembler with this script in place of the
+# reference binary and createdb, the three hot-path modules of the read/contig iterations, cyclecheck and the k-mer matcher + Hamming
+# rescoring of the final linclust go to the GPU stage binary; everything else (ancient_read_assemble, ancient_contig_merge, clust,
+# align, the DB utilities, ...) stays with the unmodified reference.  The reference exports MMSEQS=argv[0] for its workflow scripts (Application.cpp:198), so the
 # reference is exec'ed under this script's name and every "$MMSEQS" <module> call of the workflow comes back here.
 #   CARPEDEAM_REF = reference binary, CARPEDEAM_GPU = carpedeam_b200/bin/carpedeam_gpu, CARPEDEAM_SWAP_LOG = optional call log
 set -e
@@ -10,13 +10,13 @@ set -e
 : "${CARPEDEAM_GPU:?set CARPEDEAM_GPU to carpedeam_gpu}"
 gpu=0
 case "$1" in
-    ancient_correction) gpu=1 ;;
-    kmermatcher|rescorediagonal)
-        # the assembler's calls: kmermatcher -c 0, rescorediagonal --rescore-mode 3 (linclust passes -c 0.99 / --rescore-mode 0)
+    # the hot path (kmermatcher: the assembler's -c 0 calls and linclust's coverage-filtered one; rescorediagonal: --rescore-mode 3 of the
+    # iterations and --rescore-mode 0 of linclust's pre-clustering) and the steps either side of it
+    kmermatcher|ancient_correction|cyclecheck|createdb) gpu=1 ;;
+    rescorediagonal)
         prev=""
         for a in "$@"; do
-            if [ "$1" = kmermatcher ] && [ "$prev" = "-c" ] && [ "$a" = "0" ]; then gpu=1; fi
-            if [ "$1" = rescorediagonal ] && [ "$prev" = "--rescore-mode" ] && [ "$a" = "3" ]; then gpu=1; fi
+            if [ "$prev" = "--rescore-mode" ] && { [ "$a" = "3" ] || [ "$a" = "0" ]; }; then gpu=1; fi
             prev="$a"
         done ;;
 esac

@@ -4,6 +4,10 @@
 //   carpedeam_gpu kmermatcher        <seqDB> <prefDB>                 [flags]   (kmermatcher.cpp:786)
 //   carpedeam_gpu rescorediagonal    <qDB> <tDB> <prefDB> <alnDB>     [flags]   (rescorediagonal.cpp:381)
 //   carpedeam_gpu ancient_correction <seqDB> <alnDB> <outDB>          [flags]   (correction.cpp:492)
+// and, either side of the loop:
+//   carpedeam_gpu rescorediagonal    ... --rescore-mode 0 [--wrapped-scoring 1]  (linclust's Hamming pre-clustering, linclust.sh:28-32)
+//   carpedeam_gpu cyclecheck         <seqDB> <cycleDB>                [flags]   (cyclecheck.cpp:31)
+//   carpedeam_gpu createdb           <fasta/fastq[.gz]> ... <seqDB>   [flags]   (createdb.cpp; host only)
 //
 // Host side only: DBReader/DBWriter-compatible file access and the text formats; all arithmetic happens in
 // libcarpedeam_gpu.so through the C ABI.  Errors print a message and exit(EXIT_FAILURE), as the reference does.
@@ -18,11 +22,9 @@
 #include <omp.h>
 #endif
 
-#include "../../include/carpedeam_gpu.h"
+#include "../../include/carpedeam_host.h"
 #include "formats.h"
 #include "mmdb.h"
-
-extern "C" int cdh_build_damage(const char *prefix, double seq_err, cdg_damage *out, char *errbuf, size_t errlen);
 
 using namespace cdh;
 
@@ -135,7 +137,7 @@ int kmermatcher(int argc, char **argv) {
     Args a = parse_args(argc, argv, 2);
     if (a.pos.size() < 2) die("Usage: kmermatcher <i:sequenceDB> <o:prefDB> [options]");
     require_pinned(a, "kmermatcher", {{"--sub-mat", "nucleotide.out"}, {"--alph-size", "nucl:5"}, {"--spaced-kmer-mode", "0"}, {"--adjust-kmer-len", "0"},
-                                      {"--mask", "0"}, {"--mask-lower-case", "0"}, {"--ignore-multi-kmer", "1"}, {"--compressed", "0"}, {"-c", "0"}});
+                                      {"--mask", "0"}, {"--mask-lower-case", "0"}, {"--ignore-multi-kmer", "1"}, {"--compressed", "0"}});
     const double t0 = now_ms();
     Db seq; open_db(a.pos[0], seq);
     if (a.opt.count("--max-seq-len"))
@@ -154,7 +156,8 @@ int kmermatcher(int argc, char **argv) {
     p.include_only_extendable = (int) a.num("--include-only-extendable", 0);
     p.hash_lo = 0; p.hash_hi = 65535;
     p.split_passes = 0;   // --split-memory-limit 0: as many hash-range passes as the free device memory asks for (usually one)
-    if (a.num("-c", 0.0) != 0.0) die("kmermatcher: only -c 0 (the assembler's setting) is supported");
+    p.cov_thr = (float) a.num("-c", 0.0); p.cov_mode = (int) a.num("--cov-mode", 0);   // assignGroup's canBeCovered (kmermatcher.cpp:526-529)
+    if (p.cov_mode < 0 || p.cov_mode > 5) die("kmermatcher: unknown --cov-mode");
     cdg_hits h;
     ck(ctx, cdg_kmermatch(ctx, &p, &h), "cdg_kmermatch");
     const double t2 = now_ms();
@@ -174,11 +177,109 @@ int kmermatcher(int argc, char **argv) {
     return EXIT_SUCCESS;
 }
 
+// prefilter lines of every query of `seq` from a pref DB, target keys replaced by indices
+void load_pref_lines(const Args &a, const Db &seq, const Db &pref, std::vector<uint64_t> &lineOff, std::vector<uint32_t> &tgt, std::vector<int32_t> &score,
+                     std::vector<uint16_t> &diag) {
+    std::vector<PrefLine> all;
+    parse_entries_parallel(seq.size(), host_threads(a), lineOff, all, [&](size_t q, std::vector<PrefLine> &out) {
+        long pi = pref.find(seq.keys[q]);
+        const size_t before = out.size();
+        if (pi >= 0) parse_pref_entry((const char *) pref.data.data() + pref.offsets[pi], out);
+        for (size_t i = before; i < out.size(); i++) {
+            long ti = seq.find(out[i].targetKey);
+            if (ti < 0) die("Invalid database read for database data file=" + a.pos[1]);
+            out[i].targetKey = (uint32_t) ti;
+        }
+    });
+    tgt.resize(all.size()); score.resize(all.size()); diag.resize(all.size());
+    for (size_t i = 0; i < all.size(); i++) { tgt[i] = all[i].targetKey; score[i] = all[i].score; diag[i] = all[i].diag; }
+}
+
+// rescorediagonal --rescore-mode 0 (HAMMING_PAR of linclust, lib/mmseqs/src/workflow/Linclust.cpp:103-112): prefilter-format output,
+// one entry per query of the pref DB (rescorediagonal.cpp:323-352)
+int rescore_hamming(const Args &a) {
+    require_pinned(a, "rescorediagonal", {{"--sub-mat", "nucleotide.out"}, {"--filter-hits", "0"}, {"-a", "0"}, {"--add-self-matches", "0"}, {"--sort-results", "0"},
+                                          {"--compressed", "0"}});
+    Db seq; open_db(a.pos[0], seq);
+    Db pref; open_db(a.pos[2], pref);
+    cdg_ctx *ctx = make_ctx();
+    std::vector<uint32_t> lens;
+    upload(ctx, seq, lens);
+    std::vector<uint64_t> lineOff; std::vector<uint32_t> tgt; std::vector<int32_t> score; std::vector<uint16_t> diag;
+    load_pref_lines(a, seq, pref, lineOff, tgt, score, diag);
+    ck(ctx, cdg_set_pref_lines(ctx, lineOff.data(), seq.size(), tgt.data(), score.data(), diag.data(), tgt.size()), "cdg_set_pref_lines");
+    cdg_hamming_params p;
+    p.cov_thr = (float) a.num("-c", 0.0); p.cov_mode = (int) a.num("--cov-mode", 0); p.min_seq_id = (float) a.num("--min-seq-id", 0.0);
+    p.seq_id_mode = (int) a.num("--seq-id-mode", 0); p.min_aln_len = (int) a.num("--min-aln-len", 0); p.wrapped_scoring = (int) a.num("--wrapped-scoring", 0);
+    cdg_hamming_out r;
+    ck(ctx, cdg_rescore_hamming(ctx, &p, &r), "cdg_rescore_hamming");
+    // entries only for the keys of the pref DB (the reference iterates the result DB, rescorediagonal.cpp:143-147)
+    std::vector<size_t> withEntry;
+    for (size_t q = 0; q < seq.size(); q++) if (pref.find(seq.keys[q]) >= 0) withEntry.push_back(q);
+    write_entries_parallel(a.pos[3], pref.dbtype ? pref.dbtype : DBTYPE_PREFILTER_REV_RES, withEntry.size(), host_threads(a),
+                           [&](size_t i, std::string &entry, uint32_t &key, uint8_t &ext) {
+        const size_t q = withEntry[i];
+        char buf[64];
+        for (uint64_t l = r.line_off[q]; l < r.line_off[q + 1]; l++)
+            if (r.keep[l]) entry.append(buf, format_pref_line(buf, seq.keys[r.target[l]], r.pref_score[l], (int16_t) r.diag[l]));
+        key = seq.keys[q]; ext = 0;
+    });
+    fprintf(stderr, "carpedeam_gpu rescorediagonal --rescore-mode 0: %llu of %llu lines kept\n", (unsigned long long) r.n_kept, (unsigned long long) r.n_lines);
+    cdg_destroy(ctx);
+    return EXIT_SUCCESS;
+}
+
+// cyclecheck <i:sequenceDB> <o:cycleDB> (src/assembler/cyclecheck.cpp:31-269): only the reported sequences are written, whole or
+// (--chop-cycle 1) cut at the split diagonal
+int cyclecheck(int argc, char **argv) {
+    Args a = parse_args(argc, argv, 2);
+    if (a.pos.size() < 2) die("Usage: cyclecheck <i:sequenceDB> <o:cycleDB> [options]");
+    require_pinned(a, "cyclecheck", {{"--compressed", "0"}});
+    Db seq; open_db(a.pos[0], seq);
+    cdg_ctx *ctx = make_ctx();
+    std::vector<uint32_t> lens;
+    upload(ctx, seq, lens);
+    cdg_cycle_params p; p.k = 22; p.max_seq_len = (uint32_t) a.num("--max-seq-len", 65535);
+    cdg_cycle_out r;
+    ck(ctx, cdg_cyclecheck(ctx, &p, &r), "cdg_cyclecheck");
+    const bool chop = (int) a.num("--chop-cycle", 0) != 0;
+    std::vector<size_t> cyc;
+    for (size_t q = 0; q < seq.size(); q++) {
+        if (lens[q] >= p.max_seq_len) fprintf(stderr, "Sequence %u too long. It will be skipped. Max length allowed is %u\n", seq.keys[q], p.max_seq_len);
+        if (r.split_diagonal[q]) cyc.push_back(q);
+    }
+    write_entries_parallel(a.pos[1], DBTYPE_NUCLEOTIDES, cyc.size(), host_threads(a), [&](size_t i, std::string &entry, uint32_t &key, uint8_t &ext) {
+        const size_t q = cyc[i];
+        entry.assign((const char *) seq.data.data() + seq.offsets[q], chop ? r.split_diagonal[q] : lens[q]);
+        entry.push_back('\n');
+        key = seq.keys[q]; ext = 0;
+    });
+    fprintf(stderr, "carpedeam_gpu cyclecheck: %llu of %zu sequences reported\n", (unsigned long long) r.n_cyclic, seq.size());
+    cdg_destroy(ctx);
+    return EXIT_SUCCESS;
+}
+
+// createdb <i:fastaFile1[.gz]> ... <o:sequenceDB> (lib/mmseqs/src/util/createdb.cpp): host only
+int createdb(int argc, char **argv) {
+    Args a = parse_args(argc, argv, 2);
+    if (a.pos.size() < 2) die("Usage: createdb <i:fastaFile1[.gz]> ... <i:fastaFileN[.gz]> <o:sequenceDB> [options]");
+    require_pinned(a, "createdb", {{"--compressed", "0"}, {"--createdb-mode", "1"}, {"--dbtype", "0"}, {"--id-offset", "0"}});
+    std::vector<const char *> files;
+    for (size_t i = 0; i + 1 < a.pos.size(); i++) files.push_back(a.pos[i].c_str());
+    cdh_seqset s; char err[512];
+    if (cdh_createdb(files.data(), (int) files.size(), (int) a.num("--shuffle", 1), a.pos.back().c_str(), &s, err, sizeof err) != 0) die(err);
+    fprintf(stderr, "carpedeam_gpu createdb: %llu sequences, %llu residues\n", (unsigned long long) s.n, (unsigned long long) s.total_residues);
+    cdh_free_seqset(&s);
+    return EXIT_SUCCESS;
+}
+
 int rescorediagonal(int argc, char **argv) {
     Args a = parse_args(argc, argv, 2);
     if (a.pos.size() < 4) die("Usage: rescorediagonal <i:queryDB> <i:targetDB> <i:prefDB> <o:alnDB> [options]");
     if (a.pos[0] != a.pos[1]) die("rescorediagonal: query and target database must be the same (assembler usage)");
-    if ((int) a.num("--rescore-mode", 0) != 3) die("rescorediagonal: only --rescore-mode 3 is implemented");
+    const int mode = (int) a.num("--rescore-mode", 0);
+    if (mode == 0) return rescore_hamming(a);   // linclust's pre-clustering step
+    if (mode != 3) die("rescorediagonal: --rescore-mode 3 (assembler) and 0 (linclust pre-clustering) are implemented");
     require_pinned(a, "rescorediagonal", {{"--sub-mat", "nucleotide.out"}, {"--wrapped-scoring", "0"}, {"--filter-hits", "0"}, {"-a", "0"}, {"-c", "0"},
                                           {"--min-aln-len", "0"}, {"--seq-id-mode", "0"}, {"--add-self-matches", "0"}, {"--sort-results", "0"},
                                           {"--compressed", "0"}});
@@ -281,10 +382,12 @@ int ancient_correction(int argc, char **argv) {
 }   // namespace
 
 int main(int argc, char **argv) {
-    if (argc < 2) die("Usage: carpedeam_gpu <kmermatcher|rescorediagonal|ancient_correction> ...");
+    if (argc < 2) die("Usage: carpedeam_gpu <kmermatcher|rescorediagonal|ancient_correction|cyclecheck|createdb> ...");
     std::string cmd = argv[1];
     if (cmd == "kmermatcher") return kmermatcher(argc, argv);
     if (cmd == "rescorediagonal") return rescorediagonal(argc, argv);
     if (cmd == "ancient_correction") return ancient_correction(argc, argv);
+    if (cmd == "cyclecheck") return cyclecheck(argc, argv);
+    if (cmd == "createdb") return createdb(argc, argv);
     die("Invalid Command: " + cmd);
 }

@@ -85,6 +85,9 @@ typedef struct {
     int32_t split_passes;            /* hash-range passes INSIDE the call with unsplit results (--split-memory-limit): 0 = as many as
                                         the free device memory asks for (kmermatcher.cpp:615-627), 1 = never split, M > 1 = M ranges
                                         cut from the 65536-bin hash histogram (setupKmerSplits, :742-784) */
+    float cov_thr;                   /* -c and --cov-mode: with --include-only-extendable 0 a member stays in its group only if */
+    int32_t cov_mode;                /* Util::canBeCovered(cov_thr, cov_mode, repLen, memberLen) (kmermatcher.cpp:526-529); the assembler
+                                        passes -c 0 (always true), its final linclust -c 0.99 --cov-mode 1, plain linclust -c 0.8 --cov-mode 0 */
 } cdg_kmer_params;
 
 /* prefilter hits in pref-DB order: for rep index ascending, target index ascending

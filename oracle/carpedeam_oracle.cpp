@@ -157,6 +157,10 @@ static void extract_seq(const char *s, int L, u32 id, int k, int kmersPerSeq, fl
     }
 }
 
+// -c / --cov-mode of the k-mer matcher (assignGroup's Util::canBeCovered, kmermatcher.cpp:526-529); the assembler passes -c 0
+static bool can_be_covered(float covThr, int covMode, float q, float t);
+static float g_covThr = 0.f; static int g_covMode = 1;
+extern "C" void orc_set_kmermatch_cov(float covThr, int covMode) { g_covThr = covThr; g_covMode = covMode; }
 // a5..a8.  ids are sequence indices; the caller guarantees keys ascend with the index, so
 // ordering by index == ordering by dbKey (KmerPosition.id is the dbKey, kmermatcher.cpp:143).
 // hashLo/hashHi: one split of the reference's split loop (kmermatcher.cpp:665-675): only records whose 16-bit hash lies in the range
@@ -204,7 +208,8 @@ extern "C" long orc_kmermatch_range(const char *blob, const u64 *off, const u32 
                 else { q = r.pos; tp = t.pos; need = false; }
                 int d = q - tp;
                 bool canExtend = d < 0 || d > (r.seqLen - t.seqLen);
-                if (!onlyExtendable || canExtend) { G g; g.rep = r.id; g.need = need; g.id = t.id; g.diag = d; grp.push_back(g); }
+                const bool canBeCovered = can_be_covered(g_covThr, g_covMode, (float) r.seqLen, (float) t.seqLen);   // :527-529
+                if ((!onlyExtendable && canBeCovered) || (canExtend && onlyExtendable)) { G g; g.rep = r.id; g.need = need; g.id = t.id; g.diag = d; grp.push_back(g); }
             }
         }
         first = false;

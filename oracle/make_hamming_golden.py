@@ -40,7 +40,20 @@ def main():
     subprocess.run([binary, "rescorediagonal", db, db, db + "_pref", db + "_r0"] + RS + ["--wrapped-scoring", "0"], check=True)
     subprocess.run([binary, "rescorediagonal", db, db, db + "_pref", db + "_r1"] + RS + ["--wrapped-scoring", "1"], check=True,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)   # one warning per skipped target
+    # the k-mer matcher of the assembler's own final linclust call (-k 20 --kmer-per-seq 200 --ignore-multi-kmer 1, data/nuclassemble.sh -> linclust) with
+    # its coverage filter (-c 0.99 --cov-mode 1) and with plain linclust's (-c 0.8 --cov-mode 0): assignGroup's canBeCovered (kmermatcher.cpp:526-529)
+    km2 = [x for x in KM]
+    for flag, val in (("--kmer-per-seq", "200"), ("-k", "20"), ("--ignore-multi-kmer", "1")):
+        km2[km2.index(flag) + 1] = val
+    for tag, c, mode in (("c099m1", "0.99", "1"), ("c08m0", "0.8", "0")):
+        a = [x for x in km2]
+        a[a.index("-c") + 1] = c; a[a.index("--cov-mode") + 1] = mode
+        subprocess.run([binary, "kmermatcher", db, db + "_pref_" + tag] + a, check=True)
     keep = set(sorted(keys)[:N_KEEP])
+    for tag in ("c099m1", "c08m0"):
+        d = {k: v for k, v in load_db(db + "_pref_" + tag).items() if k in keep}
+        gz_write(os.path.join(GOLD, "cfg1_lin_pref_%s_9.gz" % tag), canonical(d))
+        print("lin_pref_" + tag, len(d), "entries,", sum(v[0].count(b"\n") for v in d.values()), "lines")
     for name, path in (("lin_pref_9", db + "_pref"), ("lin_rescore_9", db + "_r0"), ("lin_rescore_wrapped_9", db + "_r1")):
         d = {k: v for k, v in load_db(path).items() if k in keep}
         gz_write(os.path.join(GOLD, "cfg1_%s.gz" % name), canonical(d))

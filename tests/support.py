@@ -207,6 +207,11 @@ class Oracle:
         L.orc_load_damage.argtypes = [C.c_char_p, C.c_char_p]
         self.L = L
 
+    def set_kmermatch_cov(self, cov_thr=0.0, cov_mode=1):
+        """-c / --cov-mode for the following kmermatch calls (the assembler's setting is the default)"""
+        self.L.orc_set_kmermatch_cov.restype = None
+        self.L.orc_set_kmermatch_cov(C.c_float(cov_thr), C.c_int(cov_mode))
+
     def kmermatch(self, s, k=20, kmers_per_seq=200, scale=0.2, seed=67, only_ext=0, keep_records=False, hash_lo=0, hash_hi=65535):
         """hash_lo / hash_hi: one split of the reference's split loop (kmermatcher.cpp:665-675)"""
         self.L.orc_kmermatch_range.restype = C.c_long

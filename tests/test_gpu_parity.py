@@ -1125,3 +1125,21 @@ def test_cyclecheck_vs_reference(ctx, oracle):
         assert np.array_equal(ctx.cyclecheck(k=k, max_seq_len=mx), oracle.cyclecheck(s, k=k, max_seq_len=mx)), (k, mx)
     # the k-mer matcher still works on the same context afterwards (cyclecheck reuses its record arrays)
     _hits_equal(ctx.kmermatch(), oracle.kmermatch(s))
+
+
+@pytest.mark.parametrize("tag,cov_thr,cov_mode", [("c099m1", 0.99, 1), ("c08m0", 0.8, 0)])
+def test_kmermatch_coverage_filter_vs_reference(ctx, oracle, tag, cov_thr, cov_mode):
+    """cdg_kmermatch with linclust's coverage filter (cov_thr / cov_mode = -c / --cov-mode, kmermatcher.cpp:526-529) against
+    the pref DB the reference's k-mer matcher wrote with the same setting, and against the oracle hit by hit"""
+    import carpedeam_b200 as cd
+    s = SeqSet.from_golden("correction_9")
+    ctx.upload(s.blob, s.off, s.len, s.ext)
+    got = ctx.kmermatch(cd.kmer_params(k=20, cov_thr=cov_thr, cov_mode=cov_mode))
+    oracle.set_kmermatch_cov(np.float32(cov_thr), cov_mode)
+    try:
+        _hits_equal(got, oracle.kmermatch(s, k=20))
+    finally:
+        oracle.set_kmermatch_cov()
+    mine = format_pref(s, got)
+    gk, gp, _ = load_golden("lin_pref_%s_9" % tag)
+    assert not [k for k, p in zip(gk, gp) if mine[k] != p]

@@ -76,3 +76,16 @@ def test_createdb_files_equal_the_reference_binarys(tmp_path, shuffle):
         assert open(mine + suffix + ".dbtype", "rb").read() == open(ref + suffix + ".dbtype", "rb").read()
     assert open(mine + ".source").read() == open(ref + ".source").read()
     assert headers[0].startswith(b"seq0") and len(lens) == 240
+
+
+def test_stage_binary_createdb(tmp_path):
+    """carpedeam_gpu createdb (host only, no device needed) writes the reference's nucl_reads DB"""
+    import carpedeam_b200 as cd
+    cd.build()
+    out = str(tmp_path / "nucl_reads")
+    subprocess.run([cd.STAGE_BIN, "createdb", os.path.join(GOLD, "test_data.fq.gz"), out, "--dbtype", "0", "--shuffle", "1", "--createdb-mode", "1",
+                    "--write-lookup", "0", "--id-offset", "0", "--compressed", "0", "-v", "3"], check=True)
+    keys, pay, ext = load_golden("nucl_reads")
+    mine = read_db(out)
+    assert sorted(mine) == keys and all(mine[k] == (p, 0) for k, p in zip(keys, pay))
+    assert open(out + ".dbtype", "rb").read() == (1).to_bytes(4, "little")

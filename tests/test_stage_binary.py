@@ -47,3 +47,42 @@ def test_stage_binary_error_behaviour(tmp_path):
     cd.build()
     r = subprocess.run([cd.STAGE_BIN, "kmermatcher", str(tmp_path / "nope"), str(tmp_path / "out"), "-k", "20"], capture_output=True)
     assert r.returncode == 1
+
+
+HAMMING_ARGV = ["--sub-mat", "nucl:nucleotide.out,aa:blosum62.out", "--rescore-mode", "0", "--filter-hits", "0", "-e", "0.001", "-c", "0.8", "-a", "0",
+                "--cov-mode", "0", "--min-seq-id", "0.9", "--min-aln-len", "0", "--seq-id-mode", "0", "--add-self-matches", "0", "--sort-results", "0",
+                "--db-load-mode", "0", "--threads", "4", "--compressed", "0", "-v", "3"]   # HAMMING_PAR as `carpedeam linclust` generates it
+
+
+@pytest.mark.parametrize("wrapped,golden", [(0, "lin_rescore_9"), (1, "lin_rescore_wrapped_9")])
+def test_stage_binary_hamming_rescore_matches_reference_db(tmp_path, wrapped, golden):
+    """carpedeam_gpu rescorediagonal --rescore-mode 0 on the pref DB of the reference's linclust kmermatcher == the DB the
+    reference's rescorediagonal wrote (keys, entries, dbtype 14)"""
+    import carpedeam_b200 as cd
+    cd.build()
+    d = str(tmp_path)
+    write_db(d + "/seq", *load_golden("correction_9"), 1)
+    write_db(d + "/pref", *load_golden("lin_pref_9"), 14)
+    subprocess.run([cd.STAGE_BIN, "rescorediagonal", d + "/seq", d + "/seq", d + "/pref", d + "/out"] + HAMMING_ARGV + ["--wrapped-scoring", str(wrapped)], check=True)
+    gk, gp, ge = load_golden(golden)
+    mine = read_db(d + "/out")
+    assert sorted(mine) == gk
+    bad = [kk for kk, p in zip(gk, gp) if mine[kk][0] != p]
+    assert not bad, (len(bad), mine[bad[0]], gp[gk.index(bad[0])])
+    assert open(d + "/out.dbtype", "rb").read() == (14).to_bytes(4, "little")
+
+
+@pytest.mark.parametrize("chop", [0, 1])
+def test_stage_binary_cyclecheck_matches_reference(tmp_path, chop):
+    """carpedeam_gpu cyclecheck writes the entries the reference reported (tests/golden/cycle_kat.txt), whole or cut at the diagonal"""
+    import carpedeam_b200 as cd
+    from support import load_cycle_kat
+    cd.build()
+    s, want = load_cycle_kat()
+    d = str(tmp_path)
+    write_db(d + "/seq", *load_golden("synth_cycle", ""), 1)
+    subprocess.run([cd.STAGE_BIN, "cyclecheck", d + "/seq", d + "/cyc", "--max-seq-len", "200000", "--chop-cycle", str(chop), "--threads", "4", "-v", "3"], check=True)
+    mine = read_db(d + "/cyc")
+    assert sorted(mine) == [int(k) for k in range(s.n) if want[k]]
+    for k, (payload, ext) in mine.items():
+        assert payload == s.seq(k)[:int(want[k]) if chop else None] + b"\n" and ext == 0, k

@@ -1,7 +1,7 @@
 """The drop-in boundary inside the reference's own workflow: `ancient_assemble` of the UNMODIFIED reference binary runs with
-carpedeam_swap.sh as "$MMSEQS", so every kmermatcher / rescorediagonal / ancient_correction call of the ten iterations
-(data/nuclassemble.sh:105-175) goes to the GPU stage binary while createdb, ancient_read_assemble, ancient_contig_merge,
-cyclecheck and linclust stay with the reference.  The final out.fasta must have the SHA-256 the all-reference run produced
+carpedeam_swap.sh as "$MMSEQS", so createdb, every kmermatcher / rescorediagonal / ancient_correction call of the ten iterations
+(data/nuclassemble.sh:105-175), every cyclecheck and the k-mer matcher + Hamming rescoring of the final linclust go to the GPU stage
+binary while ancient_read_assemble, ancient_contig_merge, clust, align and the DB utilities stay with the reference.  The final out.fasta must have the SHA-256 the all-reference run produced
 (tests/golden/MANIFEST.sha256, written by oracle/make_golden.py) and the intermediate stage DBs must equal the golden ones per key."""
 import hashlib
 import os
@@ -34,8 +34,10 @@ def test_reference_workflow_with_gpu_stages_reproduces_out_fasta(tmp_path):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     calls = [l.split() for l in open(log)]
     gpu_calls = [c[1] for c in calls if c[0] == "gpu"]
-    assert gpu_calls.count("kmermatcher") == 10 and gpu_calls.count("rescorediagonal") == 10 and gpu_calls.count("ancient_correction") == 10
-    assert ["ref", "kmermatcher"] in calls and ["ref", "rescorediagonal"] in calls      # linclust's own calls stayed with the reference
+    # ten iterations + the final linclust's k-mer matcher and Hamming pre-clustering (--rescore-mode 0 --wrapped-scoring 1), createdb, five cyclechecks
+    assert gpu_calls.count("kmermatcher") == 11 and gpu_calls.count("rescorediagonal") == 11 and gpu_calls.count("ancient_correction") == 10
+    assert gpu_calls.count("cyclecheck") == 5 and gpu_calls.count("createdb") == 1
+    assert ["ref", "ancient_read_assemble"] in calls and ["ref", "ancient_contig_merge"] in calls and ["ref", "clust"] in calls
     want = dict(l.split()[::-1] for l in open(os.path.join(GOLD, "MANIFEST.sha256")))
     assert hashlib.sha256(open(out, "rb").read()).hexdigest() == want["out.fasta"]
     # intermediate DBs of the iterations the golden set holds
