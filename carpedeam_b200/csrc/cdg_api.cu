@@ -798,16 +798,12 @@ static int km_group(cdg_ctx *ctx, const cdg_kmer_params *p, const KmPlan &K, u64
     Rtot -= mainSkip;
     GroupParams G; G.idBits = K.idBits; G.diagBits = K.diagBits; G.diagBias = (i32) ctx->maxLen; G.onlyExtendable = p->include_only_extendable; G.covThr = p->cov_thr; G.covMode = p->cov_mode;
     G.firstRunQuirk = mainHasGlobalFirstRun ? 1 : 0;   // kmermatcher.cpp:466: only the globally first run
-    if (Rtot && K.wide) group_kernel<true><<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(mainK, mainV, Rtot, ctx->dLen.as<u32>(), G,
-                                                                                                                    ctx->dKey2A.as<u64>(), sc + SC_GROUPED, ctx->dKey2HiA.as<u64>());
-    else if (Rtot) group_kernel<<<(unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(mainK, mainV, Rtot, ctx->dLen.as<u32>(), G,
-                                                                                                      ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
+    if (Rtot) launch_group(ctx->st, K.wide, (unsigned) ((Rtot + GROUP_TILE - 1) / GROUP_TILE), mainK, mainV, Rtot, ctx->dLen.as<u32>(), G, ctx->dKey2A.as<u64>(), sc + SC_GROUPED,
+                           K.wide ? ctx->dKey2HiA.as<u64>() : nullptr);
     GroupParams GI = G; GI.firstRunQuirk = idHasGlobalFirstRun ? 1 : 0;
     const u64 nId = ctx->nIdent;
-    if (nId && K.wide) group_kernel<true><<<(unsigned) ((nId + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedIdK, ctx->sortedIdV, nId, ctx->dLen.as<u32>(), GI,
-                                                                                                                  ctx->dKey2A.as<u64>(), sc + SC_GROUPED, ctx->dKey2HiA.as<u64>());
-    else if (nId) group_kernel<<<(unsigned) ((nId + GROUP_TILE - 1) / GROUP_TILE), GROUP_BLOCK, 0, ctx->st>>>(ctx->sortedIdK, ctx->sortedIdV, nId, ctx->dLen.as<u32>(), GI,
-                                                                                                    ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
+    if (nId) launch_group(ctx->st, K.wide, (unsigned) ((nId + GROUP_TILE - 1) / GROUP_TILE), ctx->sortedIdK, ctx->sortedIdV, nId, ctx->dLen.as<u32>(), GI, ctx->dKey2A.as<u64>(),
+                          sc + SC_GROUPED, K.wide ? ctx->dKey2HiA.as<u64>() : nullptr);
     ctx->launches += 2;
     CKL();
     if ((rc = read_scalar(ctx, SC_GROUPED, R2out))) return rc;
@@ -995,9 +991,8 @@ static int run_kmermatch_split(cdg_ctx *ctx, const cdg_kmer_params *p, const KmP
         if (!runLen[r]) continue;
         G.firstRunQuirk = r == rStar ? 1 : 0;
         const unsigned gb = (unsigned) ((runLen[r] + GROUP_TILE - 1) / GROUP_TILE);
-        if (K.wide) group_kernel<true><<<gb, GROUP_BLOCK, 0, ctx->st>>>(side[r].as<u64>(), side[r].as<u64>() + runLen[r], runLen[r], ctx->dLen.as<u32>(), G, ctx->dKey2A.as<u64>(), sc + SC_GROUPED,
-                                                                      ctx->dKey2HiA.as<u64>());
-        else group_kernel<<<gb, GROUP_BLOCK, 0, ctx->st>>>(side[r].as<u64>(), side[r].as<u64>() + runLen[r], runLen[r], ctx->dLen.as<u32>(), G, ctx->dKey2A.as<u64>(), sc + SC_GROUPED);
+        launch_group(ctx->st, K.wide, gb, side[r].as<u64>(), side[r].as<u64>() + runLen[r], runLen[r], ctx->dLen.as<u32>(), G, ctx->dKey2A.as<u64>(), sc + SC_GROUPED,
+                     K.wide ? ctx->dKey2HiA.as<u64>() : nullptr);
         ctx->launches++;
     }
     CKL();

@@ -768,7 +768,9 @@ static constexpr int GROUP_BLOCK = 256;
 static constexpr int GROUP_ITEMS = 8;
 static constexpr int GROUP_TILE = GROUP_BLOCK * GROUP_ITEMS;
 #define GP(i) ((i) + ((i) >> 3))   // shared-memory index of tile record i (one pad word per 8)
-template <bool WIDE = false>
+// COV: assignGroup's canBeCovered filter is compiled in (-c > 0 or a length coverage mode: linclust); the assembler's calls (-c 0) run the
+// instantiation without it (the two float divisions per member cost 0.5 ms per 10 M reads)
+template <bool WIDE = false, bool COV = false>
 __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, u64 n,
                                                             const u32 *__restrict__ len, GroupParams G, u64 *__restrict__ out,
                                                             unsigned long long *__restrict__ outCount, u64 *__restrict__ outHi = nullptr) {
@@ -864,7 +866,8 @@ __global__ void __launch_bounds__(GROUP_BLOCK) group_kernel(const u64 *__restric
         const u32 id = cdg_val_id(v), tl = len[id];
         i32 d; bool need;
         member_diag(repRev, repLen, repPos, (k & CDG_B63) == 0, tl, cdg_val_pos(v), d, need);
-        if (G.onlyExtendable ? !(d < 0 || d > (i32) repLen - (i32) tl) : !can_be_covered(G.covThr, G.covMode, (float) repLen, (float) tl)) continue;   // :526-536
+        if (G.onlyExtendable && !(d < 0 || d > (i32) repLen - (i32) tl)) continue;   // :526-536
+        if (COV && !G.onlyExtendable && !can_be_covered(G.covThr, G.covMode, (float) repLen, (float) tl)) continue;   // :527-529
         outKey[j] = (WIDE ? 0ull : ((u64) repId << sh2)) | ((u64) id << sh1) | ((u64) (u32) (d + G.diagBias) << 1) | (need ? 1ull : 0ull);
         if (WIDE) outRep[j] = repId;
         keep |= 1u << j;
@@ -903,6 +906,15 @@ struct PairEndFlag {
         return id != rep ? 1u : 0u;
     }
 };
+
+// with -c 0 canBeCovered holds for every pair except in the two length modes (Util.cpp:541-544)
+inline bool group_cov_active(const GroupParams &G) { return !G.onlyExtendable && (G.covThr > 0.f || G.covMode == 3 || G.covMode == 4); }
+inline void launch_group(cudaStream_t st, bool wide, unsigned grid, const u64 *keys, const u64 *vals, u64 n, const u32 *len, const GroupParams &G, u64 *out,
+                         unsigned long long *outCount, u64 *outHi) {
+    const bool cov = group_cov_active(G);
+    if (wide) { if (cov) group_kernel<true, true><<<grid, GROUP_BLOCK, 0, st>>>(keys, vals, n, len, G, out, outCount, outHi); else group_kernel<true, false><<<grid, GROUP_BLOCK, 0, st>>>(keys, vals, n, len, G, out, outCount, outHi); }
+    else { if (cov) group_kernel<false, true><<<grid, GROUP_BLOCK, 0, st>>>(keys, vals, n, len, G, out, outCount, nullptr); else group_kernel<false, false><<<grid, GROUP_BLOCK, 0, st>>>(keys, vals, n, len, G, out, outCount, nullptr); }
+}
 
 // tile sums of PairEndFlag for one-word records: 128-bit loads (two records per thread and load), the record after the pair by shuffle
 // — the generic tile_sum_kernel evaluates the functor per record and loads every key twice
