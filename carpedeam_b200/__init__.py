@@ -214,7 +214,7 @@ def hostlib():
         H.cdh_build_merge_model.restype = C.c_int
         H.cdh_merge_less.argtypes = [C.c_uint32, C.c_float, C.c_uint32, C.c_float]; H.cdh_merge_less.restype = C.c_int
         H.cdh_merge_queue_order.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]; H.cdh_merge_queue_order.restype = None
-        H.cdh_createdb.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_char_p, C.POINTER(SeqSetC), C.c_char_p, C.c_size_t]; H.cdh_createdb.restype = C.c_int
+        H.cdh_createdb.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(SeqSetC), C.c_char_p, C.c_size_t]; H.cdh_createdb.restype = C.c_int
         H.cdh_free_seqset.argtypes = [C.POINTER(SeqSetC)]; H.cdh_free_seqset.restype = None
         H.cdh_packed_words.argtypes = [C.c_void_p, C.c_uint64]; H.cdh_packed_words.restype = C.c_uint64
         H.cdh_pack_seqs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
@@ -300,13 +300,13 @@ def load_pair_model(prefix, seq_err=0.001, rand_align_penal=0.85, excess_penal=0
     return m
 
 
-def createdb(files, shuffle=True, out_db=None):
+def createdb(files, shuffle=True, out_db=None, write_lookup=True):
     """FASTA / FASTQ [.gz] files -> (data u8, offsets u64[n], lengths u32[n], headers [bytes]) in the reference's createdb key order
     (carpedeam_b200/host/createdb.cpp); with out_db also written as MMseqs2 database files"""
     arr = (C.c_char_p * len(files))(*[f.encode() for f in files])
     s = SeqSetC()
     err = C.create_string_buffer(512)
-    if hostlib().cdh_createdb(arr, len(files), 1 if shuffle else 0, out_db.encode() if out_db else None, C.byref(s), err, 512) != 0:
+    if hostlib().cdh_createdb(arr, len(files), 1 if shuffle else 0, 1 if write_lookup else 0, out_db.encode() if out_db else None, C.byref(s), err, 512) != 0:
         raise CdgError("createdb: " + err.value.decode())
     try:
         n = int(s.n)

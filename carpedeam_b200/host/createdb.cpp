@@ -8,7 +8,7 @@
 // :277-280) — so key order = (i % 32, i / 32) order of the input, a fixed permutation.  --shuffle 0 keeps the input order.
 //   cdh_createdb        parse the files -> flat set in DB layout (data, offsets, lengths; keys = 0..n-1) and, optionally, the header
 //                       lines in the same order; with out_db != NULL also written as <out_db>{,.index,.dbtype}, <out_db>_h{,.index,.dbtype}
-//                       and <out_db>.source (the .lookup file of the reference is not written: no stage of the hot path reads it)
+//                       <out_db>.source and (write_lookup) <out_db>.lookup
 //   cdh_free_seqset     releases what cdh_createdb allocated
 // The 2-bit packed arrays for cdg_upload_packed come from cdh_pack_seqs (pack.cpp) on this set.
 #include <zlib.h>
@@ -100,7 +100,35 @@ extern "C" void cdh_free_seqset(cdh_seqset *s) {
     memset(s, 0, sizeof *s);
 }
 
-extern "C" int cdh_createdb(const char *const *files, int n_files, int shuffle, const char *out_db, cdh_seqset *out, char *errbuf, size_t errlen) {
+// Util::parseFastaHeader (lib/mmseqs/src/commons/Util.cpp:173-256): the identifier inside the first token of a header line
+static std::string fasta_identifier(const std::string &name) {
+    if (name.empty()) return "";
+    size_t offset = 0;
+    if (name.size() >= 10 && name.compare(0, 10, "consensus_") == 0) offset = 10;
+    struct Db { const char *prefix; unsigned length, bar; };
+    static const Db dbs[] = {{"uc", 2, 0}, {"cl|", 3, 1}, {"sp|", 3, 1}, {"tr|", 3, 1}, {"gb|", 3, 1}, {"ref|", 4, 1}, {"pdb|", 4, 1}, {"bbs|", 4, 1},
+                             {"lcl|", 4, 1}, {"pir||", 5, 1}, {"prf||", 5, 1}, {"gnl|", 4, 2}, {"pat|", 4, 2}, {"gi|", 3, 3}};
+    for (const Db &d : dbs) {
+        const size_t pl = strlen(d.prefix);
+        if (name.size() < pl || name.compare(offset, pl, d.prefix) != 0) continue;   // Util::startWith(prefix, header, offset)
+        size_t start = offset + d.length;
+        for (unsigned j = 0; j + 1 < d.bar; j++) {
+            const size_t end = name.find_first_of('|', start);
+            if (end == std::string::npos) return "";
+            start = end + 1;
+        }
+        size_t end = name.find_first_of('|', start);
+        if (end == std::string::npos) end = name.find_first_of(" \n", start);
+        if (end == std::string::npos) end = name.size();
+        return name.substr(start, end - start);
+    }
+    size_t end = name.find_first_of(" \n", offset);
+    if (end == std::string::npos) end = name.size();
+    return name.substr(offset, end - offset);
+}
+
+extern "C" int cdh_createdb(const char *const *files, int n_files, int shuffle, int write_lookup, const char *out_db, cdh_seqset *out, char *errbuf,
+                            size_t errlen) {
     auto fail = [&](const std::string &m) { if (errbuf && errlen) snprintf(errbuf, errlen, "%s", m.c_str()); return -1; };
     if (!files || n_files <= 0 || !out) return fail("cdh_createdb: no input");
     memset(out, 0, sizeof *out);
@@ -153,6 +181,12 @@ extern "C" int cdh_createdb(const char *const *files, int n_files, int shuffle, 
         if (!src) return fail(std::string("Cannot write ") + out_db + ".source");
         for (int fi = 0; fi < n_files; fi++) fprintf(src, "%d\t%s\n", fi, base_name(files[fi]).c_str());   // createdb.cpp:121-123
         fclose(src);
+        if (write_lookup) {   // createdb.cpp:292-330: key, identifier of the header, number of the input file
+            FILE *lk = fopen((std::string(out_db) + ".lookup").c_str(), "w");
+            if (!lk) return fail(std::string("Cannot write ") + out_db + ".lookup");
+            for (size_t k = 0; k < n; k++) fprintf(lk, "%zu\t%s\t%d\n", k, fasta_identifier(entries[order[k]].name).c_str(), fileOf[order[k]]);
+            fclose(lk);
+        }
     }
     return 0;
 }

@@ -267,7 +267,7 @@ int createdb(int argc, char **argv) {
     std::vector<const char *> files;
     for (size_t i = 0; i + 1 < a.pos.size(); i++) files.push_back(a.pos[i].c_str());
     cdh_seqset s; char err[512];
-    if (cdh_createdb(files.data(), (int) files.size(), (int) a.num("--shuffle", 1), a.pos.back().c_str(), &s, err, sizeof err) != 0) die(err);
+    if (cdh_createdb(files.data(), (int) files.size(), (int) a.num("--shuffle", 1), (int) a.num("--write-lookup", 1), a.pos.back().c_str(), &s, err, sizeof err) != 0) die(err);
     fprintf(stderr, "carpedeam_gpu createdb: %llu sequences, %llu residues\n", (unsigned long long) s.n, (unsigned long long) s.total_residues);
     cdh_free_seqset(&s);
     return EXIT_SUCCESS;

@@ -54,7 +54,8 @@ int cdh_apply_patches(uint8_t *data, uint64_t data_bytes, const cdg_patches *p);
 
 /* ---- createdb: FASTA / FASTQ [.gz] -> sequence set in DB layout (lib/mmseqs/src/util/createdb.cpp, hard split mode; kseq reader
  * lib/mmseqs/lib/kseq/kseq.h).  shuffle != 0 reproduces --shuffle 1: key order = (input index % 32, input index / 32).  With out_db
- * the set is also written as <out_db>{,.index,.dbtype}, <out_db>_h{,.index,.dbtype}, <out_db>.source.  Arrays are malloc'ed: cdh_free_seqset. */
+ * the set is also written as <out_db>{,.index,.dbtype}, <out_db>_h{,.index,.dbtype}, <out_db>.source and, with write_lookup (--write-lookup 1, the
+ * default), <out_db>.lookup (key, identifier parsed from the header by Util::parseFastaHeader, input file number).  Arrays are malloc'ed: cdh_free_seqset. */
 typedef struct {
     uint64_t n, data_bytes, header_bytes, total_residues;
     uint8_t *data;             /* entries `BASES\n\0` in key order (keys 0..n-1) */
@@ -63,7 +64,7 @@ typedef struct {
     uint8_t *headers;          /* entries `name[ comment]\n\0` in key order */
     uint64_t *header_offsets;  /* n + 1 */
 } cdh_seqset;
-int cdh_createdb(const char *const *files, int n_files, int shuffle, const char *out_db, cdh_seqset *out, char *errbuf, size_t errlen);
+int cdh_createdb(const char *const *files, int n_files, int shuffle, int write_lookup, const char *out_db, cdh_seqset *out, char *errbuf, size_t errlen);
 void cdh_free_seqset(cdh_seqset *s);
 
 #ifdef __cplusplus

@@ -52,7 +52,8 @@ def test_createdb_files_equal_the_reference_binarys(tmp_path, shuffle):
     with open(fa, "w") as f:
         for i in range(150):
             s = "".join(rng.choice(list("ACGTNacgt"), int(rng.integers(1, 400))))
-            f.write(">seq%d some comment %d\n" % (i, i) if i % 3 else ">seq%d\n" % i)
+            name = ("seq%d", "sp|P%05d|NAME_X", "gi|%d|ref|NC_1.1|", "consensus_tr|Q%d|Y", "gnl|db|id%d", "uc%d", "lcl|%d")[i % 7] % i
+            f.write(">%s some comment %d\n" % (name, i) if i % 3 else ">%s\n" % name)
             for j in range(0, len(s), 60):
                 f.write(s[j:j + 60] + "\n")
     fq = tmp_path / "b.fq.gz"
@@ -75,7 +76,8 @@ def test_createdb_files_equal_the_reference_binarys(tmp_path, shuffle):
             assert a[k][0] == b[k][0], (suffix, k, a[k][0][:80], b[k][0][:80])
         assert open(mine + suffix + ".dbtype", "rb").read() == open(ref + suffix + ".dbtype", "rb").read()
     assert open(mine + ".source").read() == open(ref + ".source").read()
-    assert headers[0].startswith(b"seq0") and len(lens) == 240
+    assert open(mine + ".lookup").read() == open(ref + ".lookup").read()   # identifiers by Util::parseFastaHeader (sp|, gi|, gnl|, consensus_ ...)
+    assert len(lens) == 240
 
 
 def test_stage_binary_createdb(tmp_path):
