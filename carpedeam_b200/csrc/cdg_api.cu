@@ -1382,8 +1382,11 @@ extern "C" int cdg_cyclecheck(cdg_ctx *ctx, const cdg_cycle_params *p, cdg_cycle
         const int l = cdgsort::radix_sort(ctx->st, ws, ctx->dKeysA.as<u64>(), ctx->dKeysB.as<u64>(), ctx->dValsA.as<u64>(), ctx->dValsB.as<u64>(), R, plan, &sk, &sv, ctx->smCount);
         if (l < 0) return fail(ctx, CDG_ERR_UNSUPPORTED, "cdg_cyclecheck: radix sort: input too large for one pass set");
         ctx->launches += l;
-        cdgcycle::cycle_match_kernel<<<(unsigned) ((R + 255) / 256), 256, 0, ctx->st>>>(sk, sv, R, ctx->dLen.as<u32>(), ctx->dCycleDiagOff.as<u64>(), ctx->dCycleHits.as<u32>());
-        ctx->launches++;
+        cdgcycle::cycle_match_kernel<<<(unsigned) ((R + 255) / 256), 256, 0, ctx->st>>>(sk, sv, R, ctx->dLen.as<u32>(), ctx->dCycleDiagOff.as<u64>(), ctx->dCycleHits.as<u32>(),
+                                                                                       cdgcycle::CYCLE_WALK_CAP);
+        cdgcycle::cycle_match_head_kernel<<<(unsigned) ((R + 255) / 256), 256, 0, ctx->st>>>(sk, sv, R, ctx->dLen.as<u32>(), ctx->dCycleDiagOff.as<u64>(),
+                                                                                            ctx->dCycleHits.as<u32>(), cdgcycle::CYCLE_WALK_CAP);
+        ctx->launches += 2;
         CKL();
     }
     cdgcycle::cycle_band_kernel<<<wgrid, 256, 0, ctx->st>>>(ctx->dLen.as<u32>(), n, p->k, p->max_seq_len, ctx->dCycleDiagOff.as<u64>(), ctx->dCycleHits.as<u32>(),

@@ -64,3 +64,25 @@ def test_oracle_cyclecheck_matches_reference_binary(oracle):
     from support import load_cycle_kat
     s, want = load_cycle_kat()
     assert np.array_equal(oracle.cyclecheck(s), want) and (want > 0).sum() > 50
+
+
+def test_cyclecheck_matching_bodies_on_the_cpu_including_the_long_subrun_path(tmp_path):
+    """the host/device bodies of the cyclecheck matching (cdg_cycle.cuh), run on the CPU by tests/cycle_host_harness.cu: with the shipped cap every
+    record walks back itself (the path the GPU tests cover); with a cap of 3 almost every repeated k-mer goes through the forward walk of its
+    sub-run head (the path for k-mers repeated thousands of times in one sequence) — both must give the reference's split diagonals"""
+    import shutil
+    import subprocess
+    from support import ROOT, load_cycle_kat
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    exe = str(tmp_path / "cycle_host_harness")
+    subprocess.run(["nvcc", "-O2", "-std=c++17", "-x", "cu", "-o", exe, os.path.join(ROOT, "tests", "cycle_host_harness.cu")], check=True)
+    s, want = load_cycle_kat()
+    inp = str(tmp_path / "set.bin")
+    with open(inp, "wb") as f:
+        f.write(np.uint32(s.n).tobytes()); f.write(s.len.astype(np.uint32).tobytes())
+        for i in range(s.n):
+            f.write(s.seq(i))
+    for cap in (4096, 3, 0):
+        out = subprocess.run([exe, inp, "22", "200000", str(cap)], check=True, capture_output=True, text=True).stdout.split()
+        assert np.array_equal(np.array(out, np.uint32), want), cap
