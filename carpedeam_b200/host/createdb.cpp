@@ -74,7 +74,6 @@ int read_entry(GzReader &r, int &last_char, Entry &e) {
     }
     if (c == '>' || c == '@') last_char = c;
     if (c != '+') { if (c == -1) last_char = 0; return 1; }
-    std::string skip;
     while ((c = r.getc()) != -1 && c != '\n') {}    // rest of the '+' line
     if (c == -1) return -2;
     size_t qual = 0;
