@@ -14,6 +14,7 @@ The binary is used (a) to validate oracle/ restatements and regenerate tests/gol
 `bench.py --impl reference`).  It is never on the product path.
 
 Usage: python oracle/build_ref.py [--ref /root/reference] [--jobs N] [--march x86-64-v3]
+       python oracle/build_ref.py --gpu-stages      (afterwards: the same reference linked with carpedeam_b200/binding/stages_gpu.cpp)
 """
 import argparse
 import os
@@ -61,13 +62,67 @@ def generate_headers(ref, gen):
                     xxd_header(os.path.join(dirpath, fn), gen)
 
 
+GPU_ENTRY_POINTS = {   # object -> (mangled entry point, name it gets so that carpedeam_b200/binding/stages_gpu.cpp can take its place)
+    "lib/mmseqs/src/linclust/kmermatcher.cpp": ("_Z11kmermatcheriPPKcRK7Command", "_Z15kmermatcher_cpuiPPKcRK7Command"),
+    "lib/mmseqs/src/alignment/rescorediagonal.cpp": ("_Z15rescorediagonaliPPKcRK7Command", "_Z19rescorediagonal_cpuiPPKcRK7Command"),
+    "src/assembler/correction.cpp": ("_Z10correctioniPPKcRK7Command", "_Z14correction_cpuiPPKcRK7Command"),
+}
+
+
+def build_gpu_stages(ref, march):
+    """oracle/_ref/carpedeam_ref_gpu: the reference with the in-tree binding (carpedeam_b200/binding/stages_gpu.cpp, compiled against the
+    reference's headers) in place of the entry points of kmermatcher, rescorediagonal and ancient_correction.  No reference source is changed:
+    the three original entry points are renamed in COPIES of their objects (objcopy --redefine-sym) and stay reachable as *_cpu for calls
+    outside the GPU path.  Needs oracle/_ref/obj (a previous run of this script) and the built libcarpedeam_gpu.so / libcarpedeam_host.so."""
+    root = os.path.dirname(HERE)
+    pkg = os.path.join(root, "carpedeam_b200")
+    obj, obj_gpu = os.path.join(OUT, "obj"), os.path.join(OUT, "obj_gpu")
+    os.makedirs(obj_gpu, exist_ok=True)
+    srcs = [l.strip() for l in open(os.path.join(HERE, "ref_sources.txt")) if l.strip()]
+    objs = []
+    for s in srcs:
+        o = os.path.join(obj, s.replace("/", "__") + ".o")
+        if not os.path.exists(o):
+            print("missing", o, "- run oracle/build_ref.py first")
+            return 1
+        if s in GPU_ENTRY_POINTS:
+            old, new = GPU_ENTRY_POINTS[s]
+            o2 = os.path.join(obj_gpu, os.path.basename(o))
+            subprocess.run(["objcopy", "--redefine-sym", "%s=%s" % (old, new), o, o2], check=True)
+            o = o2
+        objs.append(o)
+    incs = ["-I" + os.path.join(ref, d) for d in INC_SUBDIRS] + ["-I" + os.path.join(OUT, "generated"), "-I" + os.path.join(root, "include")]
+    bind_o = os.path.join(obj_gpu, "stages_gpu.o")
+    cmd = ["g++", "-std=c++1y", "-fno-exceptions", "-O2", "-fsigned-char", "-march=" + march, "-w", "-fopenmp"] + DEFS + incs + \
+          ["-c", os.path.join(pkg, "binding", "stages_gpu.cpp"), "-o", bind_o]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if p.returncode != 0:
+        print(p.stderr[-6000:], file=sys.stderr)
+        return 2
+    binary = os.path.join(OUT, "carpedeam_ref_gpu")
+    link = ["g++", "-fopenmp", "-o", binary] + objs + [bind_o, "-L" + pkg, "-lcarpedeam_gpu", "-lcarpedeam_host", "-Wl,-rpath," + pkg,
+                                                        "-latomic", "-lm", "-lz", "-lpthread"]
+    p = subprocess.run(link, capture_output=True, text=True)
+    if p.returncode != 0:
+        print(p.stderr[-6000:], file=sys.stderr)
+        return 3
+    print("built", binary)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--jobs", type=int, default=os.cpu_count() or 4)
     ap.add_argument("--march", default="x86-64-v3")
     ap.add_argument("--force", action="store_true")
+    ap.add_argument("--gpu-stages", action="store_true", help="build oracle/_ref/carpedeam_ref_gpu (the reference + the in-tree GPU binding)")
     a = ap.parse_args()
+    if a.gpu_stages:
+        if not os.path.isdir(a.ref):
+            print("reference tree %s absent" % a.ref)
+            return 1
+        return build_gpu_stages(a.ref, a.march)
     binary = os.path.join(OUT, "carpedeam_ref")
     if os.path.exists(binary) and not a.force:
         print("oracle/_ref/carpedeam_ref present")

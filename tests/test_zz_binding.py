@@ -1,0 +1,86 @@
+"""The in-tree binding (north_star: host code stays inside the reference's modules and calls CUDA through the C ABI):
+carpedeam_b200/binding/stages_gpu.cpp is compiled against the reference's own headers and linked with the UNMODIFIED reference objects in place of
+the entry points of kmermatcher / rescorediagonal / ancient_correction (oracle/build_ref.py --gpu-stages -> oracle/_ref/carpedeam_ref_gpu).
+
+CPU (needs /root/reference and oracle/_ref/obj, i.e. the build container): the binary builds; a call on the GPU path ends with the error of a missing
+device (no CPU fallback); a call outside the GPU path is delegated to the reference's own implementation and writes what the reference writes.
+GPU: the three stages of the binding binary on config 1's first iteration against the golden DBs — xfail(strict=False): the binary was finished
+after the round's GPU budget was spent and has never run on a device; the same stage logic is proven through the stage binary and the workflow swap."""
+import os
+import subprocess
+
+import pytest
+
+from support import GOLD, ROOT, load_golden, read_db, write_db
+
+REF = os.path.join(ROOT, "oracle", "_ref", "carpedeam_ref")
+BIND = os.path.join(ROOT, "oracle", "_ref", "carpedeam_ref_gpu")
+HAVE_REF_TREE = os.path.isdir("/root/reference") and os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "obj"))
+
+KM = ("--sub-mat nucl:nucleotide.out,aa:blosum62.out --alph-size nucl:5,aa:13 --min-seq-id 0.9 --kmer-per-seq 200 --spaced-kmer-mode 0 --kmer-per-seq-scale 0.200 "
+      "--adjust-kmer-len 0 --mask 0 --mask-lower-case 0 --cov-mode 1 -k 20 -c 0 --max-seq-len 200000 --hash-shift 67 --split-memory-limit 0 "
+      "--include-only-extendable 0 --threads 4 --compressed 0 -v 3").split()
+RS = ("--sub-mat nucl:nucleotide.out,aa:blosum62.out --wrapped-scoring 0 --filter-hits 0 -e 0.001 -c 0 -a 0 --cov-mode 1 --min-seq-id 0.9 --min-aln-len 0 "
+      "--seq-id-mode 0 --add-self-matches 0 --sort-results 0 --db-load-mode 0 --threads 4 --compressed 0 -v 3").split()
+
+
+def _have_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+@pytest.fixture(scope="module")
+def binding():
+    if not HAVE_REF_TREE:
+        pytest.skip("needs /root/reference and oracle/_ref/obj (the build container)")
+    import carpedeam_b200 as cd
+    cd.build()
+    r = subprocess.run(["python", os.path.join(ROOT, "oracle", "build_ref.py"), "--gpu-stages"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    return BIND
+
+
+def test_binding_compiles_against_the_reference_and_has_no_cpu_fallback(binding, tmp_path):
+    d = str(tmp_path)
+    write_db(d + "/seq", *load_golden("nucl_reads"), 1)
+    if _have_gpu():
+        pytest.skip("GPU present: see the GPU test")
+    r = subprocess.run([binding, "kmermatcher", d + "/seq", d + "/pref"] + KM + ["--ignore-multi-kmer", "1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "No usable CUDA device" in r.stdout + r.stderr
+    assert "GPU k-mer matcher" in r.stdout + r.stderr            # the call was on the GPU path (the reference's own code prints no such line)
+    assert not os.path.exists(d + "/pref.index") or os.path.getsize(d + "/pref.index") == 0
+
+
+def test_binding_delegates_calls_outside_the_gpu_path_to_the_reference(binding, tmp_path):
+    """--ignore-multi-kmer 0 (k-mer matcher) and --rescore-mode 1 (rescorediagonal) are not on the GPU path: the binding hands them to the
+    reference's own entry points (renamed *_cpu at link time) and the output equals the unmodified binary's"""
+    d = str(tmp_path)
+    write_db(d + "/seq", *load_golden("nucl_reads"), 1)
+    for exe, tag in ((binding, "b"), (REF, "r")):
+        subprocess.run([exe, "kmermatcher", d + "/seq", d + "/pref_" + tag] + KM + ["--ignore-multi-kmer", "0"], check=True, capture_output=True)
+        subprocess.run([exe, "rescorediagonal", d + "/seq", d + "/seq", d + "/pref_" + tag, d + "/resc_" + tag] + RS + ["--rescore-mode", "1"], check=True,
+                       capture_output=True)
+    for name in ("pref_", "resc_"):
+        a, b = read_db(d + "/" + name + "b"), read_db(d + "/" + name + "r")
+        assert a == b and len(a) == 14996, name
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="the binding binary was finished after the round's GPU budget was spent: never run on a device")
+def test_binding_stages_reproduce_the_golden_dbs_on_the_gpu(tmp_path):
+    if not os.path.exists(BIND) or not os.path.exists(REF):
+        pytest.skip("oracle/_ref/carpedeam_ref_gpu not present")
+    if "avx2" not in open("/proc/cpuinfo").read():
+        pytest.skip("the reference objects were built for x86-64-v3")
+    d = str(tmp_path)
+    write_db(d + "/seq", *load_golden("nucl_reads"), 1)
+    subprocess.run([BIND, "kmermatcher", d + "/seq", d + "/pref"] + KM + ["--ignore-multi-kmer", "1"], check=True, timeout=600)
+    subprocess.run([BIND, "rescorediagonal", d + "/seq", d + "/seq", d + "/pref", d + "/aln"] + RS + ["--rescore-mode", "3"], check=True, timeout=600)
+    subprocess.run([BIND, "ancient_correction", d + "/seq", d + "/aln", d + "/corr", "--min-seq-id", "0.9", "--max-seq-len", "200000", "--keep-target", "1",
+                    "--threads", "4", "-v", "3", "--rescore-mode", "3", "--min-ryseq-id-corr-reads", "0.99", "--min-seqid-corr-reads", "0.9",
+                    "--ancient-damage", os.path.join(GOLD, "dhigh"), "--unsafe", "0", "--min-cov-safe", "5"], check=True, timeout=600)
+    for name, out in (("pref_0", "pref"), ("aln_0", "aln"), ("correction_0", "corr")):
+        gk, gp, ge = load_golden(name)
+        mine = read_db(d + "/" + out)
+        assert sorted(mine) == gk, name
+        assert not [k for k, p, e in zip(gk, gp, ge) if mine[k] != (p, e)], name
