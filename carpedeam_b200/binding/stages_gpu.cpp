@@ -66,9 +66,9 @@ bool single_process() {
 #endif
 }
 
-bool plain_nucleotide_db(const Parameters &par, int dbtype) {
-    return Parameters::isEqualDbtype(dbtype, Parameters::DBTYPE_NUCLEOTIDES) && par.compressed == 0 && par.scoringMatrixFile.nucleotides != NULL &&
-           strstr(par.scoringMatrixFile.nucleotides, "nucleotide.out") != NULL;
+bool plain_nucleotide_db(const Parameters &par, DBReader<unsigned int> &dbr) {
+    return Parameters::isEqualDbtype(dbr.getDbtype(), Parameters::DBTYPE_NUCLEOTIDES) && !dbr.isCompressed() && par.compressed == 0 &&
+           par.scoringMatrixFile.nucleotides != NULL && strstr(par.scoringMatrixFile.nucleotides, "nucleotide.out") != NULL;
 }
 
 // the sequence DB as the flat arrays cdg_upload_seqs takes (entries `BASES\n\0`; a DB whose data lies in several files is gathered)
@@ -103,7 +103,7 @@ int kmermatcher(int argc, const char **argv, const Command &command) {
     seqDbr.open(DBReader<unsigned int>::NOSORT);
     const int querySeqType = seqDbr.getDbtype();
     setKmerLengthAndAlphabet(par, seqDbr.getAminoAcidDBSize(), querySeqType);
-    const bool onPath = plain_nucleotide_db(par, querySeqType) && par.spacedKmer == 0 && par.maskMode == 0 && par.maskLowerCaseMode == 0 && par.ignoreMultiKmer &&
+    const bool onPath = plain_nucleotide_db(par, seqDbr) && par.spacedKmer == 0 && par.maskMode == 0 && par.maskLowerCaseMode == 0 && par.ignoreMultiKmer &&
                         par.adjustKmerLength == 0 && par.kmerSize >= 1 && par.kmerSize <= 31 && seqDbr.getMaxSeqLen() <= par.maxSeqLen && single_process();
     if (!onPath) {
         seqDbr.close();
@@ -165,7 +165,7 @@ int rescorediagonal(int argc, const char **argv, const Command &command) {
     if (onPath) {
         seqDbr = new DBReader<unsigned int>(par.db1.c_str(), par.db1Index.c_str(), par.threads, DBReader<unsigned int>::USE_INDEX | DBReader<unsigned int>::USE_DATA);
         seqDbr->open(DBReader<unsigned int>::NOSORT);
-        onPath = plain_nucleotide_db(par, seqDbr->getDbtype());
+        onPath = plain_nucleotide_db(par, *seqDbr);
         if (!onPath) { seqDbr->close(); delete seqDbr; }
     }
     if (!onPath) return delegate(rescorediagonal_cpu, argc, argv, command);
@@ -248,7 +248,7 @@ int correction(int argc, const char **argv, const Command &command) {
     par.allowDeletion = false;
     DBReader<unsigned int> sequenceDbr(par.db1.c_str(), par.db1Index.c_str(), par.threads, DBReader<unsigned int>::USE_DATA | DBReader<unsigned int>::USE_INDEX);
     sequenceDbr.open(DBReader<unsigned int>::NOSORT);
-    if (!plain_nucleotide_db(par, sequenceDbr.getDbtype()) || !single_process()) {
+    if (!plain_nucleotide_db(par, sequenceDbr) || !single_process()) {
         sequenceDbr.close();
         return delegate(correction_cpu, argc, argv, command);
     }

@@ -74,11 +74,11 @@ def test_binding_stages_reproduce_the_golden_dbs_on_the_gpu(tmp_path):
         pytest.skip("the reference objects were built for x86-64-v3")
     d = str(tmp_path)
     write_db(d + "/seq", *load_golden("nucl_reads"), 1)
-    subprocess.run([BIND, "kmermatcher", d + "/seq", d + "/pref"] + KM + ["--ignore-multi-kmer", "1"], check=True, timeout=600)
-    subprocess.run([BIND, "rescorediagonal", d + "/seq", d + "/seq", d + "/pref", d + "/aln"] + RS + ["--rescore-mode", "3"], check=True, timeout=600)
+    subprocess.run([BIND, "kmermatcher", d + "/seq", d + "/pref"] + KM + ["--ignore-multi-kmer", "1"], check=True, timeout=180)
+    subprocess.run([BIND, "rescorediagonal", d + "/seq", d + "/seq", d + "/pref", d + "/aln"] + RS + ["--rescore-mode", "3"], check=True, timeout=180)
     subprocess.run([BIND, "ancient_correction", d + "/seq", d + "/aln", d + "/corr", "--min-seq-id", "0.9", "--max-seq-len", "200000", "--keep-target", "1",
                     "--threads", "4", "-v", "3", "--rescore-mode", "3", "--min-ryseq-id-corr-reads", "0.99", "--min-seqid-corr-reads", "0.9",
-                    "--ancient-damage", os.path.join(GOLD, "dhigh"), "--unsafe", "0", "--min-cov-safe", "5"], check=True, timeout=600)
+                    "--ancient-damage", os.path.join(GOLD, "dhigh"), "--unsafe", "0", "--min-cov-safe", "5"], check=True, timeout=180)
     for name, out in (("pref_0", "pref"), ("aln_0", "aln"), ("correction_0", "corr")):
         gk, gp, ge = load_golden(name)
         mine = read_db(d + "/" + out)
