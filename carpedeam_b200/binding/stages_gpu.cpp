@@ -6,6 +6,7 @@
 //     int kmermatcher(int, const char **, const Command &)        lib/mmseqs/src/linclust/kmermatcher.cpp:786
 //     int rescorediagonal(int, const char **, const Command &)    lib/mmseqs/src/alignment/rescorediagonal.cpp:381
 //     int correction(int, const char **, const Command &)         src/assembler/correction.cpp:492
+//     int cyclecheck(int, const char **, const Command &)         src/assembler/cyclecheck.cpp:31
 // The reference's objects keep every other symbol (setLinearFilterDefault, setKmerLengthAndAlphabet, doRescorediagonal, doCorrection, ...);
 // the build (oracle/build_ref.py --gpu-stages) renames the three original entry points to *_cpu with `objcopy --redefine-sym`, no reference
 // source is touched.  Argument parsing, parameter printing, DB opening / closing, text formats and the error convention
@@ -32,6 +33,8 @@
 int kmermatcher_cpu(int argc, const char **argv, const Command &command);       // the reference's own entry points, renamed at link time
 int rescorediagonal_cpu(int argc, const char **argv, const Command &command);
 int correction_cpu(int argc, const char **argv, const Command &command);
+int cyclecheck_cpu(int argc, const char **argv, const Command &command);
+void setCycleCheckDefaults(LocalParameters *p);   // src/assembler/cyclecheck.cpp:26 (stays in the reference's object)
 
 namespace {
 
@@ -295,5 +298,46 @@ int correction(int argc, const char **argv, const Command &command) {
     cdg_destroy(ctx);
     sequenceDbr.close();
     Debug(Debug::INFO) << "\nDone. " << changed << " bases corrected.\n";
+    return EXIT_SUCCESS;
+}
+
+// ---- cyclecheck: replaces the OpenMP region of cyclecheck (cyclecheck.cpp:72-262) ---------------------------------------------------
+int cyclecheck(int argc, const char **argv, const Command &command) {
+    LocalParameters &par = LocalParameters::getLocalInstance();
+    setCycleCheckDefaults(&par);
+    par.parseParameters(argc, argv, command, true, 0, 0);
+    DBReader<unsigned int> seqDbr(par.db1.c_str(), par.db1Index.c_str(), par.threads, DBReader<unsigned int>::USE_DATA | DBReader<unsigned int>::USE_INDEX);
+    seqDbr.open(DBReader<unsigned int>::NOSORT);
+    if (!plain_nucleotide_db(par, seqDbr) || par.kmerSize != 22) {
+        seqDbr.close();
+        return delegate(cyclecheck_cpu, argc, argv, command);
+    }
+    DBWriter cycleResultWriter(par.db2.c_str(), par.db2Index.c_str(), 1, par.compressed, Parameters::DBTYPE_NUCLEOTIDES);
+    cycleResultWriter.open();
+    FlatSeqs s;
+    flatten(seqDbr, s);
+    cdg_ctx *ctx = gpu_context();
+    upload(ctx, s);
+    cdg_cycle_params cp; cp.k = par.kmerSize; cp.max_seq_len = (uint32_t) par.maxSeqLen;
+    cdg_cycle_out co;
+    check(ctx, cdg_cyclecheck(ctx, &cp, &co), "cdg_cyclecheck");
+    for (size_t id = 0; id < seqDbr.getSize(); id++) {
+        if (s.len[id] >= par.maxSeqLen)
+            Debug(Debug::WARNING) << "Sequence " << seqDbr.getDbKey(id) << " too long. It will be skipped. Max length allowed is " << par.maxSeqLen << "\n";
+        if (co.split_diagonal[id] == 0) continue;
+        char *nuclSeq = seqDbr.getData(id, 0);                       // :238-252
+        unsigned int len = seqDbr.getEntryLen(id) - 1;
+        std::string seq;
+        if (par.chopCycle) {
+            seq = std::string(nuclSeq, co.split_diagonal[id]);
+            seq.push_back('\n');
+            nuclSeq = (char *) seq.c_str();
+            len = seq.size();
+        }
+        cycleResultWriter.writeData(nuclSeq, len, seqDbr.getDbKey(id), 0);
+    }
+    cycleResultWriter.close(true);
+    cdg_destroy(ctx);
+    seqDbr.close();
     return EXIT_SUCCESS;
 }

@@ -66,12 +66,13 @@ GPU_ENTRY_POINTS = {   # object -> (mangled entry point, name it gets so that ca
     "lib/mmseqs/src/linclust/kmermatcher.cpp": ("_Z11kmermatcheriPPKcRK7Command", "_Z15kmermatcher_cpuiPPKcRK7Command"),
     "lib/mmseqs/src/alignment/rescorediagonal.cpp": ("_Z15rescorediagonaliPPKcRK7Command", "_Z19rescorediagonal_cpuiPPKcRK7Command"),
     "src/assembler/correction.cpp": ("_Z10correctioniPPKcRK7Command", "_Z14correction_cpuiPPKcRK7Command"),
+    "src/assembler/cyclecheck.cpp": ("_Z10cyclecheckiPPKcRK7Command", "_Z14cyclecheck_cpuiPPKcRK7Command"),
 }
 
 
 def build_gpu_stages(ref, march):
     """oracle/_ref/carpedeam_ref_gpu: the reference with the in-tree binding (carpedeam_b200/binding/stages_gpu.cpp, compiled against the
-    reference's headers) in place of the entry points of kmermatcher, rescorediagonal and ancient_correction.  No reference source is changed:
+    reference's headers) in place of the entry points of kmermatcher, rescorediagonal, ancient_correction and cyclecheck.  No reference source is changed:
     the three original entry points are renamed in COPIES of their objects (objcopy --redefine-sym) and stay reachable as *_cpu for calls
     outside the GPU path.  Needs oracle/_ref/obj (a previous run of this script) and the built libcarpedeam_gpu.so / libcarpedeam_host.so."""
     root = os.path.dirname(HERE)

@@ -1,6 +1,6 @@
 """The in-tree binding (north_star: host code stays inside the reference's modules and calls CUDA through the C ABI):
 carpedeam_b200/binding/stages_gpu.cpp is compiled against the reference's own headers and linked with the UNMODIFIED reference objects in place of
-the entry points of kmermatcher / rescorediagonal / ancient_correction (oracle/build_ref.py --gpu-stages -> oracle/_ref/carpedeam_ref_gpu).
+the entry points of kmermatcher / rescorediagonal / ancient_correction / cyclecheck (oracle/build_ref.py --gpu-stages -> oracle/_ref/carpedeam_ref_gpu).
 
 CPU (needs /root/reference and oracle/_ref/obj, i.e. the build container): the binary builds; a call on the GPU path ends with the error of a missing
 device (no CPU fallback); a call outside the GPU path is delegated to the reference's own implementation and writes what the reference writes.
@@ -49,6 +49,10 @@ def test_binding_compiles_against_the_reference_and_has_no_cpu_fallback(binding,
     assert r.returncode != 0 and "No usable CUDA device" in r.stdout + r.stderr
     assert "GPU k-mer matcher" in r.stdout + r.stderr            # the call was on the GPU path (the reference's own code prints no such line)
     assert not os.path.exists(d + "/pref.index") or os.path.getsize(d + "/pref.index") == 0
+    write_db(d + "/contigs", *load_golden("synth_cycle", ""), 1)
+    r = subprocess.run([binding, "cyclecheck", d + "/contigs", d + "/cyc", "--max-seq-len", "200000", "--chop-cycle", "1", "--threads", "4", "-v", "3"],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "No usable CUDA device" in r.stdout + r.stderr
 
 
 def test_binding_delegates_calls_outside_the_gpu_path_to_the_reference(binding, tmp_path):
@@ -84,3 +88,10 @@ def test_binding_stages_reproduce_the_golden_dbs_on_the_gpu(tmp_path):
         mine = read_db(d + "/" + out)
         assert sorted(mine) == gk, name
         assert not [k for k, p, e in zip(gk, gp, ge) if mine[k] != (p, e)], name
+    from support import load_cycle_kat
+    s, want = load_cycle_kat()
+    write_db(d + "/contigs", *load_golden("synth_cycle", ""), 1)
+    subprocess.run([BIND, "cyclecheck", d + "/contigs", d + "/cyc", "--max-seq-len", "200000", "--chop-cycle", "1", "--threads", "4", "-v", "3"], check=True, timeout=180)
+    mine = read_db(d + "/cyc")
+    assert sorted(mine) == [int(k) for k in range(s.n) if want[k]]
+    assert all(payload == s.seq(k)[:int(want[k])] + b"\n" for k, (payload, ext) in mine.items())
