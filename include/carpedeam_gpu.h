@@ -10,6 +10,12 @@
  *   rescorediagonal    lib/mmseqs/src/alignment/rescorediagonal.cpp:45 (doRescorediagonal) -> cdg_rescore
  *   ancient_correction src/assembler/correction.cpp:128 (doCorrection)                   -> cdg_correct
  *   one fused reads-only iteration (data/nuclassemble.sh:105-126)                         -> cdg_iteration
+ * and, for the modules either side of the loop:
+ *   ancient_read_assemble, before its queue   src/assembler/ancientReadsResults.cpp:200-370     -> cdg_extension_scores, cdg_pair_loglik*
+ *   ancient_contig_merge, before its queue    src/assembler/ancientContigsResults.cpp:187-262   -> cdg_merge_scores
+ *   cyclecheck                                src/assembler/cyclecheck.cpp:72-262               -> cdg_cyclecheck
+ *   rescorediagonal --rescore-mode 0          rescorediagonal.cpp:194-334 (HAMMING branch)      -> cdg_rescore_hamming
+ * The in-tree form of the bindings (compiled against the reference's own classes): carpedeam_b200/binding/stages_gpu.cpp.
  *
  * Conventions: every function returns 0 on success or a negative cdg_status; cdg_last_error()
  * gives the message.  Input buffers are caller-owned host memory (pinned memory makes the copies
