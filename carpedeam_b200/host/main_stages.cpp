@@ -8,6 +8,7 @@
 //   carpedeam_gpu rescorediagonal    ... --rescore-mode 0 [--wrapped-scoring 1]  (linclust's Hamming pre-clustering, linclust.sh:28-32)
 //   carpedeam_gpu cyclecheck         <seqDB> <cycleDB>                [flags]   (cyclecheck.cpp:31)
 //   carpedeam_gpu createdb           <fasta/fastq[.gz]> ... <seqDB>   [flags]   (createdb.cpp; host only)
+//   carpedeam_gpu iteration          <seqDB> <prefDB> <alnDB> <corrDB> [flags]  (the three hot-path stages fused: one process, one upload, three DBs)
 //
 // Host side only: DBReader/DBWriter-compatible file access and the text formats; all arithmetic happens in
 // libcarpedeam_gpu.so through the C ABI.  Errors print a message and exit(EXIT_FAILURE), as the reference does.
@@ -379,6 +380,71 @@ int ancient_correction(int argc, char **argv) {
     return EXIT_SUCCESS;
 }
 
+// iteration <i:sequenceDB> <o:prefDB> <o:alnDB> <o:correctedDB>: the three hot-path stages of one assembler iteration in ONE process and
+// one upload (cdg_iteration: no pref / aln text round trip between the stages on the device side), emitting the same three databases the
+// separate stages write (binary in-process hand-off with DB emission for drop-in compatibility).  Flags: the union of the
+// three stages' (kmermatcher's -k / --kmer-per-seq / --include-only-extendable ..., rescorediagonal's --min-seq-id / -e, the correction's
+// --ancient-damage / --min-ryseq-id-corr-reads).
+int iteration(int argc, char **argv) {
+    Args a = parse_args(argc, argv, 2);
+    if (a.pos.size() < 4) die("Usage: iteration <i:sequenceDB> <o:prefDB> <o:alnDB> <o:correctedDB> [options]");
+    require_pinned(a, "iteration", {{"--sub-mat", "nucleotide.out"}, {"--alph-size", "nucl:5"}, {"--spaced-kmer-mode", "0"}, {"--adjust-kmer-len", "0"}, {"--mask", "0"},
+                                    {"--mask-lower-case", "0"}, {"--ignore-multi-kmer", "1"}, {"--compressed", "0"}, {"-c", "0"}, {"--rescore-mode", "3"},
+                                    {"--wrapped-scoring", "0"}, {"--filter-hits", "0"}, {"-a", "0"}, {"--min-aln-len", "0"}, {"--seq-id-mode", "0"},
+                                    {"--add-self-matches", "0"}, {"--sort-results", "0"}});
+    const double t0 = now_ms();
+    Db seq; open_db(a.pos[0], seq);
+    cdg_ctx *ctx = make_ctx();
+    std::vector<uint32_t> lens;
+    upload(ctx, seq, lens);
+    cdg_damage dmg; char err[512];
+    if (cdh_build_damage(a.get("--ancient-damage", "").c_str(), 0.01, &dmg, err, sizeof err) != 0) die(err);
+    ck(ctx, cdg_set_damage(ctx, &dmg), "cdg_set_damage");
+    cdg_iter_params ip;
+    ip.kmer.k = (int) a.num("-k", 0);
+    if (ip.kmer.k == 0) die("iteration: -k is required");
+    ip.kmer.kmers_per_seq = (int) a.num("--kmer-per-seq", 21); ip.kmer.kmers_per_seq_scale = (float) a.num("--kmer-per-seq-scale", 0.2);
+    ip.kmer.hash_shift = (uint64_t) a.num("--hash-shift", 67); ip.kmer.include_only_extendable = (int) a.num("--include-only-extendable", 0);
+    ip.kmer.hash_lo = 0; ip.kmer.hash_hi = 65535; ip.kmer.split_passes = 0; ip.kmer.cov_thr = 0.f; ip.kmer.cov_mode = (int) a.num("--cov-mode", 0);
+    ip.rescore.min_seq_id = (float) a.num("--min-seq-id", 0.0); ip.rescore.evalue_thr = a.num("-e", 0.001); ip.rescore.db_residues = 0;
+    ip.corr.min_seqid_corr_reads = (float) a.num("--min-seq-id", 0.0); ip.corr.min_ryseq_id_corr_reads = (float) a.num("--min-ryseq-id-corr-reads", 0.99);
+    cdg_hits h; cdg_alns r;
+    std::vector<uint8_t> out(seq.data.size());
+    uint64_t changed = 0;
+    const double t1 = now_ms();
+    ck(ctx, cdg_iteration(ctx, &ip, &h, &r, out.data(), &changed), "cdg_iteration");
+    const double t2 = now_ms();
+    const int threads = host_threads(a);
+    std::vector<uint64_t> first(seq.size() + 1, 0);
+    for (uint64_t i = 0; i < h.n_hits; i++) first[h.rep[i] + 1]++;
+    for (size_t q = 0; q < seq.size(); q++) first[q + 1] += first[q];
+    write_entries_parallel(a.pos[1], DBTYPE_PREFILTER_REV_RES, seq.size(), threads, [&](size_t q, std::string &entry, uint32_t &key, uint8_t &ext) {
+        char buf[64];
+        entry.append(buf, format_pref_line(buf, seq.keys[q], 0, 0));
+        for (uint64_t i = first[q]; i < first[q + 1]; i++) entry.append(buf, format_pref_line(buf, seq.keys[h.target[i]], h.score[i], h.diag[i]));
+        key = seq.keys[q]; ext = first[q + 1] > first[q] ? 0 : seq.ext[q];
+    });
+    write_entries_parallel(a.pos[2], DBTYPE_ALIGNMENT_RES, seq.size(), threads, [&](size_t q, std::string &entry, uint32_t &key, uint8_t &ext) {
+        char buf[256];
+        for (uint64_t l = r.line_off[q]; l < r.line_off[q + 1]; l++) {
+            if (!r.keep[l]) continue;
+            const uint32_t t = r.target[l];
+            entry.append(buf, format_aln_line(buf, seq.keys[t], r.bits[l], r.seq_id[l], r.evalue[l], r.q_start[l], r.q_end[l], (int32_t) lens[q], r.db_start[l],
+                                              r.db_end[l], (int32_t) lens[t]));
+        }
+        key = seq.keys[q]; ext = 0;
+    });
+    write_entries_parallel(a.pos[3], seq.dbtype ? seq.dbtype : DBTYPE_NUCLEOTIDES, seq.size(), threads, [&](size_t q, std::string &entry, uint32_t &key, uint8_t &ext) {
+        entry.assign((const char *) out.data() + seq.offsets[q], lens[q]);
+        entry.push_back('\n');
+        key = seq.keys[q]; ext = seq.ext[q];
+    });
+    fprintf(stderr, "carpedeam_gpu iteration: %llu hits, %llu bases corrected; read DB + upload %.1f ms, GPU + export %.1f ms, format + write 3 DBs %.1f ms\n",
+            (unsigned long long) h.n_hits, (unsigned long long) changed, t1 - t0, t2 - t1, now_ms() - t2);
+    cdg_destroy(ctx);
+    return EXIT_SUCCESS;
+}
+
 }   // namespace
 
 int main(int argc, char **argv) {
@@ -387,6 +453,7 @@ int main(int argc, char **argv) {
     if (cmd == "kmermatcher") return kmermatcher(argc, argv);
     if (cmd == "rescorediagonal") return rescorediagonal(argc, argv);
     if (cmd == "ancient_correction") return ancient_correction(argc, argv);
+    if (cmd == "iteration") return iteration(argc, argv);
     if (cmd == "cyclecheck") return cyclecheck(argc, argv);
     if (cmd == "createdb") return createdb(argc, argv);
     die("Invalid Command: " + cmd);
