@@ -12,6 +12,8 @@ size_t format_pref_line(char *buf, uint32_t targetKey, int32_t score, int16_t di
 struct PrefLine { uint32_t targetKey; int32_t score; uint16_t diag; };
 void parse_pref_entry(const char *data, std::vector<PrefLine> &out);
 
+// snprintf("%.3E") without snprintf (exactly the same characters; returns the end)
+char *put_e3(char *p, double v);
 // alignment line (Matcher::resultToBuffer, Matcher.cpp:356-401; Util::fastSeqIdToBuffer, Util.cpp:278-307)
 size_t format_aln_line(char *buf, uint32_t targetKey, int32_t bits, float seqId, double evalue, int32_t qStart, int32_t qEnd,
                        int32_t qLen, int32_t dbStart, int32_t dbEnd, int32_t dbLen);

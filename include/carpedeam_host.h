@@ -38,6 +38,7 @@ size_t cdh_pref_roundtrip(const char *entry, char *out, size_t cap);
 size_t cdh_format_aln_line(char *buf, uint32_t target_key, int32_t bits, float seq_id, double evalue, int32_t q_start, int32_t q_end, int32_t q_len,
                            int32_t db_start, int32_t db_end, int32_t db_len);
 size_t cdh_parse_aln_entry(const char *entry, size_t index, uint32_t *target_key, float *seq_id, int32_t *coords4);
+uint64_t cdh_format_selftest(uint64_t n, uint64_t seed);   /* the hand-written formatters / parsers against snprintf / strtod on n seeded values: mismatches */
 
 /* ---- MMseqs2 database files: DBReader / DBWriter (lib/mmseqs/src/commons/DBReader.cpp:792-817, DBWriter.cpp:360-426); reads a DB
  * (split data files, unordered index, ext column) and writes it back; returns the number of entries */

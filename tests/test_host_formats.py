@@ -120,3 +120,13 @@ def test_db_reader_writer_round_trip(tmp_path, split, shuffle):
         assert got[k] == (p, e)
     idx_keys = [int(l.split()[0]) for l in open(dst + ".index")]
     assert idx_keys == sorted(idx_keys)          # DBWriter::close sorts the index by key
+
+
+def test_fast_formatters_equal_the_c_library(host):
+    """the hand-written integer / %.3E formatters and field parsers of the stage binaries (0.10 us per alignment line instead of 0.90 with
+    sprintf) against snprintf / strtol / strtod on 4 million seeded values: random doubles over 120 decades, values next to decimal ties,
+    short decimals, zero"""
+    host.cdh_format_selftest.restype = C.c_uint64
+    host.cdh_format_selftest.argtypes = [C.c_uint64, C.c_uint64]
+    for seed in (1, 2):
+        assert host.cdh_format_selftest(2000000, seed) == 0
