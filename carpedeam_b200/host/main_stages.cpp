@@ -95,8 +95,7 @@ void write_entries_parallel(const std::string &path, int dbtype, size_t n, int t
             parts[t].write(entry.data(), entry.size(), key, ext);
         }
     }
-    for (int t = 1; t < threads; t++) parts[0].append(parts[t]);
-    parts[0].close();
+    parts[0].close_parts(threads > 1 ? &parts[1] : nullptr, (size_t) (threads - 1));
 }
 
 // per-query variable-length records parsed by `threads` host threads into one CSR: parseOf(q, push) calls push(record)

@@ -37,6 +37,7 @@ struct DbWriter {
     void write(const char *payload, size_t len, uint32_t key, uint8_t extFlag);
     void append(const DbWriter &other);   // entries of another (per-thread) writer behind this one's
     void close();   // data, .index (sorted by key, 4 columns), .dbtype
+    void close_parts(DbWriter *more, size_t nMore);   // close() of this writer + the entries of further (per-thread) writers behind it, without copying their data
 };
 
 [[noreturn]] void die(const std::string &msg);
