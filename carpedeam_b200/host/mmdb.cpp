@@ -155,3 +155,18 @@ extern "C" long cdh_db_roundtrip(const char *inPath, const char *outPath, int *d
     if (dbtypeOut) *dbtypeOut = db.dbtype;
     return (long) db.size();
 }
+
+// the same through `parts` writers over contiguous blocks of entries, closed into one database (what the stage binaries do per host thread)
+extern "C" long cdh_db_roundtrip_parts(const char *inPath, const char *outPath, int parts) {
+    cdh::Db db;
+    cdh::open_db(inPath, db);
+    if (parts < 1) parts = 1;
+    std::vector<cdh::DbWriter> w;
+    for (int t = 0; t < parts; t++) w.emplace_back(outPath, db.dbtype);
+    const size_t n = db.size();
+    for (int t = 0; t < parts; t++)
+        for (size_t i = n * (size_t) t / (size_t) parts; i < n * (size_t) (t + 1) / (size_t) parts; i++)
+            w[t].write((const char *) db.data.data() + db.offsets[i], db.lengths[i] ? db.lengths[i] - 1 : 0, db.keys[i], db.ext[i]);
+    w[0].close_parts(parts > 1 ? &w[1] : nullptr, (size_t) (parts - 1));
+    return (long) n;
+}

@@ -43,6 +43,7 @@ uint64_t cdh_format_selftest(uint64_t n, uint64_t seed);   /* the hand-written f
 /* ---- MMseqs2 database files: DBReader / DBWriter (lib/mmseqs/src/commons/DBReader.cpp:792-817, DBWriter.cpp:360-426); reads a DB
  * (split data files, unordered index, ext column) and writes it back; returns the number of entries */
 long cdh_db_roundtrip(const char *in_path, const char *out_path, int *dbtype_out);
+long cdh_db_roundtrip_parts(const char *in_path, const char *out_path, int parts);   /* through `parts` per-thread writers closed into one DB */
 
 /* ---- 2-bit packing for cdg_upload_packed, and the host views of the compact results (carpedeam_gpu.h: cdg_alns_compact, cdg_patches) */
 uint64_t cdh_packed_words(const uint32_t *lens, uint64_t n);
