@@ -28,6 +28,7 @@ static void append_file(const std::string &p, std::vector<uint8_t> &out) {
 }
 
 long Db::find(uint32_t key) const {
+    if (dense) return key < keys.size() ? (long) key : -1;   // keys 0..n-1 (createdb, and every DB the assembler derives from it): no search
     auto it = std::lower_bound(keys.begin(), keys.end(), key);
     if (it == keys.end() || *it != key) return -1;
     return (long) (it - keys.begin());
@@ -85,6 +86,8 @@ void open_db(const std::string &path, Db &db) {
         if (r.off + r.len > db.data.size()) die("Index of " + path + " points past the end of the data file");
         db.keys.push_back(r.key); db.offsets.push_back(r.off); db.lengths.push_back(r.len); db.ext.push_back(r.ext);
     }
+    db.dense = true;
+    for (size_t i = 0; i < db.keys.size() && db.dense; i++) db.dense = db.keys[i] == (uint32_t) i;
     FILE *t = fopen((path + ".dbtype").c_str(), "rb");
     if (t) { int32_t v = 0; if (fread(&v, 4, 1, t) == 1) db.dbtype = v & 0x7FFFFFFF; fclose(t); }
 }

@@ -17,6 +17,7 @@ struct Db {
     std::vector<uint64_t> lengths;  // including the trailing '\0' (and '\n' for sequences)
     std::vector<uint8_t> ext;       // CarpeDeam's "was extended" column (0 when absent)
     int dbtype = 0;
+    bool dense = false;             // keys[i] == i for every entry: find() needs no search
     size_t size() const { return keys.size(); }
     // index of `key` or -1
     long find(uint32_t key) const;
