@@ -25,6 +25,11 @@ RS = ("--sub-mat nucl:nucleotide.out,aa:blosum62.out --wrapped-scoring 0 --filte
       "--seq-id-mode 0 --add-self-matches 0 --sort-results 0 --db-load-mode 0 --threads 4 --compressed 0 -v 3").split()
 
 
+# the binding binary finds libcarpedeam_gpu.so / libcarpedeam_host.so through its rpath (the path of the build container); wherever the repository
+# lies at test time, the loader also looks in its carpedeam_b200/
+ENV = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "carpedeam_b200") + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+
+
 def _have_gpu():
     import torch
     return torch.cuda.is_available()
@@ -46,13 +51,13 @@ def test_binding_compiles_against_the_reference_and_has_no_cpu_fallback(binding,
     write_db(d + "/seq", *load_golden("nucl_reads"), 1)
     if _have_gpu():
         pytest.skip("GPU present: see the GPU test")
-    r = subprocess.run([binding, "kmermatcher", d + "/seq", d + "/pref"] + KM + ["--ignore-multi-kmer", "1"], capture_output=True, text=True)
+    r = subprocess.run([binding, "kmermatcher", d + "/seq", d + "/pref"] + KM + ["--ignore-multi-kmer", "1"], capture_output=True, text=True, env=ENV)
     assert r.returncode != 0 and "No usable CUDA device" in r.stdout + r.stderr
     assert "GPU k-mer matcher" in r.stdout + r.stderr            # the call was on the GPU path (the reference's own code prints no such line)
     assert not os.path.exists(d + "/pref.index") or os.path.getsize(d + "/pref.index") == 0
     write_db(d + "/contigs", *load_golden("synth_cycle", ""), 1)
     r = subprocess.run([binding, "cyclecheck", d + "/contigs", d + "/cyc", "--max-seq-len", "200000", "--chop-cycle", "1", "--threads", "4", "-v", "3"],
-                       capture_output=True, text=True)
+                       capture_output=True, text=True, env=ENV)
     assert r.returncode != 0 and "No usable CUDA device" in r.stdout + r.stderr
 
 
@@ -62,9 +67,9 @@ def test_binding_delegates_calls_outside_the_gpu_path_to_the_reference(binding, 
     d = str(tmp_path)
     write_db(d + "/seq", *load_golden("nucl_reads"), 1)
     for exe, tag in ((binding, "b"), (REF, "r")):
-        subprocess.run([exe, "kmermatcher", d + "/seq", d + "/pref_" + tag] + KM + ["--ignore-multi-kmer", "0"], check=True, capture_output=True)
+        subprocess.run([exe, "kmermatcher", d + "/seq", d + "/pref_" + tag] + KM + ["--ignore-multi-kmer", "0"], check=True, capture_output=True, env=ENV)
         subprocess.run([exe, "rescorediagonal", d + "/seq", d + "/seq", d + "/pref_" + tag, d + "/resc_" + tag] + RS + ["--rescore-mode", "1"], check=True,
-                       capture_output=True)
+                       capture_output=True, env=ENV)
     for name in ("pref_", "resc_"):
         a, b = read_db(d + "/" + name + "b"), read_db(d + "/" + name + "r")
         assert a == b and len(a) == 14996, name
@@ -80,11 +85,11 @@ def test_binding_stages_reproduce_the_golden_dbs_on_the_gpu(tmp_path):
         pytest.skip("the reference objects were built for x86-64-v3")
     d = str(tmp_path)
     write_db(d + "/seq", *load_golden("nucl_reads"), 1)
-    subprocess.run([BIND, "kmermatcher", d + "/seq", d + "/pref"] + KM + ["--ignore-multi-kmer", "1"], check=True, timeout=180)
-    subprocess.run([BIND, "rescorediagonal", d + "/seq", d + "/seq", d + "/pref", d + "/aln"] + RS + ["--rescore-mode", "3"], check=True, timeout=180)
+    subprocess.run([BIND, "kmermatcher", d + "/seq", d + "/pref"] + KM + ["--ignore-multi-kmer", "1"], check=True, timeout=180, env=ENV)
+    subprocess.run([BIND, "rescorediagonal", d + "/seq", d + "/seq", d + "/pref", d + "/aln"] + RS + ["--rescore-mode", "3"], check=True, timeout=180, env=ENV)
     subprocess.run([BIND, "ancient_correction", d + "/seq", d + "/aln", d + "/corr", "--min-seq-id", "0.9", "--max-seq-len", "200000", "--keep-target", "1",
                     "--threads", "4", "-v", "3", "--rescore-mode", "3", "--min-ryseq-id-corr-reads", "0.99", "--min-seqid-corr-reads", "0.9",
-                    "--ancient-damage", os.path.join(GOLD, "dhigh"), "--unsafe", "0", "--min-cov-safe", "5"], check=True, timeout=180)
+                    "--ancient-damage", os.path.join(GOLD, "dhigh"), "--unsafe", "0", "--min-cov-safe", "5"], check=True, timeout=180, env=ENV)
     for name, out in (("pref_0", "pref"), ("aln_0", "aln"), ("correction_0", "corr")):
         gk, gp, ge = load_golden(name)
         mine = read_db(d + "/" + out)
@@ -101,7 +106,7 @@ def test_binding_cyclecheck_on_the_gpu(tmp_path):
     d = str(tmp_path)
     s, want = load_cycle_kat()
     write_db(d + "/contigs", *load_golden("synth_cycle", ""), 1)
-    subprocess.run([BIND, "cyclecheck", d + "/contigs", d + "/cyc", "--max-seq-len", "200000", "--chop-cycle", "1", "--threads", "4", "-v", "3"], check=True, timeout=180)
+    subprocess.run([BIND, "cyclecheck", d + "/contigs", d + "/cyc", "--max-seq-len", "200000", "--chop-cycle", "1", "--threads", "4", "-v", "3"], check=True, timeout=180, env=ENV)
     mine = read_db(d + "/cyc")
     assert sorted(mine) == [int(k) for k in range(s.n) if want[k]]
     assert all(payload == s.seq(k)[:int(want[k])] + b"\n" for k, (payload, ext) in mine.items())
